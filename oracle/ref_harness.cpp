@@ -1,0 +1,403 @@
+/* ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Drives the UNMODIFIED reference lookahead (DJATOM/x265-aMod 3.6+1) compiled from
+ * /root/reference/source by oracle/Makefile.ref, and exposes every Lowres field the
+ * hot path produces through a tiny C ABI so tests can pin the CUDA path (and the C
+ * restatement in oracle/la_oracle.c) against the real thing.
+ *
+ * How: a real Encoder is opened (so x265_param is configured exactly as the encoder
+ * would, encoder/encoder.cpp:3608-...), then frames are pushed straight into
+ * Encoder::m_lookahead with Lookahead::addPicture (encoder/slicetype.cpp:1200) and
+ * drained with Lookahead::getDecidedPicture (:1289) -- Encoder::encode is never
+ * called.  Each drained frame's Lowres state is snapshotted.
+ *
+ * This file contains no reference source text; it only calls the reference's classes. */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <string>
+#include <new>
+#include <time.h>
+
+/* the harness needs Lookahead::frameCostRecalculate / m_tld (protected) and the
+ * BitCost tables (protected static) */
+#define protected public
+#define private public
+#include "common.h"
+#include "x265.h"
+#include "param.h"
+#include "primitives.h"
+#include "frame.h"
+#include "framedata.h"
+#include "picyuv.h"
+#include "lowres.h"
+#include "bitcost.h"
+#include "threadpool.h"
+#include "slicetype.h"
+#include "encoder.h"
+#undef protected
+#undef private
+
+using namespace X265_NS;
+
+extern "C" {
+
+struct RefLaConfig
+{
+    int32_t width, height;          /* picture size as handed to the encoder */
+    int32_t fpsNum, fpsDenom;
+    int32_t bframes, lookaheadDepth, bFrameAdaptive, bBPyramid;
+    int32_t scenecutThreshold;      /* 0 disables */
+    int32_t keyframeMax, keyframeMin; /* keyframeMin 0 = auto */
+    int32_t bOpenGOP;
+    int32_t aqMode;
+    double  aqStrength;
+    int32_t cuTree;
+    double  qCompress;
+    int32_t weightp, weightb;
+    int32_t poolThreads;            /* 0 = no pool (everything on the caller) */
+    int32_t lookaheadSlices;
+    int32_t qgSize;                 /* 16/32/64 (8 not supported by the CUDA path yet) */
+    int32_t bFrameBias;
+    double  scenecutBias;           /* percent, as --scenecut-bias */
+    int32_t vbvBufferSize, vbvMaxBitrate, bitrate; /* 0 = CRF */
+    int32_t dumpPlanes;             /* keep the 4 lowres planes of every frame */
+    int32_t bIntraRefresh;
+    int32_t reserved[7];
+};
+
+struct RefLaFrame
+{
+    int32_t poc, sliceType, bScenecut, bKeyframe, bLastMiniGopBFrame, leadingBframes;
+    int32_t bw, bh, nb;             /* 8x8 grid, nb = bframes+2 */
+    int32_t stride, planeLines;     /* lowres plane geometry (pixels) */
+    int64_t satdCost;
+    const int64_t*  costEst;        /* nb*nb */
+    const int64_t*  costEstAq;      /* nb*nb */
+    const int32_t*  intraMbs;       /* nb */
+    const int32_t*  rowSatds;       /* nb*nb*bh (row 0 == -1 => never computed) */
+    const uint16_t* lowresCosts;    /* nb*nb*ncu */
+    const int32_t*  mvs;            /* 2*nb*ncu*2 (x,y) */
+    const int32_t*  mvCosts;        /* 2*nb*ncu */
+    const int32_t*  intraCost;      /* ncu */
+    const uint8_t*  intraMode;      /* ncu */
+    const double*   qpAqOffset;     /* ncu */
+    const double*   qpCuTreeOffset; /* ncu */
+    const int32_t*  invQscaleFactor;/* ncu */
+    const uint16_t* propagateCost;  /* ncu */
+    uint64_t wp_ssd[3], wp_sum[3];
+    const double*   weightedCostDelta; /* nb */
+    const void*     planes;         /* 4*stride*planeLines pixels or NULL */
+};
+
+} // extern "C"
+
+namespace {
+
+struct FrameSnap
+{
+    RefLaFrame h;
+    std::vector<int64_t> costEst, costEstAq;
+    std::vector<int32_t> intraMbs, rowSatds, mvs, mvCosts, intraCost, invQ;
+    std::vector<uint16_t> lowresCosts, propagate;
+    std::vector<uint8_t> intraMode;
+    std::vector<double> qpAq, qpCuTree, wdelta;
+    std::vector<pixel> planes;
+};
+
+struct Handle
+{
+    RefLaConfig cfg;
+    x265_param* userParam;
+    Encoder*    enc;
+    Lookahead*  la;
+    int         pocNext;
+    bool        flushed;
+    std::vector<FrameSnap*> out;
+    std::vector<Frame*> retired;     /* frames drained from the lookahead; kept alive because
+                                        later decisions still reference m_lastNonB */
+    double      secondsInLookahead;
+};
+
+void snapshot(Handle* h, Frame* f)
+{
+    Lowres& l = f->m_lowres;
+    FrameSnap* s = new FrameSnap;
+    const int nb = h->enc->m_param->bframes + 2;
+    const int bw = l.maxBlocksInRow, bh = l.maxBlocksInCol, ncu = bw * bh;
+    memset(&s->h, 0, sizeof(s->h));
+    s->h.poc = f->m_poc; s->h.sliceType = l.sliceType; s->h.bScenecut = l.bScenecut;
+    s->h.bKeyframe = l.bKeyframe; s->h.bLastMiniGopBFrame = l.bLastMiniGopBFrame;
+    s->h.leadingBframes = l.leadingBframes;
+    s->h.bw = bw; s->h.bh = bh; s->h.nb = nb;
+    s->h.stride = (int)l.lumaStride;
+    s->h.planeLines = (int)((l.buffer[1] - l.buffer[0]) / l.lumaStride);
+    s->h.satdCost = l.satdCost;
+    for (int i = 0; i < nb; i++)
+        for (int j = 0; j < nb; j++)
+        {
+            s->costEst.push_back(l.costEst[i][j]);
+            s->costEstAq.push_back(l.costEstAq[i][j]);
+            s->rowSatds.insert(s->rowSatds.end(), l.rowSatds[i][j], l.rowSatds[i][j] + bh);
+            s->lowresCosts.insert(s->lowresCosts.end(), l.lowresCosts[i][j], l.lowresCosts[i][j] + ncu);
+        }
+    for (int i = 0; i < nb; i++)
+    {
+        s->intraMbs.push_back(l.intraMbs[i]);
+        s->wdelta.push_back(l.weightedCostDelta[i]);
+    }
+    for (int list = 0; list < 2; list++)
+        for (int i = 0; i < nb; i++)
+        {
+            for (int c = 0; c < ncu; c++)
+            {
+                s->mvs.push_back(l.lowresMvs[list][i][c].x);
+                s->mvs.push_back(l.lowresMvs[list][i][c].y);
+            }
+            s->mvCosts.insert(s->mvCosts.end(), l.lowresMvCosts[list][i], l.lowresMvCosts[list][i] + ncu);
+        }
+    s->intraCost.assign(l.intraCost, l.intraCost + ncu);
+    s->intraMode.assign(l.intraMode, l.intraMode + ncu);
+    if (l.qpAqOffset)
+    {
+        s->qpAq.assign(l.qpAqOffset, l.qpAqOffset + ncu);
+        s->qpCuTree.assign(l.qpCuTreeOffset, l.qpCuTreeOffset + ncu);
+        s->invQ.assign(l.invQscaleFactor, l.invQscaleFactor + ncu);
+    }
+    else
+    {
+        s->qpAq.assign(ncu, 0.0); s->qpCuTree.assign(ncu, 0.0); s->invQ.assign(ncu, 256);
+    }
+    s->propagate.assign(l.propagateCost, l.propagateCost + ncu);
+    for (int i = 0; i < 3; i++) { s->h.wp_ssd[i] = l.wp_ssd[i]; s->h.wp_sum[i] = l.wp_sum[i]; }
+    if (h->cfg.dumpPlanes)
+        s->planes.assign(l.buffer[0], l.buffer[0] + 4 * (size_t)s->h.stride * s->h.planeLines);
+
+    s->h.costEst = s->costEst.data(); s->h.costEstAq = s->costEstAq.data();
+    s->h.intraMbs = s->intraMbs.data(); s->h.rowSatds = s->rowSatds.data();
+    s->h.lowresCosts = s->lowresCosts.data(); s->h.mvs = s->mvs.data(); s->h.mvCosts = s->mvCosts.data();
+    s->h.intraCost = s->intraCost.data(); s->h.intraMode = s->intraMode.data();
+    s->h.qpAqOffset = s->qpAq.data(); s->h.qpCuTreeOffset = s->qpCuTree.data();
+    s->h.invQscaleFactor = s->invQ.data(); s->h.propagateCost = s->propagate.data();
+    s->h.weightedCostDelta = s->wdelta.data();
+    s->h.planes = s->planes.empty() ? NULL : (const void*)s->planes.data();
+    h->out.push_back(s);
+}
+
+double nowSec()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+void drain(Handle* h, bool snap)
+{
+    for (;;)
+    {
+        double t0 = nowSec();
+        Frame* f = h->la->getDecidedPicture();
+        h->secondsInLookahead += nowSec() - t0;
+        if (!f)
+            break;
+        if (snap)
+            snapshot(h, f);
+        else
+        {
+            FrameSnap* s = new FrameSnap;
+            memset(&s->h, 0, sizeof(s->h));
+            s->h.poc = f->m_poc; s->h.sliceType = f->m_lowres.sliceType;
+            s->h.bScenecut = f->m_lowres.bScenecut; s->h.bKeyframe = f->m_lowres.bKeyframe;
+            h->out.push_back(s);
+        }
+        h->retired.push_back(f);
+        /* keep a bounded tail alive: m_lastNonB and cuTree only ever look at the most
+         * recent non-B, so anything older than 2*(bframes+2) drained frames is dead */
+        size_t keep = 2 * (size_t)(h->enc->m_param->bframes + 2) + 2;
+        while (h->retired.size() > keep)
+        {
+            Frame* old = h->retired.front();
+            h->retired.erase(h->retired.begin());
+            old->destroy();
+            delete old;
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_la_depth(void) { return X265_DEPTH; }
+
+void* ref_la_open(const RefLaConfig* c)
+{
+    x265_param* p = PARAM_NS::x265_param_alloc();
+    if (!p) return NULL;
+    PARAM_NS::x265_param_default_preset(p, "medium", NULL);
+    p->sourceWidth = c->width; p->sourceHeight = c->height;
+    p->fpsNum = c->fpsNum; p->fpsDenom = c->fpsDenom;
+    p->internalCsp = X265_CSP_I420;
+    p->internalBitDepth = X265_DEPTH;
+    p->sourceBitDepth = X265_DEPTH;
+    p->logLevel = getenv("REF_LA_LOG") ? atoi(getenv("REF_LA_LOG")) : X265_LOG_NONE;
+    p->bframes = c->bframes;
+    p->lookaheadDepth = c->lookaheadDepth;
+    p->bFrameAdaptive = c->bFrameAdaptive;
+    p->bBPyramid = c->bBPyramid;
+    p->scenecutThreshold = c->scenecutThreshold;
+    p->scenecutBias = c->scenecutBias; /* percent; Encoder::configure divides by 100 (encoder.cpp:3948) */
+    p->keyframeMax = c->keyframeMax;
+    p->keyframeMin = c->keyframeMin;
+    p->bOpenGOP = c->bOpenGOP;
+    p->rc.aqMode = c->aqMode;
+    p->rc.aqStrength = c->aqStrength;
+    p->rc.cuTree = c->cuTree;
+    p->rc.qCompress = c->qCompress;
+    p->rc.qgSize = c->qgSize;
+    p->bEnableWeightedPred = c->weightp;
+    p->bEnableWeightedBiPred = c->weightb;
+    p->lookaheadSlices = c->lookaheadSlices;
+    p->bFrameBias = c->bFrameBias;
+    p->bIntraRefresh = c->bIntraRefresh;
+    if (c->vbvBufferSize)
+    {
+        p->rc.rateControlMode = X265_RC_ABR;
+        p->rc.bitrate = c->bitrate;
+        p->rc.vbvBufferSize = c->vbvBufferSize;
+        p->rc.vbvMaxBitrate = c->vbvMaxBitrate;
+    }
+    static char poolStr[32];
+    char* ps = (char*)malloc(32);
+    if (c->poolThreads > 0) snprintf(ps, 32, "%d", c->poolThreads);
+    else snprintf(ps, 32, "none");
+    p->numaPools = ps;
+    p->frameNumThreads = 1;
+    (void)poolStr;
+
+    x265_encoder* e = x265_encoder_open(p);
+    if (!e) { PARAM_NS::x265_param_free(p); return NULL; }
+    Handle* h = new Handle;
+    h->cfg = *c; h->userParam = p;
+    h->enc = static_cast<Encoder*>(e);
+    h->la = h->enc->m_lookahead;
+    h->pocNext = 0; h->flushed = false; h->secondsInLookahead = 0;
+    return h;
+}
+
+/* effective (encoder-configured) parameters the other side must mirror */
+void ref_la_effective(void* hv, int32_t* out /* [16] */)
+{
+    Handle* h = (Handle*)hv;
+    x265_param* p = h->enc->m_param;
+    out[0] = p->sourceWidth; out[1] = p->sourceHeight; out[2] = p->keyframeMin; out[3] = p->keyframeMax;
+    out[4] = p->bframes; out[5] = p->lookaheadDepth; out[6] = p->bFrameAdaptive; out[7] = p->bBPyramid;
+    out[8] = p->rc.aqMode; out[9] = p->rc.cuTree; out[10] = p->rc.qgSize; out[11] = p->lookaheadSlices;
+    out[12] = h->la->m_pool ? h->la->m_pool->m_numWorkers : 0;
+    out[13] = p->bEnableWeightedPred; out[14] = p->bEnableWeightedBiPred; out[15] = p->scenecutThreshold;
+}
+
+/* push one 4:2:0 picture (pixel = uint8_t or uint16_t per this library's depth);
+ * strides in pixels.  Returns total frames decided so far. */
+int ref_la_put(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap)
+{
+    Handle* h = (Handle*)hv;
+    x265_param* p = h->enc->m_param;
+    Frame* f = new Frame;
+    if (!f->create(p, NULL)) return -1;
+    x265_picture pic;
+    x265_picture_init(p, &pic);
+    pic.bitDepth = X265_DEPTH;
+    pic.colorSpace = X265_CSP_I420;
+    pic.planes[0] = (void*)y; pic.planes[1] = (void*)u; pic.planes[2] = (void*)v;
+    pic.stride[0] = strideY * (int)sizeof(pixel);
+    pic.stride[1] = pic.stride[2] = strideC * (int)sizeof(pixel);
+    /* conformance-window padding exactly as Encoder::encode passes it (encoder.cpp:1645) */
+    f->m_fencPic->copyFromPicture(pic, *p, h->enc->m_sps.conformanceWindow.rightOffset,
+                                  h->enc->m_sps.conformanceWindow.bottomOffset);
+    f->m_poc = h->pocNext;
+    f->m_pts = h->pocNext;
+    h->pocNext++;
+    f->m_lowres.sliceTypeReq = X265_TYPE_AUTO;
+    f->m_lowres.bScenecut = false;
+    f->m_lowres.satdCost = (int64_t)-1;
+    f->m_lowresInit = false;
+    double t0 = nowSec();
+    h->la->addPicture(*f, X265_TYPE_AUTO);
+    h->secondsInLookahead += nowSec() - t0;
+    drain(h, snap != 0);
+    return (int)h->out.size();
+}
+
+int ref_la_flush(void* hv, int snap)
+{
+    Handle* h = (Handle*)hv;
+    h->la->flush();
+    h->flushed = true;
+    /* getDecidedPicture returns NULL only once both queues are empty */
+    for (;;)
+    {
+        size_t before = h->out.size();
+        drain(h, snap != 0);
+        if (h->out.size() == before)
+            break;
+    }
+    return (int)h->out.size();
+}
+
+int ref_la_num_out(void* hv) { return (int)((Handle*)hv)->out.size(); }
+double ref_la_seconds(void* hv) { return ((Handle*)hv)->secondsInLookahead; }
+
+int ref_la_get(void* hv, int idx, RefLaFrame* out)
+{
+    Handle* h = (Handle*)hv;
+    if (idx < 0 || idx >= (int)h->out.size()) return -1;
+    *out = h->out[idx]->h;
+    return 0;
+}
+
+void ref_la_close(void* hv)
+{
+    Handle* h = (Handle*)hv;
+    for (size_t i = 0; i < h->out.size(); i++) delete h->out[i];
+    /* Lookahead::destroy (via encoder close) frees frames still queued; drained ones are ours */
+    h->la->stopJobs();
+    for (size_t i = 0; i < h->retired.size(); i++) { h->retired[i]->destroy(); delete h->retired[i]; }
+    x265_encoder_close(h->enc);
+    PARAM_NS::x265_param_free(h->userParam);
+    delete h;
+}
+
+/* ---- primitive-level taps: the reference's own C primitives on caller buffers ---- */
+
+/* the lookahead's mvcost table row (encoder/bitcost.cpp:30-54) for X265_LOOKAHEAD_QP,
+ * entries [-n..n] copied to out[0..2n] */
+int ref_mvcost_table(uint16_t* out, int n)
+{
+    BitCost bc;
+    bc.setQP(X265_LOOKAHEAD_QP);
+    for (int i = -n; i <= n; i++) out[i + n] = bc.m_cost[i];
+    return X265_LOOKAHEAD_QP;
+}
+
+int ref_lookahead_lambda(void) { return (int)x265_lambda_tab[X265_LOOKAHEAD_QP]; }
+
+int ref_satd8x8(const void* a, int sa, const void* b, int sb)
+{ return primitives.pu[LUMA_8x8].satd((const pixel*)a, sa, (const pixel*)b, sb); }
+int ref_sad8x8(const void* a, int sa, const void* b, int sb)
+{ return primitives.pu[LUMA_8x8].sad((const pixel*)a, sa, (const pixel*)b, sb); }
+int ref_exp2fix8(double x) { return x265_exp2fix8(x); }
+
+void ref_setup_primitives(void)
+{
+    x265_param* p = PARAM_NS::x265_param_alloc();
+    PARAM_NS::x265_param_default(p);
+    p->logLevel = X265_LOG_NONE;
+    x265_setup_primitives(p);
+    PARAM_NS::x265_param_free(p);
+}
+
+} // extern "C"
