@@ -1,0 +1,201 @@
+/* x265cu.h -- C ABI of the B200 lookahead engine (libx265cu.so).
+ *
+ * This is the drop-in boundary for the reference's lookahead hot path.  The reference has no
+ * FFI for this path (the only operator-style interface is the per-8x8-block EncoderPrimitives
+ * table, source/common/primitives.h:239-436); these entry points are what a CMake ENABLE_CUDA
+ * build of the reference binds underneath the bodies listed per function below.  Host code
+ * (x265-amod_b200/host/, or the patched reference) owns every decision;
+ * the engine owns every pixel/block operation and keeps a whole lookahead window resident in HBM.
+ *
+ * Conventions: extern "C", opaque context, plain pointers and sizes, every call returns an
+ * int status (0 = X265CU_OK, negative = error; x265cu_strerror() names it).  Nothing throws
+ * (the reference is built -fno-exceptions, source/CMakeLists.txt:358-362).  A context is
+ * bound to one Lookahead instance and one GPU; contexts are independent (abrEncApp runs
+ * several Lookaheads per process, source/abrEncApp.cpp:510).  One caller thread at a time per
+ * context.  There is NO CPU fallback: x265cu_create fails with X265CU_ERR_NO_DEVICE when no
+ * sm_100 device is usable.
+ *
+ * Work is expressed as explicit batches of jobs.  Calls that enqueue work are asynchronous;
+ * the calls documented as "synchronises" wait for the results they return.
+ */
+#ifndef X265CU_H
+#define X265CU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X265CU_OK               0
+#define X265CU_ERR_NO_DEVICE   -1   /* no usable CUDA device / driver */
+#define X265CU_ERR_BAD_ARG     -2
+#define X265CU_ERR_NO_MEMORY   -3
+#define X265CU_ERR_CUDA        -4   /* a CUDA call or kernel failed; see x265cu_last_error */
+#define X265CU_ERR_UNSUPPORTED -5   /* configuration outside the hot path (qg-size 8, HME, ...) */
+
+typedef struct x265cu_ctx x265cu_ctx;
+
+/* Geometry and constants fixed for the life of a Lookahead
+ * (Lookahead::Lookahead, encoder/slicetype.cpp:982-1059; Lowres::create, common/lowres.cpp:72-251). */
+typedef struct
+{
+    int32_t width, height;      /* x265_param::sourceWidth/Height after Encoder::configure padding */
+    int32_t depth;              /* X265_DEPTH: 8, 10 or 12 */
+    int32_t max_cu_size;        /* x265_param::maxCUSize (plane margins, picyuv.cpp:87-88) */
+    int32_t bframes;            /* x265_param::bframes; per-frame arrays are (bframes+2) wide */
+    int32_t max_slots;          /* frame slots resident in HBM */
+    int32_t qg_size;            /* x265_param::rc.qgSize; 16/32/64 (8 -> X265CU_ERR_UNSUPPORTED) */
+    int32_t aq_mode;            /* x265_param::rc.aqMode 0..3 */
+    double  aq_strength;        /* x265_param::rc.aqStrength */
+    int32_t need_aq;            /* Lookahead::m_bAdaptiveQuant (slicetype.cpp:1013-1017) */
+    int32_t need_wp_stats;      /* bEnableWeightedPred || bEnableWeightedBiPred */
+    int32_t lambda;             /* (int)x265_lambda_tab[X265_LOOKAHEAD_QP] */
+    const uint16_t* mvcost;     /* BitCost row for X265_LOOKAHEAD_QP (bitcost.cpp:46-54): entries */
+    int32_t mvcost_half;        /*   [-mvcost_half, +mvcost_half], centre at mvcost[mvcost_half]   */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t reserved[8];
+} x265cu_config;
+
+/* derived geometry, as Lowres::create computes it */
+typedef struct
+{
+    int32_t low_width, low_height;   /* lowres plane size (multiples of 8) */
+    int32_t bw, bh, ncu;             /* 8x8 block grid: m_8x8Width/Height/m_cuCount */
+    int32_t stride, plane_lines;     /* plane stride (pixels) and lines incl. margins */
+    int32_t margin_x, margin_y;
+    int32_t nb;                      /* bframes + 2 */
+    int32_t n_mv_stores;             /* MV stores per slot  = 3*nb (see x265cu_search_job::store) */
+    int32_t n_cost_stores;           /* cost stores per slot = 2*nb*nb */
+} x265cu_geometry;
+
+int  x265cu_device_count(void);
+int  x265cu_create(const x265cu_config* cfg, x265cu_ctx** out);
+void x265cu_destroy(x265cu_ctx* ctx);
+int  x265cu_get_geometry(const x265cu_ctx* ctx, x265cu_geometry* out);
+const char* x265cu_strerror(int status);
+const char* x265cu_last_error(const x265cu_ctx* ctx);
+
+/* Page-lock / unlock a host picture buffer so uploads run at full PCIe rate (optional). */
+int  x265cu_pin_host(x265cu_ctx* ctx, void* ptr, uint64_t bytes);
+int  x265cu_unpin_host(x265cu_ctx* ctx, void* ptr);
+
+/* ---- pre-lookahead: replaces the body of PreLookaheadGroup::processTasks
+ * (slicetype.cpp:1726-1752): Lowres::init pixel work (lowres.cpp:367-376), calcAdaptiveQuantFrame
+ * (slicetype.cpp:452-713) and lowresIntraEstimate (:715-824) for one frame.
+ * Planes are `depth`-bit samples in uint8_t (depth 8) or uint16_t; strides in samples; the
+ * picture is width x height (chroma 4:2:0, may be NULL for 4:0:0).  Asynchronous: the host
+ * buffers must stay valid until the next synchronising call on this context. */
+int  x265cu_frame_upload(x265cu_ctx* ctx, int32_t slot, const void* y, const void* u, const void* v,
+                         int32_t stride_y, int32_t stride_c);
+
+typedef struct
+{
+    int64_t  cost_est;      /* Lowres::costEst[0][0]   */
+    int64_t  cost_est_aq;   /* Lowres::costEstAq[0][0] */
+    uint64_t wp_ssd[3];     /* Lowres::wp_ssd (finalised, slicetype.cpp:681-694) */
+    uint64_t wp_sum[3];     /* Lowres::wp_sum */
+} x265cu_frame_stats;
+/* synchronises */
+int  x265cu_frame_stats_get(x265cu_ctx* ctx, const int32_t* slots, int32_t n, x265cu_frame_stats* out);
+
+/* ---- motion search: the search half of CostEstimateGroup::estimateCUCost (slicetype.cpp:
+ * 4103-4183) + MotionEstimate::motionEstimate (motion.cpp:764-1594, HEX + lowres subpel) for one
+ * (frame, list, distance) over the whole frame, reverse-raster dependency order preserved. */
+typedef struct
+{
+    int32_t fenc_slot, ref_slot;
+    int32_t bidir_ctx;      /* 1 when the reference would run this search inside a B estimate
+                               (b < p1): enables the zero-MV skip rule, slicetype.cpp:4165-4181 */
+    int32_t store;          /* MV store of fenc_slot that receives MVs + MV costs:
+                               kind*nb + dist, kind 0 = L0 in P context, 1 = L0 in B context, 2 = L1 */
+    int32_t weighted;       /* search the weighted copy of the reference (slicetype.cpp:4083,4128) */
+    int32_t w_scale, w_denom, w_offset; /* WeightParam inputWeight/log2WeightDenom/inputOffset */
+} x265cu_search_job;
+int  x265cu_search_batch(x265cu_ctx* ctx, const x265cu_search_job* jobs, int32_t n);
+
+/* ---- frame cost: the cost half of estimateCUCost (slicetype.cpp:4187-4248) and the sums of
+ * estimateFrameCost (:4050-4062) for one (p0,p1,b).  P estimate: p1_slot == b_slot, l1_store < 0. */
+typedef struct
+{
+    int32_t b_slot, p0_slot, p1_slot;
+    int32_t l0_store, l1_store;   /* MV stores of b_slot to read */
+    int32_t out;                  /* cost store of b_slot: (d0*nb + d1)*2 + variant */
+} x265cu_cost_job;
+int  x265cu_cost_batch(x265cu_ctx* ctx, const x265cu_cost_job* jobs, int32_t n);
+
+typedef struct
+{
+    int64_t cost_est;       /* sum over interior blocks, before the B-frame scaling of :4064-4065 */
+    int64_t cost_est_aq;
+    int32_t intra_mbs;      /* P estimates only */
+    int32_t reserved;
+} x265cu_cost_result;
+/* synchronises; result i is for (slots[i], outs[i]) */
+int  x265cu_cost_results_get(x265cu_ctx* ctx, const int32_t* slots, const int32_t* outs, int32_t n,
+                             x265cu_cost_result* res);
+
+/* ---- weightp: LookaheadTLD::weightCostLuma (slicetype.cpp:826-859).  weighted == 0 scores the
+ * plain reference; else weight_pp (pixel.cpp:518-541) is applied first.  synchronises. */
+typedef struct
+{
+    int32_t fenc_slot, ref_slot;
+    int32_t weighted, w_scale, w_denom, w_offset;
+} x265cu_wcost_job;
+int  x265cu_weight_cost_batch(x265cu_ctx* ctx, const x265cu_wcost_job* jobs, int32_t n, uint32_t* costs);
+
+/* ---- cuTree: Lookahead::estimateCUPropagate (slicetype.cpp:3502-3604) with
+ * primitives.propagateCost (pixel.cpp:931-957), cuTreeFinish (:3750-3798) and
+ * frameCostRecalculate (:3802-3879). */
+int  x265cu_cutree_reset(x265cu_ctx* ctx, int32_t slot);   /* memset(propagateCost, 0) */
+int  x265cu_cutree_propagate(x265cu_ctx* ctx, int32_t b_slot, int32_t p0_slot, int32_t p1_slot,
+                             int32_t cost_store, int32_t l0_store, int32_t l1_store,
+                             int32_t referenced, int32_t bipred_weight, double fps_factor);
+int  x265cu_cutree_finish(x265cu_ctx* ctx, int32_t slot, int32_t fps_factor_fix8, double weightdelta,
+                          double cutree_strength);
+/* synchronises; row_satds may be NULL */
+int  x265cu_cost_recalc(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, int32_t use_cutree_offsets,
+                        int64_t* score, int32_t* row_satds);
+
+/* ---- host mirrors of Lowres fields (all synchronise; NULL pointers are skipped) */
+typedef struct
+{
+    int32_t*  intra_cost;        /* ncu */
+    uint8_t*  intra_mode;        /* ncu */
+    double*   qp_aq_offset;      /* ncu */
+    double*   qp_cutree_offset;  /* ncu */
+    int32_t*  inv_qscale_factor; /* ncu */
+    uint16_t* propagate_cost;    /* ncu */
+    void*     planes;            /* 4 * stride * plane_lines samples: Lowres::buffer[0] */
+    uint16_t* lowres_costs00;    /* ncu: lowresCosts[0][0] */
+    int32_t*  row_satds00;       /* bh:  rowSatds[0][0] */
+} x265cu_frame_out;
+int  x265cu_fetch_frame(x265cu_ctx* ctx, int32_t slot, const x265cu_frame_out* out);
+int  x265cu_fetch_mvs(x265cu_ctx* ctx, int32_t slot, int32_t store, int32_t* mv_xy /* ncu*2 */,
+                      int32_t* mv_costs /* ncu */);
+int  x265cu_fetch_costs(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, uint16_t* lowres_costs /* ncu */,
+                        int32_t* row_satds /* bh */);
+
+/* wait for everything enqueued on this context */
+int  x265cu_sync(x265cu_ctx* ctx);
+
+/* counters for bench.py: kernels launched and bytes copied since create */
+typedef struct { uint64_t kernel_launches, h2d_bytes, d2h_bytes; } x265cu_counters;
+int  x265cu_get_counters(const x265cu_ctx* ctx, x265cu_counters* out);
+
+/* timing hook for bench.py: device time (ms, CUDA events on the engine's stream) spent in each
+ * kernel family since the last reset; enabling it adds two event records per launch */
+#define X265CU_K_LOWRES 0
+#define X265CU_K_AQ     1
+#define X265CU_K_INTRA  2
+#define X265CU_K_SEARCH 3
+#define X265CU_K_COST   4
+#define X265CU_K_WEIGHT 5
+#define X265CU_K_CUTREE 6
+#define X265CU_K_COUNT  7
+int  x265cu_profile_enable(x265cu_ctx* ctx, int32_t on);
+int  x265cu_profile_get(x265cu_ctx* ctx, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

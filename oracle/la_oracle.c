@@ -1,0 +1,903 @@
+/* la_oracle.c -- CPU restatement of the reference lookahead's block-level arithmetic.
+ * TEST INFRASTRUCTURE ONLY; see la_oracle.h for scope, pinning status and usage rules.
+ * Citations are file:line under /root/reference/source/. */
+#include "la_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define OR_MAXV ((1 << OR_DEPTH) - 1)
+#define OR_COST_MAX (1 << 28)            /* encoder/motion.h:65 */
+#define OR_LOWRES_COST_MASK 16383        /* encoder/slicetype.h:41 */
+#define OR_LOWRES_COST_SHIFT 14
+
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+int or_depth(void) { return OR_DEPTH; }
+
+/* common/lowres.cpp:72-97, common/picyuv.cpp:87-88 */
+void or_geom_init(or_geom* g, int picW, int picH, int maxCUSize)
+{
+    g->picW = picW; g->picH = picH;
+    int lw = picW / 2, lh = picH / 2;
+    g->mx = maxCUSize + 32; g->my = maxCUSize + 16;
+    g->stride = lw + 2 * g->mx;
+    if (g->stride & 31) g->stride += 32 - (g->stride & 31);
+    g->bw = (lw + 7) >> 3; g->bh = (lh + 7) >> 3; g->ncu = g->bw * g->bh;
+    g->w = g->bw * 8; g->h = g->bh * 8;
+    g->planeLines = g->h + 2 * g->my;
+    g->planeSize = (int64_t)g->stride * g->planeLines;
+    g->padOffset = (int64_t)g->stride * g->my + g->mx;
+}
+
+/* common/constants.cpp:34-90: lambda = 2^(qp/6 - 2) * 2^(depth-8); X265_LOOKAHEAD_QP = 12 + 6*(depth-8)
+ * (common/common.h:209-213) -> 1, 16, 256 for 8/10/12 bit */
+int or_lookahead_lambda(void) { return 1 << (2 * (OR_DEPTH - 8)); }
+
+/* encoder/bitcost.cpp:46-54 (cost row) and :98-113 (bit sizes, float arithmetic) */
+void or_build_mvcost(uint16_t* table, int half)
+{
+    double lambda = (double)or_lookahead_lambda();
+    float log2_2 = 2.0f / logf(2.0f);
+    for (int i = 0; i <= half; i++)
+    {
+        float bits = i ? logf((float)(i + 1)) * log2_2 + 1.718f : 0.718f;
+        double c = bits * lambda + 0.5f;
+        if (c > (double)((1 << 15) - 1)) c = (double)((1 << 15) - 1);
+        table[half + i] = table[half - i] = (uint16_t)c;
+    }
+}
+
+/* common/constants.cpp:552-558 */
+static const uint8_t exp2_lut[64] = {
+    0, 3, 6, 8, 11, 14, 17, 20, 23, 26, 29, 32, 36, 39, 42, 45,
+    48, 52, 55, 58, 62, 65, 69, 72, 76, 80, 83, 87, 91, 94, 98, 102,
+    106, 110, 114, 118, 122, 126, 130, 135, 139, 143, 147, 152, 156, 161, 165, 170,
+    175, 179, 184, 189, 194, 198, 203, 208, 214, 219, 224, 229, 234, 240, 245, 250 };
+
+/* common/common.cpp:96-103 */
+int or_exp2fix8(double x)
+{
+    int i = (int)(x * (-64.f / 6.f) + 512.5f);
+    if (i < 0) return 0;
+    if (i > 1023) return 0xffff;
+    return (exp2_lut[i & 63] + 256) << (i >> 6) >> 8;
+}
+
+/* common/pixel.cpp:40-56 */
+int or_sad8x8(const or_pixel* a, int sa, const or_pixel* b, int sb)
+{
+    int sum = 0;
+    for (int y = 0; y < 8; y++, a += sa, b += sb)
+        for (int x = 0; x < 8; x++)
+            sum += abs((int)a[x] - (int)b[x]);
+    return sum;
+}
+
+/* SATD of an 8x8 block as the reference defines it (pixel.cpp:239-297): two 8x4 halves, each
+ * the sum of |4x4 Hadamard coefficients| of its two 4x4 blocks, halved (>>1) per 8x4. */
+static int hadamard4x4_abs(const or_pixel* a, int sa, const or_pixel* b, int sb)
+{
+    int d[4][4], t[4][4], sum = 0;
+    for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++)
+            d[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+    for (int y = 0; y < 4; y++)
+    {
+        int s01 = d[y][0] + d[y][1], d01 = d[y][0] - d[y][1];
+        int s23 = d[y][2] + d[y][3], d23 = d[y][2] - d[y][3];
+        t[y][0] = s01 + s23; t[y][1] = s01 - s23; t[y][2] = d01 + d23; t[y][3] = d01 - d23;
+    }
+    for (int x = 0; x < 4; x++)
+    {
+        int s01 = t[0][x] + t[1][x], d01 = t[0][x] - t[1][x];
+        int s23 = t[2][x] + t[3][x], d23 = t[2][x] - t[3][x];
+        sum += abs(s01 + s23) + abs(s01 - s23) + abs(d01 + d23) + abs(d01 - d23);
+    }
+    return sum;
+}
+
+int or_satd8x8(const or_pixel* a, int sa, const or_pixel* b, int sb)
+{
+    int total = 0;
+    for (int row = 0; row < 8; row += 4)
+    {
+        int s = hadamard4x4_abs(a + row * sa, sa, b + row * sb, sb) +
+                hadamard4x4_abs(a + row * sa + 4, sa, b + row * sb + 4, sb);
+        total += s >> 1;
+    }
+    return total;
+}
+
+/* ------------------------------------------------------------------ lowres planes */
+
+static inline int src_at(const or_pixel* src, int stride, int W, int H, int x, int y)
+{
+    if (x > W - 1) x = W - 1;
+    if (y > H - 1) y = H - 1;
+    return src[(int64_t)y * stride + x];
+}
+
+#define OR_FILTER(a, b, c, d) ((((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1)
+
+/* common/pixel.cpp:605-628 + common/lowres.cpp:367-376 + pixel.cpp:1044-1058 + ipfilter.cpp:59-77 */
+void or_lowres_init(const or_geom* g, const or_pixel* srcY, int srcStride, or_pixel* buf)
+{
+    or_pixel* pl[4];
+    for (int i = 0; i < 4; i++) pl[i] = buf + i * g->planeSize + g->padOffset;
+    const int W = g->picW, H = g->picH, st = g->stride;
+    for (int y = 0; y < g->h; y++)
+        for (int x = 0; x < g->w; x++)
+        {
+            int a00 = src_at(srcY, srcStride, W, H, 2 * x, 2 * y),     a01 = src_at(srcY, srcStride, W, H, 2 * x + 1, 2 * y),     a02 = src_at(srcY, srcStride, W, H, 2 * x + 2, 2 * y);
+            int a10 = src_at(srcY, srcStride, W, H, 2 * x, 2 * y + 1), a11 = src_at(srcY, srcStride, W, H, 2 * x + 1, 2 * y + 1), a12 = src_at(srcY, srcStride, W, H, 2 * x + 2, 2 * y + 1);
+            int a20 = src_at(srcY, srcStride, W, H, 2 * x, 2 * y + 2), a21 = src_at(srcY, srcStride, W, H, 2 * x + 1, 2 * y + 2), a22 = src_at(srcY, srcStride, W, H, 2 * x + 2, 2 * y + 2);
+            pl[0][y * st + x] = (or_pixel)OR_FILTER(a00, a10, a01, a11);
+            pl[1][y * st + x] = (or_pixel)OR_FILTER(a01, a11, a02, a12);
+            pl[2][y * st + x] = (or_pixel)OR_FILTER(a10, a20, a11, a21);
+            pl[3][y * st + x] = (or_pixel)OR_FILTER(a11, a21, a12, a22);
+        }
+    for (int i = 0; i < 4; i++)
+    {
+        or_pixel* p = pl[i];
+        for (int y = 0; y < g->h; y++)
+            for (int x = 0; x < g->mx; x++)
+            {
+                p[y * st - g->mx + x] = p[y * st];
+                p[y * st + g->w + x] = p[y * st + g->w - 1];
+            }
+        /* rows above/below copy one whole buffer row of `stride` pixels */
+        or_pixel* top = p - g->mx;
+        for (int y = 0; y < g->my; y++)
+            memcpy(top - (y + 1) * st, top, st * sizeof(or_pixel));
+        or_pixel* bot = p - g->mx + (g->h - 1) * st;
+        for (int y = 0; y < g->my; y++)
+            memcpy(bot + (y + 1) * st, bot, st * sizeof(or_pixel));
+    }
+}
+
+/* ------------------------------------------------------------------ adaptive quant */
+
+/* pixel_var<N> + acEnergyVar (pixel.cpp:720-737, slicetype.cpp:49-57); source is addressed
+ * with replicate clamping (blocks may overhang the picture into PicYuv's padding) */
+static uint32_t block_energy(const or_pixel* p, int stride, int W, int H, int bx, int by, int size, int shift,
+                             uint64_t* wpSum, uint64_t* wpSsd)
+{
+    uint32_t sum = 0, sqr = 0;
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++)
+        {
+            uint32_t v = (uint32_t)src_at(p, stride, W, H, bx + x, by + y);
+            sum += v; sqr += v * v;
+        }
+    *wpSum += sum; *wpSsd += sqr;
+    return sqr - (uint32_t)(((uint64_t)sum * sum) >> shift);
+}
+
+/* encoder/slicetype.cpp:452-713, qg-size > 8 */
+void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v,
+                 int strideC, int aqMode, double aqStrength, int bWeightP,
+                 double* qpAqOffset, double* qpCuTreeOffset, int32_t* invQscaleFactor,
+                 uint32_t* blockEnergy, uint64_t wp_ssd[3], uint64_t wp_sum[3])
+{
+    const int W = g->picW, H = g->picH;
+    const int blockCount = g->ncu;
+    const float modeOneConst = 14.427f, modeTwoConst = 11.f;
+    for (int i = 0; i < 3; i++) wp_ssd[i] = wp_sum[i] = 0;
+    uint32_t* energy = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)blockCount);
+    int n = 0;
+    for (int by = 0; by < H; by += 16)
+        for (int bx = 0; bx < W; bx += 16, n++)
+        {
+            uint32_t e = block_energy(y, strideY, W, H, bx, by, 16, 8, &wp_sum[0], &wp_ssd[0]);
+            if (u && v)
+            {
+                e += block_energy(u, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, 8, 6, &wp_sum[1], &wp_ssd[1]);
+                e += block_energy(v, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, 8, 6, &wp_sum[2], &wp_ssd[2]);
+            }
+            energy[n] = e;
+            if (blockEnergy) blockEnergy[n] = e;
+        }
+
+    if (aqMode == 0 || aqStrength == 0)
+    {
+        if (aqMode && aqStrength == 0)
+            for (int i = 0; i < blockCount; i++) { qpAqOffset[i] = qpCuTreeOffset[i] = 0; invQscaleFactor[i] = 256; }
+    }
+    else
+    {
+        double avg_adj_pow2 = 0, avg_adj = 0, qp_adj = 0, bias_strength = 0, strength = 0;
+        if (aqMode == 2 || aqMode == 3)
+        {
+            double bit_depth_correction = 1.f / (1 << (2 * (OR_DEPTH - 8)));
+            for (int i = 0; i < blockCount; i++)
+            {
+                qp_adj = pow(energy[i] * bit_depth_correction + 1, 0.1);
+                qpCuTreeOffset[i] = qp_adj;
+                avg_adj += qp_adj;
+                avg_adj_pow2 += qp_adj * qp_adj;
+            }
+            avg_adj /= blockCount;
+            avg_adj_pow2 /= blockCount;
+            strength = aqStrength * avg_adj;
+            avg_adj = avg_adj - 0.5f * (avg_adj_pow2 - modeTwoConst) / avg_adj;
+            bias_strength = 1.0 /* aqBiasStrength default */ * aqStrength;
+        }
+        else
+            strength = aqStrength * 1.0397f;
+        for (int i = 0; i < blockCount; i++)
+        {
+            if (aqMode == 3)
+            {
+                qp_adj = qpCuTreeOffset[i];
+                qp_adj = strength * (qp_adj - avg_adj) + bias_strength * (1.f - modeTwoConst / (qp_adj * qp_adj));
+            }
+            else if (aqMode == 2)
+            {
+                qp_adj = qpCuTreeOffset[i];
+                qp_adj = strength * (qp_adj - avg_adj);
+            }
+            else
+            {
+                uint32_t e = energy[i] > 1 ? energy[i] : 1;
+                qp_adj = strength * (log2((double)e) - (modeOneConst + 2 * (OR_DEPTH - 8)));
+            }
+            qpAqOffset[i] = qp_adj;
+            qpCuTreeOffset[i] = qp_adj;
+            invQscaleFactor[i] = or_exp2fix8(qp_adj);
+        }
+    }
+    if (bWeightP)
+    {
+        int maxCol = ((W + 8) >> 4) << 4, maxRow = ((H + 8) >> 4) << 4;
+        int wd[3] = { maxCol, maxCol >> 1, maxCol >> 1 }, ht[3] = { maxRow, maxRow >> 1, maxRow >> 1 };
+        for (int i = 0; i < 3; i++)
+        {
+            uint64_t sum = wp_sum[i], ssd = wp_ssd[i];
+            wp_ssd[i] = ssd - (sum * sum + (uint64_t)(wd[i] * ht[i]) / 2) / (uint64_t)(wd[i] * ht[i]);
+        }
+    }
+    free(energy);
+}
+
+/* ------------------------------------------------------------------ intra */
+
+/* common/constants.cpp:561-567 */
+static const uint8_t intraFilterFlags[35] = {
+    0x38, 0x00,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38 };
+
+/* common/intrapred.cpp:31-51 (tuSize 8): nb[0]=top-left, [1..16]=top, [17..32]=left */
+static void intra_filter8(const or_pixel* s, or_pixel* f)
+{
+    int topLeft = s[0], topLast = s[16], leftLast = s[32];
+    for (int i = 1; i < 16; i++) f[i] = (or_pixel)(((s[i] << 1) + s[i - 1] + s[i + 1] + 2) >> 2);
+    f[16] = (or_pixel)topLast;
+    f[0] = (or_pixel)(((topLeft << 1) + s[1] + s[17] + 2) >> 2);
+    f[17] = (or_pixel)(((s[17] << 1) + topLeft + s[18] + 2) >> 2);
+    for (int i = 18; i < 32; i++) f[i] = (or_pixel)(((s[i] << 1) + s[i - 1] + s[i + 1] + 2) >> 2);
+    f[32] = (or_pixel)leftLast;
+}
+
+/* common/intrapred.cpp:53-85 */
+static void pred_dc8(or_pixel* dst, const or_pixel* s)
+{
+    int dc = 8;
+    for (int i = 0; i < 8; i++) dc += s[1 + i] + s[17 + i];
+    dc /= 16;
+    for (int i = 0; i < 64; i++) dst[i] = (or_pixel)dc;
+    const or_pixel* above = s + 1; const or_pixel* left = s + 17;
+    dst[0] = (or_pixel)((above[0] + left[0] + 2 * dst[0] + 2) >> 2);
+    for (int x = 1; x < 8; x++) dst[x] = (or_pixel)((above[x] + 3 * dst[x] + 2) >> 2);
+    for (int y = 1; y < 8; y++) dst[y * 8] = (or_pixel)((left[y] + 3 * dst[y * 8] + 2) >> 2);
+}
+
+/* common/intrapred.cpp:87-100 */
+static void pred_planar8(or_pixel* dst, const or_pixel* s)
+{
+    const or_pixel* above = s + 1; const or_pixel* left = s + 17;
+    int topRight = above[8], bottomLeft = left[8];
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++)
+            dst[y * 8 + x] = (or_pixel)(((7 - x) * left[y] + (7 - y) * above[x] + (x + 1) * topRight + (y + 1) * bottomLeft + 8) >> 4);
+}
+
+/* common/intrapred.cpp:102-204 (width 8, bFilter = 1) */
+static void pred_ang8(or_pixel* dst, const or_pixel* s0, int mode)
+{
+    static const int8_t angleTable[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+    static const int16_t invAngleTable[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+    int hor = mode < 18;
+    or_pixel nb[33];
+    const or_pixel* s = s0;
+    if (hor)
+    {
+        nb[0] = s0[0];
+        for (int i = 0; i < 16; i++) { nb[1 + i] = s0[17 + i]; nb[17 + i] = s0[1 + i]; }
+        s = nb;
+    }
+    int angleOffset = hor ? 10 - mode : mode - 26;
+    int angle = angleTable[8 + angleOffset];
+    if (!angle)
+    {
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) dst[y * 8 + x] = s[1 + x];
+        int topLeft = s[0], top = s[1];
+        for (int y = 0; y < 8; y++)
+        {
+            int v = (int16_t)(top + ((s[17 + y] - topLeft) >> 1));
+            dst[y * 8] = (or_pixel)(v < 0 ? 0 : (v > OR_MAXV ? OR_MAXV : v));
+        }
+    }
+    else
+    {
+        or_pixel refBuf[64]; const or_pixel* ref;
+        if (angle < 0)
+        {
+            int nbProjected = -((8 * angle) >> 5) - 1;
+            or_pixel* rp = refBuf + nbProjected + 1;
+            int invAngle = invAngleTable[-angleOffset - 1], invAngleSum = 128;
+            for (int i = 0; i < nbProjected; i++) { invAngleSum += invAngle; rp[-2 - i] = s[16 + (invAngleSum >> 8)]; }
+            for (int i = 0; i < 9; i++) rp[-1 + i] = s[i];
+            ref = rp;
+        }
+        else
+            ref = s + 1;
+        int angleSum = 0;
+        for (int y = 0; y < 8; y++)
+        {
+            angleSum += angle;
+            int off = angleSum >> 5, frac = angleSum & 31;
+            for (int x = 0; x < 8; x++)
+                dst[y * 8 + x] = frac ? (or_pixel)(((32 - frac) * ref[off + x] + frac * ref[off + x + 1] + 16) >> 5) : ref[off + x];
+        }
+    }
+    if (hor)
+        for (int y = 0; y < 7; y++)
+            for (int x = y + 1; x < 8; x++)
+            { or_pixel t = dst[y * 8 + x]; dst[y * 8 + x] = dst[x * 8 + y]; dst[x * 8 + y] = t; }
+}
+
+/* encoder/slicetype.cpp:715-824 */
+void or_intra_estimate(const or_geom* g, const or_pixel* plane0, const int32_t* invQ,
+                       int32_t* intraCost, uint8_t* intraMode, uint16_t* lowresCosts00,
+                       int32_t* rowSatds00, int64_t* costEst00, int64_t* costEstAq00)
+{
+    const int lambda = or_lookahead_lambda();
+    const int intraPenalty = 5 * lambda, lowresPenalty = 4;
+    const int st = g->stride;
+    int64_t costEst = 0, costEstAq = 0;
+    or_pixel pred[64], fenc[64], nbA[33], nbF[33];
+    for (int cuY = 0; cuY < g->bh; cuY++)
+    {
+        rowSatds00[cuY] = 0;
+        for (int cuX = 0; cuX < g->bw; cuX++)
+        {
+            const int cuXY = cuX + cuY * g->bw;
+            const or_pixel* pix = plane0 + 8 * cuX + (int64_t)8 * cuY * st;
+            for (int y = 0; y < 8; y++) memcpy(fenc + 8 * y, pix + y * st, 8 * sizeof(or_pixel));
+            const or_pixel* c = pix - st - 1;
+            memcpy(nbA, c, 17 * sizeof(or_pixel));
+            for (int i = 1; i <= 16; i++) nbA[16 + i] = c[(int64_t)i * st];
+            intra_filter8(nbA, nbF);
+
+            int cost, icost = OR_COST_MAX, ilow = 0;
+            pred_dc8(pred, nbA);
+            cost = or_satd8x8(fenc, 8, pred, 8);
+            if (cost < icost) { icost = cost; ilow = 1; }
+            pred_planar8(pred, nbF);
+            cost = or_satd8x8(fenc, 8, pred, 8);
+            if (cost < icost) { icost = cost; ilow = 0; }
+            int acost = OR_COST_MAX, alow = 4;
+            for (int mode = 5; mode < 35; mode += 5)
+            {
+                pred_ang8(pred, (intraFilterFlags[mode] & 8) ? nbF : nbA, mode);
+                cost = or_satd8x8(fenc, 8, pred, 8);
+                if (cost < acost) { acost = cost; alow = mode; }
+            }
+            for (int dist = 2; dist >= 1; dist--)
+            {
+                int minus = alow - dist, plus = alow + dist;
+                pred_ang8(pred, (intraFilterFlags[minus] & 8) ? nbF : nbA, minus);
+                cost = or_satd8x8(fenc, 8, pred, 8);
+                if (cost < acost) { acost = cost; alow = minus; }
+                pred_ang8(pred, (intraFilterFlags[plus] & 8) ? nbF : nbA, plus);
+                cost = or_satd8x8(fenc, 8, pred, 8);
+                if (cost < acost) { acost = cost; alow = plus; }
+            }
+            if (acost < icost) { icost = acost; ilow = alow; }
+            icost += intraPenalty + lowresPenalty;
+            lowresCosts00[cuXY] = (uint16_t)imin(icost, OR_LOWRES_COST_MASK);
+            intraCost[cuXY] = icost;
+            intraMode[cuXY] = (uint8_t)ilow;
+            int scored = (cuX > 0 && cuX < g->bw - 1 && cuY > 0 && cuY < g->bh - 1) || g->bw <= 2 || g->bh <= 2;
+            int icostAq = (scored && invQ) ? ((icost * invQ[cuXY] + 128) >> 8) : icost;
+            if (scored) { costEst += icost; costEstAq += icostAq; }
+            rowSatds00[cuY] += icostAq;
+        }
+    }
+    *costEst00 = costEst;
+    *costEstAq00 = costEstAq;
+}
+
+/* ------------------------------------------------------------------ motion search */
+
+typedef struct { int x, y; } or_mv;
+
+typedef struct
+{
+    const or_geom* g;
+    or_pixel fenc[64];
+    const or_pixel* ref[4];      /* lowresPlane[0..3] + block offset */
+    int stride;
+    const uint16_t* mvcost;      /* centre */
+    or_mv mvp;
+} or_me;
+
+static inline int mvcost_q(const or_me* m, int qx, int qy)   /* bitcost.h:46 */
+{
+    return (uint16_t)(m->mvcost[qx - m->mvp.x] + m->mvcost[qy - m->mvp.y]);
+}
+
+/* ReferencePlanes::lowresMC (common/lowres.h:71-96): returns pointer+stride of the 8x8 prediction */
+static const or_pixel* lowres_mc(const or_me* m, int qx, int qy, or_pixel* buf, int* outStride)
+{
+    const int st = m->stride;
+    if ((qx | qy) & 1)
+    {
+        int hpelA = (qy & 2) | ((qx & 2) >> 1);
+        const or_pixel* a = m->ref[hpelA] + (qx >> 2) + (int64_t)(qy >> 2) * st;
+        int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
+        int hpelB = (qy2 & 2) | ((qx2 & 2) >> 1);
+        const or_pixel* b = m->ref[hpelB] + (qx2 >> 2) + (int64_t)(qy2 >> 2) * st;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++)
+                buf[y * 8 + x] = (or_pixel)((a[y * st + x] + b[y * st + x] + 1) >> 1);
+        *outStride = 8;
+        return buf;
+    }
+    int hpel = (qy & 2) | ((qx & 2) >> 1);
+    *outStride = st;
+    return m->ref[hpel] + (qx >> 2) + (int64_t)(qy >> 2) * st;
+}
+
+/* ReferencePlanes::lowresQPelCost (common/lowres.h:98-124) */
+static int qpel_cost(const or_me* m, int qx, int qy, int useSatd)
+{
+    or_pixel buf[64]; int st;
+    const or_pixel* p = lowres_mc(m, qx, qy, buf, &st);
+    return useSatd ? or_satd8x8(m->fenc, 8, p, st) : or_sad8x8(m->fenc, 8, p, st);
+}
+
+static inline int sad_fpel(const or_me* m, int x, int y)
+{
+    return or_sad8x8(m->fenc, 8, m->ref[0] + x + (int64_t)y * m->stride, m->stride);
+}
+
+static const or_mv hex2[8] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };   /* motion.cpp:64 */
+static const uint8_t mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };                                               /* motion.cpp:65 */
+static const or_mv square1[9] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} }; /* :66 */
+
+/* MotionEstimate::motionEstimate, lowres path: HEX search + lowres subpel, merange 16, subpelRefine 1
+ * (encoder/motion.cpp:764-821, 870-969, 1473-1528) */
+static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv* out)
+{
+    const int merange = 16;
+    m->mvp = qmvp;
+    or_mv qmin = { mvmin.x << 2, mvmin.y << 2 }, qmax = { mvmax.x << 2, mvmax.y << 2 };
+    or_mv pmv = { imax(imin(qmvp.x, qmax.x), qmin.x), imax(imin(qmvp.y, qmax.y), qmin.y) };
+    or_mv bestpre = pmv;
+    int bprecost = qpel_cost(m, pmv.x, pmv.y, 0);
+    or_mv bmv = { (pmv.x + 2) >> 2, (pmv.y + 2) >> 2 };
+    int bcost = bprecost;
+    if ((pmv.x & 3) | (pmv.y & 3))
+        bcost = sad_fpel(m, bmv.x, bmv.y) + mvcost_q(m, bmv.x << 2, bmv.y << 2);
+    if (pmv.x | pmv.y)
+    {
+        int cost = sad_fpel(m, 0, 0) + mvcost_q(m, 0, 0);
+        if (cost < bcost)
+        {
+            bcost = cost;
+            bmv.x = 0;
+            bmv.y = imax(imin(0, mvmax.y), mvmin.y);
+        }
+    }
+#define YOK(dy) ((bmv.y + (dy) >= mvmin.y) & (bmv.y + (dy) <= mvmax.y))
+#define COSTAT(dx, dy) (sad_fpel(m, bmv.x + (dx), bmv.y + (dy)) + mvcost_q(m, (bmv.x + (dx)) << 2, (bmv.y + (dy)) << 2))
+    {
+        int c0 = COSTAT(-2, 0), c1 = COSTAT(-1, 2), c2 = COSTAT(1, 2);
+        bcost <<= 3;
+        if (YOK(0)) { if ((c0 << 3) + 2 < bcost) bcost = (c0 << 3) + 2; }
+        if (YOK(2)) { if ((c1 << 3) + 3 < bcost) bcost = (c1 << 3) + 3; if ((c2 << 3) + 4 < bcost) bcost = (c2 << 3) + 4; }
+        c0 = COSTAT(2, 0); c1 = COSTAT(1, -2); c2 = COSTAT(-1, -2);
+        if (YOK(0)) { if ((c0 << 3) + 5 < bcost) bcost = (c0 << 3) + 5; }
+        if (YOK(-2)) { if ((c1 << 3) + 6 < bcost) bcost = (c1 << 3) + 6; if ((c2 << 3) + 7 < bcost) bcost = (c2 << 3) + 7; }
+        if (bcost & 7)
+        {
+            int dir = (bcost & 7) - 2;
+            if (YOK(hex2[dir + 1].y))
+            {
+                bmv.x += hex2[dir + 1].x; bmv.y += hex2[dir + 1].y;
+                for (int i = (merange >> 1) - 1;
+                     i > 0 && bmv.x >= mvmin.x && bmv.x <= mvmax.x && bmv.y >= mvmin.y && bmv.y <= mvmax.y; i--)
+                {
+                    c0 = COSTAT(hex2[dir + 0].x, hex2[dir + 0].y);
+                    c1 = COSTAT(hex2[dir + 1].x, hex2[dir + 1].y);
+                    c2 = COSTAT(hex2[dir + 2].x, hex2[dir + 2].y);
+                    bcost &= ~7;
+                    if (YOK(hex2[dir + 0].y)) { if ((c0 << 3) + 1 < bcost) bcost = (c0 << 3) + 1; }
+                    if (YOK(hex2[dir + 1].y)) { if ((c1 << 3) + 2 < bcost) bcost = (c1 << 3) + 2; }
+                    if (YOK(hex2[dir + 2].y)) { if ((c2 << 3) + 3 < bcost) bcost = (c2 << 3) + 3; }
+                    if (!(bcost & 7))
+                        break;
+                    dir += (bcost & 7) - 2;
+                    dir = mod6m1[dir + 1];
+                    bmv.x += hex2[dir + 1].x; bmv.y += hex2[dir + 1].y;
+                }
+            }
+        }
+        bcost >>= 3;
+    }
+    {   /* square refine, motion.cpp:950-967 */
+        int dir = 0;
+        int c0 = COSTAT(0, -1), c1 = COSTAT(0, 1), c2 = COSTAT(-1, 0), c3 = COSTAT(1, 0);
+        if (YOK(-1)) { if (c0 < bcost) { bcost = c0; dir = 1; } }
+        if (YOK(1))  { if (c1 < bcost) { bcost = c1; dir = 2; } }
+        if (c2 < bcost) { bcost = c2; dir = 3; }
+        if (c3 < bcost) { bcost = c3; dir = 4; }
+        c0 = COSTAT(-1, -1); c1 = COSTAT(-1, 1); c2 = COSTAT(1, -1); c3 = COSTAT(1, 1);
+        if (YOK(-1)) { if (c0 < bcost) { bcost = c0; dir = 5; } }
+        if (YOK(1))  { if (c1 < bcost) { bcost = c1; dir = 6; } }
+        if (YOK(-1)) { if (c2 < bcost) { bcost = c2; dir = 7; } }
+        if (YOK(1))  { if (c3 < bcost) { bcost = c3; dir = 8; } }
+        bmv.x += square1[dir].x; bmv.y += square1[dir].y;
+    }
+#undef YOK
+#undef COSTAT
+    if (bprecost < bcost) { bmv = bestpre; bcost = bprecost; }
+    else { bmv.x <<= 2; bmv.y <<= 2; }
+
+    if (!bcost)
+        bcost = mvcost_q(m, bmv.x, bmv.y);
+    else
+    {
+        int bdir = 0;
+        for (int i = 1; i <= 4; i++)
+        {
+            int qx = bmv.x + square1[i].x * 2, qy = bmv.y + square1[i].y * 2;
+            if ((qy < qmin.y) | (qy > qmax.y)) continue;
+            int cost = qpel_cost(m, qx, qy, 0) + mvcost_q(m, qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bmv.x += square1[bdir].x * 2; bmv.y += square1[bdir].y * 2;
+        bcost = qpel_cost(m, bmv.x, bmv.y, 1) + mvcost_q(m, bmv.x, bmv.y);
+        bdir = 0;
+        for (int i = 1; i <= 4; i++)
+        {
+            int qx = bmv.x + square1[i].x, qy = bmv.y + square1[i].y;
+            if ((qy < qmin.y) | (qy > qmax.y)) continue;
+            int cost = qpel_cost(m, qx, qy, 1) + mvcost_q(m, qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bmv.x += square1[bdir].x; bmv.y += square1[bdir].y;
+    }
+    *out = bmv;
+    return bcost;
+}
+
+/* search half of estimateCUCost over a whole frame (slicetype.cpp:4050-4059, 4103-4183) */
+void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
+                    const uint16_t* mvcost, int bBidir, int32_t* mvs, int32_t* mvCosts)
+{
+    or_me m;
+    m.g = g; m.stride = g->stride; m.mvcost = mvcost;
+    const int bw = g->bw, bh = g->bh;
+    for (int cuY = bh - 1; cuY >= 0; cuY--)
+    {
+        const int lastRow = cuY == bh - 1;
+        for (int cuX = bw - 1; cuX >= 0; cuX--)
+        {
+            const int cuXY = cuX + cuY * bw;
+            const int64_t pel = 8 * cuX + (int64_t)8 * cuY * g->stride;
+            for (int y = 0; y < 8; y++) memcpy(m.fenc + 8 * y, fencPlane0 + pel + (int64_t)y * g->stride, 8 * sizeof(or_pixel));
+            for (int i = 0; i < 4; i++) m.ref[i] = refPlanes[i] + pel;
+            or_mv mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
+            or_mv mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
+
+            or_mv mvc[4]; int numc = 0;
+#define MVC(idx) { mvc[numc].x = mvs[2 * (idx)]; mvc[numc].y = mvs[2 * (idx) + 1]; numc++; }
+            if (cuX < bw - 1) MVC(cuXY + 1);
+            if (!lastRow)
+            {
+                MVC(cuXY + bw);
+                if (cuX > 0) MVC(cuXY + bw - 1);
+                if (cuX < bw - 1) MVC(cuXY + bw + 1);
+            }
+#undef MVC
+            or_mv mvp = { 0, 0 };
+            int skipCost = 0x7fffffff;
+            if (numc)
+            {
+                int mvpcost = OR_COST_MAX;
+                or_pixel buf[64];
+                for (int i = 0; i < numc; i++)
+                {
+                    int st;
+                    const or_pixel* src = lowres_mc(&m, mvc[i].x, mvc[i].y, buf, &st);
+                    int cost = or_satd8x8(m.fenc, 8, src, st);
+                    if (cost < mvpcost) { mvpcost = cost; mvp = mvc[i]; }
+                    if (!(mvp.x | mvp.y) && bBidir)
+                        skipCost = cost;
+                }
+            }
+            or_mv best;
+            int fencCost = motion_estimate(&m, mvmin, mvmax, mvp, &best);
+            if (skipCost < 64 && skipCost < fencCost && bBidir)
+            {
+                fencCost = skipCost;
+                best.x = best.y = 0;
+            }
+            mvs[2 * cuXY] = best.x; mvs[2 * cuXY + 1] = best.y;
+            mvCosts[cuXY] = fencCost;
+        }
+    }
+}
+
+/* cost half of estimateCUCost + frame sums (slicetype.cpp:4187-4248) */
+void or_frame_cost(const or_geom* g, const or_pixel* fencPlane0,
+                   const or_pixel* const ref0Planes[4], const or_pixel* const ref1Planes[4],
+                   const int32_t* mvs0, const int32_t* mvCosts0,
+                   const int32_t* mvs1, const int32_t* mvCosts1,
+                   const int32_t* intraCost, const int32_t* invQ,
+                   uint16_t* lowresCosts, int32_t* rowSatds,
+                   int64_t* costEstOut, int64_t* costEstAqOut, int32_t* intraMbsOut)
+{
+    const int bw = g->bw, bh = g->bh, bBidir = ref1Planes != 0;
+    int64_t costEst = 0, costEstAq = 0; int intraMbs = 0;
+    or_me m0, m1;
+    m0.stride = m1.stride = g->stride;
+    for (int cuY = bh - 1; cuY >= 0; cuY--)
+    {
+        rowSatds[cuY] = 0;
+        for (int cuX = bw - 1; cuX >= 0; cuX--)
+        {
+            const int cuXY = cuX + cuY * bw;
+            const int64_t pel = 8 * cuX + (int64_t)8 * cuY * g->stride;
+            int bcost = OR_COST_MAX, listused = 0;
+            if (mvCosts0[cuXY] < bcost) { bcost = mvCosts0[cuXY]; listused = 1; }
+            if (bBidir)
+            {
+                if (mvCosts1[cuXY] < bcost) { bcost = mvCosts1[cuXY]; listused = 2; }
+                or_pixel fenc[64], b0[64], b1[64], avg[64];
+                for (int y = 0; y < 8; y++) memcpy(fenc + 8 * y, fencPlane0 + pel + (int64_t)y * g->stride, 8 * sizeof(or_pixel));
+                for (int i = 0; i < 4; i++) { m0.ref[i] = ref0Planes[i] + pel; m1.ref[i] = ref1Planes[i] + pel; }
+                int s0, s1;
+                const or_pixel* p0 = lowres_mc(&m0, mvs0[2 * cuXY], mvs0[2 * cuXY + 1], b0, &s0);
+                const or_pixel* p1 = lowres_mc(&m1, mvs1[2 * cuXY], mvs1[2 * cuXY + 1], b1, &s1);
+                for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) avg[y * 8 + x] = (or_pixel)((p0[y * s0 + x] + p1[y * s1 + x] + 1) >> 1);
+                int bicost = or_satd8x8(fenc, 8, avg, 8);
+                if (bicost < bcost) { bcost = bicost; listused = 3; }
+                p0 = m0.ref[0]; p1 = m1.ref[0];
+                for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) avg[y * 8 + x] = (or_pixel)((p0[(int64_t)y * g->stride + x] + p1[(int64_t)y * g->stride + x] + 1) >> 1);
+                bicost = or_satd8x8(fenc, 8, avg, 8);
+                if (bicost < bcost) { bcost = bicost; listused = 3; }
+                bcost += 4;
+            }
+            else
+            {
+                bcost += 4;
+                if (intraCost[cuXY] < bcost) { bcost = intraCost[cuXY]; listused = 0; }
+            }
+            int scored = (cuX > 0 && cuX < bw - 1 && cuY > 0 && cuY < bh - 1) || bw <= 2 || bh <= 2;
+            int bcostAq = (scored && invQ) ? ((bcost * invQ[cuXY] + 128) >> 8) : bcost;
+            if (scored)
+            {
+                costEst += bcost; costEstAq += bcostAq;
+                if (!listused && !bBidir) intraMbs++;
+            }
+            rowSatds[cuY] += bcostAq;
+            lowresCosts[cuXY] = (uint16_t)(imin(bcost, OR_LOWRES_COST_MASK) | (listused << OR_LOWRES_COST_SHIFT));
+        }
+    }
+    *costEstOut = costEst; *costEstAqOut = costEstAq; *intraMbsOut = intraMbs;
+}
+
+/* ------------------------------------------------------------------ weighted prediction */
+
+/* weight_pp_c over whole padded planes (pixel.cpp:518-541, slicetype.cpp:833-842,966-976) */
+void or_weight_planes(const or_geom* g, const or_pixel* refBuf, or_pixel* dstBuf, int nPlanes,
+                      int scale, int denom, int offsetIn)
+{
+    const int correction = 14 - OR_DEPTH;
+    const int offset = offsetIn << (OR_DEPTH - 8);
+    const int round = (denom ? 1 << (denom - 1) : 0) << correction;
+    const int shift = denom + correction;
+    const int64_t n = g->planeSize * nPlanes;
+    for (int64_t i = 0; i < n; i++)
+    {
+        int16_t val = (int16_t)(refBuf[i] << correction);
+        int v = ((scale * val + round) >> shift) + offset;
+        dstBuf[i] = (or_pixel)(v < 0 ? 0 : (v > OR_MAXV ? OR_MAXV : v));
+    }
+}
+
+/* slicetype.cpp:845-858 */
+uint32_t or_weight_cost_luma(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* refPlane0,
+                             const int32_t* intraCost)
+{
+    uint32_t cost = 0; int mb = 0;
+    for (int y = 0; y < g->h; y += 8)
+        for (int x = 0; x < g->w; x += 8, mb++)
+        {
+            int64_t off = (int64_t)y * g->stride + x;
+            int satd = or_satd8x8(refPlane0 + off, g->stride, fencPlane0 + off, g->stride);
+            cost += (uint32_t)imin(satd, intraCost[mb]);
+        }
+    return cost;
+}
+
+/* slicetype.cpp:879-980 */
+int or_weights_analyse(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* refBuf,
+                       const int32_t* intraCost, const uint64_t fenc_ssd, const uint64_t fenc_sum,
+                       const uint64_t ref_ssd, const uint64_t ref_sum,
+                       or_pixel* wbuf, int* scaleOut, int* denomOut, int* offsetOut, double* costDelta)
+{
+    const float epsilon = 1.f / 128.f;
+    float guessScale, fencMean, refMean;
+    if (fenc_ssd && ref_ssd) guessScale = sqrtf((float)fenc_ssd / ref_ssd);
+    else guessScale = 1.0f;
+    fencMean = (float)fenc_sum / (g->h * g->w) / (1 << (OR_DEPTH - 8));
+    refMean = (float)ref_sum / (g->h * g->w) / (1 << (OR_DEPTH - 8));
+    if (fabsf(refMean - fencMean) < 0.5f && fabsf(1.f - guessScale) < epsilon)
+        return 0;
+
+    int minoff = 0, minscale, mindenom, found = 0;
+    unsigned int minscore, origscore;
+    {   /* WeightParam::setFromWeightAndOffset(w, 0, 7, true) (common/slice.h:304-316) */
+        int w = (int)(guessScale * 128 + 0.5f), d = 7;
+        while (d > 0 && w > 127) { d--; w >>= 1; }
+        w = imin(w, 127);
+        mindenom = d; minscale = w;
+    }
+    const or_pixel* refPlane0 = refBuf + g->padOffset;
+    origscore = minscore = or_weight_cost_luma(g, fencPlane0, refPlane0, intraCost);
+    if (!minscore)
+        return 0;
+    int curScale = minscale;
+    int curOffset = (int)(fencMean - refMean * curScale / (1 << mindenom) + 0.5f);
+    if (curOffset < -128 || curOffset > 127)
+    {
+        curOffset = imax(-128, imin(127, curOffset));
+        curScale = (int)((1 << mindenom) * (fencMean - curOffset) / refMean + 0.5f);
+        curScale = imax(0, imin(127, curScale));
+    }
+    or_weight_planes(g, refBuf, wbuf, 1, curScale, mindenom, curOffset);
+    unsigned int s = or_weight_cost_luma(g, fencPlane0, wbuf + g->padOffset, intraCost);
+    if (s < minscore) { minscore = s; minscale = curScale; minoff = curOffset; found = 1; }
+    if (mindenom > 0 && !(minscale & 1))
+    {
+        int idx = 0;
+        while (!((minscale >> idx) & 1)) idx++;      /* CTZ */
+        int shift = imin(idx, mindenom);
+        mindenom -= shift;
+        minscale >>= shift;
+    }
+    if (!found || (minscale == (1 << mindenom) && minoff == 0) || (float)minscore / origscore > 0.998f)
+        return 0;
+    *costDelta = (double)(minscore / origscore);     /* integer division, as the reference (slicetype.cpp:964) */
+    or_weight_planes(g, refBuf, wbuf, 4, minscale, mindenom, minoff);
+    *scaleOut = minscale; *denomOut = mindenom; *offsetOut = minoff;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ cuTree */
+
+static inline void clip_add(uint16_t* s, int x)
+{
+    int v = *s + x;
+    *s = (uint16_t)(v < 65535 ? v : 65535);
+}
+
+/* slicetype.cpp:3502-3604 + pixel.cpp:931-957 */
+void or_cutree_propagate(const or_geom* g, const int32_t* intraCost, const uint16_t* lowresCosts,
+                         const int32_t* invQ, const int32_t* mvs0, const int32_t* mvs1,
+                         uint16_t* propagateB, uint16_t* refCost0, uint16_t* refCost1,
+                         int referenced, int bipredWeight, double fpsFactor)
+{
+    const int bw = g->bw, bh = g->bh;
+    uint16_t* refCosts[2] = { refCost0, refCost1 };
+    const int32_t* mvsL[2] = { mvs0, mvs1 };
+    const int bipredWeights[2] = { bipredWeight, 64 - bipredWeight };
+    if (!referenced)
+        memset(propagateB, 0, bw * sizeof(uint16_t));
+    const uint16_t* propIn = propagateB;
+    const double fps = fpsFactor / 256;
+    for (int by = 0; by < bh; by++)
+    {
+        for (int bx = 0; bx < bw; bx++)
+        {
+            const int cu = by * bw + bx;
+            int intra = intraCost[cu];
+            int inter = imin(intraCost[cu], lowresCosts[cu] & OR_LOWRES_COST_MASK);
+            double propagateIntra = intra * (invQ ? invQ[cu] : 256);
+            double propagateAmount = (double)propIn[bx] + propagateIntra * fps;
+            double propagateNum = (double)(intra - inter);
+            double propagateDenom = (double)intra;
+            int amount = (int)(propagateAmount * propagateNum / propagateDenom + 0.5);
+            if (amount <= 0) continue;
+            int lists_used = lowresCosts[cu] >> OR_LOWRES_COST_SHIFT;
+            for (int list = 0; list < 2; list++)
+            {
+                if (!((lists_used >> list) & 1)) continue;
+                int listamount = amount;
+                if (lists_used == 3)
+                    listamount = (listamount * bipredWeights[list] + 32) >> 6;
+                int x = mvsL[list][2 * cu], y = mvsL[list][2 * cu + 1];
+                if (!x && !y) { clip_add(&refCosts[list][cu], listamount); continue; }
+                int cux = (x >> 5) + bx, cuy = (y >> 5) + by;
+                int idx0 = cux + cuy * bw, idx1 = idx0 + 1, idx2 = idx0 + bw, idx3 = idx0 + bw + 1;
+                x &= 31; y &= 31;
+                int w0 = (32 - y) * (32 - x), w1 = (32 - y) * x, w2 = y * (32 - x), w3 = y * x;
+                if (cux < bw - 1 && cuy < bh - 1 && cux >= 0 && cuy >= 0)
+                {
+                    clip_add(&refCosts[list][idx0], (listamount * w0 + 512) >> 10);
+                    clip_add(&refCosts[list][idx1], (listamount * w1 + 512) >> 10);
+                    clip_add(&refCosts[list][idx2], (listamount * w2 + 512) >> 10);
+                    clip_add(&refCosts[list][idx3], (listamount * w3 + 512) >> 10);
+                }
+                else
+                {
+                    if (cux < bw && cuy < bh && cux >= 0 && cuy >= 0)
+                        clip_add(&refCosts[list][idx0], (listamount * w0 + 512) >> 10);
+                    if (cux + 1 < bw && cuy < bh && cux + 1 >= 0 && cuy >= 0)
+                        clip_add(&refCosts[list][idx1], (listamount * w1 + 512) >> 10);
+                    if (cux < bw && cuy + 1 < bh && cux >= 0 && cuy + 1 >= 0)
+                        clip_add(&refCosts[list][idx2], (listamount * w2 + 512) >> 10);
+                    if (cux + 1 < bw && cuy + 1 < bh && cux + 1 >= 0 && cuy + 1 >= 0)
+                        clip_add(&refCosts[list][idx3], (listamount * w3 + 512) >> 10);
+                }
+            }
+        }
+        if (referenced)
+            propIn += bw;
+    }
+}
+
+/* slicetype.cpp:3784-3796 */
+void or_cutree_finish(const or_geom* g, const int32_t* intraCost, const int32_t* invQ,
+                      const uint16_t* propagateCost, const double* qpAqOffset, double* qpCuTreeOffset,
+                      int fpsFactorFix8, double weightdelta, double cuTreeStrength)
+{
+    for (int i = 0; i < g->ncu; i++)
+    {
+        int intracost = (intraCost[i] * invQ[i] + 128) >> 8;
+        if (intracost)
+        {
+            int propagate = (propagateCost[i] * fpsFactorFix8 + 128) >> 8;
+            double log2_ratio = log2((double)(intracost + propagate)) - log2((double)intracost) + weightdelta;
+            qpCuTreeOffset[i] = qpAqOffset[i] - cuTreeStrength * log2_ratio;
+        }
+    }
+}
+
+/* slicetype.cpp:3847-3878 */
+int64_t or_frame_cost_recalc(const or_geom* g, const uint16_t* lowresCosts, const double* qpOffset, int32_t* rowSatds)
+{
+    int64_t score = 0;
+    for (int cuy = g->bh - 1; cuy >= 0; cuy--)
+    {
+        rowSatds[cuy] = 0;
+        for (int cux = g->bw - 1; cux >= 0; cux--)
+        {
+            int cu = cux + cuy * g->bw;
+            int cuCost = lowresCosts[cu] & OR_LOWRES_COST_MASK;
+            cuCost = (cuCost * or_exp2fix8(qpOffset[cu]) + 128) >> 8;
+            rowSatds[cuy] += cuCost;
+            if ((cuy > 0 && cuy < g->bh - 1 && cux > 0 && cux < g->bw - 1) || g->bw <= 2 || g->bh <= 2)
+                score += cuCost;
+        }
+    }
+    return score;
+}

@@ -1,0 +1,123 @@
+/* la_oracle.h -- CPU restatement of the reference lookahead's block-level arithmetic.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (x265-amod_b200/) may include,
+ * link or call this.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+ * leg use it, and only as the checker.
+ *
+ * Parity status: PINNED.  Every function here is checked bit-for-bit against the
+ * unmodified reference compiled from /root/reference (oracle/_ref, see Makefile.ref and
+ * ref_harness.cpp) by tests/test_oracle_vs_ref.py, and against the committed golden
+ * vectors under tests/golden/ (generated from that reference build by
+ * tests/golden/make_golden.py) when the reference build is absent.
+ *
+ * Plain C99, scalar, written for clarity.  Compiled twice: -DOR_DEPTH=8 (pixel =
+ * uint8_t) and -DOR_DEPTH=10 (pixel = uint16_t).  Citations are file:line under
+ * /root/reference/source/. */
+#ifndef LA_ORACLE_H
+#define LA_ORACLE_H
+#include <stdint.h>
+
+#ifndef OR_DEPTH
+#define OR_DEPTH 8
+#endif
+#if OR_DEPTH == 8
+typedef uint8_t or_pixel;
+#else
+typedef uint16_t or_pixel;
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Lowres geometry (common/lowres.cpp:72-97, common/picyuv.cpp:84-99) */
+typedef struct
+{
+    int32_t picW, picH;     /* full-res luma size handed to the lookahead */
+    int32_t w, h;           /* lowres plane size, rounded up to 8 */
+    int32_t bw, bh, ncu;    /* 8x8 block grid */
+    int32_t mx, my;         /* plane margins */
+    int32_t stride;         /* plane stride in pixels */
+    int32_t planeLines;     /* h + 2*my */
+    int64_t planeSize;      /* stride * planeLines */
+    int64_t padOffset;      /* my*stride + mx */
+} or_geom;
+
+int  or_depth(void);
+void or_geom_init(or_geom* g, int picW, int picH, int maxCUSize);
+
+/* lambda and mv-cost table of the lookahead (encoder/bitcost.cpp:30-54,98-113) */
+int  or_lookahead_lambda(void);
+void or_build_mvcost(uint16_t* table /* [2*half+1], centre at half */, int half);
+
+int  or_exp2fix8(double x);                 /* common/common.cpp:96-103 */
+int  or_sad8x8(const or_pixel* a, int sa, const or_pixel* b, int sb);   /* pixel.cpp:40-56 */
+int  or_satd8x8(const or_pixel* a, int sa, const or_pixel* b, int sb);  /* pixel.cpp:239-297 */
+
+/* Lowres::init pixel work: downscale + 4 hpel planes + border extension
+ * (common/lowres.cpp:367-376, pixel.cpp:605-628,1044-1058).  `buf` is 4*planeSize pixels,
+ * zero-initialised by the caller; the source is addressed with replicate clamping, which is
+ * what PicYuv::copyFromPicture's padding (picyuv.cpp:261-285,480-512) amounts to. */
+void or_lowres_init(const or_geom* g, const or_pixel* srcY, int srcStride, or_pixel* buf);
+
+/* calcAdaptiveQuantFrame for qg-size > 8 (16x16 luma blocks), aq-mode 0..3
+ * (encoder/slicetype.cpp:452-713).  Chroma may be NULL (treated as 4:0:0). */
+void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v,
+                 int strideC, int aqMode, double aqStrength, int bWeightP,
+                 double* qpAqOffset, double* qpCuTreeOffset, int32_t* invQscaleFactor,
+                 uint32_t* blockEnergy /* ncu or NULL */, uint64_t wp_ssd[3], uint64_t wp_sum[3]);
+
+/* lowresIntraEstimate (encoder/slicetype.cpp:715-824) */
+void or_intra_estimate(const or_geom* g, const or_pixel* plane0 /* lowresPlane[0] */,
+                       const int32_t* invQscaleFactor /* may be NULL */,
+                       int32_t* intraCost, uint8_t* intraMode, uint16_t* lowresCosts00,
+                       int32_t* rowSatds00, int64_t* costEst00, int64_t* costEstAq00);
+
+/* One list's motion search over the whole frame, reverse raster order, exactly the search
+ * half of CostEstimateGroup::estimateCUCost (slicetype.cpp:4114-4183) + MotionEstimate::
+ * motionEstimate (motion.cpp:764-1594, HEX + lowres subpel).  refPlanes[4] point at
+ * lowresPlane[0..3] of the (possibly weighted) reference.  bBidir selects the B-frame
+ * zero-MV skip rule (slicetype.cpp:4165-4181).  rowsPerSlice <= 0 means no slices. */
+void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
+                    const uint16_t* mvcost /* centre */, int bBidir,
+                    int32_t* mvs /* ncu*2 */, int32_t* mvCosts /* ncu */);
+
+/* Cost half of estimateCUCost + the sums of estimateFrameCost (slicetype.cpp:4187-4248,
+ * 4050-4067).  For a P estimate pass ref1Planes = NULL. */
+void or_frame_cost(const or_geom* g, const or_pixel* fencPlane0,
+                   const or_pixel* const ref0Planes[4], const or_pixel* const ref1Planes[4],
+                   const int32_t* mvs0, const int32_t* mvCosts0,
+                   const int32_t* mvs1, const int32_t* mvCosts1,
+                   const int32_t* intraCost, const int32_t* invQscaleFactor /* may be NULL */,
+                   uint16_t* lowresCosts, int32_t* rowSatds,
+                   int64_t* costEst, int64_t* costEstAq, int32_t* intraMbs);
+
+/* weightCostLuma / weight_pp_c (slicetype.cpp:826-859, pixel.cpp:518-541) */
+void or_weight_planes(const or_geom* g, const or_pixel* refBuf, or_pixel* dstBuf, int nPlanes,
+                      int scale, int denom, int offset);
+uint32_t or_weight_cost_luma(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* refPlane0,
+                             const int32_t* intraCost);
+/* weightsAnalyse (slicetype.cpp:879-980): returns 1 and fills (scale,denom,offset,costDelta)
+ * when a weight is accepted; wbuf is 4*planeSize scratch that receives the weighted planes. */
+int or_weights_analyse(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* refBuf,
+                       const int32_t* intraCost, const uint64_t fenc_wp_ssd0, const uint64_t fenc_wp_sum0,
+                       const uint64_t ref_wp_ssd0, const uint64_t ref_wp_sum0,
+                       or_pixel* wbuf, int* scale, int* denom, int* offset, double* costDelta);
+
+/* estimateCUPropagate for one (p0,p1,b) (slicetype.cpp:3502-3604 + pixel.cpp:931-957) */
+void or_cutree_propagate(const or_geom* g, const int32_t* intraCost, const uint16_t* lowresCosts,
+                         const int32_t* invQscaleFactor, const int32_t* mvs0, const int32_t* mvs1,
+                         uint16_t* propagateB, uint16_t* refCost0, uint16_t* refCost1,
+                         int referenced, int bipredWeight, double fpsFactor);
+/* cuTreeFinish (slicetype.cpp:3750-3798, qg-size > 8 branch) */
+void or_cutree_finish(const or_geom* g, const int32_t* intraCost, const int32_t* invQscaleFactor,
+                      const uint16_t* propagateCost, const double* qpAqOffset, double* qpCuTreeOffset,
+                      int fpsFactorFix8, double weightdelta, double cuTreeStrength);
+/* frameCostRecalculate (slicetype.cpp:3802-3879, non-hevc-aq branch) */
+int64_t or_frame_cost_recalc(const or_geom* g, const uint16_t* lowresCosts, const double* qpOffset,
+                             int32_t* rowSatds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,80 @@
+"""Field-by-field comparison of decided-frame dicts (oracle/refbind.py layout)."""
+import numpy as np
+
+EXACT_SCALARS = ["poc", "sliceType", "bScenecut", "bKeyframe", "bLastMiniGopBFrame", "leadingBframes"]
+
+
+def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutree=True, label=""):
+    """ref: dict from the reference harness; got: dict from our Lookahead.  Returns list of
+    mismatch strings (empty = parity)."""
+    bad = []
+    tag = "%sframe poc=%d: " % (label, ref["poc"])
+    for k in EXACT_SCALARS:
+        if int(ref[k]) != int(got[k]):
+            bad.append(tag + "%s ref=%s got=%s" % (k, ref[k], got[k]))
+    if bad:
+        return bad
+    nb = ref["nb"]
+    if not np.array_equal(ref["costEst"], got["costEst"]):
+        bad.append(tag + "costEst\nref=%s\ngot=%s" % (ref["costEst"], got["costEst"]))
+    if not np.array_equal(ref["costEstAq"], got["costEstAq"]):
+        bad.append(tag + "costEstAq\nref=%s\ngot=%s" % (ref["costEstAq"], got["costEstAq"]))
+    if not np.array_equal(ref["intraMbs"], got["intraMbs"]):
+        bad.append(tag + "intraMbs ref=%s got=%s" % (ref["intraMbs"], got["intraMbs"]))
+    for k in ("intraCost", "intraMode", "invQscaleFactor"):
+        if not np.array_equal(ref[k], got[k]):
+            n = int(np.sum(ref[k] != got[k]))
+            bad.append(tag + "%s differs in %d blocks" % (k, n))
+    for k in ("qpAqOffset", "qpCuTreeOffset"):
+        d = np.max(np.abs(ref[k] - got[k])) if len(ref[k]) else 0.0
+        if not d <= qp_tol:
+            bad.append(tag + "%s max|delta|=%g" % (k, d))
+    # propagateCost is only defined for I/P frames: the reference never initialises it for B frames, and
+    # for B-refs cuTree resets frames[curnonb + (bframes+1)/2] (slicetype.cpp:3460) while placeBref marks
+    # list[bframes/2] (:1757), which are different frames for even mini-GOP sizes.
+    if cutree and ref["sliceType"] in (1, 2, 3) and not np.array_equal(ref["propagateCost"], got["propagateCost"]):
+        n = int(np.sum(ref["propagateCost"] != got["propagateCost"]))
+        bad.append(tag + "propagateCost differs in %d blocks" % n)
+    if weightp:
+        if not np.array_equal(ref["wp_ssd"], got["wp_ssd"]) or not np.array_equal(ref["wp_sum"], got["wp_sum"]):
+            bad.append(tag + "wp stats ref=%s/%s got=%s/%s" % (ref["wp_ssd"], ref["wp_sum"], got["wp_ssd"], got["wp_sum"]))
+    for l in range(2):
+        for d in range(nb):
+            ref_searched = ref["mvs"][l, d, 0, 0] != 0x7FFF
+            if bool(ref_searched) != bool(got["searched"][l, d]):
+                bad.append(tag + "mv sentinel list=%d dist=%d ref_searched=%s got=%s" % (l, d, ref_searched, got["searched"][l, d]))
+                continue
+            if ref_searched:
+                if not np.array_equal(ref["mvs"][l, d], got["mvs"][l, d]):
+                    n = int(np.sum(np.any(ref["mvs"][l, d] != got["mvs"][l, d], axis=1)))
+                    bad.append(tag + "lowresMvs[%d][%d] differ in %d blocks" % (l, d, n))
+                if not np.array_equal(ref["mvCosts"][l, d], got["mvCosts"][l, d]):
+                    n = int(np.sum(ref["mvCosts"][l, d] != got["mvCosts"][l, d]))
+                    bad.append(tag + "lowresMvCosts[%d][%d] differ in %d blocks" % (l, d, n))
+    for i in range(nb):
+        for j in range(nb):
+            ref_done = ref["rowSatds"][i, j, 0] != -1 and ref["costEst"][i, j] >= 0
+            if not ref_done:
+                continue
+            if not np.array_equal(ref["lowresCosts"][i, j], got["lowresCosts"][i, j]):
+                n = int(np.sum(ref["lowresCosts"][i, j] != got["lowresCosts"][i, j]))
+                bad.append(tag + "lowresCosts[%d][%d] differ in %d blocks" % (i, j, n))
+            # non-B frames' rowSatds of the coded estimate are rewritten by frameCostRecalculate
+            if not np.array_equal(ref["rowSatds"][i, j], got["rowSatds"][i, j]):
+                bad.append(tag + "rowSatds[%d][%d] differ" % (i, j))
+    if check_planes and "planes" in ref and "planes" in got:
+        if not np.array_equal(ref["planes"], got["planes"]):
+            n = int(np.sum(ref["planes"] != got["planes"]))
+            bad.append(tag + "lowres planes differ in %d samples" % n)
+    return bad
+
+
+def compare_runs(ref_frames, got_frames, **kw):
+    bad = []
+    if len(ref_frames) != len(got_frames):
+        bad.append("frame count ref=%d got=%d" % (len(ref_frames), len(got_frames)))
+    for r, g in zip(ref_frames, got_frames):
+        bad += compare_frames(r, g, **kw)
+        if len(bad) > 20:
+            break
+    return bad

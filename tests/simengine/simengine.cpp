@@ -1,0 +1,264 @@
+/* simengine.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Implements the engine C ABI (include/x265cu.h) on the CPU with the oracle's block-level
+ * functions (oracle/la_oracle.c), so that the PRODUCT's host decision logic
+ * (x265-amod_b200/host/lookahead.cpp) can be exercised against the real reference on machines
+ * without a GPU.  It is linked only into tests/_build/libx265la_sim{8,10}.so by tests/build_sim.py;
+ * the shipped libraries (libx265cu.so, libx265la.so) never contain or load it, and the shipped
+ * engine has no CPU path at all.  Results produced through this file prove nothing about the
+ * CUDA kernels -- those are checked by the `-m gpu` tests.
+ */
+#include "x265cu.h"
+#include "la_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+struct SimSlot
+{
+    std::vector<or_pixel> y, u, v;
+    std::vector<or_pixel> planes;
+    std::vector<int32_t> intraCost, invQ, rowSatds00;
+    std::vector<uint8_t> intraMode;
+    std::vector<uint16_t> lowresCosts00, propagate;
+    std::vector<double> qpAq, qpCuTree;
+    std::vector<std::vector<int32_t> > mvs, mvCosts;          /* per MV store */
+    std::vector<std::vector<uint16_t> > costs;                /* per cost store */
+    std::vector<std::vector<int32_t> > rowSatds;
+    std::vector<x265cu_cost_result> results;
+    x265cu_frame_stats stats;
+};
+
+struct x265cu_ctx
+{
+    x265cu_config cfg;
+    or_geom g;
+    x265cu_geometry geom;
+    std::vector<uint16_t> mvcost;
+    std::vector<SimSlot> slots;
+    std::vector<or_pixel> wbuf;
+    x265cu_counters counters;
+    char err[64];
+};
+
+extern "C" {
+
+int x265cu_device_count(void) { return 0; }
+const char* x265cu_strerror(int s) { return s == 0 ? "ok" : "simengine error"; }
+const char* x265cu_last_error(const x265cu_ctx*) { return ""; }
+
+int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
+{
+    if (cfg->depth != or_depth()) return X265CU_ERR_BAD_ARG;
+    if (cfg->qg_size < 16) return X265CU_ERR_UNSUPPORTED;
+    x265cu_ctx* c = new x265cu_ctx;
+    c->cfg = *cfg;
+    or_geom_init(&c->g, cfg->width, cfg->height, cfg->max_cu_size);
+    c->mvcost.assign(cfg->mvcost, cfg->mvcost + 2 * (size_t)cfg->mvcost_half + 1);
+    memset(&c->geom, 0, sizeof(c->geom));
+    c->geom.low_width = c->g.w; c->geom.low_height = c->g.h; c->geom.bw = c->g.bw; c->geom.bh = c->g.bh;
+    c->geom.ncu = c->g.ncu; c->geom.stride = c->g.stride; c->geom.plane_lines = c->g.planeLines;
+    c->geom.margin_x = c->g.mx; c->geom.margin_y = c->g.my; c->geom.nb = cfg->bframes + 2;
+    c->geom.n_mv_stores = 3 * c->geom.nb; c->geom.n_cost_stores = 2 * c->geom.nb * c->geom.nb;
+    c->slots.resize(cfg->max_slots);
+    memset(&c->counters, 0, sizeof(c->counters));
+    *out = c;
+    return 0;
+}
+
+void x265cu_destroy(x265cu_ctx* c) { delete c; }
+int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* g) { *g = c->geom; return 0; }
+int x265cu_pin_host(x265cu_ctx*, void*, uint64_t) { return 0; }
+int x265cu_unpin_host(x265cu_ctx*, void*) { return 0; }
+int x265cu_sync(x265cu_ctx*) { return 0; }
+int x265cu_get_counters(const x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return 0; }
+int x265cu_profile_enable(x265cu_ctx*, int32_t) { return 0; }
+int x265cu_profile_get(x265cu_ctx*, double* ms, uint64_t* n, int32_t) { for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = 0; n[i] = 0; } return 0; }
+
+int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* u, const void* v, int32_t sy, int32_t sc)
+{
+    SimSlot& s = c->slots[slot];
+    const or_geom& g = c->g;
+    const int W = g.picW, H = g.picH, CW = (W + 1) / 2, CH = (H + 1) / 2;
+    s.y.resize((size_t)W * H);
+    for (int r = 0; r < H; r++) memcpy(&s.y[(size_t)r * W], (const or_pixel*)y + (size_t)r * sy, W * sizeof(or_pixel));
+    if (u && v)
+    {
+        s.u.resize((size_t)CW * CH); s.v.resize((size_t)CW * CH);
+        for (int r = 0; r < CH; r++)
+        {
+            memcpy(&s.u[(size_t)r * CW], (const or_pixel*)u + (size_t)r * sc, CW * sizeof(or_pixel));
+            memcpy(&s.v[(size_t)r * CW], (const or_pixel*)v + (size_t)r * sc, CW * sizeof(or_pixel));
+        }
+    }
+    else { s.u.clear(); s.v.clear(); }
+    s.planes.assign((size_t)(4 * g.planeSize), 0);
+    or_lowres_init(&g, &s.y[0], W, &s.planes[0]);
+    const int ncu = g.ncu, nb = c->geom.nb;
+    s.intraCost.assign(ncu, 0); s.invQ.assign(ncu, 256); s.intraMode.assign(ncu, 0);
+    s.lowresCosts00.assign(ncu, 0); s.rowSatds00.assign(g.bh, 0); s.propagate.assign(ncu, 0);
+    s.qpAq.assign(ncu, 0.0); s.qpCuTree.assign(ncu, 0.0);
+    s.mvs.assign(3 * nb, std::vector<int32_t>()); s.mvCosts.assign(3 * nb, std::vector<int32_t>());
+    s.costs.assign(2 * nb * nb, std::vector<uint16_t>()); s.rowSatds.assign(2 * nb * nb, std::vector<int32_t>());
+    s.results.assign(2 * nb * nb, x265cu_cost_result());
+    memset(&s.stats, 0, sizeof(s.stats));
+    if (c->cfg.need_aq)
+        or_aq_frame(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW,
+                    c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats, &s.qpAq[0], &s.qpCuTree[0], &s.invQ[0],
+                    NULL, s.stats.wp_ssd, s.stats.wp_sum);
+    or_intra_estimate(&g, &s.planes[g.padOffset], c->cfg.need_aq ? &s.invQ[0] : NULL, &s.intraCost[0], &s.intraMode[0],
+                      &s.lowresCosts00[0], &s.rowSatds00[0], &s.stats.cost_est, &s.stats.cost_est_aq);
+    c->counters.h2d_bytes += (uint64_t)W * H * sizeof(or_pixel) * 3 / 2;
+    return 0;
+}
+
+int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)
+{
+    for (int i = 0; i < n; i++) out[i] = c->slots[slots[i]].stats;
+    return 0;
+}
+
+static void planePtrs(const x265cu_ctx* c, const std::vector<or_pixel>& buf, const or_pixel* p[4])
+{
+    for (int i = 0; i < 4; i++) p[i] = &buf[(size_t)(i * c->g.planeSize + c->g.padOffset)];
+}
+
+int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
+{
+    const or_geom& g = c->g;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_search_job& j = jobs[i];
+        SimSlot& f = c->slots[j.fenc_slot]; SimSlot& r = c->slots[j.ref_slot];
+        const or_pixel* rp[4];
+        if (j.weighted)
+        {
+            c->wbuf.resize((size_t)(4 * g.planeSize));
+            or_weight_planes(&g, &r.planes[0], &c->wbuf[0], 4, j.w_scale, j.w_denom, j.w_offset);
+            planePtrs(c, c->wbuf, rp);
+        }
+        else
+            planePtrs(c, r.planes, rp);
+        f.mvs[j.store].assign(2 * g.ncu, 0); f.mvCosts[j.store].assign(g.ncu, 0);
+        or_search_list(&g, &f.planes[g.padOffset], rp, &c->mvcost[c->cfg.mvcost_half], j.bidir_ctx,
+                       &f.mvs[j.store][0], &f.mvCosts[j.store][0]);
+        c->counters.kernel_launches++;
+    }
+    return 0;
+}
+
+int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
+{
+    const or_geom& g = c->g;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_cost_job& j = jobs[i];
+        SimSlot& b = c->slots[j.b_slot]; SimSlot& p0 = c->slots[j.p0_slot]; SimSlot& p1 = c->slots[j.p1_slot];
+        const or_pixel *r0[4], *r1[4];
+        planePtrs(c, p0.planes, r0); planePtrs(c, p1.planes, r1);
+        const bool bidir = j.l1_store >= 0;
+        b.costs[j.out].assign(g.ncu, 0); b.rowSatds[j.out].assign(g.bh, 0);
+        x265cu_cost_result& res = b.results[j.out];
+        or_frame_cost(&g, &b.planes[g.padOffset], r0, bidir ? r1 : NULL,
+                      &b.mvs[j.l0_store][0], &b.mvCosts[j.l0_store][0],
+                      bidir ? &b.mvs[j.l1_store][0] : NULL, bidir ? &b.mvCosts[j.l1_store][0] : NULL,
+                      &b.intraCost[0], c->cfg.need_aq ? &b.invQ[0] : NULL, &b.costs[j.out][0], &b.rowSatds[j.out][0],
+                      &res.cost_est, &res.cost_est_aq, &res.intra_mbs);
+        c->counters.kernel_launches++;
+    }
+    return 0;
+}
+
+int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* outs, int32_t n, x265cu_cost_result* res)
+{
+    for (int i = 0; i < n; i++) res[i] = c->slots[slots[i]].results[outs[i]];
+    return 0;
+}
+
+int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_t n, uint32_t* costs)
+{
+    const or_geom& g = c->g;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_wcost_job& j = jobs[i];
+        SimSlot& f = c->slots[j.fenc_slot]; SimSlot& r = c->slots[j.ref_slot];
+        const or_pixel* ref0 = &r.planes[g.padOffset];
+        if (j.weighted)
+        {
+            c->wbuf.resize((size_t)(4 * g.planeSize));
+            or_weight_planes(&g, &r.planes[0], &c->wbuf[0], 1, j.w_scale, j.w_denom, j.w_offset);
+            ref0 = &c->wbuf[g.padOffset];
+        }
+        costs[i] = or_weight_cost_luma(&g, &f.planes[g.padOffset], ref0, &f.intraCost[0]);
+    }
+    return 0;
+}
+
+int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
+{
+    std::fill(c->slots[slot].propagate.begin(), c->slots[slot].propagate.end(), 0);
+    return 0;
+}
+
+int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s, int32_t cost_store, int32_t l0, int32_t l1,
+                            int32_t referenced, int32_t bipred_weight, double fps_factor)
+{
+    SimSlot& b = c->slots[bs];
+    or_cutree_propagate(&c->g, &b.intraCost[0], &b.costs[cost_store][0], &b.invQ[0], &b.mvs[l0][0],
+                        l1 >= 0 ? &b.mvs[l1][0] : &b.mvs[l0][0], &b.propagate[0],
+                        &c->slots[p0s].propagate[0], &c->slots[p1s].propagate[0], referenced, bipred_weight, fps_factor);
+    return 0;
+}
+
+int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double weightdelta, double strength)
+{
+    SimSlot& s = c->slots[slot];
+    or_cutree_finish(&c->g, &s.intraCost[0], &s.invQ[0], &s.propagate[0], &s.qpAq[0], &s.qpCuTree[0], fps_fix8, weightdelta, strength);
+    return 0;
+}
+
+int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree, int64_t* score, int32_t* rows)
+{
+    SimSlot& s = c->slots[slot];
+    std::vector<uint16_t>& costs = cost_store == 0 ? s.lowresCosts00 : s.costs[cost_store];
+    std::vector<int32_t>& rs = cost_store == 0 ? s.rowSatds00 : s.rowSatds[cost_store];
+    *score = or_frame_cost_recalc(&c->g, &costs[0], use_cutree ? &s.qpCuTree[0] : &s.qpAq[0], &rs[0]);
+    if (rows) memcpy(rows, &rs[0], c->g.bh * sizeof(int32_t));
+    return 0;
+}
+
+int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
+{
+    SimSlot& s = c->slots[slot];
+    const int ncu = c->g.ncu;
+    if (o->intra_cost) memcpy(o->intra_cost, &s.intraCost[0], ncu * 4);
+    if (o->intra_mode) memcpy(o->intra_mode, &s.intraMode[0], ncu);
+    if (o->qp_aq_offset) memcpy(o->qp_aq_offset, &s.qpAq[0], ncu * 8);
+    if (o->qp_cutree_offset) memcpy(o->qp_cutree_offset, &s.qpCuTree[0], ncu * 8);
+    if (o->inv_qscale_factor) memcpy(o->inv_qscale_factor, &s.invQ[0], ncu * 4);
+    if (o->propagate_cost) memcpy(o->propagate_cost, &s.propagate[0], ncu * 2);
+    if (o->planes) memcpy(o->planes, &s.planes[0], (size_t)(4 * c->g.planeSize) * sizeof(or_pixel));
+    if (o->lowres_costs00) memcpy(o->lowres_costs00, &s.lowresCosts00[0], ncu * 2);
+    if (o->row_satds00) memcpy(o->row_satds00, &s.rowSatds00[0], c->g.bh * 4);
+    return 0;
+}
+
+int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost)
+{
+    SimSlot& s = c->slots[slot];
+    if (s.mvs[store].empty()) return X265CU_ERR_BAD_ARG;
+    if (mv) memcpy(mv, &s.mvs[store][0], c->g.ncu * 8);
+    if (cost) memcpy(cost, &s.mvCosts[store][0], c->g.ncu * 4);
+    return 0;
+}
+
+int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* costs, int32_t* rows)
+{
+    SimSlot& s = c->slots[slot];
+    if (s.costs[store].empty()) return X265CU_ERR_BAD_ARG;
+    if (costs) memcpy(costs, &s.costs[store][0], c->g.ncu * 2);
+    if (rows) memcpy(rows, &s.rowSatds[store][0], c->g.bh * 4);
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,139 @@
+/* la_capi.cpp -- C surface of x265cu::Lookahead (see la_capi.h). */
+#include "la_capi.h"
+#include "lookahead.h"
+#include <string.h>
+#include <stdio.h>
+#include <new>
+
+using namespace x265cu;
+
+extern "C" {
+
+void x265la_param_default(x265la_param* q)
+{
+    LookaheadParam p;
+    lookaheadParamDefault(&p);
+    memset(q, 0, sizeof(*q));
+    q->internalBitDepth = p.internalBitDepth; q->maxCUSize = p.maxCUSize;
+    q->fpsNum = p.fpsNum; q->fpsDenom = p.fpsDenom;
+    q->bframes = p.bframes; q->lookaheadDepth = p.lookaheadDepth; q->bFrameAdaptive = p.bFrameAdaptive;
+    q->bBPyramid = p.bBPyramid; q->scenecutThreshold = p.scenecutThreshold; q->scenecutBias = 5.0;
+    q->keyframeMax = p.keyframeMax; q->keyframeMin = p.keyframeMin; q->bOpenGOP = p.bOpenGOP;
+    q->bEnableWeightedPred = p.bEnableWeightedPred; q->maxNumReferences = p.maxNumReferences;
+    q->aqMode = p.rc.aqMode; q->aqStrength = p.rc.aqStrength; q->cuTree = p.rc.cuTree;
+    q->qCompress = p.rc.qCompress; q->qgSize = p.rc.qgSize; q->rateControlMode = p.rc.rateControlMode;
+    q->extraSlots = p.extraSlots; q->speculate = p.speculate;
+}
+
+void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
+{
+    LookaheadParam p;
+    lookaheadParamDefault(&p);
+    p.sourceWidth = q->sourceWidth; p.sourceHeight = q->sourceHeight; p.internalBitDepth = q->internalBitDepth;
+    p.maxCUSize = q->maxCUSize; p.fpsNum = q->fpsNum; p.fpsDenom = q->fpsDenom;
+    p.bframes = q->bframes; p.lookaheadDepth = q->lookaheadDepth; p.bFrameAdaptive = q->bFrameAdaptive;
+    p.bBPyramid = q->bBPyramid; p.bFrameBias = q->bFrameBias; p.scenecutThreshold = q->scenecutThreshold;
+    p.scenecutBias = q->scenecutBias / 100.0;
+    p.keyframeMax = q->keyframeMax; p.keyframeMin = q->keyframeMin; p.bOpenGOP = q->bOpenGOP;
+    p.bIntraRefresh = q->bIntraRefresh; p.bEnableWeightedPred = q->bEnableWeightedPred;
+    p.bEnableWeightedBiPred = q->bEnableWeightedBiPred; p.lookaheadSlices = q->lookaheadSlices;
+    p.maxNumReferences = q->maxNumReferences;
+    p.rc.aqMode = q->aqMode; p.rc.aqStrength = q->aqStrength; p.rc.cuTree = q->cuTree; p.rc.qCompress = q->qCompress;
+    p.rc.qgSize = q->qgSize; p.rc.vbvBufferSize = q->vbvBufferSize; p.rc.vbvMaxBitrate = q->vbvMaxBitrate;
+    p.rc.rateControlMode = q->rateControlMode;
+    p.poolWorkers = q->poolWorkers; p.device = q->device; p.extraSlots = q->extraSlots; p.speculate = q->speculate;
+    p.pinHost = q->pinHost;
+    /* the adjustments Encoder::configure makes before the Lookahead sees the params
+     * (encoder.cpp:3511-3516,3730-3753): cuTree needs AQ; strength 0 without cuTree disables AQ */
+    if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }
+    if (p.rc.aqStrength == 0 && p.rc.cuTree == 0) p.rc.aqMode = 0;
+    if (!p.bframes) p.bBPyramid = 0;
+    Lookahead* la = new (std::nothrow) Lookahead(p);
+    if (!la) { if (err && errLen) snprintf(err, errLen, "out of memory"); return NULL; }
+    if (!la->create())
+    {
+        if (err && errLen) snprintf(err, errLen, "%s", la->lastError());
+        delete la;
+        return NULL;
+    }
+    return la;
+}
+
+void x265la_close(void* la) { delete (Lookahead*)la; }
+
+int x265la_get_geometry(void* la, x265cu_geometry* g) { *g = ((Lookahead*)la)->geometry(); return 0; }
+const char* x265la_last_error(void* la) { return ((Lookahead*)la)->lastError(); }
+x265cu_ctx* x265la_engine(void* la) { return ((Lookahead*)la)->engine(); }
+
+void* x265la_add_picture(void* la, const void* y, const void* u, const void* v, int32_t strideY, int32_t strideC,
+                         int64_t pts, int32_t sliceType)
+{
+    return ((Lookahead*)la)->addPicture(y, u, v, strideY, strideC, pts, sliceType);
+}
+
+void x265la_flush(void* la) { ((Lookahead*)la)->flush(); }
+
+int x265la_get_decided(void* lav, x265la_frame_info* out)
+{
+    Lookahead* la = (Lookahead*)lav;
+    Frame* f = la->getDecidedPicture();
+    if (!la->ok()) return -1;
+    if (!f) return 0;
+    const Lowres& l = f->m_lowres;
+    out->poc = f->m_poc; out->sliceType = l.sliceType; out->bScenecut = l.bScenecut; out->bKeyframe = l.bKeyframe;
+    out->bLastMiniGopBFrame = l.bLastMiniGopBFrame; out->leadingBframes = l.leadingBframes;
+    out->pts = f->m_pts; out->reorderedPts = f->m_reorderedPts; out->satdCost = l.satdCost;
+    out->handle = f;
+    return 1;
+}
+
+int64_t x265la_estimated_picture_cost(void* la, void* frame, void* ref0, void* ref1)
+{
+    ((Lookahead*)la)->getEstimatedPictureCost((Frame*)frame, (Frame*)ref0, (Frame*)ref1);
+    return ((Frame*)frame)->m_lowres.satdCost;
+}
+
+void x265la_release(void* la, void* frame) { ((Lookahead*)la)->releaseFrame((Frame*)frame); }
+
+int x265la_frame_scalars(void* lav, void* frame, int64_t* costEst, int64_t* costEstAq, int32_t* intraMbs,
+                         int32_t* rowSatdsValid, uint64_t* wp_ssd, uint64_t* wp_sum, double* wdelta)
+{
+    Lookahead* la = (Lookahead*)lav;
+    const Lowres& l = ((Frame*)frame)->m_lowres;
+    const int nb = la->geometry().nb;
+    for (int i = 0; i < nb; i++)
+    {
+        for (int j = 0; j < nb; j++)
+        {
+            if (costEst) costEst[i * nb + j] = l.costEst[i][j];
+            if (costEstAq) costEstAq[i * nb + j] = l.costEstAq[i][j];
+            if (rowSatdsValid) rowSatdsValid[i * nb + j] = l.rowSatdsValid[i][j];
+        }
+        if (intraMbs) intraMbs[i] = l.intraMbs[i];
+        if (wdelta) wdelta[i] = l.weightedCostDelta[i];
+    }
+    for (int k = 0; k < 3; k++) { if (wp_ssd) wp_ssd[k] = l.wp_ssd[k]; if (wp_sum) wp_sum[k] = l.wp_sum[k]; }
+    return 0;
+}
+
+int x265la_frame_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t* mvXY, int32_t* mvCosts)
+{ return ((Lookahead*)la)->fetchMvs((Frame*)frame, list, dist, mvXY, mvCosts) ? 1 : 0; }
+
+int x265la_frame_costs(void* la, void* frame, int32_t d0, int32_t d1, uint16_t* lowresCosts, int32_t* rowSatds)
+{ return ((Lookahead*)la)->fetchCosts((Frame*)frame, d0, d1, lowresCosts, rowSatds) ? 1 : 0; }
+
+int x265la_frame_weights(void* lav, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset)
+{
+    const Lowres& l = ((Frame*)frame)->m_lowres;
+    const int nb = ((Lookahead*)lav)->geometry().nb;
+    for (int i = 0; i < nb; i++)
+    {
+        state[i] = l.weightState[i]; scale[i] = l.wScale[i]; denom[i] = l.wDenom[i]; offset[i] = l.wOffset[i];
+    }
+    return 0;
+}
+
+int x265la_frame_fetch(void* la, void* frame, const x265cu_frame_out* out)
+{ return ((Lookahead*)la)->fetchFrame((Frame*)frame, out) ? 0 : -1; }
+
+} // extern "C"

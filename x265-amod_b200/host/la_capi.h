@@ -1,0 +1,65 @@
+/* la_capi.h -- plain C surface of the host Lookahead (x265-amod_b200/host/lookahead.h) so that
+ * bench.py, the tests and non-C++ callers can drive it with host buffers.  Thin: every call maps
+ * 1:1 to a method of x265cu::Lookahead, which mirrors the reference's class Lookahead
+ * (source/encoder/slicetype.h:151-259). */
+#ifndef X265LA_CAPI_H
+#define X265LA_CAPI_H
+#include <stdint.h>
+#include "x265cu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct
+{
+    int32_t sourceWidth, sourceHeight, internalBitDepth, maxCUSize;
+    int32_t fpsNum, fpsDenom;
+    int32_t bframes, lookaheadDepth, bFrameAdaptive, bBPyramid, bFrameBias;
+    int32_t scenecutThreshold;
+    double  scenecutBias;            /* percent, like --scenecut-bias (divided by 100 internally) */
+    int32_t keyframeMax, keyframeMin, bOpenGOP, bIntraRefresh;
+    int32_t bEnableWeightedPred, bEnableWeightedBiPred;
+    int32_t lookaheadSlices, maxNumReferences;
+    int32_t aqMode; double aqStrength; int32_t cuTree; double qCompress; int32_t qgSize;
+    int32_t vbvBufferSize, vbvMaxBitrate, rateControlMode;
+    int32_t poolWorkers, device, extraSlots, speculate, pinHost;
+    int32_t reserved[8];
+} x265la_param;
+
+typedef struct
+{
+    int32_t poc, sliceType, bScenecut, bKeyframe, bLastMiniGopBFrame, leadingBframes;
+    int64_t pts, reorderedPts, satdCost;
+    void*   handle;                  /* pass to the x265la_frame_* calls and x265la_release */
+} x265la_frame_info;
+
+void  x265la_param_default(x265la_param* p);
+void* x265la_open(const x265la_param* p, char* err, int32_t errLen);   /* NULL on failure */
+void  x265la_close(void* la);
+int   x265la_get_geometry(void* la, x265cu_geometry* g);
+const char* x265la_last_error(void* la);
+/* Lookahead::addPicture; returns the frame handle or NULL */
+void* x265la_add_picture(void* la, const void* y, const void* u, const void* v, int32_t strideY, int32_t strideC,
+                         int64_t pts, int32_t sliceType);
+void  x265la_flush(void* la);
+/* Lookahead::getDecidedPicture; 1 = frame returned, 0 = none yet, <0 = error */
+int   x265la_get_decided(void* la, x265la_frame_info* out);
+/* Lookahead::getEstimatedPictureCost with explicit references (handles, may be NULL) */
+int64_t x265la_estimated_picture_cost(void* la, void* frame, void* ref0, void* ref1);
+void  x265la_release(void* la, void* frame);
+
+/* published Lowres state of one frame, reference layout (common/lowres.h:171-263) */
+int   x265la_frame_scalars(void* la, void* frame, int64_t* costEst /* nb*nb */, int64_t* costEstAq /* nb*nb */,
+                           int32_t* intraMbs /* nb */, int32_t* rowSatdsValid /* nb*nb */,
+                           uint64_t* wp_ssd /* 3 */, uint64_t* wp_sum /* 3 */, double* weightedCostDelta /* nb */);
+int   x265la_frame_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t* mvXY, int32_t* mvCosts);  /* 1 ok, 0 unsearched */
+int   x265la_frame_costs(void* la, void* frame, int32_t d0, int32_t d1, uint16_t* lowresCosts, int32_t* rowSatds);
+int   x265la_frame_fetch(void* la, void* frame, const x265cu_frame_out* out);
+/* weightp analysis outcome per L0 distance: state 0 = not analysed, 1 = no weight, 2 = weighted */
+int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset /* nb each */);
+x265cu_ctx* x265la_engine(void* la);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1339 @@
+/* lookahead.cpp -- host decision logic of the B200 lookahead (see lookahead.h).
+ *
+ * Behavioural reference: source/encoder/slicetype.cpp of DJATOM/x265-aMod 3.6+1.  Each routine
+ * names the reference lines whose observable behaviour it reproduces.  The code is organised
+ * around a publish/consume cache over GPU batches rather than around the reference's thread
+ * pool, so only the decisions (and their order of first touch) are shared with it.
+ *
+ * Not supported (create() fails with an error string rather than silently diverging):
+ * --lookahead-slices > 0, --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
+ * zones, radl, gop-lookahead, temporal sub-layers, analysis load, fades, chunked encodes.
+ */
+#include "lookahead.h"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <algorithm>
+
+namespace x265cu {
+
+static inline double clipDuration(double f) { return f < 0.01 ? 0.01 : (f > 1.0 ? 1.0 : f); }  /* ratecontrol.h:43-48 */
+
+/* x265_lambda_tab[X265_LOOKAHEAD_QP] (constants.cpp:34-90, common.h:209-213): exactly 1, 16, 256 */
+int lookaheadLambda(int depth) { return 1 << (2 * (depth - 8)); }
+
+/* The BitCost row the lookahead's MotionEstimate uses (bitcost.cpp:30-54, 98-113).  Built on the
+ * host in float exactly like the reference and uploaded; the device never recomputes it. */
+void buildMvCostTable(std::vector<uint16_t>& table, int half, int depth)
+{
+    table.assign(2 * (size_t)half + 1, 0);
+    const double lambda = (double)lookaheadLambda(depth);
+    const float log2_2 = 2.0f / logf(2.0f);
+    for (int i = 0; i <= half; i++)
+    {
+        float bits = i ? logf((float)(i + 1)) * log2_2 + 1.718f : 0.718f;
+        double c = bits * lambda + 0.5f;
+        if (c > 32767.0) c = 32767.0;
+        table[half + i] = table[half - i] = (uint16_t)c;
+    }
+}
+
+void lookaheadParamDefault(LookaheadParam* p)
+{
+    memset(p, 0, sizeof(*p));
+    p->internalBitDepth = 8; p->maxCUSize = 64;
+    p->fpsNum = 25; p->fpsDenom = 1;
+    p->bframes = 4; p->lookaheadDepth = 20; p->bFrameAdaptive = B_ADAPT_TRELLIS; p->bBPyramid = 1;
+    p->scenecutThreshold = 40; p->scenecutBias = 0.05;
+    p->keyframeMax = 250; p->keyframeMin = 0; p->bOpenGOP = 1;
+    p->bEnableWeightedPred = 1; p->maxNumReferences = 3;
+    p->rc.aqMode = 2; p->rc.aqStrength = 1.0; p->rc.cuTree = 1; p->rc.qCompress = 0.6; p->rc.qgSize = 32;
+    p->rc.rateControlMode = 2 /* X265_RC_CRF */;
+    p->extraSlots = 8; p->speculate = 1;
+}
+
+Lookahead::Lookahead(const LookaheadParam& param)
+    : m_param(param), m_filled(false), m_inputCount(0), m_lastNonB(NULL), m_lastNonBFrame(NULL),
+      m_isSceneTransition(false), m_extendGopBoundary(false), m_ctx(NULL), m_pocNext(0), m_failed(false)
+{
+    m_error[0] = 0;
+    /* slicetype.cpp:996-1033 */
+    m_8x8Height = ((m_param.sourceHeight / 2) + 7) >> 3;
+    m_8x8Width = ((m_param.sourceWidth / 2) + 7) >> 3;
+    m_cuCount = m_8x8Width * m_8x8Height;
+    m_8x8Blocks = m_8x8Width > 2 && m_8x8Height > 2 ? (m_cuCount + 4 - 2 * (m_8x8Width + m_8x8Height)) : m_cuCount;
+    m_cuTreeStrength = 5.0 * (1.0 - m_param.rc.qCompress);
+    if (!m_param.keyframeMin)   /* Encoder::configure, encoder.cpp:3658-3663 */
+    {
+        double fps = (double)m_param.fpsNum / m_param.fpsDenom;
+        m_param.keyframeMin = std::min((int)fps, m_param.keyframeMax / 10);
+    }
+    m_param.keyframeMin = std::max(1, m_param.keyframeMin);
+    m_lastKeyframe = -m_param.keyframeMax;
+    m_fullQueueSize = std::max(1, m_param.lookaheadDepth);
+    m_bAdaptiveQuant = m_param.rc.aqMode || m_param.bEnableWeightedPred || m_param.bEnableWeightedBiPred;
+    m_bBatchMotionSearch = m_param.poolWorkers > 0 && m_param.bFrameAdaptive == B_ADAPT_TRELLIS;
+    m_bBatchFrameCosts = m_bBatchMotionSearch;
+    memset(&m_geom, 0, sizeof(m_geom));
+}
+
+Lookahead::~Lookahead() { destroy(); }
+
+void Lookahead::fail(const char* what)
+{
+    if (!m_failed)
+    {
+        snprintf(m_error, sizeof(m_error), "%s%s%s", what, m_ctx ? ": " : "", m_ctx ? x265cu_last_error(m_ctx) : "");
+        m_failed = true;
+    }
+}
+
+bool Lookahead::check(int status, const char* what)
+{
+    if (status == X265CU_OK)
+        return true;
+    char buf[200];
+    snprintf(buf, sizeof(buf), "%s failed (%s)", what, x265cu_strerror(status));
+    fail(buf);
+    return false;
+}
+
+bool Lookahead::create()
+{
+    const LookaheadParam& p = m_param;
+    if (p.lookaheadSlices > 0) { fail("lookahead-slices > 0 is not supported by the GPU lookahead"); return false; }
+    if (p.rc.qgSize < 16) { fail("qg-size 8 is not supported by the GPU lookahead"); return false; }
+    if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
+    if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
+    if (p.lookaheadDepth && p.lookaheadDepth <= p.bframes) { fail("rc-lookahead must exceed bframes"); return false; }
+    if (p.lookaheadDepth > LOOKAHEAD_MAX) { fail("rc-lookahead too large"); return false; }
+
+    const int lowW = 8 * m_8x8Width;
+    const int half = std::min(2 * 32768, 4 * (lowW + 8 * m_8x8Height) * 2 + 4096);
+    buildMvCostTable(m_mvcost, half, p.internalBitDepth);
+
+    x265cu_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.width = p.sourceWidth; cfg.height = p.sourceHeight; cfg.depth = p.internalBitDepth;
+    cfg.max_cu_size = p.maxCUSize; cfg.bframes = p.bframes;
+    cfg.max_slots = std::max(1, p.lookaheadDepth) + 2 * (p.bframes + 2) + 4 + p.extraSlots;
+    cfg.qg_size = p.rc.qgSize; cfg.aq_mode = p.rc.aqMode; cfg.aq_strength = p.rc.aqStrength;
+    cfg.need_aq = m_bAdaptiveQuant; cfg.need_wp_stats = p.bEnableWeightedPred || p.bEnableWeightedBiPred;
+    cfg.lambda = lookaheadLambda(p.internalBitDepth);
+    cfg.mvcost = &m_mvcost[0]; cfg.mvcost_half = half;
+    cfg.device = p.device;
+    if (!check(x265cu_create(&cfg, &m_ctx), "x265cu_create"))
+        return false;
+    if (!check(x265cu_get_geometry(m_ctx, &m_geom), "x265cu_get_geometry"))
+        return false;
+    if (m_geom.bw != m_8x8Width || m_geom.bh != m_8x8Height) { fail("engine geometry mismatch"); return false; }
+    m_pool.resize(cfg.max_slots);
+    for (size_t i = 0; i < m_pool.size(); i++)
+    {
+        Frame* f = new Frame;
+        memset(f, 0, sizeof(*f));
+        f->m_lowres.slot = (int)i;
+        f->m_owner = this;
+        m_pool[i] = f;
+    }
+    return true;
+}
+
+void Lookahead::destroy()
+{
+    for (size_t i = 0; i < m_pool.size(); i++) delete m_pool[i];
+    m_pool.clear(); m_inputQueue.clear(); m_outputQueue.clear(); m_resident.clear();
+    if (m_ctx) { x265cu_destroy(m_ctx); m_ctx = NULL; }
+}
+
+/* Lowres::init minus the pixel work (common/lowres.cpp:337-365) */
+void Lookahead::initLowres(Frame* f, int poc)
+{
+    Lowres& l = f->m_lowres;
+    int slot = l.slot;
+    memset(&l, 0, sizeof(l));
+    l.slot = slot;
+    l.frameNum = poc;
+    l.satdCost = -1;
+    for (int i = 0; i < BFRAME_MAX + 2; i++)
+        for (int j = 0; j < BFRAME_MAX + 2; j++)
+        {
+            /* costEstAq is only reset to -1 when the AQ arrays exist (lowres.cpp:348-349) */
+            l.costEst[i][j] = -1; l.costEstAq[i][j] = m_bAdaptiveQuant ? -1 : 0; l.costStore[i][j] = -1;
+        }
+    for (int i = 0; i < BFRAME_MAX + 2; i++)
+        l.mvStore[0][i] = l.mvStore[1][i] = -1;
+}
+
+Frame* Lookahead::frameOfPoc(int poc)
+{
+    for (size_t i = m_resident.size(); i-- > 0;)
+        if (m_resident[i]->m_poc == poc)
+            return m_resident[i];
+    return NULL;
+}
+
+/* Release slots nobody can reference any more: the caller is done with the frame, it is not
+ * m_lastNonB, and it is more than bframes+1 behind the newest arrival (no future search or
+ * estimate can name it, slicetype.cpp:2674-2689 / 3221). */
+void Lookahead::recycle()
+{
+    size_t w = 0;
+    for (size_t i = 0; i < m_resident.size(); i++)
+    {
+        Frame* f = m_resident[i];
+        bool dead = f->m_released && f != m_lastNonBFrame && f->m_poc + m_param.bframes + 1 < m_pocNext - 1;
+        if (dead) f->m_inUse = false;
+        else m_resident[w++] = f;
+    }
+    m_resident.resize(w);
+}
+
+void Lookahead::releaseFrame(Frame* f) { if (f) { f->m_released = true; recycle(); } }
+
+/* slicetype.cpp:1200-1243 */
+Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int strideY, int strideC,
+                             int64_t pts, int sliceType)
+{
+    if (m_failed) return NULL;
+    if (!m_filled)   /* checkLookaheadQueue */
+    {
+        if (!m_param.bframes & !m_param.lookaheadDepth) m_filled = true;
+        else if (m_inputCount >= m_param.lookaheadDepth + 2 + m_param.bframes) m_filled = true;
+    }
+    Frame* f = NULL;
+    for (size_t i = 0; i < m_pool.size(); i++)
+        if (!m_pool[i]->m_inUse) { f = m_pool[i]; break; }
+    if (!f) { recycle(); for (size_t i = 0; i < m_pool.size(); i++) if (!m_pool[i]->m_inUse) { f = m_pool[i]; break; } }
+    if (!f) return NULL;
+    f->m_inUse = true; f->m_released = false; f->m_speculated = false; f->m_lowresInit = false;
+    f->m_poc = m_pocNext++; f->m_pts = pts; f->m_reorderedPts = 0;
+    f->m_planes[0] = y; f->m_planes[1] = u; f->m_planes[2] = v; f->m_strideY = strideY; f->m_strideC = strideC;
+    initLowres(f, f->m_poc);
+    f->m_lowres.sliceType = sliceType;
+    f->m_lowres.sliceTypeReq = TYPE_AUTO;
+    /* the device starts the frame's pre-lookahead now; results are collected in slicetypeDecide */
+    if (!check(x265cu_frame_upload(m_ctx, f->m_lowres.slot, y, u, v, strideY, strideC), "x265cu_frame_upload"))
+        return NULL;
+    m_resident.push_back(f);
+    m_inputQueue.push_back(f);
+    m_inputCount++;
+    return f;
+}
+
+void Lookahead::flush() { m_fullQueueSize = 1; m_filled = true; }   /* slicetype.cpp:1246-1251 */
+
+/* slicetype.cpp:1259-1322 without the thread hand-off: the decision runs on the caller */
+Frame* Lookahead::getDecidedPicture()
+{
+    if (!m_filled || m_failed)
+        return NULL;
+    if (m_outputQueue.empty() && (int)m_inputQueue.size() >= m_fullQueueSize && !m_inputQueue.empty())
+        slicetypeDecide();
+    if (m_outputQueue.empty() || m_failed)
+        return NULL;
+    Frame* out = m_outputQueue.front();
+    m_outputQueue.pop_front();
+    m_inputCount--;
+    return out;
+}
+
+int Lookahead::findSliceType(int poc)   /* slicetype.cpp:3248-3266 */
+{
+    if (m_filled)
+        for (size_t i = 0; i < m_outputQueue.size(); i++)
+            if (m_outputQueue[i]->m_poc == poc)
+                return m_outputQueue[i]->m_lowres.sliceType;
+    return TYPE_AUTO;
+}
+
+/* -------------------------------------------------------------------------------------------
+ * device orchestration
+ * ------------------------------------------------------------------------------------------- */
+
+/* PreLookaheadGroup::processTasks (slicetype.cpp:1726-1752): the pixel work was enqueued by
+ * addPicture; collect the scalars the decisions need. */
+void Lookahead::preLookahead(const std::vector<Frame*>& fr)
+{
+    if (fr.empty()) return;
+    std::vector<int32_t> slots(fr.size());
+    std::vector<x265cu_frame_stats> st(fr.size());
+    for (size_t i = 0; i < fr.size(); i++) slots[i] = fr[i]->m_lowres.slot;
+    if (!check(x265cu_frame_stats_get(m_ctx, &slots[0], (int)slots.size(), &st[0]), "x265cu_frame_stats_get"))
+        return;
+    for (size_t i = 0; i < fr.size(); i++)
+    {
+        Lowres& l = fr[i]->m_lowres;
+        l.costEst[0][0] = st[i].cost_est;
+        l.costEstAq[0][0] = st[i].cost_est_aq;
+        l.rowSatdsValid[0][0] = true;
+        l.costStore[0][0] = 0;
+        for (int k = 0; k < 3; k++) { l.wp_ssd[k] = st[i].wp_ssd[k]; l.wp_sum[k] = st[i].wp_sum[k]; }
+        l.statsFetched = true;
+        fr[i]->m_lowresInit = true;
+    }
+}
+
+/* LookaheadTLD::weightsAnalyse (slicetype.cpp:879-980) for many (fenc, ref) pairs at once.  The
+ * scalar logic is the reference's; the two whole-frame SATD scores per pair are GPU batches. */
+void Lookahead::weightsAnalyseBatch(const std::vector<std::pair<Lowres*, Lowres*> >& pairs)
+{
+    struct Cand { Lowres* fenc; Lowres* ref; int d; int mindenom, minscale, curScale, curOffset; unsigned orig; float fencMean, refMean; };
+    std::vector<Cand> cands;
+    const int depthShift = m_param.internalBitDepth - 8;
+    const int lowW = m_geom.low_width, lowH = m_geom.low_height;
+    for (size_t i = 0; i < pairs.size(); i++)
+    {
+        Lowres* fenc = pairs[i].first; Lowres* ref = pairs[i].second;
+        int d = fenc->frameNum - ref->frameNum;
+        if (fenc->weightState[d]) continue;
+        fenc->weightState[d] = 1;
+        const float epsilon = 1.f / 128.f;
+        float guessScale, fencMean, refMean;
+        if (fenc->wp_ssd[0] && ref->wp_ssd[0])
+            guessScale = sqrtf((float)fenc->wp_ssd[0] / ref->wp_ssd[0]);
+        else
+            guessScale = 1.0f;
+        fencMean = (float)fenc->wp_sum[0] / (lowH * lowW) / (1 << depthShift);
+        refMean = (float)ref->wp_sum[0] / (lowH * lowW) / (1 << depthShift);
+        if (fabsf(refMean - fencMean) < 0.5f && fabsf(1.f - guessScale) < epsilon)
+            continue;
+        Cand c; c.fenc = fenc; c.ref = ref; c.d = d; c.fencMean = fencMean; c.refMean = refMean;
+        int w = (int)(guessScale * 128 + 0.5f), den = 7;     /* setFromWeightAndOffset(w,0,7,true), slice.h:304-316 */
+        while (den > 0 && w > 127) { den--; w >>= 1; }
+        c.mindenom = den; c.minscale = std::min(w, 127);
+        c.curScale = c.curOffset = 0; c.orig = 0;
+        cands.push_back(c);
+    }
+    if (cands.empty()) return;
+    std::vector<x265cu_wcost_job> jobs(cands.size());
+    std::vector<uint32_t> costs(cands.size());
+    for (size_t i = 0; i < cands.size(); i++)
+    {
+        memset(&jobs[i], 0, sizeof(jobs[i]));
+        jobs[i].fenc_slot = cands[i].fenc->slot; jobs[i].ref_slot = cands[i].ref->slot;
+    }
+    if (!check(x265cu_weight_cost_batch(m_ctx, &jobs[0], (int)jobs.size(), &costs[0]), "x265cu_weight_cost_batch"))
+        return;
+    std::vector<Cand> second;
+    for (size_t i = 0; i < cands.size(); i++)
+    {
+        Cand c = cands[i];
+        c.orig = costs[i];
+        if (!c.orig) continue;
+        c.curScale = c.minscale;
+        c.curOffset = (int)(c.fencMean - c.refMean * c.curScale / (1 << c.mindenom) + 0.5f);
+        if (c.curOffset < -128 || c.curOffset > 127)
+        {
+            c.curOffset = std::max(-128, std::min(127, c.curOffset));
+            c.curScale = (int)((1 << c.mindenom) * (c.fencMean - c.curOffset) / c.refMean + 0.5f);
+            c.curScale = std::max(0, std::min(127, c.curScale));
+        }
+        second.push_back(c);
+    }
+    if (second.empty()) return;
+    jobs.resize(second.size()); costs.resize(second.size());
+    for (size_t i = 0; i < second.size(); i++)
+    {
+        jobs[i].fenc_slot = second[i].fenc->slot; jobs[i].ref_slot = second[i].ref->slot;
+        jobs[i].weighted = 1; jobs[i].w_scale = second[i].curScale; jobs[i].w_denom = second[i].mindenom;
+        jobs[i].w_offset = second[i].curOffset;
+    }
+    if (!check(x265cu_weight_cost_batch(m_ctx, &jobs[0], (int)jobs.size(), &costs[0]), "x265cu_weight_cost_batch"))
+        return;
+    for (size_t i = 0; i < second.size(); i++)
+    {
+        Cand& c = second[i];
+        unsigned minscore = c.orig, s = costs[i];
+        int minscale = c.minscale, mindenom = c.mindenom, minoff = 0, found = 0;
+        if (s < minscore) { minscore = s; minscale = c.curScale; minoff = c.curOffset; found = 1; }
+        if (mindenom > 0 && !(minscale & 1))
+        {
+            int idx = 0;
+            while (minscale && !((minscale >> idx) & 1)) idx++;
+            if (!minscale) idx = 32;
+            int shift = std::min(idx, mindenom);
+            mindenom -= shift; minscale >>= shift;
+        }
+        if (!found || (minscale == (1 << mindenom) && minoff == 0) || (float)minscore / c.orig > 0.998f)
+            continue;
+        c.fenc->weightedCostDelta[c.d] = (double)(minscore / c.orig);   /* integer division, slicetype.cpp:964 */
+        c.fenc->weightState[c.d] = 2;
+        c.fenc->wScale[c.d] = minscale; c.fenc->wDenom[c.d] = mindenom; c.fenc->wOffset[c.d] = minoff;
+    }
+}
+
+static void addSearch(std::vector<x265cu_search_job>& jobs, Lowres* fenc, Lowres* ref, int kind, int d, int nb)
+{
+    if (fenc->haveSearch[kind][d]) return;
+    fenc->haveSearch[kind][d] = 1;
+    x265cu_search_job j;
+    memset(&j, 0, sizeof(j));
+    j.fenc_slot = fenc->slot; j.ref_slot = ref->slot;
+    j.bidir_ctx = kind != 0;
+    j.store = kind * nb + d;
+    if (kind < 2 && fenc->weightState[d] == 2)
+    {
+        j.weighted = 1; j.w_scale = fenc->wScale[d]; j.w_denom = fenc->wDenom[d]; j.w_offset = fenc->wOffset[d];
+    }
+    jobs.push_back(j);
+}
+
+static void addCost(std::vector<x265cu_cost_job>& jobs, Lowres* b, Lowres* p0, Lowres* p1, int d0, int d1, int variant, int nb)
+{
+    if (b->haveCost[d0][d1][variant]) return;
+    b->haveCost[d0][d1][variant] = 1;
+    x265cu_cost_job j;
+    j.b_slot = b->slot; j.p0_slot = p0->slot; j.p1_slot = p1 ? p1->slot : b->slot;
+    j.l0_store = variant * nb + d0;
+    j.l1_store = p1 ? 2 * nb + d1 : -1;
+    j.out = (d0 * nb + d1) * 2 + variant;
+    jobs.push_back(j);
+}
+
+/* Eager whole-window batch: for every frame that arrived since the last decision, every motion
+ * search and frame cost the reference could ask for (distances <= bframes+1, slicetype.cpp:
+ * 2674-2689, 3221-3305) whose frames are all resident. */
+void Lookahead::speculate()
+{
+    const int B = m_param.bframes, nb = m_geom.nb;
+    std::vector<Frame*> fresh;
+    for (size_t i = 0; i < m_resident.size(); i++)
+        if (!m_resident[i]->m_speculated && m_resident[i]->m_lowresInit)
+            fresh.push_back(m_resident[i]);
+    if (fresh.empty()) return;
+
+    if (m_param.bEnableWeightedPred)
+    {
+        std::vector<std::pair<Lowres*, Lowres*> > pairs;
+        for (size_t i = 0; i < fresh.size(); i++)
+            for (int d = 1; d <= B + 1; d++)
+            {
+                Frame* r = frameOfPoc(fresh[i]->m_poc - d);
+                if (!r || !r->m_lowresInit) break;
+                pairs.push_back(std::make_pair(&fresh[i]->m_lowres, &r->m_lowres));
+            }
+        weightsAnalyseBatch(pairs);
+    }
+
+    m_searchJobs.clear(); m_costJobs.clear();
+    const int maxD1 = B;                                  /* p1 - b <= bframes */
+    for (size_t i = 0; i < fresh.size(); i++)
+    {
+        Frame* fn = fresh[i];
+        Lowres* n = &fn->m_lowres;
+        fn->m_speculated = true;
+        for (int d = 1; d <= B + 1; d++)
+        {
+            Frame* rf = frameOfPoc(fn->m_poc - d);
+            if (!rf || !rf->m_lowresInit) break;
+            Lowres* r = &rf->m_lowres;
+            addSearch(m_searchJobs, n, r, 0, d, nb);                 /* L0(n,d), P context */
+            addCost(m_costJobs, n, r, NULL, d, 0, 0, nb);
+            if (B > 0)
+            {
+                addSearch(m_searchJobs, n, r, 1, d, nb);             /* L0(n,d), B context */
+                addCost(m_costJobs, n, r, NULL, d, 0, 1, nb);
+                if (d <= maxD1)
+                    addSearch(m_searchJobs, r, n, 2, d, nb);         /* L1(n-d,d), reference = n */
+            }
+        }
+        /* B estimates completed by n's arrival: b = n - d1, p0 = b - d0 */
+        for (int d1 = 1; d1 <= maxD1; d1++)
+        {
+            Frame* bf = frameOfPoc(fn->m_poc - d1);
+            if (!bf || !bf->m_lowresInit) break;
+            int maxD0 = m_bBatchFrameCosts ? B + 1 : B + 1 - d1;
+            for (int d0 = 1; d0 <= maxD0; d0++)
+            {
+                Frame* p0f = frameOfPoc(bf->m_poc - d0);
+                if (!p0f || !p0f->m_lowresInit) break;
+                Lowres* b = &bf->m_lowres;
+                if (!b->haveSearch[0][d0] || !b->haveSearch[1][d0] || !b->haveSearch[2][d1]) continue;
+                addCost(m_costJobs, b, &p0f->m_lowres, n, d0, d1, 0, nb);
+                addCost(m_costJobs, b, &p0f->m_lowres, n, d0, d1, 1, nb);
+            }
+        }
+    }
+    if (!m_searchJobs.empty())
+        check(x265cu_search_batch(m_ctx, &m_searchJobs[0], (int)m_searchJobs.size()), "x265cu_search_batch");
+    if (!m_costJobs.empty())
+        check(x265cu_cost_batch(m_ctx, &m_costJobs[0], (int)m_costJobs.size()), "x265cu_cost_batch");
+    std::vector<Lowres*> who;
+    for (size_t i = 0; i < m_resident.size(); i++) who.push_back(&m_resident[i]->m_lowres);
+    fetchResults(who);
+}
+
+/* one synchronising gather of every computed-but-unread cost scalar */
+void Lookahead::fetchResults(const std::vector<Lowres*>& who)
+{
+    const int nb = m_geom.nb;
+    std::vector<int32_t> slots, outs;
+    struct Ref { Lowres* l; int d0, d1, v; };
+    std::vector<Ref> refs;
+    for (size_t i = 0; i < who.size(); i++)
+        for (int d0 = 1; d0 < nb; d0++)
+            for (int d1 = 0; d1 < nb; d1++)
+                for (int v = 0; v < 2; v++)
+                    if (who[i]->haveCost[d0][d1][v] && !who[i]->resultFetched[d0][d1][v])
+                    {
+                        slots.push_back(who[i]->slot); outs.push_back((d0 * nb + d1) * 2 + v);
+                        Ref r = { who[i], d0, d1, v };
+                        refs.push_back(r);
+                    }
+    if (slots.empty()) return;
+    std::vector<x265cu_cost_result> res(slots.size());
+    if (!check(x265cu_cost_results_get(m_ctx, &slots[0], &outs[0], (int)slots.size(), &res[0]), "x265cu_cost_results_get"))
+        return;
+    for (size_t i = 0; i < refs.size(); i++)
+    {
+        refs[i].l->result[refs[i].d0][refs[i].d1][refs[i].v] = res[i];
+        refs[i].l->resultFetched[refs[i].d0][refs[i].d1][refs[i].v] = 1;
+    }
+}
+
+/* demand path: make sure the searches and the cost of one estimate exist on the device and its
+ * scalars on the host (everything already speculated is a no-op) */
+void Lookahead::ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind)
+{
+    const int nb = m_geom.nb;
+    if (fenc->resultFetched[d0][d1][l0kind]) return;
+    m_searchJobs.clear(); m_costJobs.clear();
+    if (!fenc->haveSearch[l0kind][d0])
+    {
+        if (m_param.bEnableWeightedPred && !fenc->weightState[d0])
+        {
+            std::vector<std::pair<Lowres*, Lowres*> > one(1, std::make_pair(fenc, ref0));
+            weightsAnalyseBatch(one);
+        }
+        addSearch(m_searchJobs, fenc, ref0, l0kind, d0, nb);
+    }
+    if (ref1 && !fenc->haveSearch[2][d1])
+        addSearch(m_searchJobs, fenc, ref1, 2, d1, nb);
+    addCost(m_costJobs, fenc, ref0, ref1, d0, d1, l0kind, nb);
+    if (!m_searchJobs.empty())
+        check(x265cu_search_batch(m_ctx, &m_searchJobs[0], (int)m_searchJobs.size()), "x265cu_search_batch");
+    if (!m_costJobs.empty())
+        check(x265cu_cost_batch(m_ctx, &m_costJobs[0], (int)m_costJobs.size()), "x265cu_cost_batch");
+    std::vector<Lowres*> who(1, fenc);
+    fetchResults(who);
+}
+
+/* -------------------------------------------------------------------------------------------
+ * CostEstimateGroup::singleCost / estimateFrameCost (slicetype.cpp:3882-3886, 3976-4075)
+ * ------------------------------------------------------------------------------------------- */
+
+int64_t Lookahead::singleCost(Lowres** frames, int p0, int p1, int b, bool bIntraPenalty)
+{
+    return estimateFrameCost(frames, p0, p1, b, bIntraPenalty);
+}
+
+int64_t Lookahead::estimateFrameCost(Lowres** frames, int p0, int p1, int b, bool bIntraPenalty)
+{
+    Lowres* fenc = frames[b];
+    const int d0 = b - p0, d1 = p1 - b, nb = m_geom.nb;
+    int64_t score = 0;
+    if (m_failed) return 0;
+
+    if (fenc->costEst[d0][d1] >= 0 && fenc->rowSatdsValid[d0][d1])
+        score = fenc->costEst[d0][d1];
+    else
+    {
+        if (d0 <= 0 || d0 >= nb || d1 < 0 || d1 >= nb) { fail("estimate outside the (bframes+2) window"); return 0; }
+        const bool bDoSearch0 = fenc->mvStore[0][d0] < 0;
+        const bool bDoSearch1 = p1 > b && fenc->mvStore[1][d1] < 0;
+        /* first touch decides which variant of the L0 search the reference would hold */
+        int l0kind = bDoSearch0 ? (p1 > b ? 1 : 0) : fenc->mvStore[0][d0] / nb;
+        ensureEstimate(fenc, frames[p0], p1 > b ? frames[p1] : NULL, d0, d1, l0kind);
+        if (m_failed) return 0;
+        if (bDoSearch0) fenc->mvStore[0][d0] = l0kind * nb + d0;
+        if (bDoSearch1) fenc->mvStore[1][d1] = 2 * nb + d1;
+        const x265cu_cost_result& r = fenc->result[d0][d1][l0kind];
+        fenc->costEstAq[d0][d1] = r.cost_est_aq;
+        if (p1 == b) fenc->intraMbs[d0] += r.intra_mbs;
+        fenc->rowSatdsValid[d0][d1] = true;
+        fenc->costStore[d0][d1] = (d0 * nb + d1) * 2 + l0kind;
+        score = r.cost_est;
+        if (b != p1)
+            score = score * 100 / (130 + m_param.bFrameBias);
+        fenc->costEst[d0][d1] = score;
+    }
+    if (bIntraPenalty)
+        score += score * fenc->intraMbs[b - p0] / (m_8x8Blocks * 8);
+    return score;
+}
+
+/* -------------------------------------------------------------------------------------------
+ * slicetypeDecide (slicetype.cpp:1802-2508; non-temporal-layer, non-analysis-load branches)
+ * ------------------------------------------------------------------------------------------- */
+
+void Lookahead::placeBref(Frame** list, int start, int end, int /*num*/, int* brefs)   /* :1755-1777 */
+{
+    int avg = (start + end) / 2;
+    list[avg]->m_lowres.sliceType = TYPE_BREF;
+    (*brefs)++;
+}
+
+void Lookahead::slicetypeDecide()
+{
+    Lowres* frames[LOOKAHEAD_MAX + BFRAME_MAX + 4];
+    Frame*  fr[LOOKAHEAD_MAX + BFRAME_MAX + 4];
+    Frame*  list[BFRAME_MAX + 4];
+    memset(frames, 0, sizeof(frames)); memset(fr, 0, sizeof(fr)); memset(list, 0, sizeof(list));
+    int maxSearch = std::max(1, std::min(m_param.lookaheadDepth, (int)LOOKAHEAD_MAX));
+
+    int j;
+    for (j = 0; j < m_param.bframes + 2 && j < (int)m_inputQueue.size(); j++)
+        list[j] = m_inputQueue[j];
+    frames[0] = m_lastNonB; fr[0] = m_lastNonBFrame;
+    std::vector<Frame*> pre;
+    for (j = 0; j < maxSearch && j < (int)m_inputQueue.size(); j++)
+    {
+        fr[j + 1] = m_inputQueue[j];
+        frames[j + 1] = &m_inputQueue[j]->m_lowres;
+        if (!m_inputQueue[j]->m_lowresInit) pre.push_back(m_inputQueue[j]);
+    }
+    maxSearch = j;
+
+    /* pre-analysis results for every frame that arrived (not only the first maxSearch): the
+     * GPU already ran it, and speculation wants all resident frames */
+    for (size_t i = 0; i < m_resident.size(); i++)
+        if (!m_resident[i]->m_lowresInit && std::find(pre.begin(), pre.end(), m_resident[i]) == pre.end())
+            pre.push_back(m_resident[i]);
+    preLookahead(pre);
+    if (m_failed) return;
+    if (m_param.speculate)
+        speculate();
+    if (m_failed) return;
+
+    const LookaheadParam& p = m_param;
+    if (m_lastNonB && ((p.bFrameAdaptive && p.bframes) || p.rc.cuTree || p.scenecutThreshold ||
+                       (p.lookaheadDepth && p.rc.vbvBufferSize)))
+        slicetypeAnalyse(frames, fr, false);
+    if (m_failed) return;
+
+    int bframes, brefs;
+    for (bframes = 0, brefs = 0;; bframes++)
+    {
+        Lowres& frm = list[bframes]->m_lowres;
+        if (frm.sliceTypeReq != TYPE_AUTO && frm.sliceTypeReq != frm.sliceType)
+            frm.sliceType = frm.sliceTypeReq;
+        if (frm.sliceType == TYPE_BREF && !p.bBPyramid && brefs == p.bBPyramid)
+            frm.sliceType = TYPE_B;
+        else if (frm.sliceType == TYPE_BREF && p.bBPyramid && brefs && p.maxNumReferences <= (brefs + 3))
+            frm.sliceType = TYPE_B;
+        if ((!p.bIntraRefresh || frm.frameNum == 0) && frm.frameNum - m_lastKeyframe >= p.keyframeMax)
+        {
+            if (frm.sliceType == TYPE_AUTO || frm.sliceType == TYPE_I)
+                frm.sliceType = p.bOpenGOP && m_lastKeyframe >= 0 ? TYPE_I : TYPE_IDR;
+            bool warn = frm.sliceType != TYPE_IDR;
+            if (warn && p.bOpenGOP) warn &= frm.sliceType != TYPE_I;
+            if (warn)
+                frm.sliceType = p.bOpenGOP && m_lastKeyframe >= 0 ? TYPE_I : TYPE_IDR;
+        }
+        if (frm.sliceType == TYPE_I && frm.frameNum - m_lastKeyframe >= p.keyframeMin)
+        {
+            if (p.bOpenGOP) { m_lastKeyframe = frm.frameNum; frm.bKeyframe = true; }
+            else frm.sliceType = TYPE_IDR;
+        }
+        if (frm.sliceType == TYPE_IDR)
+        {
+            m_lastKeyframe = frm.frameNum;
+            frm.bKeyframe = true;
+            if (bframes > 0)
+            {
+                list[bframes - 1]->m_lowres.sliceType = TYPE_P;
+                bframes--;
+            }
+        }
+        if (bframes == p.bframes || !list[bframes + 1])
+        {
+            if (frm.sliceType == TYPE_AUTO || isTypeB(frm.sliceType))
+                frm.sliceType = TYPE_P;
+        }
+        if (frm.sliceType == TYPE_BREF) brefs++;
+        if (frm.sliceType == TYPE_AUTO) frm.sliceType = TYPE_B;
+        else if (!isTypeB(frm.sliceType)) break;
+    }
+
+    if (bframes) list[bframes - 1]->m_lowres.bLastMiniGopBFrame = true;
+    list[bframes]->m_lowres.leadingBframes = bframes;
+    m_lastNonB = &list[bframes]->m_lowres;
+    m_lastNonBFrame = list[bframes];
+
+    if (p.bBPyramid && bframes > 1 && !brefs)
+        placeBref(list, 0, bframes, bframes + 1, &brefs);
+
+    /* costs RateControl will ask for (slicetype.cpp:2378-2427) */
+    if (p.rc.rateControlMode != 1 /* X265_RC_CQP */)
+    {
+        int p0, p1, b;
+        if (!maxSearch)
+            for (int i = 0; i <= bframes; i++) { frames[i + 1] = &list[i]->m_lowres; fr[i + 1] = list[i]; }
+        p1 = b = bframes + 1;
+        p0 = isTypeI(frames[bframes + 1]->sliceType) ? b : 0;
+        singleCost(frames, p0, p1, b);
+        if (bframes)
+        {
+            p0 = 0;
+            bool isp0available = frames[bframes + 1]->sliceType != TYPE_IDR;
+            for (b = 1; b <= bframes; b++)
+            {
+                if (!isp0available) p0 = b;
+                if (frames[b]->sliceType == TYPE_B)
+                    for (p1 = b; frames[p1]->sliceType == TYPE_B; p1++) ;
+                else
+                    p1 = bframes + 1;
+                singleCost(frames, p0, p1, b);
+                if (frames[b]->sliceType == TYPE_BREF) { p0 = b; isp0available = true; }
+            }
+        }
+    }
+    if (m_failed) return;
+
+    /* move the mini-GOP to the output queue in coded order (:2429-2472) */
+    int64_t pts[BFRAME_MAX + 1];
+    for (int i = 0; i <= bframes; i++)
+    {
+        pts[i] = m_inputQueue.front()->m_pts;
+        m_inputQueue.pop_front();
+        maxSearch--;
+    }
+    int idx = 0;
+    list[bframes]->m_reorderedPts = pts[idx++];
+    m_outputQueue.push_back(list[bframes]);
+    if (brefs)
+        for (int i = 0; i < bframes; i++)
+            if (list[i]->m_lowres.sliceType == TYPE_BREF)
+            {
+                list[i]->m_reorderedPts = pts[idx++];
+                m_outputQueue.push_back(list[i]);
+            }
+    for (int i = 0; i < bframes; i++)
+        if (list[i]->m_lowres.sliceType != TYPE_BREF)
+        {
+            list[i]->m_reorderedPts = pts[idx++];
+            m_outputQueue.push_back(list[i]);
+        }
+
+    /* keyframe re-analysis for cuTree / VBV (:2475-2504) */
+    bool isKeyFrameAnalyse = p.rc.cuTree || (p.rc.vbvBufferSize && p.lookaheadDepth);
+    if (isKeyFrameAnalyse && isTypeI(m_lastNonB->sliceType))
+    {
+        memset(frames, 0, sizeof(frames)); memset(fr, 0, sizeof(fr));
+        frames[0] = m_lastNonB; fr[0] = m_lastNonBFrame;
+        for (j = 0; j < maxSearch && j < (int)m_inputQueue.size(); j++)
+        {
+            frames[j + 1] = &m_inputQueue[j]->m_lowres;
+            fr[j + 1] = m_inputQueue[j];
+        }
+        frames[j + 1] = NULL;
+        slicetypeAnalyse(frames, fr, true);
+    }
+}
+
+/* slicetype.cpp:2603-2919 */
+void Lookahead::slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe)
+{
+    const LookaheadParam& p = m_param;
+    int numFrames, origNumFrames, keyintLimit, framecnt;
+    int maxSearch = std::min(p.lookaheadDepth, (int)LOOKAHEAD_MAX);
+    int cuCount = m_8x8Blocks;
+    int resetStart;
+    bool bIsVbvLookahead = p.rc.vbvBufferSize && p.lookaheadDepth;
+    (void)fr;
+
+    for (framecnt = 0; framecnt < maxSearch; framecnt++)
+    {
+        Lowres* fenc = frames[framecnt + 1];
+        if (!fenc || fenc->sliceType != TYPE_AUTO)
+            break;
+    }
+    if (!framecnt)
+    {
+        if (p.rc.cuTree)
+            cuTree(frames, 0, bKeyframe);
+        return;
+    }
+    frames[framecnt + 1] = NULL;
+
+    int keyFrameLimit = p.keyframeMax + m_lastKeyframe - frames[0]->frameNum - 1;
+    keyintLimit = keyFrameLimit;
+    origNumFrames = numFrames = p.bIntraRefresh ? framecnt : std::min(framecnt, keyintLimit);
+    if (bIsVbvLookahead)
+        numFrames = framecnt;
+    else if (p.bOpenGOP && numFrames < framecnt)
+        numFrames++;
+    else if (numFrames == 0)
+    {
+        frames[1]->sliceType = TYPE_I;
+        return;
+    }
+
+    if (m_bBatchMotionSearch)
+    {
+        /* the reference's thread-pool batches (:2668-2736); here they only fix the order of first
+         * touch, the work itself was done by speculate() */
+        for (int b = 2; b < numFrames; b++)
+            for (int i = 1; i <= p.bframes + 1; i++)
+            {
+                int p0 = b - i;
+                if (p0 < 0) continue;
+                if (frames[b]->mvStore[0][i] >= 0) continue;
+                int p1 = b + i;
+                if (p1 >= numFrames || frames[b]->mvStore[1][i] >= 0)
+                    p1 = b;
+                estimateFrameCost(frames, p0, p1, b, false);
+            }
+        m_bBatchMotionSearch &= p.poolWorkers >= 4;
+        if (m_bBatchFrameCosts)
+        {
+            for (int b = 2; b < numFrames; b++)
+                for (int i = 1; i <= p.bframes + 1; i++)
+                {
+                    if (b < i) continue;
+                    if (frames[b]->mvStore[0][i] < 0) continue;
+                    int p0 = b - i;
+                    for (int jj = 0; jj <= p.bframes; jj++)
+                    {
+                        int p1 = b + jj;
+                        if (p1 >= numFrames) break;
+                        if (jj && frames[b]->mvStore[1][jj] < 0) continue;
+                        if (frames[b]->costEst[i][jj] >= 0) continue;
+                        estimateFrameCost(frames, p0, p1, b, false);
+                    }
+                }
+            m_bBatchFrameCosts &= p.poolWorkers > 12;
+        }
+    }
+
+    int numBFrames = 0, numAnalyzed = numFrames;
+    bool isScenecut = scenecut(frames, 0, 1, true, origNumFrames);
+    if (p.scenecutThreshold && isScenecut)
+    {
+        frames[1]->sliceType = TYPE_I;
+        return;
+    }
+    if (p.bframes)
+    {
+        if (p.bFrameAdaptive == B_ADAPT_TRELLIS)
+        {
+            if (numFrames > 1)
+            {
+                char best_paths[BFRAME_MAX + 1][LOOKAHEAD_MAX + 1];
+                memset(best_paths, 0, sizeof(best_paths));
+                best_paths[1][0] = 'P';
+                int best_path_index = numFrames % (BFRAME_MAX + 1);
+                for (int j = 2; j <= numFrames; j++)
+                    slicetypePath(frames, j, best_paths);
+                numBFrames = (int)strspn(best_paths[best_path_index], "B");
+                for (int j = 1; j < numFrames; j++)
+                    frames[j]->sliceType = best_paths[best_path_index][j - 1] == 'B' ? TYPE_B : TYPE_P;
+            }
+            frames[numFrames]->sliceType = TYPE_P;
+        }
+        else if (p.bFrameAdaptive == B_ADAPT_FAST)
+        {
+            int64_t cost1p0, cost2p0, cost1b1, cost2p1;
+            for (int i = 0; i <= numFrames - 2;)
+            {
+                cost2p1 = singleCost(frames, i + 0, i + 2, i + 2, true);
+                if (frames[i + 2]->intraMbs[2] > cuCount / 2)
+                {
+                    frames[i + 1]->sliceType = TYPE_P;
+                    frames[i + 2]->sliceType = TYPE_P;
+                    i += 2;
+                    continue;
+                }
+                cost1b1 = singleCost(frames, i + 0, i + 2, i + 1);
+                cost1p0 = singleCost(frames, i + 0, i + 1, i + 1);
+                cost2p0 = singleCost(frames, i + 1, i + 2, i + 2);
+                if (cost1p0 + cost2p0 < cost1b1 + cost2p1)
+                {
+                    frames[i + 1]->sliceType = TYPE_P;
+                    i += 1;
+                    continue;
+                }
+                frames[i + 1]->sliceType = TYPE_B;
+                int j;
+                for (j = i + 2; j <= std::min(i + p.bframes, numFrames - 1); j++)
+                {
+                    int64_t pthresh = std::max(300 - (50 - p.bFrameBias) * (j - i - 1), 300 / 10);
+                    int64_t pcost = singleCost(frames, i + 0, j + 1, j + 1, true);
+                    if (pcost > pthresh * cuCount || frames[j + 1]->intraMbs[j - i + 1] > cuCount / 3)
+                        break;
+                    frames[j]->sliceType = TYPE_B;
+                }
+                frames[j]->sliceType = TYPE_P;
+                i = j;
+            }
+            frames[numFrames]->sliceType = TYPE_P;
+            numBFrames = 0;
+            while (numBFrames < numFrames && frames[numBFrames + 1]->sliceType == TYPE_B)
+                numBFrames++;
+        }
+        else
+        {
+            numBFrames = std::min(numFrames - 1, p.bframes);
+            for (int j = 1; j < numFrames; j++)
+                frames[j]->sliceType = (j % (numBFrames + 1)) ? TYPE_B : TYPE_P;
+            frames[numFrames]->sliceType = TYPE_P;
+        }
+        /* scenecut check on the first mini-GOP (:2868-2880) */
+        for (int j = 1; j < numBFrames + 1; j++)
+            if (scenecut(frames, j, j + 1, false, origNumFrames))
+            {
+                frames[j]->sliceType = TYPE_P;
+                numAnalyzed = j;
+                break;
+            }
+        resetStart = bKeyframe ? 1 : std::min(numBFrames + 2, numAnalyzed + 1);
+    }
+    else
+    {
+        for (int j = 1; j <= numFrames; j++)
+            frames[j]->sliceType = TYPE_P;
+        resetStart = bKeyframe ? 1 : 2;
+    }
+
+    if (p.rc.cuTree)
+        cuTree(frames, std::min(numFrames, p.keyframeMax), bKeyframe);
+
+    if (!p.bIntraRefresh)
+        for (int j = keyintLimit + 1; j <= numFrames; j += p.keyframeMax)
+        {
+            frames[j]->sliceType = TYPE_I;
+            resetStart = std::min(resetStart, j + 1);
+        }
+
+    if (bIsVbvLookahead)
+        vbvLookahead(frames, numFrames, bKeyframe);
+    int maxp1 = std::min(p.bframes + 1, origNumFrames);
+    for (int j = resetStart; j <= numFrames; j++)
+    {
+        frames[j]->sliceType = TYPE_AUTO;
+        if (j <= maxp1 && frames[j]->bScenecut && m_isSceneTransition)
+            m_isSceneTransition = false;
+    }
+}
+
+/* slicetype.cpp:2921-3014 */
+bool Lookahead::scenecut(Lowres** frames, int p0, int p1, bool bRealScenecut, int numFrames)
+{
+    if (bRealScenecut && m_param.bframes)
+    {
+        int origmaxp1 = p0 + 1 + m_param.bframes;
+        int maxp1 = std::min(origmaxp1, numFrames);
+        bool fluctuate = false, noScenecuts = false;
+        int64_t avgSatdCost = 0;
+        if (frames[p0]->costEst[p1 - p0][0] > -1)
+            avgSatdCost = frames[p0]->costEst[p1 - p0][0];
+        int cnt = 1;
+        for (int cp1 = p1; cp1 <= maxp1; cp1++)
+        {
+            if (!scenecutInternal(frames, p0, cp1, false))
+            {
+                for (int i = cp1; i > p0; i--)
+                {
+                    frames[i]->bScenecut = false;
+                    noScenecuts = false;
+                }
+            }
+            else if (scenecutInternal(frames, cp1 - 1, cp1, false))
+            {
+                frames[cp1]->bScenecut = true;
+                noScenecuts = true;
+            }
+            avgSatdCost += frames[cp1]->costEst[cp1 - p0][0];
+            cnt++;
+        }
+        if (noScenecuts)
+        {
+            fluctuate = false;
+            avgSatdCost /= cnt;
+            for (int i = p1; i <= maxp1; i++)
+            {
+                int64_t curCost = frames[i]->costEst[i - p0][0];
+                int64_t prevCost = frames[i - 1]->costEst[i - 1 - p0][0];
+                if (fabs((double)(curCost - avgSatdCost)) > 0.1 * avgSatdCost ||
+                    fabs((double)(curCost - prevCost)) > 0.1 * prevCost)
+                {
+                    fluctuate = true;
+                    if (!m_isSceneTransition && frames[i]->bScenecut)
+                    {
+                        m_isSceneTransition = true;
+                        for (int j = i + 1; j <= maxp1; j++)
+                            frames[j]->bScenecut = false;
+                        break;
+                    }
+                }
+                frames[i]->bScenecut = false;
+            }
+        }
+        if (!fluctuate && !noScenecuts)
+            m_isSceneTransition = false;
+    }
+    if (!frames[p1]->bScenecut)
+        return false;
+    return scenecutInternal(frames, p0, p1, bRealScenecut);
+}
+
+/* slicetype.cpp:3016-3055 */
+bool Lookahead::scenecutInternal(Lowres** frames, int p0, int p1, bool bRealScenecut)
+{
+    Lowres* frame = frames[p1];
+    singleCost(frames, p0, p1, p1);
+    int64_t icost = frame->costEst[0][0];
+    int64_t pcost = frame->costEst[p1 - p0][0];
+    int gopSize = (frame->frameNum - m_lastKeyframe) % m_param.keyframeMax;
+    float threshMax = (float)(m_param.scenecutThreshold / 100.0);
+    float threshMin = (float)(threshMax * 0.25);
+    double bias = m_param.scenecutBias;
+    if (bRealScenecut)
+    {
+        if (m_param.keyframeMin == m_param.keyframeMax)
+            threshMin = threshMax;
+        if (gopSize <= m_param.keyframeMin / 4 || m_param.bIntraRefresh)
+            bias = threshMin / 4;
+        else if (gopSize <= m_param.keyframeMin)
+            bias = threshMin * gopSize / m_param.keyframeMin;
+        else
+            bias = threshMin + (threshMax - threshMin) * (gopSize - m_param.keyframeMin) /
+                   (m_param.keyframeMax - m_param.keyframeMin);
+    }
+    return pcost >= (1.0 - bias) * icost;
+}
+
+/* slicetype.cpp:3218-3245 */
+void Lookahead::slicetypePath(Lowres** frames, int length, char (*best_paths)[LOOKAHEAD_MAX + 1])
+{
+    char paths[2][LOOKAHEAD_MAX + 1];
+    int num_paths = std::min(m_param.bframes + 1, length);
+    int64_t best_cost = 1LL << 62;
+    int idx = 0;
+    for (int path = 0; path < num_paths; path++)
+    {
+        int len = length - (path + 1);
+        memcpy(paths[idx], best_paths[len % (BFRAME_MAX + 1)], len);
+        memset(paths[idx] + len, 'B', path);
+        strcpy(paths[idx] + len + path, "P");
+        int64_t cost = slicetypePathCost(frames, paths[idx], best_cost);
+        if (cost < best_cost)
+        {
+            best_cost = cost;
+            idx ^= 1;
+        }
+    }
+    memcpy(best_paths[length % (BFRAME_MAX + 1)], paths[idx ^ 1], length);
+}
+
+/* slicetype.cpp:3268-3313 */
+int64_t Lookahead::slicetypePathCost(Lowres** frames, char* path, int64_t threshold)
+{
+    int64_t cost = 0;
+    int loc = 1, cur_p = 0;
+    path--;
+    while (path[loc])
+    {
+        int next_p = loc;
+        while (path[next_p] != 'P')
+            next_p++;
+        cost += singleCost(frames, cur_p, next_p, next_p);
+        if (cost > threshold)
+            break;
+        if (m_param.bBPyramid && next_p - cur_p > 2)
+        {
+            int middle = cur_p + (next_p - cur_p) / 2;
+            cost += singleCost(frames, cur_p, next_p, middle);
+            for (int next_b = loc; next_b < middle && cost < threshold; next_b++)
+                cost += singleCost(frames, cur_p, middle, next_b);
+            for (int next_b = middle + 1; next_b < next_p && cost < threshold; next_b++)
+                cost += singleCost(frames, middle, next_p, next_b);
+        }
+        else
+        {
+            for (int next_b = loc; next_b < next_p && cost < threshold; next_b++)
+                cost += singleCost(frames, cur_p, next_p, next_b);
+        }
+        loc = next_p + 1;
+        cur_p = next_p;
+    }
+    return cost;
+}
+
+/* -------------------------------------------------------------------------------------------
+ * cuTree (slicetype.cpp:3399-3500) -- the chain walk is host logic, each step is a GPU launch
+ * ------------------------------------------------------------------------------------------- */
+
+void Lookahead::cuTree(Lowres** frames, int numframes, bool bIntra)
+{
+    const LookaheadParam& p = m_param;
+    int idx = !bIntra;
+    int lastnonb, curnonb = 1;
+    int bframes = 0;
+
+    double totalDuration = 0.0;
+    for (int j = 0; j <= numframes; j++)
+        totalDuration += (double)p.fpsDenom / p.fpsNum;
+    double averageDuration = totalDuration / (numframes + 1);
+
+    int i = numframes;
+    while (i > 0 && frames[i]->sliceType == TYPE_B)
+        i--;
+    lastnonb = i;
+
+    if (!p.lookaheadDepth)
+    {
+        fail("cuTree with rc-lookahead 0 is not supported");
+        return;
+    }
+    if (lastnonb < idx)
+        return;
+    check(x265cu_cutree_reset(m_ctx, frames[lastnonb]->slot), "x265cu_cutree_reset");
+
+    while (i-- > idx)
+    {
+        curnonb = i;
+        while (frames[curnonb]->sliceType == TYPE_B && curnonb > 0)
+            curnonb--;
+        if (curnonb < idx)
+            break;
+        singleCost(frames, curnonb, lastnonb, lastnonb);
+        check(x265cu_cutree_reset(m_ctx, frames[curnonb]->slot), "x265cu_cutree_reset");
+        bframes = lastnonb - curnonb - 1;
+        if (p.bBPyramid && bframes > 1)
+        {
+            int middle = (bframes + 1) / 2 + curnonb;
+            singleCost(frames, curnonb, lastnonb, middle);
+            check(x265cu_cutree_reset(m_ctx, frames[middle]->slot), "x265cu_cutree_reset");
+            while (i > curnonb)
+            {
+                int p0 = i > middle ? middle : curnonb;
+                int p1 = i < middle ? middle : lastnonb;
+                if (i != middle)
+                {
+                    singleCost(frames, p0, p1, i);
+                    estimateCUPropagate(frames, averageDuration, p0, p1, i, 0);
+                }
+                i--;
+            }
+            estimateCUPropagate(frames, averageDuration, curnonb, lastnonb, middle, 1);
+        }
+        else
+        {
+            while (i > curnonb)
+            {
+                singleCost(frames, curnonb, lastnonb, i);
+                estimateCUPropagate(frames, averageDuration, curnonb, lastnonb, i, 0);
+                i--;
+            }
+        }
+        estimateCUPropagate(frames, averageDuration, curnonb, lastnonb, lastnonb, 1);
+        lastnonb = curnonb;
+        if (m_failed) return;
+    }
+
+    cuTreeFinish(frames[lastnonb], averageDuration, lastnonb);
+    if (p.bBPyramid && bframes > 1 && !p.rc.vbvBufferSize)
+        cuTreeFinish(frames[lastnonb + (bframes + 1) / 2], averageDuration, 0);
+}
+
+/* slicetype.cpp:3502-3608 */
+void Lookahead::estimateCUPropagate(Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced)
+{
+    const LookaheadParam& p = m_param;
+    int32_t distScaleFactor = (((b - p0) << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
+    int32_t bipredWeight = p.bEnableWeightedBiPred ? 64 - (distScaleFactor >> 2) : 32;
+    double fpsFactor = clipDuration((double)p.fpsDenom / p.fpsNum) / clipDuration(averageDuration);
+    Lowres* fb = frames[b];
+    int cs = fb->costStore[b - p0][p1 - b];
+    int l0 = fb->mvStore[0][b - p0];
+    int l1 = p1 > b ? fb->mvStore[1][p1 - b] : -1;
+    if (cs < 0 || l0 < 0) { fail("cuTree propagate on an estimate that was never computed"); return; }
+    check(x265cu_cutree_propagate(m_ctx, fb->slot, frames[p0]->slot, frames[p1]->slot, cs, l0, l1,
+                                  referenced, bipredWeight, fpsFactor), "x265cu_cutree_propagate");
+    if (p.rc.vbvBufferSize && p.lookaheadDepth && referenced)
+        cuTreeFinish(frames[b], averageDuration, b == p1 ? b - p0 : 0);
+}
+
+/* slicetype.cpp:3750-3798 (non-hevc-aq, qg-size > 8) */
+void Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Distance)
+{
+    const LookaheadParam& p = m_param;
+    int fpsFactor = (int)(clipDuration(averageDuration) / clipDuration((double)p.fpsDenom / p.fpsNum) * 256);
+    double weightdelta = 0.0;
+    if (ref0Distance && frame->weightedCostDelta[ref0Distance - 1] > 0)
+        weightdelta = (1.0 - frame->weightedCostDelta[ref0Distance - 1]);
+    check(x265cu_cutree_finish(m_ctx, frame->slot, fpsFactor, weightdelta, m_cuTreeStrength), "x265cu_cutree_finish");
+}
+
+/* slicetype.cpp:3802-3879 */
+int64_t Lookahead::frameCostRecalculate(Lowres** frames, int p0, int p1, int b)
+{
+    if (frames[b]->sliceType == TYPE_B)
+        return frames[b]->costEstAq[b - p0][p1 - b];
+    int64_t score = 0;
+    int cs = frames[b]->costStore[b - p0][p1 - b];
+    if (cs < 0) { fail("frameCostRecalculate on an estimate that was never computed"); return 0; }
+    check(x265cu_cost_recalc(m_ctx, frames[b]->slot, cs, 1, &score, NULL), "x265cu_cost_recalc");
+    return score;
+}
+
+/* slicetype.cpp:2587-2601 */
+int64_t Lookahead::vbvFrameCost(Lowres** frames, int p0, int p1, int b)
+{
+    int64_t cost = singleCost(frames, p0, p1, b);
+    if (m_param.rc.aqMode)
+    {
+        if (m_param.rc.cuTree)
+            return frameCostRecalculate(frames, p0, p1, b);
+        else
+            return frames[b]->costEstAq[b - p0][p1 - b];
+    }
+    return cost;
+}
+
+/* slicetype.cpp:2510-2585 */
+void Lookahead::vbvLookahead(Lowres** frames, int numFrames, int keyframe)
+{
+    int prevNonB = 0, curNonB = 1, idx = 0;
+    while (curNonB < numFrames && isTypeB(frames[curNonB]->sliceType))
+        curNonB++;
+    int nextNonB = keyframe ? prevNonB : curNonB;
+    int nextB = prevNonB + 1;
+    int nextBRef = 0, curBRef = 0;
+    if (m_param.bBPyramid && curNonB - prevNonB > 1)
+        curBRef = (prevNonB + curNonB + 1) / 2;
+    int miniGopEnd = keyframe ? prevNonB : curNonB;
+    while (curNonB <= numFrames)
+    {
+        if (nextNonB != curNonB)
+        {
+            int p0 = isTypeI(frames[curNonB]->sliceType) ? curNonB : prevNonB;
+            frames[nextNonB]->plannedSatd[idx] = vbvFrameCost(frames, p0, curNonB, curNonB);
+            frames[nextNonB]->plannedType[idx] = frames[curNonB]->sliceType;
+            if (curNonB > miniGopEnd)
+                for (int j = nextB; j < miniGopEnd; j++)
+                {
+                    frames[j]->plannedSatd[frames[j]->indB] = frames[nextNonB]->plannedSatd[idx];
+                    frames[j]->plannedType[frames[j]->indB++] = frames[nextNonB]->plannedType[idx];
+                }
+            idx++;
+        }
+        if (m_param.bBPyramid && curNonB - prevNonB > 1)
+            nextBRef = (prevNonB + curNonB + 1) / 2;
+        for (int i = prevNonB + 1; i < curNonB; i++, idx++)
+        {
+            int64_t satdCost = 0;
+            int type = TYPE_B;
+            if (nextBRef)
+            {
+                if (i == nextBRef)
+                {
+                    satdCost = vbvFrameCost(frames, prevNonB, curNonB, nextBRef);
+                    type = TYPE_BREF;
+                }
+                else if (i < nextBRef)
+                    satdCost = vbvFrameCost(frames, prevNonB, nextBRef, i);
+                else
+                    satdCost = vbvFrameCost(frames, nextBRef, curNonB, i);
+            }
+            else
+                satdCost = vbvFrameCost(frames, prevNonB, curNonB, i);
+            frames[nextNonB]->plannedSatd[idx] = satdCost;
+            frames[nextNonB]->plannedType[idx] = type;
+            for (int j = nextB; j < miniGopEnd; j++)
+            {
+                if (curBRef && curBRef == i)
+                    break;
+                if (j >= i && j != nextBRef)
+                    continue;
+                frames[j]->plannedSatd[frames[j]->indB] = satdCost;
+                frames[j]->plannedType[frames[j]->indB++] = type;
+            }
+        }
+        prevNonB = curNonB;
+        curNonB++;
+        while (curNonB <= numFrames && isTypeB(frames[curNonB]->sliceType))
+            curNonB++;
+    }
+    frames[nextNonB]->plannedType[idx] = TYPE_AUTO;
+}
+
+/* slicetype.cpp:1327-1386 (the VBV row aggregation of :1387-1436 needs FrameData and stays
+ * with the encoder; it reads the arrays fetchCosts/fetchFrame mirror) */
+void Lookahead::getEstimatedPictureCost(Frame* cur, Frame* ref0, Frame* ref1)
+{
+    Lowres* frames[2 * (BFRAME_MAX + 2) + 2];
+    memset(frames, 0, sizeof(frames));
+    int p0 = 0, p1, b;
+    int type = cur->m_lowres.sliceType;
+    if (isTypeI(type))
+    {
+        frames[0] = &cur->m_lowres;
+        b = p1 = 0;
+    }
+    else if (type == TYPE_P)
+    {
+        if (!ref0) return;
+        b = p1 = cur->m_poc - ref0->m_poc;
+        frames[0] = &ref0->m_lowres;
+        frames[b] = &cur->m_lowres;
+    }
+    else
+    {
+        if (!ref0 || !ref1) return;
+        b = cur->m_poc - ref0->m_poc;
+        p1 = b + ref1->m_poc - cur->m_poc;
+        frames[0] = &ref0->m_lowres;
+        frames[b] = &cur->m_lowres;
+        frames[p1] = &ref1->m_lowres;
+    }
+    if (m_param.rc.cuTree)
+        cur->m_lowres.satdCost = frameCostRecalculate(frames, p0, p1, b);
+    else if (m_param.rc.aqMode)
+        cur->m_lowres.satdCost = cur->m_lowres.costEstAq[b - p0][p1 - b];
+    else
+        cur->m_lowres.satdCost = cur->m_lowres.costEst[b - p0][p1 - b];
+}
+
+/* -------------------------------------------------------------------------------------------
+ * host mirrors
+ * ------------------------------------------------------------------------------------------- */
+
+bool Lookahead::fetchMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t* mvCosts)
+{
+    int store = f->m_lowres.mvStore[list][dist];
+    if (store < 0)
+    {
+        if (mvXY) mvXY[0] = 0x7FFF;      /* the reference's "not searched" sentinel, lowres.cpp:355-359 */
+        return false;
+    }
+    return check(x265cu_fetch_mvs(m_ctx, f->m_lowres.slot, store, mvXY, mvCosts), "x265cu_fetch_mvs");
+}
+
+bool Lookahead::fetchCosts(Frame* f, int d0, int d1, uint16_t* lowresCosts, int32_t* rowSatds)
+{
+    int cs = f->m_lowres.costStore[d0][d1];
+    if (cs < 0)
+    {
+        if (rowSatds) rowSatds[0] = -1;
+        return false;
+    }
+    if (d0 == 0 && d1 == 0)
+    {
+        x265cu_frame_out o;
+        memset(&o, 0, sizeof(o));
+        o.lowres_costs00 = lowresCosts; o.row_satds00 = rowSatds;
+        return check(x265cu_fetch_frame(m_ctx, f->m_lowres.slot, &o), "x265cu_fetch_frame");
+    }
+    return check(x265cu_fetch_costs(m_ctx, f->m_lowres.slot, cs, lowresCosts, rowSatds), "x265cu_fetch_costs");
+}
+
+bool Lookahead::fetchFrame(Frame* f, const x265cu_frame_out* out)
+{
+    return check(x265cu_fetch_frame(m_ctx, f->m_lowres.slot, out), "x265cu_fetch_frame");
+}
+
+} // namespace x265cu

@@ -1,0 +1,207 @@
+/* lookahead.h -- host side of the B200 lookahead, above the C ABI in include/x265cu.h.
+ *
+ * Mirrors the reference's `class Lookahead` (source/encoder/slicetype.h:151-259): same public
+ * method names, argument meaning and error behaviour (bool returns, no exceptions), and the
+ * same `Lowres` output fields (source/common/lowres.h:171-263) that RateControl / Analysis /
+ * weightPrediction consume.  All decision logic (queues, scenecut, B-adapt, keyframe rules,
+ * cuTree chain walk) runs here on the host as scalar code; every pixel / block operation is a
+ * batch of jobs sent to the GPU engine (libx265cu.so).  There is no CPU path for those jobs.
+ *
+ * Difference in mechanism, not in results: the reference computes motion searches and frame
+ * costs on demand (or in thread-pool batches).  Here they are computed eagerly, in large GPU
+ * batches, as soon as the frames involved are resident ("speculation"), and PUBLISHED into the
+ * Lowres view in exactly the order the reference's control flow would have computed them.  An L0
+ * search has two variants (run inside a P estimate or inside a B estimate, which differ by the
+ * zero-MV skip rule, slicetype.cpp:4165-4181); both are kept on the device and the first touch
+ * selects the one the reference would hold.
+ */
+#ifndef X265CU_LOOKAHEAD_H
+#define X265CU_LOOKAHEAD_H
+
+#include <stdint.h>
+#include <deque>
+#include <vector>
+#include "x265cu.h"
+
+namespace x265cu {
+
+enum { TYPE_AUTO = 0, TYPE_IDR = 1, TYPE_I = 2, TYPE_P = 3, TYPE_BREF = 4, TYPE_B = 5 };   /* x265.h:572-577 */
+enum { B_ADAPT_NONE = 0, B_ADAPT_FAST = 1, B_ADAPT_TRELLIS = 2 };                           /* x265.h:558-560 */
+enum { BFRAME_MAX = 16, LOOKAHEAD_MAX = 250 };                                              /* x265.h:569,101 */
+enum { LOWRES_COST_MASK = (1 << 14) - 1, LOWRES_COST_SHIFT = 14 };                          /* slicetype.h:41-42 */
+
+inline bool isTypeI(int t) { return t == TYPE_I || t == TYPE_IDR; }
+inline bool isTypeB(int t) { return t == TYPE_B || t == TYPE_BREF; }
+
+/* The x265_param fields the lookahead reads (same names as source/x265.h). */
+struct LookaheadParam
+{
+    int sourceWidth, sourceHeight, internalBitDepth, maxCUSize;
+    uint32_t fpsNum, fpsDenom;
+    int bframes, lookaheadDepth, bFrameAdaptive, bBPyramid, bFrameBias;
+    int scenecutThreshold; double scenecutBias;   /* bias already divided by 100 (encoder.cpp:3948) */
+    int keyframeMax, keyframeMin, bOpenGOP, bIntraRefresh;
+    int bEnableWeightedPred, bEnableWeightedBiPred;
+    int lookaheadSlices;
+    int maxNumReferences;
+    struct
+    {
+        int aqMode; double aqStrength; int cuTree; double qCompress; int qgSize;
+        int vbvBufferSize, vbvMaxBitrate, rateControlMode;
+    } rc;
+    /* Emulated ThreadPool::m_numWorkers.  The reference's results depend on it only through
+     * m_bBatchMotionSearch / m_bBatchFrameCosts (slicetype.cpp:1024,1033,2693,2733), which decide
+     * in which context an L0 search is first performed.  0 = "no pool" behaviour. */
+    int poolWorkers;
+    int device;          /* CUDA device ordinal */
+    int extraSlots;      /* frames the caller may hold after getDecidedPicture before release */
+    int speculate;       /* 1 (default): eager whole-window batches; 0: on-demand jobs only */
+    int pinHost;         /* page-lock pictures handed to addPicture */
+};
+void lookaheadParamDefault(LookaheadParam* p);   /* x265_param_default + preset medium, param.cpp:164-349 */
+
+class Lookahead;
+
+/* Host view of one frame's lookahead state: the reference's Lowres (common/lowres.h:171-263),
+ * minus pixel planes and big arrays, which stay on the device until fetched. */
+struct Lowres
+{
+    int     frameNum, sliceType, sliceTypeReq, leadingBframes;
+    bool    bScenecut, bKeyframe, bLastMiniGopBFrame, bIsFadeEnd;
+    double  ipCostRatio;
+    int64_t costEst[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    int64_t costEstAq[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    bool    rowSatdsValid[BFRAME_MAX + 2][BFRAME_MAX + 2];   /* rowSatds[i][j][0] != -1 */
+    int     intraMbs[BFRAME_MAX + 2];
+    int64_t satdCost;
+    uint64_t wp_ssd[3], wp_sum[3];
+    double  weightedCostDelta[BFRAME_MAX + 2];
+    int     plannedType[LOOKAHEAD_MAX + 1];
+    int64_t plannedSatd[LOOKAHEAD_MAX + 1];
+    int     indB;
+
+    /* publication state: which device store holds what the reference would hold */
+    int     mvStore[2][BFRAME_MAX + 2];                      /* -1 = lowresMvs[l][d][0].x == 0x7FFF */
+    int     costStore[BFRAME_MAX + 2][BFRAME_MAX + 2];       /* -1 = never computed */
+    /* weightp state per L0 distance: 0 unknown, 1 analysed/no weight, 2 weighted */
+    int     weightState[BFRAME_MAX + 2];
+    int     wScale[BFRAME_MAX + 2], wDenom[BFRAME_MAX + 2], wOffset[BFRAME_MAX + 2];
+
+    /* device-side bookkeeping */
+    int     slot;
+    bool    statsFetched;
+    uint8_t haveSearch[3][BFRAME_MAX + 2];                   /* store kind x dist computed on device */
+    uint8_t haveCost[BFRAME_MAX + 2][BFRAME_MAX + 2][2];     /* cost store computed on device */
+    uint8_t resultFetched[BFRAME_MAX + 2][BFRAME_MAX + 2][2];
+    x265cu_cost_result result[BFRAME_MAX + 2][BFRAME_MAX + 2][2];
+};
+
+struct Frame
+{
+    int      m_poc;
+    int64_t  m_pts, m_reorderedPts;
+    Lowres   m_lowres;
+    bool     m_lowresInit;
+    bool     m_speculated;
+    bool     m_released;      /* caller is done with it */
+    bool     m_inUse;
+    const void* m_planes[3];  /* caller's picture (valid until the frame's upload completed) */
+    int      m_strideY, m_strideC;
+    Lookahead* m_owner;
+};
+
+class Lookahead
+{
+public:
+    explicit Lookahead(const LookaheadParam& param);
+    ~Lookahead();
+
+    /* same surface as the reference (slicetype.h:214-227) */
+    bool    create();
+    void    destroy();
+    void    stopJobs() {}
+    /* the reference takes a Frame the encoder filled; here the picture is handed over directly.
+     * Returns NULL when no frame slot is free (caller holds too many unreleased frames). */
+    Frame*  addPicture(const void* y, const void* u, const void* v, int strideY, int strideC,
+                       int64_t pts, int sliceType);
+    void    flush();
+    Frame*  getDecidedPicture();
+    /* RateControl's entry point (slicetype.cpp:1327-1439).  The reference derives p0/p1 from the
+     * slice's reference lists; the caller passes the POC distances instead (0 = none). */
+    void    getEstimatedPictureCost(Frame* curFrame, Frame* ref0, Frame* ref1);
+    int     findSliceType(int poc);
+    void    releaseFrame(Frame* f);        /* encoder is done with the frame (DPB recycle) */
+
+    /* host mirrors of device-resident Lowres arrays, in the reference's layout */
+    bool    fetchMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t* mvCosts);  /* false + x=0x7FFF if unsearched */
+    bool    fetchCosts(Frame* f, int d0, int d1, uint16_t* lowresCosts, int32_t* rowSatds);
+    bool    fetchFrame(Frame* f, const x265cu_frame_out* out);
+
+    const x265cu_geometry& geometry() const { return m_geom; }
+    x265cu_ctx* engine() { return m_ctx; }
+    const char* lastError() const { return m_error; }
+    bool    ok() const { return !m_failed; }
+
+    LookaheadParam m_param;
+    bool    m_filled;
+    int     m_inputCount;
+
+private:
+    /* reference state (slicetype.h:155-203) */
+    std::deque<Frame*> m_inputQueue, m_outputQueue;
+    Lowres* m_lastNonB; Frame* m_lastNonBFrame;
+    int     m_8x8Width, m_8x8Height, m_8x8Blocks, m_cuCount;
+    int     m_lastKeyframe, m_fullQueueSize;
+    bool    m_isSceneTransition, m_bBatchMotionSearch, m_bBatchFrameCosts, m_bAdaptiveQuant, m_extendGopBoundary;
+    double  m_cuTreeStrength;
+
+    /* engine */
+    x265cu_ctx* m_ctx;
+    x265cu_geometry m_geom;
+    std::vector<uint16_t> m_mvcost;
+    std::vector<Frame*> m_pool;           /* one per slot */
+    std::vector<Frame*> m_resident;       /* frames with live slots, by arrival */
+    int     m_pocNext;
+    bool    m_failed; char m_error[256];
+
+    /* decision logic (same names as the reference) */
+    void    slicetypeDecide();
+    void    slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe);
+    bool    scenecut(Lowres** frames, int p0, int p1, bool bRealScenecut, int numFrames);
+    bool    scenecutInternal(Lowres** frames, int p0, int p1, bool bRealScenecut);
+    void    slicetypePath(Lowres** frames, int length, char (*best_paths)[LOOKAHEAD_MAX + 1]);
+    int64_t slicetypePathCost(Lowres** frames, char* path, int64_t threshold);
+    void    cuTree(Lowres** frames, int numframes, bool bIntra);
+    void    estimateCUPropagate(Lowres** frames, double avgDuration, int p0, int p1, int b, int referenced);
+    void    cuTreeFinish(Lowres* frame, double averageDuration, int ref0Distance);
+    int64_t frameCostRecalculate(Lowres** frames, int p0, int p1, int b);
+    void    vbvLookahead(Lowres** frames, int numFrames, int keyframe);
+    int64_t vbvFrameCost(Lowres** frames, int p0, int p1, int b);
+    void    placeBref(Frame** list, int start, int end, int num, int* brefs);
+    void    compCostBref(Lowres** frames, int start, int end, int num);
+
+    /* CostEstimateGroup (slicetype.h:261-326) folded in */
+    int64_t singleCost(Lowres** frames, int p0, int p1, int b, bool bIntraPenalty = false);
+    int64_t estimateFrameCost(Lowres** frames, int p0, int p1, int b, bool bIntraPenalty);
+
+    /* device orchestration */
+    void    preLookahead(const std::vector<Frame*>& fr);
+    void    speculate();
+    void    weightsAnalyseBatch(const std::vector<std::pair<Lowres*, Lowres*> >& pairs);
+    void    ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind);
+    void    fetchResults(const std::vector<Lowres*>& who);
+    Frame*  frameOfPoc(int poc);
+    void    recycle();
+    void    initLowres(Frame* f, int poc);
+    bool    check(int status, const char* what);
+    void    fail(const char* what);
+
+    std::vector<x265cu_search_job> m_searchJobs;
+    std::vector<x265cu_cost_job>   m_costJobs;
+};
+
+void buildMvCostTable(std::vector<uint16_t>& table, int half, int depth);
+int  lookaheadLambda(int depth);
+
+} // namespace x265cu
+#endif
