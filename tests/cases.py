@@ -1,0 +1,82 @@
+"""Shared parity cases: (name, depth, width, height, frames, synth kwargs, lookahead kwargs in the
+reference harness' vocabulary)."""
+
+CASES = [
+    ("base8", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10)),
+    ("base10", 10, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10)),
+    ("pool4", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, poolThreads=4)),
+    ("pool16", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, poolThreads=16)),
+    ("pool16_10bit", 10, 320, 192, 60, dict(cuts=(30,)), dict(bframes=4, lookaheadDepth=20, poolThreads=16)),
+    ("nob", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=0, lookaheadDepth=10)),
+    ("b8", 8, 320, 192, 60, dict(cuts=(33,)), dict(bframes=8, lookaheadDepth=25)),
+    ("badapt1", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=4, lookaheadDepth=12, bFrameAdaptive=1)),
+    ("badapt0", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=4, lookaheadDepth=12, bFrameAdaptive=0)),
+    ("nocutree", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0)),
+    ("plain", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0, aqMode=0, weightp=0)),
+    ("aq1", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, aqMode=1)),
+    ("aq3", 10, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, aqMode=3)),
+    ("closedgop", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, bBPyramid=0, bOpenGOP=0, keyframeMax=24, keyframeMin=2)),
+    ("fade8", 8, 320, 192, 60, dict(cuts=(), fades=[(20, 12, 0.3), (40, 10, 1.0)]), dict(bframes=4, lookaheadDepth=12)),
+    ("fade10", 10, 320, 192, 60, dict(cuts=(), fades=[(20, 12, 0.3), (40, 10, 1.0)]), dict(bframes=4, lookaheadDepth=12)),
+    ("static", 8, 320, 192, 40, dict(cuts=(), static=True, noise=0), dict(bframes=4, lookaheadDepth=12)),
+    ("static_noise", 8, 320, 192, 40, dict(cuts=(), static=True, noise=1), dict(bframes=4, lookaheadDepth=12)),
+    ("static_pool", 8, 320, 192, 40, dict(cuts=(), static=True, noise=1), dict(bframes=4, lookaheadDepth=12, poolThreads=16)),
+    ("flash", 8, 320, 192, 50, dict(cuts=(25,), flashes=[(10, 1), (35, 2)]), dict(bframes=4, lookaheadDepth=12)),
+    ("weightb", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, weightb=1)),
+    ("ragged", 8, 328, 184, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10)),
+    ("small", 8, 176, 144, 30, dict(cuts=(15,)), dict(bframes=3, lookaheadDepth=10)),
+    ("vbv", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
+    ("sd", 8, 640, 360, 50, dict(cuts=(25,)), dict(bframes=4, lookaheadDepth=20)),
+]
+
+# subset small enough to commit as golden fixtures and to run in the quick CPU suite
+GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob"]
+
+REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive="bFrameAdaptive", bBPyramid="bBPyramid",
+              scenecutThreshold="scenecutThreshold", keyframeMax="keyframeMax", keyframeMin="keyframeMin",
+              bOpenGOP="bOpenGOP", aqMode="aqMode", aqStrength="aqStrength", cuTree="cuTree", qCompress="qCompress",
+              weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
+              scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
+              poolThreads="poolWorkers")
+
+
+def la_kwargs(refkw):
+    kw = {REF2LA[k]: v for k, v in refkw.items() if k in REF2LA}
+    if "bitrate" in refkw:
+        kw["rateControlMode"] = 0
+    return kw
+
+
+def get_case(name):
+    for c in CASES:
+        if c[0] == name:
+            return c
+    raise KeyError(name)
+
+
+def make_seq(synth, case):
+    name, depth, w, h, n, skw, _ = case
+    return synth.SynthSequence(w, h, depth=depth, seed=1, **skw)
+
+
+def run_reference(refbind, synth, case, planes=True):
+    name, depth, w, h, n, skw, rkw = case
+    seq = make_seq(synth, case)
+    ref = refbind.RefLookahead(w, h, depth=depth, dumpPlanes=1 if planes else 0, **rkw)
+    for i in range(n):
+        ref.put(*seq.frame(i))
+    ref.flush()
+    out = ref.frames()
+    ref.close()
+    return out
+
+
+def run_ours(pkg, synth, case, lib_path=None, planes=True, **extra):
+    name, depth, w, h, n, skw, rkw = case
+    seq = make_seq(synth, case)
+    kw = la_kwargs(rkw)
+    kw.update(extra)
+    la = pkg.Lookahead(w, h, depth=depth, lib_path=lib_path, **kw)
+    out = pkg.run_sequence(la, (seq.frame(i) for i in range(n)), planes=planes)
+    la.close()
+    return out

@@ -1,0 +1,117 @@
+"""GPU suite (-m gpu): the CUDA lookahead, called through the C ABI / the host Lookahead, against
+(1) the C oracle at primitive level, (2) the committed golden fixtures of the unmodified reference,
+(3) the live reference build (oracle/_ref) when its libraries travelled with the snapshot, and
+(4) the oracle-backed host pipeline for every configuration, incl. full-size property checks."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import compare
+import golden_io
+import refbind
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cmp(want, got, case, planes=True):
+    rkw = case[6]
+    return compare.compare_runs(want, got, check_planes=planes, cutree=rkw.get("cuTree", 1), weightp=rkw.get("weightp", 1))
+
+
+def _sim(simdir, depth):
+    return os.path.join(simdir, "libx265la_sim%d.so" % depth)
+
+
+def _as_ref_layout(frames):
+    for f in frames:
+        f["mvs"][~f["searched"]] = 0
+        f["mvs"][~f["searched"], 0, 0] = 0x7FFF
+    return frames
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_block_metrics_vs_oracle(depth, pkg, simdir):
+    """T1: SAD/SATD kernels on the reference's pixelharness recipe (random / min / max buffers)"""
+    la = pkg.Lookahead(320, 192, depth=depth)
+    eng = pkg.load_engine()
+    eng.x265cu_debug_block_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    orc = C.CDLL(os.path.join(simdir, "liboracle%d.so" % depth))
+    dt = np.uint8 if depth == 8 else np.uint16
+    maxv = (1 << depth) - 1
+    rng = np.random.default_rng(5)
+    n = 4096
+    a = rng.integers(0, maxv + 1, (n, 64)).astype(dt)
+    b = rng.integers(0, maxv + 1, (n, 64)).astype(dt)
+    a[:64] = 0; b[:64] = maxv; a[64:128] = maxv; b[64:128] = 0; b[128:192] = a[128:192]
+    b[192:1024] = np.clip(a[192:1024].astype(np.int64) + rng.integers(-3, 4, (832, 64)), 0, maxv).astype(dt)
+    sad = np.zeros(n, np.int32); satd = np.zeros(n, np.int32)
+    assert eng.x265cu_debug_block_metrics(la.engine(), a.ctypes.data, b.ctypes.data, n, sad.ctypes.data, satd.ctypes.data) == 0
+    for i in range(n):
+        pa = a[i].ctypes.data_as(C.c_void_p); pb = b[i].ctypes.data_as(C.c_void_p)
+        assert sad[i] == orc.or_sad8x8(pa, 8, pb, 8), i
+        assert satd[i] == orc.or_satd8x8(pa, 8, pb, 8), i
+    la.close()
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_cuda_pipeline_matches_golden(name, pkg, synth):
+    case = cases.get_case(name)
+    want = golden_io.load(name)
+    got = cases.run_ours(pkg, synth, case, planes=True)
+    bad = _cmp(want, got, case, planes=False)
+    assert not bad, "\n".join(bad[:10])
+    for w, g in zip(want, got):
+        assert w["planesum"] == golden_io.planesum(g["planes"]), "lowres planes differ at poc %d" % w["poc"]
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.CASES])
+def test_cuda_pipeline_matches_reference_or_oracle(name, pkg, synth, simdir):
+    case = cases.get_case(name)
+    if refbind.available(case[1]):
+        want = cases.run_reference(refbind, synth, case)
+    else:
+        want = _as_ref_layout(cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, case[1])))
+    got = cases.run_ours(pkg, synth, case)
+    bad = _cmp(want, got, case)
+    assert not bad, "\n".join(bad[:10])
+
+
+def test_cuda_speculation_off_is_identical(pkg, synth):
+    case = cases.get_case("base8")
+    b = cases.run_ours(pkg, synth, case, speculate=0, planes=False)
+    bad = compare.compare_runs(golden_io.load("base8"), b, check_planes=False)
+    assert not bad, "\n".join(bad[:10])
+
+
+@pytest.mark.parametrize("depth,w,h", [(8, 1920, 1080), (10, 3840, 2160)])
+def test_full_size_properties(depth, w, h, pkg, synth, simdir):
+    """BASELINE sizes: oracle spot-check of whole frames plus size-independent properties
+    (determinism across runs and across speculation on/off; intra cost independent of neighbours)."""
+    n = 14
+    seq = synth.SynthSequence(w, h, depth=depth, seed=2, cuts=(7,), n_rects=4)
+    frames = [seq.frame(i) for i in range(n)]
+    kw = dict(bframes=3, lookaheadDepth=8)
+
+    def run(**extra):
+        la = pkg.Lookahead(w, h, depth=depth, **dict(kw, **extra))
+        out = pkg.run_sequence(la, iter(frames), planes=False)
+        la.close()
+        return out
+    a = run()
+    b = run(speculate=0)
+    assert [f["sliceType"] for f in a] == [f["sliceType"] for f in b]
+    for x, y in zip(a, b):
+        assert np.array_equal(x["costEst"], y["costEst"]) and np.array_equal(x["costEstAq"], y["costEstAq"])
+        assert np.array_equal(x["intraCost"], y["intraCost"]) and np.array_equal(x["mvs"], y["mvs"])
+        assert np.array_equal(x["qpCuTreeOffset"], y["qpCuTreeOffset"])
+    # full-size oracle check through the sim engine (the C oracle finishes 14 frames in seconds at 1080p;
+    # at 2160p only when the run is affordable)
+    if w <= 1920:
+        want = _as_ref_layout(pkg.run_sequence(pkg.Lookahead(w, h, depth=depth, lib_path=_sim(simdir, depth), **kw), iter(frames), planes=False))
+        bad = compare.compare_runs(want, a, check_planes=False)
+        assert not bad, "\n".join(bad[:10])

@@ -1,0 +1,133 @@
+"""CPU suite (no GPU): the C oracle + the PRODUCT's host decision logic, run through the CPU
+sim-engine (tests/simengine), must reproduce the unmodified reference bit for bit -- against the
+committed golden fixtures always, and against the live reference build (oracle/_ref) when present."""
+import numpy as np
+import pytest
+
+import cases
+import compare
+import golden_io
+import refbind
+
+
+def _sim(simdir, depth):
+    import os
+    return os.path.join(simdir, "libx265la_sim%d.so" % depth)
+
+
+def _cmp(want, got, case):
+    rkw = case[6]
+    return compare.compare_runs(want, got, check_planes=True, cutree=rkw.get("cuTree", 1), weightp=rkw.get("weightp", 1))
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_sim_pipeline_matches_golden(name, pkg, synth, simdir):
+    case = cases.get_case(name)
+    want = golden_io.load(name)
+    got = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, case[1]), planes=True)
+    bad = _cmp(want, got, case)
+    assert not bad, "\n".join(bad[:10])
+    for w, g in zip(want, got):
+        assert w["planesum"] == golden_io.planesum(g["planes"]), "lowres planes differ at poc %d" % w["poc"]
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.CASES])
+def test_sim_pipeline_matches_live_reference(name, pkg, synth, simdir):
+    case = cases.get_case(name)
+    if not refbind.available(case[1]):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    want = cases.run_reference(refbind, synth, case)
+    got = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, case[1]))
+    bad = _cmp(want, got, case)
+    assert not bad, "\n".join(bad[:10])
+
+
+def test_speculation_off_gives_same_results(pkg, synth, simdir):
+    case = cases.get_case("base8")
+    a = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, 8), speculate=1)
+    b = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, 8), speculate=0)
+    bad = compare.compare_runs(golden_io.load("base8"), b, check_planes=False)
+    assert not bad, "\n".join(bad[:10])
+    for x, y in zip(a, b):
+        assert np.array_equal(x["costEst"], y["costEst"]) and x["sliceType"] == y["sliceType"]
+
+
+def test_coverage_of_special_paths(pkg, synth, simdir):
+    """the fixtures really exercise weightp and the B-frame zero-MV skip rule"""
+    got = cases.run_ours(pkg, synth, cases.get_case("fade8"), lib_path=_sim(simdir, 8), planes=False)
+    assert sum(int(np.sum(g["weightState"] == 2)) for g in got) > 0
+    got = cases.run_ours(pkg, synth, cases.get_case("static_noise"), lib_path=_sim(simdir, 8), planes=False)
+    cheap = sum(int(np.sum((g["mvs"][0, 1:, :, 0] == 0) & (g["mvs"][0, 1:, :, 1] == 0) & (g["mvCosts"][0, 1:] < 64) &
+                           (g["mvCosts"][0, 1:] > 0))) for g in got)
+    assert cheap > 0
+    types = [g["sliceType"] for g in cases.run_ours(pkg, synth, cases.get_case("base8"), lib_path=_sim(simdir, 8), planes=False)]
+    assert 2 in types, "scene cut not detected"
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_mvcost_table_and_lambda(depth):
+    if not refbind.available(depth):
+        pytest.skip("oracle/_ref not built")
+    import ctypes as C, os
+    lib = C.CDLL(os.path.join(os.path.dirname(__file__), "_build", "liboracle%d.so" % depth))
+    n = 20000
+    qp, ref = refbind.mvcost_table(depth, n)
+    tab = np.zeros(2 * n + 1, np.uint16)
+    lib.or_build_mvcost(tab.ctypes.data_as(C.c_void_p), n)
+    assert np.array_equal(tab, ref)
+    assert lib.or_lookahead_lambda() == refbind.load(depth).ref_lookahead_lambda()
+    assert qp == 12 + 6 * (depth - 8)
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_oracle_block_primitives_vs_reference(depth, simdir):
+    """the reference's own pixelharness recipe: random, all-min and all-max buffers"""
+    if not refbind.available(depth):
+        pytest.skip("oracle/_ref not built")
+    import ctypes as C, os
+    lib = C.CDLL(os.path.join(simdir, "liboracle%d.so" % depth))
+    ref = refbind.load(depth)
+    dt = np.uint8 if depth == 8 else np.uint16
+    maxv = (1 << depth) - 1
+    rng = np.random.default_rng(3)
+    bufs = [rng.integers(0, maxv + 1, (64, 64)).astype(dt), np.zeros((64, 64), dt), np.full((64, 64), maxv, dt)]
+    for a in bufs:
+        for b in bufs:
+            for (ox, oy) in ((0, 0), (3, 5), (17, 1)):
+                pa = a[oy:, ox:]; pb = b[1:, 2:]
+                args = (pa.ctypes.data_as(C.c_void_p), 64, pb.ctypes.data_as(C.c_void_p), 64)
+                assert lib.or_sad8x8(*args) == ref.ref_sad8x8(*args)
+                assert lib.or_satd8x8(*args) == ref.ref_satd8x8(*args)
+    lib.or_exp2fix8.argtypes = [C.c_double]
+    for x in np.linspace(-60, 60, 4001):
+        assert lib.or_exp2fix8(float(x)) == ref.ref_exp2fix8(float(x))
+
+
+def test_libraries_export_the_declared_abi():
+    """libx265cu.so loads without a GPU and exports every symbol include/x265cu.h declares"""
+    import ctypes as C, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "x265cu.h")).read()
+    names = sorted(set(re.findall(r"\b(x265cu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    libp = os.path.join(root, "x265-amod_b200", "lib", "libx265cu.so")
+    if not os.path.exists(libp):
+        import __graft_entry__ as ge
+        ge.build_product()
+    lib = C.CDLL(libp)
+    for n in names:
+        assert hasattr(lib, n), n
+    la = C.CDLL(os.path.join(root, "x265-amod_b200", "lib", "libx265la.so"))
+    cap = open(os.path.join(root, "x265-amod_b200", "host", "la_capi.h")).read()
+    for n in sorted(set(re.findall(r"\b(x265la_[a-z0-9_]+)\s*\(", cap))):
+        assert hasattr(la, n), n
+
+
+def test_no_cpu_fallback_without_gpu(pkg):
+    """without a CUDA device the product fails loudly instead of computing on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError) as e:
+        pkg.Lookahead(320, 192, depth=8)
+    assert "no usable CUDA device" in str(e.value) or "x265cu_create" in str(e.value)

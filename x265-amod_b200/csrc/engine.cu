@@ -1,0 +1,739 @@
+/* engine.cu -- libx265cu.so: the C ABI of include/x265cu.h on one B200.
+ *
+ * Host side of the engine: owns the frame slots in HBM, turns job batches into kernel launches on
+ * one CUDA stream, and copies results back.  All arithmetic lives in la_kernels.cuh.  There is no
+ * CPU implementation of any job here: without a usable CUDA device x265cu_create fails.
+ *
+ * HBM layout of one frame slot (one cudaMalloc, 256-byte aligned sections):
+ *   srcY/U/V        packed full-res picture (only needed until K1/K2 ran)
+ *   planes          4 half-pel planes with margins, contiguous, exactly Lowres::buffer[0..3]
+ *   intraCost, intraMode, invQscale, qpAq, qpCuTree, propagate (int32 accumulators), energy
+ *   lowresCosts00, rowSatds00, stats
+ *   mvStores        3*nb x { int packedMv[ncu], int mvCost[ncu] }
+ *   costStores      2*nb*nb x { u16 lowresCosts[ncu], int rowSatds[bh], CostResultDev }
+ */
+#include "x265cu.h"
+#include "la_kernels.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <map>
+#include <new>
+
+using namespace la;
+
+namespace {
+
+struct SlotLayout
+{
+    size_t srcY, srcU, srcV, planes, intraCost, intraMode, invQ, qpAq, qpCuTree, propagate, energy,
+           lowresCosts00, rowSatds00, stats, mvStores, costStores, total;
+    size_t mvStoreStride, costStoreStride, costRowOff, costResOff;
+};
+
+inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+struct x265cu_ctx
+{
+    x265cu_config cfg;
+    Geom g;
+    x265cu_geometry geom;
+    int bpp;
+    SlotLayout lay;
+    cudaStream_t stream;
+    std::vector<char*> slots;
+    unsigned short* d_mvcost;       /* whole table; centre at +mvcost_half */
+    char* d_jobs; size_t jobsCap;   /* device copy of the current job array */
+    int* d_sync; size_t syncCap;    /* ticket counter + per-(job,band) progress */
+    char* d_results; size_t resultsCap;
+    char* h_results; size_t hResultsCap;      /* pinned staging for gathers */
+    std::vector<char*> weightScratch;         /* 4 weighted planes each */
+    x265cu_counters counters;
+    bool profile;
+    double profMs[X265CU_K_COUNT];
+    uint64_t profN[X265CU_K_COUNT];
+    cudaEvent_t ev0, ev1;
+    char err[256];
+};
+
+namespace {
+
+bool cudaOk(x265cu_ctx* c, cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+    return false;
+}
+#define CK(call) do { if (!cudaOk(c, (call), #call)) return X265CU_ERR_CUDA; } while (0)
+
+struct Prof
+{
+    x265cu_ctx* c; int k;
+    Prof(x265cu_ctx* ctx, int kind, int launches) : c(ctx), k(kind)
+    {
+        c->counters.kernel_launches += launches;
+        c->profN[k] += launches;
+        if (c->profile) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~Prof()
+    {
+        if (c->profile)
+        {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            c->profMs[k] += ms;
+        }
+    }
+};
+
+template <typename T> T* slotPtr(x265cu_ctx* c, int slot, size_t off) { return (T*)(c->slots[slot] + off); }
+
+int ensureDev(x265cu_ctx* c, char** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return X265CU_OK;
+    if (*p) { cudaStreamSynchronize(c->stream); cudaFree(*p); *p = NULL; *cap = 0; }
+    size_t n = alignUp(need * 2, 4096);
+    CK(cudaMalloc((void**)p, n));
+    *cap = n;
+    return X265CU_OK;
+}
+
+int ensureHost(x265cu_ctx* c, size_t need)
+{
+    if (c->hResultsCap >= need) return X265CU_OK;
+    if (c->h_results) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_results); c->h_results = NULL; c->hResultsCap = 0; }
+    size_t n = alignUp(need * 2, 4096);
+    CK(cudaMallocHost((void**)&c->h_results, n));
+    c->hResultsCap = n;
+    return X265CU_OK;
+}
+
+bool slotOk(const x265cu_ctx* c, int s) { return s >= 0 && s < (int)c->slots.size(); }
+
+char* mvStorePtr(x265cu_ctx* c, int slot, int store) { return c->slots[slot] + c->lay.mvStores + (size_t)store * c->lay.mvStoreStride; }
+char* costStorePtr(x265cu_ctx* c, int slot, int store) { return c->slots[slot] + c->lay.costStores + (size_t)store * c->lay.costStoreStride; }
+
+/* ---------------------------------------------------------------- typed implementations */
+
+template <typename P>
+int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v, int sy, int sc)
+{
+    const Geom& g = c->g;
+    const SlotLayout& L = c->lay;
+    P* dY = slotPtr<P>(c, slot, L.srcY);
+    P* dU = slotPtr<P>(c, slot, L.srcU);
+    P* dV = slotPtr<P>(c, slot, L.srcV);
+    CK(cudaMemcpy2DAsync(dY, g.picW * sizeof(P), y, (size_t)sy * sizeof(P), g.picW * sizeof(P), g.picH, cudaMemcpyHostToDevice, c->stream));
+    c->counters.h2d_bytes += (uint64_t)g.picW * g.picH * sizeof(P);
+    const bool chroma = u && v;
+    if (chroma && c->cfg.need_aq)
+    {
+        CK(cudaMemcpy2DAsync(dU, g.cW * sizeof(P), u, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpy2DAsync(dV, g.cW * sizeof(P), v, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyHostToDevice, c->stream));
+        c->counters.h2d_bytes += 2ull * g.cW * g.cH * sizeof(P);
+    }
+    /* stats + rowSatds00 start at zero */
+    CK(cudaMemsetAsync(c->slots[slot] + L.rowSatds00, 0, L.stats + sizeof(FrameStatsDev) - L.rowSatds00, c->stream));
+    P* planes = slotPtr<P>(c, slot, L.planes);
+    {
+        Prof pr(c, X265CU_K_LOWRES, 1);
+        dim3 block(256), grid((g.stride / 4 + 255) / 256, g.planeLines);
+        lowres_kernel<P><<<grid, block, 0, c->stream>>>(g, dY, planes);
+    }
+    FrameStatsDev* stats = slotPtr<FrameStatsDev>(c, slot, L.stats);
+    int* invQ = slotPtr<int>(c, slot, L.invQ);
+    if (c->cfg.need_aq)
+    {
+        Prof pr(c, X265CU_K_AQ, 2);
+        unsigned* energy = slotPtr<unsigned>(c, slot, L.energy);
+        aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, c->stream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
+        aq_finish_kernel<<<1, 1024, 0, c->stream>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
+                                                    slotPtr<double>(c, slot, L.qpAq), slotPtr<double>(c, slot, L.qpCuTree), invQ, stats);
+    }
+    {
+        Prof pr(c, X265CU_K_INTRA, 1);
+        intra_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, planes + g.padOffset, c->cfg.need_aq ? invQ : NULL,
+                                                                  slotPtr<int>(c, slot, L.intraCost), slotPtr<unsigned char>(c, slot, L.intraMode),
+                                                                  slotPtr<unsigned short>(c, slot, L.lowresCosts00),
+                                                                  slotPtr<int>(c, slot, L.rowSatds00), stats);
+    }
+    CK(cudaGetLastError());
+    return X265CU_OK;
+}
+
+template <typename P>
+int weightPlanes(x265cu_ctx* c, const P* src, P* dst, int nPlanes, int scale, int denom, int offsetIn)
+{
+    const int correction = 14 - c->g.depth;
+    const int offset = offsetIn << (c->g.depth - 8);
+    const int round = (denom ? 1 << (denom - 1) : 0) << correction;
+    const int shift = denom + correction;
+    const long long n = c->g.planeSize * nPlanes;
+    Prof pr(c, X265CU_K_WEIGHT, 1);
+    weight_planes_kernel<P><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(src, dst, n, scale, round, shift, offset, correction,
+                                                                                (1 << c->g.depth) - 1);
+    CK(cudaGetLastError());
+    return X265CU_OK;
+}
+
+int ensureScratch(x265cu_ctx* c, size_t count)
+{
+    while (c->weightScratch.size() < count)
+    {
+        char* p = NULL;
+        CK(cudaMalloc((void**)&p, (size_t)(4 * c->g.planeSize) * c->bpp + 256));
+        CK(cudaMemsetAsync(p, 0, (size_t)(4 * c->g.planeSize) * c->bpp + 256, c->stream));
+        c->weightScratch.push_back(p);
+    }
+    return X265CU_OK;
+}
+
+template <typename P>
+int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
+{
+    const Geom& g = c->g;
+    const SlotLayout& L = c->lay;
+    std::vector<SearchJobDev<P> > dev(n);
+    /* weighted references: one scratch set per distinct (ref, weight) in this batch */
+    std::map<std::vector<int>, int> wmap;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_search_job& j = jobs[i];
+        if (!slotOk(c, j.fenc_slot) || !slotOk(c, j.ref_slot) || j.store < 0 || j.store >= c->geom.n_mv_stores)
+        { snprintf(c->err, sizeof(c->err), "search job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
+        const P* refBuf = slotPtr<P>(c, j.ref_slot, L.planes);
+        if (j.weighted)
+        {
+            std::vector<int> key(4);
+            key[0] = j.ref_slot; key[1] = j.w_scale; key[2] = j.w_denom; key[3] = j.w_offset;
+            std::map<std::vector<int>, int>::iterator it = wmap.find(key);
+            int idx;
+            if (it == wmap.end())
+            {
+                idx = (int)wmap.size();
+                wmap[key] = idx;
+                int st = ensureScratch(c, idx + 1);
+                if (st) return st;
+                st = weightPlanes<P>(c, refBuf, (P*)c->weightScratch[idx], 4, j.w_scale, j.w_denom, j.w_offset);
+                if (st) return st;
+            }
+            else
+                idx = it->second;
+            refBuf = (const P*)c->weightScratch[idx];
+        }
+        dev[i].fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes) + g.padOffset;
+        dev[i].ref0 = refBuf + g.padOffset;
+        char* st = mvStorePtr(c, j.fenc_slot, j.store);
+        dev[i].mvOut = (int*)st;
+        dev[i].costOut = (int*)st + g.ncu;
+        dev[i].bidir = j.bidir_ctx;
+        dev[i].pad = 0;
+    }
+    const int nbands = (g.bh + LA_BAND_ROWS - 1) / LA_BAND_ROWS;
+    int st = ensureDev(c, &c->d_jobs, &c->jobsCap, n * sizeof(SearchJobDev<P>));
+    if (st) return st;
+    st = ensureDev(c, (char**)&c->d_sync, &c->syncCap, (size_t)(1 + n * nbands) * sizeof(int));
+    if (st) return st;
+    CK(cudaMemcpyAsync(c->d_jobs, &dev[0], n * sizeof(SearchJobDev<P>), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_sync, 0, (size_t)(1 + n * nbands) * sizeof(int), c->stream));
+    {
+        Prof pr(c, X265CU_K_SEARCH, 1);
+        const size_t smem = (size_t)LA_BAND_ROWS * g.bw * sizeof(int);
+        search_kernel<P><<<n * nbands, LA_BAND_ROWS * 8, smem, c->stream>>>(g, (const SearchJobDev<P>*)c->d_jobs, nbands,
+                                                                            c->d_mvcost + c->cfg.mvcost_half, c->d_sync, c->d_sync + 1);
+    }
+    CK(cudaGetLastError());
+    return X265CU_OK;
+}
+
+template <typename P>
+int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
+{
+    const Geom& g = c->g;
+    const SlotLayout& L = c->lay;
+    std::vector<CostJobDev<P> > dev(n);
+    bool anyB = false;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_cost_job& j = jobs[i];
+        if (!slotOk(c, j.b_slot) || !slotOk(c, j.p0_slot) || !slotOk(c, j.p1_slot) || j.out < 2 || j.out >= c->geom.n_cost_stores ||
+            j.l0_store < 0 || j.l0_store >= c->geom.n_mv_stores || j.l1_store >= c->geom.n_mv_stores)
+        { snprintf(c->err, sizeof(c->err), "cost job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
+        CostJobDev<P>& d = dev[i];
+        d.fenc0 = slotPtr<P>(c, j.b_slot, L.planes) + g.padOffset;
+        d.ref0 = slotPtr<P>(c, j.p0_slot, L.planes) + g.padOffset;
+        d.ref1 = j.l1_store >= 0 ? slotPtr<P>(c, j.p1_slot, L.planes) + g.padOffset : NULL;
+        anyB |= j.l1_store >= 0;
+        char* m0 = mvStorePtr(c, j.b_slot, j.l0_store);
+        d.mv0 = (const int*)m0; d.cost0 = (const int*)m0 + g.ncu;
+        if (j.l1_store >= 0)
+        {
+            char* m1 = mvStorePtr(c, j.b_slot, j.l1_store);
+            d.mv1 = (const int*)m1; d.cost1 = (const int*)m1 + g.ncu;
+        }
+        else { d.mv1 = NULL; d.cost1 = NULL; }
+        d.intraCost = slotPtr<int>(c, j.b_slot, L.intraCost);
+        d.invQ = c->cfg.need_aq ? slotPtr<int>(c, j.b_slot, L.invQ) : NULL;
+        char* cs = costStorePtr(c, j.b_slot, j.out);
+        d.lowresCosts = (unsigned short*)cs;
+        d.rowSatds = (int*)(cs + L.costRowOff);
+        d.result = (CostResultDev*)(cs + L.costResOff);
+    }
+    int st = ensureDev(c, &c->d_jobs, &c->jobsCap, n * sizeof(CostJobDev<P>));
+    if (st) return st;
+    CK(cudaMemcpyAsync(c->d_jobs, &dev[0], n * sizeof(CostJobDev<P>), cudaMemcpyHostToDevice, c->stream));
+    {
+        Prof pr(c, X265CU_K_COST, 2);
+        cost_clear_kernel<P><<<n, 256, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs);
+        /* P jobs use one thread per block, B jobs 8 lanes per block; the grid is sized for the larger */
+        dim3 grid(anyB ? (g.ncu + 15) / 16 : (g.ncu + 127) / 128, n);
+        for (int base = 0; base < n; base += 65535)
+        {
+            dim3 gg(grid.x, (unsigned)((n - base) < 65535 ? (n - base) : 65535));
+            cost_kernel<P><<<gg, 128, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs + base);
+        }
+    }
+    CK(cudaGetLastError());
+    return X265CU_OK;
+}
+
+template <typename P>
+int weightCostT(x265cu_ctx* c, const x265cu_wcost_job* jobs, int n, uint32_t* costs)
+{
+    const Geom& g = c->g;
+    const SlotLayout& L = c->lay;
+    int st = ensureDev(c, &c->d_results, &c->resultsCap, n * sizeof(unsigned));
+    if (st) return st;
+    st = ensureHost(c, n * sizeof(unsigned));
+    if (st) return st;
+    CK(cudaMemsetAsync(c->d_results, 0, n * sizeof(unsigned), c->stream));
+    st = ensureScratch(c, 1);
+    if (st) return st;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_wcost_job& j = jobs[i];
+        if (!slotOk(c, j.fenc_slot) || !slotOk(c, j.ref_slot)) return X265CU_ERR_BAD_ARG;
+        const P* ref = slotPtr<P>(c, j.ref_slot, L.planes);
+        if (j.weighted)
+        {
+            st = weightPlanes<P>(c, ref, (P*)c->weightScratch[0], 1, j.w_scale, j.w_denom, j.w_offset);
+            if (st) return st;
+            ref = (const P*)c->weightScratch[0];
+        }
+        Prof pr(c, X265CU_K_WEIGHT, 1);
+        weight_cost_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, slotPtr<P>(c, j.fenc_slot, L.planes) + g.padOffset,
+                                                                        ref + g.padOffset, slotPtr<int>(c, j.fenc_slot, L.intraCost),
+                                                                        (unsigned*)c->d_results + i);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_results, c->d_results, n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(costs, c->h_results, n * sizeof(unsigned));
+    c->counters.d2h_bytes += n * sizeof(unsigned);
+    return X265CU_OK;
+}
+
+template <typename P>
+int blockMetricsT(x265cu_ctx* c, const void* a, const void* b, int n, int32_t* sad, int32_t* satd)
+{
+    P *da = NULL, *db = NULL; int *ds = NULL, *dt = NULL;
+    const size_t bytes = (size_t)n * 64 * sizeof(P);
+    CK(cudaMalloc((void**)&da, bytes + 64)); CK(cudaMalloc((void**)&db, bytes + 64));
+    CK(cudaMalloc((void**)&ds, n * sizeof(int))); CK(cudaMalloc((void**)&dt, n * sizeof(int)));
+    CK(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, c->stream));
+    block_metrics_kernel<P><<<(n + 15) / 16, 128, 0, c->stream>>>(da, db, n, ds, dt);
+    c->counters.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sad, ds, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(satd, dt, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(da); cudaFree(db); cudaFree(ds); cudaFree(dt);
+    return X265CU_OK;
+}
+
+#define DISPATCH(fn, ...) (c->bpp == 1 ? fn<uint8_t>(__VA_ARGS__) : fn<uint16_t>(__VA_ARGS__))
+
+} // namespace
+
+extern "C" {
+
+int x265cu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* x265cu_strerror(int s)
+{
+    switch (s)
+    {
+    case X265CU_OK: return "ok";
+    case X265CU_ERR_NO_DEVICE: return "no usable CUDA device (the GPU lookahead has no CPU fallback)";
+    case X265CU_ERR_BAD_ARG: return "bad argument";
+    case X265CU_ERR_NO_MEMORY: return "out of memory";
+    case X265CU_ERR_CUDA: return "CUDA error";
+    case X265CU_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+    }
+}
+
+const char* x265cu_last_error(const x265cu_ctx* c) { return c ? c->err : ""; }
+
+int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
+{
+    if (!cfg || !out) return X265CU_ERR_BAD_ARG;
+    *out = NULL;
+    if (cfg->qg_size < 16) return X265CU_ERR_UNSUPPORTED;
+    if (cfg->depth != 8 && cfg->depth != 10) return X265CU_ERR_UNSUPPORTED;     /* SWAR SATD range, la_device.cuh */
+    if (cfg->width < 16 || cfg->height < 16 || cfg->bframes < 0 || cfg->bframes > 16 || cfg->max_slots < 1 || !cfg->mvcost)
+        return X265CU_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return X265CU_ERR_NO_DEVICE;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return X265CU_ERR_NO_DEVICE;
+    x265cu_ctx* c = new (std::nothrow) x265cu_ctx();
+    if (!c) return X265CU_ERR_NO_MEMORY;
+    c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_jobs = NULL; c->jobsCap = 0; c->d_sync = NULL; c->syncCap = 0;
+    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->profile = false;
+    memset(&c->counters, 0, sizeof(c->counters)); memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN));
+    c->bpp = cfg->depth > 8 ? 2 : 1;
+
+    /* geometry: Lowres::create (lowres.cpp:72-97) */
+    Geom& g = c->g;
+    g.picW = cfg->width; g.picH = cfg->height; g.cW = (cfg->width + 1) / 2; g.cH = (cfg->height + 1) / 2;
+    const int lw = cfg->width / 2, lh = cfg->height / 2;
+    g.mx = cfg->max_cu_size + 32; g.my = cfg->max_cu_size + 16;
+    g.stride = lw + 2 * g.mx;
+    if (g.stride & 31) g.stride += 32 - (g.stride & 31);
+    g.bw = (lw + 7) >> 3; g.bh = (lh + 7) >> 3; g.ncu = g.bw * g.bh;
+    g.w = g.bw * 8; g.h = g.bh * 8;
+    g.planeLines = g.h + 2 * g.my;
+    g.planeSize = (long long)g.stride * g.planeLines;
+    g.padOffset = (long long)g.stride * g.my + g.mx;
+    g.lambda = cfg->lambda; g.depth = cfg->depth; g.nb = cfg->bframes + 2;
+    x265cu_geometry& G = c->geom;
+    G.low_width = g.w; G.low_height = g.h; G.bw = g.bw; G.bh = g.bh; G.ncu = g.ncu; G.stride = g.stride;
+    G.plane_lines = g.planeLines; G.margin_x = g.mx; G.margin_y = g.my; G.nb = g.nb;
+    G.n_mv_stores = 3 * g.nb; G.n_cost_stores = 2 * g.nb * g.nb;
+
+    SlotLayout& L = c->lay;
+    size_t o = 0;
+#define SECTION(name, bytes) L.name = o; o = alignUp(o + (bytes), 256)
+    SECTION(srcY, (size_t)g.picW * g.picH * c->bpp + 64);
+    SECTION(srcU, (size_t)g.cW * g.cH * c->bpp + 64);
+    SECTION(srcV, (size_t)g.cW * g.cH * c->bpp + 64);
+    SECTION(planes, (size_t)(4 * g.planeSize) * c->bpp + 256);
+    SECTION(intraCost, (size_t)g.ncu * 4);
+    SECTION(intraMode, (size_t)g.ncu);
+    SECTION(invQ, (size_t)g.ncu * 4);
+    SECTION(qpAq, (size_t)g.ncu * 8);
+    SECTION(qpCuTree, (size_t)g.ncu * 8);
+    SECTION(propagate, (size_t)g.ncu * 4);
+    SECTION(energy, (size_t)g.ncu * 4);
+    SECTION(lowresCosts00, (size_t)g.ncu * 2);
+    L.rowSatds00 = o; o += alignUp((size_t)g.bh * 4, 16);
+    L.stats = o; o = alignUp(o + sizeof(FrameStatsDev), 256);
+    L.mvStoreStride = alignUp((size_t)g.ncu * 8, 256);
+    SECTION(mvStores, L.mvStoreStride * G.n_mv_stores);
+    L.costRowOff = alignUp((size_t)g.ncu * 2, 16);
+    L.costResOff = L.costRowOff + alignUp((size_t)g.bh * 4, 16);
+    L.costStoreStride = alignUp(L.costResOff + sizeof(CostResultDev), 256);
+    SECTION(costStores, L.costStoreStride * G.n_cost_stores);
+#undef SECTION
+    L.total = o;
+
+    int rc = X265CU_OK;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    const size_t tabBytes = (2 * (size_t)cfg->mvcost_half + 1) * sizeof(unsigned short);
+    if (cudaMalloc((void**)&c->d_mvcost, tabBytes) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+    if (!rc && cudaMemcpy(c->d_mvcost, cfg->mvcost, tabBytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    for (int i = 0; !rc && i < cfg->max_slots; i++)
+    {
+        char* p = NULL;
+        if (cudaMalloc((void**)&p, L.total) != cudaSuccess) { rc = X265CU_ERR_NO_MEMORY; break; }
+        c->slots.push_back(p);
+        /* planes must start zeroed: columns past the right margin are never written (K1) */
+        if (cudaMemsetAsync(p, 0, L.total, c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    }
+    if (!rc)
+    {
+        cudaFuncSetAttribute(search_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(search_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    }
+    if (rc) { x265cu_destroy(c); return rc; }
+    c->cfg.mvcost = NULL;
+    *out = c;
+    return X265CU_OK;
+}
+
+void x265cu_destroy(x265cu_ctx* c)
+{
+    if (!c) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->slots.size(); i++) cudaFree(c->slots[i]);
+    for (size_t i = 0; i < c->weightScratch.size(); i++) cudaFree(c->weightScratch[i]);
+    cudaFree(c->d_mvcost); cudaFree(c->d_jobs); cudaFree(c->d_sync); cudaFree(c->d_results);
+    if (c->h_results) cudaFreeHost(c->h_results);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* out) { if (!c || !out) return X265CU_ERR_BAD_ARG; *out = c->geom; return X265CU_OK; }
+
+int x265cu_pin_host(x265cu_ctx* c, void* ptr, uint64_t bytes)
+{
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return X265CU_OK;
+}
+int x265cu_unpin_host(x265cu_ctx* c, void* ptr)
+{
+    CK(cudaHostUnregister(ptr));
+    return X265CU_OK;
+}
+
+int x265cu_sync(x265cu_ctx* c) { CK(cudaStreamSynchronize(c->stream)); return X265CU_OK; }
+
+int x265cu_get_counters(const x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return X265CU_OK; }
+
+int x265cu_profile_enable(x265cu_ctx* c, int32_t on) { c->profile = on != 0; return X265CU_OK; }
+
+int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset)
+{
+    for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = c->profMs[i]; launches[i] = c->profN[i]; }
+    if (reset) { memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN)); }
+    return X265CU_OK;
+}
+
+int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* u, const void* v, int32_t sy, int32_t sc)
+{
+    if (!c || !slotOk(c, slot) || !y) return X265CU_ERR_BAD_ARG;
+    return DISPATCH(uploadT, c, slot, y, u, v, sy, sc);
+}
+
+int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)
+{
+    if (n <= 0) return X265CU_OK;
+    int st = ensureHost(c, n * sizeof(FrameStatsDev));
+    if (st) return st;
+    for (int i = 0; i < n; i++)
+    {
+        if (!slotOk(c, slots[i])) return X265CU_ERR_BAD_ARG;
+        CK(cudaMemcpyAsync(c->h_results + i * sizeof(FrameStatsDev), c->slots[slots[i]] + c->lay.stats, sizeof(FrameStatsDev),
+                           cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++)
+    {
+        const FrameStatsDev* s = (const FrameStatsDev*)(c->h_results + i * sizeof(FrameStatsDev));
+        out[i].cost_est = s->costEst; out[i].cost_est_aq = s->costEstAq;
+        for (int k = 0; k < 3; k++) { out[i].wp_ssd[k] = s->wp_ssd[k]; out[i].wp_sum[k] = s->wp_sum[k]; }
+    }
+    c->counters.d2h_bytes += n * sizeof(FrameStatsDev);
+    return X265CU_OK;
+}
+
+int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
+{
+    if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
+    if (n <= 0) return X265CU_OK;
+    return DISPATCH(searchBatchT, c, jobs, n);
+}
+
+int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
+{
+    if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
+    if (n <= 0) return X265CU_OK;
+    return DISPATCH(costBatchT, c, jobs, n);
+}
+
+int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* outs, int32_t n, x265cu_cost_result* res)
+{
+    if (n <= 0) return X265CU_OK;
+    int st = ensureHost(c, n * sizeof(CostResultDev));
+    if (st) return st;
+    for (int i = 0; i < n; i++)
+    {
+        if (!slotOk(c, slots[i]) || outs[i] < 0 || outs[i] >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
+        CK(cudaMemcpyAsync(c->h_results + i * sizeof(CostResultDev), costStorePtr(c, slots[i], outs[i]) + c->lay.costResOff,
+                           sizeof(CostResultDev), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++)
+    {
+        const CostResultDev* r = (const CostResultDev*)(c->h_results + i * sizeof(CostResultDev));
+        res[i].cost_est = r->costEst; res[i].cost_est_aq = r->costEstAq; res[i].intra_mbs = r->intraMbs; res[i].reserved = 0;
+    }
+    c->counters.d2h_bytes += n * sizeof(CostResultDev);
+    return X265CU_OK;
+}
+
+int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_t n, uint32_t* costs)
+{
+    if (!c || (n > 0 && (!jobs || !costs))) return X265CU_ERR_BAD_ARG;
+    if (n <= 0) return X265CU_OK;
+    return DISPATCH(weightCostT, c, jobs, n, costs);
+}
+
+int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
+{
+    if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
+    CK(cudaMemsetAsync(c->slots[slot] + c->lay.propagate, 0, (size_t)c->g.ncu * 4, c->stream));
+    return X265CU_OK;
+}
+
+int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s, int32_t cost_store, int32_t l0, int32_t l1,
+                            int32_t referenced, int32_t bipred_weight, double fps_factor)
+{
+    if (!slotOk(c, bs) || !slotOk(c, p0s) || !slotOk(c, p1s) || cost_store < 2 || cost_store >= c->geom.n_cost_stores ||
+        l0 < 0 || l0 >= c->geom.n_mv_stores || l1 >= c->geom.n_mv_stores)
+        return X265CU_ERR_BAD_ARG;
+    const SlotLayout& L = c->lay;
+    const int* mv0 = (const int*)mvStorePtr(c, bs, l0);
+    const int* mv1 = l1 >= 0 ? (const int*)mvStorePtr(c, bs, l1) : mv0;
+    Prof pr(c, X265CU_K_CUTREE, 1);
+    cutree_propagate_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
+        c->g, slotPtr<int>(c, bs, L.intraCost), (const unsigned short*)costStorePtr(c, bs, cost_store), slotPtr<int>(c, bs, L.invQ),
+        mv0, mv1, referenced ? slotPtr<int>(c, bs, L.propagate) : NULL, slotPtr<int>(c, p0s, L.propagate),
+        slotPtr<int>(c, p1s, L.propagate), bipred_weight, fps_factor);
+    CK(cudaGetLastError());
+    return X265CU_OK;
+}
+
+int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double weightdelta, double strength)
+{
+    if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
+    const SlotLayout& L = c->lay;
+    Prof pr(c, X265CU_K_CUTREE, 1);
+    cutree_finish_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
+        c->g, slotPtr<int>(c, slot, L.intraCost), slotPtr<int>(c, slot, L.invQ), slotPtr<int>(c, slot, L.propagate),
+        slotPtr<double>(c, slot, L.qpAq), slotPtr<double>(c, slot, L.qpCuTree), fps_fix8, weightdelta, strength);
+    CK(cudaGetLastError());
+    return X265CU_OK;
+}
+
+int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree, int64_t* score, int32_t* rows)
+{
+    if (!slotOk(c, slot) || cost_store < 0 || cost_store >= c->geom.n_cost_stores || cost_store == 1 || !score) return X265CU_ERR_BAD_ARG;
+    const SlotLayout& L = c->lay;
+    const Geom& g = c->g;
+    const unsigned short* costs; int* rs;
+    if (cost_store == 0) { costs = slotPtr<unsigned short>(c, slot, L.lowresCosts00); rs = slotPtr<int>(c, slot, L.rowSatds00); }
+    else { char* cs = costStorePtr(c, slot, cost_store); costs = (const unsigned short*)cs; rs = (int*)(cs + L.costRowOff); }
+    int st = ensureDev(c, &c->d_results, &c->resultsCap, 8);
+    if (st) return st;
+    st = ensureHost(c, 8 + (size_t)g.bh * 4);
+    if (st) return st;
+    CK(cudaMemsetAsync(rs, 0, (size_t)g.bh * 4, c->stream));
+    CK(cudaMemsetAsync(c->d_results, 0, 8, c->stream));
+    {
+        Prof pr(c, X265CU_K_CUTREE, 1);
+        cost_recalc_kernel<<<(g.ncu + 255) / 256, 256, 0, c->stream>>>(g, costs, slotPtr<double>(c, slot, use_cutree ? L.qpCuTree : L.qpAq),
+                                                                      rs, (unsigned long long*)c->d_results);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_results, c->d_results, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (rows) CK(cudaMemcpyAsync(c->h_results + 8, rs, (size_t)g.bh * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *score = *(const long long*)c->h_results;
+    if (rows) memcpy(rows, c->h_results + 8, (size_t)g.bh * 4);
+    c->counters.d2h_bytes += 8 + (rows ? (size_t)g.bh * 4 : 0);
+    return X265CU_OK;
+}
+
+static int d2h(x265cu_ctx* c, void* dst, const void* src, size_t bytes)
+{
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->counters.d2h_bytes += bytes;
+    return X265CU_OK;
+}
+
+__global__ void clamp_u16_kernel(const int* __restrict__ src, unsigned short* __restrict__ dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (unsigned short)min(max(src[i], 0), 65535);
+}
+
+__global__ void unpack_mv_kernel(const int* __restrict__ src, int* __restrict__ dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int p = src[i]; dst[2 * i] = (int)(short)(p & 0xffff); dst[2 * i + 1] = p >> 16; }
+}
+
+int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
+{
+    if (!slotOk(c, slot) || !o) return X265CU_ERR_BAD_ARG;
+    const SlotLayout& L = c->lay;
+    const Geom& g = c->g;
+    int st = X265CU_OK;
+    if (o->intra_cost && !st) st = d2h(c, o->intra_cost, c->slots[slot] + L.intraCost, (size_t)g.ncu * 4);
+    if (o->intra_mode && !st) st = d2h(c, o->intra_mode, c->slots[slot] + L.intraMode, (size_t)g.ncu);
+    if (o->qp_aq_offset && !st) st = d2h(c, o->qp_aq_offset, c->slots[slot] + L.qpAq, (size_t)g.ncu * 8);
+    if (o->qp_cutree_offset && !st) st = d2h(c, o->qp_cutree_offset, c->slots[slot] + L.qpCuTree, (size_t)g.ncu * 8);
+    if (o->inv_qscale_factor && !st) st = d2h(c, o->inv_qscale_factor, c->slots[slot] + L.invQ, (size_t)g.ncu * 4);
+    if (o->propagate_cost && !st)
+    {
+        st = ensureDev(c, &c->d_results, &c->resultsCap, (size_t)g.ncu * 2);
+        if (!st)
+        {
+            clamp_u16_kernel<<<(g.ncu + 255) / 256, 256, 0, c->stream>>>(slotPtr<int>(c, slot, L.propagate), (unsigned short*)c->d_results, g.ncu);
+            c->counters.kernel_launches++;
+            st = d2h(c, o->propagate_cost, c->d_results, (size_t)g.ncu * 2);
+        }
+    }
+    if (o->planes && !st) st = d2h(c, o->planes, c->slots[slot] + L.planes, (size_t)(4 * g.planeSize) * c->bpp);
+    if (o->lowres_costs00 && !st) st = d2h(c, o->lowres_costs00, c->slots[slot] + L.lowresCosts00, (size_t)g.ncu * 2);
+    if (o->row_satds00 && !st) st = d2h(c, o->row_satds00, c->slots[slot] + L.rowSatds00, (size_t)g.bh * 4);
+    if (st) return st;
+    CK(cudaStreamSynchronize(c->stream));
+    return X265CU_OK;
+}
+
+int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost)
+{
+    if (!slotOk(c, slot) || store < 0 || store >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
+    const Geom& g = c->g;
+    const int* st0 = (const int*)mvStorePtr(c, slot, store);
+    int st = X265CU_OK;
+    if (mv)
+    {
+        st = ensureDev(c, &c->d_results, &c->resultsCap, (size_t)g.ncu * 8);
+        if (st) return st;
+        unpack_mv_kernel<<<(g.ncu + 255) / 256, 256, 0, c->stream>>>(st0, (int*)c->d_results, g.ncu);
+        c->counters.kernel_launches++;
+        st = d2h(c, mv, c->d_results, (size_t)g.ncu * 8);
+    }
+    if (cost && !st) st = d2h(c, cost, st0 + g.ncu, (size_t)g.ncu * 4);
+    if (st) return st;
+    CK(cudaStreamSynchronize(c->stream));
+    return X265CU_OK;
+}
+
+int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* costs, int32_t* rows)
+{
+    if (!slotOk(c, slot) || store < 2 || store >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
+    char* cs = costStorePtr(c, slot, store);
+    int st = X265CU_OK;
+    if (costs) st = d2h(c, costs, cs, (size_t)c->g.ncu * 2);
+    if (rows && !st) st = d2h(c, rows, cs + c->lay.costRowOff, (size_t)c->g.bh * 4);
+    if (st) return st;
+    CK(cudaStreamSynchronize(c->stream));
+    return X265CU_OK;
+}
+
+/* unit-test hook (not part of the drop-in surface): SAD / SATD of n packed 8x8 block pairs */
+int x265cu_debug_block_metrics(x265cu_ctx* c, const void* a, const void* b, int32_t n, int32_t* sad, int32_t* satd)
+{
+    if (!c || !a || !b || n <= 0) return X265CU_ERR_BAD_ARG;
+    return DISPATCH(blockMetricsT, c, a, b, n, sad, satd);
+}
+
+} // extern "C"

@@ -1,0 +1,904 @@
+/* la_kernels.cuh -- the lookahead kernels (sm_100a).  See la_device.cuh for the 8-lanes-per-block
+ * decomposition.  Each kernel names the reference lines whose results it reproduces.
+ * Compile with -fmad=false: the few floating-point expressions must round like the reference's
+ * x86-64 (no FMA) build. */
+#pragma once
+#include "la_device.cuh"
+
+namespace la {
+
+#define LA_COST_MAX (1 << 28)
+#define LA_LOWRES_COST_MASK 16383
+#define LA_LOWRES_COST_SHIFT 14
+
+struct FrameStatsDev            /* mirrors x265cu_frame_stats */
+{
+    long long costEst, costEstAq;
+    unsigned long long wp_ssd[3], wp_sum[3];
+};
+
+struct CostResultDev            /* mirrors x265cu_cost_result */
+{
+    long long costEst, costEstAq;
+    int intraMbs, reserved;
+};
+
+/* ------------------------------------------------------------------------------------------
+ * K1: downscale to the four half-pel planes and write the WHOLE padded plane (margins included)
+ * in one pass.  frame_init_lowres_core (pixel.cpp:605-628) + 4x extendPicBorder (lowres.cpp:
+ * 373-376, pixel.cpp:1044-1058).  Margin samples replicate the edge sample, which is the same as
+ * evaluating the filter at the clamped lowres coordinate; columns past the right margin (stride
+ * alignment) stay 0 exactly as in the reference's zero-initialised buffer.  The source is read
+ * with replicate clamping = PicYuv's padding (picyuv.cpp:261-285).
+ * One thread = 4 consecutive output samples of all 4 planes: coalesced vector stores.
+ * HBM-bound: reads F (full-res luma), writes 4 planes.
+ * ------------------------------------------------------------------------------------------ */
+template <typename P> struct Vec4;
+template <> struct Vec4<uint8_t>  { typedef uchar4 T; };
+template <> struct Vec4<uint16_t> { typedef ushort4 T; };
+
+template <typename P>
+__global__ void __launch_bounds__(256) lowres_kernel(Geom g, const P* __restrict__ src, P* __restrict__ buf)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int py = blockIdx.y;
+    if (x4 >= g.stride) return;
+    typename Vec4<P>::T o0, o1, o2, o3;
+    P* op[4] = { (P*)&o0, (P*)&o1, (P*)&o2, (P*)&o3 };
+    const int ly = min(max(py - g.my, 0), g.h - 1);
+    const int r0 = min(2 * ly, g.picH - 1), r1 = min(2 * ly + 1, g.picH - 1), r2 = min(2 * ly + 2, g.picH - 1);
+    const P* s0 = src + (long long)r0 * g.picW;
+    const P* s1 = src + (long long)r1 * g.picW;
+    const P* s2 = src + (long long)r2 * g.picW;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int pxx = x4 + i;
+        if (pxx >= 2 * g.mx + g.w)
+        {
+            op[0][i] = op[1][i] = op[2][i] = op[3][i] = 0;
+            continue;
+        }
+        const int lx = min(max(pxx - g.mx, 0), g.w - 1);
+        const int c0 = min(2 * lx, g.picW - 1), c1 = min(2 * lx + 1, g.picW - 1), c2 = min(2 * lx + 2, g.picW - 1);
+        const int a00 = __ldg(s0 + c0), a01 = __ldg(s0 + c1), a02 = __ldg(s0 + c2);
+        const int a10 = __ldg(s1 + c0), a11 = __ldg(s1 + c1), a12 = __ldg(s1 + c2);
+        const int a20 = __ldg(s2 + c0), a21 = __ldg(s2 + c1), a22 = __ldg(s2 + c2);
+#define LA_FILTER(a, b, c, d) ((((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1)
+        op[0][i] = (P)LA_FILTER(a00, a10, a01, a11);
+        op[1][i] = (P)LA_FILTER(a01, a11, a02, a12);
+        op[2][i] = (P)LA_FILTER(a10, a20, a11, a21);
+        op[3][i] = (P)LA_FILTER(a11, a21, a12, a22);
+#undef LA_FILTER
+    }
+    const long long o = (long long)py * g.stride + x4;
+    *(typename Vec4<P>::T*)(buf + o) = o0;
+    *(typename Vec4<P>::T*)(buf + g.planeSize + o) = o1;
+    *(typename Vec4<P>::T*)(buf + 2 * g.planeSize + o) = o2;
+    *(typename Vec4<P>::T*)(buf + 3 * g.planeSize + o) = o3;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K2a: per-16x16 AC energy of Y + the two co-located 8x8 chroma blocks, and the frame sums for
+ * weightp.  acEnergyCu / acEnergyPlane / acEnergyVar / pixel_var (slicetype.cpp:49-84,264-283,
+ * pixel.cpp:720-737).  One warp per 16x16 block.  HBM-bound: reads 1.5 F.
+ * ------------------------------------------------------------------------------------------ */
+template <typename P>
+__device__ __forceinline__ void warpVar(const P* __restrict__ p, int stride, int W, int H, int bx, int by, int size,
+                                        unsigned& sum, unsigned& sqr)
+{
+    sum = 0; sqr = 0;
+    const int lane = threadIdx.x & 31;
+    const int n = size * size;
+    for (int i = lane; i < n; i += 32)
+    {
+        const int x = min(bx + (i % size), W - 1), y = min(by + (i / size), H - 1);
+        const unsigned v = __ldg(p + (long long)y * stride + x);
+        sum += v; sqr += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+    {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sqr += __shfl_xor_sync(0xffffffffu, sqr, o);
+    }
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) aq_energy_kernel(Geom g, const P* __restrict__ y, const P* __restrict__ u,
+                                                        const P* __restrict__ v, unsigned* __restrict__ energy,
+                                                        FrameStatsDev* stats)
+{
+    __shared__ unsigned long long s_acc[6];
+    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * 8 + warp;
+    if (blk < g.ncu)
+    {
+        const int bx = (blk % g.bw) * 16, by = (blk / g.bw) * 16;
+        unsigned sum, sqr, e;
+        warpVar(y, g.picW, g.picW, g.picH, bx, by, 16, sum, sqr);
+        e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
+        if (lane == 0) { atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr); }
+        if (u)
+        {
+            warpVar(u, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
+            e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
+            if (lane == 0) { atomicAdd(&s_acc[1], (unsigned long long)sum); atomicAdd(&s_acc[4], (unsigned long long)sqr); }
+            warpVar(v, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
+            e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
+            if (lane == 0) { atomicAdd(&s_acc[2], (unsigned long long)sum); atomicAdd(&s_acc[5], (unsigned long long)sqr); }
+        }
+        if (lane == 0) energy[blk] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(&stats->wp_sum[threadIdx.x], s_acc[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicAdd(&stats->wp_ssd[threadIdx.x - 3], s_acc[threadIdx.x]);
+}
+
+/* K2b: the transcendental finish of calcAdaptiveQuantFrame (slicetype.cpp:537-652, 681-694) for
+ * aq-mode 0..3, qg-size > 8.  One CTA; the two frame means are reduced in a fixed order so the
+ * result is deterministic.  (The reference sums sequentially in double; a different summation
+ * order perturbs qp_adj by ~1e-15, far below the 1/64-QP grid of exp2fix8.) */
+__global__ void __launch_bounds__(1024) aq_finish_kernel(Geom g, const unsigned* __restrict__ energy, int aqMode,
+                                                         double aqStrength, int bWeightP, double* __restrict__ qpAq,
+                                                         double* __restrict__ qpCuTree, int* __restrict__ invQ,
+                                                         FrameStatsDev* stats)
+{
+    __shared__ double s_a[1024], s_b[1024];
+    __shared__ double s_strength, s_avg, s_bias;
+    const int tid = threadIdx.x, n = g.ncu;
+    const float modeOneConst = 14.427f, modeTwoConst = 11.f;
+    if (tid == 0 && bWeightP)
+    {
+        const int maxCol = ((g.picW + 8) >> 4) << 4, maxRow = ((g.picH + 8) >> 4) << 4;
+        const int wd[3] = { maxCol, maxCol >> 1, maxCol >> 1 }, ht[3] = { maxRow, maxRow >> 1, maxRow >> 1 };
+        for (int i = 0; i < 3; i++)
+        {
+            const unsigned long long sum = stats->wp_sum[i], ssd = stats->wp_ssd[i];
+            const unsigned long long area = (unsigned long long)(wd[i] * ht[i]);
+            stats->wp_ssd[i] = ssd - (sum * sum + area / 2) / area;
+        }
+    }
+    if (aqMode == 0 || aqStrength == 0)
+    {
+        if (aqMode && aqStrength == 0)
+            for (int i = tid; i < n; i += blockDim.x) { qpAq[i] = 0; qpCuTree[i] = 0; invQ[i] = 256; }
+        return;
+    }
+    if (aqMode == 2 || aqMode == 3)
+    {
+        const double bdc = (double)(1.f / (1 << (2 * (g.depth - 8))));
+        double a = 0, b = 0;
+        for (int i = tid; i < n; i += blockDim.x)
+        {
+            const double q = pow(__dadd_rn(__dmul_rn((double)energy[i], bdc), 1.0), 0.1);
+            qpCuTree[i] = q;
+            a = __dadd_rn(a, q);
+            b = __dadd_rn(b, __dmul_rn(q, q));
+        }
+        s_a[tid] = a; s_b[tid] = b;
+        __syncthreads();
+        for (int o = 512; o; o >>= 1)
+        {
+            if (tid < o) { s_a[tid] = __dadd_rn(s_a[tid], s_a[tid + o]); s_b[tid] = __dadd_rn(s_b[tid], s_b[tid + o]); }
+            __syncthreads();
+        }
+        if (tid == 0)
+        {
+            double avg_adj = __ddiv_rn(s_a[0], (double)n), avg_adj_pow2 = __ddiv_rn(s_b[0], (double)n);
+            s_strength = __dmul_rn(aqStrength, avg_adj);
+            s_avg = __dadd_rn(avg_adj, -__ddiv_rn(__dmul_rn((double)0.5f, __dadd_rn(avg_adj_pow2, -(double)modeTwoConst)), avg_adj));
+            s_bias = __dmul_rn(1.0, aqStrength);
+        }
+        __syncthreads();
+    }
+    else if (tid == 0)
+        s_strength = __dmul_rn(aqStrength, (double)1.0397f);
+    __syncthreads();
+    const double strength = s_strength, avg_adj = s_avg, bias_strength = s_bias;
+    for (int i = tid; i < n; i += blockDim.x)
+    {
+        double qp_adj;
+        if (aqMode == 3)
+        {
+            const double q = qpCuTree[i];
+            qp_adj = __dadd_rn(__dmul_rn(strength, __dadd_rn(q, -avg_adj)),
+                               __dmul_rn(bias_strength, __dadd_rn(1.0, -__ddiv_rn((double)modeTwoConst, __dmul_rn(q, q)))));
+        }
+        else if (aqMode == 2)
+            qp_adj = __dmul_rn(strength, __dadd_rn(qpCuTree[i], -avg_adj));
+        else
+        {
+            const unsigned e = energy[i] > 1 ? energy[i] : 1;
+            const float c = modeOneConst + (float)(2 * (g.depth - 8));
+            qp_adj = __dmul_rn(strength, __dadd_rn(log2((double)e), -(double)c));
+        }
+        qpAq[i] = qp_adj;
+        qpCuTree[i] = qp_adj;
+        invQ[i] = exp2fix8(qp_adj);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K3: lowres intra cost.  LookaheadTLD::lowresIntraEstimate (slicetype.cpp:715-824) with
+ * intraFilter<8>, intra_pred_dc_c<8>, planar_pred_c<3>, intra_pred_ang_c<8> (intrapred.cpp:31-204).
+ * 8 lanes per block, 16 blocks per CTA; neighbours staged in shared memory; 12 predictions +
+ * SATDs per block.  Works out of L2 (plane 0 of one frame); integer-pipe bound.
+ * ------------------------------------------------------------------------------------------ */
+__device__ const signed char c_angleTable[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+__device__ const short c_invAngleTable[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
+__device__ const unsigned char c_intraFilterFlags[35] = {
+    0x38, 0x00,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30, 0x20, 0x00, 0x20, 0x30, 0x30, 0x30, 0x30, 0x30, 0x30,
+    0x38 };
+
+/* neighbour accessor after the horizontal-mode swap of intra_pred_ang_c (intrapred.cpp:112-121) */
+__device__ __forceinline__ int nbSwap(const unsigned short* s, int i, bool hor)
+{
+    if (!hor || i == 0) return s[i];
+    return i <= 16 ? s[16 + i] : s[i - 16];
+}
+
+template <typename P>
+__device__ __forceinline__ Row<P> predAngular(const unsigned short* s, int mode, int y, int maxv)
+{
+    const bool hor = mode < 18;
+    const int angleOffset = hor ? 10 - mode : mode - 26;
+    const int angle = c_angleTable[8 + angleOffset];
+    Row<P> out;
+#pragma unroll
+    for (int x = 0; x < 8; x++)
+    {
+        const int yy = hor ? x : y, xx = hor ? y : x;       /* coordinates before the final transpose */
+        int val;
+        if (!angle)
+        {
+            val = nbSwap(s, 1 + xx, hor);
+            if (xx == 0)
+            {
+                int t = (short)(nbSwap(s, 1, hor) + ((nbSwap(s, 17 + yy, hor) - nbSwap(s, 0, hor)) >> 1));
+                val = min(max(t, 0), maxv);
+            }
+        }
+        else
+        {
+            const int angleSum = (yy + 1) * angle;
+            const int off = angleSum >> 5, frac = angleSum & 31;
+            int k0 = off + xx, k1 = k0 + 1, r0, r1;
+            /* ref[k] = S(k+1) for k >= -1; projected left neighbours for k <= -2 (angle < 0) */
+            if (k0 >= -1) r0 = nbSwap(s, k0 + 1, hor);
+            else r0 = nbSwap(s, 16 + ((128 + (-1 - k0) * c_invAngleTable[-angleOffset - 1]) >> 8), hor);
+            if (frac)
+            {
+                if (k1 >= -1) r1 = nbSwap(s, k1 + 1, hor);
+                else r1 = nbSwap(s, 16 + ((128 + (-1 - k1) * c_invAngleTable[-angleOffset - 1]) >> 8), hor);
+                val = ((32 - frac) * r0 + frac * r1 + 16) >> 5;
+            }
+            else
+                val = r0;
+        }
+        setPx(out, x, val);
+    }
+    return out;
+}
+
+template <typename P>
+__global__ void __launch_bounds__(128) intra_kernel(Geom g, const P* __restrict__ plane0, const int* __restrict__ invQ,
+                                                    int* __restrict__ intraCost, unsigned char* __restrict__ intraMode,
+                                                    unsigned short* __restrict__ lowresCosts00, int* __restrict__ rowSatds00,
+                                                    FrameStatsDev* stats)
+{
+    __shared__ unsigned short s_nb[16][2][34];
+    __shared__ unsigned long long s_cost[2];
+    if (threadIdx.x < 2) s_cost[threadIdx.x] = 0;
+    __syncthreads();
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const unsigned gmask = groupMask();
+    const int cu = blockIdx.x * 16 + grp;
+    const int maxv = (1 << g.depth) - 1;
+    if (cu < g.ncu)
+    {
+        const int cuX = cu % g.bw, cuY = cu / g.bw;
+        const P* pix = plane0 + 8 * cuX + (long long)8 * cuY * g.stride;
+        const Row<P> fenc = loadRow(pix + (long long)r * g.stride);
+        unsigned short* nbA = s_nb[grp][0];
+        unsigned short* nbF = s_nb[grp][1];
+        const P* c = pix - g.stride - 1;
+        nbA[2 * r] = __ldg(c + 2 * r);
+        nbA[2 * r + 1] = __ldg(c + 2 * r + 1);
+        if (r == 0) nbA[16] = __ldg(c + 16);
+        nbA[17 + 2 * r] = __ldg(c + (long long)(2 * r + 1) * g.stride);
+        nbA[18 + 2 * r] = __ldg(c + (long long)(2 * r + 2) * g.stride);
+        __syncwarp(gmask);
+        /* intraFilter<8> (intrapred.cpp:31-51) */
+        for (int i = r; i <= 32; i += 8)
+        {
+            int f;
+            if (i == 0) f = ((nbA[0] << 1) + nbA[1] + nbA[17] + 2) >> 2;
+            else if (i == 16 || i == 32) f = nbA[i];
+            else if (i == 17) f = ((nbA[17] << 1) + nbA[0] + nbA[18] + 2) >> 2;
+            else f = ((nbA[i] << 1) + nbA[i - 1] + nbA[i + 1] + 2) >> 2;
+            nbF[i] = (unsigned short)f;
+        }
+        __syncwarp(gmask);
+
+        int cost, icost = LA_COST_MAX, ilow = 0;
+        {   /* DC with edge filter (intrapred.cpp:53-85) */
+            int dc = groupSum(nbA[1 + r] + nbA[17 + r], gmask) + 8;
+            dc = dc / 16;
+            Row<P> pred;
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+            {
+                int v = dc;
+                if (r == 0) v = x == 0 ? (nbA[1] + nbA[17] + 2 * dc + 2) >> 2 : (nbA[1 + x] + 3 * dc + 2) >> 2;
+                else if (x == 0) v = (nbA[17 + r] + 3 * dc + 2) >> 2;
+                setPx(pred, x, v);
+            }
+            cost = groupSatdRows(fenc, pred, gmask);
+            if (cost < icost) { icost = cost; ilow = 1; }
+        }
+        {   /* planar on the filtered neighbours (intrapred.cpp:87-100) */
+            const int topRight = nbF[9], bottomLeft = nbF[25], left = nbF[17 + r];
+            Row<P> pred;
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+                setPx(pred, x, ((7 - x) * left + (7 - r) * nbF[1 + x] + (x + 1) * topRight + (r + 1) * bottomLeft + 8) >> 4);
+            cost = groupSatdRows(fenc, pred, gmask);
+            if (cost < icost) { icost = cost; ilow = 0; }
+        }
+        int acost = LA_COST_MAX, alow = 4;
+        for (int mode = 5; mode < 35; mode += 5)
+        {
+            const Row<P> pred = predAngular<P>((c_intraFilterFlags[mode] & 8) ? nbF : nbA, mode, r, maxv);
+            cost = groupSatdRows(fenc, pred, gmask);
+            if (cost < acost) { acost = cost; alow = mode; }
+        }
+        for (int dist = 2; dist >= 1; dist--)
+        {
+            const int minusmode = alow - dist, plusmode = alow + dist;
+            Row<P> pred = predAngular<P>((c_intraFilterFlags[minusmode] & 8) ? nbF : nbA, minusmode, r, maxv);
+            cost = groupSatdRows(fenc, pred, gmask);
+            if (cost < acost) { acost = cost; alow = minusmode; }
+            pred = predAngular<P>((c_intraFilterFlags[plusmode] & 8) ? nbF : nbA, plusmode, r, maxv);
+            cost = groupSatdRows(fenc, pred, gmask);
+            if (cost < acost) { acost = cost; alow = plusmode; }
+        }
+        if (acost < icost) { icost = acost; ilow = alow; }
+        icost += 5 * g.lambda + 4;
+        if (r == 0)
+        {
+            lowresCosts00[cu] = (unsigned short)min(icost, LA_LOWRES_COST_MASK);
+            intraCost[cu] = icost;
+            intraMode[cu] = (unsigned char)ilow;
+            const bool scored = (cuX > 0 && cuX < g.bw - 1 && cuY > 0 && cuY < g.bh - 1) || g.bw <= 2 || g.bh <= 2;
+            const int icostAq = (scored && invQ) ? ((icost * invQ[cu] + 128) >> 8) : icost;
+            if (scored)
+            {
+                atomicAdd(&s_cost[0], (unsigned long long)icost);
+                atomicAdd(&s_cost[1], (unsigned long long)icostAq);
+            }
+            atomicAdd(&rowSatds00[cuY], icostAq);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        atomicAdd((unsigned long long*)&stats->costEst, s_cost[0]);
+        atomicAdd((unsigned long long*)&stats->costEstAq, s_cost[1]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K4: motion search of one (frame, list, distance) over the whole frame.
+ * Search half of CostEstimateGroup::estimateCUCost (slicetype.cpp:4103-4183) and
+ * MotionEstimate::motionEstimate (motion.cpp:764-821 start, 870-969 HEX + square refine,
+ * 1473-1528 lowres subpel), merange 16, subpelRefine 1.
+ *
+ * Dependencies: block (x,y) takes MV predictors from (x+1,y), (x,y+1), (x-1,y+1), (x+1,y+1)
+ * (reverse raster order), so a frame is a wavefront.  A job is cut into bands of LA_BAND_ROWS rows;
+ * one CTA per band; inside a CTA row j runs 2 steps behind row j-1 (one __syncthreads per step);
+ * bands of one job are chained through a release/acquire progress counter in global memory.
+ * CTAs take their (job, band) from a ticket counter so a band never waits on a CTA that has not
+ * started.  Throughput comes from running many independent jobs concurrently.
+ * ------------------------------------------------------------------------------------------ */
+#define LA_BAND_ROWS 16
+
+template <typename P>
+struct SearchJobDev
+{
+    const P* fenc0;         /* lowresPlane[0] of the frame being searched */
+    const P* ref0;          /* lowresPlane[0] of the (possibly weighted) reference; planes at +i*planeSize */
+    int*     mvOut;         /* ncu packed MVs: (x & 0xffff) | (y << 16), quarter-pel */
+    int*     costOut;       /* ncu */
+    int      bidir;
+    int      pad;
+};
+
+struct MV2 { int x, y; };
+
+template <typename P>
+struct MeCtx
+{
+    Row<P> fenc;
+    RefBlock<P> rb;
+    const unsigned short* mvcost;   /* centre */
+    int mvpx, mvpy;
+    int r;
+    unsigned gmask;
+
+    __device__ __forceinline__ int mvc(int qx, int qy) const
+    {
+        return (int)(unsigned short)(__ldg(mvcost + (qx - mvpx)) + __ldg(mvcost + (qy - mvpy)));
+    }
+    __device__ __forceinline__ int sadFpelPart(int x, int y) const
+    {
+        return sadRow(fenc, loadRow(rb.base + x + (long long)(y + r) * rb.stride));
+    }
+    __device__ __forceinline__ int sadFpel(int x, int y) const { return groupSum(sadFpelPart(x, y), gmask); }
+    __device__ __forceinline__ int qpelSad(int qx, int qy) const { return groupSum(sadRow(fenc, mcRow(rb, qx, qy, r)), gmask); }
+    __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return groupSatdRows(fenc, mcRow(rb, qx, qy, r), gmask); }
+};
+
+__device__ const signed char c_hex2[8][2] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };
+__device__ const unsigned char c_mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };
+__device__ const signed char c_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };
+
+template <typename P>
+__device__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& out)
+{
+    const int merange = 16;
+    m.mvpx = qmvp.x; m.mvpy = qmvp.y;
+    const MV2 qmin = { mvmin.x << 2, mvmin.y << 2 }, qmax = { mvmax.x << 2, mvmax.y << 2 };
+    const MV2 pmv = { max(min(qmvp.x, qmax.x), qmin.x), max(min(qmvp.y, qmax.y), qmin.y) };
+    const MV2 bestpre = pmv;
+    const int bprecost = m.qpelSad(pmv.x, pmv.y);
+    MV2 bmv = { (pmv.x + 2) >> 2, (pmv.y + 2) >> 2 };
+    int bcost = bprecost;
+    if ((pmv.x & 3) | (pmv.y & 3))
+        bcost = m.sadFpel(bmv.x, bmv.y) + m.mvc(bmv.x << 2, bmv.y << 2);
+    if (pmv.x | pmv.y)
+    {
+        const int cost = m.sadFpel(0, 0) + m.mvc(0, 0);
+        if (cost < bcost)
+        {
+            bcost = cost;
+            bmv.x = 0;
+            bmv.y = max(min(0, mvmax.y), mvmin.y);
+        }
+    }
+#define LA_YOK(dy) ((bmv.y + (dy) >= mvmin.y) & (bmv.y + (dy) <= mvmax.y))
+#define LA_COST3(c0, c1, c2, x0, y0, x1, y1, x2, y2) \
+    { \
+        int p0 = m.sadFpelPart(bmv.x + (x0), bmv.y + (y0)), p1 = m.sadFpelPart(bmv.x + (x1), bmv.y + (y1)), \
+            p2 = m.sadFpelPart(bmv.x + (x2), bmv.y + (y2)); \
+        c0 = groupSum(p0, m.gmask) + m.mvc((bmv.x + (x0)) << 2, (bmv.y + (y0)) << 2); \
+        c1 = groupSum(p1, m.gmask) + m.mvc((bmv.x + (x1)) << 2, (bmv.y + (y1)) << 2); \
+        c2 = groupSum(p2, m.gmask) + m.mvc((bmv.x + (x2)) << 2, (bmv.y + (y2)) << 2); \
+    }
+    {   /* hexagon, motion.cpp:892-946 */
+        int c0, c1, c2;
+        LA_COST3(c0, c1, c2, -2, 0, -1, 2, 1, 2);
+        bcost <<= 3;
+        if (LA_YOK(0)) { bcost = min(bcost, (c0 << 3) + 2); }
+        if (LA_YOK(2)) { bcost = min(bcost, (c1 << 3) + 3); bcost = min(bcost, (c2 << 3) + 4); }
+        LA_COST3(c0, c1, c2, 2, 0, 1, -2, -1, -2);
+        if (LA_YOK(0)) { bcost = min(bcost, (c0 << 3) + 5); }
+        if (LA_YOK(-2)) { bcost = min(bcost, (c1 << 3) + 6); bcost = min(bcost, (c2 << 3) + 7); }
+        if (bcost & 7)
+        {
+            int dir = (bcost & 7) - 2;
+            if (LA_YOK(c_hex2[dir + 1][1]))
+            {
+                bmv.x += c_hex2[dir + 1][0]; bmv.y += c_hex2[dir + 1][1];
+                for (int i = (merange >> 1) - 1;
+                     i > 0 && bmv.x >= mvmin.x && bmv.x <= mvmax.x && bmv.y >= mvmin.y && bmv.y <= mvmax.y; i--)
+                {
+                    const int x0 = c_hex2[dir][0], y0 = c_hex2[dir][1], x1 = c_hex2[dir + 1][0], y1 = c_hex2[dir + 1][1],
+                              x2 = c_hex2[dir + 2][0], y2 = c_hex2[dir + 2][1];
+                    LA_COST3(c0, c1, c2, x0, y0, x1, y1, x2, y2);
+                    bcost &= ~7;
+                    if (LA_YOK(y0)) bcost = min(bcost, (c0 << 3) + 1);
+                    if (LA_YOK(y1)) bcost = min(bcost, (c1 << 3) + 2);
+                    if (LA_YOK(y2)) bcost = min(bcost, (c2 << 3) + 3);
+                    if (!(bcost & 7))
+                        break;
+                    dir += (bcost & 7) - 2;
+                    dir = c_mod6m1[dir + 1];
+                    bmv.x += c_hex2[dir + 1][0]; bmv.y += c_hex2[dir + 1][1];
+                }
+            }
+        }
+        bcost >>= 3;
+    }
+    {   /* square refine, motion.cpp:950-967 */
+        int dir = 0, c0, c1, c2, c3;
+        LA_COST3(c0, c1, c2, 0, -1, 0, 1, -1, 0);
+        c3 = m.sadFpel(bmv.x + 1, bmv.y) + m.mvc((bmv.x + 1) << 2, bmv.y << 2);
+        if (LA_YOK(-1)) { if (c0 < bcost) { bcost = c0; dir = 1; } }
+        if (LA_YOK(1))  { if (c1 < bcost) { bcost = c1; dir = 2; } }
+        if (c2 < bcost) { bcost = c2; dir = 3; }
+        if (c3 < bcost) { bcost = c3; dir = 4; }
+        LA_COST3(c0, c1, c2, -1, -1, -1, 1, 1, -1);
+        c3 = m.sadFpel(bmv.x + 1, bmv.y + 1) + m.mvc((bmv.x + 1) << 2, (bmv.y + 1) << 2);
+        if (LA_YOK(-1)) { if (c0 < bcost) { bcost = c0; dir = 5; } }
+        if (LA_YOK(1))  { if (c1 < bcost) { bcost = c1; dir = 6; } }
+        if (LA_YOK(-1)) { if (c2 < bcost) { bcost = c2; dir = 7; } }
+        if (LA_YOK(1))  { if (c3 < bcost) { bcost = c3; dir = 8; } }
+        bmv.x += c_square1[dir][0]; bmv.y += c_square1[dir][1];
+    }
+#undef LA_YOK
+#undef LA_COST3
+    if (bprecost < bcost) { bmv = bestpre; bcost = bprecost; }
+    else { bmv.x <<= 2; bmv.y <<= 2; }
+
+    if (!bcost)
+        bcost = m.mvc(bmv.x, bmv.y);
+    else
+    {   /* lowres subpel, motion.cpp:1496-1528: 4 half-pel SADs, re-measure with SATD, 4 quarter-pel SATDs */
+        int bdir = 0;
+        for (int i = 1; i <= 4; i++)
+        {
+            const int qx = bmv.x + c_square1[i][0] * 2, qy = bmv.y + c_square1[i][1] * 2;
+            if ((qy < qmin.y) | (qy > qmax.y)) continue;
+            const int cost = m.qpelSad(qx, qy) + m.mvc(qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bmv.x += c_square1[bdir][0] * 2; bmv.y += c_square1[bdir][1] * 2;
+        bcost = m.qpelSatd(bmv.x, bmv.y) + m.mvc(bmv.x, bmv.y);
+        bdir = 0;
+        for (int i = 1; i <= 4; i++)
+        {
+            const int qx = bmv.x + c_square1[i][0], qy = bmv.y + c_square1[i][1];
+            if ((qy < qmin.y) | (qy > qmax.y)) continue;
+            const int cost = m.qpelSatd(qx, qy) + m.mvc(qx, qy);
+            if (cost < bcost) { bcost = cost; bdir = i; }
+        }
+        bmv.x += c_square1[bdir][0]; bmv.y += c_square1[bdir][1];
+    }
+    out = bmv;
+    return bcost;
+}
+
+__device__ __forceinline__ MV2 unpackMv(int p) { MV2 m = { (int)(short)(p & 0xffff), p >> 16 }; return m; }
+__device__ __forceinline__ int packMv(MV2 m) { return (m.x & 0xffff) | (m.y << 16); }
+
+template <typename P>
+__global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nbands,
+                                                                  const unsigned short* __restrict__ mvcost,
+                                                                  int* ticketCounter, int* progress)
+{
+    extern __shared__ int s_mv[];                   /* LA_BAND_ROWS x bw packed MVs of this band */
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticketCounter, 1);
+    __syncthreads();
+    const int job = s_ticket / nbands, band = s_ticket % nbands;
+    const SearchJobDev<P> J = jobs[job];
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const unsigned gmask = groupMask();
+    const int bw = g.bw, bh = g.bh;
+    const int rowsInBand = min(LA_BAND_ROWS, bh - band * LA_BAND_ROWS);
+    const int cuY = bh - 1 - band * LA_BAND_ROWS - grp;
+    const bool lastRow = cuY == bh - 1;
+    const int steps = bw + 2 * (rowsInBand - 1);
+    int* myProgress = progress + job * nbands + band;
+    const int* belowProgress = myProgress - 1;
+    MeCtx<P> m;
+    m.mvcost = mvcost; m.r = r; m.gmask = gmask;
+    m.rb.planeSize = g.planeSize; m.rb.stride = g.stride;
+
+    for (int s = 0; s < steps; s++)
+    {
+        const int k = s - 2 * grp;
+        if (grp < rowsInBand && k >= 0 && k < bw)
+        {
+            const int cuX = bw - 1 - k;
+            const int cu = cuX + cuY * bw;
+            const long long pel = 8 * cuX + (long long)8 * cuY * g.stride;
+            m.fenc = loadRow(J.fenc0 + pel + (long long)r * g.stride);
+            m.rb.base = J.ref0 + pel;
+
+            /* reverse-order MV predictors (slicetype.cpp:4131-4141) */
+            int cand[4], numc = 0;
+            if (cuX < bw - 1) cand[numc++] = s_mv[grp * bw + cuX + 1];
+            if (!lastRow)
+            {
+                if (grp == 0)
+                {
+                    /* row below belongs to the previous band: wait until it has finished column cuX-1 */
+                    const int need = min(bw, k + 2);
+                    if (r == 0)
+                        while (ldAcquire(belowProgress) < need) __nanosleep(64);
+                    __syncwarp(gmask);
+                    const int* below = J.mvOut + (cuY + 1) * bw;
+                    cand[numc++] = __ldcg(below + cuX);
+                    if (cuX > 0) cand[numc++] = __ldcg(below + cuX - 1);
+                    if (cuX < bw - 1) cand[numc++] = __ldcg(below + cuX + 1);
+                }
+                else
+                {
+                    const int* below = s_mv + (grp - 1) * bw;
+                    cand[numc++] = below[cuX];
+                    if (cuX > 0) cand[numc++] = below[cuX - 1];
+                    if (cuX < bw - 1) cand[numc++] = below[cuX + 1];
+                }
+            }
+            MV2 mvp = { 0, 0 };
+            int skipCost = 0x7fffffff;
+            if (numc)
+            {
+                int mvpcost = LA_COST_MAX;
+                for (int i = 0; i < numc; i++)
+                {
+                    const MV2 c = unpackMv(cand[i]);
+                    const int cost = m.qpelSatd(c.x, c.y);
+                    if (cost < mvpcost) { mvpcost = cost; mvp = c; }
+                    if (!(mvp.x | mvp.y) && J.bidir)
+                        skipCost = cost;
+                }
+            }
+            const MV2 mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
+            const MV2 mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
+            MV2 best;
+            int fencCost = motionEstimate(m, mvmin, mvmax, mvp, best);
+            if (skipCost < 64 && skipCost < fencCost && J.bidir)
+            {
+                fencCost = skipCost;
+                best.x = best.y = 0;
+            }
+            if (r == 0)
+            {
+                const int packed = packMv(best);
+                s_mv[grp * bw + cuX] = packed;
+                __stcg(J.mvOut + cu, packed);
+                J.costOut[cu] = fencCost;
+                if (grp == rowsInBand - 1)
+                {
+                    __threadfence();
+                    stRelease(myProgress, k + 1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K5: frame cost.  Cost half of estimateCUCost (slicetype.cpp:4187-4248) + the frame sums of
+ * estimateFrameCost (:4050-4062).  P estimates need no pixels (one thread per block); B estimates
+ * evaluate the two bidir candidates with 8 lanes per block.  Sums are integer atomics, so the
+ * result does not depend on the order of accumulation.
+ * ------------------------------------------------------------------------------------------ */
+template <typename P>
+struct CostJobDev
+{
+    const P* fenc0; const P* ref0; const P* ref1;   /* lowresPlane[0] of b, p0, p1 (ref1 = NULL: P estimate) */
+    const int* mv0; const int* cost0; const int* mv1; const int* cost1;
+    const int* intraCost; const int* invQ;
+    unsigned short* lowresCosts; int* rowSatds; CostResultDev* result;
+};
+
+template <typename P>
+__global__ void __launch_bounds__(256) cost_clear_kernel(Geom g, const CostJobDev<P>* __restrict__ jobs)
+{
+    const CostJobDev<P> J = jobs[blockIdx.x];
+    for (int i = threadIdx.x; i < g.bh; i += blockDim.x) J.rowSatds[i] = 0;
+    if (threadIdx.x == 0) { J.result->costEst = 0; J.result->costEstAq = 0; J.result->intraMbs = 0; J.result->reserved = 0; }
+}
+
+template <typename P>
+__device__ __forceinline__ void costEpilogue(const Geom& g, const CostJobDev<P>& J, int cu, int bcost, int listused, bool bBidir,
+                                             unsigned long long* s_acc, int* s_intra)
+{
+    const int cuX = cu % g.bw, cuY = cu / g.bw;
+    const bool scored = (cuX > 0 && cuX < g.bw - 1 && cuY > 0 && cuY < g.bh - 1) || g.bw <= 2 || g.bh <= 2;
+    const int bcostAq = (scored && J.invQ) ? ((bcost * J.invQ[cu] + 128) >> 8) : bcost;
+    if (scored)
+    {
+        atomicAdd(&s_acc[0], (unsigned long long)bcost);
+        atomicAdd(&s_acc[1], (unsigned long long)bcostAq);
+        if (!listused && !bBidir) atomicAdd(s_intra, 1);
+    }
+    atomicAdd(&J.rowSatds[cuY], bcostAq);
+    J.lowresCosts[cu] = (unsigned short)(min(bcost, LA_LOWRES_COST_MASK) | (listused << LA_LOWRES_COST_SHIFT));
+}
+
+template <typename P>
+__global__ void __launch_bounds__(128) cost_kernel(Geom g, const CostJobDev<P>* __restrict__ jobs)
+{
+    __shared__ unsigned long long s_acc[2];
+    __shared__ int s_intra;
+    if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
+    if (threadIdx.x == 2) s_intra = 0;
+    __syncthreads();
+    const CostJobDev<P> J = jobs[blockIdx.y];
+    if (!J.ref1)
+    {   /* P estimate: one thread per block */
+        const int cu = blockIdx.x * 128 + threadIdx.x;
+        if (cu < g.ncu && blockIdx.x * 128 < g.ncu)
+        {
+            int bcost = J.cost0[cu] + 4, listused = 1;      /* COST_MAX > any search cost */
+            const int ic = J.intraCost[cu];
+            if (ic < bcost) { bcost = ic; listused = 0; }
+            costEpilogue(g, J, cu, bcost, listused, false, s_acc, &s_intra);
+        }
+    }
+    else
+    {   /* B estimate: 16 blocks per CTA */
+        const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+        const unsigned gmask = groupMask();
+        const int cu = blockIdx.x * 16 + grp;
+        if (cu < g.ncu)
+        {
+            const int cuX = cu % g.bw, cuY = cu / g.bw;
+            const long long pel = 8 * cuX + (long long)8 * cuY * g.stride;
+            int bcost = LA_COST_MAX, listused = 0;
+            const int c0 = J.cost0[cu], c1 = J.cost1[cu];
+            if (c0 < bcost) { bcost = c0; listused = 1; }
+            if (c1 < bcost) { bcost = c1; listused = 2; }
+            const Row<P> fenc = loadRow(J.fenc0 + pel + (long long)r * g.stride);
+            RefBlock<P> rb0 = { J.ref0 + pel, g.planeSize, g.stride }, rb1 = { J.ref1 + pel, g.planeSize, g.stride };
+            const MV2 m0 = unpackMv(J.mv0[cu]), m1 = unpackMv(J.mv1[cu]);
+            /* avg(L0 MC, L1 MC), unweighted references (slicetype.cpp:4189-4200) */
+            Row<P> a = avgRow(mcRow(rb0, m0.x, m0.y, r), mcRow(rb1, m1.x, m1.y, r));
+            int bicost = groupSatdRows(fenc, a, gmask);
+            if (bicost < bcost) { bcost = bicost; listused = 3; }
+            /* co-located average (:4201-4206) */
+            a = avgRow(loadRow(rb0.base + (long long)r * g.stride), loadRow(rb1.base + (long long)r * g.stride));
+            bicost = groupSatdRows(fenc, a, gmask);
+            if (bicost < bcost) { bcost = bicost; listused = 3; }
+            bcost += 4;
+            if (r == 0)
+                costEpilogue(g, J, cu, bcost, listused, true, s_acc, &s_intra);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (s_acc[0]) atomicAdd((unsigned long long*)&J.result->costEst, s_acc[0]);
+        if (s_acc[1]) atomicAdd((unsigned long long*)&J.result->costEstAq, s_acc[1]);
+        if (s_intra) atomicAdd(&J.result->intraMbs, s_intra);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K6: weighted prediction.  weight_pp_c over whole padded planes (pixel.cpp:518-541 as called
+ * from slicetype.cpp:833-842, 966-976) and weightCostLuma's whole-frame score (:845-858).
+ * ------------------------------------------------------------------------------------------ */
+template <typename P>
+__global__ void __launch_bounds__(256) weight_planes_kernel(const P* __restrict__ src, P* __restrict__ dst, long long n,
+                                                            int scale, int round, int shift, int offset, int correction, int maxv)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int val = (short)((int)src[i] << correction);
+    const int v = ((scale * val + round) >> shift) + offset;
+    dst[i] = (P)min(max(v, 0), maxv);
+}
+
+template <typename P>
+__global__ void __launch_bounds__(128) weight_cost_kernel(Geom g, const P* __restrict__ fenc0, const P* __restrict__ ref0,
+                                                          const int* __restrict__ intraCost, unsigned* result)
+{
+    __shared__ unsigned s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const unsigned gmask = groupMask();
+    const int cu = blockIdx.x * 16 + grp;
+    if (cu < g.ncu)
+    {
+        const long long pel = 8 * (cu % g.bw) + (long long)8 * (cu / g.bw) * g.stride;
+        const int satd = groupSatdRows(loadRow(ref0 + pel + (long long)r * g.stride), loadRow(fenc0 + pel + (long long)r * g.stride), gmask);
+        if (r == 0) atomicAdd(&s_sum, (unsigned)min(satd, intraCost[cu]));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(result, s_sum);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K7/K8: cuTree.  estimateCUPropagateCost (pixel.cpp:931-957) + the MV-directed scatter of
+ * Lookahead::estimateCUPropagate (slicetype.cpp:3537-3603); cuTreeFinish (:3784-3796);
+ * frameCostRecalculate (:3847-3878).  The reference's CLIP_ADD saturates a uint16 after every
+ * add; all addends are >= 0, so min(sum, 65535) taken when the value is read is identical and lets
+ * the scatter use plain 32-bit atomics in any order.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) cutree_propagate_kernel(Geom g, const int* __restrict__ intraCost,
+                                                               const unsigned short* __restrict__ lowresCosts,
+                                                               const int* __restrict__ invQ, const int* __restrict__ mv0,
+                                                               const int* __restrict__ mv1, const int* __restrict__ propagateIn,
+                                                               int* ref0, int* ref1, int bipredWeight, double fpsFactor)
+{
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu >= g.ncu) return;
+    const int bw = g.bw, bh = g.bh;
+    const int bx = cu % bw, by = cu / bw;
+    const double fps = __ddiv_rn(fpsFactor, 256.0);
+    const int intra = intraCost[cu];
+    const int lc = lowresCosts[cu];
+    const int inter = min(intra, lc & LA_LOWRES_COST_MASK);
+    const double propagateIntra = (double)(intra * invQ[cu]);
+    const int pin = propagateIn ? min(propagateIn[cu], 65535) : 0;
+    const double propagateAmount = __dadd_rn((double)pin, __dmul_rn(propagateIntra, fps));
+    const double propagateNum = (double)(intra - inter);
+    const int amount = (int)__dadd_rn(__ddiv_rn(__dmul_rn(propagateAmount, propagateNum), (double)intra), 0.5);
+    if (amount <= 0) return;
+    const int lists_used = lc >> LA_LOWRES_COST_SHIFT;
+    for (int list = 0; list < 2; list++)
+    {
+        if (!((lists_used >> list) & 1)) continue;
+        int listamount = amount;
+        if (lists_used == 3)
+            listamount = (listamount * (list ? 64 - bipredWeight : bipredWeight) + 32) >> 6;
+        int* ref = list ? ref1 : ref0;
+        const MV2 mv = unpackMv(list ? mv1[cu] : mv0[cu]);
+        if (!(mv.x | mv.y)) { atomicAdd(ref + cu, listamount); continue; }
+        int x = mv.x, y = mv.y;
+        const int cux = (x >> 5) + bx, cuy = (y >> 5) + by;
+        const int idx0 = cux + cuy * bw;
+        x &= 31; y &= 31;
+        const int w0 = (32 - y) * (32 - x), w1 = (32 - y) * x, w2 = y * (32 - x), w3 = y * x;
+        if (cux < bw && cuy < bh && cux >= 0 && cuy >= 0)             atomicAdd(ref + idx0, (listamount * w0 + 512) >> 10);
+        if (cux + 1 < bw && cuy < bh && cux + 1 >= 0 && cuy >= 0)     atomicAdd(ref + idx0 + 1, (listamount * w1 + 512) >> 10);
+        if (cux < bw && cuy + 1 < bh && cux >= 0 && cuy + 1 >= 0)     atomicAdd(ref + idx0 + bw, (listamount * w2 + 512) >> 10);
+        if (cux + 1 < bw && cuy + 1 < bh && cux + 1 >= 0 && cuy + 1 >= 0) atomicAdd(ref + idx0 + bw + 1, (listamount * w3 + 512) >> 10);
+    }
+}
+
+__global__ void __launch_bounds__(256) cutree_finish_kernel(Geom g, const int* __restrict__ intraCost, const int* __restrict__ invQ,
+                                                            const int* __restrict__ propagate, const double* __restrict__ qpAq,
+                                                            double* __restrict__ qpCuTree, int fpsFactor, double weightdelta,
+                                                            double strength)
+{
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu >= g.ncu) return;
+    const int intracost = (intraCost[cu] * invQ[cu] + 128) >> 8;
+    if (intracost)
+    {
+        const int propagateCost = (min(propagate[cu], 65535) * fpsFactor + 128) >> 8;
+        const double log2_ratio = __dadd_rn(__dadd_rn(log2((double)(intracost + propagateCost)), -log2((double)intracost)), weightdelta);
+        qpCuTree[cu] = __dadd_rn(qpAq[cu], -__dmul_rn(strength, log2_ratio));
+    }
+}
+
+__global__ void __launch_bounds__(256) cost_recalc_kernel(Geom g, const unsigned short* __restrict__ lowresCosts,
+                                                          const double* __restrict__ qpOffset, int* rowSatds,
+                                                          unsigned long long* score)
+{
+    __shared__ unsigned long long s_score;
+    if (threadIdx.x == 0) s_score = 0;
+    __syncthreads();
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu < g.ncu)
+    {
+        const int cux = cu % g.bw, cuy = cu / g.bw;
+        int cuCost = lowresCosts[cu] & LA_LOWRES_COST_MASK;
+        cuCost = (cuCost * exp2fix8(qpOffset[cu]) + 128) >> 8;
+        atomicAdd(&rowSatds[cuy], cuCost);
+        if ((cuy > 0 && cuy < g.bh - 1 && cux > 0 && cux < g.bw - 1) || g.bw <= 2 || g.bh <= 2)
+            atomicAdd(&s_score, (unsigned long long)cuCost);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_score) atomicAdd(score, s_score);
+}
+
+/* debug / unit-test kernel: SAD and SATD of n pairs of packed 8x8 blocks (mirrors the reference's
+ * check_pixelcmp, source/test/pixelharness.cpp:82) */
+template <typename P>
+__global__ void __launch_bounds__(128) block_metrics_kernel(const P* __restrict__ a, const P* __restrict__ b, int n,
+                                                            int* sadOut, int* satdOut)
+{
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const unsigned gmask = groupMask();
+    const int i = blockIdx.x * 16 + grp;
+    if (i >= n) return;
+    const Row<P> ra = loadRow(a + (long long)i * 64 + r * 8), rb = loadRow(b + (long long)i * 64 + r * 8);
+    const int sad = groupSum(sadRow(ra, rb), gmask);
+    const int satd = groupSatdRows(ra, rb, gmask);
+    if (r == 0) { sadOut[i] = sad; satdOut[i] = satd; }
+}
+
+} // namespace la
