@@ -178,12 +178,16 @@ int  x265cu_fetch_costs(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, uint1
 /* wait for everything enqueued on this context */
 int  x265cu_sync(x265cu_ctx* ctx);
 
+/* device-side stopwatch: CUDA events on the engine's compute stream (start ... stop -> elapsed ms) */
+int  x265cu_timer_start(x265cu_ctx* ctx);
+int  x265cu_timer_stop(x265cu_ctx* ctx, double* ms);
+
 /* counters for bench.py: kernels launched and bytes copied since create */
-typedef struct { uint64_t kernel_launches, h2d_bytes, d2h_bytes; } x265cu_counters;
+typedef struct { uint64_t kernel_launches, h2d_bytes, d2h_bytes, search_jobs, cost_jobs; } x265cu_counters;
 int  x265cu_get_counters(const x265cu_ctx* ctx, x265cu_counters* out);
 
 /* timing hook for bench.py: device time (ms, CUDA events on the engine's stream) spent in each
- * kernel family since the last reset; enabling it adds two event records per launch */
+ * kernel family since the last reset; enabling it adds two non-blocking event records per launch */
 #define X265CU_K_LOWRES 0
 #define X265CU_K_AQ     1
 #define X265CU_K_INTRA  2

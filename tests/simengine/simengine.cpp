@@ -71,6 +71,8 @@ int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* g) { *g = c->geom;
 int x265cu_pin_host(x265cu_ctx*, void*, uint64_t) { return 0; }
 int x265cu_unpin_host(x265cu_ctx*, void*) { return 0; }
 int x265cu_sync(x265cu_ctx*) { return 0; }
+int x265cu_timer_start(x265cu_ctx*) { return 0; }
+int x265cu_timer_stop(x265cu_ctx*, double* ms) { *ms = 0; return 0; }
 int x265cu_get_counters(const x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return 0; }
 int x265cu_profile_enable(x265cu_ctx*, int32_t) { return 0; }
 int x265cu_profile_get(x265cu_ctx*, double* ms, uint64_t* n, int32_t) { for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = 0; n[i] = 0; } return 0; }

@@ -51,7 +51,8 @@ class FrameOut(C.Structure):
 
 
 class Counters(C.Structure):
-    _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+    _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("search_jobs", C.c_uint64), ("cost_jobs", C.c_uint64)]
 
 
 K_NAMES = ["lowres", "aq", "intra", "search", "cost", "weight", "cutree"]
@@ -111,6 +112,8 @@ def load_engine(path=None):
     lib.x265cu_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.x265cu_profile_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int32]
     lib.x265cu_sync.argtypes = [C.c_void_p]
+    lib.x265cu_timer_start.argtypes = [C.c_void_p]
+    lib.x265cu_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.x265cu_pin_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.x265cu_unpin_host.argtypes = [C.c_void_p, C.c_void_p]
     return lib
@@ -148,6 +151,13 @@ class Lookahead:
         self.lib.x265la_get_geometry(self.h, C.byref(self.geom))
         self._keep = {}      # handle -> planes kept alive until the frame is released
         self.dtype = np.uint8 if depth == 8 else np.uint16
+
+    def add_picture_ptr(self, y_ptr, u_ptr, v_ptr, stride_y, stride_c, pts=0, slice_type=TYPE_AUTO):
+        """addPicture with raw pointers (host, pinned host or device memory); the caller keeps them alive."""
+        h = self.lib.x265la_add_picture(self.h, y_ptr, u_ptr, v_ptr, stride_y, stride_c, pts, slice_type)
+        if not h:
+            raise RuntimeError("addPicture failed: %s" % self.lib.x265la_last_error(self.h).decode())
+        return h
 
     def add_picture(self, y, u, v, pts=0, slice_type=TYPE_AUTO):
         y = np.ascontiguousarray(y, self.dtype)

@@ -43,8 +43,10 @@ struct x265cu_ctx
     x265cu_geometry geom;
     int bpp;
     SlotLayout lay;
-    cudaStream_t stream;
+    cudaStream_t stream;            /* every kernel and every D2H */
+    cudaStream_t copyStream;        /* picture uploads, so they overlap the kernels of earlier frames */
     std::vector<char*> slots;
+    std::vector<cudaEvent_t> slotCopied, slotConsumed;   /* per slot: upload done / source planes no longer needed */
     unsigned short* d_mvcost;       /* whole table; centre at +mvcost_half */
     char* d_jobs; size_t jobsCap;   /* device copy of the current job array */
     int* d_sync; size_t syncCap;    /* ticket counter + per-(job,band) progress */
@@ -55,7 +57,10 @@ struct x265cu_ctx
     bool profile;
     double profMs[X265CU_K_COUNT];
     uint64_t profN[X265CU_K_COUNT];
-    cudaEvent_t ev0, ev1;
+    struct EvPair { cudaEvent_t a, b; int kind; };
+    std::vector<EvPair> evPool;     /* non-blocking per-launch timing: resolved in x265cu_profile_get */
+    size_t evUsed;
+    cudaEvent_t tm0, tm1;           /* x265cu_timer_* */
     char err[256];
 };
 
@@ -69,27 +74,46 @@ bool cudaOk(x265cu_ctx* c, cudaError_t e, const char* what)
 }
 #define CK(call) do { if (!cudaOk(c, (call), #call)) return X265CU_ERR_CUDA; } while (0)
 
+/* Brackets the launches of one kernel family with a pair of CUDA events on the launching stream.
+ * Nothing blocks here; the pairs are resolved when the caller asks for the totals. */
 struct Prof
 {
-    x265cu_ctx* c; int k;
-    Prof(x265cu_ctx* ctx, int kind, int launches) : c(ctx), k(kind)
+    x265cu_ctx* c; int k; int idx;
+    Prof(x265cu_ctx* ctx, int kind, int launches) : c(ctx), k(kind), idx(-1)
     {
         c->counters.kernel_launches += launches;
         c->profN[k] += launches;
-        if (c->profile) cudaEventRecord(c->ev0, c->stream);
+        if (c->profile)
+        {
+            if (c->evUsed == c->evPool.size())
+            {
+                x265cu_ctx::EvPair e;
+                cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.kind = 0;
+                c->evPool.push_back(e);
+            }
+            idx = (int)c->evUsed++;
+            c->evPool[idx].kind = k;
+            cudaEventRecord(c->evPool[idx].a, c->stream);
+        }
     }
     ~Prof()
     {
-        if (c->profile)
-        {
-            cudaEventRecord(c->ev1, c->stream);
-            cudaEventSynchronize(c->ev1);
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-            c->profMs[k] += ms;
-        }
+        if (idx >= 0) cudaEventRecord(c->evPool[idx].b, c->stream);
     }
 };
+
+void resolveProfile(x265cu_ctx* c)
+{
+    if (!c->evUsed) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->evUsed; i++)
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->evPool[i].a, c->evPool[i].b) == cudaSuccess)
+            c->profMs[c->evPool[i].kind] += ms;
+    }
+    c->evUsed = 0;
+}
 
 template <typename T> T* slotPtr(x265cu_ctx* c, int slot, size_t off) { return (T*)(c->slots[slot] + off); }
 
@@ -128,15 +152,20 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     P* dY = slotPtr<P>(c, slot, L.srcY);
     P* dU = slotPtr<P>(c, slot, L.srcU);
     P* dV = slotPtr<P>(c, slot, L.srcV);
-    CK(cudaMemcpy2DAsync(dY, g.picW * sizeof(P), y, (size_t)sy * sizeof(P), g.picW * sizeof(P), g.picH, cudaMemcpyHostToDevice, c->stream));
+    /* the copy may not overwrite the staging planes while the previous tenant's K1/K2 still read them */
+    CK(cudaStreamWaitEvent(c->copyStream, c->slotConsumed[slot], 0));
+    /* cudaMemcpyDefault: the picture may live in host memory (pageable or pinned) or already in HBM */
+    CK(cudaMemcpy2DAsync(dY, g.picW * sizeof(P), y, (size_t)sy * sizeof(P), g.picW * sizeof(P), g.picH, cudaMemcpyDefault, c->copyStream));
     c->counters.h2d_bytes += (uint64_t)g.picW * g.picH * sizeof(P);
     const bool chroma = u && v;
     if (chroma && c->cfg.need_aq)
     {
-        CK(cudaMemcpy2DAsync(dU, g.cW * sizeof(P), u, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpy2DAsync(dV, g.cW * sizeof(P), v, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpy2DAsync(dU, g.cW * sizeof(P), u, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
+        CK(cudaMemcpy2DAsync(dV, g.cW * sizeof(P), v, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
         c->counters.h2d_bytes += 2ull * g.cW * g.cH * sizeof(P);
     }
+    CK(cudaEventRecord(c->slotCopied[slot], c->copyStream));
+    CK(cudaStreamWaitEvent(c->stream, c->slotCopied[slot], 0));
     /* stats + rowSatds00 start at zero */
     CK(cudaMemsetAsync(c->slots[slot] + L.rowSatds00, 0, L.stats + sizeof(FrameStatsDev) - L.rowSatds00, c->stream));
     P* planes = slotPtr<P>(c, slot, L.planes);
@@ -163,6 +192,7 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
                                                                   slotPtr<int>(c, slot, L.rowSatds00), stats);
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->slotConsumed[slot], c->stream));
     return X265CU_OK;
 }
 
@@ -235,6 +265,7 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
         dev[i].pad = 0;
     }
     const int nbands = (g.bh + LA_BAND_ROWS - 1) / LA_BAND_ROWS;
+    c->counters.search_jobs += n;
     int st = ensureDev(c, &c->d_jobs, &c->jobsCap, n * sizeof(SearchJobDev<P>));
     if (st) return st;
     st = ensureDev(c, (char**)&c->d_sync, &c->syncCap, (size_t)(1 + n * nbands) * sizeof(int));
@@ -284,6 +315,7 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         d.rowSatds = (int*)(cs + L.costRowOff);
         d.result = (CostResultDev*)(cs + L.costResOff);
     }
+    c->counters.cost_jobs += n;
     int st = ensureDev(c, &c->d_jobs, &c->jobsCap, n * sizeof(CostJobDev<P>));
     if (st) return st;
     CK(cudaMemcpyAsync(c->d_jobs, &dev[0], n * sizeof(CostJobDev<P>), cudaMemcpyHostToDevice, c->stream));
@@ -400,7 +432,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     x265cu_ctx* c = new (std::nothrow) x265cu_ctx();
     if (!c) return X265CU_ERR_NO_MEMORY;
     c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_jobs = NULL; c->jobsCap = 0; c->d_sync = NULL; c->syncCap = 0;
-    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->profile = false;
+    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->profile = false; c->evUsed = 0;
     memset(&c->counters, 0, sizeof(c->counters)); memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN));
     c->bpp = cfg->depth > 8 ? 2 : 1;
 
@@ -450,7 +482,8 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 
     int rc = X265CU_OK;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
-    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    if (cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return X265CU_ERR_CUDA; }
+    cudaEventCreate(&c->tm0); cudaEventCreate(&c->tm1);
     const size_t tabBytes = (2 * (size_t)cfg->mvcost_half + 1) * sizeof(unsigned short);
     if (cudaMalloc((void**)&c->d_mvcost, tabBytes) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     if (!rc && cudaMemcpy(c->d_mvcost, cfg->mvcost, tabBytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = X265CU_ERR_CUDA;
@@ -459,6 +492,9 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
         char* p = NULL;
         if (cudaMalloc((void**)&p, L.total) != cudaSuccess) { rc = X265CU_ERR_NO_MEMORY; break; }
         c->slots.push_back(p);
+        cudaEvent_t e0, e1;
+        cudaEventCreateWithFlags(&e0, cudaEventDisableTiming); cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
+        c->slotCopied.push_back(e0); c->slotConsumed.push_back(e1);
         /* planes must start zeroed: columns past the right margin are never written (K1) */
         if (cudaMemsetAsync(p, 0, L.total, c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
     }
@@ -477,12 +513,16 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 void x265cu_destroy(x265cu_ctx* c)
 {
     if (!c) return;
+    cudaStreamSynchronize(c->copyStream);
     cudaStreamSynchronize(c->stream);
     for (size_t i = 0; i < c->slots.size(); i++) cudaFree(c->slots[i]);
+    for (size_t i = 0; i < c->slotCopied.size(); i++) { cudaEventDestroy(c->slotCopied[i]); cudaEventDestroy(c->slotConsumed[i]); }
+    for (size_t i = 0; i < c->evPool.size(); i++) { cudaEventDestroy(c->evPool[i].a); cudaEventDestroy(c->evPool[i].b); }
     for (size_t i = 0; i < c->weightScratch.size(); i++) cudaFree(c->weightScratch[i]);
     cudaFree(c->d_mvcost); cudaFree(c->d_jobs); cudaFree(c->d_sync); cudaFree(c->d_results);
     if (c->h_results) cudaFreeHost(c->h_results);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
+    cudaStreamDestroy(c->copyStream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -500,14 +540,28 @@ int x265cu_unpin_host(x265cu_ctx* c, void* ptr)
     return X265CU_OK;
 }
 
-int x265cu_sync(x265cu_ctx* c) { CK(cudaStreamSynchronize(c->stream)); return X265CU_OK; }
+int x265cu_sync(x265cu_ctx* c) { CK(cudaStreamSynchronize(c->copyStream)); CK(cudaStreamSynchronize(c->stream)); return X265CU_OK; }
+
+/* device-side stopwatch on the engine's compute stream (bench.py times its steps with it) */
+int x265cu_timer_start(x265cu_ctx* c) { CK(cudaEventRecord(c->tm0, c->stream)); return X265CU_OK; }
+int x265cu_timer_stop(x265cu_ctx* c, double* ms)
+{
+    CK(cudaStreamSynchronize(c->copyStream));
+    CK(cudaEventRecord(c->tm1, c->stream));
+    CK(cudaEventSynchronize(c->tm1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->tm0, c->tm1));
+    *ms = f;
+    return X265CU_OK;
+}
 
 int x265cu_get_counters(const x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return X265CU_OK; }
 
-int x265cu_profile_enable(x265cu_ctx* c, int32_t on) { c->profile = on != 0; return X265CU_OK; }
+int x265cu_profile_enable(x265cu_ctx* c, int32_t on) { resolveProfile(c); c->profile = on != 0; return X265CU_OK; }
 
 int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset)
 {
+    resolveProfile(c);
     for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = c->profMs[i]; launches[i] = c->profN[i]; }
     if (reset) { memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN)); }
     return X265CU_OK;
@@ -678,7 +732,11 @@ int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
     if (o->intra_mode && !st) st = d2h(c, o->intra_mode, c->slots[slot] + L.intraMode, (size_t)g.ncu);
     if (o->qp_aq_offset && !st) st = d2h(c, o->qp_aq_offset, c->slots[slot] + L.qpAq, (size_t)g.ncu * 8);
     if (o->qp_cutree_offset && !st) st = d2h(c, o->qp_cutree_offset, c->slots[slot] + L.qpCuTree, (size_t)g.ncu * 8);
-    if (o->inv_qscale_factor && !st) st = d2h(c, o->inv_qscale_factor, c->slots[slot] + L.invQ, (size_t)g.ncu * 4);
+    if (o->inv_qscale_factor && !st)
+    {
+        if (c->cfg.need_aq) st = d2h(c, o->inv_qscale_factor, c->slots[slot] + L.invQ, (size_t)g.ncu * 4);
+        else for (int i = 0; i < g.ncu; i++) o->inv_qscale_factor[i] = 256;   /* no AQ arrays: neutral scale */
+    }
     if (o->propagate_cost && !st)
     {
         st = ensureDev(c, &c->d_results, &c->resultsCap, (size_t)g.ncu * 2);
