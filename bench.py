@@ -243,6 +243,10 @@ def main():
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1000.0
         cnt1 = pkg.Counters(); eng.x265cu_get_counters(ctx, C.byref(cnt1))
+        ht = (C.c_double * 8)()
+        la.lib.x265la_get_timers(la.h, ht, 1)
+        host_t = dict(prelookahead_wait=ht[0], weightp=ht[1], enqueue=ht[2], result_wait=ht[3], decisions=ht[4],
+                      slicetype_decide=ht[5], calls=ht[6], wall=wall / 1000.0)
         pm = (C.c_double * 7)(); pn = (C.c_uint64 * 7)()
         eng.x265cu_profile_get(ctx, pm, pn, 1)
         prof = {k: (pm[i], int(pn[i])) for i, k in enumerate(pkg.K_NAMES)}
@@ -251,6 +255,7 @@ def main():
                      cost_jobs=cnt1.cost_jobs - cnt0.cost_jobs)
         assert len(types) == len(pics), (len(types), len(pics))
         la.close()
+        prof["host"] = host_t
         return max(ms.value, 0.0), wall, types, delta, prof
 
     def reduce_max(x):
@@ -304,6 +309,7 @@ def main():
                 "search_launches_per_step": s_launch // max(1, len(profs)),
                 "avg_launch_ms": round(s_ms / max(1, s_launch), 4),
                 "kernel_ms_per_step": kernel_ms,
+                "host_ms_per_step": {k: round(1000.0 * sum(p["host"][k] for p in profs) / len(profs), 2) for k in profs[0]["host"]},
                 "note": "K4 runs out of L2 and is bound by the integer pipe / wavefront latency, not HBM (SURVEY 8d); "
                         "the HBM fraction is the conservative checkable figure, see profiles/ for pipe utilisation"}
 

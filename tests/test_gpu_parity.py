@@ -58,6 +58,61 @@ def test_block_metrics_vs_oracle(depth, pkg, simdir):
     la.close()
 
 
+@pytest.mark.parametrize("depth", [8, 10])
+def test_tiled_motion_compensation_vs_oracle(depth, pkg, synth, simdir):
+    """T1: the tiled row fetch + lowresMC + SAD/SATD (lowresQPelCost, lowres.h:98-124) for random blocks and
+    quarter-pel vectors, including vectors that reach into the plane margins"""
+    w, h = 328, 184
+    la = pkg.Lookahead(w, h, depth=depth)
+    eng = pkg.load_engine()
+    seq = synth.SynthSequence(w, h, depth=depth, seed=9)
+    la.add_picture(*seq.frame(0)); la.add_picture(*seq.frame(3))
+    ctx = la.engine()
+    g = la.geom
+    dt = np.uint8 if depth == 8 else np.uint16
+    planes = []
+    eng.x265cu_fetch_frame.argtypes = [C.c_void_p, C.c_int32, C.POINTER(pkg.FrameOut)]
+    for slot in (0, 1):
+        pl = np.zeros((4, g.plane_lines, g.stride), dt)
+        fo = pkg.FrameOut(); fo.planes = pl.ctypes.data
+        assert eng.x265cu_fetch_frame(ctx, slot, C.byref(fo)) == 0
+        planes.append(pl)
+    orc = C.CDLL(os.path.join(simdir, "liboracle%d.so" % depth))
+    rng = np.random.default_rng(11)
+    n = 2048
+    cu = rng.integers(0, g.ncu, n).astype(np.int32)
+    mv = rng.integers(-60, 61, (n, 2)).astype(np.int32)
+    mv[:64] = 0
+    # vectors to the allowed extremes: frame edge +- 8 full-pel, plus the hexagon overshoot
+    for i in range(64, 192):
+        cx, cy = cu[i] % g.bw, cu[i] // g.bw
+        mv[i, 0] = 4 * rng.choice([-cx * 8 - 12, (g.bw - cx - 1) * 8 + 12]) + rng.integers(0, 4)
+        mv[i, 1] = 4 * rng.choice([-cy * 8 - 11, (g.bh - cy - 1) * 8 + 11]) + rng.integers(0, 4)
+    sad = np.zeros(n, np.int32); satd = np.zeros(n, np.int32)
+    eng.x265cu_debug_mc_metrics.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    assert eng.x265cu_debug_mc_metrics(ctx, 1, 0, cu.ctypes.data, mv.ctypes.data, n, sad.ctypes.data, satd.ctypes.data) == 0
+    mx, my = g.margin_x, g.margin_y
+
+    def blk(pl, X, Y):
+        return pl[Y:Y + 8, X:X + 8].astype(np.int64)
+    for i in range(n):
+        cx, cy = cu[i] % g.bw, cu[i] // g.bw
+        X0, Y0 = mx + 8 * cx, my + 8 * cy
+        qx, qy = int(mv[i, 0]), int(mv[i, 1])
+        fenc = np.ascontiguousarray(blk(planes[1][0], X0, Y0).astype(dt))
+        hA = (qy & 2) | ((qx & 2) >> 1)
+        A = blk(planes[0][hA], X0 + (qx >> 2), Y0 + (qy >> 2))
+        if (qx | qy) & 1:
+            qx2, qy2 = qx + (qx & 1), qy + (qy & 1)
+            hB = (qy2 & 2) | ((qx2 & 2) >> 1)
+            B = blk(planes[0][hB], X0 + (qx2 >> 2), Y0 + (qy2 >> 2))
+            A = (A + B + 1) >> 1
+        pred = np.ascontiguousarray(A.astype(dt))
+        assert sad[i] == int(np.abs(fenc.astype(np.int64) - A).sum()), (i, cu[i], mv[i])
+        assert satd[i] == orc.or_satd8x8(fenc.ctypes.data_as(C.c_void_p), 8, pred.ctypes.data_as(C.c_void_p), 8), (i, cu[i], mv[i])
+    la.close()
+
+
 @pytest.mark.parametrize("name", cases.GOLDEN)
 def test_cuda_pipeline_matches_golden(name, pkg, synth):
     case = cases.get_case(name)

@@ -1,0 +1,33 @@
+"""Summarise an .ncu-rep (raw page) into the handful of metrics that matter for these kernels."""
+import csv, subprocess, sys
+WANT = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_warps',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
+        'l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed']
+STALL = 'smsp__average_warp'
+def main(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print('=' * 100)
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print('%-75s %s %s' % (w, r[i][:90], units[i]))
+        stalls = []
+        for i, h in enumerate(hdr):
+            if 'warp_issue_stalled' in h and h.endswith('_per_warp_active.pct'):
+                try: stalls.append((float(r[i]), h.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', '')))
+                except ValueError: pass
+        stalls.sort(reverse=True)
+        print('stall reasons (% of warp-active cycles): ' + ', '.join('%s %.1f' % (n, v) for v, n in stalls[:10]))
+if __name__ == '__main__':
+    main(sys.argv[1])

@@ -93,6 +93,7 @@ def load_lib(path=None):
     lib.x265la_frame_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.x265la_frame_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FrameOut)]
     lib.x265la_frame_weights.argtypes = [C.c_void_p] * 6
+    lib.x265la_get_timers.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int32]
     lib.x265la_engine.restype = C.c_void_p
     lib.x265la_engine.argtypes = [C.c_void_p]
     _libs[path] = lib

@@ -171,8 +171,8 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     P* planes = slotPtr<P>(c, slot, L.planes);
     {
         Prof pr(c, X265CU_K_LOWRES, 1);
-        dim3 block(256), grid((g.stride / 4 + 255) / 256, g.planeLines);
-        lowres_kernel<P><<<grid, block, 0, c->stream>>>(g, dY, planes);
+        const long long threads = (long long)g.tpr * (g.planeLines >> 3) * 16;
+        lowres_kernel<P><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(g, dY, planes);
     }
     FrameStatsDev* stats = slotPtr<FrameStatsDev>(c, slot, L.stats);
     int* invQ = slotPtr<int>(c, slot, L.invQ);
@@ -186,7 +186,7 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     }
     {
         Prof pr(c, X265CU_K_INTRA, 1);
-        intra_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, planes + g.padOffset, c->cfg.need_aq ? invQ : NULL,
+        intra_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, planes, c->cfg.need_aq ? invQ : NULL,
                                                                   slotPtr<int>(c, slot, L.intraCost), slotPtr<unsigned char>(c, slot, L.intraMode),
                                                                   slotPtr<unsigned short>(c, slot, L.lowresCosts00),
                                                                   slotPtr<int>(c, slot, L.rowSatds00), stats);
@@ -256,8 +256,8 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
                 idx = it->second;
             refBuf = (const P*)c->weightScratch[idx];
         }
-        dev[i].fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes) + g.padOffset;
-        dev[i].ref0 = refBuf + g.padOffset;
+        dev[i].fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes);
+        dev[i].ref0 = refBuf;
         char* st = mvStorePtr(c, j.fenc_slot, j.store);
         dev[i].mvOut = (int*)st;
         dev[i].costOut = (int*)st + g.ncu;
@@ -296,9 +296,9 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
             j.l0_store < 0 || j.l0_store >= c->geom.n_mv_stores || j.l1_store >= c->geom.n_mv_stores)
         { snprintf(c->err, sizeof(c->err), "cost job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
         CostJobDev<P>& d = dev[i];
-        d.fenc0 = slotPtr<P>(c, j.b_slot, L.planes) + g.padOffset;
-        d.ref0 = slotPtr<P>(c, j.p0_slot, L.planes) + g.padOffset;
-        d.ref1 = j.l1_store >= 0 ? slotPtr<P>(c, j.p1_slot, L.planes) + g.padOffset : NULL;
+        d.fenc0 = slotPtr<P>(c, j.b_slot, L.planes);
+        d.ref0 = slotPtr<P>(c, j.p0_slot, L.planes);
+        d.ref1 = j.l1_store >= 0 ? slotPtr<P>(c, j.p1_slot, L.planes) : NULL;
         anyB |= j.l1_store >= 0;
         char* m0 = mvStorePtr(c, j.b_slot, j.l0_store);
         d.mv0 = (const int*)m0; d.cost0 = (const int*)m0 + g.ncu;
@@ -358,8 +358,8 @@ int weightCostT(x265cu_ctx* c, const x265cu_wcost_job* jobs, int n, uint32_t* co
             ref = (const P*)c->weightScratch[0];
         }
         Prof pr(c, X265CU_K_WEIGHT, 1);
-        weight_cost_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, slotPtr<P>(c, j.fenc_slot, L.planes) + g.padOffset,
-                                                                        ref + g.padOffset, slotPtr<int>(c, j.fenc_slot, L.intraCost),
+        weight_cost_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, slotPtr<P>(c, j.fenc_slot, L.planes),
+                                                                        ref, slotPtr<int>(c, j.fenc_slot, L.intraCost),
                                                                         (unsigned*)c->d_results + i);
     }
     CK(cudaGetLastError());
@@ -386,6 +386,25 @@ int blockMetricsT(x265cu_ctx* c, const void* a, const void* b, int n, int32_t* s
     CK(cudaMemcpyAsync(satd, dt, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(da); cudaFree(db); cudaFree(ds); cudaFree(dt);
+    return X265CU_OK;
+}
+
+template <typename P>
+int mcMetricsT(x265cu_ctx* c, int fencSlot, int refSlot, const int32_t* cuIdx, const int32_t* mvs, int n, int32_t* sad, int32_t* satd)
+{
+    int *dc = NULL, *dm = NULL, *ds = NULL, *dt = NULL;
+    CK(cudaMalloc((void**)&dc, n * sizeof(int))); CK(cudaMalloc((void**)&dm, 2 * n * sizeof(int)));
+    CK(cudaMalloc((void**)&ds, n * sizeof(int))); CK(cudaMalloc((void**)&dt, n * sizeof(int)));
+    CK(cudaMemcpyAsync(dc, cuIdx, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dm, mvs, 2 * n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    mc_metrics_kernel<P><<<(n + 15) / 16, 128, 0, c->stream>>>(c->g, slotPtr<P>(c, fencSlot, c->lay.planes), slotPtr<P>(c, refSlot, c->lay.planes),
+                                                               dc, dm, n, ds, dt);
+    c->counters.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sad, ds, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(satd, dt, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dc); cudaFree(dm); cudaFree(ds); cudaFree(dt);
     return X265CU_OK;
 }
 
@@ -449,6 +468,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     g.planeSize = (long long)g.stride * g.planeLines;
     g.padOffset = (long long)g.stride * g.my + g.mx;
     g.lambda = cfg->lambda; g.depth = cfg->depth; g.nb = cfg->bframes + 2;
+    g.tpr = g.stride / 8;
     x265cu_geometry& G = c->geom;
     G.low_width = g.w; G.low_height = g.h; G.bw = g.bw; G.bh = g.bh; G.ncu = g.ncu; G.stride = g.stride;
     G.plane_lines = g.planeLines; G.margin_x = g.mx; G.margin_y = g.my; G.nb = g.nb;
@@ -745,9 +765,24 @@ int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
             clamp_u16_kernel<<<(g.ncu + 255) / 256, 256, 0, c->stream>>>(slotPtr<int>(c, slot, L.propagate), (unsigned short*)c->d_results, g.ncu);
             c->counters.kernel_launches++;
             st = d2h(c, o->propagate_cost, c->d_results, (size_t)g.ncu * 2);
+            if (!st && cudaStreamSynchronize(c->stream) != cudaSuccess) st = X265CU_ERR_CUDA;   /* d_results is reused below */
         }
     }
-    if (o->planes && !st) st = d2h(c, o->planes, c->slots[slot] + L.planes, (size_t)(4 * g.planeSize) * c->bpp);
+    if (o->planes && !st)
+    {
+        /* planes live tiled in HBM; the mirror is the reference's pitched Lowres::buffer[0..3] */
+        const size_t bytes = (size_t)(4 * g.planeSize) * c->bpp;
+        st = ensureDev(c, &c->d_results, &c->resultsCap, bytes);
+        if (!st)
+        {
+            const unsigned blocks = (unsigned)((4 * g.planeSize + 255) / 256);
+            if (c->bpp == 1) detile_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>(g, slotPtr<uint8_t>(c, slot, L.planes), (uint8_t*)c->d_results);
+            else detile_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>(g, slotPtr<uint16_t>(c, slot, L.planes), (uint16_t*)c->d_results);
+            c->counters.kernel_launches++;
+            st = d2h(c, o->planes, c->d_results, bytes);
+            if (!st && cudaStreamSynchronize(c->stream) != cudaSuccess) st = X265CU_ERR_CUDA;   /* d_results is reused below */
+        }
+    }
     if (o->lowres_costs00 && !st) st = d2h(c, o->lowres_costs00, c->slots[slot] + L.lowresCosts00, (size_t)g.ncu * 2);
     if (o->row_satds00 && !st) st = d2h(c, o->row_satds00, c->slots[slot] + L.rowSatds00, (size_t)g.bh * 4);
     if (st) return st;
@@ -792,6 +827,15 @@ int x265cu_debug_block_metrics(x265cu_ctx* c, const void* a, const void* b, int3
 {
     if (!c || !a || !b || n <= 0) return X265CU_ERR_BAD_ARG;
     return DISPATCH(blockMetricsT, c, a, b, n, sad, satd);
+}
+
+/* unit-test hook: lowresQPelCost (SAD and SATD) of n (block index, quarter-pel MV) pairs, fenc vs ref slot */
+int x265cu_debug_mc_metrics(x265cu_ctx* c, int32_t fenc_slot, int32_t ref_slot, const int32_t* cu_idx, const int32_t* mvs, int32_t n,
+                            int32_t* sad, int32_t* satd)
+{
+    if (!c || !slotOk(c, fenc_slot) || !slotOk(c, ref_slot) || n <= 0) return X265CU_ERR_BAD_ARG;
+    CK(cudaStreamSynchronize(c->copyStream));
+    return DISPATCH(mcMetricsT, c, fenc_slot, ref_slot, cu_idx, mvs, n, sad, satd);
 }
 
 } // extern "C"

@@ -1,11 +1,20 @@
 /* la_device.cuh -- device primitives shared by the lookahead kernels (sm_100a).
  *
  * Work decomposition used by every block-level kernel: ONE 8x8 LOWRES BLOCK = 8 LANES, lane r owns
- * pixel row r of the block.  A row of 8 samples lives in registers as packed words (2 x u32 for
- * 8-bit, 4 x u32 for 16-bit samples) so SAD / averaging run on the packed-integer SIMD path
- * (__vsadu4/__vavgu4, __vsadu2/__vavgu2) and the Hadamard butterflies run as SWAR adds plus
- * warp shuffles inside the 8-lane group.  No tensor cores: this is integer
- * sum-of-absolute-(transformed-)differences, not a contraction.
+ * pixel row r of the block; a warp always works on 4 blocks in lockstep (control flow is kept
+ * warp-uniform with predicates), so every shuffle runs with the full mask and stays inside its
+ * 8-lane group by construction (xor 1/2/4).  A row of 8 samples lives in registers as packed words
+ * (2 x u32 for 8-bit, 4 x u32 for 16-bit samples) so SAD / averaging run on the packed-integer SIMD
+ * path (__vsadu4/__vavgu4, __vsadu2/__vavgu2) and the Hadamard butterflies run as SWAR adds plus
+ * warp shuffles.  No tensor cores: this is integer sum-of-absolute-(transformed-)differences, not a
+ * contraction.
+ *
+ * Plane layout in HBM: the four half-pel planes are stored TILED, 8x8 samples per tile (one 128-byte
+ * line for 16-bit samples, half a line for 8-bit), tiles in raster order over the padded plane.  An
+ * arbitrary 8x8 block then touches at most 4 tiles (instead of 8-16 separate lines in a pitched
+ * layout), and a lane fetches its row with two aligned vector loads (2 x LDG.128 / 2 x LDG.64).
+ * ncu on the first (pitched, 32-bit-load) version showed the L1 tag stage at 83 % and issue at 22 %:
+ * one warp-level load touched 32 different lines.  Host mirrors are de-tiled on fetch.
  *
  * Arithmetic definitions (what must be bit-exact) come from the reference's C primitives:
  *   SAD 8x8            source/common/pixel.cpp:40-56
@@ -19,6 +28,8 @@
 
 namespace la {
 
+#define LA_FULL 0xffffffffu
+
 struct Geom
 {
     int picW, picH, cW, cH;     /* full-res luma / chroma size */
@@ -26,37 +37,82 @@ struct Geom
     int mx, my, stride, planeLines;
     long long planeSize, padOffset;
     int lambda, depth, nb;
+    int tpr;                    /* tiles per plane row = stride / 8 */
 };
+
+/* sample offset of buffer coordinate (X, Y) (margins included, X,Y >= 0) inside a tiled plane */
+__host__ __device__ __forceinline__ long long tileOff(int X, int Y, int tpr)
+{
+    return ((long long)((Y >> 3) * tpr + (X >> 3)) << 6) + ((Y & 7) << 3) + (X & 7);
+}
 
 template <typename P> struct Row;
 template <> struct Row<uint8_t>  { uint32_t v[2]; };
 template <> struct Row<uint16_t> { uint32_t v[4]; };
 
-/* 8 samples starting at an arbitrary sample address: aligned 32-bit loads + funnel shift.
- * Reads up to 3 bytes past the row; every plane buffer is allocated with tail padding. */
-__device__ __forceinline__ Row<uint8_t> loadRow(const uint8_t* p)
+/* 8 samples of row Y starting at column X of a tiled plane: two aligned vector loads + funnel shift */
+__device__ __forceinline__ Row<uint8_t> loadRowT(const uint8_t* plane, int tpr, int X, int Y)
 {
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a & 3) * 8;
-    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    const uint8_t* t = plane + (((long long)((Y >> 3) * tpr + (X >> 3))) << 6) + ((Y & 7) << 3);
+    const uint2 a = __ldg((const uint2*)t);
+    const uint2 b = __ldg((const uint2*)(t + 64));
+    const int fx = X & 7;
+    const bool s1 = fx & 4;
+    const uint32_t u0 = s1 ? a.y : a.x, u1 = s1 ? b.x : a.y, u2 = s1 ? b.y : b.x;
+    const uint32_t sh = (uint32_t)(fx & 3) * 8;
     Row<uint8_t> r;
-    r.v[0] = __funnelshift_r(w0, w1, sh);
-    r.v[1] = __funnelshift_r(w1, w2, sh);
+    r.v[0] = __funnelshift_r(u0, u1, sh);
+    r.v[1] = __funnelshift_r(u1, u2, sh);
     return r;
 }
 
-__device__ __forceinline__ Row<uint16_t> loadRow(const uint16_t* p)
+__device__ __forceinline__ Row<uint16_t> loadRowT(const uint16_t* plane, int tpr, int X, int Y)
 {
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a & 2) * 8;
-    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = __ldg(q + 4);
+    const uint16_t* t = plane + (((long long)((Y >> 3) * tpr + (X >> 3))) << 6) + ((Y & 7) << 3);
+    const uint4 a = __ldg((const uint4*)t);
+    const uint4 b = __ldg((const uint4*)(t + 64));
+    const int fx = X & 7;
+    const bool s2 = fx & 4, s1 = fx & 2;
+    /* words needed: W[ws .. ws+4], ws = fx >> 1 */
+    const uint32_t u0 = s2 ? a.z : a.x, u1 = s2 ? a.w : a.y, u2 = s2 ? b.x : a.z, u3 = s2 ? b.y : a.w,
+                   u4 = s2 ? b.z : b.x, u5 = s2 ? b.w : b.y;
+    const uint32_t t0 = s1 ? u1 : u0, t1 = s1 ? u2 : u1, t2 = s1 ? u3 : u2, t3 = s1 ? u4 : u3, t4 = s1 ? u5 : u4;
+    const uint32_t sh = (uint32_t)(fx & 1) * 16;
     Row<uint16_t> r;
-    r.v[0] = __funnelshift_r(w0, w1, sh);
-    r.v[1] = __funnelshift_r(w1, w2, sh);
-    r.v[2] = __funnelshift_r(w2, w3, sh);
-    r.v[3] = __funnelshift_r(w3, w4, sh);
+    r.v[0] = __funnelshift_r(t0, t1, sh);
+    r.v[1] = __funnelshift_r(t1, t2, sh);
+    r.v[2] = __funnelshift_r(t2, t3, sh);
+    r.v[3] = __funnelshift_r(t3, t4, sh);
+    return r;
+}
+
+/* row of a block whose column is a multiple of 8: one vector load */
+__device__ __forceinline__ Row<uint8_t> loadRowAligned(const uint8_t* plane, int tpr, int X, int Y)
+{
+    const uint2 a = __ldg((const uint2*)(plane + (((long long)((Y >> 3) * tpr + (X >> 3))) << 6) + ((Y & 7) << 3)));
+    Row<uint8_t> r; r.v[0] = a.x; r.v[1] = a.y;
+    return r;
+}
+__device__ __forceinline__ Row<uint16_t> loadRowAligned(const uint16_t* plane, int tpr, int X, int Y)
+{
+    const uint4 a = __ldg((const uint4*)(plane + (((long long)((Y >> 3) * tpr + (X >> 3))) << 6) + ((Y & 7) << 3)));
+    Row<uint16_t> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    return r;
+}
+
+/* pitched (ordinary) memory: 8 samples at an arbitrary sample address (used by the unit-test kernel) */
+__device__ __forceinline__ Row<uint8_t> loadRowPitched(const uint8_t* p)
+{
+    Row<uint8_t> r; r.v[0] = r.v[1] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i >> 2] |= (uint32_t)p[i] << ((i & 3) * 8);
+    return r;
+}
+__device__ __forceinline__ Row<uint16_t> loadRowPitched(const uint16_t* p)
+{
+    Row<uint16_t> r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i >> 1] |= (uint32_t)p[i] << ((i & 1) * 16);
     return r;
 }
 
@@ -89,15 +145,16 @@ __device__ __forceinline__ int sadRow(const Row<uint16_t>& a, const Row<uint16_t
 __device__ __forceinline__ int px(const Row<uint8_t>& r, int i)  { return (int)((r.v[i >> 2] >> ((i & 3) * 8)) & 0xffu); }
 __device__ __forceinline__ int px(const Row<uint16_t>& r, int i) { return (int)((r.v[i >> 1] >> ((i & 1) * 16)) & 0xffffu); }
 
-__device__ __forceinline__ void setPx(Row<uint8_t>& r, int i, int val)
+/* build a row from 8 sample values (compile-time indices after unrolling) */
+__device__ __forceinline__ void packRow(Row<uint8_t>& r, const int v[8])
 {
-    const int sh = (i & 3) * 8;
-    r.v[i >> 2] = (r.v[i >> 2] & ~(0xffu << sh)) | ((uint32_t)val << sh);
+    r.v[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    r.v[1] = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
 }
-__device__ __forceinline__ void setPx(Row<uint16_t>& r, int i, int val)
+__device__ __forceinline__ void packRow(Row<uint16_t>& r, const int v[8])
 {
-    const int sh = (i & 1) * 16;
-    r.v[i >> 1] = (r.v[i >> 1] & ~(0xffffu << sh)) | ((uint32_t)val << sh);
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.v[i] = (uint32_t)v[2 * i] | ((uint32_t)v[2 * i + 1] << 16);
 }
 
 template <typename P>
@@ -107,14 +164,12 @@ __device__ __forceinline__ void diffRow(const Row<P>& a, const Row<P>& b, int d[
     for (int i = 0; i < 8; i++) d[i] = px(a, i) - px(b, i);
 }
 
-/* the 8 lanes of one block: lanes [8k, 8k+8) of the warp */
-__device__ __forceinline__ unsigned groupMask() { return 0xFFu << ((threadIdx.x & 31u) & ~7u); }
-
-__device__ __forceinline__ int groupSum(int v, unsigned gmask)
+/* sum over the 8 lanes of a group; the whole warp must call it converged */
+__device__ __forceinline__ int groupSum(int v)
 {
-    v += __shfl_xor_sync(gmask, v, 1);
-    v += __shfl_xor_sync(gmask, v, 2);
-    v += __shfl_xor_sync(gmask, v, 4);
+    v += __shfl_xor_sync(LA_FULL, v, 1);
+    v += __shfl_xor_sync(LA_FULL, v, 2);
+    v += __shfl_xor_sync(LA_FULL, v, 4);
     return v;
 }
 
@@ -125,12 +180,12 @@ __device__ __forceinline__ uint32_t abs2(uint32_t a)
     return (a + s) ^ s;
 }
 
-/* 8x8 SATD of the group's block from each lane's row of differences.  The reference sums two
- * 8x4 SATDs, each = (sum |4x4 Hadamard coefficients| of its two 4x4 blocks) >> 1.  Lanes 0-3 hold
- * the upper 8x4, lanes 4-7 the lower.  Horizontal butterflies in-lane; the two 4x4 blocks of a
- * row are packed lo/hi in one word; vertical butterflies are two xor-shuffle stages.
+/* 8x8 SATD of each group's block from each lane's row of differences.  The reference sums two
+ * 8x4 SATDs, each = (sum |4x4 Hadamard coefficients| of its two 4x4 blocks) >> 1.  Lanes 0-3 of a
+ * group hold the upper 8x4, lanes 4-7 the lower.  Horizontal butterflies in-lane; the two 4x4 blocks
+ * of a row are packed lo/hi in one word; vertical butterflies are two xor-shuffle stages.
  * Valid for |d| <= 1023 (8- and 10-bit): coefficients stay below 2^15.  Every lane returns the total. */
-__device__ __forceinline__ int groupSatd(const int d[8], unsigned gmask)
+__device__ __forceinline__ int groupSatd(const int d[8])
 {
     const int a0 = d[0] + d[1], a1 = d[0] - d[1], a2 = d[2] + d[3], a3 = d[2] - d[3];
     const int b0 = d[4] + d[5], b1 = d[4] - d[5], b2 = d[6] + d[7], b3 = d[6] - d[7];
@@ -144,50 +199,51 @@ __device__ __forceinline__ int groupSatd(const int d[8], unsigned gmask)
 #pragma unroll
     for (int i = 0; i < 4; i++)
     {
-        uint32_t t = __shfl_xor_sync(gmask, p[i], 1);
+        uint32_t t = __shfl_xor_sync(LA_FULL, p[i], 1);
         uint32_t q = odd1 ? t - p[i] : p[i] + t;
-        t = __shfl_xor_sync(gmask, q, 2);
+        t = __shfl_xor_sync(LA_FULL, q, 2);
         q = odd2 ? t - q : q + t;
         sum += abs2(q);
     }
     int s = (int)((sum & 0xffffu) + (sum >> 16));
-    s += __shfl_xor_sync(gmask, s, 1);
-    s += __shfl_xor_sync(gmask, s, 2);
-    return (s >> 1) + (__shfl_xor_sync(gmask, s, 4) >> 1);
+    s += __shfl_xor_sync(LA_FULL, s, 1);
+    s += __shfl_xor_sync(LA_FULL, s, 2);
+    return (s >> 1) + (__shfl_xor_sync(LA_FULL, s, 4) >> 1);
 }
 
 template <typename P>
-__device__ __forceinline__ int groupSatdRows(const Row<P>& a, const Row<P>& b, unsigned gmask)
+__device__ __forceinline__ int groupSatdRows(const Row<P>& a, const Row<P>& b)
 {
     int d[8];
     diffRow(a, b, d);
-    return groupSatd(d, gmask);
+    return groupSatd(d);
 }
 
-/* the four half-pel planes of one frame and the position of the group's block in them */
+/* the four tiled half-pel planes of one frame and the origin of the group's block in buffer coordinates */
 template <typename P>
 struct RefBlock
 {
-    const P* base;          /* lowresPlane[0] + pelOffset of the block */
-    long long planeSize;    /* lowresPlane[i] = lowresPlane[0] + i * planeSize */
-    int stride;
+    const P* plane0;        /* start of the tiled buffer of plane 0; plane i at + i * planeSize */
+    long long planeSize;
+    int tpr;
+    int X0, Y0;             /* buffer coordinates (margins included) of the block's top-left sample */
 };
 
 /* this lane's row of the motion-compensated block: ReferencePlanes::lowresMC (lowres.h:71-96) */
 template <typename P>
 __device__ __forceinline__ Row<P> mcRow(const RefBlock<P>& rb, int qx, int qy, int r)
 {
-    if ((qx | qy) & 1)
+    const int hA = (qy & 2) | ((qx & 2) >> 1);
+    const Row<P> A = loadRowT(rb.plane0 + hA * rb.planeSize, rb.tpr, rb.X0 + (qx >> 2), rb.Y0 + (qy >> 2) + r);
+    if (__any_sync(LA_FULL, (qx | qy) & 1))
     {
-        const int hA = (qy & 2) | ((qx & 2) >> 1);
-        const Row<P> A = loadRow(rb.base + hA * rb.planeSize + (qx >> 2) + (long long)((qy >> 2) + r) * rb.stride);
         const int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
         const int hB = (qy2 & 2) | ((qx2 & 2) >> 1);
-        const Row<P> B = loadRow(rb.base + hB * rb.planeSize + (qx2 >> 2) + (long long)((qy2 >> 2) + r) * rb.stride);
+        const Row<P> B = loadRowT(rb.plane0 + hB * rb.planeSize, rb.tpr, rb.X0 + (qx2 >> 2), rb.Y0 + (qy2 >> 2) + r);
+        /* for a half/full-pel vector B == A and the rounded average returns A unchanged */
         return avgRow(A, B);
     }
-    const int hp = (qy & 2) | ((qx & 2) >> 1);
-    return loadRow(rb.base + hp * rb.planeSize + (qx >> 2) + (long long)((qy >> 2) + r) * rb.stride);
+    return A;
 }
 
 __device__ __forceinline__ int ldAcquire(const int* p)

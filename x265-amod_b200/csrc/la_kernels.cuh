@@ -37,12 +37,17 @@ template <typename P> struct Vec4;
 template <> struct Vec4<uint8_t>  { typedef uchar4 T; };
 template <> struct Vec4<uint16_t> { typedef ushort4 T; };
 
+/* 16 consecutive threads write one whole 8x8 tile (thread = one row half of 4 samples), so the
+ * stores of a warp are two contiguous tiles per plane. */
 template <typename P>
 __global__ void __launch_bounds__(256) lowres_kernel(Geom g, const P* __restrict__ src, P* __restrict__ buf)
 {
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int py = blockIdx.y;
-    if (x4 >= g.stride) return;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tile = t >> 4;
+    const int sub = (int)(t & 15);
+    if (tile >= (long long)g.tpr * (g.planeLines >> 3)) return;
+    const int x4 = (int)(tile % g.tpr) * 8 + (sub & 1) * 4;
+    const int py = (int)(tile / g.tpr) * 8 + (sub >> 1);
     typename Vec4<P>::T o0, o1, o2, o3;
     P* op[4] = { (P*)&o0, (P*)&o1, (P*)&o2, (P*)&o3 };
     const int ly = min(max(py - g.my, 0), g.h - 1);
@@ -71,11 +76,23 @@ __global__ void __launch_bounds__(256) lowres_kernel(Geom g, const P* __restrict
         op[3][i] = (P)LA_FILTER(a11, a21, a12, a22);
 #undef LA_FILTER
     }
-    const long long o = (long long)py * g.stride + x4;
+    const long long o = tileOff(x4, py, g.tpr);
     *(typename Vec4<P>::T*)(buf + o) = o0;
     *(typename Vec4<P>::T*)(buf + g.planeSize + o) = o1;
     *(typename Vec4<P>::T*)(buf + 2 * g.planeSize + o) = o2;
     *(typename Vec4<P>::T*)(buf + 3 * g.planeSize + o) = o3;
+}
+
+/* tiled -> pitched copy of the four planes, for the host mirror of Lowres::buffer[0..3] */
+template <typename P>
+__global__ void __launch_bounds__(256) detile_kernel(Geom g, const P* __restrict__ tiled, P* __restrict__ linear)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * g.planeSize) return;
+    const int pl = (int)(i / g.planeSize);
+    const long long o = i % g.planeSize;
+    const int Y = (int)(o / g.stride), X = (int)(o % g.stride);
+    linear[i] = tiled[pl * g.planeSize + tileOff(X, Y, g.tpr)];
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -226,6 +243,7 @@ __global__ void __launch_bounds__(1024) aq_finish_kernel(Geom g, const unsigned*
  * intraFilter<8>, intra_pred_dc_c<8>, planar_pred_c<3>, intra_pred_ang_c<8> (intrapred.cpp:31-204).
  * 8 lanes per block, 16 blocks per CTA; neighbours staged in shared memory; 12 predictions +
  * SATDs per block.  Works out of L2 (plane 0 of one frame); integer-pipe bound.
+ * Control flow is warp-uniform: the data-dependent mode choices only select operands.
  * ------------------------------------------------------------------------------------------ */
 __device__ const signed char c_angleTable[17] = { -32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
 __device__ const short c_invAngleTable[8] = { 4096, 1638, 910, 630, 482, 390, 315, 256 };
@@ -248,7 +266,8 @@ __device__ __forceinline__ Row<P> predAngular(const unsigned short* s, int mode,
     const bool hor = mode < 18;
     const int angleOffset = hor ? 10 - mode : mode - 26;
     const int angle = c_angleTable[8 + angleOffset];
-    Row<P> out;
+    const int invAngle = c_invAngleTable[angle < 0 ? -angleOffset - 1 : 0];
+    int v[8];
 #pragma unroll
     for (int x = 0; x < 8; x++)
     {
@@ -267,21 +286,17 @@ __device__ __forceinline__ Row<P> predAngular(const unsigned short* s, int mode,
         {
             const int angleSum = (yy + 1) * angle;
             const int off = angleSum >> 5, frac = angleSum & 31;
-            int k0 = off + xx, k1 = k0 + 1, r0, r1;
+            const int k0 = off + xx, k1 = k0 + 1;
             /* ref[k] = S(k+1) for k >= -1; projected left neighbours for k <= -2 (angle < 0) */
-            if (k0 >= -1) r0 = nbSwap(s, k0 + 1, hor);
-            else r0 = nbSwap(s, 16 + ((128 + (-1 - k0) * c_invAngleTable[-angleOffset - 1]) >> 8), hor);
-            if (frac)
-            {
-                if (k1 >= -1) r1 = nbSwap(s, k1 + 1, hor);
-                else r1 = nbSwap(s, 16 + ((128 + (-1 - k1) * c_invAngleTable[-angleOffset - 1]) >> 8), hor);
-                val = ((32 - frac) * r0 + frac * r1 + 16) >> 5;
-            }
-            else
-                val = r0;
+            const int i0 = k0 >= -1 ? k0 + 1 : 16 + ((128 + (-1 - k0) * invAngle) >> 8);
+            const int i1 = k1 >= -1 ? k1 + 1 : 16 + ((128 + (-1 - k1) * invAngle) >> 8);
+            const int r0 = nbSwap(s, i0, hor), r1 = nbSwap(s, i1, hor);
+            val = frac ? ((32 - frac) * r0 + frac * r1 + 16) >> 5 : r0;
         }
-        setPx(out, x, val);
+        v[x] = val;
     }
+    Row<P> out;
+    packRow(out, v);
     return out;
 }
 
@@ -296,23 +311,24 @@ __global__ void __launch_bounds__(128) intra_kernel(Geom g, const P* __restrict_
     if (threadIdx.x < 2) s_cost[threadIdx.x] = 0;
     __syncthreads();
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-    const unsigned gmask = groupMask();
-    const int cu = blockIdx.x * 16 + grp;
+    const int cuRaw = blockIdx.x * 16 + grp;
+    const bool act = cuRaw < g.ncu;
+    const int cu = act ? cuRaw : g.ncu - 1;        /* tail groups shadow the last block and write nothing */
     const int maxv = (1 << g.depth) - 1;
-    if (cu < g.ncu)
+    const int tpr = g.tpr;
     {
         const int cuX = cu % g.bw, cuY = cu / g.bw;
-        const P* pix = plane0 + 8 * cuX + (long long)8 * cuY * g.stride;
-        const Row<P> fenc = loadRow(pix + (long long)r * g.stride);
+        const int X0 = g.mx + 8 * cuX, Y0 = g.my + 8 * cuY;
+        const Row<P> fenc = loadRowAligned(plane0, tpr, X0, Y0 + r);
         unsigned short* nbA = s_nb[grp][0];
         unsigned short* nbF = s_nb[grp][1];
-        const P* c = pix - g.stride - 1;
-        nbA[2 * r] = __ldg(c + 2 * r);
-        nbA[2 * r + 1] = __ldg(c + 2 * r + 1);
-        if (r == 0) nbA[16] = __ldg(c + 16);
-        nbA[17 + 2 * r] = __ldg(c + (long long)(2 * r + 1) * g.stride);
-        nbA[18 + 2 * r] = __ldg(c + (long long)(2 * r + 2) * g.stride);
-        __syncwarp(gmask);
+        /* top-left, 16 above, 16 left of the block (slicetype.cpp:749-752) */
+        nbA[2 * r] = __ldg(plane0 + tileOff(X0 - 1 + 2 * r, Y0 - 1, tpr));
+        nbA[2 * r + 1] = __ldg(plane0 + tileOff(X0 + 2 * r, Y0 - 1, tpr));
+        if (r == 0) nbA[16] = __ldg(plane0 + tileOff(X0 + 15, Y0 - 1, tpr));
+        nbA[17 + 2 * r] = __ldg(plane0 + tileOff(X0 - 1, Y0 + 2 * r, tpr));
+        nbA[18 + 2 * r] = __ldg(plane0 + tileOff(X0 - 1, Y0 + 2 * r + 1, tpr));
+        __syncwarp();
         /* intraFilter<8> (intrapred.cpp:31-51) */
         for (int i = r; i <= 32; i += 8)
         {
@@ -323,53 +339,55 @@ __global__ void __launch_bounds__(128) intra_kernel(Geom g, const P* __restrict_
             else f = ((nbA[i] << 1) + nbA[i - 1] + nbA[i + 1] + 2) >> 2;
             nbF[i] = (unsigned short)f;
         }
-        __syncwarp(gmask);
+        __syncwarp();
 
         int cost, icost = LA_COST_MAX, ilow = 0;
         {   /* DC with edge filter (intrapred.cpp:53-85) */
-            int dc = groupSum(nbA[1 + r] + nbA[17 + r], gmask) + 8;
+            int dc = groupSum(nbA[1 + r] + nbA[17 + r]) + 8;
             dc = dc / 16;
-            Row<P> pred;
+            int v[8];
 #pragma unroll
             for (int x = 0; x < 8; x++)
             {
-                int v = dc;
-                if (r == 0) v = x == 0 ? (nbA[1] + nbA[17] + 2 * dc + 2) >> 2 : (nbA[1 + x] + 3 * dc + 2) >> 2;
-                else if (x == 0) v = (nbA[17 + r] + 3 * dc + 2) >> 2;
-                setPx(pred, x, v);
+                int t = dc;
+                if (r == 0) t = x == 0 ? (nbA[1] + nbA[17] + 2 * dc + 2) >> 2 : (nbA[1 + x] + 3 * dc + 2) >> 2;
+                else if (x == 0) t = (nbA[17 + r] + 3 * dc + 2) >> 2;
+                v[x] = t;
             }
-            cost = groupSatdRows(fenc, pred, gmask);
+            Row<P> pred; packRow(pred, v);
+            cost = groupSatdRows(fenc, pred);
             if (cost < icost) { icost = cost; ilow = 1; }
         }
         {   /* planar on the filtered neighbours (intrapred.cpp:87-100) */
             const int topRight = nbF[9], bottomLeft = nbF[25], left = nbF[17 + r];
-            Row<P> pred;
+            int v[8];
 #pragma unroll
             for (int x = 0; x < 8; x++)
-                setPx(pred, x, ((7 - x) * left + (7 - r) * nbF[1 + x] + (x + 1) * topRight + (r + 1) * bottomLeft + 8) >> 4);
-            cost = groupSatdRows(fenc, pred, gmask);
+                v[x] = ((7 - x) * left + (7 - r) * nbF[1 + x] + (x + 1) * topRight + (r + 1) * bottomLeft + 8) >> 4;
+            Row<P> pred; packRow(pred, v);
+            cost = groupSatdRows(fenc, pred);
             if (cost < icost) { icost = cost; ilow = 0; }
         }
         int acost = LA_COST_MAX, alow = 4;
         for (int mode = 5; mode < 35; mode += 5)
         {
             const Row<P> pred = predAngular<P>((c_intraFilterFlags[mode] & 8) ? nbF : nbA, mode, r, maxv);
-            cost = groupSatdRows(fenc, pred, gmask);
+            cost = groupSatdRows(fenc, pred);
             if (cost < acost) { acost = cost; alow = mode; }
         }
         for (int dist = 2; dist >= 1; dist--)
         {
             const int minusmode = alow - dist, plusmode = alow + dist;
             Row<P> pred = predAngular<P>((c_intraFilterFlags[minusmode] & 8) ? nbF : nbA, minusmode, r, maxv);
-            cost = groupSatdRows(fenc, pred, gmask);
+            cost = groupSatdRows(fenc, pred);
             if (cost < acost) { acost = cost; alow = minusmode; }
             pred = predAngular<P>((c_intraFilterFlags[plusmode] & 8) ? nbF : nbA, plusmode, r, maxv);
-            cost = groupSatdRows(fenc, pred, gmask);
+            cost = groupSatdRows(fenc, pred);
             if (cost < acost) { acost = cost; alow = plusmode; }
         }
         if (acost < icost) { icost = acost; ilow = alow; }
         icost += 5 * g.lambda + 4;
-        if (r == 0)
+        if (r == 0 && act)
         {
             lowresCosts00[cu] = (unsigned short)min(icost, LA_LOWRES_COST_MASK);
             intraCost[cu] = icost;
@@ -404,14 +422,18 @@ __global__ void __launch_bounds__(128) intra_kernel(Geom g, const P* __restrict_
  * bands of one job are chained through a release/acquire progress counter in global memory.
  * CTAs take their (job, band) from a ticket counter so a band never waits on a CTA that has not
  * started.  Throughput comes from running many independent jobs concurrently.
+ *
+ * A warp searches 4 blocks (4 consecutive rows) in lockstep.  The search is data dependent (MVP
+ * choice, hexagon iterations, early exits); it is written with per-group predicates and
+ * warp-votes so the warp never diverges, which keeps every shuffle on the full mask.
  * ------------------------------------------------------------------------------------------ */
 #define LA_BAND_ROWS 16
 
 template <typename P>
 struct SearchJobDev
 {
-    const P* fenc0;         /* lowresPlane[0] of the frame being searched */
-    const P* ref0;          /* lowresPlane[0] of the (possibly weighted) reference; planes at +i*planeSize */
+    const P* fenc0;         /* tiled buffer of lowresPlane[0] of the frame being searched */
+    const P* ref0;          /* tiled buffer of plane 0 of the (possibly weighted) reference; planes at +i*planeSize */
     int*     mvOut;         /* ncu packed MVs: (x & 0xffff) | (y << 16), quarter-pel */
     int*     costOut;       /* ncu */
     int      bidir;
@@ -428,7 +450,6 @@ struct MeCtx
     const unsigned short* mvcost;   /* centre */
     int mvpx, mvpy;
     int r;
-    unsigned gmask;
 
     __device__ __forceinline__ int mvc(int qx, int qy) const
     {
@@ -436,19 +457,20 @@ struct MeCtx
     }
     __device__ __forceinline__ int sadFpelPart(int x, int y) const
     {
-        return sadRow(fenc, loadRow(rb.base + x + (long long)(y + r) * rb.stride));
+        return sadRow(fenc, loadRowT(rb.plane0, rb.tpr, rb.X0 + x, rb.Y0 + y + r));
     }
-    __device__ __forceinline__ int sadFpel(int x, int y) const { return groupSum(sadFpelPart(x, y), gmask); }
-    __device__ __forceinline__ int qpelSad(int qx, int qy) const { return groupSum(sadRow(fenc, mcRow(rb, qx, qy, r)), gmask); }
-    __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return groupSatdRows(fenc, mcRow(rb, qx, qy, r), gmask); }
+    __device__ __forceinline__ int sadFpel(int x, int y) const { return groupSum(sadFpelPart(x, y)); }
+    __device__ __forceinline__ int qpelSad(int qx, int qy) const { return groupSum(sadRow(fenc, mcRow(rb, qx, qy, r))); }
+    __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return groupSatdRows(fenc, mcRow(rb, qx, qy, r)); }
 };
 
 __device__ const signed char c_hex2[8][2] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };
 __device__ const unsigned char c_mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };
 __device__ const signed char c_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };
 
+/* The whole warp calls this converged; every value is uniform inside an 8-lane group. */
 template <typename P>
-__device__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& out)
+__device__ __forceinline__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& out)
 {
     const int merange = 16;
     m.mvpx = qmvp.x; m.mvpy = qmvp.y;
@@ -458,12 +480,17 @@ __device__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& 
     const int bprecost = m.qpelSad(pmv.x, pmv.y);
     MV2 bmv = { (pmv.x + 2) >> 2, (pmv.y + 2) >> 2 };
     int bcost = bprecost;
-    if ((pmv.x & 3) | (pmv.y & 3))
-        bcost = m.sadFpel(bmv.x, bmv.y) + m.mvc(bmv.x << 2, bmv.y << 2);
-    if (pmv.x | pmv.y)
+    const bool sub = ((pmv.x & 3) | (pmv.y & 3)) != 0;
+    if (__any_sync(LA_FULL, sub))
+    {
+        const int c = m.sadFpel(bmv.x, bmv.y) + m.mvc(bmv.x << 2, bmv.y << 2);
+        if (sub) bcost = c;
+    }
+    const bool nz = (pmv.x | pmv.y) != 0;
+    if (__any_sync(LA_FULL, nz))
     {
         const int cost = m.sadFpel(0, 0) + m.mvc(0, 0);
-        if (cost < bcost)
+        if (nz && cost < bcost)
         {
             bcost = cost;
             bmv.x = 0;
@@ -475,9 +502,9 @@ __device__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& 
     { \
         int p0 = m.sadFpelPart(bmv.x + (x0), bmv.y + (y0)), p1 = m.sadFpelPart(bmv.x + (x1), bmv.y + (y1)), \
             p2 = m.sadFpelPart(bmv.x + (x2), bmv.y + (y2)); \
-        c0 = groupSum(p0, m.gmask) + m.mvc((bmv.x + (x0)) << 2, (bmv.y + (y0)) << 2); \
-        c1 = groupSum(p1, m.gmask) + m.mvc((bmv.x + (x1)) << 2, (bmv.y + (y1)) << 2); \
-        c2 = groupSum(p2, m.gmask) + m.mvc((bmv.x + (x2)) << 2, (bmv.y + (y2)) << 2); \
+        c0 = groupSum(p0) + m.mvc((bmv.x + (x0)) << 2, (bmv.y + (y0)) << 2); \
+        c1 = groupSum(p1) + m.mvc((bmv.x + (x1)) << 2, (bmv.y + (y1)) << 2); \
+        c2 = groupSum(p2) + m.mvc((bmv.x + (x2)) << 2, (bmv.y + (y2)) << 2); \
     }
     {   /* hexagon, motion.cpp:892-946 */
         int c0, c1, c2;
@@ -488,27 +515,36 @@ __device__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& 
         LA_COST3(c0, c1, c2, 2, 0, 1, -2, -1, -2);
         if (LA_YOK(0)) { bcost = min(bcost, (c0 << 3) + 5); }
         if (LA_YOK(-2)) { bcost = min(bcost, (c1 << 3) + 6); bcost = min(bcost, (c2 << 3) + 7); }
-        if (bcost & 7)
+        int dir = 0, iter = (merange >> 1) - 1;
+        bool go = (bcost & 7) != 0;
+        if (go)
         {
-            int dir = (bcost & 7) - 2;
-            if (LA_YOK(c_hex2[dir + 1][1]))
+            dir = (bcost & 7) - 2;
+            go = LA_YOK(c_hex2[dir + 1][1]);
+            if (go) { bmv.x += c_hex2[dir + 1][0]; bmv.y += c_hex2[dir + 1][1]; }
+        }
+        go = go && iter > 0 && bmv.x >= mvmin.x && bmv.x <= mvmax.x && bmv.y >= mvmin.y && bmv.y <= mvmax.y;
+        while (__any_sync(LA_FULL, go))
+        {
+            /* half hexagon around bmv; groups that already stopped re-measure harmlessly and ignore the result */
+            const int x0 = c_hex2[dir][0], y0 = c_hex2[dir][1], x1 = c_hex2[dir + 1][0], y1 = c_hex2[dir + 1][1],
+                      x2 = c_hex2[dir + 2][0], y2 = c_hex2[dir + 2][1];
+            LA_COST3(c0, c1, c2, x0, y0, x1, y1, x2, y2);
+            if (go)
             {
-                bmv.x += c_hex2[dir + 1][0]; bmv.y += c_hex2[dir + 1][1];
-                for (int i = (merange >> 1) - 1;
-                     i > 0 && bmv.x >= mvmin.x && bmv.x <= mvmax.x && bmv.y >= mvmin.y && bmv.y <= mvmax.y; i--)
+                bcost &= ~7;
+                if (LA_YOK(y0)) bcost = min(bcost, (c0 << 3) + 1);
+                if (LA_YOK(y1)) bcost = min(bcost, (c1 << 3) + 2);
+                if (LA_YOK(y2)) bcost = min(bcost, (c2 << 3) + 3);
+                if (!(bcost & 7))
+                    go = false;
+                else
                 {
-                    const int x0 = c_hex2[dir][0], y0 = c_hex2[dir][1], x1 = c_hex2[dir + 1][0], y1 = c_hex2[dir + 1][1],
-                              x2 = c_hex2[dir + 2][0], y2 = c_hex2[dir + 2][1];
-                    LA_COST3(c0, c1, c2, x0, y0, x1, y1, x2, y2);
-                    bcost &= ~7;
-                    if (LA_YOK(y0)) bcost = min(bcost, (c0 << 3) + 1);
-                    if (LA_YOK(y1)) bcost = min(bcost, (c1 << 3) + 2);
-                    if (LA_YOK(y2)) bcost = min(bcost, (c2 << 3) + 3);
-                    if (!(bcost & 7))
-                        break;
                     dir += (bcost & 7) - 2;
                     dir = c_mod6m1[dir + 1];
                     bmv.x += c_hex2[dir + 1][0]; bmv.y += c_hex2[dir + 1][1];
+                    iter--;
+                    go = iter > 0 && bmv.x >= mvmin.x && bmv.x <= mvmax.x && bmv.y >= mvmin.y && bmv.y <= mvmax.y;
                 }
             }
         }
@@ -535,30 +571,35 @@ __device__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& 
     if (bprecost < bcost) { bmv = bestpre; bcost = bprecost; }
     else { bmv.x <<= 2; bmv.y <<= 2; }
 
-    if (!bcost)
-        bcost = m.mvc(bmv.x, bmv.y);
-    else
+    /* zero residual at the start point: no subpel, cost = mvcost (motion.cpp:1490-1495) */
+    const bool doSub = bcost != 0;
+    const int zeroCost = m.mvc(bmv.x, bmv.y);
+    if (__any_sync(LA_FULL, doSub))
     {   /* lowres subpel, motion.cpp:1496-1528: 4 half-pel SADs, re-measure with SATD, 4 quarter-pel SATDs */
         int bdir = 0;
+#pragma unroll 1
         for (int i = 1; i <= 4; i++)
         {
             const int qx = bmv.x + c_square1[i][0] * 2, qy = bmv.y + c_square1[i][1] * 2;
-            if ((qy < qmin.y) | (qy > qmax.y)) continue;
+            const bool ok = doSub && !((qy < qmin.y) | (qy > qmax.y));
             const int cost = m.qpelSad(qx, qy) + m.mvc(qx, qy);
-            if (cost < bcost) { bcost = cost; bdir = i; }
+            if (ok && cost < bcost) { bcost = cost; bdir = i; }
         }
         bmv.x += c_square1[bdir][0] * 2; bmv.y += c_square1[bdir][1] * 2;
-        bcost = m.qpelSatd(bmv.x, bmv.y) + m.mvc(bmv.x, bmv.y);
+        const int c = m.qpelSatd(bmv.x, bmv.y) + m.mvc(bmv.x, bmv.y);
+        if (doSub) bcost = c;
         bdir = 0;
+#pragma unroll 1
         for (int i = 1; i <= 4; i++)
         {
             const int qx = bmv.x + c_square1[i][0], qy = bmv.y + c_square1[i][1];
-            if ((qy < qmin.y) | (qy > qmax.y)) continue;
+            const bool ok = doSub && !((qy < qmin.y) | (qy > qmax.y));
             const int cost = m.qpelSatd(qx, qy) + m.mvc(qx, qy);
-            if (cost < bcost) { bcost = cost; bdir = i; }
+            if (ok && cost < bcost) { bcost = cost; bdir = i; }
         }
         bmv.x += c_square1[bdir][0]; bmv.y += c_square1[bdir][1];
     }
+    if (!doSub) bcost = zeroCost;
     out = bmv;
     return bcost;
 }
@@ -578,66 +619,93 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
     const int job = s_ticket / nbands, band = s_ticket % nbands;
     const SearchJobDev<P> J = jobs[job];
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-    const unsigned gmask = groupMask();
+    const int warp = threadIdx.x >> 5;
     const int bw = g.bw, bh = g.bh;
     const int rowsInBand = min(LA_BAND_ROWS, bh - band * LA_BAND_ROWS);
-    const int cuY = bh - 1 - band * LA_BAND_ROWS - grp;
+    const bool rowOk = grp < rowsInBand;
+    const int cuY = rowOk ? bh - 1 - band * LA_BAND_ROWS - grp : 0;
     const bool lastRow = cuY == bh - 1;
     const int steps = bw + 2 * (rowsInBand - 1);
     int* myProgress = progress + job * nbands + band;
     const int* belowProgress = myProgress - 1;
     MeCtx<P> m;
-    m.mvcost = mvcost; m.r = r; m.gmask = gmask;
-    m.rb.planeSize = g.planeSize; m.rb.stride = g.stride;
+    m.mvcost = mvcost; m.r = r;
+    m.rb.plane0 = J.ref0; m.rb.planeSize = g.planeSize; m.rb.tpr = g.tpr;
 
     for (int s = 0; s < steps; s++)
     {
-        const int k = s - 2 * grp;
-        if (grp < rowsInBand && k >= 0 && k < bw)
+        /* is any of this warp's 4 rows inside its column range at this step? (warp-uniform) */
+        const int kLo = s - 2 * (warp * 4 + 3), kHi = s - 2 * (warp * 4);
+        if (kHi >= 0 && kLo < bw && warp * 4 < rowsInBand)
         {
+            const int kRaw = s - 2 * grp;
+            const bool act = rowOk && kRaw >= 0 && kRaw < bw;
+            const int k = min(max(kRaw, 0), bw - 1);     /* idle groups shadow a valid block and write nothing */
             const int cuX = bw - 1 - k;
             const int cu = cuX + cuY * bw;
-            const long long pel = 8 * cuX + (long long)8 * cuY * g.stride;
-            m.fenc = loadRow(J.fenc0 + pel + (long long)r * g.stride);
-            m.rb.base = J.ref0 + pel;
+            m.rb.X0 = g.mx + 8 * cuX; m.rb.Y0 = g.my + 8 * cuY;
+            m.fenc = loadRowAligned(J.fenc0, g.tpr, m.rb.X0, m.rb.Y0 + r);
 
-            /* reverse-order MV predictors (slicetype.cpp:4131-4141) */
-            int cand[4], numc = 0;
-            if (cuX < bw - 1) cand[numc++] = s_mv[grp * bw + cuX + 1];
-            if (!lastRow)
+            /* reverse-order MV predictors (slicetype.cpp:4131-4141): right, below, below-left, below-right */
+            int cand[4]; bool valid[4];
+            /* idle groups get no predictors: they must never follow an MV that is not there yet */
+            valid[0] = act && cuX < bw - 1;
+            valid[1] = act && !lastRow; valid[2] = act && !lastRow && cuX > 0; valid[3] = act && !lastRow && cuX < bw - 1;
+            cand[0] = s_mv[grp * bw + min(cuX + 1, bw - 1)];
+            if (warp == 0 && band > 0)
             {
+                /* row below group 0 belongs to the previous band: wait until it has finished column cuX-1 */
+                if (threadIdx.x == 0 && act)
+                {
+                    const int need = min(bw, k + 2);
+                    while (ldAcquire(belowProgress) < need) __nanosleep(64);
+                }
+                __syncwarp();
+            }
+            {
+                const int xl = max(cuX - 1, 0), xr = min(cuX + 1, bw - 1);
                 if (grp == 0)
                 {
-                    /* row below belongs to the previous band: wait until it has finished column cuX-1 */
-                    const int need = min(bw, k + 2);
-                    if (r == 0)
-                        while (ldAcquire(belowProgress) < need) __nanosleep(64);
-                    __syncwarp(gmask);
-                    const int* below = J.mvOut + (cuY + 1) * bw;
-                    cand[numc++] = __ldcg(below + cuX);
-                    if (cuX > 0) cand[numc++] = __ldcg(below + cuX - 1);
-                    if (cuX < bw - 1) cand[numc++] = __ldcg(below + cuX + 1);
+                    const int* below = J.mvOut + min(cuY + 1, bh - 1) * bw;
+                    cand[1] = __ldcg(below + cuX); cand[2] = __ldcg(below + xl); cand[3] = __ldcg(below + xr);
                 }
                 else
                 {
                     const int* below = s_mv + (grp - 1) * bw;
-                    cand[numc++] = below[cuX];
-                    if (cuX > 0) cand[numc++] = below[cuX - 1];
-                    if (cuX < bw - 1) cand[numc++] = below[cuX + 1];
+                    cand[1] = below[cuX]; cand[2] = below[xl]; cand[3] = below[xr];
                 }
             }
             MV2 mvp = { 0, 0 };
             int skipCost = 0x7fffffff;
-            if (numc)
             {
                 int mvpcost = LA_COST_MAX;
-                for (int i = 0; i < numc; i++)
+                int costs[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
                 {
-                    const MV2 c = unpackMv(cand[i]);
-                    const int cost = m.qpelSatd(c.x, c.y);
-                    if (cost < mvpcost) { mvpcost = cost; mvp = c; }
-                    if (!(mvp.x | mvp.y) && J.bidir)
-                        skipCost = cost;
+                    /* identical predictors cost the same: measure each distinct one once */
+                    int dup = -1;
+#pragma unroll
+                    for (int q = 0; q < i; q++)
+                        if (valid[q] && cand[q] == cand[i] && dup < 0) dup = q;
+                    const bool need = valid[i] && dup < 0;
+                    int cost = 0;
+                    if (__any_sync(LA_FULL, need))
+                    {
+                        const MV2 zero = { 0, 0 };
+                        const MV2 c = need ? unpackMv(cand[i]) : zero;
+                        cost = m.qpelSatd(c.x, c.y);
+                    }
+#pragma unroll
+                    for (int q = 0; q < i; q++)
+                        if (dup == q) cost = costs[q];
+                    costs[i] = cost;
+                    if (valid[i])
+                    {
+                        if (cost < mvpcost) { mvpcost = cost; mvp = unpackMv(cand[i]); }
+                        if (!(mvp.x | mvp.y) && J.bidir)
+                            skipCost = cost;
+                    }
                 }
             }
             const MV2 mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
@@ -649,7 +717,7 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
                 fencCost = skipCost;
                 best.x = best.y = 0;
             }
-            if (r == 0)
+            if (r == 0 && act)
             {
                 const int packed = packMv(best);
                 s_mv[grp * bw + cuX] = packed;
@@ -675,7 +743,7 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
 template <typename P>
 struct CostJobDev
 {
-    const P* fenc0; const P* ref0; const P* ref1;   /* lowresPlane[0] of b, p0, p1 (ref1 = NULL: P estimate) */
+    const P* fenc0; const P* ref0; const P* ref1;   /* tiled plane-0 buffers of b, p0, p1 (ref1 = NULL: P estimate) */
     const int* mv0; const int* cost0; const int* mv1; const int* cost1;
     const int* intraCost; const int* invQ;
     unsigned short* lowresCosts; int* rowSatds; CostResultDev* result;
@@ -718,7 +786,7 @@ __global__ void __launch_bounds__(128) cost_kernel(Geom g, const CostJobDev<P>* 
     if (!J.ref1)
     {   /* P estimate: one thread per block */
         const int cu = blockIdx.x * 128 + threadIdx.x;
-        if (cu < g.ncu && blockIdx.x * 128 < g.ncu)
+        if (cu < g.ncu)
         {
             int bcost = J.cost0[cu] + 4, listused = 1;      /* COST_MAX > any search cost */
             const int ic = J.intraCost[cu];
@@ -727,33 +795,31 @@ __global__ void __launch_bounds__(128) cost_kernel(Geom g, const CostJobDev<P>* 
         }
     }
     else
-    {   /* B estimate: 16 blocks per CTA */
+    {   /* B estimate: 16 blocks per CTA, warp-uniform */
         const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-        const unsigned gmask = groupMask();
-        const int cu = blockIdx.x * 16 + grp;
-        if (cu < g.ncu)
-        {
-            const int cuX = cu % g.bw, cuY = cu / g.bw;
-            const long long pel = 8 * cuX + (long long)8 * cuY * g.stride;
-            int bcost = LA_COST_MAX, listused = 0;
-            const int c0 = J.cost0[cu], c1 = J.cost1[cu];
-            if (c0 < bcost) { bcost = c0; listused = 1; }
-            if (c1 < bcost) { bcost = c1; listused = 2; }
-            const Row<P> fenc = loadRow(J.fenc0 + pel + (long long)r * g.stride);
-            RefBlock<P> rb0 = { J.ref0 + pel, g.planeSize, g.stride }, rb1 = { J.ref1 + pel, g.planeSize, g.stride };
-            const MV2 m0 = unpackMv(J.mv0[cu]), m1 = unpackMv(J.mv1[cu]);
-            /* avg(L0 MC, L1 MC), unweighted references (slicetype.cpp:4189-4200) */
-            Row<P> a = avgRow(mcRow(rb0, m0.x, m0.y, r), mcRow(rb1, m1.x, m1.y, r));
-            int bicost = groupSatdRows(fenc, a, gmask);
-            if (bicost < bcost) { bcost = bicost; listused = 3; }
-            /* co-located average (:4201-4206) */
-            a = avgRow(loadRow(rb0.base + (long long)r * g.stride), loadRow(rb1.base + (long long)r * g.stride));
-            bicost = groupSatdRows(fenc, a, gmask);
-            if (bicost < bcost) { bcost = bicost; listused = 3; }
-            bcost += 4;
-            if (r == 0)
-                costEpilogue(g, J, cu, bcost, listused, true, s_acc, &s_intra);
-        }
+        const int cuRaw = blockIdx.x * 16 + grp;
+        const bool act = cuRaw < g.ncu;
+        const int cu = act ? cuRaw : g.ncu - 1;
+        const int cuX = cu % g.bw, cuY = cu / g.bw;
+        const int X0 = g.mx + 8 * cuX, Y0 = g.my + 8 * cuY;
+        int bcost = LA_COST_MAX, listused = 0;
+        const int c0 = J.cost0[cu], c1 = J.cost1[cu];
+        if (c0 < bcost) { bcost = c0; listused = 1; }
+        if (c1 < bcost) { bcost = c1; listused = 2; }
+        const Row<P> fenc = loadRowAligned(J.fenc0, g.tpr, X0, Y0 + r);
+        RefBlock<P> rb0 = { J.ref0, g.planeSize, g.tpr, X0, Y0 }, rb1 = { J.ref1, g.planeSize, g.tpr, X0, Y0 };
+        const MV2 m0 = unpackMv(J.mv0[cu]), m1 = unpackMv(J.mv1[cu]);
+        /* avg(L0 MC, L1 MC), unweighted references (slicetype.cpp:4189-4200) */
+        Row<P> a = avgRow(mcRow(rb0, m0.x, m0.y, r), mcRow(rb1, m1.x, m1.y, r));
+        int bicost = groupSatdRows(fenc, a);
+        if (bicost < bcost) { bcost = bicost; listused = 3; }
+        /* co-located average (:4201-4206) */
+        a = avgRow(loadRowAligned(J.ref0, g.tpr, X0, Y0 + r), loadRowAligned(J.ref1, g.tpr, X0, Y0 + r));
+        bicost = groupSatdRows(fenc, a);
+        if (bicost < bcost) { bcost = bicost; listused = 3; }
+        bcost += 4;
+        if (r == 0 && act)
+            costEpilogue(g, J, cu, bcost, listused, true, s_acc, &s_intra);
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -787,14 +853,12 @@ __global__ void __launch_bounds__(128) weight_cost_kernel(Geom g, const P* __res
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-    const unsigned gmask = groupMask();
-    const int cu = blockIdx.x * 16 + grp;
-    if (cu < g.ncu)
-    {
-        const long long pel = 8 * (cu % g.bw) + (long long)8 * (cu / g.bw) * g.stride;
-        const int satd = groupSatdRows(loadRow(ref0 + pel + (long long)r * g.stride), loadRow(fenc0 + pel + (long long)r * g.stride), gmask);
-        if (r == 0) atomicAdd(&s_sum, (unsigned)min(satd, intraCost[cu]));
-    }
+    const int cuRaw = blockIdx.x * 16 + grp;
+    const bool act = cuRaw < g.ncu;
+    const int cu = act ? cuRaw : g.ncu - 1;
+    const int X0 = g.mx + 8 * (cu % g.bw), Y0 = g.my + 8 * (cu / g.bw);
+    const int satd = groupSatdRows(loadRowAligned(ref0, g.tpr, X0, Y0 + r), loadRowAligned(fenc0, g.tpr, X0, Y0 + r));
+    if (r == 0 && act) atomicAdd(&s_sum, (unsigned)min(satd, intraCost[cu]));
     __syncthreads();
     if (threadIdx.x == 0 && s_sum) atomicAdd(result, s_sum);
 }
@@ -886,19 +950,38 @@ __global__ void __launch_bounds__(256) cost_recalc_kernel(Geom g, const unsigned
 }
 
 /* debug / unit-test kernel: SAD and SATD of n pairs of packed 8x8 blocks (mirrors the reference's
- * check_pixelcmp, source/test/pixelharness.cpp:82) */
+ * check_pixelcmp, source/test/pixelharness.cpp:82).  n must be a multiple of 4 (whole warps). */
 template <typename P>
 __global__ void __launch_bounds__(128) block_metrics_kernel(const P* __restrict__ a, const P* __restrict__ b, int n,
                                                             int* sadOut, int* satdOut)
 {
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-    const unsigned gmask = groupMask();
-    const int i = blockIdx.x * 16 + grp;
-    if (i >= n) return;
-    const Row<P> ra = loadRow(a + (long long)i * 64 + r * 8), rb = loadRow(b + (long long)i * 64 + r * 8);
-    const int sad = groupSum(sadRow(ra, rb), gmask);
-    const int satd = groupSatdRows(ra, rb, gmask);
-    if (r == 0) { sadOut[i] = sad; satdOut[i] = satd; }
+    const int iRaw = blockIdx.x * 16 + grp;
+    const int i = min(iRaw, n - 1);
+    const Row<P> ra = loadRowPitched(a + (long long)i * 64 + r * 8), rb = loadRowPitched(b + (long long)i * 64 + r * 8);
+    const int sad = groupSum(sadRow(ra, rb));
+    const int satd = groupSatdRows(ra, rb);
+    if (r == 0 && iRaw < n) { sadOut[i] = sad; satdOut[i] = satd; }
+}
+
+/* unit-test kernel for the tiled row fetch + motion compensation: for n (block, mv) pairs returns SATD and
+ * SAD of the motion-compensated reference block against the source block, i.e. lowresQPelCost (lowres.h:98-124) */
+template <typename P>
+__global__ void __launch_bounds__(128) mc_metrics_kernel(Geom g, const P* __restrict__ fenc0, const P* __restrict__ ref0,
+                                                         const int* __restrict__ cuIdx, const int* __restrict__ mvs, int n,
+                                                         int* sadOut, int* satdOut)
+{
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int iRaw = blockIdx.x * 16 + grp;
+    const int i = min(iRaw, n - 1);
+    const int cu = cuIdx[i];
+    const int X0 = g.mx + 8 * (cu % g.bw), Y0 = g.my + 8 * (cu / g.bw);
+    const Row<P> fenc = loadRowAligned(fenc0, g.tpr, X0, Y0 + r);
+    RefBlock<P> rb = { ref0, g.planeSize, g.tpr, X0, Y0 };
+    const Row<P> p = mcRow(rb, mvs[2 * i], mvs[2 * i + 1], r);
+    const int sad = groupSum(sadRow(fenc, p));
+    const int satd = groupSatdRows(fenc, p);
+    if (r == 0 && iRaw < n) { sadOut[i] = sad; satdOut[i] = satd; }
 }
 
 } // namespace la

@@ -133,6 +133,14 @@ int x265la_frame_weights(void* lav, void* frame, int32_t* state, int32_t* scale,
     return 0;
 }
 
+int x265la_get_timers(void* lav, double* t, int32_t reset)
+{
+    Lookahead* la = (Lookahead*)lav;
+    for (int i = 0; i < 8; i++) t[i] = la->m_timers[i];
+    if (reset) memset(la->m_timers, 0, sizeof(la->m_timers));
+    return 0;
+}
+
 int x265la_frame_fetch(void* la, void* frame, const x265cu_frame_out* out)
 { return ((Lookahead*)la)->fetchFrame((Frame*)frame, out) ? 0 : -1; }
 

@@ -57,6 +57,8 @@ int   x265la_frame_costs(void* la, void* frame, int32_t d0, int32_t d1, uint16_t
 int   x265la_frame_fetch(void* la, void* frame, const x265cu_frame_out* out);
 /* weightp analysis outcome per L0 distance: state 0 = not analysed, 1 = no weight, 2 = weighted */
 int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset /* nb each */);
+/* host wall-clock per phase, seconds (see Lookahead::m_timers); reset != 0 clears them */
+int   x265la_get_timers(void* la, double* t /* 8 */, int32_t reset);
 x265cu_ctx* x265la_engine(void* la);
 
 #ifdef __cplusplus

@@ -15,8 +15,14 @@
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <chrono>
 
 namespace x265cu {
+
+static inline double nowSec()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static inline double clipDuration(double f) { return f < 0.01 ? 0.01 : (f > 1.0 ? 1.0 : f); }  /* ratecontrol.h:43-48 */
 
@@ -58,6 +64,7 @@ Lookahead::Lookahead(const LookaheadParam& param)
       m_isSceneTransition(false), m_extendGopBoundary(false), m_ctx(NULL), m_pocNext(0), m_failed(false)
 {
     m_error[0] = 0;
+    memset(m_timers, 0, sizeof(m_timers));
     /* slicetype.cpp:996-1033 */
     m_8x8Height = ((m_param.sourceHeight / 2) + 7) >> 3;
     m_8x8Width = ((m_param.sourceWidth / 2) + 7) >> 3;
@@ -404,6 +411,7 @@ void Lookahead::speculate()
             fresh.push_back(m_resident[i]);
     if (fresh.empty()) return;
 
+    double t0 = nowSec();
     if (m_param.bEnableWeightedPred)
     {
         std::vector<std::pair<Lowres*, Lowres*> > pairs;
@@ -416,6 +424,8 @@ void Lookahead::speculate()
             }
         weightsAnalyseBatch(pairs);
     }
+    m_timers[1] += nowSec() - t0;
+    t0 = nowSec();
 
     m_searchJobs.clear(); m_costJobs.clear();
     const int maxD1 = B;                                  /* p1 - b <= bframes */
@@ -460,9 +470,12 @@ void Lookahead::speculate()
         check(x265cu_search_batch(m_ctx, &m_searchJobs[0], (int)m_searchJobs.size()), "x265cu_search_batch");
     if (!m_costJobs.empty())
         check(x265cu_cost_batch(m_ctx, &m_costJobs[0], (int)m_costJobs.size()), "x265cu_cost_batch");
+    m_timers[2] += nowSec() - t0;
+    t0 = nowSec();
     std::vector<Lowres*> who;
     for (size_t i = 0; i < m_resident.size(); i++) who.push_back(&m_resident[i]->m_lowres);
     fetchResults(who);
+    m_timers[3] += nowSec() - t0;
 }
 
 /* one synchronising gather of every computed-but-unread cost scalar */
@@ -601,11 +614,14 @@ void Lookahead::slicetypeDecide()
     for (size_t i = 0; i < m_resident.size(); i++)
         if (!m_resident[i]->m_lowresInit && std::find(pre.begin(), pre.end(), m_resident[i]) == pre.end())
             pre.push_back(m_resident[i]);
+    const double tStart = nowSec();
     preLookahead(pre);
+    m_timers[0] += nowSec() - tStart;
     if (m_failed) return;
     if (m_param.speculate)
         speculate();
     if (m_failed) return;
+    const double tAnalyse = nowSec();
 
     const LookaheadParam& p = m_param;
     if (m_lastNonB && ((p.bFrameAdaptive && p.bframes) || p.rc.cuTree || p.scenecutThreshold ||
@@ -731,6 +747,9 @@ void Lookahead::slicetypeDecide()
         frames[j + 1] = NULL;
         slicetypeAnalyse(frames, fr, true);
     }
+    m_timers[4] += nowSec() - tAnalyse;
+    m_timers[5] += nowSec() - tStart;
+    m_timers[6] += 1;
 }
 
 /* slicetype.cpp:2603-2919 */

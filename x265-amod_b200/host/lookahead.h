@@ -142,6 +142,10 @@ public:
     const char* lastError() const { return m_error; }
     bool    ok() const { return !m_failed; }
 
+    /* host-side wall-clock per phase (seconds), for bench.py: 0 pre-lookahead wait, 1 weightp, 2 enqueue,
+     * 3 result wait, 4 decisions (host logic incl. cuTree enqueue), 5 whole slicetypeDecide, 6 calls */
+    double  m_timers[8];
+
     LookaheadParam m_param;
     bool    m_filled;
     int     m_inputCount;
