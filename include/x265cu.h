@@ -112,6 +112,10 @@ typedef struct
     int32_t w_scale, w_denom, w_offset; /* WeightParam inputWeight/log2WeightDenom/inputOffset */
 } x265cu_search_job;
 int  x265cu_search_batch(x265cu_ctx* ctx, const x265cu_search_job* jobs, int32_t n);
+/* synchronises; flags[i] != 0 when the search stored in (slots[i], stores[i]) applied the zero-MV skip rule to at
+ * least one block.  A B-context L0 search that never did is identical to the P-context search of the same
+ * (frame, distance), which lets the host skip the second variant. */
+int  x265cu_search_flags_get(x265cu_ctx* ctx, const int32_t* slots, const int32_t* stores, int32_t n, int32_t* flags);
 
 /* ---- frame cost: the cost half of estimateCUCost (slicetype.cpp:4187-4248) and the sums of
  * estimateFrameCost (:4050-4062) for one (p0,p1,b).  P estimate: p1_slot == b_slot, l1_store < 0. */

@@ -589,8 +589,9 @@ static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv
 
 /* search half of estimateCUCost over a whole frame (slicetype.cpp:4050-4059, 4103-4183) */
 void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
-                    const uint16_t* mvcost, int bBidir, int32_t* mvs, int32_t* mvCosts)
+                    const uint16_t* mvcost, int bBidir, int32_t* mvs, int32_t* mvCosts, int32_t* skipCount)
 {
+    int skips = 0;
     or_me m;
     m.g = g; m.stride = g->stride; m.mvcost = mvcost;
     const int bw = g->bw, bh = g->bh;
@@ -638,11 +639,13 @@ void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel
             {
                 fencCost = skipCost;
                 best.x = best.y = 0;
+                skips++;
             }
             mvs[2 * cuXY] = best.x; mvs[2 * cuXY + 1] = best.y;
             mvCosts[cuXY] = fencCost;
         }
     }
+    if (skipCount) *skipCount = skips;
 }
 
 /* cost half of estimateCUCost + frame sums (slicetype.cpp:4187-4248) */

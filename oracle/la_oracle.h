@@ -80,7 +80,7 @@ void or_intra_estimate(const or_geom* g, const or_pixel* plane0 /* lowresPlane[0
  * zero-MV skip rule (slicetype.cpp:4165-4181).  rowsPerSlice <= 0 means no slices. */
 void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
                     const uint16_t* mvcost /* centre */, int bBidir,
-                    int32_t* mvs /* ncu*2 */, int32_t* mvCosts /* ncu */);
+                    int32_t* mvs /* ncu*2 */, int32_t* mvCosts /* ncu */, int32_t* skipCount /* may be NULL */);
 
 /* Cost half of estimateCUCost + the sums of estimateFrameCost (slicetype.cpp:4187-4248,
  * 4050-4067).  For a P estimate pass ref1Planes = NULL. */

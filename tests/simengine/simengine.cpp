@@ -23,6 +23,7 @@ struct SimSlot
     std::vector<uint16_t> lowresCosts00, propagate;
     std::vector<double> qpAq, qpCuTree;
     std::vector<std::vector<int32_t> > mvs, mvCosts;          /* per MV store */
+    std::vector<int32_t> skipFlag;
     std::vector<std::vector<uint16_t> > costs;                /* per cost store */
     std::vector<std::vector<int32_t> > rowSatds;
     std::vector<x265cu_cost_result> results;
@@ -101,6 +102,7 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     s.lowresCosts00.assign(ncu, 0); s.rowSatds00.assign(g.bh, 0); s.propagate.assign(ncu, 0);
     s.qpAq.assign(ncu, 0.0); s.qpCuTree.assign(ncu, 0.0);
     s.mvs.assign(3 * nb, std::vector<int32_t>()); s.mvCosts.assign(3 * nb, std::vector<int32_t>());
+    s.skipFlag.assign(3 * nb, 0);
     s.costs.assign(2 * nb * nb, std::vector<uint16_t>()); s.rowSatds.assign(2 * nb * nb, std::vector<int32_t>());
     s.results.assign(2 * nb * nb, x265cu_cost_result());
     memset(&s.stats, 0, sizeof(s.stats));
@@ -143,9 +145,15 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
             planePtrs(c, r.planes, rp);
         f.mvs[j.store].assign(2 * g.ncu, 0); f.mvCosts[j.store].assign(g.ncu, 0);
         or_search_list(&g, &f.planes[g.padOffset], rp, &c->mvcost[c->cfg.mvcost_half], j.bidir_ctx,
-                       &f.mvs[j.store][0], &f.mvCosts[j.store][0]);
+                       &f.mvs[j.store][0], &f.mvCosts[j.store][0], &f.skipFlag[j.store]);
         c->counters.kernel_launches++;
     }
+    return 0;
+}
+
+int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* stores, int32_t n, int32_t* flags)
+{
+    for (int i = 0; i < n; i++) flags[i] = c->slots[slots[i]].skipFlag[stores[i]] != 0;
     return 0;
 }
 

@@ -261,6 +261,7 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
         char* st = mvStorePtr(c, j.fenc_slot, j.store);
         dev[i].mvOut = (int*)st;
         dev[i].costOut = (int*)st + g.ncu;
+        dev[i].flagOut = (int*)st + 2 * g.ncu;
         dev[i].bidir = j.bidir_ctx;
         dev[i].pad = 0;
     }
@@ -287,19 +288,22 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
 {
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
+    /* P estimates (one thread per block) first, then B estimates (8 lanes per block): two launches with the
+     * grid each needs */
     std::vector<CostJobDev<P> > dev(n);
-    bool anyB = false;
+    int nP = 0;
+    for (int i = 0; i < n; i++) nP += jobs[i].l1_store < 0;
+    int iP = 0, iB = nP;
     for (int i = 0; i < n; i++)
     {
         const x265cu_cost_job& j = jobs[i];
         if (!slotOk(c, j.b_slot) || !slotOk(c, j.p0_slot) || !slotOk(c, j.p1_slot) || j.out < 2 || j.out >= c->geom.n_cost_stores ||
             j.l0_store < 0 || j.l0_store >= c->geom.n_mv_stores || j.l1_store >= c->geom.n_mv_stores)
         { snprintf(c->err, sizeof(c->err), "cost job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
-        CostJobDev<P>& d = dev[i];
+        CostJobDev<P>& d = dev[j.l1_store < 0 ? iP++ : iB++];
         d.fenc0 = slotPtr<P>(c, j.b_slot, L.planes);
         d.ref0 = slotPtr<P>(c, j.p0_slot, L.planes);
         d.ref1 = j.l1_store >= 0 ? slotPtr<P>(c, j.p1_slot, L.planes) : NULL;
-        anyB |= j.l1_store >= 0;
         char* m0 = mvStorePtr(c, j.b_slot, j.l0_store);
         d.mv0 = (const int*)m0; d.cost0 = (const int*)m0 + g.ncu;
         if (j.l1_store >= 0)
@@ -320,13 +324,17 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
     if (st) return st;
     CK(cudaMemcpyAsync(c->d_jobs, &dev[0], n * sizeof(CostJobDev<P>), cudaMemcpyHostToDevice, c->stream));
     {
-        Prof pr(c, X265CU_K_COST, 2);
-        cost_clear_kernel<P><<<n, 256, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs);
-        /* P jobs use one thread per block, B jobs 8 lanes per block; the grid is sized for the larger */
-        dim3 grid(anyB ? (g.ncu + 15) / 16 : (g.ncu + 127) / 128, n);
+        Prof pr(c, X265CU_K_COST, 1 + (nP > 0) + (n > nP));
         for (int base = 0; base < n; base += 65535)
+            cost_clear_kernel<P><<<(n - base) < 65535 ? (n - base) : 65535, 256, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs + base);
+        for (int base = 0; base < nP; base += 65535)
         {
-            dim3 gg(grid.x, (unsigned)((n - base) < 65535 ? (n - base) : 65535));
+            dim3 gg((g.ncu + 127) / 128, (unsigned)((nP - base) < 65535 ? (nP - base) : 65535));
+            cost_kernel<P><<<gg, 128, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs + base);
+        }
+        for (int base = nP; base < n; base += 65535)
+        {
+            dim3 gg((g.ncu + 15) / 16, (unsigned)((n - base) < 65535 ? (n - base) : 65535));
             cost_kernel<P><<<gg, 128, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs + base);
         }
     }
@@ -491,7 +499,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     SECTION(lowresCosts00, (size_t)g.ncu * 2);
     L.rowSatds00 = o; o += alignUp((size_t)g.bh * 4, 16);
     L.stats = o; o = alignUp(o + sizeof(FrameStatsDev), 256);
-    L.mvStoreStride = alignUp((size_t)g.ncu * 8, 256);
+    L.mvStoreStride = alignUp((size_t)g.ncu * 8 + 16, 256);     /* packed MVs, costs, skip flag */
     SECTION(mvStores, L.mvStoreStride * G.n_mv_stores);
     L.costRowOff = alignUp((size_t)g.ncu * 2, 16);
     L.costResOff = L.costRowOff + alignUp((size_t)g.bh * 4, 16);
@@ -620,6 +628,23 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
     if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
     if (n <= 0) return X265CU_OK;
     return DISPATCH(searchBatchT, c, jobs, n);
+}
+
+int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* stores, int32_t n, int32_t* flags)
+{
+    if (n <= 0) return X265CU_OK;
+    int st = ensureHost(c, n * sizeof(int));
+    if (st) return st;
+    for (int i = 0; i < n; i++)
+    {
+        if (!slotOk(c, slots[i]) || stores[i] < 0 || stores[i] >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
+        CK(cudaMemcpyAsync(c->h_results + i * sizeof(int), mvStorePtr(c, slots[i], stores[i]) + (size_t)c->g.ncu * 8, sizeof(int),
+                           cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(flags, c->h_results, n * sizeof(int));
+    c->counters.d2h_bytes += n * sizeof(int);
+    return X265CU_OK;
 }
 
 int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)

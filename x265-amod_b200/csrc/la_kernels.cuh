@@ -436,6 +436,7 @@ struct SearchJobDev
     const P* ref0;          /* tiled buffer of plane 0 of the (possibly weighted) reference; planes at +i*planeSize */
     int*     mvOut;         /* ncu packed MVs: (x & 0xffff) | (y << 16), quarter-pel */
     int*     costOut;       /* ncu */
+    int*     flagOut;       /* set to 1 when any block took the zero-MV skip (slicetype.cpp:4177-4181) */
     int      bidir;
     int      pad;
 };
@@ -618,6 +619,8 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
     __syncthreads();
     const int job = s_ticket / nbands, band = s_ticket % nbands;
     const SearchJobDev<P> J = jobs[job];
+    /* band 0 owns the lowest ticket of its job and every other band waits on its progress chain */
+    if (band == 0 && threadIdx.x == 0) *J.flagOut = 0;
     const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
     const int warp = threadIdx.x >> 5;
     const int bw = g.bw, bh = g.bh;
@@ -712,13 +715,16 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
             const MV2 mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
             MV2 best;
             int fencCost = motionEstimate(m, mvmin, mvmax, mvp, best);
+            bool skipped = false;
             if (skipCost < 64 && skipCost < fencCost && J.bidir)
             {
                 fencCost = skipCost;
                 best.x = best.y = 0;
+                skipped = true;
             }
             if (r == 0 && act)
             {
+                if (skipped) *J.flagOut = 1;
                 const int packed = packMv(best);
                 s_mv[grp * bw + cuX] = packed;
                 __stcg(J.mvOut + cu, packed);

@@ -399,9 +399,50 @@ static void addCost(std::vector<x265cu_cost_job>& jobs, Lowres* b, Lowres* p0, L
     jobs.push_back(j);
 }
 
+void Lookahead::launchJobs()
+{
+    if (!m_searchJobs.empty())
+        check(x265cu_search_batch(m_ctx, &m_searchJobs[0], (int)m_searchJobs.size()), "x265cu_search_batch");
+    if (!m_costJobs.empty())
+        check(x265cu_cost_batch(m_ctx, &m_costJobs[0], (int)m_costJobs.size()), "x265cu_cost_batch");
+    m_searchJobs.clear(); m_costJobs.clear();
+}
+
+/* every frame cost of `variant` (= kind of the L0 search it reads) whose searches exist on the device and whose
+ * frames are resident: P estimates (d0, 0) and B estimates (d0, d1) the reference can ask for (p1 - p0 <= bframes+1,
+ * slicetype.cpp:3221-3305; every (d0, d1) when the frame-cost batches of :2696-2735 are emulated) */
+void Lookahead::enqueueCosts(int variant)
+{
+    const int B = m_param.bframes, nb = m_geom.nb;
+    for (size_t i = 0; i < m_resident.size(); i++)
+    {
+        Frame* bf = m_resident[i];
+        if (!bf->m_lowresInit) continue;
+        Lowres* b = &bf->m_lowres;
+        for (int d0 = 1; d0 <= B + 1; d0++)
+        {
+            if (!b->haveSearch[variant][d0]) continue;
+            Frame* p0f = frameOfPoc(bf->m_poc - d0);
+            if (!p0f) continue;
+            addCost(m_costJobs, b, &p0f->m_lowres, NULL, d0, 0, variant, nb);
+            const int maxD1 = m_bBatchFrameCosts ? B : B + 1 - d0;
+            for (int d1 = 1; d1 <= maxD1; d1++)
+            {
+                if (!b->haveSearch[2][d1]) continue;
+                Frame* p1f = frameOfPoc(bf->m_poc + d1);
+                if (!p1f) continue;
+                addCost(m_costJobs, b, &p0f->m_lowres, &p1f->m_lowres, d0, d1, variant, nb);
+            }
+        }
+    }
+}
+
 /* Eager whole-window batch: for every frame that arrived since the last decision, every motion
  * search and frame cost the reference could ask for (distances <= bframes+1, slicetype.cpp:
- * 2674-2689, 3221-3305) whose frames are all resident. */
+ * 2674-2689, 3221-3305) whose frames are all resident.
+ * With B frames an L0 search exists in two variants (P / B context).  Phase 1 runs the B-context variant only
+ * and learns from the engine whether the zero-MV skip rule ever fired; where it did not, the P-context variant is
+ * the same search and is aliased instead of computed.  Phase 2 computes the P-context variant for the rest. */
 void Lookahead::speculate()
 {
     const int B = m_param.bframes, nb = m_geom.nb;
@@ -428,7 +469,7 @@ void Lookahead::speculate()
     t0 = nowSec();
 
     m_searchJobs.clear(); m_costJobs.clear();
-    const int maxD1 = B;                                  /* p1 - b <= bframes */
+    const int firstKind = B > 0 ? 1 : 0;
     for (size_t i = 0; i < fresh.size(); i++)
     {
         Frame* fn = fresh[i];
@@ -439,42 +480,66 @@ void Lookahead::speculate()
             Frame* rf = frameOfPoc(fn->m_poc - d);
             if (!rf || !rf->m_lowresInit) break;
             Lowres* r = &rf->m_lowres;
-            addSearch(m_searchJobs, n, r, 0, d, nb);                 /* L0(n,d), P context */
-            addCost(m_costJobs, n, r, NULL, d, 0, 0, nb);
-            if (B > 0)
-            {
-                addSearch(m_searchJobs, n, r, 1, d, nb);             /* L0(n,d), B context */
-                addCost(m_costJobs, n, r, NULL, d, 0, 1, nb);
-                if (d <= maxD1)
-                    addSearch(m_searchJobs, r, n, 2, d, nb);         /* L1(n-d,d), reference = n */
-            }
-        }
-        /* B estimates completed by n's arrival: b = n - d1, p0 = b - d0 */
-        for (int d1 = 1; d1 <= maxD1; d1++)
-        {
-            Frame* bf = frameOfPoc(fn->m_poc - d1);
-            if (!bf || !bf->m_lowresInit) break;
-            int maxD0 = m_bBatchFrameCosts ? B + 1 : B + 1 - d1;
-            for (int d0 = 1; d0 <= maxD0; d0++)
-            {
-                Frame* p0f = frameOfPoc(bf->m_poc - d0);
-                if (!p0f || !p0f->m_lowresInit) break;
-                Lowres* b = &bf->m_lowres;
-                if (!b->haveSearch[0][d0] || !b->haveSearch[1][d0] || !b->haveSearch[2][d1]) continue;
-                addCost(m_costJobs, b, &p0f->m_lowres, n, d0, d1, 0, nb);
-                addCost(m_costJobs, b, &p0f->m_lowres, n, d0, d1, 1, nb);
-            }
+            addSearch(m_searchJobs, n, r, firstKind, d, nb);        /* L0(n,d) */
+            if (B > 0 && d <= B)
+                addSearch(m_searchJobs, r, n, 2, d, nb);            /* L1(n-d,d), reference = n */
         }
     }
-    if (!m_searchJobs.empty())
-        check(x265cu_search_batch(m_ctx, &m_searchJobs[0], (int)m_searchJobs.size()), "x265cu_search_batch");
-    if (!m_costJobs.empty())
-        check(x265cu_cost_batch(m_ctx, &m_costJobs[0], (int)m_costJobs.size()), "x265cu_cost_batch");
+    enqueueCosts(firstKind);
+    launchJobs();
     m_timers[2] += nowSec() - t0;
     t0 = nowSec();
     std::vector<Lowres*> who;
     for (size_t i = 0; i < m_resident.size(); i++) who.push_back(&m_resident[i]->m_lowres);
     fetchResults(who);
+    if (B > 0 && !m_failed)
+    {
+        /* which B-context searches applied the skip rule? */
+        std::vector<int32_t> slots, stores, flags;
+        std::vector<std::pair<Lowres*, int> > ref;
+        for (size_t i = 0; i < who.size(); i++)
+            for (int d = 1; d <= B + 1; d++)
+                if (who[i]->haveSearch[1][d] && !who[i]->flagFetched[d])
+                {
+                    slots.push_back(who[i]->slot); stores.push_back(1 * nb + d);
+                    ref.push_back(std::make_pair(who[i], d));
+                }
+        if (!slots.empty())
+        {
+            flags.resize(slots.size());
+            if (check(x265cu_search_flags_get(m_ctx, &slots[0], &stores[0], (int)slots.size(), &flags[0]), "x265cu_search_flags_get"))
+                for (size_t i = 0; i < ref.size(); i++)
+                {
+                    Lowres* l = ref[i].first; int d = ref[i].second;
+                    l->flagFetched[d] = 1;
+                    if (!l->haveSearch[0][d])
+                        l->l0Alias[d] = flags[i] ? 2 : 1;
+                }
+        }
+        m_timers[3] += nowSec() - t0;
+        t0 = nowSec();
+        /* phase 2: P-context variants that really differ */
+        for (size_t i = 0; i < m_resident.size(); i++)
+        {
+            Frame* fn = m_resident[i];
+            if (!fn->m_lowresInit) continue;
+            Lowres* n = &fn->m_lowres;
+            for (int d = 1; d <= B + 1; d++)
+                if (n->l0Alias[d] == 2 && !n->haveSearch[0][d])
+                {
+                    Frame* rf = frameOfPoc(fn->m_poc - d);
+                    if (rf) addSearch(m_searchJobs, n, &rf->m_lowres, 0, d, nb);
+                }
+        }
+        enqueueCosts(0);
+        if (!m_searchJobs.empty() || !m_costJobs.empty())
+        {
+            launchJobs();
+            m_timers[2] += nowSec() - t0;
+            t0 = nowSec();
+            fetchResults(who);
+        }
+    }
     m_timers[3] += nowSec() - t0;
 }
 
@@ -558,6 +623,7 @@ int64_t Lookahead::estimateFrameCost(Lowres** frames, int p0, int p1, int b, boo
         const bool bDoSearch1 = p1 > b && fenc->mvStore[1][d1] < 0;
         /* first touch decides which variant of the L0 search the reference would hold */
         int l0kind = bDoSearch0 ? (p1 > b ? 1 : 0) : fenc->mvStore[0][d0] / nb;
+        l0kind = effKind(fenc, d0, l0kind);      /* identical variants share one store */
         ensureEstimate(fenc, frames[p0], p1 > b ? frames[p1] : NULL, d0, d1, l0kind);
         if (m_failed) return 0;
         if (bDoSearch0) fenc->mvStore[0][d0] = l0kind * nb + d0;

@@ -91,6 +91,10 @@ struct Lowres
     int     slot;
     bool    statsFetched;
     uint8_t haveSearch[3][BFRAME_MAX + 2];                   /* store kind x dist computed on device */
+    /* L0 distance d: 0 = unknown, 1 = the B-context search never applied the zero-MV skip, so the P-context
+     * search is the same search and store kind 0 aliases kind 1; 2 = the two variants differ */
+    uint8_t l0Alias[BFRAME_MAX + 2];
+    uint8_t flagFetched[BFRAME_MAX + 2];
     uint8_t haveCost[BFRAME_MAX + 2][BFRAME_MAX + 2][2];     /* cost store computed on device */
     uint8_t resultFetched[BFRAME_MAX + 2][BFRAME_MAX + 2][2];
     x265cu_cost_result result[BFRAME_MAX + 2][BFRAME_MAX + 2][2];
@@ -191,6 +195,9 @@ private:
     /* device orchestration */
     void    preLookahead(const std::vector<Frame*>& fr);
     void    speculate();
+    void    enqueueCosts(int variant);
+    void    launchJobs();
+    int     effKind(const Lowres* l, int d0, int kind) const { return (kind == 0 && l->l0Alias[d0] == 1) ? 1 : kind; }
     void    weightsAnalyseBatch(const std::vector<std::pair<Lowres*, Lowres*> >& pairs);
     void    ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind);
     void    fetchResults(const std::vector<Lowres*>& who);
