@@ -276,7 +276,7 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
     {
         Prof pr(c, X265CU_K_SEARCH, 1);
         const size_t smem = (size_t)LA_BAND_ROWS * g.bw * sizeof(int);
-        search_kernel<P><<<n * nbands, LA_BAND_ROWS * 8, smem, c->stream>>>(g, (const SearchJobDev<P>*)c->d_jobs, nbands,
+        search_kernel<P><<<n * nbands, LA_BAND_ROWS * 8, smem, c->stream>>>(g, (const SearchJobDev<P>*)c->d_jobs, nbands, n,
                                                                             c->d_mvcost + c->cfg.mvcost_half, c->d_sync, c->d_sync + 1);
     }
     CK(cudaGetLastError());

@@ -126,9 +126,11 @@ __device__ __forceinline__ Row<uint8_t> avgRow(const Row<uint8_t>& a, const Row<
 }
 __device__ __forceinline__ Row<uint16_t> avgRow(const Row<uint16_t>& a, const Row<uint16_t>& b)
 {
+    /* samples are at most 10 bits wide (x265cu_create rejects more), so the two 16-bit lanes cannot carry into
+     * each other: one 3-input add, one shift, one mask */
     Row<uint16_t> r;
 #pragma unroll
-    for (int i = 0; i < 4; i++) r.v[i] = __vavgu2(a.v[i], b.v[i]);
+    for (int i = 0; i < 4; i++) r.v[i] = ((a.v[i] + b.v[i] + 0x00010001u) >> 1) & 0x7fff7fffu;
     return r;
 }
 
@@ -137,9 +139,19 @@ __device__ __forceinline__ int sadRow(const Row<uint8_t>& a, const Row<uint8_t>&
 {
     return (int)(__vsadu4(a.v[0], b.v[0]) + __vsadu4(a.v[1], b.v[1]));
 }
+/* packed 16-bit min / max are native on sm_100 (VIMNMX.U16x2); max - min never borrows across the lanes */
+__device__ __forceinline__ uint32_t absdiffU16x2(uint32_t a, uint32_t b)
+{
+    uint32_t mx, mn;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(a), "r"(b));
+    asm("min.u16x2 %0, %1, %2;" : "=r"(mn) : "r"(a), "r"(b));
+    return mx - mn;
+}
 __device__ __forceinline__ int sadRow(const Row<uint16_t>& a, const Row<uint16_t>& b)
 {
-    return (int)(__vsadu2(a.v[0], b.v[0]) + __vsadu2(a.v[1], b.v[1]) + __vsadu2(a.v[2], b.v[2]) + __vsadu2(a.v[3], b.v[3]));
+    /* four packed |a-b| pairs; each lane sums to at most 4 * 1023 */
+    const uint32_t s = absdiffU16x2(a.v[0], b.v[0]) + absdiffU16x2(a.v[1], b.v[1]) + absdiffU16x2(a.v[2], b.v[2]) + absdiffU16x2(a.v[3], b.v[3]);
+    return (int)((s & 0xffffu) + (s >> 16));
 }
 
 __device__ __forceinline__ int px(const Row<uint8_t>& r, int i)  { return (int)((r.v[i >> 2] >> ((i & 3) * 8)) & 0xffu); }
@@ -180,20 +192,40 @@ __device__ __forceinline__ uint32_t abs2(uint32_t a)
     return (a + s) ^ s;
 }
 
-/* 8x8 SATD of each group's block from each lane's row of differences.  The reference sums two
- * 8x4 SATDs, each = (sum |4x4 Hadamard coefficients| of its two 4x4 blocks) >> 1.  Lanes 0-3 of a
- * group hold the upper 8x4, lanes 4-7 the lower.  Horizontal butterflies in-lane; the two 4x4 blocks
- * of a row are packed lo/hi in one word; vertical butterflies are two xor-shuffle stages.
- * Valid for |d| <= 1023 (8- and 10-bit): coefficients stay below 2^15.  Every lane returns the total. */
-__device__ __forceinline__ int groupSatd(const int d[8])
+/* A row re-ordered for the SWAR Hadamard: word i holds sample i in its low half and sample i+4 in its high half
+ * (the x264 sum2_t pairing of pixel.cpp:248-251), so one 32-bit subtract yields two differences and one add /
+ * subtract is a butterfly of both 4x4 blocks of the row at once. */
+struct RowH { uint32_t v[4]; };
+
+__device__ __forceinline__ RowH toH(const Row<uint8_t>& r)
 {
-    const int a0 = d[0] + d[1], a1 = d[0] - d[1], a2 = d[2] + d[3], a3 = d[2] - d[3];
-    const int b0 = d[4] + d[5], b1 = d[4] - d[5], b2 = d[6] + d[7], b3 = d[6] - d[7];
-    uint32_t p[4];
-    p[0] = (uint32_t)(a0 + a2) + ((uint32_t)(b0 + b2) << 16);
-    p[1] = (uint32_t)(a1 + a3) + ((uint32_t)(b1 + b3) << 16);
-    p[2] = (uint32_t)(a0 - a2) + ((uint32_t)(b0 - b2) << 16);
-    p[3] = (uint32_t)(a1 - a3) + ((uint32_t)(b1 - b3) << 16);
+    RowH h;
+    h.v[0] = __byte_perm(r.v[0], r.v[1], 0x7470) & 0x00ff00ffu;     /* bytes: s0, -, s4, - */
+    h.v[1] = __byte_perm(r.v[0], r.v[1], 0x7571) & 0x00ff00ffu;
+    h.v[2] = __byte_perm(r.v[0], r.v[1], 0x7672) & 0x00ff00ffu;
+    h.v[3] = __byte_perm(r.v[0], r.v[1], 0x7773) & 0x00ff00ffu;
+    return h;
+}
+__device__ __forceinline__ RowH toH(const Row<uint16_t>& r)
+{
+    RowH h;
+    h.v[0] = __byte_perm(r.v[0], r.v[2], 0x5410);      /* s0 | s4 << 16 */
+    h.v[1] = __byte_perm(r.v[0], r.v[2], 0x7632);      /* s1 | s5 << 16 */
+    h.v[2] = __byte_perm(r.v[1], r.v[3], 0x5410);      /* s2 | s6 << 16 */
+    h.v[3] = __byte_perm(r.v[1], r.v[3], 0x7632);      /* s3 | s7 << 16 */
+    return h;
+}
+
+/* 8x8 SATD of each group's block, lane r holding row r of both operands in RowH order.  The reference sums two
+ * 8x4 SATDs, each = (sum |4x4 Hadamard coefficients| of its two 4x4 blocks) >> 1 (pixel.cpp:239-297).  Lanes 0-3 of a
+ * group hold the upper 8x4, lanes 4-7 the lower.  Differences and horizontal butterflies are SWAR (low half = left
+ * 4x4 block, high half = right one), vertical butterflies are two xor-shuffle stages, abs2 undoes the borrows.
+ * Valid for |d| <= 1023 (8- and 10-bit): coefficients stay below 2^15.  Every lane returns the total. */
+__device__ __forceinline__ int groupSatdH(const RowH& a, const RowH& b)
+{
+    const uint32_t d0 = a.v[0] - b.v[0], d1 = a.v[1] - b.v[1], d2 = a.v[2] - b.v[2], d3 = a.v[3] - b.v[3];
+    const uint32_t a0 = d0 + d1, a1 = d0 - d1, a2 = d2 + d3, a3 = d2 - d3;
+    uint32_t p[4] = { a0 + a2, a1 + a3, a0 - a2, a1 - a3 };
     const bool odd1 = threadIdx.x & 1, odd2 = threadIdx.x & 2;
     uint32_t sum = 0;
 #pragma unroll
@@ -214,9 +246,7 @@ __device__ __forceinline__ int groupSatd(const int d[8])
 template <typename P>
 __device__ __forceinline__ int groupSatdRows(const Row<P>& a, const Row<P>& b)
 {
-    int d[8];
-    diffRow(a, b, d);
-    return groupSatd(d);
+    return groupSatdH(toH(a), toH(b));
 }
 
 /* the four tiled half-pel planes of one frame and the origin of the group's block in buffer coordinates */
@@ -246,10 +276,14 @@ __device__ __forceinline__ Row<P> mcRow(const RefBlock<P>& rb, int qx, int qy, i
     return A;
 }
 
-__device__ __forceinline__ int ldAcquire(const int* p)
+/* Progress counters between CTAs are polled with a RELAXED load: on this architecture ld.acquire.gpu (and
+ * __threadfence) is followed by CCTL.IVALL, which throws away the SM's whole L1 on every poll (ncu on the first
+ * version: 2.2e9 polls, L1 hit rate 13 %).  The data guarded by the counter is read with ld.cg, i.e. from L2, the
+ * point of coherence, so no L1 invalidation is needed; the producer publishes with st.release.gpu. */
+__device__ __forceinline__ int ldRelaxed(const int* p)
 {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void stRelease(int* p, int v)

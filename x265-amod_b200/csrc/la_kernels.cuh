@@ -609,7 +609,7 @@ __device__ __forceinline__ MV2 unpackMv(int p) { MV2 m = { (int)(short)(p & 0xff
 __device__ __forceinline__ int packMv(MV2 m) { return (m.x & 0xffff) | (m.y << 16); }
 
 template <typename P>
-__global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nbands,
+__global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nbands, int njobs,
                                                                   const unsigned short* __restrict__ mvcost,
                                                                   int* ticketCounter, int* progress)
 {
@@ -617,7 +617,9 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
     __shared__ int s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticketCounter, 1);
     __syncthreads();
-    const int job = s_ticket / nbands, band = s_ticket % nbands;
+    /* band-major: every job's band 0 first, then every band 1, ...  With more jobs than resident CTAs a band is
+     * only started when the band below it is (nearly) finished, so no resident CTA idles on its predecessor */
+    const int band = s_ticket / njobs, job = s_ticket % njobs;
     const SearchJobDev<P> J = jobs[job];
     /* band 0 owns the lowest ticket of its job and every other band waits on its progress chain */
     if (band == 0 && threadIdx.x == 0) *J.flagOut = 0;
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
                 if (threadIdx.x == 0 && act)
                 {
                     const int need = min(bw, k + 2);
-                    while (ldAcquire(belowProgress) < need) __nanosleep(64);
+                    while (ldRelaxed(belowProgress) < need) __nanosleep(100);
                 }
                 __syncwarp();
             }
@@ -730,10 +732,7 @@ __global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const 
                 __stcg(J.mvOut + cu, packed);
                 J.costOut[cu] = fencCost;
                 if (grp == rowsInBand - 1)
-                {
-                    __threadfence();
-                    stRelease(myProgress, k + 1);
-                }
+                    stRelease(myProgress, k + 1);      /* orders this thread's MV store before the counter */
             }
         }
         __syncthreads();
