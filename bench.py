@@ -162,12 +162,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the lookahead engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl")
-
     import _pkg
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("x265_amod_b200_shard", os.path.join(ROOT, "x265-amod_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec); spec.loader.exec_module(shard)
+    dist = shard.init("nccl") if world > 1 else None
     pkg = _pkg.load_pkg()
     eng = pkg.load_engine()
 
@@ -259,11 +258,7 @@ def main():
         return max(ms.value, 0.0), wall, types, delta, prof
 
     def reduce_max(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.reduce_max(dist, x, device="cuda")
 
     # --- value: pictures resident in HBM ---------------------------------------------------------------
     for _ in range(args.warmup):

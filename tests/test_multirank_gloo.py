@@ -1,0 +1,63 @@
+"""N > 1 path on CPU: two gloo ranks, each driving its own independent lookahead stream (through the CPU
+sim-engine), then the same barrier / max-over-ranks / sum-of-frames plumbing bench.py uses under NCCL."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, simdir, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import importlib.util
+    import _pkg
+    pkg = _pkg.load_pkg(); synth = _pkg.load_synth()
+    spec = importlib.util.spec_from_file_location("shard", os.path.join(ROOT, "x265-amod_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec); spec.loader.exec_module(shard)
+    dist = shard.init("gloo")
+    r, w, _ = shard.rank_info()
+    mine = shard.streams_for_rank(4, r, w)
+    frames = 0
+    types = {}
+    for s in mine:
+        seq = synth.SynthSequence(176, 144, depth=8, seed=10 + s, cuts=(9,))
+        la = pkg.Lookahead(176, 144, depth=8, lib_path=os.path.join(simdir, "libx265la_sim8.so"), bframes=3, lookaheadDepth=8)
+        out = pkg.run_sequence(la, (seq.frame(i) for i in range(16)), collect=False)
+        la.close()
+        frames += len(out)
+        types[s] = [f["sliceType"] for f in out]
+    dist.barrier()
+    fps, ms = shard.aggregate_throughput(dist, frames, 100.0 + 50.0 * r)
+    q.put((r, mine, frames, fps, ms, types))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_streams(simdir):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, simdir, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, s0, f0, fps0, ms0, t0), (r1, s1, f1, fps1, ms1, t1) = res
+    assert s0 == [0, 2] and s1 == [1, 3]                 # every stream owned by exactly one rank
+    assert f0 == 32 and f1 == 32
+    assert ms0 == ms1 == 150.0                           # max over ranks
+    assert abs(fps0 - 64 / 0.150) < 1e-6 and fps0 == fps1  # total frames / slowest rank
+    # streams are independent: a single-rank run of stream 1 gives the same decisions
+    sys.path.insert(0, ROOT)
+    import _pkg
+    pkg = _pkg.load_pkg(); synth = _pkg.load_synth()
+    seq = synth.SynthSequence(176, 144, depth=8, seed=11, cuts=(9,))
+    la = pkg.Lookahead(176, 144, depth=8, lib_path=os.path.join(simdir, "libx265la_sim8.so"), bframes=3, lookaheadDepth=8)
+    out = pkg.run_sequence(la, (seq.frame(i) for i in range(16)), collect=False)
+    assert [f["sliceType"] for f in out] == t1[1]
