@@ -34,7 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the >=20x target is quoted on
-    "2160p-main10": dict(width=3840, height=2160, depth=10, frames=120, cpu_frames=36, seed=2,
+    "2160p-main10": dict(width=3840, height=2160, depth=10, frames=120, cpu_frames=72, seed=2,
                          la=dict(bframes=8, lookaheadDepth=60, bFrameAdaptive=2),
                          text="2160p main10 --rc-lookahead 60 --bframes 8 --b-adapt 2 cutree (BASELINE configs[1])"),
     # BASELINE.json configs[0]
