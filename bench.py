@@ -146,6 +146,10 @@ def main():
     ap.add_argument("--workload", default="2160p-main10", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--async-depth", type=int, default=16,
+                    help="extra frames of input delay (LookaheadParam::asyncDepth): same decisions, GPU slack")
+    ap.add_argument("--speculate", type=int, default=1)
+    ap.add_argument("--pending-max", type=int, default=0)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.frames:
@@ -183,7 +187,7 @@ def main():
     torch.cuda.synchronize()
     bytes_in = sum(t.numel() * t.element_size() for t in host[0])
 
-    la_kw = dict(wl["la"])
+    la_kw = dict(wl["la"], asyncDepth=args.async_depth, speculate=args.speculate, pendingMax=args.pending_max)
     geom = {}
 
     def one_step(pics, fetch_results):
@@ -245,10 +249,11 @@ def main():
         ht = (C.c_double * 8)()
         la.lib.x265la_get_timers(la.h, ht, 1)
         host_t = dict(prelookahead_wait=ht[0], weightp=ht[1], enqueue=ht[2], result_wait=ht[3], decisions=ht[4],
-                      slicetype_decide=ht[5], calls=ht[6], wall=wall / 1000.0)
-        pm = (C.c_double * 7)(); pn = (C.c_uint64 * 7)()
+                      slicetype_decide=ht[5], calls=ht[6], add_picture_speculation=ht[7], wall=wall / 1000.0)
+        pm = (C.c_double * 7)(); pn = (C.c_uint64 * 7)(); pb = (C.c_double * 7)()
+        eng.x265cu_profile_get_busy(ctx, pb)
         eng.x265cu_profile_get(ctx, pm, pn, 1)
-        prof = {k: (pm[i], int(pn[i])) for i, k in enumerate(pkg.K_NAMES)}
+        prof = {k: (pm[i], int(pn[i]), pb[i]) for i, k in enumerate(pkg.K_NAMES)}
         delta = dict(launches=cnt1.kernel_launches - cnt0.kernel_launches, h2d=cnt1.h2d_bytes - cnt0.h2d_bytes,
                      d2h=(cnt1.d2h_bytes - cnt0.d2h_bytes), search_jobs=cnt1.search_jobs - cnt0.search_jobs,
                      cost_jobs=cnt1.cost_jobs - cnt0.cost_jobs)
@@ -294,16 +299,26 @@ def main():
     bpp = 2 if depth > 8 else 1
     P = geom["low_w"] * geom["low_h"] * bpp
     bytes_per_search = 5 * P + 12 * geom["ncu"]            # fenc P + ref 4P read, 12 B/block written
-    s_ms = sum(p["search"][0] for p in profs); s_launch = sum(p["search"][1] for p in profs)
+    # batches overlap on the GPU: the denominator is the time during which at least one search launch was running
+    # (union of the CUDA-event intervals of the launches), not the sum of the individual launch durations
+    s_ms = sum(p["search"][2] for p in profs); s_launch = sum(p["search"][1] for p in profs)
+    s_sum_ms = sum(p["search"][0] for p in profs)
     s_jobs = sum(d["search_jobs"] for d in deltas)
     achieved = (s_jobs * bytes_per_search / 1e9) / (s_ms / 1000.0) if s_ms > 0 else 0.0
-    kernel_ms = {k: round(sum(p[k][0] for p in profs) / len(profs), 3) for k in pkg.K_NAMES}
+    kernel_ms = {k: round(sum(p[k][2] for p in profs) / len(profs), 3) for k in pkg.K_NAMES}
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")))
+        traffic = tj.get(args.workload)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "search_kernel (K4 motion search)", "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_search_job": bytes_per_search, "search_jobs_per_step": s_jobs // max(1, len(deltas)),
                 "search_launches_per_step": s_launch // max(1, len(profs)),
-                "avg_launch_ms": round(s_ms / max(1, s_launch), 4),
-                "kernel_ms_per_step": kernel_ms,
+                "avg_launch_ms": round(s_sum_ms / max(1, s_launch), 4),
+                "search_busy_ms_per_step": round(s_ms / max(1, len(profs)), 3),
+                "kernel_busy_ms_per_step": kernel_ms,
                 "host_ms_per_step": {k: round(1000.0 * sum(p["host"][k] for p in profs) / len(profs), 2) for k in profs[0]["host"]},
                 "note": "K4 runs out of L2 and is bound by the integer pipe / wavefront latency, not HBM (SURVEY 8d); "
                         "the HBM fraction is the conservative checkable figure, see profiles/ for pipe utilisation"}
@@ -312,7 +327,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16" if depth > 8 else "u8", "data": "synthetic",
             "config": {"workload": wl["text"], "frames_per_step": F, "resolution": "%dx%d" % (W, H), "bit_depth": depth,
-                       "lookahead_slices": 0, "streams": world, "parallelism": "independent stream per GPU" if world > 1 else "1 GPU",
+                       "lookahead_slices": 0, "async_depth": args.async_depth, "speculate": args.speculate, "streams": world, "parallelism": "independent stream per GPU" if world > 1 else "1 GPU",
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * bytes_in // (1 << 20))},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(e2e_delta["h2d"]), "d2h_bytes_per_step": int(e2e_delta["d2h"])},

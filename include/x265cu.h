@@ -95,8 +95,21 @@ typedef struct
     uint64_t wp_ssd[3];     /* Lowres::wp_ssd (finalised, slicetype.cpp:681-694) */
     uint64_t wp_sum[3];     /* Lowres::wp_sum */
 } x265cu_frame_stats;
-/* synchronises */
+/* 1 when the pre-lookahead of the frame in `slot` has finished (x265cu_frame_stats_get would not wait), 0 when it is
+ * still running, negative on error.  Never blocks. */
+int  x265cu_frame_ready(x265cu_ctx* ctx, int32_t slot);
+/* synchronises (with the pre-lookahead of these frames only) */
 int  x265cu_frame_stats_get(x265cu_ctx* ctx, const int32_t* slots, int32_t n, x265cu_frame_stats* out);
+
+/* ---- asynchronous batches.  Search / cost jobs enqueued between batch_begin and batch_end run on one of the
+ * engine's worker streams, concurrently with the batches opened before and after (a lowres search is a ~500-step
+ * wavefront, so one frame's jobs cannot fill the GPU; a window of frames in flight can).  The engine orders a
+ * batch after the pre-lookahead of every frame uploaded before batch_begin and after the searches whose MV stores
+ * its cost jobs read; every call that reads a store waits for the batch that writes it, and a frame upload waits
+ * for the batches that still use the slot's previous tenant.  Jobs enqueued outside begin/end form a batch of their
+ * own.  Nothing here blocks the caller. */
+int  x265cu_batch_begin(x265cu_ctx* ctx, int64_t* batch_id /* may be NULL */);
+int  x265cu_batch_end(x265cu_ctx* ctx);
 
 /* ---- motion search: the search half of CostEstimateGroup::estimateCUCost (slicetype.cpp:
  * 4103-4183) + MotionEstimate::motionEstimate (motion.cpp:764-1594, HEX + lowres subpel) for one
@@ -110,6 +123,10 @@ typedef struct
                                kind*nb + dist, kind 0 = L0 in P context, 1 = L0 in B context, 2 = L1 */
     int32_t weighted;       /* search the weighted copy of the reference (slicetype.cpp:4083,4128) */
     int32_t w_scale, w_denom, w_offset; /* WeightParam inputWeight/log2WeightDenom/inputOffset */
+    int32_t cond_store;     /* -1 = always run.  Else the job runs only if the search held in MV store `cond_store`
+                               of fenc_slot applied the zero-MV skip rule to at least one block; decided on the
+                               device when the job starts, so the host need not wait for that search (a B-context
+                               L0 search that never skipped IS the P-context search, see x265cu_search_flags_get) */
 } x265cu_search_job;
 int  x265cu_search_batch(x265cu_ctx* ctx, const x265cu_search_job* jobs, int32_t n);
 /* synchronises; flags[i] != 0 when the search stored in (slots[i], stores[i]) applied the zero-MV skip rule to at
@@ -124,6 +141,7 @@ typedef struct
     int32_t b_slot, p0_slot, p1_slot;
     int32_t l0_store, l1_store;   /* MV stores of b_slot to read */
     int32_t out;                  /* cost store of b_slot: (d0*nb + d1)*2 + variant */
+    int32_t cond_store;           /* -1 = always; else like x265cu_search_job::cond_store (MV store of b_slot) */
 } x265cu_cost_job;
 int  x265cu_cost_batch(x265cu_ctx* ctx, const x265cu_cost_job* jobs, int32_t n);
 
@@ -186,9 +204,10 @@ int  x265cu_sync(x265cu_ctx* ctx);
 int  x265cu_timer_start(x265cu_ctx* ctx);
 int  x265cu_timer_stop(x265cu_ctx* ctx, double* ms);
 
-/* counters for bench.py: kernels launched and bytes copied since create */
+/* counters for bench.py: kernels launched and bytes copied since create; search_jobs / cost_jobs count the jobs that
+ * ran (conditional jobs whose condition was false are not counted).  synchronises */
 typedef struct { uint64_t kernel_launches, h2d_bytes, d2h_bytes, search_jobs, cost_jobs; } x265cu_counters;
-int  x265cu_get_counters(const x265cu_ctx* ctx, x265cu_counters* out);
+int  x265cu_get_counters(x265cu_ctx* ctx, x265cu_counters* out);
 
 /* timing hook for bench.py: device time (ms, CUDA events on the engine's stream) spent in each
  * kernel family since the last reset; enabling it adds two non-blocking event records per launch */
@@ -202,6 +221,9 @@ int  x265cu_get_counters(const x265cu_ctx* ctx, x265cu_counters* out);
 #define X265CU_K_COUNT  7
 int  x265cu_profile_enable(x265cu_ctx* ctx, int32_t on);
 int  x265cu_profile_get(x265cu_ctx* ctx, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset);
+/* like x265cu_profile_get, but the time during which at least one kernel of the family was running (batches overlap,
+ * so the sum of the launch durations can exceed the wall clock); call before a resetting x265cu_profile_get */
+int  x265cu_profile_get_busy(x265cu_ctx* ctx, double busy_ms[X265CU_K_COUNT]);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,11 @@ int x265cu_unpin_host(x265cu_ctx*, void*) { return 0; }
 int x265cu_sync(x265cu_ctx*) { return 0; }
 int x265cu_timer_start(x265cu_ctx*) { return 0; }
 int x265cu_timer_stop(x265cu_ctx*, double* ms) { *ms = 0; return 0; }
-int x265cu_get_counters(const x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return 0; }
+int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return 0; }
+int x265cu_batch_begin(x265cu_ctx*, int64_t* id) { static int64_t n = 0; if (id) *id = n++; return 0; }
+int x265cu_batch_end(x265cu_ctx*) { return 0; }
+int x265cu_frame_ready(x265cu_ctx*, int32_t slot) { return (slot % 3) != 1; }   /* exercise both answers */
+int x265cu_profile_get_busy(x265cu_ctx*, double* ms) { for (int i = 0; i < X265CU_K_COUNT; i++) ms[i] = 0; return 0; }
 int x265cu_profile_enable(x265cu_ctx*, int32_t) { return 0; }
 int x265cu_profile_get(x265cu_ctx*, double* ms, uint64_t* n, int32_t) { for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = 0; n[i] = 0; } return 0; }
 
@@ -134,6 +138,8 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
     {
         const x265cu_search_job& j = jobs[i];
         SimSlot& f = c->slots[j.fenc_slot]; SimSlot& r = c->slots[j.ref_slot];
+        if (j.cond_store >= 0 && !f.skipFlag[j.cond_store]) continue;     /* conditional job, x265cu.h */
+        c->counters.search_jobs++;
         const or_pixel* rp[4];
         if (j.weighted)
         {
@@ -164,6 +170,8 @@ int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
     {
         const x265cu_cost_job& j = jobs[i];
         SimSlot& b = c->slots[j.b_slot]; SimSlot& p0 = c->slots[j.p0_slot]; SimSlot& p1 = c->slots[j.p1_slot];
+        if (j.cond_store >= 0 && !b.skipFlag[j.cond_store]) continue;
+        c->counters.cost_jobs++;
         const or_pixel *r0[4], *r1[4];
         planePtrs(c, p0.planes, r0); planePtrs(c, p1.planes, r1);
         const bool bidir = j.l1_store >= 0;

@@ -143,6 +143,21 @@ def test_cuda_speculation_off_is_identical(pkg, synth):
     assert not bad, "\n".join(bad[:10])
 
 
+@pytest.mark.parametrize("name", ["base8", "static_noise", "fade10", "pool16", "b8"])
+@pytest.mark.parametrize("mode", [(2, 9), (2, 0), (1, 12), (1, 3), (0, 0)])
+def test_cuda_speculation_modes_and_async_depth(name, mode, pkg, synth, simdir):
+    """streaming (default) / per-decision / on-demand scheduling of the GPU batches and extra input delay:
+    same published Lowres state, bit for bit"""
+    case = cases.get_case(name)
+    if refbind.available(case[1]):
+        want = cases.run_reference(refbind, synth, case, planes=False)
+    else:
+        want = _as_ref_layout(cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, case[1]), planes=False))
+    got = cases.run_ours(pkg, synth, case, planes=False, speculate=mode[0], asyncDepth=mode[1])
+    bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1))
+    assert not bad, "\n".join(bad[:10])
+
+
 @pytest.mark.parametrize("depth,w,h", [(8, 1920, 1080), (10, 3840, 2160)])
 def test_full_size_properties(depth, w, h, pkg, synth, simdir):
     """BASELINE sizes: oracle spot-check of whole frames plus size-independent properties
@@ -159,8 +174,9 @@ def test_full_size_properties(depth, w, h, pkg, synth, simdir):
         return out
     a = run()
     b = run(speculate=0)
-    assert [f["sliceType"] for f in a] == [f["sliceType"] for f in b]
-    for x, y in zip(a, b):
+    c = run(asyncDepth=6)
+    assert [f["sliceType"] for f in a] == [f["sliceType"] for f in b] == [f["sliceType"] for f in c]
+    for x, y in list(zip(a, b)) + list(zip(a, c)):
         assert np.array_equal(x["costEst"], y["costEst"]) and np.array_equal(x["costEstAq"], y["costEstAq"])
         assert np.array_equal(x["intraCost"], y["intraCost"]) and np.array_equal(x["mvs"], y["mvs"])
         assert np.array_equal(x["qpCuTreeOffset"], y["qpCuTreeOffset"])

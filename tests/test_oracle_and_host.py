@@ -52,6 +52,17 @@ def test_speculation_off_gives_same_results(pkg, synth, simdir):
         assert np.array_equal(x["costEst"], y["costEst"]) and x["sliceType"] == y["sliceType"]
 
 
+@pytest.mark.parametrize("name", ["base8", "static_noise", "fade8", "pool16", "nob"])
+@pytest.mark.parametrize("mode", [(2, 0), (2, 7), (1, 0), (1, 5), (0, 3)])
+def test_speculation_modes_and_async_depth_do_not_change_results(name, mode, pkg, synth, simdir):
+    """streaming / per-decision / on-demand job scheduling and any extra input delay publish the same Lowres state"""
+    case = cases.get_case(name)
+    got = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, case[1]), planes=False, speculate=mode[0], asyncDepth=mode[1])
+    bad = compare.compare_runs(golden_io.load(name), got, check_planes=False, cutree=case[6].get("cuTree", 1),
+                               weightp=case[6].get("weightp", 1))
+    assert not bad, "\n".join(bad[:10])
+
+
 def test_coverage_of_special_paths(pkg, synth, simdir):
     """the fixtures really exercise weightp and the B-frame zero-MV skip rule"""
     got = cases.run_ours(pkg, synth, cases.get_case("fade8"), lib_path=_sim(simdir, 8), planes=False)

@@ -35,7 +35,7 @@ class LaParam(C.Structure):
                 ("qgSize", C.c_int32), ("vbvBufferSize", C.c_int32), ("vbvMaxBitrate", C.c_int32),
                 ("rateControlMode", C.c_int32), ("poolWorkers", C.c_int32), ("device", C.c_int32),
                 ("extraSlots", C.c_int32), ("speculate", C.c_int32), ("pinHost", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("asyncDepth", C.c_int32), ("pendingMax", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class FrameInfo(C.Structure):
@@ -112,6 +112,7 @@ def load_engine(path=None):
     lib.x265cu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.x265cu_profile_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.x265cu_profile_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int32]
+    lib.x265cu_profile_get_busy.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.x265cu_sync.argtypes = [C.c_void_p]
     lib.x265cu_timer_start.argtypes = [C.c_void_p]
     lib.x265cu_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -128,7 +129,7 @@ def make_param(width, height, depth=8, **kw):
              keyframeMax=250, keyframeMin=0, bOpenGOP=1, bIntraRefresh=0, bEnableWeightedPred=1,
              bEnableWeightedBiPred=0, lookaheadSlices=0, maxNumReferences=3, aqMode=2, aqStrength=1.0,
              cuTree=1, qCompress=0.6, qgSize=32, vbvBufferSize=0, vbvMaxBitrate=0, rateControlMode=2,
-             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0)
+             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0)
     d.update(kw)
     lib_defaults.sourceWidth, lib_defaults.sourceHeight = width, height
     for k, v in d.items():

@@ -1,8 +1,16 @@
 /* engine.cu -- libx265cu.so: the C ABI of include/x265cu.h on one B200.
  *
- * Host side of the engine: owns the frame slots in HBM, turns job batches into kernel launches on
- * one CUDA stream, and copies results back.  All arithmetic lives in la_kernels.cuh.  There is no
- * CPU implementation of any job here: without a usable CUDA device x265cu_create fails.
+ * Host side of the engine: owns the frame slots in HBM, turns job batches into kernel launches and
+ * copies results back.  All arithmetic lives in la_kernels.cuh.  There is no CPU implementation of
+ * any job here: without a usable CUDA device x265cu_create fails.
+ *
+ * Streams: `copyStream` carries the picture uploads; `preStream` the pre-lookahead kernels (K1-K3); `stream`
+ * (main) weightp scores, cuTree and every result copy, so the decisions never queue behind an upload;
+ * `auxStream` the early read of a frame's statistics; and
+ * LA_NUM_LANES worker streams carry the search / cost batches, round-robin, so the wavefront searches of
+ * consecutive batches overlap.  Ordering between them is by events: batch after the pre-lookahead stream at
+ * batch_begin; main-stream work after the pre-lookahead of the slots it reads; cost jobs after the batches whose MV stores they read; main-stream readers after the batch
+ * that writes the store they read; an upload after every batch that touched the slot's previous tenant.
  *
  * HBM layout of one frame slot (one cudaMalloc, 256-byte aligned sections):
  *   srcY/U/V        packed full-res picture (only needed until K1/K2 ran)
@@ -19,6 +27,7 @@
 #include <string.h>
 #include <vector>
 #include <map>
+#include <algorithm>
 #include <new>
 
 using namespace la;
@@ -36,6 +45,24 @@ inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
+enum { LA_NUM_LANES = 16, LA_NUM_BATCHES = 48 };
+
+/* One asynchronous batch of search / cost jobs (x265cu_batch_begin ... x265cu_batch_end).  Everything a batch's
+ * kernels read besides the frame slots is private to it, so batches never wait for each other's buffers. */
+struct Batch
+{
+    long long id;                       /* -1 = never used; the object serves ids id, id + LA_NUM_BATCHES, ... */
+    cudaStream_t stream;                /* lane id % LA_NUM_LANES */
+    cudaEvent_t begun, searchDone, done;
+    bool open;
+    char* h_stage; char* d_stage;       /* pinned host / device copy of the job arrays */
+    size_t stageCap, stageUsed;
+    int* d_sync; size_t syncCap, syncUsed;      /* ticket counter + per-(job, strip) progress of every search call */
+    std::vector<char*> weightScratch;   /* 4 weighted planes each */
+    std::vector<void*> retiredDev, retiredHost; /* outgrown buffers, freed when the object is reused */
+    std::vector<long long> waited;      /* batches this one already waits for */
+};
+
 struct x265cu_ctx
 {
     x265cu_config cfg;
@@ -43,23 +70,37 @@ struct x265cu_ctx
     x265cu_geometry geom;
     int bpp;
     SlotLayout lay;
-    cudaStream_t stream;            /* every kernel and every D2H */
+    cudaStream_t stream;            /* main: weightp scores, cuTree, every D2H */
     cudaStream_t copyStream;        /* picture uploads, so they overlap the kernels of earlier frames */
+    cudaStream_t preStream;         /* pre-lookahead kernels K1-K3 of every uploaded frame */
+    cudaStream_t auxStream;         /* early read of frame statistics, past whatever the other streams have queued */
+    cudaEvent_t mainMark;
+    std::vector<char> slotMainTouched;          /* main-stream work read the slot's current tenant */
+    cudaStream_t lanes[LA_NUM_LANES];
+    Batch batches[LA_NUM_BATCHES];
+    long long nextBatch;
+    Batch* cur;                     /* the open batch or NULL */
     std::vector<char*> slots;
-    std::vector<cudaEvent_t> slotCopied, slotConsumed;   /* per slot: upload done / source planes no longer needed */
+    std::vector<cudaEvent_t> slotCopied, slotConsumed;   /* per slot: upload done / pre-lookahead done */
+    std::vector<std::vector<long long> > slotUsers;      /* batches that read or write the slot's current tenant */
+    std::vector<long long> mvWriter, costWriter;         /* [slot * n_stores + store] -> batch that writes it, -1 */
     unsigned short* d_mvcost;       /* whole table; centre at +mvcost_half */
-    char* d_jobs; size_t jobsCap;   /* device copy of the current job array */
-    int* d_sync; size_t syncCap;    /* ticket counter + per-(job,band) progress */
+    double* d_aqPartial;            /* per-CTA partial sums of the AQ frame means (K2b) */
+    unsigned long long* d_executed; /* [0] search jobs, [1] cost jobs that passed their condition */
     char* d_results; size_t resultsCap;
     char* h_results; size_t hResultsCap;      /* pinned staging for gathers */
-    std::vector<char*> weightScratch;         /* 4 weighted planes each */
+    char* h_stats; size_t hStatsCap;          /* pinned staging of x265cu_frame_stats_get (aux stream) */
+    std::vector<char*> mainScratch;           /* weighted plane for x265cu_weight_cost_batch (main stream) */
     x265cu_counters counters;
+    uint64_t searchEnq, costEnq;    /* jobs enqueued (conditional ones included) */
+    int searchWorkers;              /* worker warps per search job; 0 = default (env X265CU_SEARCH_WORKERS, for tuning) */
     bool profile;
-    double profMs[X265CU_K_COUNT];
+    double profMs[X265CU_K_COUNT], profBusy[X265CU_K_COUNT];
     uint64_t profN[X265CU_K_COUNT];
     struct EvPair { cudaEvent_t a, b; int kind; };
     std::vector<EvPair> evPool;     /* non-blocking per-launch timing: resolved in x265cu_profile_get */
     size_t evUsed;
+    cudaEvent_t profBase;           /* origin of the busy-interval timestamps */
     cudaEvent_t tm0, tm1;           /* x265cu_timer_* */
     char err[256];
 };
@@ -78,8 +119,8 @@ bool cudaOk(x265cu_ctx* c, cudaError_t e, const char* what)
  * Nothing blocks here; the pairs are resolved when the caller asks for the totals. */
 struct Prof
 {
-    x265cu_ctx* c; int k; int idx;
-    Prof(x265cu_ctx* ctx, int kind, int launches) : c(ctx), k(kind), idx(-1)
+    x265cu_ctx* c; int k; int idx; cudaStream_t st;
+    Prof(x265cu_ctx* ctx, int kind, int launches, cudaStream_t stream = 0) : c(ctx), k(kind), idx(-1), st(stream ? stream : ctx->stream)
     {
         c->counters.kernel_launches += launches;
         c->profN[k] += launches;
@@ -93,24 +134,49 @@ struct Prof
             }
             idx = (int)c->evUsed++;
             c->evPool[idx].kind = k;
-            cudaEventRecord(c->evPool[idx].a, c->stream);
+            cudaEventRecord(c->evPool[idx].a, st);
         }
     }
     ~Prof()
     {
-        if (idx >= 0) cudaEventRecord(c->evPool[idx].b, c->stream);
+        if (idx >= 0) cudaEventRecord(c->evPool[idx].b, st);
     }
 };
 
+void syncAll(x265cu_ctx* c)
+{
+    cudaStreamSynchronize(c->copyStream);
+    cudaStreamSynchronize(c->preStream);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->auxStream);
+    for (int i = 0; i < LA_NUM_LANES; i++) cudaStreamSynchronize(c->lanes[i]);
+}
+
+/* per family: sum of the launch durations, and the length of the union of the launch intervals (batches overlap) */
 void resolveProfile(x265cu_ctx* c)
 {
     if (!c->evUsed) return;
-    cudaStreamSynchronize(c->stream);
+    syncAll(c);
+    std::vector<std::pair<float, float> > iv[X265CU_K_COUNT];
     for (size_t i = 0; i < c->evUsed; i++)
     {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->evPool[i].a, c->evPool[i].b) == cudaSuccess)
-            c->profMs[c->evPool[i].kind] += ms;
+        float t0 = 0, t1 = 0;
+        if (cudaEventElapsedTime(&t0, c->profBase, c->evPool[i].a) == cudaSuccess &&
+            cudaEventElapsedTime(&t1, c->profBase, c->evPool[i].b) == cudaSuccess)
+        {
+            c->profMs[c->evPool[i].kind] += t1 - t0;
+            iv[c->evPool[i].kind].push_back(std::make_pair(t0, t1));
+        }
+    }
+    for (int k = 0; k < X265CU_K_COUNT; k++)
+    {
+        std::sort(iv[k].begin(), iv[k].end());
+        float end = -1e30f;
+        for (size_t i = 0; i < iv[k].size(); i++)
+        {
+            if (iv[k][i].first > end) { c->profBusy[k] += iv[k][i].second - iv[k][i].first; end = iv[k][i].second; }
+            else if (iv[k][i].second > end) { c->profBusy[k] += iv[k][i].second - end; end = iv[k][i].second; }
+        }
     }
     c->evUsed = 0;
 }
@@ -139,6 +205,119 @@ int ensureHost(x265cu_ctx* c, size_t need)
 
 bool slotOk(const x265cu_ctx* c, int s) { return s >= 0 && s < (int)c->slots.size(); }
 
+/* ---------------------------------------------------------------- batches */
+
+Batch* batchOf(x265cu_ctx* c, long long id)
+{
+    if (id < 0) return NULL;
+    Batch* b = &c->batches[id % LA_NUM_BATCHES];
+    return b->id == id ? b : NULL;      /* NULL: the object was reused, i.e. batch `id` finished long ago */
+}
+
+int endBatch(x265cu_ctx* c)
+{
+    if (!c->cur) return X265CU_OK;
+    Batch* b = c->cur;
+    c->cur = NULL;
+    b->open = false;
+    CK(cudaEventRecord(b->done, b->stream));
+    return X265CU_OK;
+}
+
+int beginBatch(x265cu_ctx* c)
+{
+    int st = endBatch(c);
+    if (st) return st;
+    Batch* b = &c->batches[c->nextBatch % LA_NUM_BATCHES];
+    if (b->id >= 0) CK(cudaEventSynchronize(b->done));       /* blocks only with LA_NUM_BATCHES batches in flight */
+    for (size_t i = 0; i < b->retiredDev.size(); i++) cudaFree(b->retiredDev[i]);
+    for (size_t i = 0; i < b->retiredHost.size(); i++) cudaFreeHost(b->retiredHost[i]);
+    b->retiredDev.clear(); b->retiredHost.clear(); b->waited.clear();
+    b->id = c->nextBatch++;
+    b->stream = c->lanes[b->id % LA_NUM_LANES];
+    b->stageUsed = 0; b->syncUsed = 0; b->open = true;
+    /* the batch reads planes / intra costs / AQ factors of every frame uploaded so far */
+    CK(cudaEventRecord(b->begun, c->preStream));
+    CK(cudaStreamWaitEvent(b->stream, b->begun, 0));
+    c->cur = b;
+    return X265CU_OK;
+}
+
+/* room for `bytes` of job array in the batch's pinned + device staging */
+int batchStage(x265cu_ctx* c, Batch* b, size_t bytes, char** h, char** d)
+{
+    bytes = alignUp(bytes, 256);
+    if (b->stageUsed + bytes > b->stageCap)
+    {
+        if (b->h_stage) { b->retiredHost.push_back(b->h_stage); b->retiredDev.push_back(b->d_stage); }
+        b->h_stage = NULL; b->d_stage = NULL; b->stageUsed = 0;
+        b->stageCap = alignUp(std::max(bytes * 2, (size_t)64 << 10), 4096);
+        CK(cudaMallocHost((void**)&b->h_stage, b->stageCap));
+        CK(cudaMalloc((void**)&b->d_stage, b->stageCap));
+    }
+    *h = b->h_stage + b->stageUsed; *d = b->d_stage + b->stageUsed;
+    b->stageUsed += bytes;
+    return X265CU_OK;
+}
+
+int batchSync(x265cu_ctx* c, Batch* b, size_t ints, int** d)
+{
+    const size_t bytes = alignUp(ints * sizeof(int), 256);
+    if (b->syncUsed + bytes > b->syncCap)
+    {
+        if (b->d_sync) b->retiredDev.push_back(b->d_sync);
+        b->d_sync = NULL; b->syncUsed = 0;
+        b->syncCap = alignUp(std::max(bytes * 2, (size_t)64 << 10), 4096);
+        CK(cudaMalloc((void**)&b->d_sync, b->syncCap));
+    }
+    *d = (int*)((char*)b->d_sync + b->syncUsed);
+    b->syncUsed += bytes;
+    return X265CU_OK;
+}
+
+/* the batch's stream waits for the searches of batch `id` (another lane) */
+int batchWaitSearches(x265cu_ctx* c, Batch* b, long long id)
+{
+    if (id < 0 || id == b->id) return X265CU_OK;
+    if (std::find(b->waited.begin(), b->waited.end(), id) != b->waited.end()) return X265CU_OK;
+    b->waited.push_back(id);
+    Batch* w = batchOf(c, id);
+    if (w) CK(cudaStreamWaitEvent(b->stream, w->searchDone, 0));
+    return X265CU_OK;
+}
+
+/* the main stream waits for batch `id` (its searches only, or all of it) */
+int mainWaitBatch(x265cu_ctx* c, long long id, bool searchesOnly)
+{
+    Batch* w = batchOf(c, id);
+    if (!w) return X265CU_OK;
+    if (w->open) { int st = endBatch(c); if (st) return st; }
+    CK(cudaStreamWaitEvent(c->stream, searchesOnly ? w->searchDone : w->done, 0));
+    return X265CU_OK;
+}
+int mainWaitMv(x265cu_ctx* c, int slot, int store)
+{
+    return store < 0 ? X265CU_OK : mainWaitBatch(c, c->mvWriter[(size_t)slot * c->geom.n_mv_stores + store], true);
+}
+int mainWaitCost(x265cu_ctx* c, int slot, int store)
+{
+    return store < 2 ? X265CU_OK : mainWaitBatch(c, c->costWriter[(size_t)slot * c->geom.n_cost_stores + store], false);
+}
+
+/* main-stream work is about to read what the pre-lookahead of `slot` produced (planes, intra costs, AQ arrays) */
+int mainWaitPre(x265cu_ctx* c, int slot)
+{
+    c->slotMainTouched[slot] = 1;
+    CK(cudaStreamWaitEvent(c->stream, c->slotConsumed[slot], 0));
+    return X265CU_OK;
+}
+
+void touchSlot(x265cu_ctx* c, int slot, long long id)
+{
+    std::vector<long long>& u = c->slotUsers[slot];
+    if (std::find(u.begin(), u.end(), id) == u.end()) u.push_back(id);
+}
+
 char* mvStorePtr(x265cu_ctx* c, int slot, int store) { return c->slots[slot] + c->lay.mvStores + (size_t)store * c->lay.mvStoreStride; }
 char* costStorePtr(x265cu_ctx* c, int slot, int store) { return c->slots[slot] + c->lay.costStores + (size_t)store * c->lay.costStoreStride; }
 
@@ -165,60 +344,86 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
         c->counters.h2d_bytes += 2ull * g.cW * g.cH * sizeof(P);
     }
     CK(cudaEventRecord(c->slotCopied[slot], c->copyStream));
-    CK(cudaStreamWaitEvent(c->stream, c->slotCopied[slot], 0));
+    CK(cudaStreamWaitEvent(c->preStream, c->slotCopied[slot], 0));
+    /* K1-K3 overwrite the slot: every batch that still reads or writes its previous tenant goes first (the copy
+     * above only touches the staging planes, which batches never read, so it is not held back) */
+    {
+        std::vector<long long>& users = c->slotUsers[slot];
+        for (size_t i = 0; i < users.size(); i++)
+        {
+            Batch* w = batchOf(c, users[i]);
+            if (!w) continue;
+            if (w->open) { int st = endBatch(c); if (st) return st; }
+            CK(cudaStreamWaitEvent(c->preStream, w->done, 0));
+        }
+        users.clear();
+        std::fill(c->mvWriter.begin() + (size_t)slot * c->geom.n_mv_stores, c->mvWriter.begin() + (size_t)(slot + 1) * c->geom.n_mv_stores, -1LL);
+        std::fill(c->costWriter.begin() + (size_t)slot * c->geom.n_cost_stores, c->costWriter.begin() + (size_t)(slot + 1) * c->geom.n_cost_stores, -1LL);
+    }
+    if (c->slotMainTouched[slot])
+    {
+        /* ... and whatever the main stream (cuTree, recalc, mirrors) still reads of it */
+        CK(cudaEventRecord(c->mainMark, c->stream));
+        CK(cudaStreamWaitEvent(c->preStream, c->mainMark, 0));
+        c->slotMainTouched[slot] = 0;
+    }
     /* stats + rowSatds00 start at zero */
-    CK(cudaMemsetAsync(c->slots[slot] + L.rowSatds00, 0, L.stats + sizeof(FrameStatsDev) - L.rowSatds00, c->stream));
+    CK(cudaMemsetAsync(c->slots[slot] + L.rowSatds00, 0, L.stats + sizeof(FrameStatsDev) - L.rowSatds00, c->preStream));
     P* planes = slotPtr<P>(c, slot, L.planes);
     {
-        Prof pr(c, X265CU_K_LOWRES, 1);
+        Prof pr(c, X265CU_K_LOWRES, 1, c->preStream);
         const long long threads = (long long)g.tpr * (g.planeLines >> 3) * 16;
-        lowres_kernel<P><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(g, dY, planes);
+        lowres_kernel<P><<<(unsigned)((threads + 255) / 256), 256, 0, c->preStream>>>(g, dY, planes);
     }
     FrameStatsDev* stats = slotPtr<FrameStatsDev>(c, slot, L.stats);
     int* invQ = slotPtr<int>(c, slot, L.invQ);
     if (c->cfg.need_aq)
     {
-        Prof pr(c, X265CU_K_AQ, 2);
+        const bool twoPass = (c->cfg.aq_mode == 2 || c->cfg.aq_mode == 3) && c->cfg.aq_strength != 0;
+        Prof pr(c, X265CU_K_AQ, 2 + twoPass, c->preStream);
         unsigned* energy = slotPtr<unsigned>(c, slot, L.energy);
-        aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, c->stream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
-        aq_finish_kernel<<<1, 1024, 0, c->stream>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
-                                                    slotPtr<double>(c, slot, L.qpAq), slotPtr<double>(c, slot, L.qpCuTree), invQ, stats);
+        double* qpCuTree = slotPtr<double>(c, slot, L.qpCuTree);
+        aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, c->preStream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
+        if (twoPass)
+            aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, c->preStream>>>(g, energy, qpCuTree, c->d_aqPartial);
+        aq_finish_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, c->preStream>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
+                                                                      c->d_aqPartial, slotPtr<double>(c, slot, L.qpAq), qpCuTree, invQ, stats);
     }
     {
-        Prof pr(c, X265CU_K_INTRA, 1);
-        intra_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, planes, c->cfg.need_aq ? invQ : NULL,
+        Prof pr(c, X265CU_K_INTRA, 1, c->preStream);
+        intra_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->preStream>>>(g, planes, c->cfg.need_aq ? invQ : NULL,
                                                                   slotPtr<int>(c, slot, L.intraCost), slotPtr<unsigned char>(c, slot, L.intraMode),
                                                                   slotPtr<unsigned short>(c, slot, L.lowresCosts00),
                                                                   slotPtr<int>(c, slot, L.rowSatds00), stats);
     }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->slotConsumed[slot], c->stream));
+    CK(cudaEventRecord(c->slotConsumed[slot], c->preStream));
     return X265CU_OK;
 }
 
 template <typename P>
-int weightPlanes(x265cu_ctx* c, const P* src, P* dst, int nPlanes, int scale, int denom, int offsetIn)
+int weightPlanes(x265cu_ctx* c, cudaStream_t stream, const P* src, P* dst, int nPlanes, int scale, int denom, int offsetIn)
 {
     const int correction = 14 - c->g.depth;
     const int offset = offsetIn << (c->g.depth - 8);
     const int round = (denom ? 1 << (denom - 1) : 0) << correction;
     const int shift = denom + correction;
     const long long n = c->g.planeSize * nPlanes;
-    Prof pr(c, X265CU_K_WEIGHT, 1);
-    weight_planes_kernel<P><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(src, dst, n, scale, round, shift, offset, correction,
+    Prof pr(c, X265CU_K_WEIGHT, 1, stream);
+    weight_planes_kernel<P><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n, scale, round, shift, offset, correction,
                                                                                 (1 << c->g.depth) - 1);
     CK(cudaGetLastError());
     return X265CU_OK;
 }
 
-int ensureScratch(x265cu_ctx* c, size_t count)
+int ensureScratch(x265cu_ctx* c, std::vector<char*>& scratch, cudaStream_t stream, size_t count)
 {
-    while (c->weightScratch.size() < count)
+    while (scratch.size() < count)
     {
         char* p = NULL;
         CK(cudaMalloc((void**)&p, (size_t)(4 * c->g.planeSize) * c->bpp + 256));
-        CK(cudaMemsetAsync(p, 0, (size_t)(4 * c->g.planeSize) * c->bpp + 256, c->stream));
-        c->weightScratch.push_back(p);
+        CK(cudaMemsetAsync(p, 0, (size_t)(4 * c->g.planeSize) * c->bpp + 256, stream));
+        scratch.push_back(p);
     }
     return X265CU_OK;
 }
@@ -228,13 +433,20 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
 {
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
-    std::vector<SearchJobDev<P> > dev(n);
-    /* weighted references: one scratch set per distinct (ref, weight) in this batch */
+    const bool implicit = !c->cur;
+    if (implicit) { int st = beginBatch(c); if (st) return st; }
+    Batch* b = c->cur;
+    char *hst, *dst;
+    int st = batchStage(c, b, n * sizeof(SearchJobDev<P>), &hst, &dst);
+    if (st) return st;
+    SearchJobDev<P>* dev = (SearchJobDev<P>*)hst;
+    /* weighted references: one scratch set per distinct (ref, weight) in this call */
     std::map<std::vector<int>, int> wmap;
     for (int i = 0; i < n; i++)
     {
         const x265cu_search_job& j = jobs[i];
-        if (!slotOk(c, j.fenc_slot) || !slotOk(c, j.ref_slot) || j.store < 0 || j.store >= c->geom.n_mv_stores)
+        if (!slotOk(c, j.fenc_slot) || !slotOk(c, j.ref_slot) || j.store < 0 || j.store >= c->geom.n_mv_stores ||
+            j.cond_store >= c->geom.n_mv_stores)
         { snprintf(c->err, sizeof(c->err), "search job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
         const P* refBuf = slotPtr<P>(c, j.ref_slot, L.planes);
         if (j.weighted)
@@ -247,39 +459,51 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
             {
                 idx = (int)wmap.size();
                 wmap[key] = idx;
-                int st = ensureScratch(c, idx + 1);
+                st = ensureScratch(c, b->weightScratch, b->stream, idx + 1);
                 if (st) return st;
-                st = weightPlanes<P>(c, refBuf, (P*)c->weightScratch[idx], 4, j.w_scale, j.w_denom, j.w_offset);
+                st = weightPlanes<P>(c, b->stream, refBuf, (P*)b->weightScratch[idx], 4, j.w_scale, j.w_denom, j.w_offset);
                 if (st) return st;
             }
             else
                 idx = it->second;
-            refBuf = (const P*)c->weightScratch[idx];
+            refBuf = (const P*)b->weightScratch[idx];
         }
         dev[i].fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes);
         dev[i].ref0 = refBuf;
-        char* st = mvStorePtr(c, j.fenc_slot, j.store);
-        dev[i].mvOut = (int*)st;
-        dev[i].costOut = (int*)st + g.ncu;
-        dev[i].flagOut = (int*)st + 2 * g.ncu;
+        char* ms = mvStorePtr(c, j.fenc_slot, j.store);
+        dev[i].mvOut = (int*)ms;
+        dev[i].costOut = (int*)ms + g.ncu;
+        dev[i].flagOut = (int*)ms + 2 * g.ncu;
+        dev[i].cond = NULL;
+        if (j.cond_store >= 0)
+        {
+            dev[i].cond = (const int*)mvStorePtr(c, j.fenc_slot, j.cond_store) + 2 * g.ncu;
+            st = batchWaitSearches(c, b, c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.cond_store]);
+            if (st) return st;
+        }
         dev[i].bidir = j.bidir_ctx;
         dev[i].pad = 0;
+        touchSlot(c, j.fenc_slot, b->id); touchSlot(c, j.ref_slot, b->id);
+        c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.store] = b->id;
     }
-    const int nbands = (g.bh + LA_BAND_ROWS - 1) / LA_BAND_ROWS;
-    c->counters.search_jobs += n;
-    int st = ensureDev(c, &c->d_jobs, &c->jobsCap, n * sizeof(SearchJobDev<P>));
+    const int nstrips = (g.bh + LA_STRIP_ROWS - 1) / LA_STRIP_ROWS;      /* strips of 4 rows, one warp each */
+    c->searchEnq += n;
+    int* dsync;
+    st = batchSync(c, b, (size_t)(1 + n * nstrips), &dsync);
     if (st) return st;
-    st = ensureDev(c, (char**)&c->d_sync, &c->syncCap, (size_t)(1 + n * nbands) * sizeof(int));
-    if (st) return st;
-    CK(cudaMemcpyAsync(c->d_jobs, &dev[0], n * sizeof(SearchJobDev<P>), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->d_sync, 0, (size_t)(1 + n * nbands) * sizeof(int), c->stream));
+    CK(cudaMemcpyAsync(dst, hst, n * sizeof(SearchJobDev<P>), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemsetAsync(dsync, 0, (size_t)(1 + n * nstrips) * sizeof(int), b->stream));
     {
-        Prof pr(c, X265CU_K_SEARCH, 1);
-        const size_t smem = (size_t)LA_BAND_ROWS * g.bw * sizeof(int);
-        search_kernel<P><<<n * nbands, LA_BAND_ROWS * 8, smem, c->stream>>>(g, (const SearchJobDev<P>*)c->d_jobs, nbands, n,
-                                                                            c->d_mvcost + c->cfg.mvcost_half, c->d_sync, c->d_sync + 1);
+        Prof pr(c, X265CU_K_SEARCH, 1, b->stream);
+        /* workers per job: a job's strips start 8 steps apart and run ~bw steps, so beyond ~bw/8 of them some only
+         * sit resident waiting for their turn; that matters when the launch is too small to oversubscribe the GPU */
+        const int workers = std::max(1, std::min(nstrips, c->searchWorkers > 0 ? c->searchWorkers : (nstrips + 1) / 2));
+        search_kernel<P><<<n * workers, 32, 0, b->stream>>>(g, (const SearchJobDev<P>*)dst, nstrips, n,
+                                                           c->d_mvcost + c->cfg.mvcost_half, dsync, dsync + 1, c->d_executed);
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(b->searchDone, b->stream));
+    if (implicit) return endBatch(c);
     return X265CU_OK;
 }
 
@@ -288,17 +512,24 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
 {
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
+    const bool implicit = !c->cur;
+    if (implicit) { int st = beginBatch(c); if (st) return st; }
+    Batch* b = c->cur;
+    char *hst, *dst;
+    int st = batchStage(c, b, n * sizeof(CostJobDev<P>), &hst, &dst);
+    if (st) return st;
     /* P estimates (one thread per block) first, then B estimates (8 lanes per block): two launches with the
      * grid each needs */
-    std::vector<CostJobDev<P> > dev(n);
+    CostJobDev<P>* dev = (CostJobDev<P>*)hst;
     int nP = 0;
     for (int i = 0; i < n; i++) nP += jobs[i].l1_store < 0;
     int iP = 0, iB = nP;
+    const int nmv = c->geom.n_mv_stores;
     for (int i = 0; i < n; i++)
     {
         const x265cu_cost_job& j = jobs[i];
         if (!slotOk(c, j.b_slot) || !slotOk(c, j.p0_slot) || !slotOk(c, j.p1_slot) || j.out < 2 || j.out >= c->geom.n_cost_stores ||
-            j.l0_store < 0 || j.l0_store >= c->geom.n_mv_stores || j.l1_store >= c->geom.n_mv_stores)
+            j.l0_store < 0 || j.l0_store >= nmv || j.l1_store >= nmv || j.cond_store >= nmv)
         { snprintf(c->err, sizeof(c->err), "cost job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
         CostJobDev<P>& d = dev[j.l1_store < 0 ? iP++ : iB++];
         d.fenc0 = slotPtr<P>(c, j.b_slot, L.planes);
@@ -306,39 +537,51 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         d.ref1 = j.l1_store >= 0 ? slotPtr<P>(c, j.p1_slot, L.planes) : NULL;
         char* m0 = mvStorePtr(c, j.b_slot, j.l0_store);
         d.mv0 = (const int*)m0; d.cost0 = (const int*)m0 + g.ncu;
+        st = batchWaitSearches(c, b, c->mvWriter[(size_t)j.b_slot * nmv + j.l0_store]);
+        if (st) return st;
         if (j.l1_store >= 0)
         {
             char* m1 = mvStorePtr(c, j.b_slot, j.l1_store);
             d.mv1 = (const int*)m1; d.cost1 = (const int*)m1 + g.ncu;
+            st = batchWaitSearches(c, b, c->mvWriter[(size_t)j.b_slot * nmv + j.l1_store]);
+            if (st) return st;
         }
         else { d.mv1 = NULL; d.cost1 = NULL; }
+        d.cond = NULL;
+        if (j.cond_store >= 0)
+        {
+            d.cond = (const int*)mvStorePtr(c, j.b_slot, j.cond_store) + 2 * g.ncu;
+            st = batchWaitSearches(c, b, c->mvWriter[(size_t)j.b_slot * nmv + j.cond_store]);
+            if (st) return st;
+        }
         d.intraCost = slotPtr<int>(c, j.b_slot, L.intraCost);
         d.invQ = c->cfg.need_aq ? slotPtr<int>(c, j.b_slot, L.invQ) : NULL;
         char* cs = costStorePtr(c, j.b_slot, j.out);
         d.lowresCosts = (unsigned short*)cs;
         d.rowSatds = (int*)(cs + L.costRowOff);
         d.result = (CostResultDev*)(cs + L.costResOff);
+        touchSlot(c, j.b_slot, b->id); touchSlot(c, j.p0_slot, b->id); touchSlot(c, j.p1_slot, b->id);
+        c->costWriter[(size_t)j.b_slot * c->geom.n_cost_stores + j.out] = b->id;
     }
-    c->counters.cost_jobs += n;
-    int st = ensureDev(c, &c->d_jobs, &c->jobsCap, n * sizeof(CostJobDev<P>));
-    if (st) return st;
-    CK(cudaMemcpyAsync(c->d_jobs, &dev[0], n * sizeof(CostJobDev<P>), cudaMemcpyHostToDevice, c->stream));
+    c->costEnq += n;
+    CK(cudaMemcpyAsync(dst, hst, n * sizeof(CostJobDev<P>), cudaMemcpyHostToDevice, b->stream));
     {
-        Prof pr(c, X265CU_K_COST, 1 + (nP > 0) + (n > nP));
+        Prof pr(c, X265CU_K_COST, 1 + (nP > 0) + (n > nP), b->stream);
         for (int base = 0; base < n; base += 65535)
-            cost_clear_kernel<P><<<(n - base) < 65535 ? (n - base) : 65535, 256, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs + base);
+            cost_clear_kernel<P><<<(n - base) < 65535 ? (n - base) : 65535, 256, 0, b->stream>>>(g, (const CostJobDev<P>*)dst + base, c->d_executed + 1);
         for (int base = 0; base < nP; base += 65535)
         {
             dim3 gg((g.ncu + 127) / 128, (unsigned)((nP - base) < 65535 ? (nP - base) : 65535));
-            cost_kernel<P><<<gg, 128, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs + base);
+            cost_kernel<P><<<gg, 128, 0, b->stream>>>(g, (const CostJobDev<P>*)dst + base);
         }
         for (int base = nP; base < n; base += 65535)
         {
             dim3 gg((g.ncu + 15) / 16, (unsigned)((n - base) < 65535 ? (n - base) : 65535));
-            cost_kernel<P><<<gg, 128, 0, c->stream>>>(g, (const CostJobDev<P>*)c->d_jobs + base);
+            cost_kernel<P><<<gg, 128, 0, b->stream>>>(g, (const CostJobDev<P>*)dst + base);
         }
     }
     CK(cudaGetLastError());
+    if (implicit) return endBatch(c);
     return X265CU_OK;
 }
 
@@ -352,18 +595,21 @@ int weightCostT(x265cu_ctx* c, const x265cu_wcost_job* jobs, int n, uint32_t* co
     st = ensureHost(c, n * sizeof(unsigned));
     if (st) return st;
     CK(cudaMemsetAsync(c->d_results, 0, n * sizeof(unsigned), c->stream));
-    st = ensureScratch(c, 1);
+    st = ensureScratch(c, c->mainScratch, c->stream, 1);
     if (st) return st;
     for (int i = 0; i < n; i++)
     {
         const x265cu_wcost_job& j = jobs[i];
         if (!slotOk(c, j.fenc_slot) || !slotOk(c, j.ref_slot)) return X265CU_ERR_BAD_ARG;
+        st = mainWaitPre(c, j.fenc_slot);
+        if (!st) st = mainWaitPre(c, j.ref_slot);
+        if (st) return st;
         const P* ref = slotPtr<P>(c, j.ref_slot, L.planes);
         if (j.weighted)
         {
-            st = weightPlanes<P>(c, ref, (P*)c->weightScratch[0], 1, j.w_scale, j.w_denom, j.w_offset);
+            st = weightPlanes<P>(c, c->stream, ref, (P*)c->mainScratch[0], 1, j.w_scale, j.w_denom, j.w_offset);
             if (st) return st;
-            ref = (const P*)c->weightScratch[0];
+            ref = (const P*)c->mainScratch[0];
         }
         Prof pr(c, X265CU_K_WEIGHT, 1);
         weight_cost_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->stream>>>(g, slotPtr<P>(c, j.fenc_slot, L.planes),
@@ -458,9 +704,20 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     if (cudaSetDevice(cfg->device) != cudaSuccess) return X265CU_ERR_NO_DEVICE;
     x265cu_ctx* c = new (std::nothrow) x265cu_ctx();
     if (!c) return X265CU_ERR_NO_MEMORY;
-    c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_jobs = NULL; c->jobsCap = 0; c->d_sync = NULL; c->syncCap = 0;
-    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->profile = false; c->evUsed = 0;
+    c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_aqPartial = NULL; c->d_executed = NULL;
+    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->h_stats = NULL; c->hStatsCap = 0;
+    c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
+    c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
+    c->stream = c->copyStream = c->auxStream = c->preStream = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
+    for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
+    for (int i = 0; i < LA_NUM_BATCHES; i++)
+    {
+        Batch& b = c->batches[i];
+        b.id = -1; b.stream = NULL; b.begun = b.searchDone = b.done = NULL; b.open = false;
+        b.h_stage = b.d_stage = NULL; b.stageCap = b.stageUsed = 0; b.d_sync = NULL; b.syncCap = b.syncUsed = 0;
+    }
     memset(&c->counters, 0, sizeof(c->counters)); memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN));
+    memset(c->profBusy, 0, sizeof(c->profBusy));
     c->bpp = cfg->depth > 8 ? 2 : 1;
 
     /* geometry: Lowres::create (lowres.cpp:72-97) */
@@ -509,12 +766,31 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     L.total = o;
 
     int rc = X265CU_OK;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
+    /* The worker lanes run at the lowest priority: their search warps live for milliseconds and would otherwise
+     * leave the short pre-lookahead / cuTree kernels (which the host waits for) queueing for a free SM slot */
+    int prLeast = 0, prGreatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return X265CU_ERR_CUDA; }
-    cudaEventCreate(&c->tm0); cudaEventCreate(&c->tm1);
+    if (cudaStreamCreateWithPriority(&c->auxStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    if (cudaStreamCreateWithPriority(&c->preStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&c->mainMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    for (int i = 0; !rc && i < LA_NUM_LANES; i++)
+        if (cudaStreamCreateWithPriority(&c->lanes[i], cudaStreamNonBlocking, prLeast) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    for (int i = 0; !rc && i < LA_NUM_BATCHES; i++)
+    {
+        Batch& b = c->batches[i];
+        if (cudaEventCreateWithFlags(&b.begun, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b.searchDone, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    }
+    cudaEventCreate(&c->tm0); cudaEventCreate(&c->tm1); cudaEventCreate(&c->profBase);
+    if (!rc && cudaMalloc((void**)&c->d_executed, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+    if (!rc && cudaMemset(c->d_executed, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = X265CU_ERR_CUDA;
     const size_t tabBytes = (2 * (size_t)cfg->mvcost_half + 1) * sizeof(unsigned short);
     if (cudaMalloc((void**)&c->d_mvcost, tabBytes) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     if (!rc && cudaMemcpy(c->d_mvcost, cfg->mvcost, tabBytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    if (!rc && cudaMalloc((void**)&c->d_aqPartial, 2 * LA_AQ_CTAS * sizeof(double)) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     for (int i = 0; !rc && i < cfg->max_slots; i++)
     {
         char* p = NULL;
@@ -523,13 +799,16 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
         cudaEvent_t e0, e1;
         cudaEventCreateWithFlags(&e0, cudaEventDisableTiming); cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
         c->slotCopied.push_back(e0); c->slotConsumed.push_back(e1);
+        c->slotUsers.push_back(std::vector<long long>());
+        c->slotMainTouched.push_back(0);
         /* planes must start zeroed: columns past the right margin are never written (K1) */
         if (cudaMemsetAsync(p, 0, L.total, c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
     }
     if (!rc)
     {
-        cudaFuncSetAttribute(search_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(search_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        c->mvWriter.assign(c->slots.size() * (size_t)G.n_mv_stores, -1LL);
+        c->costWriter.assign(c->slots.size() * (size_t)G.n_cost_stores, -1LL);
+        cudaEventRecord(c->profBase, c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
     }
     if (rc) { x265cu_destroy(c); return rc; }
@@ -541,17 +820,35 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 void x265cu_destroy(x265cu_ctx* c)
 {
     if (!c) return;
-    cudaStreamSynchronize(c->copyStream);
-    cudaStreamSynchronize(c->stream);
+    syncAll(c);
     for (size_t i = 0; i < c->slots.size(); i++) cudaFree(c->slots[i]);
     for (size_t i = 0; i < c->slotCopied.size(); i++) { cudaEventDestroy(c->slotCopied[i]); cudaEventDestroy(c->slotConsumed[i]); }
     for (size_t i = 0; i < c->evPool.size(); i++) { cudaEventDestroy(c->evPool[i].a); cudaEventDestroy(c->evPool[i].b); }
-    for (size_t i = 0; i < c->weightScratch.size(); i++) cudaFree(c->weightScratch[i]);
-    cudaFree(c->d_mvcost); cudaFree(c->d_jobs); cudaFree(c->d_sync); cudaFree(c->d_results);
+    for (size_t i = 0; i < c->mainScratch.size(); i++) cudaFree(c->mainScratch[i]);
+    for (int i = 0; i < LA_NUM_BATCHES; i++)
+    {
+        Batch& b = c->batches[i];
+        for (size_t k = 0; k < b.weightScratch.size(); k++) cudaFree(b.weightScratch[k]);
+        for (size_t k = 0; k < b.retiredDev.size(); k++) cudaFree(b.retiredDev[k]);
+        for (size_t k = 0; k < b.retiredHost.size(); k++) cudaFreeHost(b.retiredHost[k]);
+        cudaFree(b.d_stage); cudaFree(b.d_sync);
+        if (b.h_stage) cudaFreeHost(b.h_stage);
+        if (b.begun) cudaEventDestroy(b.begun);
+        if (b.searchDone) cudaEventDestroy(b.searchDone);
+        if (b.done) cudaEventDestroy(b.done);
+    }
+    cudaFree(c->d_mvcost); cudaFree(c->d_aqPartial); cudaFree(c->d_executed); cudaFree(c->d_results);
     if (c->h_results) cudaFreeHost(c->h_results);
-    cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1);
-    cudaStreamDestroy(c->copyStream);
-    cudaStreamDestroy(c->stream);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->tm0) cudaEventDestroy(c->tm0);
+    if (c->tm1) cudaEventDestroy(c->tm1);
+    if (c->profBase) cudaEventDestroy(c->profBase);
+    for (int i = 0; i < LA_NUM_LANES; i++) if (c->lanes[i]) cudaStreamDestroy(c->lanes[i]);
+    if (c->auxStream) cudaStreamDestroy(c->auxStream);
+    if (c->preStream) cudaStreamDestroy(c->preStream);
+    if (c->mainMark) cudaEventDestroy(c->mainMark);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -568,13 +865,46 @@ int x265cu_unpin_host(x265cu_ctx* c, void* ptr)
     return X265CU_OK;
 }
 
-int x265cu_sync(x265cu_ctx* c) { CK(cudaStreamSynchronize(c->copyStream)); CK(cudaStreamSynchronize(c->stream)); return X265CU_OK; }
+/* the main stream waits for every batch in flight (so an event recorded on it afterwards covers all the work) */
+static int mainJoinBatches(x265cu_ctx* c)
+{
+    int st = endBatch(c);
+    if (st) return st;
+    for (int i = 0; i < LA_NUM_BATCHES; i++)
+        if (c->batches[i].id >= 0) CK(cudaStreamWaitEvent(c->stream, c->batches[i].done, 0));
+    return X265CU_OK;
+}
 
-/* device-side stopwatch on the engine's compute stream (bench.py times its steps with it) */
+int x265cu_sync(x265cu_ctx* c)
+{
+    int st = endBatch(c);
+    if (st) return st;
+    CK(cudaStreamSynchronize(c->copyStream)); CK(cudaStreamSynchronize(c->preStream)); CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->auxStream));
+    for (int i = 0; i < LA_NUM_LANES; i++) CK(cudaStreamSynchronize(c->lanes[i]));
+    return X265CU_OK;
+}
+
+int x265cu_batch_begin(x265cu_ctx* c, int64_t* batch_id)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    int st = beginBatch(c);
+    if (!st && batch_id) *batch_id = c->cur->id;
+    return st;
+}
+
+int x265cu_batch_end(x265cu_ctx* c) { return c ? endBatch(c) : X265CU_ERR_BAD_ARG; }
+
+/* device-side stopwatch (bench.py times its steps with it): start on the main stream; stop after everything
+ * enqueued on any stream of the context */
 int x265cu_timer_start(x265cu_ctx* c) { CK(cudaEventRecord(c->tm0, c->stream)); return X265CU_OK; }
 int x265cu_timer_stop(x265cu_ctx* c, double* ms)
 {
+    int st = mainJoinBatches(c);
+    if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream));
+    CK(cudaStreamSynchronize(c->preStream));
+    CK(cudaStreamSynchronize(c->auxStream));
     CK(cudaEventRecord(c->tm1, c->stream));
     CK(cudaEventSynchronize(c->tm1));
     float f = 0;
@@ -583,15 +913,32 @@ int x265cu_timer_stop(x265cu_ctx* c, double* ms)
     return X265CU_OK;
 }
 
-int x265cu_get_counters(const x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return X265CU_OK; }
+/* synchronises: the job counts are those that passed their condition on the device */
+int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o)
+{
+    int st = x265cu_sync(c);
+    if (st) return st;
+    unsigned long long ex[2] = { 0, 0 };
+    CK(cudaMemcpy(ex, c->d_executed, sizeof(ex), cudaMemcpyDeviceToHost));
+    c->counters.search_jobs = ex[0]; c->counters.cost_jobs = ex[1];
+    *o = c->counters;
+    return X265CU_OK;
+}
 
 int x265cu_profile_enable(x265cu_ctx* c, int32_t on) { resolveProfile(c); c->profile = on != 0; return X265CU_OK; }
+
+int x265cu_profile_get_busy(x265cu_ctx* c, double busy[X265CU_K_COUNT])
+{
+    resolveProfile(c);
+    for (int i = 0; i < X265CU_K_COUNT; i++) busy[i] = c->profBusy[i];
+    return X265CU_OK;
+}
 
 int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset)
 {
     resolveProfile(c);
     for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = c->profMs[i]; launches[i] = c->profN[i]; }
-    if (reset) { memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN)); }
+    if (reset) { memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN)); memset(c->profBusy, 0, sizeof(c->profBusy)); }
     return X265CU_OK;
 }
 
@@ -601,21 +948,39 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     return DISPATCH(uploadT, c, slot, y, u, v, sy, sc);
 }
 
+int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
+{
+    if (!c || !slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
+    const cudaError_t e = cudaEventQuery(c->slotConsumed[slot]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    cudaOk(c, e, "cudaEventQuery");
+    return X265CU_ERR_CUDA;
+}
+
 int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)
 {
     if (n <= 0) return X265CU_OK;
-    int st = ensureHost(c, n * sizeof(FrameStatsDev));
-    if (st) return st;
+    const size_t need = n * sizeof(FrameStatsDev);
+    if (c->hStatsCap < need)
+    {
+        if (c->h_stats) { cudaStreamSynchronize(c->auxStream); cudaFreeHost(c->h_stats); c->h_stats = NULL; c->hStatsCap = 0; }
+        CK(cudaMallocHost((void**)&c->h_stats, alignUp(need * 2, 4096)));
+        c->hStatsCap = alignUp(need * 2, 4096);
+    }
+    /* on the aux stream, after each frame's own pre-lookahead: the read does not queue behind the uploads and
+     * pre-lookaheads of newer frames on the main stream */
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i])) return X265CU_ERR_BAD_ARG;
-        CK(cudaMemcpyAsync(c->h_results + i * sizeof(FrameStatsDev), c->slots[slots[i]] + c->lay.stats, sizeof(FrameStatsDev),
-                           cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamWaitEvent(c->auxStream, c->slotConsumed[slots[i]], 0));
+        CK(cudaMemcpyAsync(c->h_stats + i * sizeof(FrameStatsDev), c->slots[slots[i]] + c->lay.stats, sizeof(FrameStatsDev),
+                           cudaMemcpyDeviceToHost, c->auxStream));
     }
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->auxStream));
     for (int i = 0; i < n; i++)
     {
-        const FrameStatsDev* s = (const FrameStatsDev*)(c->h_results + i * sizeof(FrameStatsDev));
+        const FrameStatsDev* s = (const FrameStatsDev*)(c->h_stats + i * sizeof(FrameStatsDev));
         out[i].cost_est = s->costEst; out[i].cost_est_aq = s->costEstAq;
         for (int k = 0; k < 3; k++) { out[i].wp_ssd[k] = s->wp_ssd[k]; out[i].wp_sum[k] = s->wp_sum[k]; }
     }
@@ -638,6 +1003,8 @@ int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i]) || stores[i] < 0 || stores[i] >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
+        st = mainWaitMv(c, slots[i], stores[i]);
+        if (st) return st;
         CK(cudaMemcpyAsync(c->h_results + i * sizeof(int), mvStorePtr(c, slots[i], stores[i]) + (size_t)c->g.ncu * 8, sizeof(int),
                            cudaMemcpyDeviceToHost, c->stream));
     }
@@ -662,6 +1029,8 @@ int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i]) || outs[i] < 0 || outs[i] >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
+        st = mainWaitCost(c, slots[i], outs[i]);
+        if (st) return st;
         CK(cudaMemcpyAsync(c->h_results + i * sizeof(CostResultDev), costStorePtr(c, slots[i], outs[i]) + c->lay.costResOff,
                            sizeof(CostResultDev), cudaMemcpyDeviceToHost, c->stream));
     }
@@ -685,6 +1054,8 @@ int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_
 int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
 {
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
+    int st = mainWaitPre(c, slot);
+    if (st) return st;
     CK(cudaMemsetAsync(c->slots[slot] + c->lay.propagate, 0, (size_t)c->g.ncu * 4, c->stream));
     return X265CU_OK;
 }
@@ -696,6 +1067,13 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
         l0 < 0 || l0 >= c->geom.n_mv_stores || l1 >= c->geom.n_mv_stores)
         return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
+    int st = mainWaitCost(c, bs, cost_store);
+    if (!st) st = mainWaitMv(c, bs, l0);
+    if (!st) st = mainWaitMv(c, bs, l1);
+    if (!st) st = mainWaitPre(c, bs);
+    if (!st) st = mainWaitPre(c, p0s);
+    if (!st) st = mainWaitPre(c, p1s);
+    if (st) return st;
     const int* mv0 = (const int*)mvStorePtr(c, bs, l0);
     const int* mv1 = l1 >= 0 ? (const int*)mvStorePtr(c, bs, l1) : mv0;
     Prof pr(c, X265CU_K_CUTREE, 1);
@@ -711,6 +1089,8 @@ int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double w
 {
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
+    int st = mainWaitPre(c, slot);
+    if (st) return st;
     Prof pr(c, X265CU_K_CUTREE, 1);
     cutree_finish_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
         c->g, slotPtr<int>(c, slot, L.intraCost), slotPtr<int>(c, slot, L.invQ), slotPtr<int>(c, slot, L.propagate),
@@ -727,7 +1107,10 @@ int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t 
     const unsigned short* costs; int* rs;
     if (cost_store == 0) { costs = slotPtr<unsigned short>(c, slot, L.lowresCosts00); rs = slotPtr<int>(c, slot, L.rowSatds00); }
     else { char* cs = costStorePtr(c, slot, cost_store); costs = (const unsigned short*)cs; rs = (int*)(cs + L.costRowOff); }
-    int st = ensureDev(c, &c->d_results, &c->resultsCap, 8);
+    int st = mainWaitCost(c, slot, cost_store);
+    if (!st) st = mainWaitPre(c, slot);
+    if (st) return st;
+    st = ensureDev(c, &c->d_results, &c->resultsCap, 8);
     if (st) return st;
     st = ensureHost(c, 8 + (size_t)g.bh * 4);
     if (st) return st;
@@ -772,7 +1155,7 @@ int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
     if (!slotOk(c, slot) || !o) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
     const Geom& g = c->g;
-    int st = X265CU_OK;
+    int st = mainWaitPre(c, slot);
     if (o->intra_cost && !st) st = d2h(c, o->intra_cost, c->slots[slot] + L.intraCost, (size_t)g.ncu * 4);
     if (o->intra_mode && !st) st = d2h(c, o->intra_mode, c->slots[slot] + L.intraMode, (size_t)g.ncu);
     if (o->qp_aq_offset && !st) st = d2h(c, o->qp_aq_offset, c->slots[slot] + L.qpAq, (size_t)g.ncu * 8);
@@ -820,7 +1203,8 @@ int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, in
     if (!slotOk(c, slot) || store < 0 || store >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
     const Geom& g = c->g;
     const int* st0 = (const int*)mvStorePtr(c, slot, store);
-    int st = X265CU_OK;
+    int st = mainWaitMv(c, slot, store);
+    if (st) return st;
     if (mv)
     {
         st = ensureDev(c, &c->d_results, &c->resultsCap, (size_t)g.ncu * 8);
@@ -839,7 +1223,8 @@ int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* cos
 {
     if (!slotOk(c, slot) || store < 2 || store >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
     char* cs = costStorePtr(c, slot, store);
-    int st = X265CU_OK;
+    int st = mainWaitCost(c, slot, store);
+    if (st) return st;
     if (costs) st = d2h(c, costs, cs, (size_t)c->g.ncu * 2);
     if (rows && !st) st = d2h(c, rows, cs + c->lay.costRowOff, (size_t)c->g.bh * 4);
     if (st) return st;
@@ -859,7 +1244,9 @@ int x265cu_debug_mc_metrics(x265cu_ctx* c, int32_t fenc_slot, int32_t ref_slot, 
                             int32_t* sad, int32_t* satd)
 {
     if (!c || !slotOk(c, fenc_slot) || !slotOk(c, ref_slot) || n <= 0) return X265CU_ERR_BAD_ARG;
-    CK(cudaStreamSynchronize(c->copyStream));
+    int st = mainWaitPre(c, fenc_slot);
+    if (!st) st = mainWaitPre(c, ref_slot);
+    if (st) return st;
     return DISPATCH(mcMetricsT, c, fenc_slot, ref_slot, cu_idx, mvs, n, sad, satd);
 }
 

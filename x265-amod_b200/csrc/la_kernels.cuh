@@ -121,6 +121,31 @@ __device__ __forceinline__ void warpVar(const P* __restrict__ p, int stride, int
     }
 }
 
+/* 8 consecutive samples with one vector load (the caller guarantees the alignment), summed and square-summed */
+__device__ __forceinline__ void sumSqr8(const uint8_t* p, unsigned& sum, unsigned& sqr)
+{
+    const uint2 v = __ldg((const uint2*)p);
+    const unsigned w[2] = { v.x, v.y };
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+    {
+        sum += __vsadu4(w[i], 0);
+        sqr = __dp4a(w[i], w[i], sqr);
+    }
+}
+__device__ __forceinline__ void sumSqr8(const uint16_t* p, unsigned& sum, unsigned& sqr)
+{
+    const uint4 v = __ldg((const uint4*)p);
+    const unsigned w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const unsigned lo = w[i] & 0xffffu, hi = w[i] >> 16;
+        sum += lo + hi;
+        sqr += lo * lo + hi * hi;
+    }
+}
+
 template <typename P>
 __global__ void __launch_bounds__(256) aq_energy_kernel(Geom g, const P* __restrict__ y, const P* __restrict__ u,
                                                         const P* __restrict__ v, unsigned* __restrict__ energy,
@@ -131,21 +156,61 @@ __global__ void __launch_bounds__(256) aq_energy_kernel(Geom g, const P* __restr
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blk = blockIdx.x * 8 + warp;
+    /* rows of the packed picture are 16-byte aligned (8-byte for 8-bit chroma rows): whole-row vector loads */
+    const bool vecOk = ((g.picW * (int)sizeof(P)) & 15) == 0 && ((g.cW * (int)sizeof(P)) & (8 * (int)sizeof(P) - 1)) == 0;
     if (blk < g.ncu)
     {
         const int bx = (blk % g.bw) * 16, by = (blk / g.bw) * 16;
         unsigned sum, sqr, e;
-        warpVar(y, g.picW, g.picW, g.picH, bx, by, 16, sum, sqr);
-        e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
-        if (lane == 0) { atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr); }
-        if (u)
+        if (vecOk && bx + 16 <= g.picW && by + 16 <= g.picH)
         {
-            warpVar(u, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
-            e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
-            if (lane == 0) { atomicAdd(&s_acc[1], (unsigned long long)sum); atomicAdd(&s_acc[4], (unsigned long long)sqr); }
-            warpVar(v, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
-            e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
-            if (lane == 0) { atomicAdd(&s_acc[2], (unsigned long long)sum); atomicAdd(&s_acc[5], (unsigned long long)sqr); }
+            /* interior block: lane = (row, half row) of the 16x16 luma block; lanes 0-7 / 8-15 = rows of the U / V 8x8 */
+            sum = 0; sqr = 0;
+            sumSqr8(y + (long long)(by + (lane >> 1)) * g.picW + bx + (lane & 1) * 8, sum, sqr);
+            unsigned cs = 0, cq = 0;
+            if (u && lane < 16)
+                sumSqr8((lane < 8 ? u : v) + (long long)((by >> 1) + (lane & 7)) * g.cW + (bx >> 1), cs, cq);
+#pragma unroll
+            for (int o = 16; o; o >>= 1)
+            {
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                sqr += __shfl_xor_sync(0xffffffffu, sqr, o);
+            }
+#pragma unroll
+            for (int o = 4; o; o >>= 1)     /* inside each 8-lane group */
+            {
+                cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                cq += __shfl_xor_sync(0xffffffffu, cq, o);
+            }
+            const unsigned vs = __shfl_sync(0xffffffffu, cs, 8), vq = __shfl_sync(0xffffffffu, cq, 8);
+            e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
+            if (lane == 0) { atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr); }
+            if (u)
+            {
+                e += cq - (unsigned)(((unsigned long long)cs * cs) >> 6);
+                e += vq - (unsigned)(((unsigned long long)vs * vs) >> 6);
+                if (lane == 0)
+                {
+                    atomicAdd(&s_acc[1], (unsigned long long)cs); atomicAdd(&s_acc[4], (unsigned long long)cq);
+                    atomicAdd(&s_acc[2], (unsigned long long)vs); atomicAdd(&s_acc[5], (unsigned long long)vq);
+                }
+            }
+        }
+        else
+        {
+            /* picture edge: replicate-clamped samples (PicYuv padding, picyuv.cpp:261-285) */
+            warpVar(y, g.picW, g.picW, g.picH, bx, by, 16, sum, sqr);
+            e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
+            if (lane == 0) { atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr); }
+            if (u)
+            {
+                warpVar(u, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
+                e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
+                if (lane == 0) { atomicAdd(&s_acc[1], (unsigned long long)sum); atomicAdd(&s_acc[4], (unsigned long long)sqr); }
+                warpVar(v, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
+                e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
+                if (lane == 0) { atomicAdd(&s_acc[2], (unsigned long long)sum); atomicAdd(&s_acc[5], (unsigned long long)sqr); }
+            }
         }
         if (lane == 0) energy[blk] = e;
     }
@@ -155,19 +220,48 @@ __global__ void __launch_bounds__(256) aq_energy_kernel(Geom g, const P* __restr
 }
 
 /* K2b: the transcendental finish of calcAdaptiveQuantFrame (slicetype.cpp:537-652, 681-694) for
- * aq-mode 0..3, qg-size > 8.  One CTA; the two frame means are reduced in a fixed order so the
- * result is deterministic.  (The reference sums sequentially in double; a different summation
- * order perturbs qp_adj by ~1e-15, far below the 1/64-QP grid of exp2fix8.) */
-__global__ void __launch_bounds__(1024) aq_finish_kernel(Geom g, const unsigned* __restrict__ energy, int aqMode,
-                                                         double aqStrength, int bWeightP, double* __restrict__ qpAq,
-                                                         double* __restrict__ qpCuTree, int* __restrict__ invQ,
-                                                         FrameStatsDev* stats)
+ * aq-mode 0..3, qg-size > 8, in two launches of LA_AQ_CTAS CTAs.
+ *   aq_pow_kernel    (aq-mode 2/3): qp_adj = pow(energy * bdc + 1, 0.1) per block and per-CTA partial sums;
+ *   aq_finish_kernel : every CTA folds the partials (same fixed order everywhere), then finishes its blocks.
+ * The two frame means are reduced in a fixed order that depends only on the block count, so the result is
+ * deterministic.  (The reference sums sequentially in double; a different summation order perturbs qp_adj by
+ * ~1e-15, far below the 1/64-QP grid of exp2fix8.) */
+#define LA_AQ_CTAS 64
+#define LA_AQ_THREADS 256
+
+__global__ void __launch_bounds__(LA_AQ_THREADS) aq_pow_kernel(Geom g, const unsigned* __restrict__ energy,
+                                                               double* __restrict__ qpCuTree, double* __restrict__ partial)
 {
-    __shared__ double s_a[1024], s_b[1024];
+    __shared__ double s_a[LA_AQ_THREADS], s_b[LA_AQ_THREADS];
+    const int tid = threadIdx.x, n = g.ncu;
+    const double bdc = (double)(1.f / (1 << (2 * (g.depth - 8))));
+    double a = 0, b = 0;
+    for (int i = blockIdx.x * LA_AQ_THREADS + tid; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS)
+    {
+        const double q = pow(__dadd_rn(__dmul_rn((double)energy[i], bdc), 1.0), 0.1);
+        qpCuTree[i] = q;
+        a = __dadd_rn(a, q);
+        b = __dadd_rn(b, __dmul_rn(q, q));
+    }
+    s_a[tid] = a; s_b[tid] = b;
+    __syncthreads();
+    for (int o = LA_AQ_THREADS / 2; o; o >>= 1)
+    {
+        if (tid < o) { s_a[tid] = __dadd_rn(s_a[tid], s_a[tid + o]); s_b[tid] = __dadd_rn(s_b[tid], s_b[tid + o]); }
+        __syncthreads();
+    }
+    if (tid == 0) { partial[blockIdx.x] = s_a[0]; partial[LA_AQ_CTAS + blockIdx.x] = s_b[0]; }
+}
+
+__global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const unsigned* __restrict__ energy, int aqMode,
+                                                                  double aqStrength, int bWeightP, const double* __restrict__ partial,
+                                                                  double* __restrict__ qpAq, double* __restrict__ qpCuTree,
+                                                                  int* __restrict__ invQ, FrameStatsDev* stats)
+{
     __shared__ double s_strength, s_avg, s_bias;
     const int tid = threadIdx.x, n = g.ncu;
     const float modeOneConst = 14.427f, modeTwoConst = 11.f;
-    if (tid == 0 && bWeightP)
+    if (blockIdx.x == 0 && tid == 0 && bWeightP)
     {
         const int maxCol = ((g.picW + 8) >> 4) << 4, maxRow = ((g.picH + 8) >> 4) << 4;
         const int wd[3] = { maxCol, maxCol >> 1, maxCol >> 1 }, ht[3] = { maxRow, maxRow >> 1, maxRow >> 1 };
@@ -181,41 +275,26 @@ __global__ void __launch_bounds__(1024) aq_finish_kernel(Geom g, const unsigned*
     if (aqMode == 0 || aqStrength == 0)
     {
         if (aqMode && aqStrength == 0)
-            for (int i = tid; i < n; i += blockDim.x) { qpAq[i] = 0; qpCuTree[i] = 0; invQ[i] = 256; }
+            for (int i = blockIdx.x * LA_AQ_THREADS + tid; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS) { qpAq[i] = 0; qpCuTree[i] = 0; invQ[i] = 256; }
         return;
     }
-    if (aqMode == 2 || aqMode == 3)
+    if (tid == 0)
     {
-        const double bdc = (double)(1.f / (1 << (2 * (g.depth - 8))));
-        double a = 0, b = 0;
-        for (int i = tid; i < n; i += blockDim.x)
+        if (aqMode == 2 || aqMode == 3)
         {
-            const double q = pow(__dadd_rn(__dmul_rn((double)energy[i], bdc), 1.0), 0.1);
-            qpCuTree[i] = q;
-            a = __dadd_rn(a, q);
-            b = __dadd_rn(b, __dmul_rn(q, q));
-        }
-        s_a[tid] = a; s_b[tid] = b;
-        __syncthreads();
-        for (int o = 512; o; o >>= 1)
-        {
-            if (tid < o) { s_a[tid] = __dadd_rn(s_a[tid], s_a[tid + o]); s_b[tid] = __dadd_rn(s_b[tid], s_b[tid + o]); }
-            __syncthreads();
-        }
-        if (tid == 0)
-        {
-            double avg_adj = __ddiv_rn(s_a[0], (double)n), avg_adj_pow2 = __ddiv_rn(s_b[0], (double)n);
+            double sa = 0, sb = 0;
+            for (int i = 0; i < LA_AQ_CTAS; i++) { sa = __dadd_rn(sa, partial[i]); sb = __dadd_rn(sb, partial[LA_AQ_CTAS + i]); }
+            const double avg_adj = __ddiv_rn(sa, (double)n), avg_adj_pow2 = __ddiv_rn(sb, (double)n);
             s_strength = __dmul_rn(aqStrength, avg_adj);
             s_avg = __dadd_rn(avg_adj, -__ddiv_rn(__dmul_rn((double)0.5f, __dadd_rn(avg_adj_pow2, -(double)modeTwoConst)), avg_adj));
             s_bias = __dmul_rn(1.0, aqStrength);
         }
-        __syncthreads();
+        else
+            s_strength = __dmul_rn(aqStrength, (double)1.0397f);
     }
-    else if (tid == 0)
-        s_strength = __dmul_rn(aqStrength, (double)1.0397f);
     __syncthreads();
     const double strength = s_strength, avg_adj = s_avg, bias_strength = s_bias;
-    for (int i = tid; i < n; i += blockDim.x)
+    for (int i = blockIdx.x * LA_AQ_THREADS + tid; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS)
     {
         double qp_adj;
         if (aqMode == 3)
@@ -417,17 +496,21 @@ __global__ void __launch_bounds__(128) intra_kernel(Geom g, const P* __restrict_
  * 1473-1528 lowres subpel), merange 16, subpelRefine 1.
  *
  * Dependencies: block (x,y) takes MV predictors from (x+1,y), (x,y+1), (x-1,y+1), (x+1,y+1)
- * (reverse raster order), so a frame is a wavefront.  A job is cut into bands of LA_BAND_ROWS rows;
- * one CTA per band; inside a CTA row j runs 2 steps behind row j-1 (one __syncthreads per step);
- * bands of one job are chained through a release/acquire progress counter in global memory.
- * CTAs take their (job, band) from a ticket counter so a band never waits on a CTA that has not
- * started.  Throughput comes from running many independent jobs concurrently.
+ * (reverse raster order), so a frame is a wavefront.  A job is cut into STRIPS of LA_STRIP_ROWS = 4 rows and one
+ * WARP (= one 32-thread CTA) owns a strip: its 4 groups search 4 consecutive rows in lockstep, row j running 2
+ * columns behind row j-1.  Inside the warp the predictors travel through registers: every group keeps its last
+ * three results and the group above reads them with one shuffle each (no shared memory, no barrier).  Strips of
+ * a job are chained through a progress counter in global memory (st.release / relaxed polling, MVs re-read from L2
+ * with ld.cg); a strip is ~250 steps of ~10-20 us, so one L2 round trip per step is noise.  Warps take their
+ * (strip, job) from a ticket counter, strip-major, so a strip never waits on a warp that has not started.
+ * The first version used 4-warp CTAs with one __syncthreads per wavefront step: ncu showed 45 % of all warp
+ * cycles stalled on that barrier (every step cost the slowest of 16 block searches); independent warps only
+ * ever wait for the strip below.  Throughput comes from running many independent jobs concurrently.
  *
- * A warp searches 4 blocks (4 consecutive rows) in lockstep.  The search is data dependent (MVP
- * choice, hexagon iterations, early exits); it is written with per-group predicates and
- * warp-votes so the warp never diverges, which keeps every shuffle on the full mask.
+ * The search is data dependent (MVP choice, hexagon iterations, early exits); it is written with per-group
+ * predicates and warp-votes so the warp never diverges, which keeps every shuffle on the full mask.
  * ------------------------------------------------------------------------------------------ */
-#define LA_BAND_ROWS 16
+#define LA_STRIP_ROWS 4
 
 template <typename P>
 struct SearchJobDev
@@ -437,6 +520,7 @@ struct SearchJobDev
     int*     mvOut;         /* ncu packed MVs: (x & 0xffff) | (y << 16), quarter-pel */
     int*     costOut;       /* ncu */
     int*     flagOut;       /* set to 1 when any block took the zero-MV skip (slicetype.cpp:4177-4181) */
+    const int* cond;        /* NULL, or the flagOut of another search: run only if that search skipped somewhere */
     int      bidir;
     int      pad;
 };
@@ -609,133 +693,137 @@ __device__ __forceinline__ MV2 unpackMv(int p) { MV2 m = { (int)(short)(p & 0xff
 __device__ __forceinline__ int packMv(MV2 m) { return (m.x & 0xffff) | (m.y << 16); }
 
 template <typename P>
-__global__ void __launch_bounds__(LA_BAND_ROWS * 8) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nbands, int njobs,
-                                                                  const unsigned short* __restrict__ mvcost,
-                                                                  int* ticketCounter, int* progress)
+__global__ void __launch_bounds__(32, 32) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nstrips, int njobs,
+                                                    const unsigned short* __restrict__ mvcost,
+                                                    int* ticketCounter, int* progress, unsigned long long* executed)
 {
-    extern __shared__ int s_mv[];                   /* LA_BAND_ROWS x bw packed MVs of this band */
-    __shared__ int s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(ticketCounter, 1);
-    __syncthreads();
-    /* band-major: every job's band 0 first, then every band 1, ...  With more jobs than resident CTAs a band is
-     * only started when the band below it is (nearly) finished, so no resident CTA idles on its predecessor */
-    const int band = s_ticket / njobs, job = s_ticket % njobs;
-    const SearchJobDev<P> J = jobs[job];
-    /* band 0 owns the lowest ticket of its job and every other band waits on its progress chain */
-    if (band == 0 && threadIdx.x == 0) *J.flagOut = 0;
-    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x;
+    const int grp = lane >> 3, r = lane & 7;
     const int bw = g.bw, bh = g.bh;
-    const int rowsInBand = min(LA_BAND_ROWS, bh - band * LA_BAND_ROWS);
-    const bool rowOk = grp < rowsInBand;
-    const int cuY = rowOk ? bh - 1 - band * LA_BAND_ROWS - grp : 0;
-    const bool lastRow = cuY == bh - 1;
-    const int steps = bw + 2 * (rowsInBand - 1);
-    int* myProgress = progress + job * nbands + band;
-    const int* belowProgress = myProgress - 1;
     MeCtx<P> m;
     m.mvcost = mvcost; m.r = r;
-    m.rb.plane0 = J.ref0; m.rb.planeSize = g.planeSize; m.rb.tpr = g.tpr;
+    m.rb.planeSize = g.planeSize; m.rb.tpr = g.tpr;
+    /* A warp is a worker: it takes strips from the ticket counter until none are left.  The grid may hold fewer
+     * warps than strips (engine.cu sizes it); a warp that finishes a strip picks up the next one, whose
+     * predecessor is by then well under way, instead of a fresh warp sitting resident while it waits its turn.
+     * Strip-major tickets: every job's strip 0 first, then every strip 1, ...  A strip's predecessor always holds
+     * a lower ticket, i.e. it is running or done, so polling on it cannot deadlock. */
+    for (;;)
+    {
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(ticketCounter, 1);
+    ticket = __shfl_sync(LA_FULL, ticket, 0);
+    if (ticket >= nstrips * njobs) return;
+    const int strip = ticket / njobs, job = ticket % njobs;
+    const SearchJobDev<P> J = jobs[job];
+    if (J.cond && __ldcg(J.cond) == 0) continue;    /* the variant this job would compute is not needed */
+    /* strip 0 owns the lowest ticket of its job and every other strip waits on its progress chain */
+    if (strip == 0 && lane == 0) { *J.flagOut = 0; atomicAdd(executed, 1ull); }
+    const int rowsInStrip = min(LA_STRIP_ROWS, bh - strip * LA_STRIP_ROWS);
+    const bool rowOk = grp < rowsInStrip;
+    const int cuY = rowOk ? bh - 1 - strip * LA_STRIP_ROWS - grp : 0;
+    const bool lastRow = cuY == bh - 1;
+    const int steps = bw + 2 * (rowsInStrip - 1);
+    int* myProgress = progress + job * nstrips + strip;
+    const int* belowProgress = myProgress - 1;
+    const int* belowRow = J.mvOut + min(cuY + 1, bh - 1) * bw;    /* group 0: last row of the strip below (global) */
+    m.rb.plane0 = J.ref0;
+    int h0 = 0, h1 = 0, h2 = 0;     /* this group's results of the last three steps (packed MVs) */
+    int seen = 0;                   /* progress of the strip below as last observed (warp-uniform) */
 
     for (int s = 0; s < steps; s++)
     {
-        /* is any of this warp's 4 rows inside its column range at this step? (warp-uniform) */
-        const int kLo = s - 2 * (warp * 4 + 3), kHi = s - 2 * (warp * 4);
-        if (kHi >= 0 && kLo < bw && warp * 4 < rowsInBand)
-        {
-            const int kRaw = s - 2 * grp;
-            const bool act = rowOk && kRaw >= 0 && kRaw < bw;
-            const int k = min(max(kRaw, 0), bw - 1);     /* idle groups shadow a valid block and write nothing */
-            const int cuX = bw - 1 - k;
-            const int cu = cuX + cuY * bw;
-            m.rb.X0 = g.mx + 8 * cuX; m.rb.Y0 = g.my + 8 * cuY;
-            m.fenc = loadRowAligned(J.fenc0, g.tpr, m.rb.X0, m.rb.Y0 + r);
+        const int kRaw = s - 2 * grp;
+        const bool act = rowOk && kRaw >= 0 && kRaw < bw;
+        const int k = min(max(kRaw, 0), bw - 1);     /* idle groups shadow a valid block and write nothing */
+        const int cuX = bw - 1 - k;
+        const int cu = cuX + cuY * bw;
+        m.rb.X0 = g.mx + 8 * cuX; m.rb.Y0 = g.my + 8 * cuY;
+        m.fenc = loadRowAligned(J.fenc0, g.tpr, m.rb.X0, m.rb.Y0 + r);
 
-            /* reverse-order MV predictors (slicetype.cpp:4131-4141): right, below, below-left, below-right */
-            int cand[4]; bool valid[4];
-            /* idle groups get no predictors: they must never follow an MV that is not there yet */
-            valid[0] = act && cuX < bw - 1;
-            valid[1] = act && !lastRow; valid[2] = act && !lastRow && cuX > 0; valid[3] = act && !lastRow && cuX < bw - 1;
-            cand[0] = s_mv[grp * bw + min(cuX + 1, bw - 1)];
-            if (warp == 0 && band > 0)
+        /* reverse-order MV predictors (slicetype.cpp:4131-4141): right, below, below-left, below-right */
+        int cand[4]; bool valid[4];
+        /* idle groups get no predictors: they must never follow an MV that is not there yet */
+        valid[0] = act && cuX < bw - 1;
+        valid[1] = act && !lastRow; valid[2] = act && !lastRow && cuX > 0; valid[3] = act && !lastRow && cuX < bw - 1;
+        cand[0] = h0;
+        /* the row below lives in the group below: it finished columns cuX-1, cuX, cuX+1 one, two and three steps ago */
+        cand[2] = __shfl_up_sync(LA_FULL, h0, 8);
+        cand[1] = __shfl_up_sync(LA_FULL, h1, 8);
+        cand[3] = __shfl_up_sync(LA_FULL, h2, 8);
+        if (strip > 0 && s < bw)
+        {
+            /* row below group 0 belongs to the strip below: wait until it has finished column cuX-1 */
+            const int need = min(bw, s + 2);
+            if (seen < need)
             {
-                /* row below group 0 belongs to the previous band: wait until it has finished column cuX-1 */
-                if (threadIdx.x == 0 && act)
-                {
-                    const int need = min(bw, k + 2);
-                    while (ldRelaxed(belowProgress) < need) __nanosleep(100);
-                }
-                __syncwarp();
+                if (lane == 0)
+                    while ((seen = ldRelaxed(belowProgress)) < need) __nanosleep(400);
+                seen = __shfl_sync(LA_FULL, seen, 0);
             }
+            if (grp == 0)
             {
-                const int xl = max(cuX - 1, 0), xr = min(cuX + 1, bw - 1);
-                if (grp == 0)
-                {
-                    const int* below = J.mvOut + min(cuY + 1, bh - 1) * bw;
-                    cand[1] = __ldcg(below + cuX); cand[2] = __ldcg(below + xl); cand[3] = __ldcg(below + xr);
-                }
-                else
-                {
-                    const int* below = s_mv + (grp - 1) * bw;
-                    cand[1] = below[cuX]; cand[2] = below[xl]; cand[3] = below[xr];
-                }
-            }
-            MV2 mvp = { 0, 0 };
-            int skipCost = 0x7fffffff;
-            {
-                int mvpcost = LA_COST_MAX;
-                int costs[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                {
-                    /* identical predictors cost the same: measure each distinct one once */
-                    int dup = -1;
-#pragma unroll
-                    for (int q = 0; q < i; q++)
-                        if (valid[q] && cand[q] == cand[i] && dup < 0) dup = q;
-                    const bool need = valid[i] && dup < 0;
-                    int cost = 0;
-                    if (__any_sync(LA_FULL, need))
-                    {
-                        const MV2 zero = { 0, 0 };
-                        const MV2 c = need ? unpackMv(cand[i]) : zero;
-                        cost = m.qpelSatd(c.x, c.y);
-                    }
-#pragma unroll
-                    for (int q = 0; q < i; q++)
-                        if (dup == q) cost = costs[q];
-                    costs[i] = cost;
-                    if (valid[i])
-                    {
-                        if (cost < mvpcost) { mvpcost = cost; mvp = unpackMv(cand[i]); }
-                        if (!(mvp.x | mvp.y) && J.bidir)
-                            skipCost = cost;
-                    }
-                }
-            }
-            const MV2 mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
-            const MV2 mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
-            MV2 best;
-            int fencCost = motionEstimate(m, mvmin, mvmax, mvp, best);
-            bool skipped = false;
-            if (skipCost < 64 && skipCost < fencCost && J.bidir)
-            {
-                fencCost = skipCost;
-                best.x = best.y = 0;
-                skipped = true;
-            }
-            if (r == 0 && act)
-            {
-                if (skipped) *J.flagOut = 1;
-                const int packed = packMv(best);
-                s_mv[grp * bw + cuX] = packed;
-                __stcg(J.mvOut + cu, packed);
-                J.costOut[cu] = fencCost;
-                if (grp == rowsInBand - 1)
-                    stRelease(myProgress, k + 1);      /* orders this thread's MV store before the counter */
+                cand[1] = __ldcg(belowRow + cuX);
+                cand[2] = __ldcg(belowRow + max(cuX - 1, 0));
+                cand[3] = __ldcg(belowRow + min(cuX + 1, bw - 1));
             }
         }
-        __syncthreads();
+        MV2 mvp = { 0, 0 };
+        int skipCost = 0x7fffffff;
+        {
+            int mvpcost = LA_COST_MAX;
+            int costs[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+            {
+                /* identical predictors cost the same: measure each distinct one once */
+                int dup = -1;
+#pragma unroll
+                for (int q = 0; q < i; q++)
+                    if (valid[q] && cand[q] == cand[i] && dup < 0) dup = q;
+                const bool need = valid[i] && dup < 0;
+                int cost = 0;
+                if (__any_sync(LA_FULL, need))
+                {
+                    const MV2 zero = { 0, 0 };
+                    const MV2 c = need ? unpackMv(cand[i]) : zero;
+                    cost = m.qpelSatd(c.x, c.y);
+                }
+#pragma unroll
+                for (int q = 0; q < i; q++)
+                    if (dup == q) cost = costs[q];
+                costs[i] = cost;
+                if (valid[i])
+                {
+                    if (cost < mvpcost) { mvpcost = cost; mvp = unpackMv(cand[i]); }
+                    if (!(mvp.x | mvp.y) && J.bidir)
+                        skipCost = cost;
+                }
+            }
+        }
+        const MV2 mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
+        const MV2 mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
+        MV2 best;
+        int fencCost = motionEstimate(m, mvmin, mvmax, mvp, best);
+        bool skipped = false;
+        if (skipCost < 64 && skipCost < fencCost && J.bidir)
+        {
+            fencCost = skipCost;
+            best.x = best.y = 0;
+            skipped = true;
+        }
+        const int packed = packMv(best);
+        h2 = h1; h1 = h0; h0 = packed;
+        if (r == 0 && act)
+        {
+            if (skipped) *J.flagOut = 1;
+            __stcg(J.mvOut + cu, packed);
+            J.costOut[cu] = fencCost;
+            if (grp == rowsInStrip - 1)
+                stRelease(myProgress, k + 1);      /* orders this thread's MV store before the counter */
+        }
+    }
+    __syncwarp();
     }
 }
 
@@ -752,12 +840,15 @@ struct CostJobDev
     const int* mv0; const int* cost0; const int* mv1; const int* cost1;
     const int* intraCost; const int* invQ;
     unsigned short* lowresCosts; int* rowSatds; CostResultDev* result;
+    const int* cond;        /* NULL, or a search's skip flag: run only if it is set (see SearchJobDev::cond) */
 };
 
 template <typename P>
-__global__ void __launch_bounds__(256) cost_clear_kernel(Geom g, const CostJobDev<P>* __restrict__ jobs)
+__global__ void __launch_bounds__(256) cost_clear_kernel(Geom g, const CostJobDev<P>* __restrict__ jobs, unsigned long long* executed)
 {
     const CostJobDev<P> J = jobs[blockIdx.x];
+    if (J.cond && __ldcg(J.cond) == 0) return;
+    if (threadIdx.x == 0) atomicAdd(executed, 1ull);
     for (int i = threadIdx.x; i < g.bh; i += blockDim.x) J.rowSatds[i] = 0;
     if (threadIdx.x == 0) { J.result->costEst = 0; J.result->costEstAq = 0; J.result->intraMbs = 0; J.result->reserved = 0; }
 }
@@ -784,10 +875,11 @@ __global__ void __launch_bounds__(128) cost_kernel(Geom g, const CostJobDev<P>* 
 {
     __shared__ unsigned long long s_acc[2];
     __shared__ int s_intra;
+    const CostJobDev<P> J = jobs[blockIdx.y];
+    if (J.cond && __ldcg(J.cond) == 0) return;      /* uniform for the whole CTA */
     if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
     if (threadIdx.x == 2) s_intra = 0;
     __syncthreads();
-    const CostJobDev<P> J = jobs[blockIdx.y];
     if (!J.ref1)
     {   /* P estimate: one thread per block */
         const int cu = blockIdx.x * 128 + threadIdx.x;

@@ -22,7 +22,7 @@ void x265la_param_default(x265la_param* q)
     q->bEnableWeightedPred = p.bEnableWeightedPred; q->maxNumReferences = p.maxNumReferences;
     q->aqMode = p.rc.aqMode; q->aqStrength = p.rc.aqStrength; q->cuTree = p.rc.cuTree;
     q->qCompress = p.rc.qCompress; q->qgSize = p.rc.qgSize; q->rateControlMode = p.rc.rateControlMode;
-    q->extraSlots = p.extraSlots; q->speculate = p.speculate;
+    q->extraSlots = p.extraSlots; q->speculate = p.speculate; q->asyncDepth = p.asyncDepth;
 }
 
 void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
@@ -42,7 +42,8 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     p.rc.qgSize = q->qgSize; p.rc.vbvBufferSize = q->vbvBufferSize; p.rc.vbvMaxBitrate = q->vbvMaxBitrate;
     p.rc.rateControlMode = q->rateControlMode;
     p.poolWorkers = q->poolWorkers; p.device = q->device; p.extraSlots = q->extraSlots; p.speculate = q->speculate;
-    p.pinHost = q->pinHost;
+    p.pinHost = q->pinHost; p.asyncDepth = q->asyncDepth;
+    if (q->pendingMax > 0) p.pendingMax = q->pendingMax;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
      * (encoder.cpp:3511-3516,3730-3753): cuTree needs AQ; strength 0 without cuTree disables AQ */
     if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }

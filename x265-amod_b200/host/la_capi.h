@@ -23,7 +23,9 @@ typedef struct
     int32_t aqMode; double aqStrength; int32_t cuTree; double qCompress; int32_t qgSize;
     int32_t vbvBufferSize, vbvMaxBitrate, rateControlMode;
     int32_t poolWorkers, device, extraSlots, speculate, pinHost;
-    int32_t reserved[8];
+    int32_t asyncDepth;              /* LookaheadParam::asyncDepth */
+    int32_t pendingMax;              /* LookaheadParam::pendingMax; 0 = default */
+    int32_t reserved[6];
 } x265la_param;
 
 typedef struct

@@ -56,7 +56,7 @@ void lookaheadParamDefault(LookaheadParam* p)
     p->bEnableWeightedPred = 1; p->maxNumReferences = 3;
     p->rc.aqMode = 2; p->rc.aqStrength = 1.0; p->rc.cuTree = 1; p->rc.qCompress = 0.6; p->rc.qgSize = 32;
     p->rc.rateControlMode = 2 /* X265_RC_CRF */;
-    p->extraSlots = 8; p->speculate = 1;
+    p->extraSlots = 8; p->speculate = 1; p->asyncDepth = 0; p->pendingMax = 8;
 }
 
 Lookahead::Lookahead(const LookaheadParam& param)
@@ -78,7 +78,10 @@ Lookahead::Lookahead(const LookaheadParam& param)
     }
     m_param.keyframeMin = std::max(1, m_param.keyframeMin);
     m_lastKeyframe = -m_param.keyframeMax;
-    m_fullQueueSize = std::max(1, m_param.lookaheadDepth);
+    /* asyncDepth extra frames of input delay: the decision only ever analyses the first rc-lookahead frames of the
+     * queue (slicetype.cpp:1821-1827, 2609-2616), so the results are the same, but the GPU always holds that many
+     * frames of searches in flight beyond the window being decided */
+    m_fullQueueSize = std::max(1, m_param.lookaheadDepth) + std::max(0, m_param.asyncDepth);
     m_bAdaptiveQuant = m_param.rc.aqMode || m_param.bEnableWeightedPred || m_param.bEnableWeightedBiPred;
     m_bBatchMotionSearch = m_param.poolWorkers > 0 && m_param.bFrameAdaptive == B_ADAPT_TRELLIS;
     m_bBatchFrameCosts = m_bBatchMotionSearch;
@@ -124,7 +127,7 @@ bool Lookahead::create()
     memset(&cfg, 0, sizeof(cfg));
     cfg.width = p.sourceWidth; cfg.height = p.sourceHeight; cfg.depth = p.internalBitDepth;
     cfg.max_cu_size = p.maxCUSize; cfg.bframes = p.bframes;
-    cfg.max_slots = std::max(1, p.lookaheadDepth) + 2 * (p.bframes + 2) + 4 + p.extraSlots;
+    cfg.max_slots = std::max(1, p.lookaheadDepth) + 2 * (p.bframes + 2) + 4 + p.extraSlots + std::max(0, p.asyncDepth);
     cfg.qg_size = p.rc.qgSize; cfg.aq_mode = p.rc.aqMode; cfg.aq_strength = p.rc.aqStrength;
     cfg.need_aq = m_bAdaptiveQuant; cfg.need_wp_stats = p.bEnableWeightedPred || p.bEnableWeightedBiPred;
     cfg.lambda = lookaheadLambda(p.internalBitDepth);
@@ -207,7 +210,7 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     if (!m_filled)   /* checkLookaheadQueue */
     {
         if (!m_param.bframes & !m_param.lookaheadDepth) m_filled = true;
-        else if (m_inputCount >= m_param.lookaheadDepth + 2 + m_param.bframes) m_filled = true;
+        else if (m_inputCount >= m_param.lookaheadDepth + 2 + m_param.bframes + std::max(0, m_param.asyncDepth)) m_filled = true;
     }
     Frame* f = NULL;
     for (size_t i = 0; i < m_pool.size(); i++)
@@ -226,6 +229,20 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     m_resident.push_back(f);
     m_inputQueue.push_back(f);
     m_inputCount++;
+    if (m_param.speculate)
+    {
+        m_pendingSpec.push_back(f);
+        if (m_param.speculate >= 2)
+        {
+            /* streaming: the frame's searches and costs go to the GPU now, long before a decision asks for them.
+             * With weightp the analysis needs the frame's pixel sums on the host, so it runs one frame late rather
+             * than wait for this frame's upload */
+            const double t0 = nowSec();
+            drainPending((size_t)m_param.pendingMax, -1);
+            m_timers[7] += nowSec() - t0;
+            if (m_failed) return NULL;
+        }
+    }
     return f;
 }
 
@@ -371,7 +388,7 @@ void Lookahead::weightsAnalyseBatch(const std::vector<std::pair<Lowres*, Lowres*
     }
 }
 
-static void addSearch(std::vector<x265cu_search_job>& jobs, Lowres* fenc, Lowres* ref, int kind, int d, int nb)
+static void addSearch(std::vector<x265cu_search_job>& jobs, Lowres* fenc, Lowres* ref, int kind, int d, int nb, int condStore = -1)
 {
     if (fenc->haveSearch[kind][d]) return;
     fenc->haveSearch[kind][d] = 1;
@@ -380,6 +397,7 @@ static void addSearch(std::vector<x265cu_search_job>& jobs, Lowres* fenc, Lowres
     j.fenc_slot = fenc->slot; j.ref_slot = ref->slot;
     j.bidir_ctx = kind != 0;
     j.store = kind * nb + d;
+    j.cond_store = condStore;
     if (kind < 2 && fenc->weightState[d] == 2)
     {
         j.weighted = 1; j.w_scale = fenc->wScale[d]; j.w_denom = fenc->wDenom[d]; j.w_offset = fenc->wOffset[d];
@@ -387,7 +405,8 @@ static void addSearch(std::vector<x265cu_search_job>& jobs, Lowres* fenc, Lowres
     jobs.push_back(j);
 }
 
-static void addCost(std::vector<x265cu_cost_job>& jobs, Lowres* b, Lowres* p0, Lowres* p1, int d0, int d1, int variant, int nb)
+static void addCost(std::vector<x265cu_cost_job>& jobs, Lowres* b, Lowres* p0, Lowres* p1, int d0, int d1, int variant, int nb,
+                    int condStore = -1)
 {
     if (b->haveCost[d0][d1][variant]) return;
     b->haveCost[d0][d1][variant] = 1;
@@ -396,6 +415,7 @@ static void addCost(std::vector<x265cu_cost_job>& jobs, Lowres* b, Lowres* p0, L
     j.l0_store = variant * nb + d0;
     j.l1_store = p1 ? 2 * nb + d1 : -1;
     j.out = (d0 * nb + d1) * 2 + variant;
+    j.cond_store = condStore;
     jobs.push_back(j);
 }
 
@@ -410,64 +430,47 @@ void Lookahead::launchJobs()
 
 /* every frame cost of `variant` (= kind of the L0 search it reads) whose searches exist on the device and whose
  * frames are resident: P estimates (d0, 0) and B estimates (d0, d1) the reference can ask for (p1 - p0 <= bframes+1,
- * slicetype.cpp:3221-3305; every (d0, d1) when the frame-cost batches of :2696-2735 are emulated) */
-void Lookahead::enqueueCosts(int variant)
+ * slicetype.cpp:3221-3305; every (d0, d1) when the frame-cost batches of :2696-2735 are emulated).
+ * conditional: the jobs read a P-context L0 search that only exists if its B-context twin applied the skip rule */
+void Lookahead::enqueueCosts(int variant, bool conditional)
 {
     const int B = m_param.bframes, nb = m_geom.nb;
     for (size_t i = 0; i < m_resident.size(); i++)
     {
         Frame* bf = m_resident[i];
-        if (!bf->m_lowresInit) continue;
         Lowres* b = &bf->m_lowres;
         for (int d0 = 1; d0 <= B + 1; d0++)
         {
             if (!b->haveSearch[variant][d0]) continue;
             Frame* p0f = frameOfPoc(bf->m_poc - d0);
             if (!p0f) continue;
-            addCost(m_costJobs, b, &p0f->m_lowres, NULL, d0, 0, variant, nb);
+            const int cond = conditional ? 1 * nb + d0 : -1;
+            addCost(m_costJobs, b, &p0f->m_lowres, NULL, d0, 0, variant, nb, cond);
             const int maxD1 = m_bBatchFrameCosts ? B : B + 1 - d0;
             for (int d1 = 1; d1 <= maxD1; d1++)
             {
                 if (!b->haveSearch[2][d1]) continue;
                 Frame* p1f = frameOfPoc(bf->m_poc + d1);
                 if (!p1f) continue;
-                addCost(m_costJobs, b, &p0f->m_lowres, &p1f->m_lowres, d0, d1, variant, nb);
+                addCost(m_costJobs, b, &p0f->m_lowres, &p1f->m_lowres, d0, d1, variant, nb, cond);
             }
         }
     }
 }
 
-/* Eager whole-window batch: for every frame that arrived since the last decision, every motion
- * search and frame cost the reference could ask for (distances <= bframes+1, slicetype.cpp:
- * 2674-2689, 3221-3305) whose frames are all resident.
- * With B frames an L0 search exists in two variants (P / B context).  Phase 1 runs the B-context variant only
- * and learns from the engine whether the zero-MV skip rule ever fired; where it did not, the P-context variant is
- * the same search and is aliased instead of computed.  Phase 2 computes the P-context variant for the rest. */
-void Lookahead::speculate()
+/* Eager speculation: for every frame in `fresh` (in arrival order), every motion search and frame cost the
+ * reference could ask for (distances <= bframes+1, slicetype.cpp:2674-2689, 3221-3305) whose frames are
+ * resident, as ONE asynchronous batch on the engine.  Nothing here waits for the GPU.
+ * With B frames an L0 search exists in two variants (P / B context, see lookahead.h).  The B-context variant is
+ * always computed; the P-context variant and the costs that read it are enqueued as CONDITIONAL jobs which the
+ * device skips when the B-context search never applied the zero-MV skip rule (the two variants are then the same
+ * search and the host aliases them once it has read the flag, resolveAlias). */
+void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
 {
+    if (fresh.empty() || m_failed) return;
     const int B = m_param.bframes, nb = m_geom.nb;
-    std::vector<Frame*> fresh;
-    for (size_t i = 0; i < m_resident.size(); i++)
-        if (!m_resident[i]->m_speculated && m_resident[i]->m_lowresInit)
-            fresh.push_back(m_resident[i]);
-    if (fresh.empty()) return;
-
     double t0 = nowSec();
-    if (m_param.bEnableWeightedPred)
-    {
-        std::vector<std::pair<Lowres*, Lowres*> > pairs;
-        for (size_t i = 0; i < fresh.size(); i++)
-            for (int d = 1; d <= B + 1; d++)
-            {
-                Frame* r = frameOfPoc(fresh[i]->m_poc - d);
-                if (!r || !r->m_lowresInit) break;
-                pairs.push_back(std::make_pair(&fresh[i]->m_lowres, &r->m_lowres));
-            }
-        weightsAnalyseBatch(pairs);
-    }
-    m_timers[1] += nowSec() - t0;
-    t0 = nowSec();
-
+    if (!check(x265cu_batch_begin(m_ctx, NULL), "x265cu_batch_begin")) return;
     m_searchJobs.clear(); m_costJobs.clear();
     const int firstKind = B > 0 ? 1 : 0;
     for (size_t i = 0; i < fresh.size(); i++)
@@ -478,73 +481,115 @@ void Lookahead::speculate()
         for (int d = 1; d <= B + 1; d++)
         {
             Frame* rf = frameOfPoc(fn->m_poc - d);
-            if (!rf || !rf->m_lowresInit) break;
+            if (!rf) break;
             Lowres* r = &rf->m_lowres;
             addSearch(m_searchJobs, n, r, firstKind, d, nb);        /* L0(n,d) */
             if (B > 0 && d <= B)
                 addSearch(m_searchJobs, r, n, 2, d, nb);            /* L1(n-d,d), reference = n */
         }
     }
-    enqueueCosts(firstKind);
+    enqueueCosts(firstKind, false);
     launchJobs();
-    m_timers[2] += nowSec() - t0;
-    t0 = nowSec();
-    std::vector<Lowres*> who;
-    for (size_t i = 0; i < m_resident.size(); i++) who.push_back(&m_resident[i]->m_lowres);
-    fetchResults(who);
     if (B > 0 && !m_failed)
     {
-        /* which B-context searches applied the skip rule? */
-        std::vector<int32_t> slots, stores, flags;
-        std::vector<std::pair<Lowres*, int> > ref;
-        for (size_t i = 0; i < who.size(); i++)
+        for (size_t i = 0; i < fresh.size(); i++)
+        {
+            Frame* fn = fresh[i];
             for (int d = 1; d <= B + 1; d++)
-                if (who[i]->haveSearch[1][d] && !who[i]->flagFetched[d])
-                {
-                    slots.push_back(who[i]->slot); stores.push_back(1 * nb + d);
-                    ref.push_back(std::make_pair(who[i], d));
-                }
-        if (!slots.empty())
-        {
-            flags.resize(slots.size());
-            if (check(x265cu_search_flags_get(m_ctx, &slots[0], &stores[0], (int)slots.size(), &flags[0]), "x265cu_search_flags_get"))
-                for (size_t i = 0; i < ref.size(); i++)
-                {
-                    Lowres* l = ref[i].first; int d = ref[i].second;
-                    l->flagFetched[d] = 1;
-                    if (!l->haveSearch[0][d])
-                        l->l0Alias[d] = flags[i] ? 2 : 1;
-                }
+            {
+                Frame* rf = frameOfPoc(fn->m_poc - d);
+                if (!rf) break;
+                addSearch(m_searchJobs, &fn->m_lowres, &rf->m_lowres, 0, d, nb, 1 * nb + d);
+            }
         }
-        m_timers[3] += nowSec() - t0;
-        t0 = nowSec();
-        /* phase 2: P-context variants that really differ */
-        for (size_t i = 0; i < m_resident.size(); i++)
-        {
-            Frame* fn = m_resident[i];
-            if (!fn->m_lowresInit) continue;
-            Lowres* n = &fn->m_lowres;
-            for (int d = 1; d <= B + 1; d++)
-                if (n->l0Alias[d] == 2 && !n->haveSearch[0][d])
-                {
-                    Frame* rf = frameOfPoc(fn->m_poc - d);
-                    if (rf) addSearch(m_searchJobs, n, &rf->m_lowres, 0, d, nb);
-                }
-        }
-        enqueueCosts(0);
-        if (!m_searchJobs.empty() || !m_costJobs.empty())
-        {
-            launchJobs();
-            m_timers[2] += nowSec() - t0;
-            t0 = nowSec();
-            fetchResults(who);
-        }
+        enqueueCosts(0, true);
+        launchJobs();
     }
-    m_timers[3] += nowSec() - t0;
+    check(x265cu_batch_end(m_ctx), "x265cu_batch_end");
+    m_timers[2] += nowSec() - t0;
 }
 
-/* one synchronising gather of every computed-but-unread cost scalar */
-void Lookahead::fetchResults(const std::vector<Lowres*>& who)
+/* Speculate the frames that arrived but were not processed yet, oldest first.  Frames up to mustPoc are needed now
+ * and are taken unconditionally.  Newer ones are taken too -- the GPU works on them while the host decides from the
+ * results of earlier batches -- but with weightp a frame's pixel sums must be on the host first, so a newer frame is
+ * only taken if its pre-lookahead has already finished (or more than `keep` frames are waiting): the caller never
+ * stalls on the GPU for work nobody needs yet.  Scheduling only: what is computed does not depend on when.
+ * streaming mode: one batch per frame; otherwise one batch for all of them */
+void Lookahead::drainPending(size_t keep, int mustPoc)
+{
+    std::vector<Frame*> group;
+    const bool needStats = m_param.bEnableWeightedPred != 0;
+    while (!m_pendingSpec.empty() && !m_failed)
+    {
+        Frame* f = m_pendingSpec.front();
+        if (f->m_poc > mustPoc && m_pendingSpec.size() <= keep && needStats && !f->m_lowresInit &&
+            x265cu_frame_ready(m_ctx, f->m_lowres.slot) != 1)
+            break;
+        m_pendingSpec.pop_front();
+        group.push_back(f);
+    }
+    if (group.empty()) return;
+    if (needStats)
+    {
+        std::vector<Frame*> pre;
+        for (size_t i = 0; i < group.size(); i++)
+            if (!group[i]->m_lowresInit) pre.push_back(group[i]);
+        const double t0 = nowSec();
+        preLookahead(pre);
+        m_timers[0] += nowSec() - t0;
+        /* the weightp analysis of the whole group in two round trips instead of two per frame */
+        const double t1 = nowSec();
+        std::vector<std::pair<Lowres*, Lowres*> > pairs;
+        for (size_t i = 0; i < group.size(); i++)
+            for (int d = 1; d <= m_param.bframes + 1; d++)
+            {
+                Frame* r = frameOfPoc(group[i]->m_poc - d);
+                if (!r) break;
+                pairs.push_back(std::make_pair(&group[i]->m_lowres, &r->m_lowres));
+            }
+        weightsAnalyseBatch(pairs);
+        m_timers[1] += nowSec() - t1;
+    }
+    if (m_param.speculate >= 2)
+        for (size_t i = 0; i < group.size() && !m_failed; i++)
+            speculateFrames(std::vector<Frame*>(1, group[i]));
+    else
+        speculateFrames(group);
+}
+
+/* the skip flags of the B-context L0 searches of `who` that the host has not looked at yet: decides, per (frame,
+ * distance), whether the P-context variant is an alias (flag clear) or was really computed (flag set).  One
+ * synchronising gather; waits only for the batches that ran those searches */
+void Lookahead::resolveAlias(const std::vector<Lowres*>& who)
+{
+    const int B = m_param.bframes, nb = m_geom.nb;
+    if (B <= 0 || m_failed) return;
+    std::vector<int32_t> slots, stores, flags;
+    std::vector<std::pair<Lowres*, int> > ref;
+    for (size_t i = 0; i < who.size(); i++)
+        for (int d = 1; d <= B + 1; d++)
+            if (who[i]->haveSearch[1][d] && !who[i]->flagFetched[d])
+            {
+                slots.push_back(who[i]->slot); stores.push_back(1 * nb + d);
+                ref.push_back(std::make_pair(who[i], d));
+            }
+    if (slots.empty()) return;
+    flags.resize(slots.size());
+    if (!check(x265cu_search_flags_get(m_ctx, &slots[0], &stores[0], (int)slots.size(), &flags[0]), "x265cu_search_flags_get"))
+        return;
+    for (size_t i = 0; i < ref.size(); i++)
+    {
+        Lowres* l = ref[i].first; int d = ref[i].second;
+        l->flagFetched[d] = 1;
+        /* a P-context search issued unconditionally (demand path) is always the real thing */
+        if (!l->l0Alias[d])
+            l->l0Alias[d] = (flags[i] || l->haveSearch[0][d] == 2) ? 2 : 1;
+    }
+}
+
+/* one synchronising gather of every computed-but-unread cost scalar of `who` whose frames are all <= maxPoc (later
+ * ones may still be in flight and no decision can ask for them yet) */
+void Lookahead::fetchResults(const std::vector<Lowres*>& who, int maxPoc)
 {
     const int nb = m_geom.nb;
     std::vector<int32_t> slots, outs;
@@ -556,6 +601,8 @@ void Lookahead::fetchResults(const std::vector<Lowres*>& who)
                 for (int v = 0; v < 2; v++)
                     if (who[i]->haveCost[d0][d1][v] && !who[i]->resultFetched[d0][d1][v])
                     {
+                        if (who[i]->frameNum + d1 > maxPoc) continue;
+                        if (v == 0 && who[i]->l0Alias[d0] == 1) continue;   /* aliased: the conditional job did not run */
                         slots.push_back(who[i]->slot); outs.push_back((d0 * nb + d1) * 2 + v);
                         Ref r = { who[i], d0, d1, v };
                         refs.push_back(r);
@@ -586,16 +633,16 @@ void Lookahead::ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0,
             weightsAnalyseBatch(one);
         }
         addSearch(m_searchJobs, fenc, ref0, l0kind, d0, nb);
+        if (l0kind == 0) fenc->haveSearch[0][d0] = 2;       /* unconditional */
     }
     if (ref1 && !fenc->haveSearch[2][d1])
         addSearch(m_searchJobs, fenc, ref1, 2, d1, nb);
     addCost(m_costJobs, fenc, ref0, ref1, d0, d1, l0kind, nb);
-    if (!m_searchJobs.empty())
-        check(x265cu_search_batch(m_ctx, &m_searchJobs[0], (int)m_searchJobs.size()), "x265cu_search_batch");
-    if (!m_costJobs.empty())
-        check(x265cu_cost_batch(m_ctx, &m_costJobs[0], (int)m_costJobs.size()), "x265cu_cost_batch");
+    if (!check(x265cu_batch_begin(m_ctx, NULL), "x265cu_batch_begin")) return;
+    launchJobs();
+    check(x265cu_batch_end(m_ctx), "x265cu_batch_end");
     std::vector<Lowres*> who(1, fenc);
-    fetchResults(who);
+    fetchResults(who, 0x7fffffff);
 }
 
 /* -------------------------------------------------------------------------------------------
@@ -623,6 +670,8 @@ int64_t Lookahead::estimateFrameCost(Lowres** frames, int p0, int p1, int b, boo
         const bool bDoSearch1 = p1 > b && fenc->mvStore[1][d1] < 0;
         /* first touch decides which variant of the L0 search the reference would hold */
         int l0kind = bDoSearch0 ? (p1 > b ? 1 : 0) : fenc->mvStore[0][d0] / nb;
+        if (l0kind == 0 && fenc->haveSearch[1][d0] && !fenc->flagFetched[d0])
+            resolveAlias(std::vector<Lowres*>(1, fenc));
         l0kind = effKind(fenc, d0, l0kind);      /* identical variants share one store */
         ensureEstimate(fenc, frames[p0], p1 > b ? frames[p1] : NULL, d0, d1, l0kind);
         if (m_failed) return 0;
@@ -675,17 +724,34 @@ void Lookahead::slicetypeDecide()
     }
     maxSearch = j;
 
-    /* pre-analysis results for every frame that arrived (not only the first maxSearch): the
-     * GPU already ran it, and speculation wants all resident frames */
-    for (size_t i = 0; i < m_resident.size(); i++)
-        if (!m_resident[i]->m_lowresInit && std::find(pre.begin(), pre.end(), m_resident[i]) == pre.end())
-            pre.push_back(m_resident[i]);
+    for (j = maxSearch; j < m_param.bframes + 2 && j < (int)m_inputQueue.size(); j++)
+        if (!m_inputQueue[j]->m_lowresInit) pre.push_back(m_inputQueue[j]);
     const double tStart = nowSec();
+    int maxPoc = m_lastNonBFrame ? m_lastNonBFrame->m_poc : -1;
+    for (j = 0; j < (int)m_inputQueue.size() && (j < maxSearch || j < m_param.bframes + 2); j++)
+        maxPoc = std::max(maxPoc, m_inputQueue[j]->m_poc);
+    if (m_param.speculate)
+    {
+        /* everything the window can ask for goes to the GPU (most of it went long ago, at addPicture) before the
+         * host waits for anything */
+        /* per-decision mode issues every frame that has arrived, also those beyond the window (asyncDepth), so the
+         * GPU works on them while this decision is taken from the results of earlier batches */
+        drainPending(m_param.speculate >= 2 ? 0x7fffffff : (size_t)m_param.pendingMax, maxPoc);
+        if (m_failed) return;
+    }
     preLookahead(pre);
     m_timers[0] += nowSec() - tStart;
     if (m_failed) return;
     if (m_param.speculate)
-        speculate();
+    {
+        const double t0 = nowSec();
+        std::vector<Lowres*> who;
+        for (size_t i = 0; i < m_resident.size(); i++)
+            if (m_resident[i]->m_poc <= maxPoc && m_resident[i]->m_speculated) who.push_back(&m_resident[i]->m_lowres);
+        resolveAlias(who);
+        fetchResults(who, maxPoc);
+        m_timers[3] += nowSec() - t0;
+    }
     if (m_failed) return;
     const double tAnalyse = nowSec();
 

@@ -19,6 +19,7 @@
 #define X265CU_LOOKAHEAD_H
 
 #include <stdint.h>
+#include <stddef.h>
 #include <deque>
 #include <vector>
 #include "x265cu.h"
@@ -55,7 +56,13 @@ struct LookaheadParam
     int poolWorkers;
     int device;          /* CUDA device ordinal */
     int extraSlots;      /* frames the caller may hold after getDecidedPicture before release */
-    int speculate;       /* 1 (default): eager whole-window batches; 0: on-demand jobs only */
+    int speculate;       /* 1 (default): at every decision, one asynchronous GPU batch with the searches and costs of the
+                            frames that arrived since the last one (those beyond the window included, see asyncDepth);
+                            2: streaming -- one batch per frame, enqueued by addPicture (smaller launches: lower latency,
+                            lower throughput); 0: on-demand jobs only.  Results are identical in all three */
+    int pendingMax;      /* streaming + weightp: frames that may wait for their pixel sums before addPicture blocks on them */
+    int asyncDepth;      /* extra frames of input delay before a decision is taken (0 = the reference's trigger).  The
+                            decision analyses the same frames either way; the GPU gets that many frames of slack */
     int pinHost;         /* page-lock pictures handed to addPicture */
 };
 void lookaheadParamDefault(LookaheadParam* p);   /* x265_param_default + preset medium, param.cpp:164-349 */
@@ -147,7 +154,8 @@ public:
     bool    ok() const { return !m_failed; }
 
     /* host-side wall-clock per phase (seconds), for bench.py: 0 pre-lookahead wait, 1 weightp, 2 enqueue,
-     * 3 result wait, 4 decisions (host logic incl. cuTree enqueue), 5 whole slicetypeDecide, 6 calls */
+     * 3 result wait, 4 decisions (host logic incl. cuTree enqueue), 5 whole slicetypeDecide, 6 calls,
+     * 7 speculation inside addPicture (streaming mode; its weightp / enqueue shares are also in 1 / 2) */
     double  m_timers[8];
 
     LookaheadParam m_param;
@@ -169,6 +177,7 @@ private:
     std::vector<uint16_t> m_mvcost;
     std::vector<Frame*> m_pool;           /* one per slot */
     std::vector<Frame*> m_resident;       /* frames with live slots, by arrival */
+    std::deque<Frame*>  m_pendingSpec;    /* arrived, searches / costs not enqueued yet */
     int     m_pocNext;
     bool    m_failed; char m_error[256];
 
@@ -194,13 +203,15 @@ private:
 
     /* device orchestration */
     void    preLookahead(const std::vector<Frame*>& fr);
-    void    speculate();
-    void    enqueueCosts(int variant);
+    void    speculateFrames(const std::vector<Frame*>& fresh);
+    void    drainPending(size_t keep, int mustPoc);
+    void    resolveAlias(const std::vector<Lowres*>& who);
+    void    enqueueCosts(int variant, bool conditional);
     void    launchJobs();
     int     effKind(const Lowres* l, int d0, int kind) const { return (kind == 0 && l->l0Alias[d0] == 1) ? 1 : kind; }
     void    weightsAnalyseBatch(const std::vector<std::pair<Lowres*, Lowres*> >& pairs);
     void    ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind);
-    void    fetchResults(const std::vector<Lowres*>& who);
+    void    fetchResults(const std::vector<Lowres*>& who, int maxPoc);
     Frame*  frameOfPoc(int poc);
     void    recycle();
     void    initLowres(Frame* f, int poc);
