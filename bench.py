@@ -149,7 +149,7 @@ def main():
     ap.add_argument("--async-depth", type=int, default=16,
                     help="extra frames of input delay (LookaheadParam::asyncDepth): same decisions, GPU slack")
     ap.add_argument("--speculate", type=int, default=1)
-    ap.add_argument("--pending-max", type=int, default=0)
+    ap.add_argument("--pending-max", type=int, default=16)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.frames:

@@ -564,6 +564,41 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         c->costWriter[(size_t)j.b_slot * c->geom.n_cost_stores + j.out] = b->id;
     }
     c->costEnq += n;
+    /* B estimates that share the source frame and the list-1 search form one group (cost_group_kernel) */
+    std::vector<CostGroupDev<P> > groups;
+    {
+        std::map<std::pair<const void*, const void*>, int> open;       /* (fenc planes, list-1 MVs) -> group being filled */
+        for (int i = nP; i < n; i++)
+        {
+            const CostJobDev<P>& d = dev[i];
+            const std::pair<const void*, const void*> key((const void*)d.fenc0, (const void*)d.mv1);
+            std::map<std::pair<const void*, const void*>, int>::iterator it = open.find(key);
+            int gi;
+            if (it == open.end() || groups[it->second].n == LA_COST_GROUP_MAX)
+            {
+                gi = (int)groups.size();
+                CostGroupDev<P> G;
+                memset(&G, 0, sizeof(G));
+                G.fenc0 = d.fenc0; G.ref1 = d.ref1; G.mv1 = d.mv1; G.cost1 = d.cost1; G.intraCost = d.intraCost; G.invQ = d.invQ;
+                groups.push_back(G);
+                open[key] = gi;
+            }
+            else
+                gi = it->second;
+            CostGroupDev<P>& G = groups[gi];
+            typename CostGroupDev<P>::Member& M = G.m[G.n++];
+            M.ref0 = d.ref0; M.mv0 = d.mv0; M.cost0 = d.cost0; M.lowresCosts = d.lowresCosts; M.rowSatds = d.rowSatds;
+            M.result = d.result; M.cond = d.cond;
+        }
+    }
+    char *hgr = NULL, *dgr = NULL;
+    if (!groups.empty())
+    {
+        st = batchStage(c, b, groups.size() * sizeof(CostGroupDev<P>), &hgr, &dgr);
+        if (st) return st;
+        memcpy(hgr, &groups[0], groups.size() * sizeof(CostGroupDev<P>));
+        CK(cudaMemcpyAsync(dgr, hgr, groups.size() * sizeof(CostGroupDev<P>), cudaMemcpyHostToDevice, b->stream));
+    }
     CK(cudaMemcpyAsync(dst, hst, n * sizeof(CostJobDev<P>), cudaMemcpyHostToDevice, b->stream));
     {
         Prof pr(c, X265CU_K_COST, 1 + (nP > 0) + (n > nP), b->stream);
@@ -572,12 +607,13 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         for (int base = 0; base < nP; base += 65535)
         {
             dim3 gg((g.ncu + 127) / 128, (unsigned)((nP - base) < 65535 ? (nP - base) : 65535));
-            cost_kernel<P><<<gg, 128, 0, b->stream>>>(g, (const CostJobDev<P>*)dst + base);
+            cost_p_kernel<P><<<gg, 128, 0, b->stream>>>(g, (const CostJobDev<P>*)dst + base);
         }
-        for (int base = nP; base < n; base += 65535)
+        const int ng = (int)groups.size();
+        for (int base = 0; base < ng; base += 65535)
         {
-            dim3 gg((g.ncu + 15) / 16, (unsigned)((n - base) < 65535 ? (n - base) : 65535));
-            cost_kernel<P><<<gg, 128, 0, b->stream>>>(g, (const CostJobDev<P>*)dst + base);
+            dim3 gg((g.ncu + 15) / 16, (unsigned)((ng - base) < 65535 ? (ng - base) : 65535));
+            cost_group_kernel<P><<<gg, 128, 0, b->stream>>>(g, (const CostGroupDev<P>*)dgr + base);
         }
     }
     CK(cudaGetLastError());

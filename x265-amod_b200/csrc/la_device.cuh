@@ -68,15 +68,20 @@ __device__ __forceinline__ Row<uint8_t> loadRowT(const uint8_t* plane, int tpr, 
 
 __device__ __forceinline__ Row<uint16_t> loadRowT(const uint16_t* plane, int tpr, int X, int Y)
 {
+    /* The 8 samples start at sample fx of a 16-byte tile row and may run into the tile to the right (+64 samples).
+     * Three 8-byte loads fetch exactly the 4-sample chunks they touch (chunk i = fx >> 2 onwards), which leaves a
+     * one-word select and a half-word funnel shift: 9 ALU operations instead of the 15 that picking 5 of the 8
+     * words of two 16-byte loads took -- the ALU pipe is what bounds the search kernel (ncu: 65 % busy), the
+     * load pipe has room.  The chunk addresses are affine in i, so they cost multiply-adds on the FMA pipe. */
     const uint16_t* t = plane + (((long long)((Y >> 3) * tpr + (X >> 3))) << 6) + ((Y & 7) << 3);
-    const uint4 a = __ldg((const uint4*)t);
-    const uint4 b = __ldg((const uint4*)(t + 64));
     const int fx = X & 7;
-    const bool s2 = fx & 4, s1 = fx & 2;
-    /* words needed: W[ws .. ws+4], ws = fx >> 1 */
-    const uint32_t u0 = s2 ? a.z : a.x, u1 = s2 ? a.w : a.y, u2 = s2 ? b.x : a.z, u3 = s2 ? b.y : a.w,
-                   u4 = s2 ? b.z : b.x, u5 = s2 ? b.w : b.y;
-    const uint32_t t0 = s1 ? u1 : u0, t1 = s1 ? u2 : u1, t2 = s1 ? u3 : u2, t3 = s1 ? u4 : u3, t4 = s1 ? u5 : u4;
+    const int i = fx >> 2;
+    const uint2 c0 = __ldg((const uint2*)(t + 4 * i));             /* A0 | A1 */
+    const uint2 c1 = __ldg((const uint2*)(t + 4 + 60 * i));        /* A1 | B0 */
+    const uint2 c2 = __ldg((const uint2*)(t + 64 + 4 * i));        /* B0 | B1 */
+    const bool s1 = fx & 2;
+    const uint32_t t0 = s1 ? c0.y : c0.x, t1 = s1 ? c1.x : c0.y, t2 = s1 ? c1.y : c1.x, t3 = s1 ? c2.x : c1.y,
+                   t4 = s1 ? c2.y : c2.x;
     const uint32_t sh = (uint32_t)(fx & 1) * 16;
     Row<uint16_t> r;
     r.v[0] = __funnelshift_r(t0, t1, sh);

@@ -511,6 +511,11 @@ __global__ void __launch_bounds__(128) intra_kernel(Geom g, const P* __restrict_
  * predicates and warp-votes so the warp never diverges, which keeps every shuffle on the full mask.
  * ------------------------------------------------------------------------------------------ */
 #define LA_STRIP_ROWS 4
+#ifndef LA_SEARCH_MIN_CTAS
+#define LA_SEARCH_MIN_CTAS 28       /* resident one-warp CTAs per SM the register allocation must allow: 72 registers, no spills;
+                                       32 (64 registers) spills and measured 3 % slower; 28 also leaves block slots for the short
+                                       high-priority kernels */
+#endif
 
 template <typename P>
 struct SearchJobDev
@@ -693,7 +698,7 @@ __device__ __forceinline__ MV2 unpackMv(int p) { MV2 m = { (int)(short)(p & 0xff
 __device__ __forceinline__ int packMv(MV2 m) { return (m.x & 0xffff) | (m.y << 16); }
 
 template <typename P>
-__global__ void __launch_bounds__(32, 32) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nstrips, int njobs,
+__global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nstrips, int njobs,
                                                     const unsigned short* __restrict__ mvcost,
                                                     int* ticketCounter, int* progress, unsigned long long* executed)
 {
@@ -829,9 +834,9 @@ __global__ void __launch_bounds__(32, 32) search_kernel(Geom g, const SearchJobD
 
 /* ------------------------------------------------------------------------------------------
  * K5: frame cost.  Cost half of estimateCUCost (slicetype.cpp:4187-4248) + the frame sums of
- * estimateFrameCost (:4050-4062).  P estimates need no pixels (one thread per block); B estimates
- * evaluate the two bidir candidates with 8 lanes per block.  Sums are integer atomics, so the
- * result does not depend on the order of accumulation.
+ * estimateFrameCost (:4050-4062).  P estimates need no pixels (cost_p_kernel, one thread per block); B estimates
+ * evaluate the two bidir candidates with 8 lanes per block (cost_group_kernel).  Sums are integer atomics, so
+ * the result does not depend on the order of accumulation.
  * ------------------------------------------------------------------------------------------ */
 template <typename P>
 struct CostJobDev
@@ -853,25 +858,9 @@ __global__ void __launch_bounds__(256) cost_clear_kernel(Geom g, const CostJobDe
     if (threadIdx.x == 0) { J.result->costEst = 0; J.result->costEstAq = 0; J.result->intraMbs = 0; J.result->reserved = 0; }
 }
 
+/* P estimate: no pixels, one thread per block (slicetype.cpp:4209-4218) */
 template <typename P>
-__device__ __forceinline__ void costEpilogue(const Geom& g, const CostJobDev<P>& J, int cu, int bcost, int listused, bool bBidir,
-                                             unsigned long long* s_acc, int* s_intra)
-{
-    const int cuX = cu % g.bw, cuY = cu / g.bw;
-    const bool scored = (cuX > 0 && cuX < g.bw - 1 && cuY > 0 && cuY < g.bh - 1) || g.bw <= 2 || g.bh <= 2;
-    const int bcostAq = (scored && J.invQ) ? ((bcost * J.invQ[cu] + 128) >> 8) : bcost;
-    if (scored)
-    {
-        atomicAdd(&s_acc[0], (unsigned long long)bcost);
-        atomicAdd(&s_acc[1], (unsigned long long)bcostAq);
-        if (!listused && !bBidir) atomicAdd(s_intra, 1);
-    }
-    atomicAdd(&J.rowSatds[cuY], bcostAq);
-    J.lowresCosts[cu] = (unsigned short)(min(bcost, LA_LOWRES_COST_MASK) | (listused << LA_LOWRES_COST_SHIFT));
-}
-
-template <typename P>
-__global__ void __launch_bounds__(128) cost_kernel(Geom g, const CostJobDev<P>* __restrict__ jobs)
+__global__ void __launch_bounds__(128) cost_p_kernel(Geom g, const CostJobDev<P>* __restrict__ jobs)
 {
     __shared__ unsigned long long s_acc[2];
     __shared__ int s_intra;
@@ -880,43 +869,23 @@ __global__ void __launch_bounds__(128) cost_kernel(Geom g, const CostJobDev<P>* 
     if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
     if (threadIdx.x == 2) s_intra = 0;
     __syncthreads();
-    if (!J.ref1)
-    {   /* P estimate: one thread per block */
-        const int cu = blockIdx.x * 128 + threadIdx.x;
-        if (cu < g.ncu)
-        {
-            int bcost = J.cost0[cu] + 4, listused = 1;      /* COST_MAX > any search cost */
-            const int ic = J.intraCost[cu];
-            if (ic < bcost) { bcost = ic; listused = 0; }
-            costEpilogue(g, J, cu, bcost, listused, false, s_acc, &s_intra);
-        }
-    }
-    else
-    {   /* B estimate: 16 blocks per CTA, warp-uniform */
-        const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-        const int cuRaw = blockIdx.x * 16 + grp;
-        const bool act = cuRaw < g.ncu;
-        const int cu = act ? cuRaw : g.ncu - 1;
+    const int cu = blockIdx.x * 128 + threadIdx.x;
+    if (cu < g.ncu)
+    {
+        int bcost = J.cost0[cu] + 4, listused = 1;      /* COST_MAX > any search cost */
+        const int ic = J.intraCost[cu];
+        if (ic < bcost) { bcost = ic; listused = 0; }
         const int cuX = cu % g.bw, cuY = cu / g.bw;
-        const int X0 = g.mx + 8 * cuX, Y0 = g.my + 8 * cuY;
-        int bcost = LA_COST_MAX, listused = 0;
-        const int c0 = J.cost0[cu], c1 = J.cost1[cu];
-        if (c0 < bcost) { bcost = c0; listused = 1; }
-        if (c1 < bcost) { bcost = c1; listused = 2; }
-        const Row<P> fenc = loadRowAligned(J.fenc0, g.tpr, X0, Y0 + r);
-        RefBlock<P> rb0 = { J.ref0, g.planeSize, g.tpr, X0, Y0 }, rb1 = { J.ref1, g.planeSize, g.tpr, X0, Y0 };
-        const MV2 m0 = unpackMv(J.mv0[cu]), m1 = unpackMv(J.mv1[cu]);
-        /* avg(L0 MC, L1 MC), unweighted references (slicetype.cpp:4189-4200) */
-        Row<P> a = avgRow(mcRow(rb0, m0.x, m0.y, r), mcRow(rb1, m1.x, m1.y, r));
-        int bicost = groupSatdRows(fenc, a);
-        if (bicost < bcost) { bcost = bicost; listused = 3; }
-        /* co-located average (:4201-4206) */
-        a = avgRow(loadRowAligned(J.ref0, g.tpr, X0, Y0 + r), loadRowAligned(J.ref1, g.tpr, X0, Y0 + r));
-        bicost = groupSatdRows(fenc, a);
-        if (bicost < bcost) { bcost = bicost; listused = 3; }
-        bcost += 4;
-        if (r == 0 && act)
-            costEpilogue(g, J, cu, bcost, listused, true, s_acc, &s_intra);
+        const bool scored = (cuX > 0 && cuX < g.bw - 1 && cuY > 0 && cuY < g.bh - 1) || g.bw <= 2 || g.bh <= 2;
+        const int bcostAq = (scored && J.invQ) ? ((bcost * J.invQ[cu] + 128) >> 8) : bcost;
+        if (scored)
+        {
+            atomicAdd(&s_acc[0], (unsigned long long)bcost);
+            atomicAdd(&s_acc[1], (unsigned long long)bcostAq);
+            if (!listused) atomicAdd(&s_intra, 1);
+        }
+        atomicAdd(&J.rowSatds[cuY], bcostAq);
+        J.lowresCosts[cu] = (unsigned short)(min(bcost, LA_LOWRES_COST_MASK) | (listused << LA_LOWRES_COST_SHIFT));
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -924,6 +893,95 @@ __global__ void __launch_bounds__(128) cost_kernel(Geom g, const CostJobDev<P>* 
         if (s_acc[0]) atomicAdd((unsigned long long*)&J.result->costEst, s_acc[0]);
         if (s_acc[1]) atomicAdd((unsigned long long*)&J.result->costEstAq, s_acc[1]);
         if (s_intra) atomicAdd(&J.result->intraMbs, s_intra);
+    }
+}
+
+/* B estimates, grouped: every (p0, p1, b) of a batch that shares b and p1 -- i.e. the same source block, the same
+ * list-1 motion compensation and the same co-located list-1 block -- is one group; a CTA loads those once and walks
+ * the group's list-0 references.  (One launch per estimate re-fetched them up to bframes times: ncu showed the
+ * load pipe and L1 as that kernel's limit.)  8 lanes per block, 16 blocks per CTA, warp-uniform. */
+#define LA_COST_GROUP_MAX 16
+
+template <typename P>
+struct CostGroupDev
+{
+    const P* fenc0; const P* ref1;          /* tiled plane-0 buffers of b and p1 */
+    const int* mv1; const int* cost1;       /* list-1 search of b towards p1 */
+    const int* intraCost; const int* invQ;
+    int n, pad;
+    struct Member
+    {
+        const P* ref0; const int* mv0; const int* cost0;        /* p0 and the list-0 search of b towards it */
+        unsigned short* lowresCosts; int* rowSatds; CostResultDev* result;
+        const int* cond;
+    } m[LA_COST_GROUP_MAX];
+};
+
+template <typename P>
+__global__ void __launch_bounds__(128) cost_group_kernel(Geom g, const CostGroupDev<P>* __restrict__ groups)
+{
+    __shared__ unsigned long long s_acc[LA_COST_GROUP_MAX][2];
+    const CostGroupDev<P>& G = groups[blockIdx.y];
+    const int n = G.n;
+    if (threadIdx.x < 2 * LA_COST_GROUP_MAX) s_acc[threadIdx.x >> 1][threadIdx.x & 1] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int cuRaw = blockIdx.x * 16 + grp;
+    const bool act = cuRaw < g.ncu;
+    const int cu = act ? cuRaw : g.ncu - 1;
+    const int cuX = cu % g.bw, cuY = cu / g.bw;
+    const int X0 = g.mx + 8 * cuX, Y0 = g.my + 8 * cuY;
+    const bool scored = (cuX > 0 && cuX < g.bw - 1 && cuY > 0 && cuY < g.bh - 1) || g.bw <= 2 || g.bh <= 2;
+    const int invQ = (scored && G.invQ) ? G.invQ[cu] : 256;
+    const Row<P> fenc = loadRowAligned(G.fenc0, g.tpr, X0, Y0 + r);
+    const int c1 = G.cost1[cu];
+    const MV2 m1 = unpackMv(G.mv1[cu]);
+    RefBlock<P> rb1 = { G.ref1, g.planeSize, g.tpr, X0, Y0 };
+    const Row<P> mc1 = mcRow(rb1, m1.x, m1.y, r);
+    const Row<P> co1 = loadRowAligned(G.ref1, g.tpr, X0, Y0 + r);
+    for (int i = 0; i < n; i++)
+    {
+        const typename CostGroupDev<P>::Member& M = G.m[i];
+        if (M.cond && __ldcg(M.cond) == 0) continue;    /* uniform for the whole CTA */
+        int bcost = LA_COST_MAX, listused = 0;
+        const int c0 = M.cost0[cu];
+        if (c0 < bcost) { bcost = c0; listused = 1; }
+        if (c1 < bcost) { bcost = c1; listused = 2; }
+        const MV2 m0 = unpackMv(M.mv0[cu]);
+        RefBlock<P> rb0 = { M.ref0, g.planeSize, g.tpr, X0, Y0 };
+        /* avg(L0 MC, L1 MC), unweighted references (slicetype.cpp:4189-4200) */
+        const Row<P> a = avgRow(mcRow(rb0, m0.x, m0.y, r), mc1);
+        /* co-located average (:4201-4206) */
+        const Row<P> b = avgRow(loadRowAligned(M.ref0, g.tpr, X0, Y0 + r), co1);
+        int bicost = groupSatdRows(fenc, a);
+        if (bicost < bcost) { bcost = bicost; listused = 3; }
+        bicost = groupSatdRows(fenc, b);
+        if (bicost < bcost) { bcost = bicost; listused = 3; }
+        bcost += 4;
+        const int bcostAq = scored ? ((bcost * invQ + 128) >> 8) : bcost;
+        const bool lead = r == 0 && act;
+        if (lead)
+        {
+            atomicAdd(&M.rowSatds[cuY], bcostAq);
+            M.lowresCosts[cu] = (unsigned short)(min(bcost, LA_LOWRES_COST_MASK) | (listused << LA_LOWRES_COST_SHIFT));
+        }
+        /* frame sums over the interior blocks: the warp's four blocks first, then one shared atomic per warp */
+        int v0 = (lead && scored) ? bcost : 0, v1 = (lead && scored) ? bcostAq : 0;
+        v0 += __shfl_xor_sync(LA_FULL, v0, 8); v1 += __shfl_xor_sync(LA_FULL, v1, 8);
+        v0 += __shfl_xor_sync(LA_FULL, v0, 16); v1 += __shfl_xor_sync(LA_FULL, v1, 16);
+        if (lane == 0 && (v0 | v1))
+        {
+            atomicAdd(&s_acc[i][0], (unsigned long long)v0);
+            atomicAdd(&s_acc[i][1], (unsigned long long)v1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n)
+    {
+        const typename CostGroupDev<P>::Member& M = G.m[threadIdx.x];
+        if (s_acc[threadIdx.x][0]) atomicAdd((unsigned long long*)&M.result->costEst, s_acc[threadIdx.x][0]);
+        if (s_acc[threadIdx.x][1]) atomicAdd((unsigned long long*)&M.result->costEstAq, s_acc[threadIdx.x][1]);
     }
 }
 
