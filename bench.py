@@ -306,14 +306,19 @@ def main():
     s_jobs = sum(d["search_jobs"] for d in deltas)
     achieved = (s_jobs * bytes_per_search / 1e9) / (s_ms / 1000.0) if s_ms > 0 else 0.0
     kernel_ms = {k: round(sum(p[k][2] for p in profs) / len(profs), 3) for k in pkg.K_NAMES}
-    traffic = None
+    # dram__bytes_read + dram__bytes_write of the kernel from the committed ncu --set full capture, scaled from that
+    # capture's job count to this run's average launch (same unit as `achieved`: per launch)
+    traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")))
-        traffic = tj.get(args.workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json"))).get(args.workload)
+        if tj and s_launch:
+            traffic = int(tj["dram_bytes_per_search_job"] * s_jobs / s_launch)
+            traffic_src = tj["source"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "search_kernel (K4 motion search)", "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": int(bytes_per_search * s_jobs / max(1, s_launch)), "peak_source": peak_src,
                 "algorithmic_bytes_per_search_job": bytes_per_search, "search_jobs_per_step": s_jobs // max(1, len(deltas)),
                 "search_launches_per_step": s_launch // max(1, len(profs)),
                 "avg_launch_ms": round(s_sum_ms / max(1, s_launch), 4),

@@ -24,10 +24,10 @@ def main(path):
                 print('%-75s %s %s' % (w, r[i][:90], units[i]))
         stalls = []
         for i, h in enumerate(hdr):
-            if 'warp_issue_stalled' in h and h.endswith('_per_warp_active.pct'):
-                try: stalls.append((float(r[i]), h.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', '')))
+            if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio'):
+                try: stalls.append((float(r[i]), h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')))
                 except ValueError: pass
         stalls.sort(reverse=True)
-        print('stall reasons (% of warp-active cycles): ' + ', '.join('%s %.1f' % (n, v) for v, n in stalls[:10]))
+        print('stalled warps per issue-active cycle, by reason: ' + ', '.join('%s %.2f' % (n, v) for v, n in stalls[:8]))
 if __name__ == '__main__':
     main(sys.argv[1])
