@@ -149,6 +149,10 @@ def main():
     ap.add_argument("--async-depth", type=int, default=16,
                     help="extra frames of input delay (LookaheadParam::asyncDepth): same decisions, GPU slack")
     ap.add_argument("--speculate", type=int, default=1)
+    ap.add_argument("--shard", default="streams", choices=["streams", "window"],
+                    help="N > 1: 'streams' = one independent stream per GPU (weak scaling, no data-path collective); "
+                         "'window' = ONE stream whose searches / estimates are split over the GPUs by source frame, "
+                         "stores exchanged by NCCL broadcast after every batch (strong scaling)")
     ap.add_argument("--pending-max", type=int, default=16)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -176,7 +180,8 @@ def main():
 
     F = wl["frames"]
     depth, W, H = wl["depth"], wl["width"], wl["height"]
-    frames = gen_frames(wl, F, seed_offset=rank)
+    window = args.shard == "window" and world > 1
+    frames = gen_frames(wl, F, seed_offset=0 if window else rank)
     tdt = torch.uint8 if depth == 8 else torch.int16      # int16 views of the uint16 samples (bytes are what matter)
 
     def to_t(a):
@@ -187,12 +192,19 @@ def main():
     torch.cuda.synchronize()
     bytes_in = sum(t.numel() * t.element_size() for t in host[0])
 
-    la_kw = dict(wl["la"], asyncDepth=args.async_depth, speculate=args.speculate, pendingMax=args.pending_max)
+    la_kw = dict(wl["la"], asyncDepth=args.async_depth, speculate=args.speculate, pendingMax=args.pending_max,
+                 device=local_rank)
+    exchange = None
+    if window:
+        la_kw["shardCount"] = world
+        exchange = shard.make_exchange(dist, pkg.EXCHANGE_FN, cuda=True)
     geom = {}
 
     def one_step(pics, fetch_results):
         """returns (device ms, decided types, counters delta, profile)"""
         la = pkg.Lookahead(W, H, depth=depth, **la_kw)
+        if window:
+            la.shard(rank, world, exchange)
         g = la.geom
         geom.update(ncu=g.ncu, bw=g.bw, bh=g.bh, low_w=g.low_width, low_h=g.low_height)
         ctx = la.engine()
@@ -284,9 +296,10 @@ def main():
     clocks = sampler.stop()
 
     ms_step = float(np.mean(times))
-    value = world * F / (ms_step / 1000.0)
+    n_streams = 1 if window else world
+    value = n_streams * F / (ms_step / 1000.0)
     e2e_ms = float(np.mean(e2e_times))
-    e2e_value = world * F / (e2e_ms / 1000.0)
+    e2e_value = n_streams * F / (e2e_ms / 1000.0)
 
     # --- roofline of the dominant kernel (K4, motion search) ---------------------------------------------
     peaks = {}
@@ -330,9 +343,12 @@ def main():
 
     line = {"metric": "lookahead_frames_per_s", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u16" if depth > 8 else "u8", "data": "synthetic",
+            "scaling": "strong" if window else "weak", "vs_baseline": None, "dtype": "u16" if depth > 8 else "u8", "data": "synthetic",
             "config": {"workload": wl["text"], "frames_per_step": F, "resolution": "%dx%d" % (W, H), "bit_depth": depth,
-                       "lookahead_slices": 0, "async_depth": args.async_depth, "speculate": args.speculate, "streams": world, "parallelism": "independent stream per GPU" if world > 1 else "1 GPU",
+                       "lookahead_slices": 0, "async_depth": args.async_depth, "speculate": args.speculate, "streams": n_streams,
+                       "parallelism": ("one stream, searches/estimates split by source frame over %d GPUs, NCCL broadcast of the "
+                                       "stores per batch" % world) if window else
+                                      ("independent stream per GPU" if world > 1 else "1 GPU"),
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * bytes_in // (1 << 20))},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(e2e_delta["h2d"]), "d2h_bytes_per_step": int(e2e_delta["d2h"])},

@@ -111,6 +111,19 @@ int  x265cu_frame_stats_get(x265cu_ctx* ctx, const int32_t* slots, int32_t n, x2
 int  x265cu_batch_begin(x265cu_ctx* ctx, int64_t* batch_id /* may be NULL */);
 int  x265cu_batch_end(x265cu_ctx* ctx);
 
+/* ---- one stream sharded over several GPUs (SURVEY 8e level 2): every (frame, list, distance) search and every
+ * (p0, p1, b) estimate depends only on pixels, so the ranks of a job split them by source frame.  Every rank runs the
+ * same host logic on the same pictures and holds every frame; a rank only COMPUTES the search / cost jobs of the
+ * frames it owns (x265cu_slot_owner), and at the end of each batch the MV / cost stores written by their owners are
+ * exchanged so that every rank holds all of them (what cuTree and the decisions read afterwards is then identical
+ * everywhere; rank 0's output is the product).  The engine packs what it owns, calls `exchange` once per batch and
+ * unpacks the rest; the callback provides the collective (NCCL broadcasts through torch.distributed in bench.py, gloo
+ * in the CPU tests): for every root r with bytes[r] > 0 it must make bufs[r] on every rank equal rank r's bufs[r],
+ * ordered on `cuda_stream` (a cudaStream_t).  All ranks call it with the same bytes[].  Returns 0 on success. */
+typedef int (*x265cu_exchange_fn)(void* user, void* const* bufs, const uint64_t* bytes, int32_t nranks, void* cuda_stream);
+int  x265cu_shard_config(x265cu_ctx* ctx, int32_t rank, int32_t nranks /* <= 8 */, x265cu_exchange_fn exchange, void* user);
+int  x265cu_slot_owner(x265cu_ctx* ctx, int32_t slot, int32_t owner_rank);
+
 /* ---- motion search: the search half of CostEstimateGroup::estimateCUCost (slicetype.cpp:
  * 4103-4183) + MotionEstimate::motionEstimate (motion.cpp:764-1594, HEX + lowres subpel) for one
  * (frame, list, distance) over the whole frame, reverse-raster dependency order preserved. */

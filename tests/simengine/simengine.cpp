@@ -40,7 +40,47 @@ struct x265cu_ctx
     std::vector<or_pixel> wbuf;
     x265cu_counters counters;
     char err[64];
+    /* sharded stream (x265cu_shard_config): same protocol as the CUDA engine, host memory instead of HBM */
+    int rank, nranks;
+    x265cu_exchange_fn exchange; void* exchangeUser;
+    std::vector<int> owner;
+    struct Seg { void* ptr; size_t bytes; int root; };
+    std::vector<Seg> segs;
+    std::vector<char> xbuf[8];
 };
+
+static bool simMine(const x265cu_ctx* c, int slot) { return c->nranks <= 1 || c->owner[slot] == c->rank; }
+static void simSeg(x265cu_ctx* c, void* p, size_t bytes, int slot)
+{
+    if (c->nranks <= 1) return;
+    x265cu_ctx::Seg s = { p, bytes, c->owner[slot] };
+    c->segs.push_back(s);
+}
+static int simExchange(x265cu_ctx* c)
+{
+    if (c->nranks <= 1 || c->segs.empty()) return 0;
+    uint64_t total[8] = { 0 };
+    for (size_t i = 0; i < c->segs.size(); i++) total[c->segs[i].root] += c->segs[i].bytes;
+    void* bufs[8];
+    for (int r = 0; r < 8; r++) { c->xbuf[r].resize(total[r] ? total[r] : 1); bufs[r] = &c->xbuf[r][0]; }
+    size_t off[8] = { 0 };
+    for (size_t i = 0; i < c->segs.size(); i++)
+    {
+        const x265cu_ctx::Seg& s = c->segs[i];
+        if (s.root == c->rank) memcpy(&c->xbuf[s.root][off[s.root]], s.ptr, s.bytes);
+        off[s.root] += s.bytes;
+    }
+    if (c->exchange(c->exchangeUser, bufs, total, c->nranks, NULL) != 0) return X265CU_ERR_CUDA;
+    memset(off, 0, sizeof(off));
+    for (size_t i = 0; i < c->segs.size(); i++)
+    {
+        const x265cu_ctx::Seg& s = c->segs[i];
+        if (s.root != c->rank) memcpy(s.ptr, &c->xbuf[s.root][off[s.root]], s.bytes);
+        off[s.root] += s.bytes;
+    }
+    c->segs.clear();
+    return 0;
+}
 
 extern "C" {
 
@@ -62,6 +102,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     c->geom.margin_x = c->g.mx; c->geom.margin_y = c->g.my; c->geom.nb = cfg->bframes + 2;
     c->geom.n_mv_stores = 3 * c->geom.nb; c->geom.n_cost_stores = 2 * c->geom.nb * c->geom.nb;
     c->slots.resize(cfg->max_slots);
+    c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL; c->owner.assign(cfg->max_slots, 0);
     memset(&c->counters, 0, sizeof(c->counters));
     *out = c;
     return 0;
@@ -77,6 +118,13 @@ int x265cu_timer_stop(x265cu_ctx*, double* ms) { *ms = 0; return 0; }
 int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return 0; }
 int x265cu_batch_begin(x265cu_ctx*, int64_t* id) { static int64_t n = 0; if (id) *id = n++; return 0; }
 int x265cu_batch_end(x265cu_ctx*) { return 0; }
+int x265cu_shard_config(x265cu_ctx* c, int32_t rank, int32_t nranks, x265cu_exchange_fn fn, void* user)
+{
+    if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks || (nranks > 1 && !fn)) return X265CU_ERR_BAD_ARG;
+    c->rank = rank; c->nranks = nranks; c->exchange = fn; c->exchangeUser = user;
+    return 0;
+}
+int x265cu_slot_owner(x265cu_ctx* c, int32_t slot, int32_t owner) { c->owner[slot] = owner; return 0; }
 int x265cu_frame_ready(x265cu_ctx*, int32_t slot) { return (slot % 3) != 1; }   /* exercise both answers */
 int x265cu_profile_get_busy(x265cu_ctx*, double* ms) { for (int i = 0; i < X265CU_K_COUNT; i++) ms[i] = 0; return 0; }
 int x265cu_profile_enable(x265cu_ctx*, int32_t) { return 0; }
@@ -138,6 +186,11 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
     {
         const x265cu_search_job& j = jobs[i];
         SimSlot& f = c->slots[j.fenc_slot]; SimSlot& r = c->slots[j.ref_slot];
+        f.mvs[j.store].resize(2 * g.ncu); f.mvCosts[j.store].resize(g.ncu);
+        simSeg(c, &f.mvs[j.store][0], 2 * g.ncu * sizeof(int32_t), j.fenc_slot);
+        simSeg(c, &f.mvCosts[j.store][0], g.ncu * sizeof(int32_t), j.fenc_slot);
+        simSeg(c, &f.skipFlag[j.store], sizeof(int32_t), j.fenc_slot);
+        if (!simMine(c, j.fenc_slot)) continue;
         if (j.cond_store >= 0 && !f.skipFlag[j.cond_store]) continue;     /* conditional job, x265cu.h */
         c->counters.search_jobs++;
         const or_pixel* rp[4];
@@ -154,7 +207,7 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
                        &f.mvs[j.store][0], &f.mvCosts[j.store][0], &f.skipFlag[j.store]);
         c->counters.kernel_launches++;
     }
-    return 0;
+    return simExchange(c);
 }
 
 int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* stores, int32_t n, int32_t* flags)
@@ -170,6 +223,11 @@ int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
     {
         const x265cu_cost_job& j = jobs[i];
         SimSlot& b = c->slots[j.b_slot]; SimSlot& p0 = c->slots[j.p0_slot]; SimSlot& p1 = c->slots[j.p1_slot];
+        b.costs[j.out].resize(g.ncu); b.rowSatds[j.out].resize(g.bh);
+        simSeg(c, &b.costs[j.out][0], g.ncu * sizeof(uint16_t), j.b_slot);
+        simSeg(c, &b.rowSatds[j.out][0], g.bh * sizeof(int32_t), j.b_slot);
+        simSeg(c, &b.results[j.out], sizeof(x265cu_cost_result), j.b_slot);
+        if (!simMine(c, j.b_slot)) continue;
         if (j.cond_store >= 0 && !b.skipFlag[j.cond_store]) continue;
         c->counters.cost_jobs++;
         const or_pixel *r0[4], *r1[4];
@@ -184,7 +242,7 @@ int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
                       &res.cost_est, &res.cost_est_aq, &res.intra_mbs);
         c->counters.kernel_launches++;
     }
-    return 0;
+    return simExchange(c);
 }
 
 int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* outs, int32_t n, x265cu_cost_result* res)

@@ -186,3 +186,61 @@ def test_full_size_properties(depth, w, h, pkg, synth, simdir):
         want = _as_ref_layout(pkg.run_sequence(pkg.Lookahead(w, h, depth=depth, lib_path=_sim(simdir, depth), **kw), iter(frames), planes=False))
         bad = compare.compare_runs(want, a, check_planes=False)
         assert not bad, "\n".join(bad[:10])
+
+
+def _gpu_shard_worker(rank, world, port, q, case_name):
+    import sys
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests")):
+        sys.path.insert(0, p)
+    import importlib.util, pickle
+    import torch
+    import _pkg
+    import cases as cs
+    torch.cuda.set_device(rank)
+    pkg_ = _pkg.load_pkg(); synth_ = _pkg.load_synth()
+    spec = importlib.util.spec_from_file_location("shard", os.path.join(root, "x265-amod_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec); spec.loader.exec_module(shard)
+    dist = shard.init("nccl")
+    case = cs.get_case(case_name)
+    name, depth, w, h, n, skw, rkw = case
+    seq = cs.make_seq(synth_, case)
+    la = pkg_.Lookahead(w, h, depth=depth, shardCount=world, device=rank, asyncDepth=6, **cs.la_kwargs(rkw))
+    la.shard(rank, world, shard.make_exchange(dist, pkg_.EXCHANGE_FN, cuda=True))
+    out = pkg_.run_sequence(la, (seq.frame(i) for i in range(n)), planes=False)
+    la.close()
+    dist.barrier()
+    q.put((rank, pickle.dumps(out)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case_name", ["base8", "static_noise", "fade8"])
+def test_cuda_one_stream_sharded_over_two_gpus(case_name, pkg, synth):
+    """SURVEY 8e level 2 on hardware: two ranks, two GPUs, NCCL broadcasts of the stores after every batch; both ranks
+    must publish the golden / reference state bit for bit."""
+    import pickle
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gpu_shard_worker, args=(r, 2, port, q, case_name)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    case = cases.get_case(case_name)
+    if refbind.available(case[1]):
+        want = cases.run_reference(refbind, synth, case, planes=False)
+    else:
+        want = golden_io.load(case_name)
+    for rank, blob in res:
+        got = pickle.loads(blob)
+        bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1))
+        assert not bad, "rank %d:\n%s" % (rank, "\n".join(bad[:10]))

@@ -61,3 +61,64 @@ def test_two_ranks_shard_streams(simdir):
     la = pkg.Lookahead(176, 144, depth=8, lib_path=os.path.join(simdir, "libx265la_sim8.so"), bframes=3, lookaheadDepth=8)
     out = pkg.run_sequence(la, (seq.frame(i) for i in range(16)), collect=False)
     assert [f["sliceType"] for f in out] == t1[1]
+
+
+def _shard_worker(rank, world, port, simdir, q, case_name, extra):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import importlib.util
+    import _pkg
+    import cases
+    pkg = _pkg.load_pkg(); synth = _pkg.load_synth()
+    spec = importlib.util.spec_from_file_location("shard", os.path.join(ROOT, "x265-amod_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec); spec.loader.exec_module(shard)
+    dist = shard.init("gloo")
+    case = cases.get_case(case_name)
+    name, depth, w, h, n, skw, rkw = case
+    seq = cases.make_seq(synth, case)
+    kw = cases.la_kwargs(rkw); kw.update(extra)
+    la = pkg.Lookahead(w, h, depth=depth, lib_path=os.path.join(simdir, "libx265la_sim%d.so" % depth), shardCount=world, **kw)
+    la.shard(rank, world, shard.make_exchange(dist, pkg.EXCHANGE_FN, cuda=False))
+    out = pkg.run_sequence(la, (seq.frame(i) for i in range(n)), planes=False)
+    cnt = pkg.Counters()
+    la.lib.x265cu_get_counters.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").POINTER(pkg.Counters)]
+    la.lib.x265cu_get_counters(la.engine(), __import__("ctypes").byref(cnt))
+    la.close()
+    dist.barrier()
+    import pickle
+    q.put((rank, pickle.dumps(out), int(cnt.search_jobs), int(cnt.cost_jobs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case_name,extra", [("base8", {}), ("static_noise", dict(asyncDepth=5)), ("fade8", dict(speculate=2))])
+def test_two_ranks_shard_one_stream(case_name, extra, simdir):
+    """SURVEY 8e level 2: one stream, searches / estimates split by source frame over two ranks, stores exchanged after
+    every batch (gloo here, NCCL on the GPU box).  Both ranks must publish exactly what a single rank publishes (the
+    golden fixture), and each must have computed only its share of the jobs."""
+    import pickle
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases, compare, golden_io
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, simdir, q, case_name, extra)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    case = cases.get_case(case_name)
+    want = golden_io.load(case_name)
+    jobs = []
+    for rank, blob, nsearch, ncost in res:
+        got = pickle.loads(blob)
+        bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1))
+        assert not bad, "rank %d:\n%s" % (rank, "\n".join(bad[:10]))
+        jobs.append((nsearch, ncost))
+    # the work really was split: neither rank did (nearly) all of it
+    tot_s = jobs[0][0] + jobs[1][0]; tot_c = jobs[0][1] + jobs[1][1]
+    assert min(jobs[0][0], jobs[1][0]) > 0.3 * tot_s and min(jobs[0][1], jobs[1][1]) > 0.3 * tot_c, jobs

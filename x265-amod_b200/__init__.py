@@ -35,7 +35,7 @@ class LaParam(C.Structure):
                 ("qgSize", C.c_int32), ("vbvBufferSize", C.c_int32), ("vbvMaxBitrate", C.c_int32),
                 ("rateControlMode", C.c_int32), ("poolWorkers", C.c_int32), ("device", C.c_int32),
                 ("extraSlots", C.c_int32), ("speculate", C.c_int32), ("pinHost", C.c_int32),
-                ("asyncDepth", C.c_int32), ("pendingMax", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("asyncDepth", C.c_int32), ("pendingMax", C.c_int32), ("shardCount", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class FrameInfo(C.Structure):
@@ -54,6 +54,9 @@ class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("search_jobs", C.c_uint64), ("cost_jobs", C.c_uint64)]
 
+
+# x265cu_exchange_fn (include/x265cu.h): user, bufs[nranks], bytes[nranks], nranks, cuda stream
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int32, C.c_void_p)
 
 K_NAMES = ["lowres", "aq", "intra", "search", "cost", "weight", "cutree"]
 
@@ -96,6 +99,7 @@ def load_lib(path=None):
     lib.x265la_get_timers.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int32]
     lib.x265la_engine.restype = C.c_void_p
     lib.x265la_engine.argtypes = [C.c_void_p]
+    lib.x265la_shard_config.argtypes = [C.c_void_p, C.c_int32, C.c_int32, EXCHANGE_FN, C.c_void_p]
     _libs[path] = lib
     return lib
 
@@ -129,7 +133,7 @@ def make_param(width, height, depth=8, **kw):
              keyframeMax=250, keyframeMin=0, bOpenGOP=1, bIntraRefresh=0, bEnableWeightedPred=1,
              bEnableWeightedBiPred=0, lookaheadSlices=0, maxNumReferences=3, aqMode=2, aqStrength=1.0,
              cuTree=1, qCompress=0.6, qgSize=32, vbvBufferSize=0, vbvMaxBitrate=0, rateControlMode=2,
-             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0)
+             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0, shardCount=0)
     d.update(kw)
     lib_defaults.sourceWidth, lib_defaults.sourceHeight = width, height
     for k, v in d.items():
@@ -240,6 +244,12 @@ class Lookahead:
 
     def engine(self):
         return self.lib.x265la_engine(self.h)
+
+    def shard(self, rank, nranks, exchange):
+        """One stream over several ranks (open with shardCount=nranks): `exchange` is an EXCHANGE_FN, see shard.py."""
+        self._exchange = exchange      # keep the ctypes thunk alive
+        if self.lib.x265la_shard_config(self.h, rank, nranks, exchange, None) != 0:
+            raise RuntimeError("x265la_shard_config failed: %s" % self.lib.x265la_last_error(self.h).decode())
 
     def close(self):
         if self.h:

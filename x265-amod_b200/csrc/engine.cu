@@ -45,7 +45,7 @@ inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
-enum { LA_NUM_LANES = 16, LA_NUM_BATCHES = 48 };
+enum { LA_NUM_LANES = 16, LA_NUM_BATCHES = 48, LA_MAX_RANKS = 8 };
 
 /* One asynchronous batch of search / cost jobs (x265cu_batch_begin ... x265cu_batch_end).  Everything a batch's
  * kernels read besides the frame slots is private to it, so batches never wait for each other's buffers. */
@@ -61,6 +61,10 @@ struct Batch
     std::vector<char*> weightScratch;   /* 4 weighted planes each */
     std::vector<void*> retiredDev, retiredHost; /* outgrown buffers, freed when the object is reused */
     std::vector<long long> waited;      /* batches this one already waits for */
+    /* sharded stream: stores written in this batch (by their owners), exchanged at batch_end */
+    struct Seg { char* ptr; size_t bytes; int root; };
+    std::vector<Seg> segs;
+    char* xbuf[LA_MAX_RANKS]; size_t xcap[LA_MAX_RANKS];
 };
 
 struct x265cu_ctx
@@ -93,6 +97,9 @@ struct x265cu_ctx
     std::vector<char*> mainScratch;           /* weighted plane for x265cu_weight_cost_batch (main stream) */
     x265cu_counters counters;
     uint64_t searchEnq, costEnq;    /* jobs enqueued (conditional ones included) */
+    int rank, nranks;               /* sharded stream (x265cu_shard_config); nranks 1 = not sharded */
+    x265cu_exchange_fn exchange; void* exchangeUser;
+    std::vector<int> slotOwner;
     int searchWorkers;              /* worker warps per search job; 0 = default (env X265CU_SEARCH_WORKERS, for tuning) */
     bool profile;
     double profMs[X265CU_K_COUNT], profBusy[X265CU_K_COUNT];
@@ -114,6 +121,15 @@ bool cudaOk(x265cu_ctx* c, cudaError_t e, const char* what)
     return false;
 }
 #define CK(call) do { if (!cudaOk(c, (call), #call)) return X265CU_ERR_CUDA; } while (0)
+
+/* Every entry point runs with the context's GPU current and puts the caller's back afterwards (a process may drive
+ * several GPUs, and the caller -- torch, an encoder with its own CUDA code -- has its own idea of the current device) */
+struct DeviceScope
+{
+    int prev, want;
+    explicit DeviceScope(const x265cu_ctx* c);
+    ~DeviceScope() { if (prev != want && prev >= 0) cudaSetDevice(prev); }
+};
 
 /* Brackets the launches of one kernel family with a pair of CUDA events on the launching stream.
  * Nothing blocks here; the pairs are resolved when the caller asks for the totals. */
@@ -181,6 +197,13 @@ void resolveProfile(x265cu_ctx* c)
     c->evUsed = 0;
 }
 
+DeviceScope::DeviceScope(const x265cu_ctx* c) : prev(-1), want(c ? c->cfg.device : -1)
+{
+    if (want < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) cudaSetDevice(want);
+}
+
 template <typename T> T* slotPtr(x265cu_ctx* c, int slot, size_t off) { return (T*)(c->slots[slot] + off); }
 
 int ensureDev(x265cu_ctx* c, char** p, size_t* cap, size_t need)
@@ -214,12 +237,53 @@ Batch* batchOf(x265cu_ctx* c, long long id)
     return b->id == id ? b : NULL;      /* NULL: the object was reused, i.e. batch `id` finished long ago */
 }
 
+/* sharded stream: every store written in this batch travels from its owner to all the other ranks */
+int exchangeBatch(x265cu_ctx* c, Batch* b)
+{
+    if (c->nranks <= 1 || b->segs.empty()) { b->segs.clear(); return X265CU_OK; }
+    if (!c->exchange) { snprintf(c->err, sizeof(c->err), "sharded stream without an exchange callback"); return X265CU_ERR_BAD_ARG; }
+    uint64_t total[LA_MAX_RANKS] = { 0 };
+    for (size_t i = 0; i < b->segs.size(); i++) total[b->segs[i].root] += alignUp(b->segs[i].bytes, 256);
+    for (int r = 0; r < c->nranks; r++)
+        if (total[r] > b->xcap[r])
+        {
+            if (b->xbuf[r]) b->retiredDev.push_back(b->xbuf[r]);
+            b->xbuf[r] = NULL;
+            b->xcap[r] = alignUp(total[r] * 3 / 2, 4096);
+            CK(cudaMalloc((void**)&b->xbuf[r], b->xcap[r]));
+        }
+    size_t off[LA_MAX_RANKS] = { 0 };
+    for (size_t i = 0; i < b->segs.size(); i++)
+    {
+        const Batch::Seg& s = b->segs[i];
+        if (s.root == c->rank)
+            CK(cudaMemcpyAsync(b->xbuf[s.root] + off[s.root], s.ptr, s.bytes, cudaMemcpyDeviceToDevice, b->stream));
+        off[s.root] += alignUp(s.bytes, 256);
+    }
+    void* bufs[LA_MAX_RANKS];
+    for (int r = 0; r < LA_MAX_RANKS; r++) bufs[r] = b->xbuf[r];
+    if (c->exchange(c->exchangeUser, bufs, total, c->nranks, (void*)b->stream) != 0)
+    { snprintf(c->err, sizeof(c->err), "exchange callback failed"); return X265CU_ERR_CUDA; }
+    memset(off, 0, sizeof(off));
+    for (size_t i = 0; i < b->segs.size(); i++)
+    {
+        const Batch::Seg& s = b->segs[i];
+        if (s.root != c->rank)
+            CK(cudaMemcpyAsync(s.ptr, b->xbuf[s.root] + off[s.root], s.bytes, cudaMemcpyDeviceToDevice, b->stream));
+        off[s.root] += alignUp(s.bytes, 256);
+    }
+    b->segs.clear();
+    return X265CU_OK;
+}
+
 int endBatch(x265cu_ctx* c)
 {
     if (!c->cur) return X265CU_OK;
     Batch* b = c->cur;
     c->cur = NULL;
     b->open = false;
+    int st = exchangeBatch(c, b);
+    if (st) return st;
     CK(cudaEventRecord(b->done, b->stream));
     return X265CU_OK;
 }
@@ -297,7 +361,8 @@ int mainWaitBatch(x265cu_ctx* c, long long id, bool searchesOnly)
 }
 int mainWaitMv(x265cu_ctx* c, int slot, int store)
 {
-    return store < 0 ? X265CU_OK : mainWaitBatch(c, c->mvWriter[(size_t)slot * c->geom.n_mv_stores + store], true);
+    /* sharded stream: the MVs of a frame another rank owns arrive with the exchange at the end of the batch */
+    return store < 0 ? X265CU_OK : mainWaitBatch(c, c->mvWriter[(size_t)slot * c->geom.n_mv_stores + store], c->nranks <= 1);
 }
 int mainWaitCost(x265cu_ctx* c, int slot, int store)
 {
@@ -442,12 +507,23 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
     SearchJobDev<P>* dev = (SearchJobDev<P>*)hst;
     /* weighted references: one scratch set per distinct (ref, weight) in this call */
     std::map<std::vector<int>, int> wmap;
-    for (int i = 0; i < n; i++)
+    const int nAll = n;
+    int nm = 0;         /* jobs this rank computes (all of them unless the stream is sharded) */
+    for (int i = 0; i < nAll; i++)
     {
         const x265cu_search_job& j = jobs[i];
         if (!slotOk(c, j.fenc_slot) || !slotOk(c, j.ref_slot) || j.store < 0 || j.store >= c->geom.n_mv_stores ||
             j.cond_store >= c->geom.n_mv_stores)
         { snprintf(c->err, sizeof(c->err), "search job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
+        char* ms = mvStorePtr(c, j.fenc_slot, j.store);
+        touchSlot(c, j.fenc_slot, b->id); touchSlot(c, j.ref_slot, b->id);
+        c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.store] = b->id;
+        if (c->nranks > 1)
+        {
+            Batch::Seg sg = { ms, (size_t)g.ncu * 8 + 4, c->slotOwner[j.fenc_slot] };
+            b->segs.push_back(sg);
+            if (sg.root != c->rank) continue;
+        }
         const P* refBuf = slotPtr<P>(c, j.ref_slot, L.planes);
         if (j.weighted)
         {
@@ -468,23 +544,27 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
                 idx = it->second;
             refBuf = (const P*)b->weightScratch[idx];
         }
-        dev[i].fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes);
-        dev[i].ref0 = refBuf;
-        char* ms = mvStorePtr(c, j.fenc_slot, j.store);
-        dev[i].mvOut = (int*)ms;
-        dev[i].costOut = (int*)ms + g.ncu;
-        dev[i].flagOut = (int*)ms + 2 * g.ncu;
-        dev[i].cond = NULL;
+        SearchJobDev<P>& D = dev[nm++];
+        D.fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes);
+        D.ref0 = refBuf;
+        D.mvOut = (int*)ms;
+        D.costOut = (int*)ms + g.ncu;
+        D.flagOut = (int*)ms + 2 * g.ncu;
+        D.cond = NULL;
         if (j.cond_store >= 0)
         {
-            dev[i].cond = (const int*)mvStorePtr(c, j.fenc_slot, j.cond_store) + 2 * g.ncu;
+            D.cond = (const int*)mvStorePtr(c, j.fenc_slot, j.cond_store) + 2 * g.ncu;
             st = batchWaitSearches(c, b, c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.cond_store]);
             if (st) return st;
         }
-        dev[i].bidir = j.bidir_ctx;
-        dev[i].pad = 0;
-        touchSlot(c, j.fenc_slot, b->id); touchSlot(c, j.ref_slot, b->id);
-        c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.store] = b->id;
+        D.bidir = j.bidir_ctx;
+        D.pad = 0;
+    }
+    n = nm;
+    if (!n)
+    {
+        CK(cudaEventRecord(b->searchDone, b->stream));
+        return implicit ? endBatch(c) : X265CU_OK;
     }
     const int nstrips = (g.bh + LA_STRIP_ROWS - 1) / LA_STRIP_ROWS;      /* strips of 4 rows, one warp each */
     c->searchEnq += n;
@@ -521,16 +601,32 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
     /* P estimates (one thread per block) first, then B estimates (8 lanes per block): two launches with the
      * grid each needs */
     CostJobDev<P>* dev = (CostJobDev<P>*)hst;
-    int nP = 0;
-    for (int i = 0; i < n; i++) nP += jobs[i].l1_store < 0;
+    const int nAll = n;
+    int nP = 0, nMine = 0;
+    for (int i = 0; i < nAll; i++)
+    {
+        if (!slotOk(c, jobs[i].b_slot)) { snprintf(c->err, sizeof(c->err), "cost job %d: bad slot", i); return X265CU_ERR_BAD_ARG; }
+        const bool mine = c->nranks <= 1 || c->slotOwner[jobs[i].b_slot] == c->rank;
+        nMine += mine;
+        nP += mine && jobs[i].l1_store < 0;
+    }
     int iP = 0, iB = nP;
     const int nmv = c->geom.n_mv_stores;
-    for (int i = 0; i < n; i++)
+    for (int i = 0; i < nAll; i++)
     {
         const x265cu_cost_job& j = jobs[i];
         if (!slotOk(c, j.b_slot) || !slotOk(c, j.p0_slot) || !slotOk(c, j.p1_slot) || j.out < 2 || j.out >= c->geom.n_cost_stores ||
             j.l0_store < 0 || j.l0_store >= nmv || j.l1_store >= nmv || j.cond_store >= nmv)
         { snprintf(c->err, sizeof(c->err), "cost job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
+        char* cs = costStorePtr(c, j.b_slot, j.out);
+        touchSlot(c, j.b_slot, b->id); touchSlot(c, j.p0_slot, b->id); touchSlot(c, j.p1_slot, b->id);
+        c->costWriter[(size_t)j.b_slot * c->geom.n_cost_stores + j.out] = b->id;
+        if (c->nranks > 1)
+        {
+            Batch::Seg sg = { cs, L.costResOff + sizeof(CostResultDev), c->slotOwner[j.b_slot] };
+            b->segs.push_back(sg);
+            if (sg.root != c->rank) continue;
+        }
         CostJobDev<P>& d = dev[j.l1_store < 0 ? iP++ : iB++];
         d.fenc0 = slotPtr<P>(c, j.b_slot, L.planes);
         d.ref0 = slotPtr<P>(c, j.p0_slot, L.planes);
@@ -556,13 +652,12 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         }
         d.intraCost = slotPtr<int>(c, j.b_slot, L.intraCost);
         d.invQ = c->cfg.need_aq ? slotPtr<int>(c, j.b_slot, L.invQ) : NULL;
-        char* cs = costStorePtr(c, j.b_slot, j.out);
         d.lowresCosts = (unsigned short*)cs;
         d.rowSatds = (int*)(cs + L.costRowOff);
         d.result = (CostResultDev*)(cs + L.costResOff);
-        touchSlot(c, j.b_slot, b->id); touchSlot(c, j.p0_slot, b->id); touchSlot(c, j.p1_slot, b->id);
-        c->costWriter[(size_t)j.b_slot * c->geom.n_cost_stores + j.out] = b->id;
     }
+    n = nMine;
+    if (!n) return implicit ? endBatch(c) : X265CU_OK;
     c->costEnq += n;
     /* B estimates that share the source frame and the list-1 search form one group (cost_group_kernel) */
     std::vector<CostGroupDev<P> > groups;
@@ -727,7 +822,18 @@ const char* x265cu_strerror(int s)
 
 const char* x265cu_last_error(const x265cu_ctx* c) { return c ? c->err : ""; }
 
+static int createImpl(const x265cu_config* cfg, x265cu_ctx** out);
+
 int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
+{
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    const int rc = createImpl(cfg, out);
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
 {
     if (!cfg || !out) return X265CU_ERR_BAD_ARG;
     *out = NULL;
@@ -744,6 +850,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->h_stats = NULL; c->hStatsCap = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
+    c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
     c->stream = c->copyStream = c->auxStream = c->preStream = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
     for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
     for (int i = 0; i < LA_NUM_BATCHES; i++)
@@ -751,6 +858,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
         Batch& b = c->batches[i];
         b.id = -1; b.stream = NULL; b.begun = b.searchDone = b.done = NULL; b.open = false;
         b.h_stage = b.d_stage = NULL; b.stageCap = b.stageUsed = 0; b.d_sync = NULL; b.syncCap = b.syncUsed = 0;
+        for (int r = 0; r < LA_MAX_RANKS; r++) { b.xbuf[r] = NULL; b.xcap[r] = 0; }
     }
     memset(&c->counters, 0, sizeof(c->counters)); memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN));
     memset(c->profBusy, 0, sizeof(c->profBusy));
@@ -836,6 +944,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
         cudaEventCreateWithFlags(&e0, cudaEventDisableTiming); cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
         c->slotCopied.push_back(e0); c->slotConsumed.push_back(e1);
         c->slotUsers.push_back(std::vector<long long>());
+        c->slotOwner.push_back(0);
         c->slotMainTouched.push_back(0);
         /* planes must start zeroed: columns past the right margin are never written (K1) */
         if (cudaMemsetAsync(p, 0, L.total, c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
@@ -855,6 +964,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 
 void x265cu_destroy(x265cu_ctx* c)
 {
+    DeviceScope deviceScope(c);
     if (!c) return;
     syncAll(c);
     for (size_t i = 0; i < c->slots.size(); i++) cudaFree(c->slots[i]);
@@ -868,6 +978,7 @@ void x265cu_destroy(x265cu_ctx* c)
         for (size_t k = 0; k < b.retiredDev.size(); k++) cudaFree(b.retiredDev[k]);
         for (size_t k = 0; k < b.retiredHost.size(); k++) cudaFreeHost(b.retiredHost[k]);
         cudaFree(b.d_stage); cudaFree(b.d_sync);
+        for (int r = 0; r < LA_MAX_RANKS; r++) cudaFree(b.xbuf[r]);
         if (b.h_stage) cudaFreeHost(b.h_stage);
         if (b.begun) cudaEventDestroy(b.begun);
         if (b.searchDone) cudaEventDestroy(b.searchDone);
@@ -892,11 +1003,13 @@ int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* out) { if (!c || !
 
 int x265cu_pin_host(x265cu_ctx* c, void* ptr, uint64_t bytes)
 {
+    DeviceScope deviceScope(c);
     CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
     return X265CU_OK;
 }
 int x265cu_unpin_host(x265cu_ctx* c, void* ptr)
 {
+    DeviceScope deviceScope(c);
     CK(cudaHostUnregister(ptr));
     return X265CU_OK;
 }
@@ -913,6 +1026,7 @@ static int mainJoinBatches(x265cu_ctx* c)
 
 int x265cu_sync(x265cu_ctx* c)
 {
+    DeviceScope deviceScope(c);
     int st = endBatch(c);
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream)); CK(cudaStreamSynchronize(c->preStream)); CK(cudaStreamSynchronize(c->stream));
@@ -923,19 +1037,49 @@ int x265cu_sync(x265cu_ctx* c)
 
 int x265cu_batch_begin(x265cu_ctx* c, int64_t* batch_id)
 {
+    DeviceScope deviceScope(c);
     if (!c) return X265CU_ERR_BAD_ARG;
     int st = beginBatch(c);
     if (!st && batch_id) *batch_id = c->cur->id;
     return st;
 }
 
-int x265cu_batch_end(x265cu_ctx* c) { return c ? endBatch(c) : X265CU_ERR_BAD_ARG; }
+int x265cu_batch_end(x265cu_ctx* c)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    return endBatch(c);
+}
+
+int x265cu_shard_config(x265cu_ctx* c, int32_t rank, int32_t nranks, x265cu_exchange_fn fn, void* user)
+{
+    DeviceScope deviceScope(c);
+    if (!c || nranks < 1 || nranks > LA_MAX_RANKS || rank < 0 || rank >= nranks || (nranks > 1 && !fn)) return X265CU_ERR_BAD_ARG;
+    int st = x265cu_sync(c);
+    if (st) return st;
+    c->rank = rank; c->nranks = nranks; c->exchange = fn; c->exchangeUser = user;
+    return X265CU_OK;
+}
+
+int x265cu_slot_owner(x265cu_ctx* c, int32_t slot, int32_t owner)
+{
+    DeviceScope deviceScope(c);
+    if (!c || !slotOk(c, slot) || owner < 0 || owner >= c->nranks) return X265CU_ERR_BAD_ARG;
+    c->slotOwner[slot] = owner;
+    return X265CU_OK;
+}
 
 /* device-side stopwatch (bench.py times its steps with it): start on the main stream; stop after everything
  * enqueued on any stream of the context */
-int x265cu_timer_start(x265cu_ctx* c) { CK(cudaEventRecord(c->tm0, c->stream)); return X265CU_OK; }
+int x265cu_timer_start(x265cu_ctx* c)
+{
+    DeviceScope deviceScope(c);
+    CK(cudaEventRecord(c->tm0, c->stream));
+    return X265CU_OK;
+}
 int x265cu_timer_stop(x265cu_ctx* c, double* ms)
 {
+    DeviceScope deviceScope(c);
     int st = mainJoinBatches(c);
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream));
@@ -952,6 +1096,7 @@ int x265cu_timer_stop(x265cu_ctx* c, double* ms)
 /* synchronises: the job counts are those that passed their condition on the device */
 int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o)
 {
+    DeviceScope deviceScope(c);
     int st = x265cu_sync(c);
     if (st) return st;
     unsigned long long ex[2] = { 0, 0 };
@@ -961,10 +1106,17 @@ int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o)
     return X265CU_OK;
 }
 
-int x265cu_profile_enable(x265cu_ctx* c, int32_t on) { resolveProfile(c); c->profile = on != 0; return X265CU_OK; }
+int x265cu_profile_enable(x265cu_ctx* c, int32_t on)
+{
+    DeviceScope deviceScope(c);
+    resolveProfile(c);
+    c->profile = on != 0;
+    return X265CU_OK;
+}
 
 int x265cu_profile_get_busy(x265cu_ctx* c, double busy[X265CU_K_COUNT])
 {
+    DeviceScope deviceScope(c);
     resolveProfile(c);
     for (int i = 0; i < X265CU_K_COUNT; i++) busy[i] = c->profBusy[i];
     return X265CU_OK;
@@ -972,6 +1124,7 @@ int x265cu_profile_get_busy(x265cu_ctx* c, double busy[X265CU_K_COUNT])
 
 int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset)
 {
+    DeviceScope deviceScope(c);
     resolveProfile(c);
     for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = c->profMs[i]; launches[i] = c->profN[i]; }
     if (reset) { memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN)); memset(c->profBusy, 0, sizeof(c->profBusy)); }
@@ -980,12 +1133,14 @@ int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launch
 
 int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* u, const void* v, int32_t sy, int32_t sc)
 {
+    DeviceScope deviceScope(c);
     if (!c || !slotOk(c, slot) || !y) return X265CU_ERR_BAD_ARG;
     return DISPATCH(uploadT, c, slot, y, u, v, sy, sc);
 }
 
 int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
 {
+    DeviceScope deviceScope(c);
     if (!c || !slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
     const cudaError_t e = cudaEventQuery(c->slotConsumed[slot]);
     if (e == cudaSuccess) return 1;
@@ -996,6 +1151,7 @@ int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
 
 int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)
 {
+    DeviceScope deviceScope(c);
     if (n <= 0) return X265CU_OK;
     const size_t need = n * sizeof(FrameStatsDev);
     if (c->hStatsCap < need)
@@ -1026,6 +1182,7 @@ int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265c
 
 int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
 {
+    DeviceScope deviceScope(c);
     if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
     if (n <= 0) return X265CU_OK;
     return DISPATCH(searchBatchT, c, jobs, n);
@@ -1033,6 +1190,7 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
 
 int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* stores, int32_t n, int32_t* flags)
 {
+    DeviceScope deviceScope(c);
     if (n <= 0) return X265CU_OK;
     int st = ensureHost(c, n * sizeof(int));
     if (st) return st;
@@ -1052,6 +1210,7 @@ int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 
 int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
 {
+    DeviceScope deviceScope(c);
     if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
     if (n <= 0) return X265CU_OK;
     return DISPATCH(costBatchT, c, jobs, n);
@@ -1059,6 +1218,7 @@ int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
 
 int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* outs, int32_t n, x265cu_cost_result* res)
 {
+    DeviceScope deviceScope(c);
     if (n <= 0) return X265CU_OK;
     int st = ensureHost(c, n * sizeof(CostResultDev));
     if (st) return st;
@@ -1082,6 +1242,7 @@ int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 
 int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_t n, uint32_t* costs)
 {
+    DeviceScope deviceScope(c);
     if (!c || (n > 0 && (!jobs || !costs))) return X265CU_ERR_BAD_ARG;
     if (n <= 0) return X265CU_OK;
     return DISPATCH(weightCostT, c, jobs, n, costs);
@@ -1089,6 +1250,7 @@ int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_
 
 int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
 {
+    DeviceScope deviceScope(c);
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
     int st = mainWaitPre(c, slot);
     if (st) return st;
@@ -1099,6 +1261,7 @@ int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
 int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s, int32_t cost_store, int32_t l0, int32_t l1,
                             int32_t referenced, int32_t bipred_weight, double fps_factor)
 {
+    DeviceScope deviceScope(c);
     if (!slotOk(c, bs) || !slotOk(c, p0s) || !slotOk(c, p1s) || cost_store < 2 || cost_store >= c->geom.n_cost_stores ||
         l0 < 0 || l0 >= c->geom.n_mv_stores || l1 >= c->geom.n_mv_stores)
         return X265CU_ERR_BAD_ARG;
@@ -1123,6 +1286,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
 
 int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double weightdelta, double strength)
 {
+    DeviceScope deviceScope(c);
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
     int st = mainWaitPre(c, slot);
@@ -1137,6 +1301,7 @@ int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double w
 
 int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree, int64_t* score, int32_t* rows)
 {
+    DeviceScope deviceScope(c);
     if (!slotOk(c, slot) || cost_store < 0 || cost_store >= c->geom.n_cost_stores || cost_store == 1 || !score) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
     const Geom& g = c->g;
@@ -1188,6 +1353,7 @@ __global__ void unpack_mv_kernel(const int* __restrict__ src, int* __restrict__ 
 
 int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
 {
+    DeviceScope deviceScope(c);
     if (!slotOk(c, slot) || !o) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
     const Geom& g = c->g;
@@ -1236,6 +1402,7 @@ int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
 
 int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost)
 {
+    DeviceScope deviceScope(c);
     if (!slotOk(c, slot) || store < 0 || store >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
     const Geom& g = c->g;
     const int* st0 = (const int*)mvStorePtr(c, slot, store);
@@ -1257,6 +1424,7 @@ int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, in
 
 int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* costs, int32_t* rows)
 {
+    DeviceScope deviceScope(c);
     if (!slotOk(c, slot) || store < 2 || store >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
     char* cs = costStorePtr(c, slot, store);
     int st = mainWaitCost(c, slot, store);
@@ -1271,6 +1439,7 @@ int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* cos
 /* unit-test hook (not part of the drop-in surface): SAD / SATD of n packed 8x8 block pairs */
 int x265cu_debug_block_metrics(x265cu_ctx* c, const void* a, const void* b, int32_t n, int32_t* sad, int32_t* satd)
 {
+    DeviceScope deviceScope(c);
     if (!c || !a || !b || n <= 0) return X265CU_ERR_BAD_ARG;
     return DISPATCH(blockMetricsT, c, a, b, n, sad, satd);
 }
@@ -1279,6 +1448,7 @@ int x265cu_debug_block_metrics(x265cu_ctx* c, const void* a, const void* b, int3
 int x265cu_debug_mc_metrics(x265cu_ctx* c, int32_t fenc_slot, int32_t ref_slot, const int32_t* cu_idx, const int32_t* mvs, int32_t n,
                             int32_t* sad, int32_t* satd)
 {
+    DeviceScope deviceScope(c);
     if (!c || !slotOk(c, fenc_slot) || !slotOk(c, ref_slot) || n <= 0) return X265CU_ERR_BAD_ARG;
     int st = mainWaitPre(c, fenc_slot);
     if (!st) st = mainWaitPre(c, ref_slot);

@@ -44,6 +44,7 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     p.poolWorkers = q->poolWorkers; p.device = q->device; p.extraSlots = q->extraSlots; p.speculate = q->speculate;
     p.pinHost = q->pinHost; p.asyncDepth = q->asyncDepth;
     if (q->pendingMax > 0) p.pendingMax = q->pendingMax;
+    p.shardCount = q->shardCount;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
      * (encoder.cpp:3511-3516,3730-3753): cuTree needs AQ; strength 0 without cuTree disables AQ */
     if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }
@@ -65,6 +66,8 @@ void x265la_close(void* la) { delete (Lookahead*)la; }
 int x265la_get_geometry(void* la, x265cu_geometry* g) { *g = ((Lookahead*)la)->geometry(); return 0; }
 const char* x265la_last_error(void* la) { return ((Lookahead*)la)->lastError(); }
 x265cu_ctx* x265la_engine(void* la) { return ((Lookahead*)la)->engine(); }
+int x265la_shard_config(void* la, int32_t rank, int32_t nranks, x265cu_exchange_fn fn, void* user)
+{ return x265cu_shard_config(((Lookahead*)la)->engine(), rank, nranks, fn, user); }
 
 void* x265la_add_picture(void* la, const void* y, const void* u, const void* v, int32_t strideY, int32_t strideC,
                          int64_t pts, int32_t sliceType)

@@ -25,7 +25,8 @@ typedef struct
     int32_t poolWorkers, device, extraSlots, speculate, pinHost;
     int32_t asyncDepth;              /* LookaheadParam::asyncDepth */
     int32_t pendingMax;              /* LookaheadParam::pendingMax; 0 = default */
-    int32_t reserved[6];
+    int32_t shardCount;              /* LookaheadParam::shardCount; 0 / 1 = not sharded */
+    int32_t reserved[5];
 } x265la_param;
 
 typedef struct
@@ -62,6 +63,8 @@ int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale
 /* host wall-clock per phase, seconds (see Lookahead::m_timers); reset != 0 clears them */
 int   x265la_get_timers(void* la, double* t /* 8 */, int32_t reset);
 x265cu_ctx* x265la_engine(void* la);
+/* sharded stream: x265cu_shard_config on this Lookahead's engine (open it with x265la_param::shardCount = nranks) */
+int   x265la_shard_config(void* la, int32_t rank, int32_t nranks, x265cu_exchange_fn exchange, void* user);
 
 #ifdef __cplusplus
 }

@@ -223,6 +223,9 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     initLowres(f, f->m_poc);
     f->m_lowres.sliceType = sliceType;
     f->m_lowres.sliceTypeReq = TYPE_AUTO;
+    if (m_param.shardCount > 1 &&
+        !check(x265cu_slot_owner(m_ctx, f->m_lowres.slot, f->m_poc % m_param.shardCount), "x265cu_slot_owner"))
+        return NULL;
     /* the device starts the frame's pre-lookahead now; results are collected in slicetypeDecide */
     if (!check(x265cu_frame_upload(m_ctx, f->m_lowres.slot, y, u, v, strideY, strideC), "x265cu_frame_upload"))
         return NULL;
@@ -522,8 +525,9 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
     while (!m_pendingSpec.empty() && !m_failed)
     {
         Frame* f = m_pendingSpec.front();
+        /* (a sharded stream must batch the same frames on every rank, so it never looks at the clock) */
         if (f->m_poc > mustPoc && m_pendingSpec.size() <= keep && needStats && !f->m_lowresInit &&
-            x265cu_frame_ready(m_ctx, f->m_lowres.slot) != 1)
+            m_param.shardCount <= 1 && x265cu_frame_ready(m_ctx, f->m_lowres.slot) != 1)
             break;
         m_pendingSpec.pop_front();
         group.push_back(f);
