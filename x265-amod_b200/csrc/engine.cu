@@ -100,6 +100,7 @@ struct x265cu_ctx
     int rank, nranks;               /* sharded stream (x265cu_shard_config); nranks 1 = not sharded */
     x265cu_exchange_fn exchange; void* exchangeUser;
     std::vector<int> slotOwner;
+    std::vector<std::pair<char*, size_t> > xpool;    /* free exchange buffers */
     int searchWorkers;              /* worker warps per search job; 0 = default (env X265CU_SEARCH_WORKERS, for tuning) */
     bool profile;
     double profMs[X265CU_K_COUNT], profBusy[X265CU_K_COUNT];
@@ -237,6 +238,49 @@ Batch* batchOf(x265cu_ctx* c, long long id)
     return b->id == id ? b : NULL;      /* NULL: the object was reused, i.e. batch `id` finished long ago */
 }
 
+int batchStage(x265cu_ctx* c, Batch* b, size_t bytes, char** h, char** d);
+
+/* gather / scatter of the exchanged stores: one launch moves every segment (a cudaMemcpyAsync each cost more host
+ * time than the whole batch).  Pointers are 256-byte aligned, lengths multiples of 4 bytes. */
+struct SegCopy { const char* src; char* dst; unsigned long long bytes; };
+
+__global__ void __launch_bounds__(256) copy_segments_kernel(const SegCopy* __restrict__ segs)
+{
+    const SegCopy s = segs[blockIdx.y];
+    const unsigned long long n16 = s.bytes >> 4;
+    const uint4* src = (const uint4*)s.src; uint4* dst = (uint4*)s.dst;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+    if (blockIdx.x == 0)
+    {
+        const unsigned long long n4 = (s.bytes & 15) >> 2;
+        if (threadIdx.x < n4)
+            ((unsigned*)(s.dst + (n16 << 4)))[threadIdx.x] = ((const unsigned*)(s.src + (n16 << 4)))[threadIdx.x];
+    }
+}
+
+/* exchange buffers come from a per-context pool: a batch borrows one per root and gives them back when it is done */
+int xbufTake(x265cu_ctx* c, size_t need, char** p, size_t* cap)
+{
+    int best = -1;
+    for (size_t i = 0; i < c->xpool.size(); i++)
+        if (c->xpool[i].second >= need && (best < 0 || c->xpool[i].second < c->xpool[best].second)) best = (int)i;
+    if (best >= 0)
+    {
+        *p = c->xpool[best].first; *cap = c->xpool[best].second;
+        c->xpool.erase(c->xpool.begin() + best);
+        return X265CU_OK;
+    }
+    *cap = alignUp(need * 3 / 2, 1 << 20);
+    CK(cudaMalloc((void**)p, *cap));
+    return X265CU_OK;
+}
+void xbufGiveBack(x265cu_ctx* c, Batch* b)
+{
+    for (int r = 0; r < LA_MAX_RANKS; r++)
+        if (b->xbuf[r]) { c->xpool.push_back(std::make_pair(b->xbuf[r], b->xcap[r])); b->xbuf[r] = NULL; b->xcap[r] = 0; }
+}
+
 /* sharded stream: every store written in this batch travels from its owner to all the other ranks */
 int exchangeBatch(x265cu_ctx* c, Batch* b)
 {
@@ -245,33 +289,45 @@ int exchangeBatch(x265cu_ctx* c, Batch* b)
     uint64_t total[LA_MAX_RANKS] = { 0 };
     for (size_t i = 0; i < b->segs.size(); i++) total[b->segs[i].root] += alignUp(b->segs[i].bytes, 256);
     for (int r = 0; r < c->nranks; r++)
-        if (total[r] > b->xcap[r])
+        if (total[r] && !b->xbuf[r])
         {
-            if (b->xbuf[r]) b->retiredDev.push_back(b->xbuf[r]);
-            b->xbuf[r] = NULL;
-            b->xcap[r] = alignUp(total[r] * 3 / 2, 4096);
-            CK(cudaMalloc((void**)&b->xbuf[r], b->xcap[r]));
+            int st = xbufTake(c, total[r], &b->xbuf[r], &b->xcap[r]);
+            if (st) return st;
         }
+    /* copy tables: [0, nPack) owner -> exchange buffer, [nPack, n) exchange buffer -> slot on the other ranks */
+    const size_t nseg = b->segs.size();
+    char *hst, *dst;
+    int st = batchStage(c, b, nseg * sizeof(SegCopy), &hst, &dst);
+    if (st) return st;
+    SegCopy* tab = (SegCopy*)hst;
+    size_t nPack = 0;
+    for (size_t i = 0; i < nseg; i++) nPack += b->segs[i].root == c->rank;
+    size_t iPack = 0, iUnpack = nPack;
     size_t off[LA_MAX_RANKS] = { 0 };
-    for (size_t i = 0; i < b->segs.size(); i++)
+    for (size_t i = 0; i < nseg; i++)
     {
         const Batch::Seg& s = b->segs[i];
-        if (s.root == c->rank)
-            CK(cudaMemcpyAsync(b->xbuf[s.root] + off[s.root], s.ptr, s.bytes, cudaMemcpyDeviceToDevice, b->stream));
+        char* x = b->xbuf[s.root] + off[s.root];
+        if (s.root == c->rank) { SegCopy sc = { s.ptr, x, s.bytes }; tab[iPack++] = sc; }
+        else { SegCopy sc = { x, s.ptr, s.bytes }; tab[iUnpack++] = sc; }
         off[s.root] += alignUp(s.bytes, 256);
+    }
+    CK(cudaMemcpyAsync(dst, hst, nseg * sizeof(SegCopy), cudaMemcpyHostToDevice, b->stream));
+    if (nPack)
+    {
+        copy_segments_kernel<<<dim3(16, (unsigned)nPack), 256, 0, b->stream>>>((const SegCopy*)dst);
+        c->counters.kernel_launches++;
     }
     void* bufs[LA_MAX_RANKS];
     for (int r = 0; r < LA_MAX_RANKS; r++) bufs[r] = b->xbuf[r];
     if (c->exchange(c->exchangeUser, bufs, total, c->nranks, (void*)b->stream) != 0)
     { snprintf(c->err, sizeof(c->err), "exchange callback failed"); return X265CU_ERR_CUDA; }
-    memset(off, 0, sizeof(off));
-    for (size_t i = 0; i < b->segs.size(); i++)
+    if (nseg > nPack)
     {
-        const Batch::Seg& s = b->segs[i];
-        if (s.root != c->rank)
-            CK(cudaMemcpyAsync(s.ptr, b->xbuf[s.root] + off[s.root], s.bytes, cudaMemcpyDeviceToDevice, b->stream));
-        off[s.root] += alignUp(s.bytes, 256);
+        copy_segments_kernel<<<dim3(16, (unsigned)(nseg - nPack)), 256, 0, b->stream>>>((const SegCopy*)dst + nPack);
+        c->counters.kernel_launches++;
     }
+    CK(cudaGetLastError());
     b->segs.clear();
     return X265CU_OK;
 }
@@ -292,8 +348,18 @@ int beginBatch(x265cu_ctx* c)
 {
     int st = endBatch(c);
     if (st) return st;
+    if (c->nranks > 1)
+        for (int i = 0; i < LA_NUM_BATCHES; i++)
+        {
+            Batch& o = c->batches[i];
+            bool holds = false;
+            for (int r = 0; r < c->nranks; r++) holds |= o.xbuf[r] != NULL;
+            if (holds && o.id >= 0 && !o.open && cudaEventQuery(o.done) == cudaSuccess)
+                xbufGiveBack(c, &o);
+        }
     Batch* b = &c->batches[c->nextBatch % LA_NUM_BATCHES];
     if (b->id >= 0) CK(cudaEventSynchronize(b->done));       /* blocks only with LA_NUM_BATCHES batches in flight */
+    xbufGiveBack(c, b);
     for (size_t i = 0; i < b->retiredDev.size(); i++) cudaFree(b->retiredDev[i]);
     for (size_t i = 0; i < b->retiredHost.size(); i++) cudaFreeHost(b->retiredHost[i]);
     b->retiredDev.clear(); b->retiredHost.clear(); b->waited.clear();
@@ -984,6 +1050,7 @@ void x265cu_destroy(x265cu_ctx* c)
         if (b.searchDone) cudaEventDestroy(b.searchDone);
         if (b.done) cudaEventDestroy(b.done);
     }
+    for (size_t i = 0; i < c->xpool.size(); i++) cudaFree(c->xpool[i].first);
     cudaFree(c->d_mvcost); cudaFree(c->d_aqPartial); cudaFree(c->d_executed); cudaFree(c->d_results);
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_stats) cudaFreeHost(c->h_stats);

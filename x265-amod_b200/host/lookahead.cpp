@@ -525,7 +525,10 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
     while (!m_pendingSpec.empty() && !m_failed)
     {
         Frame* f = m_pendingSpec.front();
-        /* (a sharded stream must batch the same frames on every rank, so it never looks at the clock) */
+        /* (a sharded stream must batch the same frames on every rank, so it never looks at the clock: it leaves the
+         * two newest frames, whose pre-lookahead is probably still running, for the next batch) */
+        if (f->m_poc > mustPoc && m_param.shardCount > 1 && needStats && f->m_poc > m_pocNext - 3)
+            break;
         if (f->m_poc > mustPoc && m_pendingSpec.size() <= keep && needStats && !f->m_lowresInit &&
             m_param.shardCount <= 1 && x265cu_frame_ready(m_ctx, f->m_lowres.slot) != 1)
             break;
