@@ -158,7 +158,7 @@ def test_cuda_speculation_modes_and_async_depth(name, mode, pkg, synth, simdir):
     assert not bad, "\n".join(bad[:10])
 
 
-@pytest.mark.parametrize("depth,w,h", [(8, 1920, 1080), (10, 3840, 2160)])
+@pytest.mark.parametrize("depth,w,h", [(8, 1920, 1080), (10, 3840, 2160), (8, 7680, 4320)])
 def test_full_size_properties(depth, w, h, pkg, synth, simdir):
     """BASELINE sizes: oracle spot-check of whole frames plus size-independent properties
     (determinism across runs and across speculation on/off; intra cost independent of neighbours)."""
