@@ -287,11 +287,11 @@ def main():
         ms, wall, types, delta, prof = one_step(dev, False)
         times.append(reduce_max(ms)); profs.append(prof); deltas.append(delta); types0 = types
     # --- e2e: pinned host pictures, H2D + result D2H inside the timed region ----------------------------
-    e2e_times, e2e_delta = [], None
+    e2e_times, e2e_delta, e2e_prof = [], None, None
     one_step(host, True)
     for _ in range(args.steps):
         ms, wall, types, delta, prof = one_step(host, True)
-        e2e_times.append(reduce_max(ms)); e2e_delta = delta
+        e2e_times.append(reduce_max(ms)); e2e_delta = delta; e2e_prof = prof
         assert types == types0, "decisions differ between device-resident and host-fed runs"
     clocks = sampler.stop()
 
@@ -351,7 +351,8 @@ def main():
                                       ("independent stream per GPU" if world > 1 else "1 GPU"),
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * bytes_in // (1 << 20))},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
-                    "h2d_bytes_per_step": int(e2e_delta["h2d"]), "d2h_bytes_per_step": int(e2e_delta["d2h"])},
+                    "h2d_bytes_per_step": int(e2e_delta["h2d"]), "d2h_bytes_per_step": int(e2e_delta["d2h"]),
+                    "host_ms_last_step": {k: round(1000.0 * v, 2) for k, v in e2e_prof["host"].items()}},
             "gpu_launches": int(sum(d["launches"] for d in deltas)),
             "clocks": clocks, "roofline": roofline,
             "decided_types": "".join(pkg.TYPE_NAMES[t][0] if t != 4 else "b" for t in types0[:48])}

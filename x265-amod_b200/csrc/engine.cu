@@ -1015,6 +1015,22 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
         /* planes must start zeroed: columns past the right margin are never written (K1) */
         if (cudaMemsetAsync(p, 0, L.total, c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
     }
+    /* everything a steady-state batch needs exists before the first frame arrives: cudaMalloc / cudaMallocHost in
+     * the middle of a run stall the host for milliseconds while kernels are in flight */
+    for (int i = 0; !rc && i < LA_NUM_BATCHES; i++)
+    {
+        Batch& b = c->batches[i];
+        b.stageCap = (size_t)512 << 10; b.syncCap = (size_t)128 << 10;
+        if (cudaMallocHost((void**)&b.h_stage, b.stageCap) != cudaSuccess || cudaMalloc((void**)&b.d_stage, b.stageCap) != cudaSuccess ||
+            cudaMalloc((void**)&b.d_sync, b.syncCap) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+    }
+    if (!rc && cfg->need_wp_stats && ensureScratch(c, c->mainScratch, c->stream, 1) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
+    if (!rc)
+    {
+        c->resultsCap = (size_t)1 << 20; c->hResultsCap = (size_t)1 << 20; c->hStatsCap = (size_t)64 << 10;
+        if (cudaMalloc((void**)&c->d_results, c->resultsCap) != cudaSuccess || cudaMallocHost((void**)&c->h_results, c->hResultsCap) != cudaSuccess ||
+            cudaMallocHost((void**)&c->h_stats, c->hStatsCap) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+    }
     if (!rc)
     {
         c->mvWriter.assign(c->slots.size() * (size_t)G.n_mv_stores, -1LL);
