@@ -34,7 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the >=20x target is quoted on
-    "2160p-main10": dict(width=3840, height=2160, depth=10, frames=120, cpu_frames=72, seed=2,
+    "2160p-main10": dict(width=3840, height=2160, depth=10, frames=300, cpu_frames=72, seed=2,
                          la=dict(bframes=8, lookaheadDepth=60, bFrameAdaptive=2),
                          text="2160p main10 --rc-lookahead 60 --bframes 8 --b-adapt 2 cutree (BASELINE configs[1])"),
     # BASELINE.json configs[0]
@@ -258,10 +258,11 @@ def main():
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1000.0
         cnt1 = pkg.Counters(); eng.x265cu_get_counters(ctx, C.byref(cnt1))
-        ht = (C.c_double * 8)()
+        ht = (C.c_double * 10)()
         la.lib.x265la_get_timers(la.h, ht, 1)
         host_t = dict(prelookahead_wait=ht[0], weightp=ht[1], enqueue=ht[2], result_wait=ht[3], decisions=ht[4],
-                      slicetype_decide=ht[5], calls=ht[6], add_picture_speculation=ht[7], wall=wall / 1000.0)
+                      slicetype_decide=ht[5], calls=ht[6], add_picture_speculation=ht[7], estimated_picture_cost=ht[8],
+                      fetch_mirrors=ht[9], wall=wall / 1000.0)
         pm = (C.c_double * 7)(); pn = (C.c_uint64 * 7)(); pb = (C.c_double * 7)()
         eng.x265cu_profile_get_busy(ctx, pb)
         eng.x265cu_profile_get(ctx, pm, pn, 1)

@@ -5,8 +5,7 @@
  * any job here: without a usable CUDA device x265cu_create fails.
  *
  * Streams: `copyStream` carries the picture uploads; `preStream` the pre-lookahead kernels (K1-K3); `stream`
- * (main) weightp scores, cuTree and every result copy, so the decisions never queue behind an upload;
- * `auxStream` the early read of a frame's statistics; and
+ * (main) weightp scores, cuTree and every result copy, so the decisions never queue behind an upload; and
  * LA_NUM_LANES worker streams carry the search / cost batches, round-robin, so the wavefront searches of
  * consecutive batches overlap.  Ordering between them is by events: batch after the pre-lookahead stream at
  * batch_begin; main-stream work after the pre-lookahead of the slots it reads; cost jobs after the batches whose MV stores they read; main-stream readers after the batch
@@ -77,7 +76,6 @@ struct x265cu_ctx
     cudaStream_t stream;            /* main: weightp scores, cuTree, every D2H */
     cudaStream_t copyStream;        /* picture uploads, so they overlap the kernels of earlier frames */
     cudaStream_t preStream;         /* pre-lookahead kernels K1-K3 of every uploaded frame */
-    cudaStream_t auxStream;         /* early read of frame statistics, past whatever the other streams have queued */
     cudaEvent_t mainMark;
     std::vector<char> slotMainTouched;          /* main-stream work read the slot's current tenant */
     cudaStream_t lanes[LA_NUM_LANES];
@@ -93,7 +91,8 @@ struct x265cu_ctx
     unsigned long long* d_executed; /* [0] search jobs, [1] cost jobs that passed their condition */
     char* d_results; size_t resultsCap;
     char* h_results; size_t hResultsCap;      /* pinned staging for gathers */
-    char* h_stats; size_t hStatsCap;          /* pinned staging of x265cu_frame_stats_get (aux stream) */
+    FrameStatsDev* h_slotStats; FrameStatsDev* d_slotStats;   /* mapped host memory: every slot's statistics, written by K3's epilogue */
+    char* h_mapped; char* d_mapped; size_t mappedCap;         /* mapped host memory for the small gathers */
     std::vector<char*> mainScratch;           /* weighted plane for x265cu_weight_cost_batch (main stream) */
     x265cu_counters counters;
     uint64_t searchEnq, costEnq;    /* jobs enqueued (conditional ones included) */
@@ -165,7 +164,6 @@ void syncAll(x265cu_ctx* c)
     cudaStreamSynchronize(c->copyStream);
     cudaStreamSynchronize(c->preStream);
     cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->auxStream);
     for (int i = 0; i < LA_NUM_LANES; i++) cudaStreamSynchronize(c->lanes[i]);
 }
 
@@ -228,6 +226,54 @@ int ensureHost(x265cu_ctx* c, size_t need)
 }
 
 bool slotOk(const x265cu_ctx* c, int s) { return s >= 0 && s < (int)c->slots.size(); }
+
+/* ---------------------------------------------------------------- small results without the copy engine
+ * The scalars the host waits for (frame statistics, cost sums, skip flags, recalculated scores) are a few bytes
+ * each.  As cudaMemcpyAsync they queue on the copy engine behind whatever 16 MB picture chunk is in flight (measured:
+ * ~0.3 ms per call while pictures upload), so kernels write them straight into mapped pinned host memory instead and
+ * the host only waits for the event / stream. */
+__global__ void publish_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dstMapped, int nWords)
+{
+    for (int i = threadIdx.x; i < nWords; i += blockDim.x) dstMapped[i] = src[i];
+}
+
+/* out[i] = wordsEach words read from srcs[i]; srcs and out live in mapped host memory */
+__global__ void gather_small_kernel(const unsigned* const* __restrict__ srcs, int wordsEach, unsigned* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned* s = srcs[i];
+    for (int w = 0; w < wordsEach; w++) out[(size_t)i * wordsEach + w] = __ldcg(s + w);
+}
+
+int ensureMapped(x265cu_ctx* c, size_t need)
+{
+    if (c->mappedCap >= need) return X265CU_OK;
+    if (c->h_mapped) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_mapped); c->h_mapped = NULL; c->mappedCap = 0; }
+    const size_t n = alignUp(need * 2, 4096);
+    CK(cudaHostAlloc((void**)&c->h_mapped, n, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&c->d_mapped, c->h_mapped, 0));
+    c->mappedCap = n;
+    return X265CU_OK;
+}
+
+/* wordsEach words from each of srcs[0..n) into dst (host), through one kernel on the main stream; synchronises */
+int gatherSmall(x265cu_ctx* c, const std::vector<const void*>& srcs, int wordsEach, void* dst)
+{
+    const size_t n = srcs.size();
+    const size_t tabBytes = alignUp(n * sizeof(void*), 256), outBytes = n * wordsEach * sizeof(unsigned);
+    int st = ensureMapped(c, tabBytes + outBytes);
+    if (st) return st;
+    memcpy(c->h_mapped, &srcs[0], n * sizeof(void*));
+    gather_small_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const unsigned* const*)c->d_mapped, wordsEach,
+                                                                             (unsigned*)(c->d_mapped + tabBytes), (int)n);
+    c->counters.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(dst, c->h_mapped + tabBytes, outBytes);
+    c->counters.d2h_bytes += outBytes;
+    return X265CU_OK;
+}
 
 /* ---------------------------------------------------------------- batches */
 
@@ -465,13 +511,23 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     /* the copy may not overwrite the staging planes while the previous tenant's K1/K2 still read them */
     CK(cudaStreamWaitEvent(c->copyStream, c->slotConsumed[slot], 0));
     /* cudaMemcpyDefault: the picture may live in host memory (pageable or pinned) or already in HBM */
-    CK(cudaMemcpy2DAsync(dY, g.picW * sizeof(P), y, (size_t)sy * sizeof(P), g.picW * sizeof(P), g.picH, cudaMemcpyDefault, c->copyStream));
+    /* a contiguous plane goes as one linear copy (one DMA descriptor instead of one per row) */
+    if (sy == g.picW) CK(cudaMemcpyAsync(dY, y, (size_t)g.picW * g.picH * sizeof(P), cudaMemcpyDefault, c->copyStream));
+    else CK(cudaMemcpy2DAsync(dY, g.picW * sizeof(P), y, (size_t)sy * sizeof(P), g.picW * sizeof(P), g.picH, cudaMemcpyDefault, c->copyStream));
     c->counters.h2d_bytes += (uint64_t)g.picW * g.picH * sizeof(P);
     const bool chroma = u && v;
     if (chroma && c->cfg.need_aq)
     {
-        CK(cudaMemcpy2DAsync(dU, g.cW * sizeof(P), u, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
-        CK(cudaMemcpy2DAsync(dV, g.cW * sizeof(P), v, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
+        if (sc == g.cW)
+        {
+            CK(cudaMemcpyAsync(dU, u, (size_t)g.cW * g.cH * sizeof(P), cudaMemcpyDefault, c->copyStream));
+            CK(cudaMemcpyAsync(dV, v, (size_t)g.cW * g.cH * sizeof(P), cudaMemcpyDefault, c->copyStream));
+        }
+        else
+        {
+            CK(cudaMemcpy2DAsync(dU, g.cW * sizeof(P), u, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
+            CK(cudaMemcpy2DAsync(dV, g.cW * sizeof(P), v, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
+        }
         c->counters.h2d_bytes += 2ull * g.cW * g.cH * sizeof(P);
     }
     CK(cudaEventRecord(c->slotCopied[slot], c->copyStream));
@@ -527,6 +583,8 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
                                                                   slotPtr<unsigned short>(c, slot, L.lowresCosts00),
                                                                   slotPtr<int>(c, slot, L.rowSatds00), stats);
     }
+    publish_kernel<<<1, 32, 0, c->preStream>>>((const unsigned*)stats, (unsigned*)(c->d_slotStats + slot), (int)(sizeof(FrameStatsDev) / 4));
+    c->counters.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->slotConsumed[slot], c->preStream));
     return X265CU_OK;
@@ -913,11 +971,11 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     x265cu_ctx* c = new (std::nothrow) x265cu_ctx();
     if (!c) return X265CU_ERR_NO_MEMORY;
     c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_aqPartial = NULL; c->d_executed = NULL;
-    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->h_stats = NULL; c->hStatsCap = 0;
+    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->h_slotStats = NULL; c->d_slotStats = NULL; c->h_mapped = NULL; c->d_mapped = NULL; c->mappedCap = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
-    c->stream = c->copyStream = c->auxStream = c->preStream = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
+    c->stream = c->copyStream = c->preStream = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
     for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
     for (int i = 0; i < LA_NUM_BATCHES; i++)
     {
@@ -982,7 +1040,6 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
     if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return X265CU_ERR_CUDA; }
-    if (cudaStreamCreateWithPriority(&c->auxStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
     if (cudaStreamCreateWithPriority(&c->preStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
     if (cudaEventCreateWithFlags(&c->mainMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < LA_NUM_LANES; i++)
@@ -1027,9 +1084,11 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     if (!rc && cfg->need_wp_stats && ensureScratch(c, c->mainScratch, c->stream, 1) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
     if (!rc)
     {
-        c->resultsCap = (size_t)1 << 20; c->hResultsCap = (size_t)1 << 20; c->hStatsCap = (size_t)64 << 10;
+        c->resultsCap = (size_t)1 << 20; c->hResultsCap = (size_t)1 << 20;
         if (cudaMalloc((void**)&c->d_results, c->resultsCap) != cudaSuccess || cudaMallocHost((void**)&c->h_results, c->hResultsCap) != cudaSuccess ||
-            cudaMallocHost((void**)&c->h_stats, c->hStatsCap) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+            cudaHostAlloc((void**)&c->h_slotStats, cfg->max_slots * sizeof(FrameStatsDev), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&c->d_slotStats, c->h_slotStats, 0) != cudaSuccess ||
+            ensureMapped(c, (size_t)256 << 10) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
     }
     if (!rc)
     {
@@ -1069,12 +1128,12 @@ void x265cu_destroy(x265cu_ctx* c)
     for (size_t i = 0; i < c->xpool.size(); i++) cudaFree(c->xpool[i].first);
     cudaFree(c->d_mvcost); cudaFree(c->d_aqPartial); cudaFree(c->d_executed); cudaFree(c->d_results);
     if (c->h_results) cudaFreeHost(c->h_results);
-    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->h_slotStats) cudaFreeHost(c->h_slotStats);
+    if (c->h_mapped) cudaFreeHost(c->h_mapped);
     if (c->tm0) cudaEventDestroy(c->tm0);
     if (c->tm1) cudaEventDestroy(c->tm1);
     if (c->profBase) cudaEventDestroy(c->profBase);
     for (int i = 0; i < LA_NUM_LANES; i++) if (c->lanes[i]) cudaStreamDestroy(c->lanes[i]);
-    if (c->auxStream) cudaStreamDestroy(c->auxStream);
     if (c->preStream) cudaStreamDestroy(c->preStream);
     if (c->mainMark) cudaEventDestroy(c->mainMark);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
@@ -1113,7 +1172,6 @@ int x265cu_sync(x265cu_ctx* c)
     int st = endBatch(c);
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream)); CK(cudaStreamSynchronize(c->preStream)); CK(cudaStreamSynchronize(c->stream));
-    CK(cudaStreamSynchronize(c->auxStream));
     for (int i = 0; i < LA_NUM_LANES; i++) CK(cudaStreamSynchronize(c->lanes[i]));
     return X265CU_OK;
 }
@@ -1167,7 +1225,6 @@ int x265cu_timer_stop(x265cu_ctx* c, double* ms)
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream));
     CK(cudaStreamSynchronize(c->preStream));
-    CK(cudaStreamSynchronize(c->auxStream));
     CK(cudaEventRecord(c->tm1, c->stream));
     CK(cudaEventSynchronize(c->tm1));
     float f = 0;
@@ -1235,31 +1292,16 @@ int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
 int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)
 {
     DeviceScope deviceScope(c);
-    if (n <= 0) return X265CU_OK;
-    const size_t need = n * sizeof(FrameStatsDev);
-    if (c->hStatsCap < need)
-    {
-        if (c->h_stats) { cudaStreamSynchronize(c->auxStream); cudaFreeHost(c->h_stats); c->h_stats = NULL; c->hStatsCap = 0; }
-        CK(cudaMallocHost((void**)&c->h_stats, alignUp(need * 2, 4096)));
-        c->hStatsCap = alignUp(need * 2, 4096);
-    }
-    /* on the aux stream, after each frame's own pre-lookahead: the read does not queue behind the uploads and
-     * pre-lookaheads of newer frames on the main stream */
+    /* the statistics were published into mapped host memory by the frame's own pre-lookahead: wait for that only */
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i])) return X265CU_ERR_BAD_ARG;
-        CK(cudaStreamWaitEvent(c->auxStream, c->slotConsumed[slots[i]], 0));
-        CK(cudaMemcpyAsync(c->h_stats + i * sizeof(FrameStatsDev), c->slots[slots[i]] + c->lay.stats, sizeof(FrameStatsDev),
-                           cudaMemcpyDeviceToHost, c->auxStream));
-    }
-    CK(cudaStreamSynchronize(c->auxStream));
-    for (int i = 0; i < n; i++)
-    {
-        const FrameStatsDev* s = (const FrameStatsDev*)(c->h_stats + i * sizeof(FrameStatsDev));
+        CK(cudaEventSynchronize(c->slotConsumed[slots[i]]));
+        const FrameStatsDev* s = c->h_slotStats + slots[i];
         out[i].cost_est = s->costEst; out[i].cost_est_aq = s->costEstAq;
         for (int k = 0; k < 3; k++) { out[i].wp_ssd[k] = s->wp_ssd[k]; out[i].wp_sum[k] = s->wp_sum[k]; }
     }
-    c->counters.d2h_bytes += n * sizeof(FrameStatsDev);
+    c->counters.d2h_bytes += (n > 0 ? n : 0) * sizeof(FrameStatsDev);
     return X265CU_OK;
 }
 
@@ -1275,20 +1317,15 @@ int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 {
     DeviceScope deviceScope(c);
     if (n <= 0) return X265CU_OK;
-    int st = ensureHost(c, n * sizeof(int));
-    if (st) return st;
+    std::vector<const void*> srcs(n);
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i]) || stores[i] < 0 || stores[i] >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
-        st = mainWaitMv(c, slots[i], stores[i]);
+        int st = mainWaitMv(c, slots[i], stores[i]);
         if (st) return st;
-        CK(cudaMemcpyAsync(c->h_results + i * sizeof(int), mvStorePtr(c, slots[i], stores[i]) + (size_t)c->g.ncu * 8, sizeof(int),
-                           cudaMemcpyDeviceToHost, c->stream));
+        srcs[i] = mvStorePtr(c, slots[i], stores[i]) + (size_t)c->g.ncu * 8;
     }
-    CK(cudaStreamSynchronize(c->stream));
-    memcpy(flags, c->h_results, n * sizeof(int));
-    c->counters.d2h_bytes += n * sizeof(int);
-    return X265CU_OK;
+    return gatherSmall(c, srcs, 1, flags);
 }
 
 int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
@@ -1303,23 +1340,21 @@ int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 {
     DeviceScope deviceScope(c);
     if (n <= 0) return X265CU_OK;
-    int st = ensureHost(c, n * sizeof(CostResultDev));
-    if (st) return st;
+    std::vector<const void*> srcs(n);
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i]) || outs[i] < 0 || outs[i] >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
-        st = mainWaitCost(c, slots[i], outs[i]);
+        int st = mainWaitCost(c, slots[i], outs[i]);
         if (st) return st;
-        CK(cudaMemcpyAsync(c->h_results + i * sizeof(CostResultDev), costStorePtr(c, slots[i], outs[i]) + c->lay.costResOff,
-                           sizeof(CostResultDev), cudaMemcpyDeviceToHost, c->stream));
+        srcs[i] = costStorePtr(c, slots[i], outs[i]) + c->lay.costResOff;
     }
-    CK(cudaStreamSynchronize(c->stream));
+    std::vector<CostResultDev> tmp(n);
+    int st = gatherSmall(c, srcs, (int)(sizeof(CostResultDev) / 4), &tmp[0]);
+    if (st) return st;
     for (int i = 0; i < n; i++)
     {
-        const CostResultDev* r = (const CostResultDev*)(c->h_results + i * sizeof(CostResultDev));
-        res[i].cost_est = r->costEst; res[i].cost_est_aq = r->costEstAq; res[i].intra_mbs = r->intraMbs; res[i].reserved = 0;
+        res[i].cost_est = tmp[i].costEst; res[i].cost_est_aq = tmp[i].costEstAq; res[i].intra_mbs = tmp[i].intraMbs; res[i].reserved = 0;
     }
-    c->counters.d2h_bytes += n * sizeof(CostResultDev);
     return X265CU_OK;
 }
 
@@ -1406,11 +1441,15 @@ int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t 
                                                                       rs, (unsigned long long*)c->d_results);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_results, c->d_results, 8, cudaMemcpyDeviceToHost, c->stream));
-    if (rows) CK(cudaMemcpyAsync(c->h_results + 8, rs, (size_t)g.bh * 4, cudaMemcpyDeviceToHost, c->stream));
+    st = ensureMapped(c, 8 + (size_t)g.bh * 4);
+    if (st) return st;
+    publish_kernel<<<1, 32, 0, c->stream>>>((const unsigned*)c->d_results, (unsigned*)c->d_mapped, 2);
+    if (rows) publish_kernel<<<1, 128, 0, c->stream>>>((const unsigned*)rs, (unsigned*)(c->d_mapped + 8), g.bh);
+    c->counters.kernel_launches += 1 + (rows != NULL);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
-    *score = *(const long long*)c->h_results;
-    if (rows) memcpy(rows, c->h_results + 8, (size_t)g.bh * 4);
+    *score = *(const long long*)c->h_mapped;
+    if (rows) memcpy(rows, c->h_mapped + 8, (size_t)g.bh * 4);
     c->counters.d2h_bytes += 8 + (rows ? (size_t)g.bh * 4 : 0);
     return X265CU_OK;
 }

@@ -140,7 +140,7 @@ int x265la_frame_weights(void* lav, void* frame, int32_t* state, int32_t* scale,
 int x265la_get_timers(void* lav, double* t, int32_t reset)
 {
     Lookahead* la = (Lookahead*)lav;
-    for (int i = 0; i < 8; i++) t[i] = la->m_timers[i];
+    for (int i = 0; i < 10; i++) t[i] = la->m_timers[i];
     if (reset) memset(la->m_timers, 0, sizeof(la->m_timers));
     return 0;
 }

@@ -61,7 +61,7 @@ int   x265la_frame_fetch(void* la, void* frame, const x265cu_frame_out* out);
 /* weightp analysis outcome per L0 distance: state 0 = not analysed, 1 = no weight, 2 = weighted */
 int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset /* nb each */);
 /* host wall-clock per phase, seconds (see Lookahead::m_timers); reset != 0 clears them */
-int   x265la_get_timers(void* la, double* t /* 8 */, int32_t reset);
+int   x265la_get_timers(void* la, double* t /* 10 */, int32_t reset);
 x265cu_ctx* x265la_engine(void* la);
 /* sharded stream: x265cu_shard_config on this Lookahead's engine (open it with x265la_param::shardCount = nranks) */
 int   x265la_shard_config(void* la, int32_t rank, int32_t nranks, x265cu_exchange_fn exchange, void* user);

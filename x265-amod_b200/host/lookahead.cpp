@@ -746,8 +746,15 @@ void Lookahead::slicetypeDecide()
         drainPending(m_param.speculate >= 2 ? 0x7fffffff : (size_t)m_param.pendingMax, maxPoc);
         if (m_failed) return;
     }
-    preLookahead(pre);
-    m_timers[0] += nowSec() - tStart;
+    {
+        /* pixel statistics of the window's frames that nothing above had to wait for yet */
+        std::vector<Frame*> still;
+        for (size_t i = 0; i < pre.size(); i++)
+            if (!pre[i]->m_lowresInit) still.push_back(pre[i]);
+        const double t0 = nowSec();
+        preLookahead(still);
+        m_timers[0] += nowSec() - t0;
+    }
     if (m_failed) return;
     if (m_param.speculate)
     {
@@ -887,6 +894,10 @@ void Lookahead::slicetypeDecide()
         slicetypeAnalyse(frames, fr, true);
     }
     m_timers[4] += nowSec() - tAnalyse;
+    /* the pictures that were still uploading when this decision started have landed by now: hand them to the GPU
+     * before returning to the caller instead of at the next decision */
+    if (m_param.speculate == 1 && m_param.shardCount <= 1)
+        drainPending((size_t)m_param.pendingMax, -1);
     m_timers[5] += nowSec() - tStart;
     m_timers[6] += 1;
 }
@@ -1448,12 +1459,14 @@ void Lookahead::getEstimatedPictureCost(Frame* cur, Frame* ref0, Frame* ref1)
         frames[b] = &cur->m_lowres;
         frames[p1] = &ref1->m_lowres;
     }
+    const double t0 = nowSec();
     if (m_param.rc.cuTree)
         cur->m_lowres.satdCost = frameCostRecalculate(frames, p0, p1, b);
     else if (m_param.rc.aqMode)
         cur->m_lowres.satdCost = cur->m_lowres.costEstAq[b - p0][p1 - b];
     else
         cur->m_lowres.satdCost = cur->m_lowres.costEst[b - p0][p1 - b];
+    m_timers[8] += nowSec() - t0;
 }
 
 /* -------------------------------------------------------------------------------------------
@@ -1491,7 +1504,10 @@ bool Lookahead::fetchCosts(Frame* f, int d0, int d1, uint16_t* lowresCosts, int3
 
 bool Lookahead::fetchFrame(Frame* f, const x265cu_frame_out* out)
 {
-    return check(x265cu_fetch_frame(m_ctx, f->m_lowres.slot, out), "x265cu_fetch_frame");
+    const double t0 = nowSec();
+    const bool ok = check(x265cu_fetch_frame(m_ctx, f->m_lowres.slot, out), "x265cu_fetch_frame");
+    m_timers[9] += nowSec() - t0;
+    return ok;
 }
 
 } // namespace x265cu

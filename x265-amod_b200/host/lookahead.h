@@ -157,8 +157,9 @@ public:
 
     /* host-side wall-clock per phase (seconds), for bench.py: 0 pre-lookahead wait, 1 weightp, 2 enqueue,
      * 3 result wait, 4 decisions (host logic incl. cuTree enqueue), 5 whole slicetypeDecide, 6 calls,
-     * 7 speculation inside addPicture (streaming mode; its weightp / enqueue shares are also in 1 / 2) */
-    double  m_timers[8];
+     * 7 speculation inside addPicture (streaming mode; its weightp / enqueue shares are also in 1 / 2),
+     * 8 getEstimatedPictureCost, 9 host mirrors (fetchMvs / fetchCosts / fetchFrame) */
+    double  m_timers[10];
 
     LookaheadParam m_param;
     bool    m_filled;
