@@ -146,14 +146,15 @@ def main():
     ap.add_argument("--workload", default="2160p-main10", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--async-depth", type=int, default=16,
+    ap.add_argument("--async-depth", type=int, default=32,
                     help="extra frames of input delay (LookaheadParam::asyncDepth): same decisions, GPU slack")
     ap.add_argument("--speculate", type=int, default=1)
     ap.add_argument("--shard", default="streams", choices=["streams", "window"],
                     help="N > 1: 'streams' = one independent stream per GPU (weak scaling, no data-path collective); "
                          "'window' = ONE stream whose searches / estimates are split over the GPUs by source frame, "
                          "stores exchanged by NCCL broadcast after every batch (strong scaling)")
-    ap.add_argument("--pending-max", type=int, default=16)
+    ap.add_argument("--pending-max", type=int, default=0, help="0 = async depth")
+    ap.add_argument("--batch-min", type=int, default=0, help="LookaheadParam::batchMin (0 = async depth / 2)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.frames:
@@ -192,7 +193,8 @@ def main():
     torch.cuda.synchronize()
     bytes_in = sum(t.numel() * t.element_size() for t in host[0])
 
-    la_kw = dict(wl["la"], asyncDepth=args.async_depth, speculate=args.speculate, pendingMax=args.pending_max,
+    la_kw = dict(wl["la"], asyncDepth=args.async_depth, speculate=args.speculate,
+                 pendingMax=args.pending_max or max(8, args.async_depth), batchMin=args.batch_min,
                  device=local_rank)
     exchange = None
     if window:

@@ -44,7 +44,7 @@ inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
-enum { LA_NUM_LANES = 16, LA_NUM_BATCHES = 48, LA_MAX_RANKS = 8 };
+enum { LA_NUM_LANES = 16, LA_NUM_BATCHES = 48, LA_MAX_RANKS = 8, LA_CT_RING = 2048 };
 
 /* One asynchronous batch of search / cost jobs (x265cu_batch_begin ... x265cu_batch_end).  Everything a batch's
  * kernels read besides the frame slots is private to it, so batches never wait for each other's buffers. */
@@ -93,6 +93,8 @@ struct x265cu_ctx
     char* h_results; size_t hResultsCap;      /* pinned staging for gathers */
     FrameStatsDev* h_slotStats; FrameStatsDev* d_slotStats;   /* mapped host memory: every slot's statistics, written by K3's epilogue */
     char* h_mapped; char* d_mapped; size_t mappedCap;         /* mapped host memory for the small gathers */
+    CutreeJobDev* h_ctJobs; CutreeJobDev* d_ctJobs;           /* mapped ring of batched cuTree propagate jobs */
+    int ctRingPos, ctPending;                                 /* next free ring entry; jobs gathered but not launched */
     std::vector<char*> mainScratch;           /* weighted plane for x265cu_weight_cost_batch (main stream) */
     x265cu_counters counters;
     uint64_t searchEnq, costEnq;    /* jobs enqueued (conditional ones included) */
@@ -194,6 +196,17 @@ void resolveProfile(x265cu_ctx* c)
         }
     }
     c->evUsed = 0;
+}
+
+/* launch the cuTree propagate jobs gathered so far (consecutive unreferenced B frames) as one kernel.  Every entry
+ * point that touches the main stream or recycles a slot calls this first, so gathering never reorders anything. */
+void flushCutree(x265cu_ctx* c)
+{
+    if (!c || !c->ctPending) return;
+    const int n = c->ctPending;
+    c->ctPending = 0;
+    c->counters.kernel_launches++; c->profN[X265CU_K_CUTREE]++;
+    cutree_propagate_batch_kernel<<<dim3((c->g.ncu + 255) / 256, n), 256, 0, c->stream>>>(c->g, c->d_ctJobs + (c->ctRingPos - n));
 }
 
 DeviceScope::DeviceScope(const x265cu_ctx* c) : prev(-1), want(c ? c->cfg.device : -1)
@@ -972,6 +985,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     if (!c) return X265CU_ERR_NO_MEMORY;
     c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_aqPartial = NULL; c->d_executed = NULL;
     c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->h_slotStats = NULL; c->d_slotStats = NULL; c->h_mapped = NULL; c->d_mapped = NULL; c->mappedCap = 0;
+    c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
@@ -1077,7 +1091,14 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     for (int i = 0; !rc && i < LA_NUM_BATCHES; i++)
     {
         Batch& b = c->batches[i];
-        b.stageCap = (size_t)512 << 10; b.syncCap = (size_t)128 << 10;
+        /* room for a batch of ~96 frames (the first decision's): per frame 3(B+1) search jobs, (B+1)(B+4) cost jobs
+         * with their groups, and the tickets / progress counters of its searches */
+        const size_t B1 = (size_t)cfg->bframes + 1;
+        const size_t nstripsEst = (size_t)(g.bh + LA_STRIP_ROWS - 1) / LA_STRIP_ROWS;
+        const size_t perFrameStage = 3 * B1 * 64 + B1 * (B1 + 3) * 104 + 2 * B1 * 1024;
+        const size_t perFrameSync = 3 * B1 * nstripsEst * sizeof(int) + 64;
+        b.stageCap = alignUp(std::max((size_t)256 << 10, perFrameStage * 96), 4096);
+        b.syncCap = alignUp(std::max((size_t)64 << 10, perFrameSync * 96), 4096);
         if (cudaMallocHost((void**)&b.h_stage, b.stageCap) != cudaSuccess || cudaMalloc((void**)&b.d_stage, b.stageCap) != cudaSuccess ||
             cudaMalloc((void**)&b.d_sync, b.syncCap) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     }
@@ -1088,6 +1109,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
         if (cudaMalloc((void**)&c->d_results, c->resultsCap) != cudaSuccess || cudaMallocHost((void**)&c->h_results, c->hResultsCap) != cudaSuccess ||
             cudaHostAlloc((void**)&c->h_slotStats, cfg->max_slots * sizeof(FrameStatsDev), cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer((void**)&c->d_slotStats, c->h_slotStats, 0) != cudaSuccess ||
+            cudaHostAlloc((void**)&c->h_ctJobs, LA_CT_RING * sizeof(CutreeJobDev), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&c->d_ctJobs, c->h_ctJobs, 0) != cudaSuccess ||
             ensureMapped(c, (size_t)256 << 10) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
     }
     if (!rc)
@@ -1106,6 +1129,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
 void x265cu_destroy(x265cu_ctx* c)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c) return;
     syncAll(c);
     for (size_t i = 0; i < c->slots.size(); i++) cudaFree(c->slots[i]);
@@ -1130,6 +1154,7 @@ void x265cu_destroy(x265cu_ctx* c)
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_slotStats) cudaFreeHost(c->h_slotStats);
     if (c->h_mapped) cudaFreeHost(c->h_mapped);
+    if (c->h_ctJobs) cudaFreeHost(c->h_ctJobs);
     if (c->tm0) cudaEventDestroy(c->tm0);
     if (c->tm1) cudaEventDestroy(c->tm1);
     if (c->profBase) cudaEventDestroy(c->profBase);
@@ -1169,6 +1194,7 @@ static int mainJoinBatches(x265cu_ctx* c)
 int x265cu_sync(x265cu_ctx* c)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     int st = endBatch(c);
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream)); CK(cudaStreamSynchronize(c->preStream)); CK(cudaStreamSynchronize(c->stream));
@@ -1179,6 +1205,7 @@ int x265cu_sync(x265cu_ctx* c)
 int x265cu_batch_begin(x265cu_ctx* c, int64_t* batch_id)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c) return X265CU_ERR_BAD_ARG;
     int st = beginBatch(c);
     if (!st && batch_id) *batch_id = c->cur->id;
@@ -1189,12 +1216,14 @@ int x265cu_batch_end(x265cu_ctx* c)
 {
     if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
+    flushCutree(c);
     return endBatch(c);
 }
 
 int x265cu_shard_config(x265cu_ctx* c, int32_t rank, int32_t nranks, x265cu_exchange_fn fn, void* user)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c || nranks < 1 || nranks > LA_MAX_RANKS || rank < 0 || rank >= nranks || (nranks > 1 && !fn)) return X265CU_ERR_BAD_ARG;
     int st = x265cu_sync(c);
     if (st) return st;
@@ -1215,12 +1244,14 @@ int x265cu_slot_owner(x265cu_ctx* c, int32_t slot, int32_t owner)
 int x265cu_timer_start(x265cu_ctx* c)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     CK(cudaEventRecord(c->tm0, c->stream));
     return X265CU_OK;
 }
 int x265cu_timer_stop(x265cu_ctx* c, double* ms)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     int st = mainJoinBatches(c);
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream));
@@ -1237,6 +1268,7 @@ int x265cu_timer_stop(x265cu_ctx* c, double* ms)
 int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     int st = x265cu_sync(c);
     if (st) return st;
     unsigned long long ex[2] = { 0, 0 };
@@ -1249,6 +1281,7 @@ int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o)
 int x265cu_profile_enable(x265cu_ctx* c, int32_t on)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     resolveProfile(c);
     c->profile = on != 0;
     return X265CU_OK;
@@ -1257,6 +1290,7 @@ int x265cu_profile_enable(x265cu_ctx* c, int32_t on)
 int x265cu_profile_get_busy(x265cu_ctx* c, double busy[X265CU_K_COUNT])
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     resolveProfile(c);
     for (int i = 0; i < X265CU_K_COUNT; i++) busy[i] = c->profBusy[i];
     return X265CU_OK;
@@ -1265,6 +1299,7 @@ int x265cu_profile_get_busy(x265cu_ctx* c, double busy[X265CU_K_COUNT])
 int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     resolveProfile(c);
     for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = c->profMs[i]; launches[i] = c->profN[i]; }
     if (reset) { memset(c->profMs, 0, sizeof(c->profMs)); memset(c->profN, 0, sizeof(c->profN)); memset(c->profBusy, 0, sizeof(c->profBusy)); }
@@ -1274,6 +1309,7 @@ int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launch
 int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* u, const void* v, int32_t sy, int32_t sc)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c || !slotOk(c, slot) || !y) return X265CU_ERR_BAD_ARG;
     return DISPATCH(uploadT, c, slot, y, u, v, sy, sc);
 }
@@ -1292,6 +1328,7 @@ int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
 int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     /* the statistics were published into mapped host memory by the frame's own pre-lookahead: wait for that only */
     for (int i = 0; i < n; i++)
     {
@@ -1308,6 +1345,7 @@ int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265c
 int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
     if (n <= 0) return X265CU_OK;
     return DISPATCH(searchBatchT, c, jobs, n);
@@ -1316,6 +1354,7 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
 int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* stores, int32_t n, int32_t* flags)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (n <= 0) return X265CU_OK;
     std::vector<const void*> srcs(n);
     for (int i = 0; i < n; i++)
@@ -1331,6 +1370,7 @@ int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
     if (n <= 0) return X265CU_OK;
     return DISPATCH(costBatchT, c, jobs, n);
@@ -1339,6 +1379,7 @@ int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
 int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* outs, int32_t n, x265cu_cost_result* res)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (n <= 0) return X265CU_OK;
     std::vector<const void*> srcs(n);
     for (int i = 0; i < n; i++)
@@ -1361,6 +1402,7 @@ int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_t n, uint32_t* costs)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c || (n > 0 && (!jobs || !costs))) return X265CU_ERR_BAD_ARG;
     if (n <= 0) return X265CU_OK;
     return DISPATCH(weightCostT, c, jobs, n, costs);
@@ -1369,6 +1411,7 @@ int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_
 int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
     int st = mainWaitPre(c, slot);
     if (st) return st;
@@ -1393,10 +1436,28 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
     if (st) return st;
     const int* mv0 = (const int*)mvStorePtr(c, bs, l0);
     const int* mv1 = l1 >= 0 ? (const int*)mvStorePtr(c, bs, l1) : mv0;
+    if (!referenced)
+    {
+        /* gathered; launched together with its neighbours by the next call that is not one of these */
+        if (c->ctRingPos + 1 > LA_CT_RING)
+        {
+            flushCutree(c);
+            CK(cudaStreamSynchronize(c->stream));       /* the ring wraps: everything that read it has run */
+            c->ctRingPos = 0;
+        }
+        CutreeJobDev& J = c->h_ctJobs[c->ctRingPos++];
+        J.intraCost = slotPtr<int>(c, bs, L.intraCost); J.lowresCosts = (const unsigned short*)costStorePtr(c, bs, cost_store);
+        J.invQ = slotPtr<int>(c, bs, L.invQ); J.mv0 = mv0; J.mv1 = mv1;
+        J.ref0 = slotPtr<int>(c, p0s, L.propagate); J.ref1 = slotPtr<int>(c, p1s, L.propagate);
+        J.bipredWeight = bipred_weight; J.pad = 0; J.fpsFactor = fps_factor;
+        c->ctPending++;
+        return X265CU_OK;
+    }
+    flushCutree(c);
     Prof pr(c, X265CU_K_CUTREE, 1);
     cutree_propagate_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
         c->g, slotPtr<int>(c, bs, L.intraCost), (const unsigned short*)costStorePtr(c, bs, cost_store), slotPtr<int>(c, bs, L.invQ),
-        mv0, mv1, referenced ? slotPtr<int>(c, bs, L.propagate) : NULL, slotPtr<int>(c, p0s, L.propagate),
+        mv0, mv1, slotPtr<int>(c, bs, L.propagate), slotPtr<int>(c, p0s, L.propagate),
         slotPtr<int>(c, p1s, L.propagate), bipred_weight, fps_factor);
     CK(cudaGetLastError());
     return X265CU_OK;
@@ -1405,6 +1466,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
 int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double weightdelta, double strength)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
     int st = mainWaitPre(c, slot);
@@ -1420,6 +1482,7 @@ int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double w
 int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree, int64_t* score, int32_t* rows)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!slotOk(c, slot) || cost_store < 0 || cost_store >= c->geom.n_cost_stores || cost_store == 1 || !score) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
     const Geom& g = c->g;
@@ -1476,6 +1539,7 @@ __global__ void unpack_mv_kernel(const int* __restrict__ src, int* __restrict__ 
 int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!slotOk(c, slot) || !o) return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
     const Geom& g = c->g;
@@ -1525,6 +1589,7 @@ int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
 int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!slotOk(c, slot) || store < 0 || store >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
     const Geom& g = c->g;
     const int* st0 = (const int*)mvStorePtr(c, slot, store);
@@ -1547,6 +1612,7 @@ int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, in
 int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* costs, int32_t* rows)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!slotOk(c, slot) || store < 2 || store >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
     char* cs = costStorePtr(c, slot, store);
     int st = mainWaitCost(c, slot, store);
@@ -1562,6 +1628,7 @@ int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* cos
 int x265cu_debug_block_metrics(x265cu_ctx* c, const void* a, const void* b, int32_t n, int32_t* sad, int32_t* satd)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c || !a || !b || n <= 0) return X265CU_ERR_BAD_ARG;
     return DISPATCH(blockMetricsT, c, a, b, n, sad, satd);
 }
@@ -1571,6 +1638,7 @@ int x265cu_debug_mc_metrics(x265cu_ctx* c, int32_t fenc_slot, int32_t ref_slot, 
                             int32_t* sad, int32_t* satd)
 {
     DeviceScope deviceScope(c);
+    flushCutree(c);
     if (!c || !slotOk(c, fenc_slot) || !slotOk(c, ref_slot) || n <= 0) return X265CU_ERR_BAD_ARG;
     int st = mainWaitPre(c, fenc_slot);
     if (!st) st = mainWaitPre(c, ref_slot);

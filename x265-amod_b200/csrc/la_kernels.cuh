@@ -1064,14 +1064,12 @@ __global__ void __launch_bounds__(128) weight_cost_kernel(Geom g, const P* __res
  * add; all addends are >= 0, so min(sum, 65535) taken when the value is read is identical and lets
  * the scatter use plain 32-bit atomics in any order.
  * ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256) cutree_propagate_kernel(Geom g, const int* __restrict__ intraCost,
-                                                               const unsigned short* __restrict__ lowresCosts,
-                                                               const int* __restrict__ invQ, const int* __restrict__ mv0,
-                                                               const int* __restrict__ mv1, const int* __restrict__ propagateIn,
-                                                               int* ref0, int* ref1, int bipredWeight, double fpsFactor)
+__device__ __forceinline__ void cutreePropagateBlock(const Geom& g, int cu, const int* __restrict__ intraCost,
+                                                     const unsigned short* __restrict__ lowresCosts,
+                                                     const int* __restrict__ invQ, const int* __restrict__ mv0,
+                                                     const int* __restrict__ mv1, const int* __restrict__ propagateIn,
+                                                     int* ref0, int* ref1, int bipredWeight, double fpsFactor)
 {
-    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cu >= g.ncu) return;
     const int bw = g.bw, bh = g.bh;
     const int bx = cu % bw, by = cu / bw;
     const double fps = __ddiv_rn(fpsFactor, 256.0);
@@ -1104,6 +1102,36 @@ __global__ void __launch_bounds__(256) cutree_propagate_kernel(Geom g, const int
         if (cux < bw && cuy + 1 < bh && cux >= 0 && cuy + 1 >= 0)     atomicAdd(ref + idx0 + bw, (listamount * w2 + 512) >> 10);
         if (cux + 1 < bw && cuy + 1 < bh && cux + 1 >= 0 && cuy + 1 >= 0) atomicAdd(ref + idx0 + bw + 1, (listamount * w3 + 512) >> 10);
     }
+}
+
+__global__ void __launch_bounds__(256) cutree_propagate_kernel(Geom g, const int* __restrict__ intraCost,
+                                                               const unsigned short* __restrict__ lowresCosts,
+                                                               const int* __restrict__ invQ, const int* __restrict__ mv0,
+                                                               const int* __restrict__ mv1, const int* __restrict__ propagateIn,
+                                                               int* ref0, int* ref1, int bipredWeight, double fpsFactor)
+{
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu >= g.ncu) return;
+    cutreePropagateBlock(g, cu, intraCost, lowresCosts, invQ, mv0, mv1, propagateIn, ref0, ref1, bipredWeight, fpsFactor);
+}
+
+/* The unreferenced B frames of a mini-GOP only ADD into their two references (integer atomics, any order), so they
+ * propagate in one launch (blockIdx.y = frame) instead of one launch each: the cuTree chain is launch-latency bound
+ * and the caller waits for it before it can read a frame's qp offsets.  The job table lives in mapped host memory. */
+struct CutreeJobDev
+{
+    const int* intraCost; const unsigned short* lowresCosts; const int* invQ; const int* mv0; const int* mv1;
+    int* ref0; int* ref1;
+    int bipredWeight, pad;
+    double fpsFactor;
+};
+
+__global__ void __launch_bounds__(256) cutree_propagate_batch_kernel(Geom g, const CutreeJobDev* __restrict__ jobs)
+{
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu >= g.ncu) return;
+    const CutreeJobDev J = jobs[blockIdx.y];
+    cutreePropagateBlock(g, cu, J.intraCost, J.lowresCosts, J.invQ, J.mv0, J.mv1, NULL, J.ref0, J.ref1, J.bipredWeight, J.fpsFactor);
 }
 
 __global__ void __launch_bounds__(256) cutree_finish_kernel(Geom g, const int* __restrict__ intraCost, const int* __restrict__ invQ,

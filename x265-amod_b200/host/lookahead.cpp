@@ -82,6 +82,7 @@ Lookahead::Lookahead(const LookaheadParam& param)
      * queue (slicetype.cpp:1821-1827, 2609-2616), so the results are the same, but the GPU always holds that many
      * frames of searches in flight beyond the window being decided */
     m_fullQueueSize = std::max(1, m_param.lookaheadDepth) + std::max(0, m_param.asyncDepth);
+    if (m_param.batchMin <= 0) m_param.batchMin = std::max(1, m_param.asyncDepth / 2);
     m_bAdaptiveQuant = m_param.rc.aqMode || m_param.bEnableWeightedPred || m_param.bEnableWeightedBiPred;
     m_bBatchMotionSearch = m_param.poolWorkers > 0 && m_param.bFrameAdaptive == B_ADAPT_TRELLIS;
     m_bBatchFrameCosts = m_bBatchMotionSearch;
@@ -522,6 +523,12 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
 {
     std::vector<Frame*> group;
     const bool needStats = m_param.bEnableWeightedPred != 0;
+    /* per-decision mode: unless the window needs one of them now, wait until enough frames have gathered for a launch
+     * that fills the GPU (a lowres search is a ~500-step wavefront: small launches spend most of their time ramping
+     * up and draining) */
+    if (m_param.speculate == 1 && !m_pendingSpec.empty() && m_pendingSpec.front()->m_poc > mustPoc &&
+        (int)m_pendingSpec.size() < m_param.batchMin)
+        return;
     while (!m_pendingSpec.empty() && !m_failed)
     {
         Frame* f = m_pendingSpec.front();

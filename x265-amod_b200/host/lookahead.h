@@ -62,6 +62,8 @@ struct LookaheadParam
                             lower throughput); 0: on-demand jobs only.  Results are identical in all three */
     int shardCount;      /* > 1: this stream is sharded over that many ranks (x265cu_shard_config on the engine): frame poc is
                             computed by rank poc % shardCount, every rank takes the same decisions */
+    int batchMin;        /* per-decision mode: frames beyond the window are batched once this many have gathered
+                            (0 = asyncDepth / 2) */
     int pendingMax;      /* streaming + weightp: frames that may wait for their pixel sums before addPicture blocks on them */
     int asyncDepth;      /* extra frames of input delay before a decision is taken (0 = the reference's trigger).  The
                             decision analyses the same frames either way; the GPU gets that many frames of slack */
