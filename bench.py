@@ -341,8 +341,9 @@ def main():
                 "search_busy_ms_per_step": round(s_ms / max(1, len(profs)), 3),
                 "kernel_busy_ms_per_step": kernel_ms,
                 "host_ms_per_step": {k: round(1000.0 * sum(p["host"][k] for p in profs) / len(profs), 2) for k in profs[0]["host"]},
-                "note": "K4 runs out of L2 and is bound by the integer pipe / wavefront latency, not HBM (SURVEY 8d); "
-                        "the HBM fraction is the conservative checkable figure, see profiles/ for pipe utilisation"}
+                "note": "K4 runs out of L2 and is bound by the ALU pipe / wavefront latency, not HBM (SURVEY 8d; ncu at "
+                        "full occupancy: ALU pipe 65 %, issue 57 %, DRAM 0.7 %); the HBM fraction is the conservative "
+                        "checkable figure, profiles/ holds the pipe utilisation"}
 
     line = {"metric": "lookahead_frames_per_s", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
