@@ -206,7 +206,7 @@ void flushCutree(x265cu_ctx* c)
     const int n = c->ctPending;
     c->ctPending = 0;
     c->counters.kernel_launches++; c->profN[X265CU_K_CUTREE]++;
-    cutree_propagate_batch_kernel<<<dim3((c->g.ncu + LA_SMALL_CTA - 1) / LA_SMALL_CTA, n), LA_SMALL_CTA, 0, c->stream>>>(c->g, c->d_ctJobs + (c->ctRingPos - n));
+    cutree_propagate_batch_kernel<<<dim3((c->g.ncu + 255) / 256, n), 256, 0, c->stream>>>(c->g, c->d_ctJobs + (c->ctRingPos - n));
 }
 
 DeviceScope::DeviceScope(const x265cu_ctx* c) : prev(-1), want(c ? c->cfg.device : -1)
@@ -278,7 +278,7 @@ int gatherSmall(x265cu_ctx* c, const std::vector<const void*>& srcs, int wordsEa
     int st = ensureMapped(c, tabBytes + outBytes);
     if (st) return st;
     memcpy(c->h_mapped, &srcs[0], n * sizeof(void*));
-    gather_small_kernel<<<(unsigned)((n + 31) / 32), 32, 0, c->stream>>>((const unsigned* const*)c->d_mapped, wordsEach,
+    gather_small_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const unsigned* const*)c->d_mapped, wordsEach,
                                                                              (unsigned*)(c->d_mapped + tabBytes), (int)n);
     c->counters.kernel_launches++;
     CK(cudaGetLastError());
@@ -1455,7 +1455,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
     }
     flushCutree(c);
     Prof pr(c, X265CU_K_CUTREE, 1);
-    cutree_propagate_kernel<<<(c->g.ncu + LA_SMALL_CTA - 1) / LA_SMALL_CTA, LA_SMALL_CTA, 0, c->stream>>>(
+    cutree_propagate_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
         c->g, slotPtr<int>(c, bs, L.intraCost), (const unsigned short*)costStorePtr(c, bs, cost_store), slotPtr<int>(c, bs, L.invQ),
         mv0, mv1, slotPtr<int>(c, bs, L.propagate), slotPtr<int>(c, p0s, L.propagate),
         slotPtr<int>(c, p1s, L.propagate), bipred_weight, fps_factor);
@@ -1472,7 +1472,7 @@ int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double w
     int st = mainWaitPre(c, slot);
     if (st) return st;
     Prof pr(c, X265CU_K_CUTREE, 1);
-    cutree_finish_kernel<<<(c->g.ncu + LA_SMALL_CTA - 1) / LA_SMALL_CTA, LA_SMALL_CTA, 0, c->stream>>>(
+    cutree_finish_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
         c->g, slotPtr<int>(c, slot, L.intraCost), slotPtr<int>(c, slot, L.invQ), slotPtr<int>(c, slot, L.propagate),
         slotPtr<double>(c, slot, L.qpAq), slotPtr<double>(c, slot, L.qpCuTree), fps_fix8, weightdelta, strength);
     CK(cudaGetLastError());
@@ -1500,7 +1500,7 @@ int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t 
     CK(cudaMemsetAsync(c->d_results, 0, 8, c->stream));
     {
         Prof pr(c, X265CU_K_CUTREE, 1);
-        cost_recalc_kernel<<<(g.ncu + LA_SMALL_CTA - 1) / LA_SMALL_CTA, LA_SMALL_CTA, 0, c->stream>>>(g, costs, slotPtr<double>(c, slot, use_cutree ? L.qpCuTree : L.qpAq),
+        cost_recalc_kernel<<<(g.ncu + 255) / 256, 256, 0, c->stream>>>(g, costs, slotPtr<double>(c, slot, use_cutree ? L.qpCuTree : L.qpAq),
                                                                       rs, (unsigned long long*)c->d_results);
     }
     CK(cudaGetLastError());

@@ -1104,12 +1104,7 @@ __device__ __forceinline__ void cutreePropagateBlock(const Geom& g, int cu, cons
     }
 }
 
-/* The cuTree / recalc kernels run while the GPU is full of search warps (28 per SM x 72 registers leave 1 K registers
- * and 4 block slots per SM): as one-warp CTAs of at most 32 registers they fit into that remainder and start at once;
- * as 256-thread CTAs they waited until several search warps of one SM had retired (milliseconds). */
-#define LA_SMALL_CTA 32
-
-__global__ void __launch_bounds__(LA_SMALL_CTA, 64) cutree_propagate_kernel(Geom g, const int* __restrict__ intraCost,
+__global__ void __launch_bounds__(256) cutree_propagate_kernel(Geom g, const int* __restrict__ intraCost,
                                                                const unsigned short* __restrict__ lowresCosts,
                                                                const int* __restrict__ invQ, const int* __restrict__ mv0,
                                                                const int* __restrict__ mv1, const int* __restrict__ propagateIn,
@@ -1131,7 +1126,7 @@ struct CutreeJobDev
     double fpsFactor;
 };
 
-__global__ void __maxnreg__(32) cutree_propagate_batch_kernel(Geom g, const CutreeJobDev* __restrict__ jobs)
+__global__ void __launch_bounds__(256) cutree_propagate_batch_kernel(Geom g, const CutreeJobDev* __restrict__ jobs)
 {
     const int cu = blockIdx.x * blockDim.x + threadIdx.x;
     if (cu >= g.ncu) return;
@@ -1139,7 +1134,7 @@ __global__ void __maxnreg__(32) cutree_propagate_batch_kernel(Geom g, const Cutr
     cutreePropagateBlock(g, cu, J.intraCost, J.lowresCosts, J.invQ, J.mv0, J.mv1, NULL, J.ref0, J.ref1, J.bipredWeight, J.fpsFactor);
 }
 
-__global__ void __launch_bounds__(LA_SMALL_CTA, 64) cutree_finish_kernel(Geom g, const int* __restrict__ intraCost, const int* __restrict__ invQ,
+__global__ void __launch_bounds__(256) cutree_finish_kernel(Geom g, const int* __restrict__ intraCost, const int* __restrict__ invQ,
                                                             const int* __restrict__ propagate, const double* __restrict__ qpAq,
                                                             double* __restrict__ qpCuTree, int fpsFactor, double weightdelta,
                                                             double strength)
@@ -1155,7 +1150,7 @@ __global__ void __launch_bounds__(LA_SMALL_CTA, 64) cutree_finish_kernel(Geom g,
     }
 }
 
-__global__ void __launch_bounds__(LA_SMALL_CTA, 64) cost_recalc_kernel(Geom g, const unsigned short* __restrict__ lowresCosts,
+__global__ void __launch_bounds__(256) cost_recalc_kernel(Geom g, const unsigned short* __restrict__ lowresCosts,
                                                           const double* __restrict__ qpOffset, int* rowSatds,
                                                           unsigned long long* score)
 {
