@@ -90,7 +90,6 @@ struct x265cu_ctx
     double* d_aqPartial;            /* per-CTA partial sums of the AQ frame means (K2b) */
     unsigned long long* d_executed; /* [0] search jobs, [1] cost jobs that passed their condition */
     char* d_results; size_t resultsCap;
-    char* h_results; size_t hResultsCap;      /* pinned staging for gathers */
     FrameStatsDev* h_slotStats; FrameStatsDev* d_slotStats;   /* mapped host memory: every slot's statistics, written by K3's epilogue */
     char* h_mapped; char* d_mapped; size_t mappedCap;         /* mapped host memory for the small gathers */
     CutreeJobDev* h_ctJobs; CutreeJobDev* d_ctJobs;           /* mapped ring of batched cuTree propagate jobs */
@@ -225,16 +224,6 @@ int ensureDev(x265cu_ctx* c, char** p, size_t* cap, size_t need)
     size_t n = alignUp(need * 2, 4096);
     CK(cudaMalloc((void**)p, n));
     *cap = n;
-    return X265CU_OK;
-}
-
-int ensureHost(x265cu_ctx* c, size_t need)
-{
-    if (c->hResultsCap >= need) return X265CU_OK;
-    if (c->h_results) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_results); c->h_results = NULL; c->hResultsCap = 0; }
-    size_t n = alignUp(need * 2, 4096);
-    CK(cudaMallocHost((void**)&c->h_results, n));
-    c->hResultsCap = n;
     return X265CU_OK;
 }
 
@@ -440,7 +429,7 @@ int batchStage(x265cu_ctx* c, Batch* b, size_t bytes, char** h, char** d)
     {
         if (b->h_stage) { b->retiredHost.push_back(b->h_stage); b->retiredDev.push_back(b->d_stage); }
         b->h_stage = NULL; b->d_stage = NULL; b->stageUsed = 0;
-        b->stageCap = alignUp(std::max(bytes * 2, (size_t)64 << 10), 4096);
+        b->stageCap = alignUp(std::max(bytes * 2, b->stageCap * 2), 4096);
         CK(cudaMallocHost((void**)&b->h_stage, b->stageCap));
         CK(cudaMalloc((void**)&b->d_stage, b->stageCap));
     }
@@ -456,7 +445,7 @@ int batchSync(x265cu_ctx* c, Batch* b, size_t ints, int** d)
     {
         if (b->d_sync) b->retiredDev.push_back(b->d_sync);
         b->d_sync = NULL; b->syncUsed = 0;
-        b->syncCap = alignUp(std::max(bytes * 2, (size_t)64 << 10), 4096);
+        b->syncCap = alignUp(std::max(bytes * 2, b->syncCap * 2), 4096);
         CK(cudaMalloc((void**)&b->d_sync, b->syncCap));
     }
     *d = (int*)((char*)b->d_sync + b->syncUsed);
@@ -860,8 +849,6 @@ int weightCostT(x265cu_ctx* c, const x265cu_wcost_job* jobs, int n, uint32_t* co
     const SlotLayout& L = c->lay;
     int st = ensureDev(c, &c->d_results, &c->resultsCap, n * sizeof(unsigned));
     if (st) return st;
-    st = ensureHost(c, n * sizeof(unsigned));
-    if (st) return st;
     CK(cudaMemsetAsync(c->d_results, 0, n * sizeof(unsigned), c->stream));
     st = ensureScratch(c, c->mainScratch, c->stream, 1);
     if (st) return st;
@@ -885,9 +872,13 @@ int weightCostT(x265cu_ctx* c, const x265cu_wcost_job* jobs, int n, uint32_t* co
                                                                         (unsigned*)c->d_results + i);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_results, c->d_results, n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    st = ensureMapped(c, n * sizeof(unsigned));
+    if (st) return st;
+    publish_kernel<<<1, 128, 0, c->stream>>>((const unsigned*)c->d_results, (unsigned*)c->d_mapped, n);
+    c->counters.kernel_launches++;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
-    memcpy(costs, c->h_results, n * sizeof(unsigned));
+    memcpy(costs, c->h_mapped, n * sizeof(unsigned));
     c->counters.d2h_bytes += n * sizeof(unsigned);
     return X265CU_OK;
 }
@@ -984,7 +975,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     x265cu_ctx* c = new (std::nothrow) x265cu_ctx();
     if (!c) return X265CU_ERR_NO_MEMORY;
     c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_aqPartial = NULL; c->d_executed = NULL;
-    c->d_results = NULL; c->resultsCap = 0; c->h_results = NULL; c->hResultsCap = 0; c->h_slotStats = NULL; c->d_slotStats = NULL; c->h_mapped = NULL; c->d_mapped = NULL; c->mappedCap = 0;
+    c->d_results = NULL; c->resultsCap = 0; c->h_slotStats = NULL; c->d_slotStats = NULL; c->h_mapped = NULL; c->d_mapped = NULL; c->mappedCap = 0;
     c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
@@ -1105,8 +1096,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     if (!rc && cfg->need_wp_stats && ensureScratch(c, c->mainScratch, c->stream, 1) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
     if (!rc)
     {
-        c->resultsCap = (size_t)1 << 20; c->hResultsCap = (size_t)1 << 20;
-        if (cudaMalloc((void**)&c->d_results, c->resultsCap) != cudaSuccess || cudaMallocHost((void**)&c->h_results, c->hResultsCap) != cudaSuccess ||
+        c->resultsCap = (size_t)1 << 20;
+        if (cudaMalloc((void**)&c->d_results, c->resultsCap) != cudaSuccess ||
             cudaHostAlloc((void**)&c->h_slotStats, cfg->max_slots * sizeof(FrameStatsDev), cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer((void**)&c->d_slotStats, c->h_slotStats, 0) != cudaSuccess ||
             cudaHostAlloc((void**)&c->h_ctJobs, LA_CT_RING * sizeof(CutreeJobDev), cudaHostAllocMapped) != cudaSuccess ||
@@ -1151,7 +1142,6 @@ void x265cu_destroy(x265cu_ctx* c)
     }
     for (size_t i = 0; i < c->xpool.size(); i++) cudaFree(c->xpool[i].first);
     cudaFree(c->d_mvcost); cudaFree(c->d_aqPartial); cudaFree(c->d_executed); cudaFree(c->d_results);
-    if (c->h_results) cudaFreeHost(c->h_results);
     if (c->h_slotStats) cudaFreeHost(c->h_slotStats);
     if (c->h_mapped) cudaFreeHost(c->h_mapped);
     if (c->h_ctJobs) cudaFreeHost(c->h_ctJobs);
@@ -1493,8 +1483,6 @@ int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t 
     if (!st) st = mainWaitPre(c, slot);
     if (st) return st;
     st = ensureDev(c, &c->d_results, &c->resultsCap, 8);
-    if (st) return st;
-    st = ensureHost(c, 8 + (size_t)g.bh * 4);
     if (st) return st;
     CK(cudaMemsetAsync(rs, 0, (size_t)g.bh * 4, c->stream));
     CK(cudaMemsetAsync(c->d_results, 0, 8, c->stream));

@@ -154,7 +154,7 @@ bool Lookahead::create()
 void Lookahead::destroy()
 {
     for (size_t i = 0; i < m_pool.size(); i++) delete m_pool[i];
-    m_pool.clear(); m_inputQueue.clear(); m_outputQueue.clear(); m_resident.clear();
+    m_pool.clear(); m_inputQueue.clear(); m_outputQueue.clear(); m_resident.clear(); m_pendingSpec.clear();
     if (m_ctx) { x265cu_destroy(m_ctx); m_ctx = NULL; }
 }
 
