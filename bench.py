@@ -190,6 +190,8 @@ def main():
 
     host = [(to_t(y).pin_memory(), to_t(u).pin_memory(), to_t(v).pin_memory()) for (y, u, v) in frames]
     dev = [(y.cuda(), u.cuda(), v.cuda()) for (y, u, v) in host]
+    # the pageable copies are only needed for the CPU baseline's sample (rank 0, N = 1): 7.5 GB per rank otherwise
+    frames = frames[:wl["cpu_frames"]] if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     torch.cuda.synchronize()
     bytes_in = sum(t.numel() * t.element_size() for t in host[0])
 
