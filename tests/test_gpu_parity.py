@@ -244,3 +244,19 @@ def test_cuda_one_stream_sharded_over_two_gpus(case_name, pkg, synth):
         got = pickle.loads(blob)
         bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1))
         assert not bad, "rank %d:\n%s" % (rank, "\n".join(bad[:10]))
+
+
+@pytest.mark.parametrize("nframes,extra", [(0, {}), (1, {}), (2, dict(asyncDepth=4)), (5, dict(asyncDepth=4)), (5, dict(speculate=2))])
+def test_cuda_tiny_sequences(nframes, extra, pkg, synth, simdir):
+    """empty input and sequences shorter than a mini-GOP / the lookahead / the async depth"""
+    case = ("tiny", 8, 176, 144, nframes, dict(cuts=()), dict(bframes=3, lookaheadDepth=10))
+    got = cases.run_ours(pkg, synth, case, planes=False, **extra)
+    assert len(got) == nframes
+    assert sorted(g["poc"] for g in got) == list(range(nframes))
+    if nframes:
+        if refbind.available(8):
+            want = cases.run_reference(refbind, synth, case, planes=False)
+        else:
+            want = _as_ref_layout(cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, 8), planes=False))
+        bad = compare.compare_runs(want, got, check_planes=False)
+        assert not bad, "\n".join(bad[:10])

@@ -142,3 +142,17 @@ def test_no_cpu_fallback_without_gpu(pkg):
     with pytest.raises(RuntimeError) as e:
         pkg.Lookahead(320, 192, depth=8)
     assert "no usable CUDA device" in str(e.value) or "x265cu_create" in str(e.value)
+
+
+@pytest.mark.parametrize("nframes", [0, 1, 2, 5])
+def test_tiny_sequences(nframes, pkg, synth, simdir):
+    """empty input and sequences shorter than a mini-GOP / the lookahead: nothing hangs, every frame comes out once, and
+    what comes out matches the reference"""
+    case = ("tiny", 8, 176, 144, nframes, dict(cuts=()), dict(bframes=3, lookaheadDepth=10))
+    got = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, 8), planes=False)
+    assert len(got) == nframes
+    assert sorted(g["poc"] for g in got) == list(range(nframes))
+    if nframes and refbind.available(8):
+        want = cases.run_reference(refbind, synth, case, planes=False)
+        bad = compare.compare_runs(want, got, check_planes=False)
+        assert not bad, "\n".join(bad[:10])
