@@ -53,7 +53,10 @@ typedef struct
     const uint16_t* mvcost;     /* BitCost row for X265_LOOKAHEAD_QP (bitcost.cpp:46-54): entries */
     int32_t mvcost_half;        /*   [-mvcost_half, +mvcost_half], centre at mvcost[mvcost_half]   */
     int32_t device;             /* CUDA device ordinal */
-    int32_t reserved[8];
+    int32_t rows_per_slice;     /* Lookahead::m_numRowsPerSlice when every search runs as cooperative slices
+                                   (slicetype.cpp:1047-1059, 3957-3968: a slice's bottom row takes no predictors from
+                                   the slice below); 0 = whole-frame searches */
+    int32_t reserved[7];
 } x265cu_config;
 
 /* derived geometry, as Lowres::create computes it */

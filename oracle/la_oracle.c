@@ -29,6 +29,7 @@ void or_geom_init(or_geom* g, int picW, int picH, int maxCUSize)
     g->planeLines = g->h + 2 * g->my;
     g->planeSize = (int64_t)g->stride * g->planeLines;
     g->padOffset = (int64_t)g->stride * g->my + g->mx;
+    g->rowsPerSlice = 0; g->pad = 0;
 }
 
 /* common/constants.cpp:34-90: lambda = 2^(qp/6 - 2) * 2^(depth-8); X265_LOOKAHEAD_QP = 12 + 6*(depth-8)
@@ -587,6 +588,18 @@ static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv
     return bcost;
 }
 
+/* is cuY the first row a search visits in its slice?  Whole frame: the bottom row (slicetype.cpp:4050-4059);
+ * cooperative slices: the bottom row of each slice, the last slice running to the frame's end (:3957-3968) */
+static int or_last_row(const or_geom* g, int cuY)
+{
+    if (g->rowsPerSlice <= 0) return cuY == g->bh - 1;
+    const int ns = g->bh / g->rowsPerSlice;
+    int si = cuY / g->rowsPerSlice;
+    if (si > ns - 1) si = ns - 1;
+    const int lastY = si == ns - 1 ? g->bh - 1 : (si + 1) * g->rowsPerSlice - 1;
+    return cuY == lastY;
+}
+
 /* search half of estimateCUCost over a whole frame (slicetype.cpp:4050-4059, 4103-4183) */
 void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
                     const uint16_t* mvcost, int bBidir, int32_t* mvs, int32_t* mvCosts, int32_t* skipCount)
@@ -597,7 +610,7 @@ void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel
     const int bw = g->bw, bh = g->bh;
     for (int cuY = bh - 1; cuY >= 0; cuY--)
     {
-        const int lastRow = cuY == bh - 1;
+        const int lastRow = or_last_row(g, cuY);
         for (int cuX = bw - 1; cuX >= 0; cuX--)
         {
             const int cuXY = cuX + cuY * bw;

@@ -41,6 +41,9 @@ typedef struct
     int32_t planeLines;     /* h + 2*my */
     int64_t planeSize;      /* stride * planeLines */
     int64_t padOffset;      /* my*stride + mx */
+    int32_t rowsPerSlice;   /* Lookahead::m_numRowsPerSlice when the searches run as cooperative slices
+                               (slicetype.cpp:1047-1059, 3957-3968); 0 = whole frame */
+    int32_t pad;
 } or_geom;
 
 int  or_depth(void);

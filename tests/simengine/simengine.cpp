@@ -95,6 +95,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     x265cu_ctx* c = new x265cu_ctx;
     c->cfg = *cfg;
     or_geom_init(&c->g, cfg->width, cfg->height, cfg->max_cu_size);
+    c->g.rowsPerSlice = cfg->rows_per_slice;
     c->mvcost.assign(cfg->mvcost, cfg->mvcost + 2 * (size_t)cfg->mvcost_half + 1);
     memset(&c->geom, 0, sizeof(c->geom));
     c->geom.low_width = c->g.w; c->geom.low_height = c->g.h; c->geom.bw = c->g.bw; c->geom.bh = c->g.bh;

@@ -1007,6 +1007,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     g.padOffset = (long long)g.stride * g.my + g.mx;
     g.lambda = cfg->lambda; g.depth = cfg->depth; g.nb = cfg->bframes + 2;
     g.tpr = g.stride / 8;
+    g.rowsPerSlice = cfg->rows_per_slice > 0 ? cfg->rows_per_slice : 0;
     x265cu_geometry& G = c->geom;
     G.low_width = g.w; G.low_height = g.h; G.bw = g.bw; G.bh = g.bh; G.ncu = g.ncu; G.stride = g.stride;
     G.plane_lines = g.planeLines; G.margin_x = g.mx; G.margin_y = g.my; G.nb = g.nb;

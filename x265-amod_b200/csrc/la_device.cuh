@@ -38,6 +38,7 @@ struct Geom
     long long planeSize, padOffset;
     int lambda, depth, nb;
     int tpr;                    /* tiles per plane row = stride / 8 */
+    int rowsPerSlice;           /* cooperative search slices (x265cu_config::rows_per_slice); 0 = none */
 };
 
 /* sample offset of buffer coordinate (X, Y) (margins included, X,Y >= 0) inside a tiled plane */

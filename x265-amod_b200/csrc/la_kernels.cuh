@@ -766,7 +766,15 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
     const int rowsInStrip = min(LA_STRIP_ROWS, bh - strip * LA_STRIP_ROWS);
     const bool rowOk = grp < rowsInStrip;
     const int cuY = rowOk ? bh - 1 - strip * LA_STRIP_ROWS - grp : 0;
-    const bool lastRow = cuY == bh - 1;
+    /* the first row a search visits takes no predictors from below: the frame's bottom row, or with cooperative
+     * slices (slicetype.cpp:3957-3968) the bottom row of each slice, the last slice running to the frame's end */
+    bool lastRow = cuY == bh - 1;
+    if (g.rowsPerSlice > 0)
+    {
+        const int ns = bh / g.rowsPerSlice;
+        const int si = min(cuY / g.rowsPerSlice, ns - 1);
+        lastRow = cuY == (si == ns - 1 ? bh - 1 : (si + 1) * g.rowsPerSlice - 1);
+    }
     const int steps = bw + 2 * (rowsInStrip - 1);
     int* myProgress = progress + job * nstrips + strip;
     const int* belowProgress = myProgress - 1;

@@ -6,7 +6,7 @@
  * pool, so only the decisions (and their order of first touch) are shared with it.
  *
  * Not supported (create() fails with an error string rather than silently diverging):
- * --lookahead-slices > 0, --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
+ * --lookahead-slices together with b-adapt 2 and a thread pool, --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
  * zones, radl, gop-lookahead, temporal sub-layers, analysis load, fades, chunked encodes.
  */
 #include "lookahead.h"
@@ -113,7 +113,23 @@ bool Lookahead::check(int status, const char* what)
 bool Lookahead::create()
 {
     const LookaheadParam& p = m_param;
-    if (p.lookaheadSlices > 0) { fail("lookahead-slices > 0 is not supported by the GPU lookahead"); return false; }
+    /* cooperative slices (slicetype.cpp:1035-1059).  They only exist with a thread pool and >= 720 lines.  Without the
+     * pool's search batches (b-adapt 0 / 1) EVERY search runs sliced, which the engine does (rows_per_slice).  With
+     * the batches (b-adapt 2) the searches first touched by a batch are unsliced and the rest sliced: a second
+     * dimension of search variants that is not built yet. */
+    int rowsPerSlice = 0;
+    {
+        int slices = p.lookaheadSlices;
+        if (slices && p.poolWorkers <= 0) slices = 0;
+        if (slices && p.sourceHeight < 720) slices = 0;
+        if (slices > 1)
+        {
+            int rows = std::min(std::max(m_8x8Height / slices, 10), m_8x8Height);
+            if (m_8x8Height / rows > 1) rowsPerSlice = rows;
+        }
+        if (rowsPerSlice && m_bBatchMotionSearch)
+        { fail("lookahead-slices together with b-adapt 2 and a thread pool is not supported by the GPU lookahead"); return false; }
+    }
     if (p.rc.qgSize < 16) { fail("qg-size 8 is not supported by the GPU lookahead"); return false; }
     if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
@@ -134,6 +150,7 @@ bool Lookahead::create()
     cfg.lambda = lookaheadLambda(p.internalBitDepth);
     cfg.mvcost = &m_mvcost[0]; cfg.mvcost_half = half;
     cfg.device = p.device;
+    cfg.rows_per_slice = rowsPerSlice;
     if (!check(x265cu_create(&cfg, &m_ctx), "x265cu_create"))
         return false;
     if (!check(x265cu_get_geometry(m_ctx, &m_geom), "x265cu_get_geometry"))
