@@ -13,7 +13,7 @@ def main(path):
     for r in rd:
         if len(r) <= vi:
             continue
-        name = re.sub(r'[<(].*', '', r[ki].replace('(anonymous namespace)::', '')).replace('void ', '').replace('la::', '')
+        name = re.sub(r'[<(].*', '', r[ki].replace('(anonymous namespace)::', '').replace('<unnamed>::', '')).replace('void ', '').replace('la::', '')
         tot[name] += float(r[vi].replace(',', '')) * scale.get(r[ui], 1.0)
         cnt[name] += 1
     T = sum(tot.values())
