@@ -53,10 +53,13 @@ typedef struct
     const uint16_t* mvcost;     /* BitCost row for X265_LOOKAHEAD_QP (bitcost.cpp:46-54): entries */
     int32_t mvcost_half;        /*   [-mvcost_half, +mvcost_half], centre at mvcost[mvcost_half]   */
     int32_t device;             /* CUDA device ordinal */
-    int32_t rows_per_slice;     /* Lookahead::m_numRowsPerSlice when every search runs as cooperative slices
+    int32_t rows_per_slice;     /* Lookahead::m_numRowsPerSlice, the height of a cooperative search slice
                                    (slicetype.cpp:1047-1059, 3957-3968: a slice's bottom row takes no predictors from
-                                   the slice below); 0 = whole-frame searches */
-    int32_t reserved[7];
+                                   the slice below); 0 = no slices.  Applied to the search jobs that ask for it */
+    int32_t mv_store_kinds;     /* MV stores per slot = this * (bframes+2); 0 = 3 (L0 in P context, L0 in B context, L1).
+                                   6 when sliced and unsliced variants of a search can both be needed */
+    int32_t cost_variants;      /* cost stores per slot = this * (bframes+2)^2; 0 = 2 */
+    int32_t reserved[5];
 } x265cu_config;
 
 /* derived geometry, as Lowres::create computes it */
@@ -136,13 +139,16 @@ typedef struct
     int32_t bidir_ctx;      /* 1 when the reference would run this search inside a B estimate
                                (b < p1): enables the zero-MV skip rule, slicetype.cpp:4165-4181 */
     int32_t store;          /* MV store of fenc_slot that receives MVs + MV costs:
-                               kind*nb + dist, kind 0 = L0 in P context, 1 = L0 in B context, 2 = L1 */
+                               kind*nb + dist, kind 0 = L0 in P context, 1 = L0 in B context, 2 = L1
+                               (3..5 = the same, sliced, when mv_store_kinds is 6) */
     int32_t weighted;       /* search the weighted copy of the reference (slicetype.cpp:4083,4128) */
     int32_t w_scale, w_denom, w_offset; /* WeightParam inputWeight/log2WeightDenom/inputOffset */
     int32_t cond_store;     /* -1 = always run.  Else the job runs only if the search held in MV store `cond_store`
                                of fenc_slot applied the zero-MV skip rule to at least one block; decided on the
                                device when the job starts, so the host need not wait for that search (a B-context
                                L0 search that never skipped IS the P-context search, see x265cu_search_flags_get) */
+    int32_t sliced;         /* search as cooperative slices of x265cu_config::rows_per_slice rows (the reference runs a
+                               search that way when it is first needed outside a thread-pool batch, slicetype.cpp:4004) */
 } x265cu_search_job;
 int  x265cu_search_batch(x265cu_ctx* ctx, const x265cu_search_job* jobs, int32_t n);
 /* synchronises; flags[i] != 0 when the search stored in (slots[i], stores[i]) applied the zero-MV skip rule to at

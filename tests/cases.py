@@ -30,6 +30,13 @@ CASES = [
     # cooperative search slices (--lookahead-slices with a pool, >= 720 lines, no search batches)
     ("slices_badapt0", 8, 1280, 720, 24, dict(cuts=(12,)), dict(bframes=3, lookaheadDepth=10, bFrameAdaptive=0, poolThreads=4, lookaheadSlices=4)),
     ("slices_badapt1", 10, 1280, 720, 24, dict(cuts=(12,)), dict(bframes=3, lookaheadDepth=10, bFrameAdaptive=1, poolThreads=16, lookaheadSlices=3)),
+    # ... next to the pool's search batches (b-adapt 2): a search is sliced or not depending on who touched it first;
+    # pool 16 keeps both batches, pool 4 drops the frame-cost batch after the first decision, pool 2 the search batch too
+    ("slices_trellis16", 8, 1280, 720, 30, dict(cuts=(14,)), dict(bframes=3, lookaheadDepth=10, poolThreads=16, lookaheadSlices=4)),
+    ("slices_trellis4", 8, 1280, 720, 30, dict(cuts=(14,)), dict(bframes=4, lookaheadDepth=12, poolThreads=4, lookaheadSlices=4)),
+    # x265's defaults (preset medium: b-adapt 2, bframes 4, rc-lookahead 20, lookahead-slices 8) with an 8-thread pool
+    ("medium_defaults", 8, 1280, 720, 40, dict(cuts=(20,)), dict(bframes=4, lookaheadDepth=20, poolThreads=8, lookaheadSlices=8)),
+    ("slices_trellis2", 10, 1280, 720, 30, dict(cuts=(14,), static=True, noise=1), dict(bframes=3, lookaheadDepth=10, poolThreads=2, lookaheadSlices=3)),
 ]
 
 # subset small enough to commit as golden fixtures and to run in the quick CPU suite

@@ -95,13 +95,14 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     x265cu_ctx* c = new x265cu_ctx;
     c->cfg = *cfg;
     or_geom_init(&c->g, cfg->width, cfg->height, cfg->max_cu_size);
-    c->g.rowsPerSlice = cfg->rows_per_slice;
+    c->g.rowsPerSlice = 0;      /* per search job, x265cu_search_job::sliced */
     c->mvcost.assign(cfg->mvcost, cfg->mvcost + 2 * (size_t)cfg->mvcost_half + 1);
     memset(&c->geom, 0, sizeof(c->geom));
     c->geom.low_width = c->g.w; c->geom.low_height = c->g.h; c->geom.bw = c->g.bw; c->geom.bh = c->g.bh;
     c->geom.ncu = c->g.ncu; c->geom.stride = c->g.stride; c->geom.plane_lines = c->g.planeLines;
     c->geom.margin_x = c->g.mx; c->geom.margin_y = c->g.my; c->geom.nb = cfg->bframes + 2;
-    c->geom.n_mv_stores = 3 * c->geom.nb; c->geom.n_cost_stores = 2 * c->geom.nb * c->geom.nb;
+    c->geom.n_mv_stores = (cfg->mv_store_kinds > 0 ? cfg->mv_store_kinds : 3) * c->geom.nb;
+    c->geom.n_cost_stores = (cfg->cost_variants > 0 ? cfg->cost_variants : 2) * c->geom.nb * c->geom.nb;
     c->slots.resize(cfg->max_slots);
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL; c->owner.assign(cfg->max_slots, 0);
     memset(&c->counters, 0, sizeof(c->counters));
@@ -154,10 +155,11 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     s.intraCost.assign(ncu, 0); s.invQ.assign(ncu, 256); s.intraMode.assign(ncu, 0);
     s.lowresCosts00.assign(ncu, 0); s.rowSatds00.assign(g.bh, 0); s.propagate.assign(ncu, 0);
     s.qpAq.assign(ncu, 0.0); s.qpCuTree.assign(ncu, 0.0);
-    s.mvs.assign(3 * nb, std::vector<int32_t>()); s.mvCosts.assign(3 * nb, std::vector<int32_t>());
-    s.skipFlag.assign(3 * nb, 0);
-    s.costs.assign(2 * nb * nb, std::vector<uint16_t>()); s.rowSatds.assign(2 * nb * nb, std::vector<int32_t>());
-    s.results.assign(2 * nb * nb, x265cu_cost_result());
+    const int nmv = c->geom.n_mv_stores, ncs = c->geom.n_cost_stores;
+    s.mvs.assign(nmv, std::vector<int32_t>()); s.mvCosts.assign(nmv, std::vector<int32_t>());
+    s.skipFlag.assign(nmv, 0);
+    s.costs.assign(ncs, std::vector<uint16_t>()); s.rowSatds.assign(ncs, std::vector<int32_t>());
+    s.results.assign(ncs, x265cu_cost_result());
     memset(&s.stats, 0, sizeof(s.stats));
     if (c->cfg.need_aq)
         or_aq_frame(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW,
@@ -204,7 +206,9 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
         else
             planePtrs(c, r.planes, rp);
         f.mvs[j.store].assign(2 * g.ncu, 0); f.mvCosts[j.store].assign(g.ncu, 0);
-        or_search_list(&g, &f.planes[g.padOffset], rp, &c->mvcost[c->cfg.mvcost_half], j.bidir_ctx,
+        or_geom gj = g;
+        gj.rowsPerSlice = j.sliced ? c->cfg.rows_per_slice : 0;
+        or_search_list(&gj, &f.planes[g.padOffset], rp, &c->mvcost[c->cfg.mvcost_half], j.bidir_ctx,
                        &f.mvs[j.store][0], &f.mvCosts[j.store][0], &f.skipFlag[j.store]);
         c->counters.kernel_launches++;
     }

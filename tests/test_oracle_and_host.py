@@ -159,14 +159,10 @@ def test_tiny_sequences(nframes, pkg, synth, simdir):
 
 
 def test_lookahead_slices_rules(pkg, synth, simdir):
-    """--lookahead-slices: ignored without a pool or below 720 lines like the reference (slicetype.cpp:1035-1045);
-    refused loudly with b-adapt 2 + pool (mixed sliced / unsliced searches, not built)"""
+    """--lookahead-slices is ignored without a pool or below 720 lines, like the reference (slicetype.cpp:1035-1045)"""
     case = cases.get_case("base8")
     for extra in (dict(lookaheadSlices=4), dict(lookaheadSlices=4, poolWorkers=4, bFrameAdaptive=0)):
         got = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, 8), planes=False, **extra)
         if "poolWorkers" not in extra:
             bad = compare.compare_runs(golden_io.load("base8"), got, check_planes=False)
             assert not bad, "\n".join(bad[:10])
-    with pytest.raises(RuntimeError) as e:
-        pkg.Lookahead(1280, 720, depth=8, lib_path=_sim(simdir, 8), lookaheadSlices=4, poolWorkers=8, bFrameAdaptive=2)
-    assert "lookahead-slices" in str(e.value)

@@ -684,7 +684,7 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
             if (st) return st;
         }
         D.bidir = j.bidir_ctx;
-        D.pad = 0;
+        D.sliced = j.sliced;
     }
     n = nm;
     if (!n)
@@ -1011,7 +1011,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     x265cu_geometry& G = c->geom;
     G.low_width = g.w; G.low_height = g.h; G.bw = g.bw; G.bh = g.bh; G.ncu = g.ncu; G.stride = g.stride;
     G.plane_lines = g.planeLines; G.margin_x = g.mx; G.margin_y = g.my; G.nb = g.nb;
-    G.n_mv_stores = 3 * g.nb; G.n_cost_stores = 2 * g.nb * g.nb;
+    G.n_mv_stores = (cfg->mv_store_kinds > 0 ? cfg->mv_store_kinds : 3) * g.nb;
+    G.n_cost_stores = (cfg->cost_variants > 0 ? cfg->cost_variants : 2) * g.nb * g.nb;
 
     SlotLayout& L = c->lay;
     size_t o = 0;

@@ -527,7 +527,7 @@ struct SearchJobDev
     int*     flagOut;       /* set to 1 when any block took the zero-MV skip (slicetype.cpp:4177-4181) */
     const int* cond;        /* NULL, or the flagOut of another search: run only if that search skipped somewhere */
     int      bidir;
-    int      pad;
+    int      sliced;        /* search as cooperative slices of g.rowsPerSlice rows */
 };
 
 struct MV2 { int x, y; };
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
     /* the first row a search visits takes no predictors from below: the frame's bottom row, or with cooperative
      * slices (slicetype.cpp:3957-3968) the bottom row of each slice, the last slice running to the frame's end */
     bool lastRow = cuY == bh - 1;
-    if (g.rowsPerSlice > 0)
+    if (J.sliced && g.rowsPerSlice > 0)
     {
         const int ns = bh / g.rowsPerSlice;
         const int si = min(cuY / g.rowsPerSlice, ns - 1);

@@ -61,7 +61,8 @@ void lookaheadParamDefault(LookaheadParam* p)
 
 Lookahead::Lookahead(const LookaheadParam& param)
     : m_param(param), m_filled(false), m_inputCount(0), m_lastNonB(NULL), m_lastNonBFrame(NULL),
-      m_isSceneTransition(false), m_extendGopBoundary(false), m_ctx(NULL), m_pocNext(0), m_failed(false)
+      m_isSceneTransition(false), m_extendGopBoundary(false), m_rowsPerSlice(0), m_dualSlicing(false), m_inBatch(false),
+      m_costVariants(2), m_ctx(NULL), m_pocNext(0), m_failed(false)
 {
     m_error[0] = 0;
     memset(m_timers, 0, sizeof(m_timers));
@@ -113,10 +114,9 @@ bool Lookahead::check(int status, const char* what)
 bool Lookahead::create()
 {
     const LookaheadParam& p = m_param;
-    /* cooperative slices (slicetype.cpp:1035-1059).  They only exist with a thread pool and >= 720 lines.  Without the
-     * pool's search batches (b-adapt 0 / 1) EVERY search runs sliced, which the engine does (rows_per_slice).  With
-     * the batches (b-adapt 2) the searches first touched by a batch are unsliced and the rest sliced: a second
-     * dimension of search variants that is not built yet. */
+    /* cooperative slices (slicetype.cpp:1035-1059).  They only exist with a thread pool and >= 720 lines.  A search
+     * that is first needed outside one of the pool's batches runs sliced (:4004); without the batches (b-adapt 0 / 1)
+     * that is every search, with them (b-adapt 2) both variants of a search can be needed and get their own stores. */
     int rowsPerSlice = 0;
     {
         int slices = p.lookaheadSlices;
@@ -127,9 +127,10 @@ bool Lookahead::create()
             int rows = std::min(std::max(m_8x8Height / slices, 10), m_8x8Height);
             if (m_8x8Height / rows > 1) rowsPerSlice = rows;
         }
-        if (rowsPerSlice && m_bBatchMotionSearch)
-        { fail("lookahead-slices together with b-adapt 2 and a thread pool is not supported by the GPU lookahead"); return false; }
     }
+    m_rowsPerSlice = rowsPerSlice;
+    m_dualSlicing = rowsPerSlice > 0 && m_bBatchMotionSearch;
+    m_costVariants = m_dualSlicing ? 8 : 2;
     if (p.rc.qgSize < 16) { fail("qg-size 8 is not supported by the GPU lookahead"); return false; }
     if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
@@ -151,6 +152,7 @@ bool Lookahead::create()
     cfg.mvcost = &m_mvcost[0]; cfg.mvcost_half = half;
     cfg.device = p.device;
     cfg.rows_per_slice = rowsPerSlice;
+    cfg.mv_store_kinds = m_dualSlicing ? 6 : 3; cfg.cost_variants = m_costVariants;
     if (!check(x265cu_create(&cfg, &m_ctx), "x265cu_create"))
         return false;
     if (!check(x265cu_get_geometry(m_ctx, &m_geom), "x265cu_get_geometry"))
@@ -409,35 +411,37 @@ void Lookahead::weightsAnalyseBatch(const std::vector<std::pair<Lowres*, Lowres*
     }
 }
 
-static void addSearch(std::vector<x265cu_search_job>& jobs, Lowres* fenc, Lowres* ref, int kind, int d, int nb, int condStore = -1)
+void Lookahead::addSearch(Lowres* fenc, Lowres* ref, int kind, int d, int condStore)
 {
     if (fenc->haveSearch[kind][d]) return;
     fenc->haveSearch[kind][d] = 1;
+    const int nb = m_geom.nb;
     x265cu_search_job j;
     memset(&j, 0, sizeof(j));
     j.fenc_slot = fenc->slot; j.ref_slot = ref->slot;
-    j.bidir_ctx = kind != 0;
+    j.bidir_ctx = kind % 3 != 0;
     j.store = kind * nb + d;
     j.cond_store = condStore;
-    if (kind < 2 && fenc->weightState[d] == 2)
+    j.sliced = jobSliced(kind);
+    if (kind % 3 < 2 && fenc->weightState[d] == 2)
     {
         j.weighted = 1; j.w_scale = fenc->wScale[d]; j.w_denom = fenc->wDenom[d]; j.w_offset = fenc->wOffset[d];
     }
-    jobs.push_back(j);
+    m_searchJobs.push_back(j);
 }
 
-static void addCost(std::vector<x265cu_cost_job>& jobs, Lowres* b, Lowres* p0, Lowres* p1, int d0, int d1, int variant, int nb,
-                    int condStore = -1)
+void Lookahead::addCost(Lowres* b, Lowres* p0, Lowres* p1, int d0, int d1, int l0kind, int l1kind, int condStore)
 {
+    const int nb = m_geom.nb, variant = costVariant(l0kind, p1 ? l1kind : -1);
     if (b->haveCost[d0][d1][variant]) return;
     b->haveCost[d0][d1][variant] = 1;
     x265cu_cost_job j;
     j.b_slot = b->slot; j.p0_slot = p0->slot; j.p1_slot = p1 ? p1->slot : b->slot;
-    j.l0_store = variant * nb + d0;
-    j.l1_store = p1 ? 2 * nb + d1 : -1;
-    j.out = (d0 * nb + d1) * 2 + variant;
+    j.l0_store = l0kind * nb + d0;
+    j.l1_store = p1 ? l1kind * nb + d1 : -1;
+    j.out = costStoreOf(d0, d1, variant);
     j.cond_store = condStore;
-    jobs.push_back(j);
+    m_costJobs.push_back(j);
 }
 
 void Lookahead::launchJobs()
@@ -449,31 +453,34 @@ void Lookahead::launchJobs()
     m_searchJobs.clear(); m_costJobs.clear();
 }
 
-/* every frame cost of `variant` (= kind of the L0 search it reads) whose searches exist on the device and whose
+/* every frame cost reading the L0 searches of kind `l0kind` whose searches exist on the device and whose
  * frames are resident: P estimates (d0, 0) and B estimates (d0, d1) the reference can ask for (p1 - p0 <= bframes+1,
  * slicetype.cpp:3221-3305; every (d0, d1) when the frame-cost batches of :2696-2735 are emulated).
  * conditional: the jobs read a P-context L0 search that only exists if its B-context twin applied the skip rule */
-void Lookahead::enqueueCosts(int variant, bool conditional)
+void Lookahead::enqueueCosts(int l0kind, bool conditional)
 {
     const int B = m_param.bframes, nb = m_geom.nb;
+    const int l1kind = 2 + 3 * (l0kind / 3);        /* speculation pairs searches of the same slicedness */
     for (size_t i = 0; i < m_resident.size(); i++)
     {
         Frame* bf = m_resident[i];
         Lowres* b = &bf->m_lowres;
         for (int d0 = 1; d0 <= B + 1; d0++)
         {
-            if (!b->haveSearch[variant][d0]) continue;
+            if (!b->haveSearch[l0kind][d0]) continue;
             Frame* p0f = frameOfPoc(bf->m_poc - d0);
             if (!p0f) continue;
-            const int cond = conditional ? 1 * nb + d0 : -1;
-            addCost(m_costJobs, b, &p0f->m_lowres, NULL, d0, 0, variant, nb, cond);
+            /* only a P-context search that was itself queued as the conditional twin of a B-context search
+             * (haveSearch == 1) may be missing; one issued on demand (== 2) always exists */
+            const int cond = (conditional && b->haveSearch[l0kind][d0] == 1) ? (l0kind + 1) * nb + d0 : -1;
+            addCost(b, &p0f->m_lowres, NULL, d0, 0, l0kind, -1, cond);
             const int maxD1 = m_bBatchFrameCosts ? B : B + 1 - d0;
             for (int d1 = 1; d1 <= maxD1; d1++)
             {
-                if (!b->haveSearch[2][d1]) continue;
+                if (!b->haveSearch[l1kind][d1]) continue;
                 Frame* p1f = frameOfPoc(bf->m_poc + d1);
                 if (!p1f) continue;
-                addCost(m_costJobs, b, &p0f->m_lowres, &p1f->m_lowres, d0, d1, variant, nb, cond);
+                addCost(b, &p0f->m_lowres, &p1f->m_lowres, d0, d1, l0kind, l1kind, cond);
             }
         }
     }
@@ -493,7 +500,11 @@ void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
     double t0 = nowSec();
     if (!check(x265cu_batch_begin(m_ctx, NULL), "x265cu_batch_begin")) return;
     m_searchJobs.clear(); m_costJobs.clear();
-    const int firstKind = B > 0 ? 1 : 0;
+    /* dual slicing: while the reference's pool batches run, (nearly) every search is first touched by one of them, i.e.
+     * unsliced; once they are switched off (small pool, :2691) every search is first touched on demand, i.e. sliced.
+     * The other variant is computed on demand if the control flow ever asks for it */
+    const int s3 = (m_dualSlicing && !m_bBatchMotionSearch) ? 3 : 0;
+    const int firstKind = (B > 0 ? 1 : 0) + s3;
     for (size_t i = 0; i < fresh.size(); i++)
     {
         Frame* fn = fresh[i];
@@ -504,9 +515,9 @@ void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
             Frame* rf = frameOfPoc(fn->m_poc - d);
             if (!rf) break;
             Lowres* r = &rf->m_lowres;
-            addSearch(m_searchJobs, n, r, firstKind, d, nb);        /* L0(n,d) */
+            addSearch(n, r, firstKind, d);                  /* L0(n,d) */
             if (B > 0 && d <= B)
-                addSearch(m_searchJobs, r, n, 2, d, nb);            /* L1(n-d,d), reference = n */
+                addSearch(r, n, 2 + s3, d);                 /* L1(n-d,d), reference = n */
         }
     }
     enqueueCosts(firstKind, false);
@@ -520,10 +531,10 @@ void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
             {
                 Frame* rf = frameOfPoc(fn->m_poc - d);
                 if (!rf) break;
-                addSearch(m_searchJobs, &fn->m_lowres, &rf->m_lowres, 0, d, nb, 1 * nb + d);
+                addSearch(&fn->m_lowres, &rf->m_lowres, s3, d, (1 + s3) * nb + d);
             }
         }
-        enqueueCosts(0, true);
+        enqueueCosts(s3, true);
         launchJobs();
     }
     check(x265cu_batch_end(m_ctx), "x265cu_batch_end");
@@ -596,25 +607,28 @@ void Lookahead::resolveAlias(const std::vector<Lowres*>& who)
     const int B = m_param.bframes, nb = m_geom.nb;
     if (B <= 0 || m_failed) return;
     std::vector<int32_t> slots, stores, flags;
-    std::vector<std::pair<Lowres*, int> > ref;
+    struct Ref { Lowres* l; int s, d; };
+    std::vector<Ref> ref;
     for (size_t i = 0; i < who.size(); i++)
-        for (int d = 1; d <= B + 1; d++)
-            if (who[i]->haveSearch[1][d] && !who[i]->flagFetched[d])
-            {
-                slots.push_back(who[i]->slot); stores.push_back(1 * nb + d);
-                ref.push_back(std::make_pair(who[i], d));
-            }
+        for (int s = 0; s <= (m_dualSlicing ? 1 : 0); s++)
+            for (int d = 1; d <= B + 1; d++)
+                if (who[i]->haveSearch[1 + 3 * s][d] && !who[i]->flagFetched[s][d])
+                {
+                    slots.push_back(who[i]->slot); stores.push_back((1 + 3 * s) * nb + d);
+                    Ref r = { who[i], s, d };
+                    ref.push_back(r);
+                }
     if (slots.empty()) return;
     flags.resize(slots.size());
     if (!check(x265cu_search_flags_get(m_ctx, &slots[0], &stores[0], (int)slots.size(), &flags[0]), "x265cu_search_flags_get"))
         return;
     for (size_t i = 0; i < ref.size(); i++)
     {
-        Lowres* l = ref[i].first; int d = ref[i].second;
-        l->flagFetched[d] = 1;
+        Lowres* l = ref[i].l; const int s = ref[i].s, d = ref[i].d;
+        l->flagFetched[s][d] = 1;
         /* a P-context search issued unconditionally (demand path) is always the real thing */
-        if (!l->l0Alias[d])
-            l->l0Alias[d] = (flags[i] || l->haveSearch[0][d] == 2) ? 2 : 1;
+        if (!l->l0Alias[s][d])
+            l->l0Alias[s][d] = (flags[i] || l->haveSearch[3 * s][d] == 2) ? 2 : 1;
     }
 }
 
@@ -629,12 +643,13 @@ void Lookahead::fetchResults(const std::vector<Lowres*>& who, int maxPoc)
     for (size_t i = 0; i < who.size(); i++)
         for (int d0 = 1; d0 < nb; d0++)
             for (int d1 = 0; d1 < nb; d1++)
-                for (int v = 0; v < 2; v++)
+                for (int v = 0; v < m_costVariants; v++)
                     if (who[i]->haveCost[d0][d1][v] && !who[i]->resultFetched[d0][d1][v])
                     {
                         if (who[i]->frameNum + d1 > maxPoc) continue;
-                        if (v == 0 && who[i]->l0Alias[d0] == 1) continue;   /* aliased: the conditional job did not run */
-                        slots.push_back(who[i]->slot); outs.push_back((d0 * nb + d1) * 2 + v);
+                        /* P-context L0 aliased to the B-context search: the conditional job did not run */
+                        if ((v & 1) == 0 && who[i]->l0Alias[(v >> 1) & 1][d0] == 1) continue;
+                        slots.push_back(who[i]->slot); outs.push_back(costStoreOf(d0, d1, v));
                         Ref r = { who[i], d0, d1, v };
                         refs.push_back(r);
                     }
@@ -651,10 +666,9 @@ void Lookahead::fetchResults(const std::vector<Lowres*>& who, int maxPoc)
 
 /* demand path: make sure the searches and the cost of one estimate exist on the device and its
  * scalars on the host (everything already speculated is a no-op) */
-void Lookahead::ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind)
+void Lookahead::ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind, int l1kind)
 {
-    const int nb = m_geom.nb;
-    if (fenc->resultFetched[d0][d1][l0kind]) return;
+    if (fenc->resultFetched[d0][d1][costVariant(l0kind, ref1 ? l1kind : -1)]) return;
     m_searchJobs.clear(); m_costJobs.clear();
     if (!fenc->haveSearch[l0kind][d0])
     {
@@ -663,12 +677,12 @@ void Lookahead::ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0,
             std::vector<std::pair<Lowres*, Lowres*> > one(1, std::make_pair(fenc, ref0));
             weightsAnalyseBatch(one);
         }
-        addSearch(m_searchJobs, fenc, ref0, l0kind, d0, nb);
-        if (l0kind == 0) fenc->haveSearch[0][d0] = 2;       /* unconditional */
+        addSearch(fenc, ref0, l0kind, d0);
+        if (l0kind % 3 == 0) fenc->haveSearch[l0kind][d0] = 2;       /* unconditional */
     }
-    if (ref1 && !fenc->haveSearch[2][d1])
-        addSearch(m_searchJobs, fenc, ref1, 2, d1, nb);
-    addCost(m_costJobs, fenc, ref0, ref1, d0, d1, l0kind, nb);
+    if (ref1 && !fenc->haveSearch[l1kind][d1])
+        addSearch(fenc, ref1, l1kind, d1);
+    addCost(fenc, ref0, ref1, d0, d1, l0kind, l1kind);
     if (!check(x265cu_batch_begin(m_ctx, NULL), "x265cu_batch_begin")) return;
     launchJobs();
     check(x265cu_batch_end(m_ctx), "x265cu_batch_end");
@@ -699,20 +713,24 @@ int64_t Lookahead::estimateFrameCost(Lowres** frames, int p0, int p1, int b, boo
         if (d0 <= 0 || d0 >= nb || d1 < 0 || d1 >= nb) { fail("estimate outside the (bframes+2) window"); return 0; }
         const bool bDoSearch0 = fenc->mvStore[0][d0] < 0;
         const bool bDoSearch1 = p1 > b && fenc->mvStore[1][d1] < 0;
-        /* first touch decides which variant of the L0 search the reference would hold */
-        int l0kind = bDoSearch0 ? (p1 > b ? 1 : 0) : fenc->mvStore[0][d0] / nb;
-        if (l0kind == 0 && fenc->haveSearch[1][d0] && !fenc->flagFetched[d0])
+        /* first touch decides which variant of a search the reference would hold: its context (P / B estimate) and,
+         * with cooperative slices next to pool batches, whether a batch or an on-demand estimate got there first */
+        const int s3 = 3 * sliceNow();
+        int l0kind = bDoSearch0 ? (p1 > b ? 1 : 0) + s3 : fenc->mvStore[0][d0] / nb;
+        const int l1kind = p1 > b ? (bDoSearch1 ? 2 + s3 : fenc->mvStore[1][d1] / nb) : -1;
+        if (l0kind % 3 == 0 && fenc->haveSearch[l0kind + 1][d0] && !fenc->flagFetched[l0kind / 3][d0])
             resolveAlias(std::vector<Lowres*>(1, fenc));
         l0kind = effKind(fenc, d0, l0kind);      /* identical variants share one store */
-        ensureEstimate(fenc, frames[p0], p1 > b ? frames[p1] : NULL, d0, d1, l0kind);
+        ensureEstimate(fenc, frames[p0], p1 > b ? frames[p1] : NULL, d0, d1, l0kind, l1kind);
         if (m_failed) return 0;
         if (bDoSearch0) fenc->mvStore[0][d0] = l0kind * nb + d0;
-        if (bDoSearch1) fenc->mvStore[1][d1] = 2 * nb + d1;
-        const x265cu_cost_result& r = fenc->result[d0][d1][l0kind];
+        if (bDoSearch1) fenc->mvStore[1][d1] = l1kind * nb + d1;
+        const int variant = costVariant(l0kind, l1kind);
+        const x265cu_cost_result& r = fenc->result[d0][d1][variant];
         fenc->costEstAq[d0][d1] = r.cost_est_aq;
         if (p1 == b) fenc->intraMbs[d0] += r.intra_mbs;
         fenc->rowSatdsValid[d0][d1] = true;
-        fenc->costStore[d0][d1] = (d0 * nb + d1) * 2 + l0kind;
+        fenc->costStore[d0][d1] = costStoreOf(d0, d1, variant);
         score = r.cost_est;
         if (b != p1)
             score = score * 100 / (130 + m_param.bFrameBias);
@@ -967,7 +985,8 @@ void Lookahead::slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe)
     if (m_bBatchMotionSearch)
     {
         /* the reference's thread-pool batches (:2668-2736); here they only fix the order of first
-         * touch, the work itself was done by speculate() */
+         * touch (and with it the context / slicedness of the searches), the work itself was speculated */
+        m_inBatch = true;
         for (int b = 2; b < numFrames; b++)
             for (int i = 1; i <= p.bframes + 1; i++)
             {
@@ -999,6 +1018,7 @@ void Lookahead::slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe)
                 }
             m_bBatchFrameCosts &= p.poolWorkers > 12;
         }
+        m_inBatch = false;
     }
 
     int numBFrames = 0, numAnalyzed = numFrames;

@@ -98,17 +98,20 @@ struct Lowres
     int     weightState[BFRAME_MAX + 2];
     int     wScale[BFRAME_MAX + 2], wDenom[BFRAME_MAX + 2], wOffset[BFRAME_MAX + 2];
 
-    /* device-side bookkeeping */
+    /* device-side bookkeeping.  A search "kind" is context + 3 * sliced: 0 = L0 in P context, 1 = L0 in B context,
+     * 2 = L1, 3..5 = the same run as cooperative slices (only with LookaheadParam::lookaheadSlices + b-adapt 2 + pool,
+     * where a search is sliced or not depending on whether a thread-pool batch touched it first).  A cost "variant"
+     * names the searches it read: (L0 context) + 2 * (L0 sliced) + 4 * (L1 sliced). */
     int     slot;
     bool    statsFetched;
-    uint8_t haveSearch[3][BFRAME_MAX + 2];                   /* store kind x dist computed on device */
-    /* L0 distance d: 0 = unknown, 1 = the B-context search never applied the zero-MV skip, so the P-context
-     * search is the same search and store kind 0 aliases kind 1; 2 = the two variants differ */
-    uint8_t l0Alias[BFRAME_MAX + 2];
-    uint8_t flagFetched[BFRAME_MAX + 2];
-    uint8_t haveCost[BFRAME_MAX + 2][BFRAME_MAX + 2][2];     /* cost store computed on device */
-    uint8_t resultFetched[BFRAME_MAX + 2][BFRAME_MAX + 2][2];
-    x265cu_cost_result result[BFRAME_MAX + 2][BFRAME_MAX + 2][2];
+    uint8_t haveSearch[6][BFRAME_MAX + 2];                   /* kind x dist computed on (or queued for) the device */
+    /* L0 distance d, per slicedness: 0 = unknown, 1 = the B-context search never applied the zero-MV skip, so the
+     * P-context search is the same search and its store aliases the B-context one; 2 = the two variants differ */
+    uint8_t l0Alias[2][BFRAME_MAX + 2];
+    uint8_t flagFetched[2][BFRAME_MAX + 2];
+    uint8_t haveCost[BFRAME_MAX + 2][BFRAME_MAX + 2][8];     /* cost variant computed on (or queued for) the device */
+    uint8_t resultFetched[BFRAME_MAX + 2][BFRAME_MAX + 2][8];
+    x265cu_cost_result result[BFRAME_MAX + 2][BFRAME_MAX + 2][8];
 };
 
 struct Frame
@@ -175,6 +178,10 @@ private:
     int     m_lastKeyframe, m_fullQueueSize;
     bool    m_isSceneTransition, m_bBatchMotionSearch, m_bBatchFrameCosts, m_bAdaptiveQuant, m_extendGopBoundary;
     double  m_cuTreeStrength;
+    int     m_rowsPerSlice;        /* cooperative search slices (slicetype.cpp:1047-1059); 0 = none */
+    bool    m_dualSlicing;         /* sliced and unsliced variants of a search can both be needed (b-adapt 2 + pool) */
+    bool    m_inBatch;             /* replaying one of the reference's thread-pool batches (:2668-2736) */
+    int     m_costVariants;        /* 2, or 8 with dual slicing */
 
     /* engine */
     x265cu_ctx* m_ctx;
@@ -211,11 +218,19 @@ private:
     void    speculateFrames(const std::vector<Frame*>& fresh);
     void    drainPending(size_t keep, int mustPoc);
     void    resolveAlias(const std::vector<Lowres*>& who);
-    void    enqueueCosts(int variant, bool conditional);
+    void    enqueueCosts(int l0kind, bool conditional);
     void    launchJobs();
-    int     effKind(const Lowres* l, int d0, int kind) const { return (kind == 0 && l->l0Alias[d0] == 1) ? 1 : kind; }
+    int     effKind(const Lowres* l, int d0, int kind) const { return (kind % 3 == 0 && l->l0Alias[kind / 3][d0] == 1) ? kind + 1 : kind; }
+    /* cost variant of the searches (l0kind, l1kind) and the cost store it lives in */
+    int     costVariant(int l0kind, int l1kind) const { return m_dualSlicing ? (l0kind % 3) + 2 * (l0kind / 3) + (l1kind >= 3 ? 4 : 0) : l0kind; }
+    int     costStoreOf(int d0, int d1, int variant) const { return (d0 * m_geom.nb + d1) * m_costVariants + variant; }
+    /* does a search first needed right now run as cooperative slices (slicetype.cpp:4004)? */
+    int     sliceNow() const { return m_dualSlicing && !m_inBatch ? 1 : 0; }
+    int     jobSliced(int kind) const { return m_rowsPerSlice && (!m_dualSlicing || kind >= 3) ? 1 : 0; }
+    void    addSearch(Lowres* fenc, Lowres* ref, int kind, int d, int condStore = -1);
+    void    addCost(Lowres* b, Lowres* p0, Lowres* p1, int d0, int d1, int l0kind, int l1kind, int condStore = -1);
     void    weightsAnalyseBatch(const std::vector<std::pair<Lowres*, Lowres*> >& pairs);
-    void    ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind);
+    void    ensureEstimate(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1, int l0kind, int l1kind);
     void    fetchResults(const std::vector<Lowres*>& who, int maxPoc);
     Frame*  frameOfPoc(int poc);
     void    recycle();
