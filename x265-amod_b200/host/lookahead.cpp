@@ -6,7 +6,7 @@
  * pool, so only the decisions (and their order of first touch) are shared with it.
  *
  * Not supported (create() fails with an error string rather than silently diverging):
- * --lookahead-slices together with b-adapt 2 and a thread pool, --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
+ * --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
  * zones, radl, gop-lookahead, temporal sub-layers, analysis load, fades, chunked encodes.
  */
 #include "lookahead.h"
