@@ -36,11 +36,13 @@ CASES = [
     ("slices_trellis4", 8, 1280, 720, 30, dict(cuts=(14,)), dict(bframes=4, lookaheadDepth=12, poolThreads=4, lookaheadSlices=4)),
     # x265's defaults (preset medium: b-adapt 2, bframes 4, rc-lookahead 20, lookahead-slices 8) with an 8-thread pool
     ("medium_defaults", 8, 1280, 720, 40, dict(cuts=(20,)), dict(bframes=4, lookaheadDepth=20, poolThreads=8, lookaheadSlices=8)),
+    # narrow picture, tall enough for slices: small enough to commit as a golden fixture
+    ("slices_golden", 8, 256, 720, 16, dict(cuts=(8,)), dict(bframes=3, lookaheadDepth=8, poolThreads=8, lookaheadSlices=4)),
     ("slices_trellis2", 10, 1280, 720, 30, dict(cuts=(14,), static=True, noise=1), dict(bframes=3, lookaheadDepth=10, poolThreads=2, lookaheadSlices=3)),
 ]
 
 # subset small enough to commit as golden fixtures and to run in the quick CPU suite
-GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob"]
+GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob", "slices_golden"]
 
 REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive="bFrameAdaptive", bBPyramid="bBPyramid",
               scenecutThreshold="scenecutThreshold", keyframeMax="keyframeMax", keyframeMin="keyframeMin",

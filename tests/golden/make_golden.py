@@ -1,5 +1,5 @@
 """Regenerates tests/golden/*.npz from the unmodified reference (oracle/_ref, built from
-/root/reference by oracle/Makefile.ref).  Run in the build container: python tests/golden/make_golden.py"""
+/root/reference by oracle/Makefile.ref).  Run in the build container: python tests/golden/make_golden.py [names...]"""
 import os
 import sys
 
@@ -13,7 +13,7 @@ import refbind
 
 if __name__ == "__main__":
     synth = _pkg.load_synth()
-    for name in cases.GOLDEN:
+    for name in (sys.argv[1:] or cases.GOLDEN):     # optionally only the named fixtures
         case = cases.get_case(name)
         frames = cases.run_reference(refbind, synth, case, planes=True)
         golden_io.save(name, frames)
