@@ -240,7 +240,13 @@ def main():
     def to_t(a):
         return torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
 
-    host = [(to_t(y).pin_memory(), to_t(u).pin_memory(), to_t(v).pin_memory()) for (y, u, v) in frames]
+    def pin(t):
+        try:
+            return t.pin_memory()
+        except RuntimeError:        # page-locking refused (many ranks on one host): pageable uploads still work, slower
+            return t.clone()
+
+    host = [(pin(to_t(y)), pin(to_t(u)), pin(to_t(v))) for (y, u, v) in frames]
     dev = [(y.cuda(), u.cuda(), v.cuda()) for (y, u, v) in host]
     # the pageable copies are only needed for the CPU baseline's sample (rank 0, N = 1): 7.5 GB per rank otherwise
     frames = frames[:wl["cpu_frames"]] if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
