@@ -240,10 +240,13 @@ def main():
     def to_t(a):
         return torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
 
+    pinned_ok = [True]
+
     def pin(t):
         try:
             return t.pin_memory()
         except RuntimeError:        # page-locking refused (many ranks on one host): pageable uploads still work, slower
+            pinned_ok[0] = False
             return t.clone()
 
     host = [(pin(to_t(y)), pin(to_t(u)), pin(to_t(v))) for (y, u, v) in frames]
@@ -416,6 +419,7 @@ def main():
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * bytes_in // (1 << 20))},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(e2e_delta["h2d"]), "d2h_bytes_per_step": int(e2e_delta["d2h"]),
+                    "host_memory": "pinned" if pinned_ok[0] else "pageable (page-locking was refused)",
                     "host_ms_last_step": {k: round(1000.0 * v, 2) for k, v in e2e_prof["host"].items()}},
             "gpu_launches": int(sum(d["launches"] for d in deltas)),
             "clocks": clocks, "roofline": roofline,
