@@ -66,7 +66,8 @@ struct RefLaConfig
     int32_t vbvBufferSize, vbvMaxBitrate, bitrate; /* 0 = CRF */
     int32_t dumpPlanes;             /* keep the 4 lowres planes of every frame */
     int32_t bIntraRefresh;
-    int32_t reserved[7];
+    int32_t gopLookahead;           /* --gop-lookahead */
+    int32_t reserved[6];
 };
 
 struct RefLaFrame
@@ -263,6 +264,7 @@ void* ref_la_open(const RefLaConfig* c)
     p->lookaheadSlices = c->lookaheadSlices;
     p->bFrameBias = c->bFrameBias;
     p->bIntraRefresh = c->bIntraRefresh;
+    p->gopLookahead = c->gopLookahead;
     if (c->vbvBufferSize)
     {
         p->rc.rateControlMode = X265_RC_ABR;

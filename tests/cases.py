@@ -27,6 +27,9 @@ CASES = [
     ("small", 8, 176, 144, 30, dict(cuts=(15,)), dict(bframes=3, lookaheadDepth=10)),
     ("vbv", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
     ("sd", 8, 640, 360, 50, dict(cuts=(25,)), dict(bframes=4, lookaheadDepth=20)),
+    # --gop-lookahead: the keyframe due at frame 20 waits for the scene cut at 22 / has nothing to wait for
+    ("goplookahead_cut", 8, 320, 192, 50, dict(cuts=(22,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=6, bOpenGOP=0)),
+    ("goplookahead_nocut", 8, 320, 192, 50, dict(cuts=(33,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=4)),
     # cooperative search slices (--lookahead-slices with a pool, >= 720 lines, no search batches)
     ("slices_badapt0", 8, 1280, 720, 24, dict(cuts=(12,)), dict(bframes=3, lookaheadDepth=10, bFrameAdaptive=0, poolThreads=4, lookaheadSlices=4)),
     ("slices_badapt1", 10, 1280, 720, 24, dict(cuts=(12,)), dict(bframes=3, lookaheadDepth=10, bFrameAdaptive=1, poolThreads=16, lookaheadSlices=3)),
@@ -49,7 +52,7 @@ REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive
               bOpenGOP="bOpenGOP", aqMode="aqMode", aqStrength="aqStrength", cuTree="cuTree", qCompress="qCompress",
               weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
               scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
-              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices")
+              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead")
 
 
 def la_kwargs(refkw):

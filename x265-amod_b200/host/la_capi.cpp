@@ -44,7 +44,7 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     p.poolWorkers = q->poolWorkers; p.device = q->device; p.extraSlots = q->extraSlots; p.speculate = q->speculate;
     p.pinHost = q->pinHost; p.asyncDepth = q->asyncDepth;
     if (q->pendingMax > 0) p.pendingMax = q->pendingMax;
-    p.shardCount = q->shardCount; p.batchMin = q->batchMin;
+    p.shardCount = q->shardCount; p.batchMin = q->batchMin; p.gopLookahead = q->gopLookahead;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
      * (encoder.cpp:3511-3516,3730-3753): cuTree needs AQ; strength 0 without cuTree disables AQ */
     if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }

@@ -7,7 +7,7 @@
  *
  * Not supported (create() fails with an error string rather than silently diverging):
  * --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
- * zones, radl, gop-lookahead, temporal sub-layers, analysis load, fades, chunked encodes.
+ * zones, radl, temporal sub-layers, analysis load, fades, chunked encodes.
  */
 #include "lookahead.h"
 #include <math.h>
@@ -78,6 +78,8 @@ Lookahead::Lookahead(const LookaheadParam& param)
         m_param.keyframeMin = std::min((int)fps, m_param.keyframeMax / 10);
     }
     m_param.keyframeMin = std::max(1, m_param.keyframeMin);
+    if (m_param.gopLookahead && m_param.gopLookahead > m_param.lookaheadDepth - m_param.bframes - 2)   /* :1060-1064 */
+        m_param.gopLookahead = std::max(0, m_param.lookaheadDepth - m_param.bframes - 2);
     m_lastKeyframe = -m_param.keyframeMax;
     /* asyncDepth extra frames of input delay: the decision only ever analyses the first rc-lookahead frames of the
      * queue (slicetype.cpp:1821-1827, 2609-2616), so the results are the same, but the GPU always holds that many
@@ -827,7 +829,8 @@ void Lookahead::slicetypeDecide()
             frm.sliceType = TYPE_B;
         else if (frm.sliceType == TYPE_BREF && p.bBPyramid && brefs && p.maxNumReferences <= (brefs + 3))
             frm.sliceType = TYPE_B;
-        if ((!p.bIntraRefresh || frm.frameNum == 0) && frm.frameNum - m_lastKeyframe >= p.keyframeMax)
+        if ((!p.bIntraRefresh || frm.frameNum == 0) && frm.frameNum - m_lastKeyframe >= p.keyframeMax &&
+            (!m_extendGopBoundary || frm.frameNum - m_lastKeyframe >= p.keyframeMax + p.gopLookahead))
         {
             if (frm.sliceType == TYPE_AUTO || frm.sliceType == TYPE_I)
                 frm.sliceType = p.bOpenGOP && m_lastKeyframe >= 0 ? TYPE_I : TYPE_IDR;
@@ -970,7 +973,10 @@ void Lookahead::slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe)
     frames[framecnt + 1] = NULL;
 
     int keyFrameLimit = p.keyframeMax + m_lastKeyframe - frames[0]->frameNum - 1;
-    keyintLimit = keyFrameLimit;
+    if (p.gopLookahead && keyFrameLimit <= p.bframes + 1)
+        keyintLimit = keyFrameLimit + p.gopLookahead;
+    else
+        keyintLimit = keyFrameLimit;
     origNumFrames = numFrames = p.bIntraRefresh ? framecnt : std::min(framecnt, keyintLimit);
     if (bIsVbvLookahead)
         numFrames = framecnt;
@@ -1027,6 +1033,25 @@ void Lookahead::slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe)
     {
         frames[1]->sliceType = TYPE_I;
         return;
+    }
+    if (p.gopLookahead && keyFrameLimit >= 0 && keyFrameLimit <= p.bframes + 1)
+    {
+        /* a keyframe is due within this mini-GOP: is there a scene cut shortly behind it worth waiting for? (:2753-2771) */
+        const bool sceneTransition = m_isSceneTransition;
+        m_extendGopBoundary = false;
+        for (int i = p.bframes + 1; i < origNumFrames; i += p.bframes + 1)
+        {
+            scenecut(frames, i, i + 1, true, origNumFrames);
+            for (int j = i + 1; j <= std::min(i + p.bframes + 1, origNumFrames); j++)
+                if (frames[j]->bScenecut && scenecutInternal(frames, j - 1, j, true))
+                {
+                    m_extendGopBoundary = true;
+                    break;
+                }
+            if (m_extendGopBoundary)
+                break;
+        }
+        m_isSceneTransition = sceneTransition;
     }
     if (p.bframes)
     {
@@ -1112,6 +1137,9 @@ void Lookahead::slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe)
 
     if (p.rc.cuTree)
         cuTree(frames, std::min(numFrames, p.keyframeMax), bKeyframe);
+
+    if (p.gopLookahead && keyFrameLimit >= 0 && keyFrameLimit <= p.bframes + 1 && !m_extendGopBoundary)   /* :2896-2897 */
+        keyintLimit = keyFrameLimit;
 
     if (!p.bIntraRefresh)
         for (int j = keyintLimit + 1; j <= numFrames; j += p.keyframeMax)
