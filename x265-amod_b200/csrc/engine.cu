@@ -1441,6 +1441,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
         J.intraCost = slotPtr<int>(c, bs, L.intraCost); J.lowresCosts = (const unsigned short*)costStorePtr(c, bs, cost_store);
         J.invQ = slotPtr<int>(c, bs, L.invQ); J.mv0 = mv0; J.mv1 = mv1;
         J.ref0 = slotPtr<int>(c, p0s, L.propagate); J.ref1 = slotPtr<int>(c, p1s, L.propagate);
+        J.self = slotPtr<int>(c, bs, L.propagate);
         J.bipredWeight = bipred_weight; J.pad = 0; J.fpsFactor = fps_factor;
         c->ctPending++;
         return X265CU_OK;

@@ -1130,6 +1130,8 @@ struct CutreeJobDev
 {
     const int* intraCost; const unsigned short* lowresCosts; const int* invQ; const int* mv0; const int* mv1;
     int* ref0; int* ref1;
+    int* self;          /* the frame's own propagate array: the reference zeroes its first row and uses it as the
+                           (empty) incoming amount of an unreferenced frame (slicetype.cpp:3518-3519, 3534-3535) */
     int bipredWeight, pad;
     double fpsFactor;
 };
@@ -1139,6 +1141,7 @@ __global__ void __launch_bounds__(256) cutree_propagate_batch_kernel(Geom g, con
     const int cu = blockIdx.x * blockDim.x + threadIdx.x;
     if (cu >= g.ncu) return;
     const CutreeJobDev J = jobs[blockIdx.y];
+    if (cu < g.bw) J.self[cu] = 0;      /* observable: that row stays zero in the frame's propagateCost */
     cutreePropagateBlock(g, cu, J.intraCost, J.lowresCosts, J.invQ, J.mv0, J.mv1, NULL, J.ref0, J.ref1, J.bipredWeight, J.fpsFactor);
 }
 
