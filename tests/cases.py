@@ -27,6 +27,17 @@ CASES = [
     ("small", 8, 176, 144, 30, dict(cuts=(15,)), dict(bframes=3, lookaheadDepth=10)),
     ("vbv", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
     ("sd", 8, 640, 360, 50, dict(cuts=(25,)), dict(bframes=4, lookaheadDepth=20)),
+    # more of the parameter space the decisions depend on
+    ("intrarefresh", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, bIntraRefresh=1, bOpenGOP=0, keyframeMax=16)),
+    ("noscenecut", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=4, lookaheadDepth=12, scenecutThreshold=0)),
+    ("bbias", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=4, lookaheadDepth=12, bFrameBias=40)),
+    ("qg16", 10, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=16, aqStrength=1.6)),
+    ("qg64_aq1", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=64, aqMode=1, aqStrength=0.6)),
+    ("deep_la", 8, 320, 192, 70, dict(cuts=(31,)), dict(bframes=5, lookaheadDepth=40)),
+    ("b16_nopyramid", 8, 320, 192, 60, dict(cuts=(), static=True, noise=2), dict(bframes=16, lookaheadDepth=30, bBPyramid=0)),
+    ("fade_weightb_pool", 10, 320, 192, 60, dict(cuts=(), fades=[(15, 14, 0.25)]), dict(bframes=4, lookaheadDepth=12, weightb=1, poolThreads=16)),
+    ("hd_ragged_slices", 8, 1368, 768, 20, dict(cuts=(9,)), dict(bframes=3, lookaheadDepth=10, poolThreads=8, lookaheadSlices=8)),
+    ("keymin", 8, 320, 192, 50, dict(cuts=(8, 15, 22)), dict(bframes=3, lookaheadDepth=10, keyframeMax=30, keyframeMin=12)),
     # --gop-lookahead: the keyframe due at frame 20 waits for the scene cut at 22 / has nothing to wait for
     ("goplookahead_cut", 8, 320, 192, 50, dict(cuts=(22,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=6, bOpenGOP=0)),
     ("goplookahead_nocut", 8, 320, 192, 50, dict(cuts=(33,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=4)),
@@ -52,7 +63,7 @@ REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive
               bOpenGOP="bOpenGOP", aqMode="aqMode", aqStrength="aqStrength", cuTree="cuTree", qCompress="qCompress",
               weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
               scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
-              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead")
+              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh")
 
 
 def la_kwargs(refkw):

@@ -50,6 +50,12 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }
     if (p.rc.aqStrength == 0 && p.rc.cuTree == 0) p.rc.aqMode = 0;
     if (!p.bframes) p.bBPyramid = 0;
+    if (p.bIntraRefresh)        /* encoder.cpp:3761-3779 */
+    {
+        if (p.maxNumReferences > 1) p.maxNumReferences = 1;
+        p.bBPyramid = 0;
+        p.bOpenGOP = 0;
+    }
     Lookahead* la = new (std::nothrow) Lookahead(p);
     if (!la) { if (err && errLen) snprintf(err, errLen, "out of memory"); return NULL; }
     if (!la->create())
