@@ -67,7 +67,8 @@ struct RefLaConfig
     int32_t dumpPlanes;             /* keep the 4 lowres planes of every frame */
     int32_t bIntraRefresh;
     int32_t gopLookahead;           /* --gop-lookahead */
-    int32_t reserved[6];
+    int32_t radl;                   /* --radl */
+    int32_t reserved[5];
 };
 
 struct RefLaFrame
@@ -265,6 +266,7 @@ void* ref_la_open(const RefLaConfig* c)
     p->bFrameBias = c->bFrameBias;
     p->bIntraRefresh = c->bIntraRefresh;
     p->gopLookahead = c->gopLookahead;
+    p->radl = c->radl;
     if (c->vbvBufferSize)
     {
         p->rc.rateControlMode = X265_RC_ABR;

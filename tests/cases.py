@@ -38,6 +38,8 @@ CASES = [
     ("fade_weightb_pool", 10, 320, 192, 60, dict(cuts=(), fades=[(15, 14, 0.25)]), dict(bframes=4, lookaheadDepth=12, weightb=1, poolThreads=16)),
     ("hd_ragged_slices", 8, 1368, 768, 20, dict(cuts=(9,)), dict(bframes=3, lookaheadDepth=10, poolThreads=8, lookaheadSlices=8)),
     ("keymin", 8, 320, 192, 50, dict(cuts=(8, 15, 22)), dict(bframes=3, lookaheadDepth=10, keyframeMax=30, keyframeMin=12)),
+    # --radl: leading B pictures in front of the scene-cut IDRs of a closed GOP
+    ("radl2", 8, 320, 192, 50, dict(cuts=(14, 31)), dict(bframes=3, lookaheadDepth=12, bOpenGOP=0, radl=2, keyframeMax=60, keyframeMin=4)),
     # --gop-lookahead: the keyframe due at frame 20 waits for the scene cut at 22 / has nothing to wait for
     ("goplookahead_cut", 8, 320, 192, 50, dict(cuts=(22,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=6, bOpenGOP=0)),
     ("goplookahead_nocut", 8, 320, 192, 50, dict(cuts=(33,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=4)),
@@ -63,7 +65,7 @@ REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive
               bOpenGOP="bOpenGOP", aqMode="aqMode", aqStrength="aqStrength", cuTree="cuTree", qCompress="qCompress",
               weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
               scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
-              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh")
+              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh", radl="radl")
 
 
 def la_kwargs(refkw):

@@ -44,7 +44,9 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     p.poolWorkers = q->poolWorkers; p.device = q->device; p.extraSlots = q->extraSlots; p.speculate = q->speculate;
     p.pinHost = q->pinHost; p.asyncDepth = q->asyncDepth;
     if (q->pendingMax > 0) p.pendingMax = q->pendingMax;
-    p.shardCount = q->shardCount; p.batchMin = q->batchMin; p.gopLookahead = q->gopLookahead;
+    p.shardCount = q->shardCount; p.batchMin = q->batchMin; p.gopLookahead = q->gopLookahead; p.radl = q->radl;
+    if (p.radl && p.bOpenGOP) p.radl = 0;      /* encoder.cpp:4361-4365 */
+    if (p.radl > p.bframes) p.radl = p.bframes;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
      * (encoder.cpp:3511-3516,3730-3753): cuTree needs AQ; strength 0 without cuTree disables AQ */
     if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }

@@ -28,7 +28,8 @@ typedef struct
     int32_t shardCount;              /* LookaheadParam::shardCount; 0 / 1 = not sharded */
     int32_t batchMin;                /* LookaheadParam::batchMin; 0 = asyncDepth / 2 */
     int32_t gopLookahead;            /* x265_param::gopLookahead */
-    int32_t reserved[3];
+    int32_t radl;                    /* x265_param::radl */
+    int32_t reserved[2];
 } x265la_param;
 
 typedef struct

@@ -7,7 +7,7 @@
  *
  * Not supported (create() fails with an error string rather than silently diverging):
  * --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
- * zones, radl, temporal sub-layers, analysis load, fades, chunked encodes.
+ * zones, temporal sub-layers, analysis load, fades, chunked encodes.
  */
 #include "lookahead.h"
 #include <math.h>
@@ -643,7 +643,7 @@ void Lookahead::fetchResults(const std::vector<Lowres*>& who, int maxPoc)
     struct Ref { Lowres* l; int d0, d1, v; };
     std::vector<Ref> refs;
     for (size_t i = 0; i < who.size(); i++)
-        for (int d0 = 1; d0 < nb; d0++)
+        for (int d0 = 0; d0 < nb; d0++)
             for (int d1 = 0; d1 < nb; d1++)
                 for (int v = 0; v < m_costVariants; v++)
                     if (who[i]->haveCost[d0][d1][v] && !who[i]->resultFetched[d0][d1][v])
@@ -712,7 +712,9 @@ int64_t Lookahead::estimateFrameCost(Lowres** frames, int p0, int p1, int b, boo
         score = fenc->costEst[d0][d1];
     else
     {
-        if (d0 <= 0 || d0 >= nb || d1 < 0 || d1 >= nb) { fail("estimate outside the (bframes+2) window"); return 0; }
+        /* d0 == 0 with d1 > 0: a leading picture in front of a RADL IDR has no list-0 reference and the reference
+         * estimates it against itself (slicetype.cpp:2385-2392 with p0 = b) */
+        if (d0 < 0 || (d0 == 0 && d1 <= 0) || d0 >= nb || d1 < 0 || d1 >= nb) { fail("estimate outside the (bframes+2) window"); return 0; }
         const bool bDoSearch0 = fenc->mvStore[0][d0] < 0;
         const bool bDoSearch1 = p1 > b && fenc->mvStore[1][d1] < 0;
         /* first touch decides which variant of a search the reference would hold: its context (P / B estimate) and,
@@ -820,6 +822,7 @@ void Lookahead::slicetypeDecide()
     if (m_failed) return;
 
     int bframes, brefs;
+    const bool isClosedGopRadl = p.radl && p.keyframeMax != p.keyframeMin;      /* :1933 */
     for (bframes = 0, brefs = 0;; bframes++)
     {
         Lowres& frm = list[bframes]->m_lowres;
@@ -844,11 +847,20 @@ void Lookahead::slicetypeDecide()
             if (p.bOpenGOP) { m_lastKeyframe = frm.frameNum; frm.bKeyframe = true; }
             else frm.sliceType = TYPE_IDR;
         }
+        if (frm.sliceType == TYPE_IDR && frm.bScenecut && isClosedGopRadl)      /* --radl, :1995-2000 */
+        {
+            /* (the reference indexes list[] without checking that the frames exist; a closed-GOP RADL encode whose
+             * last scene cut sits in the final frames of the stream crashes there) */
+            for (int i = bframes; i < bframes + p.radl && list[i]; i++)
+                list[i]->m_lowres.sliceType = TYPE_B;
+            if (list[bframes + p.radl])
+                list[bframes + p.radl]->m_lowres.sliceType = TYPE_IDR;
+        }
         if (frm.sliceType == TYPE_IDR)
         {
             m_lastKeyframe = frm.frameNum;
             frm.bKeyframe = true;
-            if (bframes > 0)
+            if (bframes > 0 && !p.radl)
             {
                 list[bframes - 1]->m_lowres.sliceType = TYPE_P;
                 bframes--;

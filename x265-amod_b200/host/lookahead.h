@@ -42,6 +42,7 @@ struct LookaheadParam
     int bframes, lookaheadDepth, bFrameAdaptive, bBPyramid, bFrameBias;
     int scenecutThreshold; double scenecutBias;   /* bias already divided by 100 (encoder.cpp:3948) */
     int keyframeMax, keyframeMin, bOpenGOP, bIntraRefresh;
+    int radl;            /* --radl: leading pictures kept in front of a scene-cut IDR of a closed GOP */
     int gopLookahead;    /* --gop-lookahead: a keyframe due at the GOP boundary may wait this many frames for a scene cut */
     int bEnableWeightedPred, bEnableWeightedBiPred;
     int lookaheadSlices;
