@@ -306,7 +306,15 @@ void ref_la_effective(void* hv, int32_t* out /* [16] */)
 
 /* push one 4:2:0 picture (pixel = uint8_t or uint16_t per this library's depth);
  * strides in pixels.  Returns total frames decided so far. */
+int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap, int sliceType);
+
 int ref_la_put(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap)
+{
+    return ref_la_put_typed(hv, y, u, v, strideY, strideC, snap, X265_TYPE_AUTO);
+}
+
+/* sliceType: x265_picture::sliceType as the application may force it (Encoder::encode passes it to addPicture) */
+int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap, int sliceType)
 {
     Handle* h = (Handle*)hv;
     x265_param* p = h->enc->m_param;
@@ -330,7 +338,7 @@ int ref_la_put(void* hv, const void* y, const void* u, const void* v, int stride
     f->m_lowres.satdCost = (int64_t)-1;
     f->m_lowresInit = false;
     double t0 = nowSec();
-    h->la->addPicture(*f, X265_TYPE_AUTO);
+    h->la->addPicture(*f, sliceType);
     h->secondsInLookahead += nowSec() - t0;
     drain(h, snap != 0);
     return (int)h->out.size();

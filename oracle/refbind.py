@@ -61,6 +61,7 @@ def load(depth):
     lib.ref_la_open.restype = C.c_void_p
     lib.ref_la_open.argtypes = [C.POINTER(RefLaConfig)]
     lib.ref_la_put.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.ref_la_put_typed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ref_la_flush.argtypes = [C.c_void_p, C.c_int]
     lib.ref_la_num_out.argtypes = [C.c_void_p]
     lib.ref_la_seconds.argtypes = [C.c_void_p]
@@ -112,11 +113,11 @@ class RefLookahead:
         self.effective = dict(zip(names, list(eff)))
         self._fetched = 0
 
-    def put(self, y, u, v, snap=True):
+    def put(self, y, u, v, snap=True, slice_type=0):
         dt = np.uint8 if self.depth == 8 else np.uint16
         y = np.ascontiguousarray(y, dt); u = np.ascontiguousarray(u, dt); v = np.ascontiguousarray(v, dt)
-        return self.lib.ref_la_put(self.h, y.ctypes.data, u.ctypes.data, v.ctypes.data,
-                                   y.shape[1], u.shape[1], 1 if snap else 0)
+        return self.lib.ref_la_put_typed(self.h, y.ctypes.data, u.ctypes.data, v.ctypes.data,
+                                         y.shape[1], u.shape[1], 1 if snap else 0, int(slice_type))
 
     def flush(self, snap=True):
         return self.lib.ref_la_flush(self.h, 1 if snap else 0)

@@ -40,6 +40,8 @@ CASES = [
     ("keymin", 8, 320, 192, 50, dict(cuts=(8, 15, 22)), dict(bframes=3, lookaheadDepth=10, keyframeMax=30, keyframeMin=12)),
     # --radl: leading B pictures in front of the scene-cut IDRs of a closed GOP
     ("radl2", 8, 320, 192, 50, dict(cuts=(14, 31)), dict(bframes=3, lookaheadDepth=12, bOpenGOP=0, radl=2, keyframeMax=60, keyframeMin=4)),
+    # slice types forced by the application (IDR, P, B runs, I) in the middle of automatic decisions
+    ("forced_types", 8, 320, 192, 44, dict(cuts=(29,)), dict(bframes=3, lookaheadDepth=10)),
     # --gop-lookahead: the keyframe due at frame 20 waits for the scene cut at 22 / has nothing to wait for
     ("goplookahead_cut", 8, 320, 192, 50, dict(cuts=(22,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=6, bOpenGOP=0)),
     ("goplookahead_nocut", 8, 320, 192, 50, dict(cuts=(33,)), dict(bframes=3, lookaheadDepth=16, keyframeMax=20, keyframeMin=2, gopLookahead=4)),
@@ -87,12 +89,23 @@ def make_seq(synth, case):
     return synth.SynthSequence(w, h, depth=depth, seed=1, **skw)
 
 
+# application-forced slice types (x265_picture::sliceType) per case: {poc: X265_TYPE_*}; 1 IDR, 2 I, 3 P, 4 BREF, 5 B
+FORCED = {
+    "forced_types": {9: 1, 16: 3, 17: 3, 23: 5, 24: 5, 25: 3, 33: 2},
+}
+
+# cases only the CPU suite runs (host logic through the sim engine against the live reference): added after this
+# round's GPU budget was spent, they join the GPU list once they have been seen green on hardware
+CPU_ONLY = ["forced_types"]
+
+
 def run_reference(refbind, synth, case, planes=True):
     name, depth, w, h, n, skw, rkw = case
     seq = make_seq(synth, case)
     ref = refbind.RefLookahead(w, h, depth=depth, dumpPlanes=1 if planes else 0, **rkw)
+    forced = FORCED.get(name, {})
     for i in range(n):
-        ref.put(*seq.frame(i))
+        ref.put(*seq.frame(i), slice_type=forced.get(i, 0))
     ref.flush()
     out = ref.frames()
     ref.close()
@@ -105,6 +118,6 @@ def run_ours(pkg, synth, case, lib_path=None, planes=True, **extra):
     kw = la_kwargs(rkw)
     kw.update(extra)
     la = pkg.Lookahead(w, h, depth=depth, lib_path=lib_path, **kw)
-    out = pkg.run_sequence(la, (seq.frame(i) for i in range(n)), planes=planes)
+    out = pkg.run_sequence(la, (seq.frame(i) for i in range(n)), planes=planes, slice_types=FORCED.get(name))
     la.close()
     return out

@@ -124,7 +124,7 @@ def test_cuda_pipeline_matches_golden(name, pkg, synth):
         assert w["planesum"] == golden_io.planesum(g["planes"]), "lowres planes differ at poc %d" % w["poc"]
 
 
-@pytest.mark.parametrize("name", [c[0] for c in cases.CASES])
+@pytest.mark.parametrize("name", [c[0] for c in cases.CASES if c[0] not in cases.CPU_ONLY])
 def test_cuda_pipeline_matches_reference_or_oracle(name, pkg, synth, simdir):
     case = cases.get_case(name)
     if refbind.available(case[1]):

@@ -264,9 +264,10 @@ class Lookahead:
             pass
 
 
-def run_sequence(la, frames_iter, collect=True, planes=False, estimate_cost=False):
+def run_sequence(la, frames_iter, collect=True, planes=False, estimate_cost=False, slice_types=None):
     """Drive a Lookahead the way Encoder::encode does (one picture in, drain what is decided),
-    then flush.  Returns the decided frames (dicts) in output order."""
+    then flush.  Returns the decided frames (dicts) in output order.  slice_types: {poc: forced type}
+    (x265_picture::sliceType as an application may set it)."""
     out = []
 
     def drain():
@@ -282,7 +283,7 @@ def run_sequence(la, frames_iter, collect=True, planes=False, estimate_cost=Fals
             la.release(info.handle)
 
     for i, (y, u, v) in enumerate(frames_iter):
-        la.add_picture(y, u, v, pts=i)
+        la.add_picture(y, u, v, pts=i, slice_type=(slice_types or {}).get(i, TYPE_AUTO))
         drain()
     la.flush()
     drain()
