@@ -31,7 +31,7 @@ extern "C" {
 #define X265CU_ERR_BAD_ARG     -2
 #define X265CU_ERR_NO_MEMORY   -3
 #define X265CU_ERR_CUDA        -4   /* a CUDA call or kernel failed; see x265cu_last_error */
-#define X265CU_ERR_UNSUPPORTED -5   /* configuration outside the hot path (qg-size 8, HME, ...) */
+#define X265CU_ERR_UNSUPPORTED -5   /* configuration outside the hot path (12-bit, HME, ...) */
 
 typedef struct x265cu_ctx x265cu_ctx;
 
@@ -44,7 +44,8 @@ typedef struct
     int32_t max_cu_size;        /* x265_param::maxCUSize (plane margins, picyuv.cpp:87-88) */
     int32_t bframes;            /* x265_param::bframes; per-frame arrays are (bframes+2) wide */
     int32_t max_slots;          /* frame slots resident in HBM */
-    int32_t qg_size;            /* x265_param::rc.qgSize; 16/32/64 (8 -> X265CU_ERR_UNSUPPORTED) */
+    int32_t qg_size;            /* x265_param::rc.qgSize: 8, 16, 32 or 64.  8 = AQ on 8x8 full-res blocks: the qp-offset arrays
+                                   hold ncu_full = 4 * ncu entries, addressed like the reference (lowres.h:98-106) */
     int32_t aq_mode;            /* x265_param::rc.aqMode 0..3 */
     double  aq_strength;        /* x265_param::rc.aqStrength */
     int32_t need_aq;            /* Lookahead::m_bAdaptiveQuant (slicetype.cpp:1013-1017) */
@@ -72,6 +73,7 @@ typedef struct
     int32_t nb;                      /* bframes + 2 */
     int32_t n_mv_stores;             /* MV stores per slot  = 3*nb (see x265cu_search_job::store) */
     int32_t n_cost_stores;           /* cost stores per slot = 2*nb*nb */
+    int32_t ncu_full;                /* entries of qpAqOffset / qpCuTreeOffset / invQscaleFactor: ncu, or 4 * ncu with qg-size 8 */
 } x265cu_geometry;
 
 int  x265cu_device_count(void);
@@ -200,14 +202,25 @@ int  x265cu_cutree_finish(x265cu_ctx* ctx, int32_t slot, int32_t fps_factor_fix8
 int  x265cu_cost_recalc(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, int32_t use_cutree_offsets,
                         int64_t* score, int32_t* row_satds);
 
+/* The VBV half of Lookahead::getEstimatedPictureCost (slicetype.cpp:1387-1436): lowresCostForRc = the block costs of cost
+ * store `cost_store` (0 = the intra estimate) and intraCost, both scaled by the block's qp offset (qp_source 0 = none,
+ * 1 = qpAqOffset, 2 = qpCuTreeOffset), and their sums per CTU row of `ctu_rows_lowres` lowres block rows
+ * (maxCUSize / 16): what the reference adds to FrameData::m_rowStat[].satdForVbv / intraSatdForVbv.  pir_start / pir_end:
+ * the intra-refresh columns of a P slice (:1425-1427), -1 = none.  Outputs are host arrays (NULL = skip): n_rows sums each,
+ * ncu scaled costs each.  The device copies of intraCost / lowresCosts are NOT modified (the reference rewrites its host
+ * arrays in place; the caller's mirrors receive the same values).  synchronises */
+int  x265cu_vbv_row_costs(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, int32_t qp_source, int32_t ctu_rows_lowres,
+                          int32_t pir_start, int32_t pir_end, int32_t n_rows, uint32_t* satd_for_vbv, uint32_t* intra_satd_for_vbv,
+                          uint16_t* lowres_cost_for_rc, int32_t* intra_cost_scaled);
+
 /* ---- host mirrors of Lowres fields (all synchronise; NULL pointers are skipped) */
 typedef struct
 {
     int32_t*  intra_cost;        /* ncu */
     uint8_t*  intra_mode;        /* ncu */
-    double*   qp_aq_offset;      /* ncu */
-    double*   qp_cutree_offset;  /* ncu */
-    int32_t*  inv_qscale_factor; /* ncu */
+    double*   qp_aq_offset;      /* ncu_full */
+    double*   qp_cutree_offset;  /* ncu_full */
+    int32_t*  inv_qscale_factor; /* ncu_full */
     uint16_t* propagate_cost;    /* ncu */
     void*     planes;            /* 4 * stride * plane_lines samples: Lowres::buffer[0] */
     uint16_t* lowres_costs00;    /* ncu: lowresCosts[0][0] */

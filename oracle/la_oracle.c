@@ -29,7 +29,7 @@ void or_geom_init(or_geom* g, int picW, int picH, int maxCUSize)
     g->planeLines = g->h + 2 * g->my;
     g->planeSize = (int64_t)g->stride * g->planeLines;
     g->padOffset = (int64_t)g->stride * g->my + g->mx;
-    g->rowsPerSlice = 0; g->pad = 0;
+    g->rowsPerSlice = 0; g->qg8 = 0;
 }
 
 /* common/constants.cpp:34-90: lambda = 2^(qp/6 - 2) * 2^(depth-8); X265_LOOKAHEAD_QP = 12 + 6*(depth-8)
@@ -183,19 +183,24 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
                  uint32_t* blockEnergy, uint64_t wp_ssd[3], uint64_t wp_sum[3])
 {
     const int W = g->picW, H = g->picH;
-    const int blockCount = g->ncu;
-    const float modeOneConst = 14.427f, modeTwoConst = 11.f;
+    /* slicetype.cpp:459-472: qg-size 8 works on 8x8 luma / 4x4 chroma blocks; the arrays hold blockCount entries but the
+     * loops below visit ceil(W / incr) * ceil(H / incr) blocks with a running index */
+    const int qg8 = g->qg8;
+    const int blockCount = qg8 ? 4 * g->ncu : g->ncu;
+    const int incr = qg8 ? 8 : 16;
+    const float modeOneConst = qg8 ? 11.427f : 14.427f, modeTwoConst = qg8 ? 8.f : 11.f;
     for (int i = 0; i < 3; i++) wp_ssd[i] = wp_sum[i] = 0;
-    uint32_t* energy = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)blockCount);
+    const int visited = ((W + incr - 1) / incr) * ((H + incr - 1) / incr);
+    uint32_t* energy = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(visited > blockCount ? visited : blockCount));
     int n = 0;
-    for (int by = 0; by < H; by += 16)
-        for (int bx = 0; bx < W; bx += 16, n++)
+    for (int by = 0; by < H; by += incr)
+        for (int bx = 0; bx < W; bx += incr, n++)
         {
-            uint32_t e = block_energy(y, strideY, W, H, bx, by, 16, 8, &wp_sum[0], &wp_ssd[0]);
+            uint32_t e = block_energy(y, strideY, W, H, bx, by, incr, qg8 ? 6 : 8, &wp_sum[0], &wp_ssd[0]);
             if (u && v)
             {
-                e += block_energy(u, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, 8, 6, &wp_sum[1], &wp_ssd[1]);
-                e += block_energy(v, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, 8, 6, &wp_sum[2], &wp_ssd[2]);
+                e += block_energy(u, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, incr / 2, qg8 ? 4 : 6, &wp_sum[1], &wp_ssd[1]);
+                e += block_energy(v, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, incr / 2, qg8 ? 4 : 6, &wp_sum[2], &wp_ssd[2]);
             }
             energy[n] = e;
             if (blockEnergy) blockEnergy[n] = e;
@@ -212,7 +217,7 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
         if (aqMode == 2 || aqMode == 3)
         {
             double bit_depth_correction = 1.f / (1 << (2 * (OR_DEPTH - 8)));
-            for (int i = 0; i < blockCount; i++)
+            for (int i = 0; i < visited; i++)
             {
                 qp_adj = pow(energy[i] * bit_depth_correction + 1, 0.1);
                 qpCuTreeOffset[i] = qp_adj;
@@ -227,7 +232,7 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
         }
         else
             strength = aqStrength * 1.0397f;
-        for (int i = 0; i < blockCount; i++)
+        for (int i = 0; i < visited; i++)
         {
             if (aqMode == 3)
             {
@@ -886,6 +891,28 @@ void or_cutree_finish(const or_geom* g, const int32_t* intraCost, const int32_t*
                       const uint16_t* propagateCost, const double* qpAqOffset, double* qpCuTreeOffset,
                       int fpsFactorFix8, double weightdelta, double cuTreeStrength)
 {
+    if (g->qg8)
+    {
+        /* slicetype.cpp:3764-3782; invQ = invQscaleFactor8x8 */
+        const int fs = 2 * g->bw;
+        for (int cuY = 0; cuY < g->bh; cuY++)
+            for (int cuX = 0; cuX < g->bw; cuX++)
+            {
+                const int cu = cuX + cuY * g->bw;
+                int intracost = ((intraCost[cu]) / 4 * invQ[cu] + 128) >> 8;
+                if (intracost)
+                {
+                    int propagate = ((propagateCost[cu]) / 4 * fpsFactorFix8 + 128) >> 8;
+                    double log2_ratio = log2((double)(intracost + propagate)) - log2((double)intracost) + weightdelta;
+                    const int i = cuX * 2 + cuY * g->bw * 4;
+                    qpCuTreeOffset[i] = qpAqOffset[i] - cuTreeStrength * (log2_ratio);
+                    qpCuTreeOffset[i + 1] = qpAqOffset[i + 1] - cuTreeStrength * (log2_ratio);
+                    qpCuTreeOffset[i + fs] = qpAqOffset[i + fs] - cuTreeStrength * (log2_ratio);
+                    qpCuTreeOffset[i + fs + 1] = qpAqOffset[i + fs + 1] - cuTreeStrength * (log2_ratio);
+                }
+            }
+        return;
+    }
     for (int i = 0; i < g->ncu; i++)
     {
         int intracost = (intraCost[i] * invQ[i] + 128) >> 8;
@@ -896,6 +923,25 @@ void or_cutree_finish(const or_geom* g, const int32_t* intraCost, const int32_t*
             qpCuTreeOffset[i] = qpAqOffset[i] - cuTreeStrength * log2_ratio;
         }
     }
+}
+
+/* qg-size 8: the lowres block's factor is the mean of its four 8x8 factors (slicetype.cpp:656-670) */
+void or_invq8x8(const or_geom* g, const int32_t* invQ, int32_t* invQ8)
+{
+    const int fs = 2 * g->bw;
+    for (int cuY = 0; cuY < g->bh; cuY++)
+        for (int cuX = 0; cuX < g->bw; cuX++)
+        {
+            const int i = cuX * 2 + cuY * g->bw * 4;
+            invQ8[cuX + cuY * g->bw] = (invQ[i] + invQ[i + 1] + invQ[i + fs] + invQ[i + fs + 1]) / 4;
+        }
+}
+
+static double block_qp_offset(const or_geom* g, const double* qp, int cux, int cuy)
+{
+    if (!g->qg8) return qp[cux + cuy * g->bw];
+    const int fs = 2 * g->bw, i = cux * 2 + cuy * g->bw * 4;
+    return (qp[i] + qp[i + 1] + qp[i + fs] + qp[i + fs + 1]) / 4;
 }
 
 /* slicetype.cpp:3847-3878 */
@@ -909,11 +955,50 @@ int64_t or_frame_cost_recalc(const or_geom* g, const uint16_t* lowresCosts, cons
         {
             int cu = cux + cuy * g->bw;
             int cuCost = lowresCosts[cu] & OR_LOWRES_COST_MASK;
-            cuCost = (cuCost * or_exp2fix8(qpOffset[cu]) + 128) >> 8;
+            cuCost = (cuCost * or_exp2fix8(block_qp_offset(g, qpOffset, cux, cuy)) + 128) >> 8;
             rowSatds[cuy] += cuCost;
             if ((cuy > 0 && cuy < g->bh - 1 && cux > 0 && cux < g->bw - 1) || g->bw <= 2 || g->bh <= 2)
                 score += cuCost;
         }
     }
     return score;
+}
+
+/* the VBV half of getEstimatedPictureCost (slicetype.cpp:1387-1436); qpOffset may be NULL */
+void or_vbv_rows(const or_geom* g, const uint16_t* lowresCosts, const int32_t* intraCost, const double* qpOffset,
+                 int scale, int pirStart, int pirEnd, int nRows, uint32_t* satdForVbv, uint32_t* intraSatdForVbv,
+                 uint16_t* lowresCostForRc, int32_t* intraCostScaled)
+{
+    for (int i = 0; i < nRows; i++) satdForVbv[i] = intraSatdForVbv[i] = 0;
+    for (int row = 0; row < nRows; row++)
+    {
+        int lowresRow = row * scale;
+        for (int cnt = 0; cnt < scale && lowresRow < g->bh; lowresRow++, cnt++)
+        {
+            uint32_t sum = 0, intraSum = 0;
+            int diff = 0;
+            int idx = lowresRow * g->bw;
+            for (int col = 0; col < g->bw; col++, idx++)
+            {
+                uint16_t c = lowresCosts[idx] & OR_LOWRES_COST_MASK;
+                int32_t ic = intraCost[idx];
+                if (qpOffset)
+                {
+                    double q = block_qp_offset(g, qpOffset, col, lowresRow);
+                    c = (uint16_t)((c * or_exp2fix8(q) + 128) >> 8);
+                    ic = (ic * or_exp2fix8(q) + 128) >> 8;
+                }
+                if (pirStart >= 0)
+                    for (int x = pirStart; x <= pirEnd; x++)
+                        diff += ic - c;
+                lowresCostForRc[idx] = c;
+                intraCostScaled[idx] = ic;
+                sum += c;
+                intraSum += ic;
+            }
+            satdForVbv[row] += sum;
+            satdForVbv[row] += diff;
+            intraSatdForVbv[row] += intraSum;
+        }
+    }
 }

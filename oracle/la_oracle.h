@@ -43,7 +43,7 @@ typedef struct
     int64_t padOffset;      /* my*stride + mx */
     int32_t rowsPerSlice;   /* Lookahead::m_numRowsPerSlice when the searches run as cooperative slices
                                (slicetype.cpp:1047-1059, 3957-3968); 0 = whole frame */
-    int32_t pad;
+    int32_t qg8;            /* 1 = qg-size 8: AQ on 8x8 full-res blocks, 4 * ncu qp-offset entries (lowres.cpp:86-89) */
 } or_geom;
 
 int  or_depth(void);
@@ -63,8 +63,9 @@ int  or_satd8x8(const or_pixel* a, int sa, const or_pixel* b, int sb);  /* pixel
  * what PicYuv::copyFromPicture's padding (picyuv.cpp:261-285,480-512) amounts to. */
 void or_lowres_init(const or_geom* g, const or_pixel* srcY, int srcStride, or_pixel* buf);
 
-/* calcAdaptiveQuantFrame for qg-size > 8 (16x16 luma blocks), aq-mode 0..3
- * (encoder/slicetype.cpp:452-713).  Chroma may be NULL (treated as 4:0:0). */
+/* calcAdaptiveQuantFrame, aq-mode 0..3 (encoder/slicetype.cpp:452-713); g->qg8 selects 8x8 blocks, in which case the
+ * three output arrays hold 4 * ncu entries (+ a row of slack for the running index) and must come in zeroed.
+ * Chroma may be NULL (treated as 4:0:0). */
 void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v,
                  int strideC, int aqMode, double aqStrength, int bWeightP,
                  double* qpAqOffset, double* qpCuTreeOffset, int32_t* invQscaleFactor,
@@ -119,6 +120,13 @@ void or_cutree_finish(const or_geom* g, const int32_t* intraCost, const int32_t*
 /* frameCostRecalculate (slicetype.cpp:3802-3879, non-hevc-aq branch) */
 int64_t or_frame_cost_recalc(const or_geom* g, const uint16_t* lowresCosts, const double* qpOffset,
                              int32_t* rowSatds);
+/* qg-size 8: invQscaleFactor8x8 (slicetype.cpp:656-670) */
+void or_invq8x8(const or_geom* g, const int32_t* invQ, int32_t* invQ8);
+/* the VBV row aggregation of getEstimatedPictureCost (slicetype.cpp:1387-1436); qpOffset NULL = no scaling,
+ * pirStart < 0 = no intra-refresh term */
+void or_vbv_rows(const or_geom* g, const uint16_t* lowresCosts, const int32_t* intraCost, const double* qpOffset,
+                 int scale, int pirStart, int pirEnd, int nRows, uint32_t* satdForVbv, uint32_t* intraSatdForVbv,
+                 uint16_t* lowresCostForRc, int32_t* intraCostScaled);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,7 @@ struct RefLaConfig
     int32_t weightp, weightb;
     int32_t poolThreads;            /* 0 = no pool (everything on the caller) */
     int32_t lookaheadSlices;
-    int32_t qgSize;                 /* 16/32/64 (8 not supported by the CUDA path yet) */
+    int32_t qgSize;                 /* 8/16/32/64 */
     int32_t bFrameBias;
     double  scenecutBias;           /* percent, as --scenecut-bias */
     int32_t vbvBufferSize, vbvMaxBitrate, bitrate; /* 0 = CRF */
@@ -68,7 +68,9 @@ struct RefLaConfig
     int32_t bIntraRefresh;
     int32_t gopLookahead;           /* --gop-lookahead */
     int32_t radl;                   /* --radl */
-    int32_t reserved[5];
+    int32_t keepFrames;             /* drained frames kept alive (0 = just what the lookahead itself still references);
+                                       ref_la_estimate needs a frame and its references alive */
+    int32_t reserved[4];
 };
 
 struct RefLaFrame
@@ -93,6 +95,18 @@ struct RefLaFrame
     uint64_t wp_ssd[3], wp_sum[3];
     const double*   weightedCostDelta; /* nb */
     const void*     planes;         /* 4*stride*planeLines pixels or NULL */
+    int32_t ncuFull;                /* entries of qpAqOffset / qpCuTreeOffset / invQscaleFactor (4*ncu with qg-size 8) */
+    int32_t indB;                   /* Lowres::indB */
+    const int64_t*  plannedSatd;    /* X265_LOOKAHEAD_MAX + 1 */
+    const int32_t*  plannedType;    /* X265_LOOKAHEAD_MAX + 1 */
+    /* filled by ref_la_estimate (Lookahead::getEstimatedPictureCost on this frame), else estimated == 0 */
+    int32_t estimated, vbvRows;
+    int64_t estSatdCost;            /* Lowres::satdCost afterwards */
+    const uint32_t* satdForVbv;     /* vbvRows: FrameData::m_rowStat[].satdForVbv */
+    const uint32_t* intraSatdForVbv;
+    const uint16_t* lowresCostForRc;/* ncu, after the in-place scaling of slicetype.cpp:1411-1428 */
+    const int32_t*  intraCostForRc; /* ncu, Lowres::intraCost after the same */
+    const int32_t*  estRowSatds;    /* bh: rowSatds of the coded estimate after frameCostRecalculate */
 };
 
 } // extern "C"
@@ -108,6 +122,11 @@ struct FrameSnap
     std::vector<uint8_t> intraMode;
     std::vector<double> qpAq, qpCuTree, wdelta;
     std::vector<pixel> planes;
+    std::vector<int64_t> plannedSatd;
+    std::vector<int32_t> plannedType, intraCostForRc, estRowSatds;
+    std::vector<uint32_t> satdForVbv, intraSatdForVbv;
+    std::vector<uint16_t> lowresCostForRc;
+    Frame* frame;                    /* NULL once the frame was destroyed */
 };
 
 struct Handle
@@ -163,16 +182,23 @@ void snapshot(Handle* h, Frame* f)
         }
     s->intraCost.assign(l.intraCost, l.intraCost + ncu);
     s->intraMode.assign(l.intraMode, l.intraMode + ncu);
+    const int ncuFull = h->enc->m_param->rc.qgSize == 8 ? 4 * ncu : ncu;      /* lowres.cpp:89 */
+    s->h.ncuFull = ncuFull;
     if (l.qpAqOffset)
     {
-        s->qpAq.assign(l.qpAqOffset, l.qpAqOffset + ncu);
-        s->qpCuTree.assign(l.qpCuTreeOffset, l.qpCuTreeOffset + ncu);
-        s->invQ.assign(l.invQscaleFactor, l.invQscaleFactor + ncu);
+        s->qpAq.assign(l.qpAqOffset, l.qpAqOffset + ncuFull);
+        s->qpCuTree.assign(l.qpCuTreeOffset, l.qpCuTreeOffset + ncuFull);
+        s->invQ.assign(l.invQscaleFactor, l.invQscaleFactor + ncuFull);
     }
     else
     {
-        s->qpAq.assign(ncu, 0.0); s->qpCuTree.assign(ncu, 0.0); s->invQ.assign(ncu, 256);
+        s->qpAq.assign(ncuFull, 0.0); s->qpCuTree.assign(ncuFull, 0.0); s->invQ.assign(ncuFull, 256);
     }
+    s->h.indB = l.indB;
+    s->plannedSatd.assign(l.plannedSatd, l.plannedSatd + X265_LOOKAHEAD_MAX + 1);
+    s->plannedType.assign(l.plannedType, l.plannedType + X265_LOOKAHEAD_MAX + 1);
+    s->h.plannedSatd = s->plannedSatd.data(); s->h.plannedType = s->plannedType.data();
+    s->frame = f;
     s->propagate.assign(l.propagateCost, l.propagateCost + ncu);
     for (int i = 0; i < 3; i++) { s->h.wp_ssd[i] = l.wp_ssd[i]; s->h.wp_sum[i] = l.wp_sum[i]; }
     if (h->cfg.dumpPlanes)
@@ -211,6 +237,7 @@ void drain(Handle* h, bool snap)
         {
             FrameSnap* s = new FrameSnap;
             memset(&s->h, 0, sizeof(s->h));
+            s->frame = f;
             s->h.poc = f->m_poc; s->h.sliceType = f->m_lowres.sliceType;
             s->h.bScenecut = f->m_lowres.bScenecut; s->h.bKeyframe = f->m_lowres.bKeyframe;
             h->out.push_back(s);
@@ -219,10 +246,13 @@ void drain(Handle* h, bool snap)
         /* keep a bounded tail alive: m_lastNonB and cuTree only ever look at the most
          * recent non-B, so anything older than 2*(bframes+2) drained frames is dead */
         size_t keep = 2 * (size_t)(h->enc->m_param->bframes + 2) + 2;
+        if (h->cfg.keepFrames > (int)keep) keep = h->cfg.keepFrames;
         while (h->retired.size() > keep)
         {
             Frame* old = h->retired.front();
             h->retired.erase(h->retired.begin());
+            for (size_t k = 0; k < h->out.size(); k++)
+                if (h->out[k]->frame == old) h->out[k]->frame = NULL;
             old->destroy();
             delete old;
         }
@@ -306,15 +336,19 @@ void ref_la_effective(void* hv, int32_t* out /* [16] */)
 
 /* push one 4:2:0 picture (pixel = uint8_t or uint16_t per this library's depth);
  * strides in pixels.  Returns total frames decided so far. */
-int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap, int sliceType);
+int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap, int sliceType,
+                     int sliceTypeReq);
 
 int ref_la_put(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap)
 {
-    return ref_la_put_typed(hv, y, u, v, strideY, strideC, snap, X265_TYPE_AUTO);
+    return ref_la_put_typed(hv, y, u, v, strideY, strideC, snap, X265_TYPE_AUTO, X265_TYPE_AUTO);
 }
 
-/* sliceType: x265_picture::sliceType as the application may force it (Encoder::encode passes it to addPicture) */
-int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap, int sliceType)
+/* The two ways a slice type reaches the lookahead, exactly as Encoder::encode does it (encoder.cpp:1713-1714, 1863):
+ * sliceTypeReq = x265_picture::sliceType forced by the application -> Frame::m_lowres.sliceTypeReq;
+ * sliceType    = the first-pass type of a 2-pass encode            -> the argument of Lookahead::addPicture */
+int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int strideY, int strideC, int snap, int sliceType,
+                     int sliceTypeReq)
 {
     Handle* h = (Handle*)hv;
     x265_param* p = h->enc->m_param;
@@ -333,7 +367,7 @@ int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int 
     f->m_poc = h->pocNext;
     f->m_pts = h->pocNext;
     h->pocNext++;
-    f->m_lowres.sliceTypeReq = X265_TYPE_AUTO;
+    f->m_lowres.sliceTypeReq = sliceTypeReq;
     f->m_lowres.bScenecut = false;
     f->m_lowres.satdCost = (int64_t)-1;
     f->m_lowresInit = false;
@@ -358,6 +392,63 @@ int ref_la_flush(void* hv, int snap)
             break;
     }
     return (int)h->out.size();
+}
+
+/* Lookahead::getEstimatedPictureCost (slicetype.cpp:1327-1439) on decided frame `idx` (output order) with the list-0 /
+ * list-1 references `idxRef0` / `idxRef1` (-1 = none), the way Encoder::encode calls it for the frame about to be coded
+ * (encoder.cpp:2367).  The reference reads the references from the slice header, so a minimal FrameData / Slice is put
+ * in front of it.  The frame's satdCost, the per-CTU-row VBV sums and the arrays the call rescales in place are added
+ * to the frame's snapshot.  Returns 0, or -1 when one of the frames is no longer alive. */
+int ref_la_estimate(void* hv, int idx, int idxRef0, int idxRef1, int pirStartCol, int pirEndCol)
+{
+    Handle* h = (Handle*)hv;
+    const int n = (int)h->out.size();
+    if (idx < 0 || idx >= n || idxRef0 >= n || idxRef1 >= n) return -1;
+    FrameSnap* s = h->out[idx];
+    Frame* cur = s->frame;
+    Frame* r0 = idxRef0 >= 0 ? h->out[idxRef0]->frame : NULL;
+    Frame* r1 = idxRef1 >= 0 ? h->out[idxRef1]->frame : NULL;
+    if (!cur || (idxRef0 >= 0 && !r0) || (idxRef1 >= 0 && !r1)) return -1;
+    x265_param* p = h->enc->m_param;
+    const int rows = (p->sourceHeight + p->maxCUSize - 1) / p->maxCUSize;
+    FrameData fd;
+    Slice slice;
+    std::vector<FrameData::RCStatRow> rowStat(rows);
+    memset(rowStat.data(), 0, rows * sizeof(FrameData::RCStatRow));
+    fd.m_slice = &slice; fd.m_rowStat = rowStat.data();
+    fd.m_pir.pirStartCol = pirStartCol; fd.m_pir.pirEndCol = pirEndCol;
+    const int t = cur->m_lowres.sliceType;
+    slice.m_sliceType = IS_X265_TYPE_I(t) ? I_SLICE : (t == X265_TYPE_P ? P_SLICE : B_SLICE);
+    slice.m_poc = cur->m_poc;
+    slice.m_rps.numberOfNegativePictures = r0 ? 1 : 0;
+    if (r0) { slice.m_refPOCList[0][0] = r0->m_poc; slice.m_refFrameList[0][0] = r0; }
+    if (r1) { slice.m_refPOCList[1][0] = r1->m_poc; slice.m_refFrameList[1][0] = r1; }
+    FrameData* saved = cur->m_encData;
+    cur->m_encData = &fd;
+    h->la->getEstimatedPictureCost(cur);
+    cur->m_encData = saved;
+    fd.m_slice = NULL; fd.m_rowStat = NULL;
+    Lowres& l = cur->m_lowres;
+    const int ncu = l.maxBlocksInRow * l.maxBlocksInCol;
+    s->h.estimated = 1; s->h.vbvRows = rows; s->h.estSatdCost = l.satdCost;
+    s->satdForVbv.resize(rows); s->intraSatdForVbv.resize(rows);
+    for (int i = 0; i < rows; i++) { s->satdForVbv[i] = rowStat[i].satdForVbv; s->intraSatdForVbv[i] = rowStat[i].intraSatdForVbv; }
+    if (p->rc.vbvBufferSize && p->rc.vbvMaxBitrate && l.lowresCostForRc)
+        s->lowresCostForRc.assign(l.lowresCostForRc, l.lowresCostForRc + ncu);
+    else
+        s->lowresCostForRc.assign(ncu, 0);
+    s->intraCostForRc.assign(l.intraCost, l.intraCost + ncu);
+    {
+        /* which estimate it read: the same derivation as the call itself */
+        int d0 = 0, d1 = 0;
+        if (slice.m_sliceType == P_SLICE) d0 = cur->m_poc - r0->m_poc;
+        else if (slice.m_sliceType == B_SLICE) { d0 = r0 ? cur->m_poc - r0->m_poc : 0; d1 = r1->m_poc - cur->m_poc; }
+        s->estRowSatds.assign(l.rowSatds[d0][d1], l.rowSatds[d0][d1] + l.maxBlocksInCol);
+    }
+    s->h.satdForVbv = s->satdForVbv.data(); s->h.intraSatdForVbv = s->intraSatdForVbv.data();
+    s->h.lowresCostForRc = s->lowresCostForRc.data(); s->h.intraCostForRc = s->intraCostForRc.data();
+    s->h.estRowSatds = s->estRowSatds.data();
+    return 0;
 }
 
 int ref_la_num_out(void* hv) { return (int)((Handle*)hv)->out.size(); }

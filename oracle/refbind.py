@@ -19,7 +19,8 @@ class RefLaConfig(C.Structure):
                 ("lookaheadSlices", C.c_int32), ("qgSize", C.c_int32), ("bFrameBias", C.c_int32),
                 ("scenecutBias", C.c_double), ("vbvBufferSize", C.c_int32), ("vbvMaxBitrate", C.c_int32),
                 ("bitrate", C.c_int32), ("dumpPlanes", C.c_int32), ("bIntraRefresh", C.c_int32),
-                ("gopLookahead", C.c_int32), ("radl", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("gopLookahead", C.c_int32), ("radl", C.c_int32), ("keepFrames", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class RefLaFrame(C.Structure):
@@ -32,14 +33,18 @@ class RefLaFrame(C.Structure):
                 ("mvCosts", C.c_void_p), ("intraCost", C.c_void_p), ("intraMode", C.c_void_p),
                 ("qpAqOffset", C.c_void_p), ("qpCuTreeOffset", C.c_void_p), ("invQscaleFactor", C.c_void_p),
                 ("propagateCost", C.c_void_p), ("wp_ssd", C.c_uint64 * 3), ("wp_sum", C.c_uint64 * 3),
-                ("weightedCostDelta", C.c_void_p), ("planes", C.c_void_p)]
+                ("weightedCostDelta", C.c_void_p), ("planes", C.c_void_p),
+                ("ncuFull", C.c_int32), ("indB", C.c_int32), ("plannedSatd", C.c_void_p), ("plannedType", C.c_void_p),
+                ("estimated", C.c_int32), ("vbvRows", C.c_int32), ("estSatdCost", C.c_int64),
+                ("satdForVbv", C.c_void_p), ("intraSatdForVbv", C.c_void_p), ("lowresCostForRc", C.c_void_p),
+                ("intraCostForRc", C.c_void_p), ("estRowSatds", C.c_void_p)]
 
 
 DEFAULTS = dict(fpsNum=30, fpsDenom=1, bframes=4, lookaheadDepth=20, bFrameAdaptive=2, bBPyramid=1,
                 scenecutThreshold=40, keyframeMax=250, keyframeMin=0, bOpenGOP=1, aqMode=2, aqStrength=1.0,
                 cuTree=1, qCompress=0.6, weightp=1, weightb=0, poolThreads=0, lookaheadSlices=0, qgSize=32,
                 bFrameBias=0, scenecutBias=5.0, vbvBufferSize=0, vbvMaxBitrate=0, bitrate=0, dumpPlanes=0,
-                bIntraRefresh=0, gopLookahead=0, radl=0)
+                bIntraRefresh=0, gopLookahead=0, radl=0, keepFrames=0)
 
 
 def lib_path(depth):
@@ -61,7 +66,8 @@ def load(depth):
     lib.ref_la_open.restype = C.c_void_p
     lib.ref_la_open.argtypes = [C.POINTER(RefLaConfig)]
     lib.ref_la_put.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
-    lib.ref_la_put_typed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_la_put_typed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_la_estimate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ref_la_flush.argtypes = [C.c_void_p, C.c_int]
     lib.ref_la_num_out.argtypes = [C.c_void_p]
     lib.ref_la_seconds.argtypes = [C.c_void_p]
@@ -113,11 +119,32 @@ class RefLookahead:
         self.effective = dict(zip(names, list(eff)))
         self._fetched = 0
 
-    def put(self, y, u, v, snap=True, slice_type=0):
+    def put(self, y, u, v, snap=True, slice_type=0, pass2_type=0):
+        """slice_type: x265_picture::sliceType forced by the application (-> Lowres::sliceTypeReq);
+        pass2_type: the first-pass type a 2-pass encode hands to Lookahead::addPicture"""
         dt = np.uint8 if self.depth == 8 else np.uint16
         y = np.ascontiguousarray(y, dt); u = np.ascontiguousarray(u, dt); v = np.ascontiguousarray(v, dt)
         return self.lib.ref_la_put_typed(self.h, y.ctypes.data, u.ctypes.data, v.ctypes.data,
-                                         y.shape[1], u.shape[1], 1 if snap else 0, int(slice_type))
+                                         y.shape[1], u.shape[1], 1 if snap else 0, int(pass2_type), int(slice_type))
+
+    def num_out(self):
+        return self.lib.ref_la_num_out(self.h)
+
+    def out_info(self, idx):
+        """(poc, sliceType) of decided frame idx (output order)"""
+        f = RefLaFrame()
+        self.lib.ref_la_get(self.h, idx, C.byref(f))
+        return f.poc, f.sliceType
+
+    def estimate(self, idx, ref0=-1, ref1=-1, pir=(0, 0)):
+        """Lookahead::getEstimatedPictureCost on decided frame idx with references ref0 / ref1 (output indices)"""
+        if self.lib.ref_la_estimate(self.h, idx, ref0, ref1, pir[0], pir[1]) != 0:
+            raise RuntimeError("ref_la_estimate: frame %d or its references are no longer alive" % idx)
+
+    def frame(self, idx):
+        f = RefLaFrame()
+        self.lib.ref_la_get(self.h, idx, C.byref(f))
+        return self._to_dict(f)
 
     def flush(self, snap=True):
         return self.lib.ref_la_flush(self.h, 1 if snap else 0)
@@ -153,9 +180,19 @@ class RefLookahead:
         d["mvCosts"] = _arr(f.mvCosts, np.int32, 2 * nb * ncu).reshape(2, nb, ncu)
         d["intraCost"] = _arr(f.intraCost, np.int32, ncu)
         d["intraMode"] = _arr(f.intraMode, np.uint8, ncu)
-        d["qpAqOffset"] = _arr(f.qpAqOffset, np.float64, ncu)
-        d["qpCuTreeOffset"] = _arr(f.qpCuTreeOffset, np.float64, ncu)
-        d["invQscaleFactor"] = _arr(f.invQscaleFactor, np.int32, ncu)
+        nfull = f.ncuFull or ncu
+        d["qpAqOffset"] = _arr(f.qpAqOffset, np.float64, nfull)
+        d["qpCuTreeOffset"] = _arr(f.qpCuTreeOffset, np.float64, nfull)
+        d["invQscaleFactor"] = _arr(f.invQscaleFactor, np.int32, nfull)
+        d["indB"] = f.indB
+        d["plannedSatd"] = _arr(f.plannedSatd, np.int64, 251)
+        d["plannedType"] = _arr(f.plannedType, np.int32, 251)
+        if f.estimated:
+            d["est"] = dict(satdCost=f.estSatdCost, satdForVbv=_arr(f.satdForVbv, np.uint32, f.vbvRows),
+                            intraSatdForVbv=_arr(f.intraSatdForVbv, np.uint32, f.vbvRows),
+                            lowresCostForRc=_arr(f.lowresCostForRc, np.uint16, ncu),
+                            intraCostForRc=_arr(f.intraCostForRc, np.int32, ncu),
+                            rowSatds=_arr(f.estRowSatds, np.int32, bh))
         d["propagateCost"] = _arr(f.propagateCost, np.uint16, ncu)
         d["weightedCostDelta"] = _arr(f.weightedCostDelta, np.float64, nb)
         if f.planes:

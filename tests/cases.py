@@ -57,7 +57,22 @@ CASES = [
     # narrow picture, tall enough for slices: small enough to commit as a golden fixture
     ("slices_golden", 8, 256, 720, 16, dict(cuts=(8,)), dict(bframes=3, lookaheadDepth=8, poolThreads=8, lookaheadSlices=4)),
     ("slices_trellis2", 10, 1280, 720, 30, dict(cuts=(14,), static=True, noise=1), dict(bframes=3, lookaheadDepth=10, poolThreads=2, lookaheadSlices=3)),
+    # first-pass slice types of a 2-pass encode: the argument of Lookahead::addPicture (encoder.cpp:1713, 1863)
+    ("pass2_types", 8, 320, 192, 44, dict(cuts=(29,)), dict(bframes=3, lookaheadDepth=10)),
+    # qg-size 8: adaptive quant on 8x8 full-res blocks (4 qp offsets per lowres block); 328 / 8 and 184 / 8 are odd, which is
+    # where the reference's running block index and its 2bw x 2bh addressing part ways
+    ("qg8", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=8)),
+    ("qg8_ragged10", 10, 328, 184, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=8, aqMode=3)),
+    ("qg8_aq1_vbv", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=8, aqMode=1, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
+    ("vbv_nocutree", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
 ]
+
+# cases that also run Lookahead::getEstimatedPictureCost (+ its VBV row aggregation) on every decided frame, the way
+# Encoder::encode does (encoder.cpp:2367), and compare satdCost / satdForVbv / the rescaled arrays
+ESTIMATE = ["base8", "base10", "vbv", "radl2", "nocutree", "plain", "intrarefresh", "closedgop", "qg8", "qg8_aq1_vbv", "vbv_nocutree",
+            "b8", "pool16"]
+# intra-refresh column range handed to the VBV aggregation (FrameData::m_pir, slicetype.cpp:1425-1427)
+PIR = {"intrarefresh": (2, 3)}
 
 # subset small enough to commit as golden fixtures and to run in the quick CPU suite
 GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob", "slices_golden"]
@@ -89,24 +104,45 @@ def make_seq(synth, case):
     return synth.SynthSequence(w, h, depth=depth, seed=1, **skw)
 
 
-# application-forced slice types (x265_picture::sliceType) per case: {poc: X265_TYPE_*}; 1 IDR, 2 I, 3 P, 4 BREF, 5 B
+# application-forced slice types (x265_picture::sliceType -> Lowres::sliceTypeReq) per case: {poc: X265_TYPE_*};
+# 1 IDR, 2 I, 3 P, 4 BREF, 5 B
 FORCED = {
     "forced_types": {9: 1, 16: 3, 17: 3, 23: 5, 24: 5, 25: 3, 33: 2},
 }
+# first-pass types handed to addPicture (2-pass): every frame typed, like a stats file would
+PASS2 = {
+    "pass2_types": {i: t for i, t in enumerate([1, 5, 4, 5, 3, 5, 5, 3, 3, 5, 4, 5, 3, 5, 3, 3, 5, 5, 5, 3, 5, 3, 5, 4, 5, 3, 5, 5, 3, 2, 5,
+                                                5, 3, 3, 5, 4, 5, 3, 5, 3, 5, 5, 3, 3])},
+}
 
-# cases only the CPU suite runs (host logic through the sim engine against the live reference): added after this
-# round's GPU budget was spent, they join the GPU list once they have been seen green on hardware
-CPU_ONLY = ["forced_types"]
+# cases only the CPU suite runs (host logic through the sim engine against the live reference)
+CPU_ONLY = []
 
 
-def run_reference(refbind, synth, case, planes=True):
+def run_reference(refbind, synth, case, planes=True, estimate=None):
     name, depth, w, h, n, skw, rkw = case
     seq = make_seq(synth, case)
-    ref = refbind.RefLookahead(w, h, depth=depth, dumpPlanes=1 if planes else 0, **rkw)
-    forced = FORCED.get(name, {})
+    forced, pass2 = FORCED.get(name, {}), PASS2.get(name, {})
+    estimate = (name in ESTIMATE) if estimate is None else estimate
+    ref = refbind.RefLookahead(w, h, depth=depth, dumpPlanes=1 if planes else 0,
+                               keepFrames=(rkw.get("lookaheadDepth", 20) + 3 * (rkw.get("bframes", 4) + 2)) if estimate else 0, **rkw)
+    pir = PIR.get(name, (0, 0))
+    import _pkg
+    tracker = _pkg.load_pkg().RefTracker()
+    done = [0]
+
+    def estimate_new():
+        # getEstimatedPictureCost on the frames decided since the last call, while their references are alive
+        while estimate and done[0] < ref.num_out():
+            poc, t = ref.out_info(done[0])
+            r0, r1 = tracker.push(poc, t, done[0])
+            ref.estimate(done[0], -1 if r0 is None else r0, -1 if r1 is None else r1, pir)
+            done[0] += 1
     for i in range(n):
-        ref.put(*seq.frame(i), slice_type=forced.get(i, 0))
+        ref.put(*seq.frame(i), slice_type=forced.get(i, 0), pass2_type=pass2.get(i, 0))
+        estimate_new()
     ref.flush()
+    estimate_new()
     out = ref.frames()
     ref.close()
     return out
@@ -118,6 +154,7 @@ def run_ours(pkg, synth, case, lib_path=None, planes=True, **extra):
     kw = la_kwargs(rkw)
     kw.update(extra)
     la = pkg.Lookahead(w, h, depth=depth, lib_path=lib_path, **kw)
-    out = pkg.run_sequence(la, (seq.frame(i) for i in range(n)), planes=planes, slice_types=FORCED.get(name))
+    out = pkg.run_sequence(la, (seq.frame(i) for i in range(n)), planes=planes, slice_types=FORCED.get(name),
+                           pass2_types=PASS2.get(name), estimate_cost=name in ESTIMATE, pir=PIR.get(name, (-1, -1)))
     la.close()
     return out

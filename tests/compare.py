@@ -4,7 +4,7 @@ import numpy as np
 EXACT_SCALARS = ["poc", "sliceType", "bScenecut", "bKeyframe", "bLastMiniGopBFrame", "leadingBframes"]
 
 
-def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutree=True, label="", skip_propagate=()):
+def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutree=True, label="", skip_propagate=(), vbv=False):
     """ref: dict from the reference harness; got: dict from our Lookahead.  Returns list of
     mismatch strings (empty = parity)."""
     bad = []
@@ -32,8 +32,9 @@ def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutr
     # propagateCost is only defined for I/P frames: the reference never initialises it for B frames, and
     # for B-refs cuTree resets frames[curnonb + (bframes+1)/2] (slicetype.cpp:3460) while placeBref marks
     # list[bframes/2] (:1757), which are different frames for even mini-GOP sizes.
-    # ... and a frame whose type the application forced is never part of a cuTree chain as an analysed frame: the
-    # reference leaves whatever the (malloc'ed, recycled) array held.
+    # ... and a frame whose type the application forced (Lowres::sliceTypeReq) is analysed as AUTO: when the analysis made it
+    # a B frame and slicetypeDecide then imposes P on it (slicetype.cpp:1938), cuTree only ever cleared its first row and
+    # the rest is whatever the malloc'ed (lowres.cpp: CHECKED_MALLOC, not zeroed) array held.
     if cutree and ref["sliceType"] in (1, 2, 3) and ref["poc"] not in skip_propagate and \
             not np.array_equal(ref["propagateCost"], got["propagateCost"]):
         n = int(np.sum(ref["propagateCost"] != got["propagateCost"]))
@@ -65,6 +66,29 @@ def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutr
             # non-B frames' rowSatds of the coded estimate are rewritten by frameCostRecalculate
             if not np.array_equal(ref["rowSatds"][i, j], got["rowSatds"][i, j]):
                 bad.append(tag + "rowSatds[%d][%d] differ" % (i, j))
+    # what RateControl reads of the VBV lookahead (ratecontrol.cpp:2512-2577)
+    if vbv and "plannedType" in ref and "plannedType" in got:
+        if int(ref["indB"]) != int(got["indB"]):
+            bad.append(tag + "indB ref=%d got=%d" % (ref["indB"], got["indB"]))
+        nt = int(np.argmax(ref["plannedType"] == 0)) if np.any(ref["plannedType"] == 0) else len(ref["plannedType"])
+        nt = max(nt, int(ref["indB"]))
+        if not np.array_equal(ref["plannedType"][:nt], got["plannedType"][:nt]):
+            bad.append(tag + "plannedType ref=%s got=%s" % (ref["plannedType"][:nt], got["plannedType"][:nt]))
+        if not np.array_equal(ref["plannedSatd"][:nt], got["plannedSatd"][:nt]):
+            bad.append(tag + "plannedSatd ref=%s got=%s" % (ref["plannedSatd"][:nt], got["plannedSatd"][:nt]))
+    # Lookahead::getEstimatedPictureCost as the encoder calls it per coded frame
+    if "est" in ref and "est" in got:
+        e, g = ref["est"], got["est"]
+        if int(e["satdCost"]) != int(g["satdCost"]):
+            bad.append(tag + "satdCost ref=%d got=%d" % (e["satdCost"], g["satdCost"]))
+        if "rowSatds" in g and not np.array_equal(e["rowSatds"], g["rowSatds"]):
+            bad.append(tag + "rowSatds after getEstimatedPictureCost differ")
+        if vbv and "satdForVbv" in g:
+            for k in ("satdForVbv", "intraSatdForVbv", "lowresCostForRc", "intraCostForRc"):
+                if not np.array_equal(e[k], g[k]):
+                    bad.append(tag + "%s differs in %d entries" % (k, int(np.sum(e[k] != g[k]))))
+    elif "est" in ref:
+        bad.append(tag + "getEstimatedPictureCost ran on the reference side only")
     if check_planes and "planes" in ref and "planes" in got:
         if not np.array_equal(ref["planes"], got["planes"]):
             n = int(np.sum(ref["planes"] != got["planes"]))

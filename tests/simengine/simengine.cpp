@@ -18,7 +18,7 @@ struct SimSlot
 {
     std::vector<or_pixel> y, u, v;
     std::vector<or_pixel> planes;
-    std::vector<int32_t> intraCost, invQ, rowSatds00;
+    std::vector<int32_t> intraCost, invQ, invQ8, rowSatds00;
     std::vector<uint8_t> intraMode;
     std::vector<uint16_t> lowresCosts00, propagate;
     std::vector<double> qpAq, qpCuTree;
@@ -91,11 +91,11 @@ const char* x265cu_last_error(const x265cu_ctx*) { return ""; }
 int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 {
     if (cfg->depth != or_depth()) return X265CU_ERR_BAD_ARG;
-    if (cfg->qg_size < 16) return X265CU_ERR_UNSUPPORTED;
     x265cu_ctx* c = new x265cu_ctx;
     c->cfg = *cfg;
     or_geom_init(&c->g, cfg->width, cfg->height, cfg->max_cu_size);
     c->g.rowsPerSlice = 0;      /* per search job, x265cu_search_job::sliced */
+    c->g.qg8 = cfg->qg_size == 8;
     c->mvcost.assign(cfg->mvcost, cfg->mvcost + 2 * (size_t)cfg->mvcost_half + 1);
     memset(&c->geom, 0, sizeof(c->geom));
     c->geom.low_width = c->g.w; c->geom.low_height = c->g.h; c->geom.bw = c->g.bw; c->geom.bh = c->g.bh;
@@ -103,6 +103,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     c->geom.margin_x = c->g.mx; c->geom.margin_y = c->g.my; c->geom.nb = cfg->bframes + 2;
     c->geom.n_mv_stores = (cfg->mv_store_kinds > 0 ? cfg->mv_store_kinds : 3) * c->geom.nb;
     c->geom.n_cost_stores = (cfg->cost_variants > 0 ? cfg->cost_variants : 2) * c->geom.nb * c->geom.nb;
+    c->geom.ncu_full = c->g.qg8 ? 4 * c->g.ncu : c->g.ncu;
     c->slots.resize(cfg->max_slots);
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL; c->owner.assign(cfg->max_slots, 0);
     memset(&c->counters, 0, sizeof(c->counters));
@@ -152,9 +153,12 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     s.planes.assign((size_t)(4 * g.planeSize), 0);
     or_lowres_init(&g, &s.y[0], W, &s.planes[0]);
     const int ncu = g.ncu, nb = c->geom.nb;
-    s.intraCost.assign(ncu, 0); s.invQ.assign(ncu, 256); s.intraMode.assign(ncu, 0);
+    /* the qp-offset arrays are allocated zeroed once per Lowres in the reference (lowres.cpp:98-106) and entries the
+     * running AQ index never reaches stay zero */
+    const size_t nAq = (size_t)c->geom.ncu_full + 2 * g.bw + 2 + (g.qg8 ? ((g.picW + 7) / 8) * ((g.picH + 7) / 8) : 0);
+    s.intraCost.assign(ncu, 0); s.invQ.assign(nAq, g.qg8 ? 0 : 256); s.invQ8.assign(ncu, 256); s.intraMode.assign(ncu, 0);
     s.lowresCosts00.assign(ncu, 0); s.rowSatds00.assign(g.bh, 0); s.propagate.assign(ncu, 0);
-    s.qpAq.assign(ncu, 0.0); s.qpCuTree.assign(ncu, 0.0);
+    s.qpAq.assign(nAq, 0.0); s.qpCuTree.assign(nAq, 0.0);
     const int nmv = c->geom.n_mv_stores, ncs = c->geom.n_cost_stores;
     s.mvs.assign(nmv, std::vector<int32_t>()); s.mvCosts.assign(nmv, std::vector<int32_t>());
     s.skipFlag.assign(nmv, 0);
@@ -165,7 +169,8 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
         or_aq_frame(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW,
                     c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats, &s.qpAq[0], &s.qpCuTree[0], &s.invQ[0],
                     NULL, s.stats.wp_ssd, s.stats.wp_sum);
-    or_intra_estimate(&g, &s.planes[g.padOffset], c->cfg.need_aq ? &s.invQ[0] : NULL, &s.intraCost[0], &s.intraMode[0],
+    if (c->cfg.need_aq && g.qg8) or_invq8x8(&g, &s.invQ[0], &s.invQ8[0]);
+    or_intra_estimate(&g, &s.planes[g.padOffset], c->cfg.need_aq ? (g.qg8 ? &s.invQ8[0] : &s.invQ[0]) : NULL, &s.intraCost[0], &s.intraMode[0],
                       &s.lowresCosts00[0], &s.rowSatds00[0], &s.stats.cost_est, &s.stats.cost_est_aq);
     c->counters.h2d_bytes += (uint64_t)W * H * sizeof(or_pixel) * 3 / 2;
     return 0;
@@ -243,7 +248,7 @@ int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
         or_frame_cost(&g, &b.planes[g.padOffset], r0, bidir ? r1 : NULL,
                       &b.mvs[j.l0_store][0], &b.mvCosts[j.l0_store][0],
                       bidir ? &b.mvs[j.l1_store][0] : NULL, bidir ? &b.mvCosts[j.l1_store][0] : NULL,
-                      &b.intraCost[0], c->cfg.need_aq ? &b.invQ[0] : NULL, &b.costs[j.out][0], &b.rowSatds[j.out][0],
+                      &b.intraCost[0], c->cfg.need_aq ? (g.qg8 ? &b.invQ8[0] : &b.invQ[0]) : NULL, &b.costs[j.out][0], &b.rowSatds[j.out][0],
                       &res.cost_est, &res.cost_est_aq, &res.intra_mbs);
         c->counters.kernel_launches++;
     }
@@ -285,7 +290,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
                             int32_t referenced, int32_t bipred_weight, double fps_factor)
 {
     SimSlot& b = c->slots[bs];
-    or_cutree_propagate(&c->g, &b.intraCost[0], &b.costs[cost_store][0], &b.invQ[0], &b.mvs[l0][0],
+    or_cutree_propagate(&c->g, &b.intraCost[0], &b.costs[cost_store][0], c->g.qg8 ? &b.invQ8[0] : &b.invQ[0], &b.mvs[l0][0],
                         l1 >= 0 ? &b.mvs[l1][0] : &b.mvs[l0][0], &b.propagate[0],
                         &c->slots[p0s].propagate[0], &c->slots[p1s].propagate[0], referenced, bipred_weight, fps_factor);
     return 0;
@@ -294,7 +299,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
 int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double weightdelta, double strength)
 {
     SimSlot& s = c->slots[slot];
-    or_cutree_finish(&c->g, &s.intraCost[0], &s.invQ[0], &s.propagate[0], &s.qpAq[0], &s.qpCuTree[0], fps_fix8, weightdelta, strength);
+    or_cutree_finish(&c->g, &s.intraCost[0], c->g.qg8 ? &s.invQ8[0] : &s.invQ[0], &s.propagate[0], &s.qpAq[0], &s.qpCuTree[0], fps_fix8, weightdelta, strength);
     return 0;
 }
 
@@ -308,15 +313,36 @@ int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t 
     return 0;
 }
 
+int x265cu_vbv_row_costs(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t qp_source, int32_t ctu_rows_lowres,
+                         int32_t pir_start, int32_t pir_end, int32_t n_rows, uint32_t* satd, uint32_t* intra,
+                         uint16_t* cost_for_rc, int32_t* intra_scaled)
+{
+    SimSlot& s = c->slots[slot];
+    const std::vector<uint16_t>& costs = cost_store == 0 ? s.lowresCosts00 : s.costs[cost_store];
+    std::vector<uint32_t> a(n_rows), b(n_rows);
+    std::vector<uint16_t> rc(c->g.ncu); std::vector<int32_t> ic(c->g.ncu);
+    const double* qp = (qp_source == 0 || !c->cfg.need_aq) ? NULL : (qp_source == 2 ? &s.qpCuTree[0] : &s.qpAq[0]);
+    or_vbv_rows(&c->g, &costs[0], &s.intraCost[0], qp, ctu_rows_lowres, pir_start, pir_end, n_rows, &a[0], &b[0], &rc[0], &ic[0]);
+    if (satd) memcpy(satd, &a[0], n_rows * 4);
+    if (intra) memcpy(intra, &b[0], n_rows * 4);
+    if (cost_for_rc) memcpy(cost_for_rc, &rc[0], c->g.ncu * 2);
+    if (intra_scaled) memcpy(intra_scaled, &ic[0], c->g.ncu * 4);
+    return 0;
+}
+
 int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
 {
     SimSlot& s = c->slots[slot];
-    const int ncu = c->g.ncu;
+    const int ncu = c->g.ncu, nfull = c->geom.ncu_full;
     if (o->intra_cost) memcpy(o->intra_cost, &s.intraCost[0], ncu * 4);
     if (o->intra_mode) memcpy(o->intra_mode, &s.intraMode[0], ncu);
-    if (o->qp_aq_offset) memcpy(o->qp_aq_offset, &s.qpAq[0], ncu * 8);
-    if (o->qp_cutree_offset) memcpy(o->qp_cutree_offset, &s.qpCuTree[0], ncu * 8);
-    if (o->inv_qscale_factor) memcpy(o->inv_qscale_factor, &s.invQ[0], ncu * 4);
+    if (o->qp_aq_offset) memcpy(o->qp_aq_offset, &s.qpAq[0], nfull * 8);
+    if (o->qp_cutree_offset) memcpy(o->qp_cutree_offset, &s.qpCuTree[0], nfull * 8);
+    if (o->inv_qscale_factor)
+    {
+        if (c->cfg.need_aq) memcpy(o->inv_qscale_factor, &s.invQ[0], nfull * 4);
+        else for (int i = 0; i < nfull; i++) o->inv_qscale_factor[i] = 256;
+    }
     if (o->propagate_cost) memcpy(o->propagate_cost, &s.propagate[0], ncu * 2);
     if (o->planes) memcpy(o->planes, &s.planes[0], (size_t)(4 * c->g.planeSize) * sizeof(or_pixel));
     if (o->lowres_costs00) memcpy(o->lowres_costs00, &s.lowresCosts00[0], ncu * 2);

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _cmp(want, got, case, planes=True):
     rkw = case[6]
     return compare.compare_runs(want, got, check_planes=planes, cutree=rkw.get("cuTree", 1), weightp=rkw.get("weightp", 1),
-                                skip_propagate=tuple(cases.FORCED.get(case[0], {})))
+                                vbv=bool(rkw.get("vbvBufferSize")), skip_propagate=tuple(cases.FORCED.get(case[0], {})) + tuple(cases.PASS2.get(case[0], {})))
 
 
 def _sim(simdir, depth):

@@ -18,7 +18,7 @@ def _sim(simdir, depth):
 def _cmp(want, got, case):
     rkw = case[6]
     return compare.compare_runs(want, got, check_planes=True, cutree=rkw.get("cuTree", 1), weightp=rkw.get("weightp", 1),
-                                skip_propagate=tuple(cases.FORCED.get(case[0], {})))
+                                vbv=bool(rkw.get("vbvBufferSize")), skip_propagate=tuple(cases.FORCED.get(case[0], {})) + tuple(cases.PASS2.get(case[0], {})))
 
 
 @pytest.mark.parametrize("name", cases.GOLDEN)

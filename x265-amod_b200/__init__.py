@@ -20,7 +20,7 @@ TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "b", 5: "B"}
 
 class Geometry(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("low_width", "low_height", "bw", "bh", "ncu", "stride", "plane_lines",
-                                          "margin_x", "margin_y", "nb", "n_mv_stores", "n_cost_stores")]
+                                          "margin_x", "margin_y", "nb", "n_mv_stores", "n_cost_stores", "ncu_full")]
 
 
 class LaParam(C.Structure):
@@ -85,7 +85,10 @@ def load_lib(path=None):
     lib.x265la_last_error.argtypes = [C.c_void_p]
     lib.x265la_add_picture.restype = C.c_void_p
     lib.x265la_add_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
-                                       C.c_int64, C.c_int32]
+                                       C.c_int64, C.c_int32, C.c_int32]
+    lib.x265la_vbv_rows.argtypes = [C.c_void_p]
+    lib.x265la_vbv_row_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4
+    lib.x265la_frame_planned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.x265la_flush.argtypes = [C.c_void_p]
     lib.x265la_get_decided.argtypes = [C.c_void_p, C.POINTER(FrameInfo)]
     lib.x265la_estimated_picture_cost.restype = C.c_int64
@@ -158,20 +161,22 @@ class Lookahead:
         self._keep = {}      # handle -> planes kept alive until the frame is released
         self.dtype = np.uint8 if depth == 8 else np.uint16
 
-    def add_picture_ptr(self, y_ptr, u_ptr, v_ptr, stride_y, stride_c, pts=0, slice_type=TYPE_AUTO):
+    def add_picture_ptr(self, y_ptr, u_ptr, v_ptr, stride_y, stride_c, pts=0, slice_type=TYPE_AUTO, pass2_type=TYPE_AUTO):
         """addPicture with raw pointers (host, pinned host or device memory); the caller keeps them alive."""
-        h = self.lib.x265la_add_picture(self.h, y_ptr, u_ptr, v_ptr, stride_y, stride_c, pts, slice_type)
+        h = self.lib.x265la_add_picture(self.h, y_ptr, u_ptr, v_ptr, stride_y, stride_c, pts, pass2_type, slice_type)
         if not h:
             raise RuntimeError("addPicture failed: %s" % self.lib.x265la_last_error(self.h).decode())
         return h
 
-    def add_picture(self, y, u, v, pts=0, slice_type=TYPE_AUTO):
+    def add_picture(self, y, u, v, pts=0, slice_type=TYPE_AUTO, pass2_type=TYPE_AUTO):
+        """slice_type: x265_picture::sliceType as an application forces it (-> Lowres::sliceTypeReq);
+        pass2_type: the first-pass type of a 2-pass encode (the argument of the reference's Lookahead::addPicture)"""
         y = np.ascontiguousarray(y, self.dtype)
         u = None if u is None else np.ascontiguousarray(u, self.dtype)
         v = None if v is None else np.ascontiguousarray(v, self.dtype)
         h = self.lib.x265la_add_picture(self.h, y.ctypes.data, u.ctypes.data if u is not None else None,
                                         v.ctypes.data if v is not None else None, y.shape[1],
-                                        u.shape[1] if u is not None else 0, pts, slice_type)
+                                        u.shape[1] if u is not None else 0, pts, pass2_type, slice_type)
         if not h:
             raise RuntimeError("addPicture failed: %s" % self.lib.x265la_last_error(self.h).decode())
         self._keep[h] = (y, u, v)
@@ -190,6 +195,23 @@ class Lookahead:
     def estimated_picture_cost(self, frame, ref0=None, ref1=None):
         return self.lib.x265la_estimated_picture_cost(self.h, frame, ref0, ref1)
 
+    def estimate_dict(self, frame, ref0=None, ref1=None, pir=(-1, -1), vbv=True):
+        """getEstimatedPictureCost incl. its VBV half, in the layout of oracle/refbind.py's frame["est"]"""
+        g = self.geom
+        satd = self.estimated_picture_cost(frame, ref0, ref1)
+        err = self.lib.x265la_last_error(self.h)
+        if err:
+            raise RuntimeError("getEstimatedPictureCost failed: %s" % err.decode())
+        d = dict(satdCost=satd)
+        if vbv:
+            rows = self.lib.x265la_vbv_rows(self.h)
+            a = np.zeros(rows, np.uint32); b = np.zeros(rows, np.uint32)
+            rc = np.zeros(g.ncu, np.uint16); ic = np.zeros(g.ncu, np.int32)
+            if self.lib.x265la_vbv_row_costs(self.h, frame, pir[0], pir[1], a.ctypes.data, b.ctypes.data, rc.ctypes.data, ic.ctypes.data) != 0:
+                raise RuntimeError("x265la_vbv_row_costs failed: %s" % self.lib.x265la_last_error(self.h).decode())
+            d.update(satdForVbv=a, intraSatdForVbv=b, lowresCostForRc=rc, intraCostForRc=ic)
+        return d
+
     def release(self, handle):
         self._keep.pop(handle, None)
         self.lib.x265la_release(self.h, handle)
@@ -197,7 +219,7 @@ class Lookahead:
     def frame_dict(self, info, planes=False):
         """Published Lowres state of a decided frame in the same dict layout as oracle/refbind.py."""
         g, nb = self.geom, self.geom.nb
-        ncu, bh = g.ncu, g.bh
+        ncu, bh, nfull = g.ncu, g.bh, g.ncu_full
         hnd = info.handle
         d = dict(poc=info.poc, sliceType=info.sliceType, bScenecut=info.bScenecut, bKeyframe=info.bKeyframe,
                  bLastMiniGopBFrame=info.bLastMiniGopBFrame, leadingBframes=info.leadingBframes,
@@ -218,6 +240,9 @@ class Lookahead:
         ws = np.zeros((4, nb), np.int32)
         self.lib.x265la_frame_weights(self.h, hnd, ws[0].ctypes.data, ws[1].ctypes.data, ws[2].ctypes.data, ws[3].ctypes.data)
         d.update(weightState=ws[0], weightParams=ws[1:].T.copy())
+        ps = np.zeros(251, np.int64); pt = np.zeros(251, np.int32); ib = C.c_int32(0)
+        self.lib.x265la_frame_planned(self.h, hnd, ps.ctypes.data, pt.ctypes.data, 251, C.byref(ib))
+        d.update(plannedSatd=ps, plannedType=pt, indB=ib.value)
         lc = np.zeros((nb, nb, ncu), np.uint16); rs = np.zeros((nb, nb, bh), np.int32)
         for i in range(nb):
             for j in range(nb):
@@ -227,8 +252,8 @@ class Lookahead:
                     rs[i, j, 0] = -1
         d.update(lowresCosts=lc, rowSatds=rs)
         arr = dict(intraCost=np.zeros(ncu, np.int32), intraMode=np.zeros(ncu, np.uint8),
-                   qpAqOffset=np.zeros(ncu, np.float64), qpCuTreeOffset=np.zeros(ncu, np.float64),
-                   invQscaleFactor=np.zeros(ncu, np.int32), propagateCost=np.zeros(ncu, np.uint16))
+                   qpAqOffset=np.zeros(nfull, np.float64), qpCuTreeOffset=np.zeros(nfull, np.float64),
+                   invQscaleFactor=np.zeros(nfull, np.int32), propagateCost=np.zeros(ncu, np.uint16))
         fo = FrameOut()
         fo.intra_cost = arr["intraCost"].ctypes.data; fo.intra_mode = arr["intraMode"].ctypes.data
         fo.qp_aq_offset = arr["qpAqOffset"].ctypes.data; fo.qp_cutree_offset = arr["qpCuTreeOffset"].ctypes.data
@@ -264,11 +289,43 @@ class Lookahead:
             pass
 
 
-def run_sequence(la, frames_iter, collect=True, planes=False, estimate_cost=False, slice_types=None):
+class RefTracker:
+    """The nearest list-0 / list-1 reference of each decided frame, the way the encoder's DPB would hold them when
+    Encoder::encode calls getEstimatedPictureCost (encoder.cpp:2367): frames arrive in coded order; references are the
+    I / P / b-ref frames coded so far; an IDR empties the DPB first.  These are exactly the (p0, p1, b) estimates
+    slicetypeDecide pre-computes for rate control (slicetype.cpp:2378-2427)."""
+
+    def __init__(self):
+        self.refs = []      # (poc, token) of reference frames coded so far
+
+    def push(self, poc, slice_type, token):
+        """returns (ref0_token, ref1_token) for this frame (None = no such reference), then files the frame"""
+        if slice_type == TYPE_IDR:
+            self.refs = []
+        r0 = r1 = None
+        if slice_type not in (TYPE_IDR, TYPE_I):
+            lo = [r for r in self.refs if r[0] < poc]
+            hi = [r for r in self.refs if r[0] > poc]
+            if lo:
+                r0 = max(lo)[1]
+            if hi and slice_type in (TYPE_B, TYPE_BREF):
+                r1 = min(hi)[1]
+        if slice_type != TYPE_B:
+            self.refs.append((poc, token))
+            self.refs = self.refs[-4:]
+        return r0, r1
+
+
+def run_sequence(la, frames_iter, collect=True, planes=False, estimate_cost=False, slice_types=None, pass2_types=None,
+                 pir=(-1, -1)):
     """Drive a Lookahead the way Encoder::encode does (one picture in, drain what is decided),
     then flush.  Returns the decided frames (dicts) in output order.  slice_types: {poc: forced type}
-    (x265_picture::sliceType as an application may set it)."""
+    (x265_picture::sliceType as an application may set it); pass2_types: {poc: first-pass type of a 2-pass encode}.
+    estimate_cost: also call getEstimatedPictureCost (+ its VBV half) per decided frame like the encoder does, with the
+    references RefTracker derives; results under the frame's "est" key."""
     out = []
+    tracker = RefTracker()
+    held = []       # handles still needed as references
 
     def drain():
         while True:
@@ -276,15 +333,48 @@ def run_sequence(la, frames_iter, collect=True, planes=False, estimate_cost=Fals
             if info is None:
                 break
             if collect:
-                out.append(la.frame_dict(info, planes=planes))
+                d = la.frame_dict(info, planes=planes)
             else:
-                out.append(dict(poc=info.poc, sliceType=info.sliceType, bScenecut=info.bScenecut,
-                                bKeyframe=info.bKeyframe))
-            la.release(info.handle)
+                d = dict(poc=info.poc, sliceType=info.sliceType, bScenecut=info.bScenecut, bKeyframe=info.bKeyframe)
+            if estimate_cost:
+                r0, r1 = tracker.push(info.poc, info.sliceType, info.handle)
+                d["est"] = la.estimate_dict(info.handle, r0, r1, pir=pir)
+                if collect:
+                    rs = np.zeros(la.geom.bh, np.int32)
+                    la.lib.x265la_frame_costs(la.h, info.handle, (info.poc - la_poc(r0)) if r0 else 0,
+                                              (la_poc(r1) - info.poc) if r1 else 0, None, rs.ctypes.data)
+                    d["est"]["rowSatds"] = rs
+                held.append((info.poc, info.handle))
+                live = set(t for _, t in tracker.refs)
+                for ph in list(held):
+                    if ph[1] not in live and ph[1] != info.handle:
+                        held.remove(ph)
+                        la.release(ph[1])
+                if info.sliceType == TYPE_B:
+                    held.remove((info.poc, info.handle))
+                    la.release(info.handle)
+            else:
+                la.release(info.handle)
+            out.append(d)
+
+    pocs = {}
+
+    def la_poc(handle):
+        return pocs[handle]
+
+    _push = tracker.push
+
+    def push(poc, t, token):
+        pocs[token] = poc
+        return _push(poc, t, token)
+    tracker.push = push
 
     for i, (y, u, v) in enumerate(frames_iter):
-        la.add_picture(y, u, v, pts=i, slice_type=(slice_types or {}).get(i, TYPE_AUTO))
+        la.add_picture(y, u, v, pts=i, slice_type=(slice_types or {}).get(i, TYPE_AUTO),
+                       pass2_type=(pass2_types or {}).get(i, TYPE_AUTO))
         drain()
     la.flush()
     drain()
+    for _, hnd in held:
+        la.release(hnd)
     return out

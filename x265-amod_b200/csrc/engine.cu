@@ -35,7 +35,7 @@ namespace {
 
 struct SlotLayout
 {
-    size_t srcY, srcU, srcV, planes, intraCost, intraMode, invQ, qpAq, qpCuTree, propagate, energy,
+    size_t srcY, srcU, srcV, planes, intraCost, intraMode, invQ, invQ8, qpAq, qpCuTree, propagate, energy, aqSums,
            lowresCosts00, rowSatds00, stats, mvStores, costStores, total;
     size_t mvStoreStride, costStoreStride, costRowOff, costResOff;
 };
@@ -87,7 +87,6 @@ struct x265cu_ctx
     std::vector<std::vector<long long> > slotUsers;      /* batches that read or write the slot's current tenant */
     std::vector<long long> mvWriter, costWriter;         /* [slot * n_stores + store] -> batch that writes it, -1 */
     unsigned short* d_mvcost;       /* whole table; centre at +mvcost_half */
-    double* d_aqPartial;            /* per-CTA partial sums of the AQ frame means (K2b) */
     unsigned long long* d_executed; /* [0] search jobs, [1] cost jobs that passed their condition */
     char* d_results; size_t resultsCap;
     FrameStatsDev* h_slotStats; FrameStatsDev* d_slotStats;   /* mapped host memory: every slot's statistics, written by K3's epilogue */
@@ -216,6 +215,8 @@ DeviceScope::DeviceScope(const x265cu_ctx* c) : prev(-1), want(c ? c->cfg.device
 }
 
 template <typename T> T* slotPtr(x265cu_ctx* c, int slot, size_t off) { return (T*)(c->slots[slot] + off); }
+/* the per-lowres-block AQ scale the block kernels read: invQscaleFactor, or invQscaleFactor8x8 with qg-size 8 */
+int* slotInvQ(x265cu_ctx* c, int slot) { return slotPtr<int>(c, slot, c->g.aqBlock == 8 ? c->lay.invQ8 : c->lay.invQ); }
 
 int ensureDev(x265cu_ctx* c, char** p, size_t* cap, size_t need)
 {
@@ -565,18 +566,29 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
         lowres_kernel<P><<<(unsigned)((threads + 255) / 256), 256, 0, c->preStream>>>(g, dY, planes);
     }
     FrameStatsDev* stats = slotPtr<FrameStatsDev>(c, slot, L.stats);
-    int* invQ = slotPtr<int>(c, slot, L.invQ);
+    int* invQ = slotInvQ(c, slot);
     if (c->cfg.need_aq)
     {
         const bool twoPass = (c->cfg.aq_mode == 2 || c->cfg.aq_mode == 3) && c->cfg.aq_strength != 0;
-        Prof pr(c, X265CU_K_AQ, 2 + twoPass, c->preStream);
+        const bool qg8 = g.aqBlock == 8;
+        Prof pr(c, X265CU_K_AQ, 2 + 2 * twoPass + qg8, c->preStream);
         unsigned* energy = slotPtr<unsigned>(c, slot, L.energy);
         double* qpCuTree = slotPtr<double>(c, slot, L.qpCuTree);
-        aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, c->preStream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
+        double* sums = slotPtr<double>(c, slot, L.aqSums);
+        if (qg8)
+            aq_energy8_kernel<P><<<(g.aqW * g.aqH + 31) / 32, 256, 0, c->preStream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
+        else
+            aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, c->preStream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
         if (twoPass)
-            aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, c->preStream>>>(g, energy, qpCuTree, c->d_aqPartial);
+        {
+            aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, c->preStream>>>(g, energy, qpCuTree);
+            aq_mean_kernel<<<1, 32, 0, c->preStream>>>(g, qpCuTree, sums);
+        }
         aq_finish_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, c->preStream>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
-                                                                      c->d_aqPartial, slotPtr<double>(c, slot, L.qpAq), qpCuTree, invQ, stats);
+                                                                      sums, slotPtr<double>(c, slot, L.qpAq), qpCuTree,
+                                                                      slotPtr<int>(c, slot, L.invQ), stats);
+        if (qg8)
+            aq_invq8x8_kernel<<<(g.ncu + 255) / 256, 256, 0, c->preStream>>>(g, slotPtr<int>(c, slot, L.invQ), invQ);
     }
     {
         Prof pr(c, X265CU_K_INTRA, 1, c->preStream);
@@ -777,7 +789,7 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
             if (st) return st;
         }
         d.intraCost = slotPtr<int>(c, j.b_slot, L.intraCost);
-        d.invQ = c->cfg.need_aq ? slotPtr<int>(c, j.b_slot, L.invQ) : NULL;
+        d.invQ = c->cfg.need_aq ? slotInvQ(c, j.b_slot) : NULL;
         d.lowresCosts = (unsigned short*)cs;
         d.rowSatds = (int*)(cs + L.costRowOff);
         d.result = (CostResultDev*)(cs + L.costResOff);
@@ -965,7 +977,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
 {
     if (!cfg || !out) return X265CU_ERR_BAD_ARG;
     *out = NULL;
-    if (cfg->qg_size < 16) return X265CU_ERR_UNSUPPORTED;
+    if (cfg->qg_size != 8 && cfg->qg_size != 16 && cfg->qg_size != 32 && cfg->qg_size != 64) return X265CU_ERR_BAD_ARG;
     if (cfg->depth != 8 && cfg->depth != 10) return X265CU_ERR_UNSUPPORTED;     /* SWAR SATD range, la_device.cuh */
     if (cfg->width < 16 || cfg->height < 16 || cfg->bframes < 0 || cfg->bframes > 16 || cfg->max_slots < 1 || !cfg->mvcost)
         return X265CU_ERR_BAD_ARG;
@@ -974,7 +986,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     if (cudaSetDevice(cfg->device) != cudaSuccess) return X265CU_ERR_NO_DEVICE;
     x265cu_ctx* c = new (std::nothrow) x265cu_ctx();
     if (!c) return X265CU_ERR_NO_MEMORY;
-    c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_aqPartial = NULL; c->d_executed = NULL;
+    c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_executed = NULL;
     c->d_results = NULL; c->resultsCap = 0; c->h_slotStats = NULL; c->d_slotStats = NULL; c->h_mapped = NULL; c->d_mapped = NULL; c->mappedCap = 0;
     c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
@@ -1008,11 +1020,16 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     g.lambda = cfg->lambda; g.depth = cfg->depth; g.nb = cfg->bframes + 2;
     g.tpr = g.stride / 8;
     g.rowsPerSlice = cfg->rows_per_slice > 0 ? cfg->rows_per_slice : 0;
+    /* calcAdaptiveQuantFrame's block grid (slicetype.cpp:459-472, lowres.cpp:86-89) */
+    g.aqBlock = cfg->qg_size == 8 ? 8 : 16;
+    g.aqW = (g.picW + g.aqBlock - 1) / g.aqBlock; g.aqH = (g.picH + g.aqBlock - 1) / g.aqBlock;
+    g.ncuFull = cfg->qg_size == 8 ? 4 * g.ncu : g.ncu;
     x265cu_geometry& G = c->geom;
     G.low_width = g.w; G.low_height = g.h; G.bw = g.bw; G.bh = g.bh; G.ncu = g.ncu; G.stride = g.stride;
     G.plane_lines = g.planeLines; G.margin_x = g.mx; G.margin_y = g.my; G.nb = g.nb;
     G.n_mv_stores = (cfg->mv_store_kinds > 0 ? cfg->mv_store_kinds : 3) * g.nb;
     G.n_cost_stores = (cfg->cost_variants > 0 ? cfg->cost_variants : 2) * g.nb * g.nb;
+    G.ncu_full = g.ncuFull;
 
     SlotLayout& L = c->lay;
     size_t o = 0;
@@ -1023,11 +1040,15 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     SECTION(planes, (size_t)(4 * g.planeSize) * c->bpp + 256);
     SECTION(intraCost, (size_t)g.ncu * 4);
     SECTION(intraMode, (size_t)g.ncu);
-    SECTION(invQ, (size_t)g.ncu * 4);
-    SECTION(qpAq, (size_t)g.ncu * 8);
-    SECTION(qpCuTree, (size_t)g.ncu * 8);
+    /* with a ragged picture the running AQ index can visit a few more blocks than ncuFull holds: slack of one row */
+    const size_t nAq = (size_t)std::max(g.ncuFull, g.aqW * g.aqH) + 2 * g.bw + 2;
+    SECTION(invQ, nAq * 4);
+    SECTION(invQ8, (size_t)g.ncu * 4);
+    SECTION(qpAq, nAq * 8);
+    SECTION(qpCuTree, nAq * 8);
     SECTION(propagate, (size_t)g.ncu * 4);
-    SECTION(energy, (size_t)g.ncu * 4);
+    SECTION(energy, nAq * 4);
+    SECTION(aqSums, 16);
     SECTION(lowresCosts00, (size_t)g.ncu * 2);
     L.rowSatds00 = o; o += alignUp((size_t)g.bh * 4, 16);
     L.stats = o; o = alignUp(o + sizeof(FrameStatsDev), 256);
@@ -1064,7 +1085,6 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     const size_t tabBytes = (2 * (size_t)cfg->mvcost_half + 1) * sizeof(unsigned short);
     if (cudaMalloc((void**)&c->d_mvcost, tabBytes) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     if (!rc && cudaMemcpy(c->d_mvcost, cfg->mvcost, tabBytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = X265CU_ERR_CUDA;
-    if (!rc && cudaMalloc((void**)&c->d_aqPartial, 2 * LA_AQ_CTAS * sizeof(double)) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     for (int i = 0; !rc && i < cfg->max_slots; i++)
     {
         char* p = NULL;
@@ -1143,7 +1163,7 @@ void x265cu_destroy(x265cu_ctx* c)
         if (b.done) cudaEventDestroy(b.done);
     }
     for (size_t i = 0; i < c->xpool.size(); i++) cudaFree(c->xpool[i].first);
-    cudaFree(c->d_mvcost); cudaFree(c->d_aqPartial); cudaFree(c->d_executed); cudaFree(c->d_results);
+    cudaFree(c->d_mvcost); cudaFree(c->d_executed); cudaFree(c->d_results);
     if (c->h_slotStats) cudaFreeHost(c->h_slotStats);
     if (c->h_mapped) cudaFreeHost(c->h_mapped);
     if (c->h_ctJobs) cudaFreeHost(c->h_ctJobs);
@@ -1162,12 +1182,14 @@ int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* out) { if (!c || !
 
 int x265cu_pin_host(x265cu_ctx* c, void* ptr, uint64_t bytes)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
     return X265CU_OK;
 }
 int x265cu_unpin_host(x265cu_ctx* c, void* ptr)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     CK(cudaHostUnregister(ptr));
     return X265CU_OK;
@@ -1185,6 +1207,7 @@ static int mainJoinBatches(x265cu_ctx* c)
 
 int x265cu_sync(x265cu_ctx* c)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     int st = endBatch(c);
@@ -1196,6 +1219,7 @@ int x265cu_sync(x265cu_ctx* c)
 
 int x265cu_batch_begin(x265cu_ctx* c, int64_t* batch_id)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c) return X265CU_ERR_BAD_ARG;
@@ -1214,6 +1238,7 @@ int x265cu_batch_end(x265cu_ctx* c)
 
 int x265cu_shard_config(x265cu_ctx* c, int32_t rank, int32_t nranks, x265cu_exchange_fn fn, void* user)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || nranks < 1 || nranks > LA_MAX_RANKS || rank < 0 || rank >= nranks || (nranks > 1 && !fn)) return X265CU_ERR_BAD_ARG;
@@ -1225,6 +1250,7 @@ int x265cu_shard_config(x265cu_ctx* c, int32_t rank, int32_t nranks, x265cu_exch
 
 int x265cu_slot_owner(x265cu_ctx* c, int32_t slot, int32_t owner)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     if (!c || !slotOk(c, slot) || owner < 0 || owner >= c->nranks) return X265CU_ERR_BAD_ARG;
     c->slotOwner[slot] = owner;
@@ -1235,6 +1261,7 @@ int x265cu_slot_owner(x265cu_ctx* c, int32_t slot, int32_t owner)
  * enqueued on any stream of the context */
 int x265cu_timer_start(x265cu_ctx* c)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     CK(cudaEventRecord(c->tm0, c->stream));
@@ -1242,6 +1269,7 @@ int x265cu_timer_start(x265cu_ctx* c)
 }
 int x265cu_timer_stop(x265cu_ctx* c, double* ms)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     int st = mainJoinBatches(c);
@@ -1259,6 +1287,7 @@ int x265cu_timer_stop(x265cu_ctx* c, double* ms)
 /* synchronises: the job counts are those that passed their condition on the device */
 int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     int st = x265cu_sync(c);
@@ -1272,6 +1301,7 @@ int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o)
 
 int x265cu_profile_enable(x265cu_ctx* c, int32_t on)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     resolveProfile(c);
@@ -1281,6 +1311,7 @@ int x265cu_profile_enable(x265cu_ctx* c, int32_t on)
 
 int x265cu_profile_get_busy(x265cu_ctx* c, double busy[X265CU_K_COUNT])
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     resolveProfile(c);
@@ -1290,6 +1321,7 @@ int x265cu_profile_get_busy(x265cu_ctx* c, double busy[X265CU_K_COUNT])
 
 int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launches[X265CU_K_COUNT], int32_t reset)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     resolveProfile(c);
@@ -1300,6 +1332,7 @@ int x265cu_profile_get(x265cu_ctx* c, double ms[X265CU_K_COUNT], uint64_t launch
 
 int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* u, const void* v, int32_t sy, int32_t sc)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || !slotOk(c, slot) || !y) return X265CU_ERR_BAD_ARG;
@@ -1308,6 +1341,7 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
 
 int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     if (!c || !slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
     const cudaError_t e = cudaEventQuery(c->slotConsumed[slot]);
@@ -1319,6 +1353,7 @@ int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
 
 int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     /* the statistics were published into mapped host memory by the frame's own pre-lookahead: wait for that only */
@@ -1336,6 +1371,7 @@ int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265c
 
 int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
@@ -1345,6 +1381,7 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
 
 int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* stores, int32_t n, int32_t* flags)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (n <= 0) return X265CU_OK;
@@ -1361,6 +1398,7 @@ int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 
 int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || (n > 0 && !jobs)) return X265CU_ERR_BAD_ARG;
@@ -1370,6 +1408,7 @@ int x265cu_cost_batch(x265cu_ctx* c, const x265cu_cost_job* jobs, int32_t n)
 
 int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* outs, int32_t n, x265cu_cost_result* res)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (n <= 0) return X265CU_OK;
@@ -1393,6 +1432,7 @@ int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
 
 int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_t n, uint32_t* costs)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || (n > 0 && (!jobs || !costs))) return X265CU_ERR_BAD_ARG;
@@ -1402,6 +1442,7 @@ int x265cu_weight_cost_batch(x265cu_ctx* c, const x265cu_wcost_job* jobs, int32_
 
 int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
@@ -1414,6 +1455,7 @@ int x265cu_cutree_reset(x265cu_ctx* c, int32_t slot)
 int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s, int32_t cost_store, int32_t l0, int32_t l1,
                             int32_t referenced, int32_t bipred_weight, double fps_factor)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     if (!slotOk(c, bs) || !slotOk(c, p0s) || !slotOk(c, p1s) || cost_store < 2 || cost_store >= c->geom.n_cost_stores ||
         l0 < 0 || l0 >= c->geom.n_mv_stores || l1 >= c->geom.n_mv_stores)
@@ -1439,7 +1481,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
         }
         CutreeJobDev& J = c->h_ctJobs[c->ctRingPos++];
         J.intraCost = slotPtr<int>(c, bs, L.intraCost); J.lowresCosts = (const unsigned short*)costStorePtr(c, bs, cost_store);
-        J.invQ = slotPtr<int>(c, bs, L.invQ); J.mv0 = mv0; J.mv1 = mv1;
+        J.invQ = slotInvQ(c, bs); J.mv0 = mv0; J.mv1 = mv1;
         J.ref0 = slotPtr<int>(c, p0s, L.propagate); J.ref1 = slotPtr<int>(c, p1s, L.propagate);
         J.self = slotPtr<int>(c, bs, L.propagate);
         J.bipredWeight = bipred_weight; J.pad = 0; J.fpsFactor = fps_factor;
@@ -1449,7 +1491,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
     flushCutree(c);
     Prof pr(c, X265CU_K_CUTREE, 1);
     cutree_propagate_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
-        c->g, slotPtr<int>(c, bs, L.intraCost), (const unsigned short*)costStorePtr(c, bs, cost_store), slotPtr<int>(c, bs, L.invQ),
+        c->g, slotPtr<int>(c, bs, L.intraCost), (const unsigned short*)costStorePtr(c, bs, cost_store), slotInvQ(c, bs),
         mv0, mv1, slotPtr<int>(c, bs, L.propagate), slotPtr<int>(c, p0s, L.propagate),
         slotPtr<int>(c, p1s, L.propagate), bipred_weight, fps_factor);
     CK(cudaGetLastError());
@@ -1458,6 +1500,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
 
 int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double weightdelta, double strength)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
@@ -1466,7 +1509,7 @@ int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double w
     if (st) return st;
     Prof pr(c, X265CU_K_CUTREE, 1);
     cutree_finish_kernel<<<(c->g.ncu + 255) / 256, 256, 0, c->stream>>>(
-        c->g, slotPtr<int>(c, slot, L.intraCost), slotPtr<int>(c, slot, L.invQ), slotPtr<int>(c, slot, L.propagate),
+        c->g, slotPtr<int>(c, slot, L.intraCost), slotInvQ(c, slot), slotPtr<int>(c, slot, L.propagate),
         slotPtr<double>(c, slot, L.qpAq), slotPtr<double>(c, slot, L.qpCuTree), fps_fix8, weightdelta, strength);
     CK(cudaGetLastError());
     return X265CU_OK;
@@ -1474,6 +1517,7 @@ int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double w
 
 int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree, int64_t* score, int32_t* rows)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!slotOk(c, slot) || cost_store < 0 || cost_store >= c->geom.n_cost_stores || cost_store == 1 || !score) return X265CU_ERR_BAD_ARG;
@@ -1515,6 +1559,45 @@ static int d2h(x265cu_ctx* c, void* dst, const void* src, size_t bytes)
     return X265CU_OK;
 }
 
+int x265cu_vbv_row_costs(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t qp_source, int32_t ctu_rows_lowres,
+                         int32_t pir_start, int32_t pir_end, int32_t n_rows, uint32_t* satd, uint32_t* intra,
+                         uint16_t* cost_for_rc, int32_t* intra_scaled)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    flushCutree(c);
+    const Geom& g = c->g;
+    const SlotLayout& L = c->lay;
+    if (!slotOk(c, slot) || cost_store < 0 || cost_store >= c->geom.n_cost_stores || cost_store == 1 || ctu_rows_lowres < 1 ||
+        qp_source < 0 || qp_source > 2 || n_rows < (g.bh + ctu_rows_lowres - 1) / ctu_rows_lowres)
+        return X265CU_ERR_BAD_ARG;
+    const unsigned short* costs = cost_store == 0 ? slotPtr<unsigned short>(c, slot, L.lowresCosts00)
+                                                  : (const unsigned short*)costStorePtr(c, slot, cost_store);
+    int st = mainWaitCost(c, slot, cost_store);
+    if (!st) st = mainWaitPre(c, slot);
+    /* scratch: row sums (2 x n_rows u32) | scaled costs (ncu u16) | scaled intra costs (ncu i32) */
+    const size_t offCost = alignUp((size_t)n_rows * 8, 256), offIntra = offCost + alignUp((size_t)g.ncu * 2, 256);
+    if (!st) st = ensureDev(c, &c->d_results, &c->resultsCap, offIntra + (size_t)g.ncu * 4);
+    if (st) return st;
+    CK(cudaMemsetAsync(c->d_results, 0, (size_t)n_rows * 8, c->stream));
+    {
+        Prof pr(c, X265CU_K_CUTREE, 1);
+        const double* qp = qp_source == 0 || !c->cfg.need_aq ? NULL : slotPtr<double>(c, slot, qp_source == 2 ? L.qpCuTree : L.qpAq);
+        vbv_rows_kernel<<<(g.ncu + 255) / 256, 256, 0, c->stream>>>(g, costs, slotPtr<int>(c, slot, L.intraCost), qp, ctu_rows_lowres,
+                                                                   pir_start, pir_end, (unsigned short*)(c->d_results + offCost),
+                                                                   (int*)(c->d_results + offIntra), (unsigned*)c->d_results,
+                                                                   (unsigned*)c->d_results + n_rows);
+    }
+    CK(cudaGetLastError());
+    if (satd) st = d2h(c, satd, c->d_results, (size_t)n_rows * 4);
+    if (intra && !st) st = d2h(c, intra, c->d_results + (size_t)n_rows * 4, (size_t)n_rows * 4);
+    if (cost_for_rc && !st) st = d2h(c, cost_for_rc, c->d_results + offCost, (size_t)g.ncu * 2);
+    if (intra_scaled && !st) st = d2h(c, intra_scaled, c->d_results + offIntra, (size_t)g.ncu * 4);
+    if (st) return st;
+    CK(cudaStreamSynchronize(c->stream));
+    return X265CU_OK;
+}
+
 __global__ void clamp_u16_kernel(const int* __restrict__ src, unsigned short* __restrict__ dst, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1529,6 +1612,7 @@ __global__ void unpack_mv_kernel(const int* __restrict__ src, int* __restrict__ 
 
 int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!slotOk(c, slot) || !o) return X265CU_ERR_BAD_ARG;
@@ -1537,12 +1621,12 @@ int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
     int st = mainWaitPre(c, slot);
     if (o->intra_cost && !st) st = d2h(c, o->intra_cost, c->slots[slot] + L.intraCost, (size_t)g.ncu * 4);
     if (o->intra_mode && !st) st = d2h(c, o->intra_mode, c->slots[slot] + L.intraMode, (size_t)g.ncu);
-    if (o->qp_aq_offset && !st) st = d2h(c, o->qp_aq_offset, c->slots[slot] + L.qpAq, (size_t)g.ncu * 8);
-    if (o->qp_cutree_offset && !st) st = d2h(c, o->qp_cutree_offset, c->slots[slot] + L.qpCuTree, (size_t)g.ncu * 8);
+    if (o->qp_aq_offset && !st) st = d2h(c, o->qp_aq_offset, c->slots[slot] + L.qpAq, (size_t)g.ncuFull * 8);
+    if (o->qp_cutree_offset && !st) st = d2h(c, o->qp_cutree_offset, c->slots[slot] + L.qpCuTree, (size_t)g.ncuFull * 8);
     if (o->inv_qscale_factor && !st)
     {
-        if (c->cfg.need_aq) st = d2h(c, o->inv_qscale_factor, c->slots[slot] + L.invQ, (size_t)g.ncu * 4);
-        else for (int i = 0; i < g.ncu; i++) o->inv_qscale_factor[i] = 256;   /* no AQ arrays: neutral scale */
+        if (c->cfg.need_aq) st = d2h(c, o->inv_qscale_factor, c->slots[slot] + L.invQ, (size_t)g.ncuFull * 4);
+        else for (int i = 0; i < g.ncuFull; i++) o->inv_qscale_factor[i] = 256;   /* no AQ arrays: neutral scale */
     }
     if (o->propagate_cost && !st)
     {
@@ -1579,6 +1663,7 @@ int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)
 
 int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!slotOk(c, slot) || store < 0 || store >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
@@ -1602,6 +1687,7 @@ int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, in
 
 int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* costs, int32_t* rows)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!slotOk(c, slot) || store < 2 || store >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
@@ -1618,6 +1704,7 @@ int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* cos
 /* unit-test hook (not part of the drop-in surface): SAD / SATD of n packed 8x8 block pairs */
 int x265cu_debug_block_metrics(x265cu_ctx* c, const void* a, const void* b, int32_t n, int32_t* sad, int32_t* satd)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || !a || !b || n <= 0) return X265CU_ERR_BAD_ARG;
@@ -1628,6 +1715,7 @@ int x265cu_debug_block_metrics(x265cu_ctx* c, const void* a, const void* b, int3
 int x265cu_debug_mc_metrics(x265cu_ctx* c, int32_t fenc_slot, int32_t ref_slot, const int32_t* cu_idx, const int32_t* mvs, int32_t n,
                             int32_t* sad, int32_t* satd)
 {
+    if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || !slotOk(c, fenc_slot) || !slotOk(c, ref_slot) || n <= 0) return X265CU_ERR_BAD_ARG;

@@ -39,6 +39,12 @@ struct Geom
     int lambda, depth, nb;
     int tpr;                    /* tiles per plane row = stride / 8 */
     int rowsPerSlice;           /* cooperative search slices (x265cu_config::rows_per_slice); 0 = none */
+    /* adaptive-quant block grid (calcAdaptiveQuantFrame, slicetype.cpp:452-472): blocks of aqBlock x aqBlock full-res
+     * samples visited in raster order with a RUNNING index, aqW per row; the arrays hold ncuFull entries and the
+     * frame means divide by ncuFull.  qg-size > 8: aqBlock 16, ncuFull = ncu.  qg-size 8: aqBlock 8, ncuFull = 4 ncu,
+     * consumers address block (2 cuX + i, 2 cuY + j) as 2 cuX + i + (2 cuY + j) * 2 bw, which is NOT the running index
+     * when picW / 8 is odd -- the reference's behaviour, reproduced as is */
+    int aqBlock, aqW, aqH, ncuFull;
 };
 
 /* sample offset of buffer coordinate (X, Y) (margins included, X,Y >= 0) inside a tiled plane */

@@ -219,48 +219,114 @@ __global__ void __launch_bounds__(256) aq_energy_kernel(Geom g, const P* __restr
     else if (threadIdx.x < 6) atomicAdd(&stats->wp_ssd[threadIdx.x - 3], s_acc[threadIdx.x]);
 }
 
-/* K2b: the transcendental finish of calcAdaptiveQuantFrame (slicetype.cpp:537-652, 681-694) for
- * aq-mode 0..3, qg-size > 8, in two launches of LA_AQ_CTAS CTAs.
- *   aq_pow_kernel    (aq-mode 2/3): qp_adj = pow(energy * bdc + 1, 0.1) per block and per-CTA partial sums;
- *   aq_finish_kernel : every CTA folds the partials (same fixed order everywhere), then finishes its blocks.
- * The two frame means are reduced in a fixed order that depends only on the block count, so the result is
- * deterministic.  (The reference sums sequentially in double; a different summation order perturbs qp_adj by
- * ~1e-15, far below the 1/64-QP grid of exp2fix8.) */
+/* qg-size 8: the same for 8x8 luma blocks + the co-located 4x4 chroma blocks (slicetype.cpp:64-68,79-80: var shifts
+ * 6 / 4).  One 8-lane group per block: lane r sums luma row r, lanes 0-3 / 4-7 a row of the U / V block.  Blocks are
+ * numbered by the reference's running index (aqW per row).  Samples are replicate-clamped like PicYuv's padding. */
+template <typename P>
+__global__ void __launch_bounds__(256) aq_energy8_kernel(Geom g, const P* __restrict__ y, const P* __restrict__ u,
+                                                         const P* __restrict__ v, unsigned* __restrict__ energy,
+                                                         FrameStatsDev* stats)
+{
+    __shared__ unsigned long long s_acc[6];
+    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const int blkRaw = blockIdx.x * 32 + grp;
+    const int nblk = g.aqW * g.aqH;
+    const bool act = blkRaw < nblk;
+    const int blk = act ? blkRaw : nblk - 1;
+    const int bx = (blk % g.aqW) * 8, by = (blk / g.aqW) * 8;
+    unsigned sum = 0, sqr = 0;
+    {
+        const P* row = y + (long long)min(by + r, g.picH - 1) * g.picW;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const unsigned s = row[min(bx + i, g.picW - 1)]; sum += s; sqr += s * s; }
+    }
+    unsigned cs = 0, cq = 0;
+    if (u)
+    {
+        const P* row = ((r < 4) ? u : v) + (long long)min((by >> 1) + (r & 3), g.cH - 1) * g.cW;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const unsigned s = row[min((bx >> 1) + i, g.cW - 1)]; cs += s; cq += s * s; }
+    }
+    sum = groupSum((int)sum); sqr = groupSum((int)sqr);
+    cs += __shfl_xor_sync(LA_FULL, cs, 1); cq += __shfl_xor_sync(LA_FULL, cq, 1);
+    cs += __shfl_xor_sync(LA_FULL, cs, 2); cq += __shfl_xor_sync(LA_FULL, cq, 2);
+    const unsigned us = __shfl_sync(LA_FULL, cs, 0, 8), uq = __shfl_sync(LA_FULL, cq, 0, 8);
+    const unsigned vs = __shfl_sync(LA_FULL, cs, 4, 8), vq = __shfl_sync(LA_FULL, cq, 4, 8);
+    if (r == 0 && act)
+    {
+        unsigned e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
+        atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr);
+        if (u)
+        {
+            e += uq - (unsigned)(((unsigned long long)us * us) >> 4);
+            e += vq - (unsigned)(((unsigned long long)vs * vs) >> 4);
+            atomicAdd(&s_acc[1], (unsigned long long)us); atomicAdd(&s_acc[4], (unsigned long long)uq);
+            atomicAdd(&s_acc[2], (unsigned long long)vs); atomicAdd(&s_acc[5], (unsigned long long)vq);
+        }
+        energy[blk] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(&stats->wp_sum[threadIdx.x], s_acc[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicAdd(&stats->wp_ssd[threadIdx.x - 3], s_acc[threadIdx.x]);
+}
+
+/* K2b: the transcendental finish of calcAdaptiveQuantFrame (slicetype.cpp:537-652, 681-694) for aq-mode 0..3:
+ *   aq_pow_kernel    (aq-mode 2/3): qp_adj = pow(energy * bdc + 1, 0.1) per block;
+ *   aq_mean_kernel   (aq-mode 2/3): the two frame sums, accumulated by ONE thread in the reference's block order
+ *                    (avg_adj += qp_adj; avg_adj_pow2 += qp_adj * qp_adj, :566-567) so that every rounding of the
+ *                    double sums -- and with it every qp offset and invQscaleFactor -- is the reference's by
+ *                    construction.  The warp stages 1024 values at a time in shared memory (coalesced), lane 0 adds them
+ *                    in order: ~10 cycles per block (two independent add chains), 0.17 ms for the 32400 blocks of a
+ *                    2160p frame, on one warp, off the critical path of the search batches;
+ *   aq_finish_kernel : the per-block finish, LA_AQ_CTAS CTAs.
+ * n = blocks visited (aqW * aqH, the running index); the means divide by g.ncuFull (:569-570). */
 #define LA_AQ_CTAS 64
 #define LA_AQ_THREADS 256
 
 __global__ void __launch_bounds__(LA_AQ_THREADS) aq_pow_kernel(Geom g, const unsigned* __restrict__ energy,
-                                                               double* __restrict__ qpCuTree, double* __restrict__ partial)
+                                                               double* __restrict__ qpCuTree)
 {
-    __shared__ double s_a[LA_AQ_THREADS], s_b[LA_AQ_THREADS];
-    const int tid = threadIdx.x, n = g.ncu;
+    const int n = g.aqW * g.aqH;
     const double bdc = (double)(1.f / (1 << (2 * (g.depth - 8))));
+    for (int i = blockIdx.x * LA_AQ_THREADS + threadIdx.x; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS)
+        qpCuTree[i] = pow(__dadd_rn(__dmul_rn((double)energy[i], bdc), 1.0), 0.1);
+}
+
+__global__ void __launch_bounds__(32) aq_mean_kernel(Geom g, const double* __restrict__ qpAdj, double* __restrict__ sums)
+{
+    __shared__ double s_q[1024];
+    const int n = g.aqW * g.aqH, lane = threadIdx.x;
     double a = 0, b = 0;
-    for (int i = blockIdx.x * LA_AQ_THREADS + tid; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS)
+    for (int base = 0; base < n; base += 1024)
     {
-        const double q = pow(__dadd_rn(__dmul_rn((double)energy[i], bdc), 1.0), 0.1);
-        qpCuTree[i] = q;
-        a = __dadd_rn(a, q);
-        b = __dadd_rn(b, __dmul_rn(q, q));
+        const int m = min(1024, n - base);
+        for (int i = lane; i < m; i += 32) s_q[i] = qpAdj[base + i];
+        __syncwarp();
+        if (lane == 0)
+        {
+#pragma unroll 8
+            for (int i = 0; i < m; i++)
+            {
+                const double q = s_q[i];
+                a = __dadd_rn(a, q);
+                b = __dadd_rn(b, __dmul_rn(q, q));
+            }
+        }
+        __syncwarp();
     }
-    s_a[tid] = a; s_b[tid] = b;
-    __syncthreads();
-    for (int o = LA_AQ_THREADS / 2; o; o >>= 1)
-    {
-        if (tid < o) { s_a[tid] = __dadd_rn(s_a[tid], s_a[tid + o]); s_b[tid] = __dadd_rn(s_b[tid], s_b[tid + o]); }
-        __syncthreads();
-    }
-    if (tid == 0) { partial[blockIdx.x] = s_a[0]; partial[LA_AQ_CTAS + blockIdx.x] = s_b[0]; }
+    if (lane == 0) { sums[0] = a; sums[1] = b; }
 }
 
 __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const unsigned* __restrict__ energy, int aqMode,
-                                                                  double aqStrength, int bWeightP, const double* __restrict__ partial,
+                                                                  double aqStrength, int bWeightP, const double* __restrict__ sums,
                                                                   double* __restrict__ qpAq, double* __restrict__ qpCuTree,
                                                                   int* __restrict__ invQ, FrameStatsDev* stats)
 {
-    __shared__ double s_strength, s_avg, s_bias;
-    const int tid = threadIdx.x, n = g.ncu;
-    const float modeOneConst = 14.427f, modeTwoConst = 11.f;
+    const int tid = threadIdx.x, n = g.aqW * g.aqH;
+    const bool qg8 = g.aqBlock == 8;
+    const float modeOneConst = qg8 ? 11.427f : 14.427f, modeTwoConst = qg8 ? 8.f : 11.f;     /* :459-472 */
     if (blockIdx.x == 0 && tid == 0 && bWeightP)
     {
         const int maxCol = ((g.picW + 8) >> 4) << 4, maxRow = ((g.picH + 8) >> 4) << 4;
@@ -275,25 +341,19 @@ __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const 
     if (aqMode == 0 || aqStrength == 0)
     {
         if (aqMode && aqStrength == 0)
-            for (int i = blockIdx.x * LA_AQ_THREADS + tid; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS) { qpAq[i] = 0; qpCuTree[i] = 0; invQ[i] = 256; }
+            for (int i = blockIdx.x * LA_AQ_THREADS + tid; i < g.ncuFull; i += LA_AQ_CTAS * LA_AQ_THREADS) { qpAq[i] = 0; qpCuTree[i] = 0; invQ[i] = 256; }
         return;
     }
-    if (tid == 0)
+    double strength, avg_adj = 0, bias_strength = 0;
+    if (aqMode == 2 || aqMode == 3)
     {
-        if (aqMode == 2 || aqMode == 3)
-        {
-            double sa = 0, sb = 0;
-            for (int i = 0; i < LA_AQ_CTAS; i++) { sa = __dadd_rn(sa, partial[i]); sb = __dadd_rn(sb, partial[LA_AQ_CTAS + i]); }
-            const double avg_adj = __ddiv_rn(sa, (double)n), avg_adj_pow2 = __ddiv_rn(sb, (double)n);
-            s_strength = __dmul_rn(aqStrength, avg_adj);
-            s_avg = __dadd_rn(avg_adj, -__ddiv_rn(__dmul_rn((double)0.5f, __dadd_rn(avg_adj_pow2, -(double)modeTwoConst)), avg_adj));
-            s_bias = __dmul_rn(1.0, aqStrength);
-        }
-        else
-            s_strength = __dmul_rn(aqStrength, (double)1.0397f);
+        const double mean = __ddiv_rn(sums[0], (double)g.ncuFull), mean2 = __ddiv_rn(sums[1], (double)g.ncuFull);
+        strength = __dmul_rn(aqStrength, mean);
+        avg_adj = __dadd_rn(mean, -__ddiv_rn(__dmul_rn((double)0.5f, __dadd_rn(mean2, -(double)modeTwoConst)), mean));
+        bias_strength = __dmul_rn(1.0, aqStrength);
     }
-    __syncthreads();
-    const double strength = s_strength, avg_adj = s_avg, bias_strength = s_bias;
+    else
+        strength = __dmul_rn(aqStrength, (double)1.0397f);
     for (int i = blockIdx.x * LA_AQ_THREADS + tid; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS)
     {
         double qp_adj;
@@ -315,6 +375,16 @@ __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const 
         qpCuTree[i] = qp_adj;
         invQ[i] = exp2fix8(qp_adj);
     }
+}
+
+/* qg-size 8: the per-lowres-block scale is the mean of its four 8x8 factors (slicetype.cpp:656-670) */
+__global__ void __launch_bounds__(256) aq_invq8x8_kernel(Geom g, const int* __restrict__ invQ, int* __restrict__ invQ8)
+{
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu >= g.ncu) return;
+    const int cuX = cu % g.bw, cuY = cu / g.bw, fs = 2 * g.bw;
+    const int i = cuX * 2 + cuY * g.bw * 4;
+    invQ8[cu] = (invQ[i] + invQ[i + 1] + invQ[i + fs] + invQ[i + fs + 1]) / 4;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1152,6 +1222,23 @@ __global__ void __launch_bounds__(256) cutree_finish_kernel(Geom g, const int* _
 {
     const int cu = blockIdx.x * blockDim.x + threadIdx.x;
     if (cu >= g.ncu) return;
+    if (g.aqBlock == 8)
+    {
+        /* qg-size 8 (slicetype.cpp:3764-3782): invQ is invQscaleFactor8x8; one ratio for the block's four 8x8 offsets */
+        const int intracost = ((intraCost[cu]) / 4 * invQ[cu] + 128) >> 8;
+        if (intracost)
+        {
+            const int propagateCost = (min(propagate[cu], 65535) / 4 * fpsFactor + 128) >> 8;
+            const double log2_ratio = __dadd_rn(__dadd_rn(log2((double)(intracost + propagateCost)), -log2((double)intracost)), weightdelta);
+            const double d = __dmul_rn(strength, log2_ratio);
+            const int fs = 2 * g.bw, i = (cu % g.bw) * 2 + (cu / g.bw) * g.bw * 4;
+            qpCuTree[i] = __dadd_rn(qpAq[i], -d);
+            qpCuTree[i + 1] = __dadd_rn(qpAq[i + 1], -d);
+            qpCuTree[i + fs] = __dadd_rn(qpAq[i + fs], -d);
+            qpCuTree[i + fs + 1] = __dadd_rn(qpAq[i + fs + 1], -d);
+        }
+        return;
+    }
     const int intracost = (intraCost[cu] * invQ[cu] + 128) >> 8;
     if (intracost)
     {
@@ -1159,6 +1246,15 @@ __global__ void __launch_bounds__(256) cutree_finish_kernel(Geom g, const int* _
         const double log2_ratio = __dadd_rn(__dadd_rn(log2((double)(intracost + propagateCost)), -log2((double)intracost)), weightdelta);
         qpCuTree[cu] = __dadd_rn(qpAq[cu], -__dmul_rn(strength, log2_ratio));
     }
+}
+
+/* the qp offset of lowres block cu: the block's own entry, or with qg-size 8 the mean of its four 8x8 entries
+ * (slicetype.cpp:3859-3866, 1414-1421) */
+__device__ __forceinline__ double blockQpOffset(const Geom& g, const double* __restrict__ qp, int cu)
+{
+    if (g.aqBlock != 8) return qp[cu];
+    const int fs = 2 * g.bw, i = (cu % g.bw) * 2 + (cu / g.bw) * g.bw * 4;
+    return __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(qp[i], qp[i + 1]), qp[i + fs]), qp[i + fs + 1]), 4.0);
 }
 
 __global__ void __launch_bounds__(256) cost_recalc_kernel(Geom g, const unsigned short* __restrict__ lowresCosts,
@@ -1173,13 +1269,44 @@ __global__ void __launch_bounds__(256) cost_recalc_kernel(Geom g, const unsigned
     {
         const int cux = cu % g.bw, cuy = cu / g.bw;
         int cuCost = lowresCosts[cu] & LA_LOWRES_COST_MASK;
-        cuCost = (cuCost * exp2fix8(qpOffset[cu]) + 128) >> 8;
+        cuCost = (cuCost * exp2fix8(blockQpOffset(g, qpOffset, cu)) + 128) >> 8;
         atomicAdd(&rowSatds[cuy], cuCost);
         if ((cuy > 0 && cuy < g.bh - 1 && cux > 0 && cux < g.bw - 1) || g.bw <= 2 || g.bh <= 2)
             atomicAdd(&s_score, (unsigned long long)cuCost);
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_score) atomicAdd(score, s_score);
+}
+
+/* The VBV half of Lookahead::getEstimatedPictureCost (slicetype.cpp:1387-1436): the coded estimate's block costs and the
+ * intra costs scaled by the block's qp offset, and their sums per CTU row (FrameData::m_rowStat[].satdForVbv /
+ * intraSatdForVbv).  The reference rewrites lowresCostForRc / intraCost in place on the host; here the scaled arrays go to
+ * scratch that the caller mirrors, the device arrays stay as the lookahead needs them.  qpOffset NULL = no scaling.
+ * pirStart/pirEnd: the intra-refresh column range of a P slice (diff term, :1425-1427), -1 = none. */
+__global__ void __launch_bounds__(256) vbv_rows_kernel(Geom g, const unsigned short* __restrict__ lowresCosts,
+                                                       const int* __restrict__ intraCost, const double* __restrict__ qpOffset,
+                                                       int scale, int pirStart, int pirEnd,
+                                                       unsigned short* __restrict__ costForRc, int* __restrict__ intraOut,
+                                                       unsigned* rowSatd, unsigned* rowIntra)
+{
+    const int cu = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cu >= g.ncu) return;
+    const int cuy = cu / g.bw;
+    unsigned short c = lowresCosts[cu] & LA_LOWRES_COST_MASK;
+    int ic = intraCost[cu];
+    if (qpOffset)
+    {
+        const int f = exp2fix8(blockQpOffset(g, qpOffset, cu));
+        c = (unsigned short)((c * f + 128) >> 8);
+        ic = (ic * f + 128) >> 8;
+    }
+    costForRc[cu] = c;
+    intraOut[cu] = ic;
+    unsigned add = c;
+    if (pirStart >= 0)
+        add += (unsigned)((pirEnd - pirStart + 1) * (ic - (int)c));
+    atomicAdd(&rowSatd[cuy / scale], add);
+    atomicAdd(&rowIntra[cuy / scale], (unsigned)ic);
 }
 
 /* debug / unit-test kernel: SAD and SATD of n pairs of packed 8x8 blocks (mirrors the reference's

@@ -23,6 +23,8 @@ void x265la_param_default(x265la_param* q)
     q->aqMode = p.rc.aqMode; q->aqStrength = p.rc.aqStrength; q->cuTree = p.rc.cuTree;
     q->qCompress = p.rc.qCompress; q->qgSize = p.rc.qgSize; q->rateControlMode = p.rc.rateControlMode;
     q->extraSlots = p.extraSlots; q->speculate = p.speculate; q->asyncDepth = p.asyncDepth;
+    q->pendingMax = p.pendingMax; q->batchMin = p.batchMin; q->gopLookahead = p.gopLookahead; q->radl = p.radl;
+    q->bFrameBias = p.bFrameBias; q->bIntraRefresh = p.bIntraRefresh; q->lookaheadSlices = p.lookaheadSlices;
 }
 
 void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
@@ -78,9 +80,9 @@ int x265la_shard_config(void* la, int32_t rank, int32_t nranks, x265cu_exchange_
 { return x265cu_shard_config(((Lookahead*)la)->engine(), rank, nranks, fn, user); }
 
 void* x265la_add_picture(void* la, const void* y, const void* u, const void* v, int32_t strideY, int32_t strideC,
-                         int64_t pts, int32_t sliceType)
+                         int64_t pts, int32_t sliceType, int32_t sliceTypeReq)
 {
-    return ((Lookahead*)la)->addPicture(y, u, v, strideY, strideC, pts, sliceType);
+    return ((Lookahead*)la)->addPicture(y, u, v, strideY, strideC, pts, sliceType, sliceTypeReq);
 }
 
 void x265la_flush(void* la) { ((Lookahead*)la)->flush(); }
@@ -106,6 +108,27 @@ int64_t x265la_estimated_picture_cost(void* la, void* frame, void* ref0, void* r
 }
 
 void x265la_release(void* la, void* frame) { ((Lookahead*)la)->releaseFrame((Frame*)frame); }
+
+int x265la_vbv_rows(void* la) { return ((Lookahead*)la)->vbvRows(); }
+
+int x265la_vbv_row_costs(void* la, void* frame, int32_t pirStartCol, int32_t pirEndCol, uint32_t* satdForVbv,
+                         uint32_t* intraSatdForVbv, uint16_t* lowresCostForRc, int32_t* intraCostScaled)
+{
+    return ((Lookahead*)la)->getVbvRowCosts((Frame*)frame, pirStartCol, pirEndCol, satdForVbv, intraSatdForVbv,
+                                            lowresCostForRc, intraCostScaled) ? 0 : -1;
+}
+
+int x265la_frame_planned(void* /*la*/, void* frame, int64_t* plannedSatd, int32_t* plannedType, int32_t n, int32_t* indB)
+{
+    const Lowres& l = ((Frame*)frame)->m_lowres;
+    for (int i = 0; i < n && i <= LOOKAHEAD_MAX; i++)
+    {
+        if (plannedSatd) plannedSatd[i] = l.plannedSatd[i];
+        if (plannedType) plannedType[i] = l.plannedType[i];
+    }
+    if (indB) *indB = l.indB;
+    return 0;
+}
 
 int x265la_frame_scalars(void* lav, void* frame, int64_t* costEst, int64_t* costEstAq, int32_t* intraMbs,
                          int32_t* rowSatdsValid, uint64_t* wp_ssd, uint64_t* wp_sum, double* wdelta)

@@ -44,14 +44,24 @@ void* x265la_open(const x265la_param* p, char* err, int32_t errLen);   /* NULL o
 void  x265la_close(void* la);
 int   x265la_get_geometry(void* la, x265cu_geometry* g);
 const char* x265la_last_error(void* la);
-/* Lookahead::addPicture; returns the frame handle or NULL */
+/* Lookahead::addPicture; returns the frame handle or NULL.  sliceType: the argument of the reference's addPicture (first-pass
+ * type of a 2-pass encode, else X265_TYPE_AUTO); sliceTypeReq: x265_picture::sliceType as an application forces it
+ * (Encoder::encode stores it in Lowres::sliceTypeReq, encoder.cpp:1714) */
 void* x265la_add_picture(void* la, const void* y, const void* u, const void* v, int32_t strideY, int32_t strideC,
-                         int64_t pts, int32_t sliceType);
+                         int64_t pts, int32_t sliceType, int32_t sliceTypeReq);
 void  x265la_flush(void* la);
 /* Lookahead::getDecidedPicture; 1 = frame returned, 0 = none yet, <0 = error */
 int   x265la_get_decided(void* la, x265la_frame_info* out);
 /* Lookahead::getEstimatedPictureCost with explicit references (handles, may be NULL) */
 int64_t x265la_estimated_picture_cost(void* la, void* frame, void* ref0, void* ref1);
+/* the VBV half of getEstimatedPictureCost (slicetype.cpp:1387-1436) for the estimate the last
+ * x265la_estimated_picture_cost of this frame read: x265la_vbv_rows() row sums, ncu scaled costs (NULL = skip); 0 = ok */
+int   x265la_vbv_rows(void* la);
+int   x265la_vbv_row_costs(void* la, void* frame, int32_t pirStartCol, int32_t pirEndCol, uint32_t* satdForVbv,
+                           uint32_t* intraSatdForVbv, uint16_t* lowresCostForRc, int32_t* intraCostScaled);
+/* what RateControl reads of the VBV lookahead (ratecontrol.cpp:2512-2577): Lowres::plannedSatd / plannedType (n entries
+ * each, n <= 251) and indB */
+int   x265la_frame_planned(void* la, void* frame, int64_t* plannedSatd, int32_t* plannedType, int32_t n, int32_t* indB);
 void  x265la_release(void* la, void* frame);
 
 /* published Lowres state of one frame, reference layout (common/lowres.h:171-263) */

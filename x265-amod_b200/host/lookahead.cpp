@@ -6,7 +6,7 @@
  * pool, so only the decisions (and their order of first touch) are shared with it.
  *
  * Not supported (create() fails with an error string rather than silently diverging):
- * --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion, qg-size 8,
+ * --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion,
  * zones, temporal sub-layers, analysis load, fades, chunked encodes.
  */
 #include "lookahead.h"
@@ -133,7 +133,7 @@ bool Lookahead::create()
     m_rowsPerSlice = rowsPerSlice;
     m_dualSlicing = rowsPerSlice > 0 && m_bBatchMotionSearch;
     m_costVariants = m_dualSlicing ? 8 : 2;
-    if (p.rc.qgSize < 16) { fail("qg-size 8 is not supported by the GPU lookahead"); return false; }
+    if (p.rc.qgSize != 8 && p.rc.qgSize != 16 && p.rc.qgSize != 32 && p.rc.qgSize != 64) { fail("qg-size must be 8, 16, 32 or 64"); return false; }
     if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
     if (p.lookaheadDepth && p.lookaheadDepth <= p.bframes) { fail("rc-lookahead must exceed bframes"); return false; }
@@ -176,7 +176,14 @@ void Lookahead::destroy()
 {
     for (size_t i = 0; i < m_pool.size(); i++) delete m_pool[i];
     m_pool.clear(); m_inputQueue.clear(); m_outputQueue.clear(); m_resident.clear(); m_pendingSpec.clear();
-    if (m_ctx) { x265cu_destroy(m_ctx); m_ctx = NULL; }
+    if (m_ctx)
+    {
+        x265cu_sync(m_ctx);
+        for (std::map<const void*, bool>::iterator it = m_pinned.begin(); it != m_pinned.end(); ++it)
+            if (it->second) x265cu_unpin_host(m_ctx, const_cast<void*>(it->first));
+        m_pinned.clear();
+        x265cu_destroy(m_ctx); m_ctx = NULL;
+    }
 }
 
 /* Lowres::init minus the pixel work (common/lowres.cpp:337-365) */
@@ -188,6 +195,7 @@ void Lookahead::initLowres(Frame* f, int poc)
     l.slot = slot;
     l.frameNum = poc;
     l.satdCost = -1;
+    l.rcD0 = l.rcD1 = -1;
     for (int i = 0; i < BFRAME_MAX + 2; i++)
         for (int j = 0; j < BFRAME_MAX + 2; j++)
         {
@@ -226,7 +234,7 @@ void Lookahead::releaseFrame(Frame* f) { if (f) { f->m_released = true; recycle(
 
 /* slicetype.cpp:1200-1243 */
 Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int strideY, int strideC,
-                             int64_t pts, int sliceType)
+                             int64_t pts, int sliceType, int sliceTypeReq)
 {
     if (m_failed) return NULL;
     if (!m_filled)   /* checkLookaheadQueue */
@@ -238,16 +246,40 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     for (size_t i = 0; i < m_pool.size(); i++)
         if (!m_pool[i]->m_inUse) { f = m_pool[i]; break; }
     if (!f) { recycle(); for (size_t i = 0; i < m_pool.size(); i++) if (!m_pool[i]->m_inUse) { f = m_pool[i]; break; } }
-    if (!f) return NULL;
+    if (!f)
+    {
+        /* recoverable (the caller can release frames and retry), so the context is not marked failed */
+        snprintf(m_error, sizeof(m_error), "no free frame slot: the caller holds too many unreleased frames (raise LookaheadParam::extraSlots)");
+        return NULL;
+    }
     f->m_inUse = true; f->m_released = false; f->m_speculated = false; f->m_lowresInit = false;
     f->m_poc = m_pocNext++; f->m_pts = pts; f->m_reorderedPts = 0;
     f->m_planes[0] = y; f->m_planes[1] = u; f->m_planes[2] = v; f->m_strideY = strideY; f->m_strideC = strideC;
     initLowres(f, f->m_poc);
+    /* Encoder::encode (encoder.cpp:1713-1714, 1863): the type an application forces through x265_picture::sliceType goes
+     * to Lowres::sliceTypeReq -- the frame is analysed as AUTO and the type re-imposed at slicetype.cpp:1938 --, while
+     * addPicture's own argument is the first-pass type of a 2-pass encode and lands in Lowres::sliceType */
     f->m_lowres.sliceType = sliceType;
-    f->m_lowres.sliceTypeReq = TYPE_AUTO;
+    f->m_lowres.sliceTypeReq = sliceTypeReq;
     if (m_param.shardCount > 1 &&
         !check(x265cu_slot_owner(m_ctx, f->m_lowres.slot, f->m_poc % m_param.shardCount), "x265cu_slot_owner"))
         return NULL;
+    if (m_param.pinHost)
+    {
+        /* page-lock the caller's picture buffers the first time they are seen (an encoder recycles a fixed set of them,
+         * PicYuv via the DPB free list, encoder.cpp:1632): pinned uploads run at full PCIe rate and truly asynchronously */
+        const size_t bpp = m_param.internalBitDepth > 8 ? 2 : 1;
+        const int cw = (m_param.sourceWidth + 1) / 2, ch = (m_param.sourceHeight + 1) / 2;
+        const void* ptr[3] = { y, u, v };
+        const size_t len[3] = { ((size_t)strideY * (m_param.sourceHeight - 1) + m_param.sourceWidth) * bpp,
+                                ((size_t)strideC * (ch - 1) + cw) * bpp, ((size_t)strideC * (ch - 1) + cw) * bpp };
+        for (int i = 0; i < 3; i++)
+            if (ptr[i] && !m_pinned.count(ptr[i]))
+            {
+                /* best effort: a refusal (locked-memory limit) only costs speed */
+                m_pinned[ptr[i]] = x265cu_pin_host(m_ctx, const_cast<void*>(ptr[i]), len[i]) == X265CU_OK;
+            }
+    }
     /* the device starts the frame's pre-lookahead now; results are collected in slicetypeDecide */
     if (!check(x265cu_frame_upload(m_ctx, f->m_lowres.slot, y, u, v, strideY, strideC), "x265cu_frame_upload"))
         return NULL;
@@ -1514,8 +1546,8 @@ void Lookahead::vbvLookahead(Lowres** frames, int numFrames, int keyframe)
     frames[nextNonB]->plannedType[idx] = TYPE_AUTO;
 }
 
-/* slicetype.cpp:1327-1386 (the VBV row aggregation of :1387-1436 needs FrameData and stays
- * with the encoder; it reads the arrays fetchCosts/fetchFrame mirror) */
+/* slicetype.cpp:1327-1386.  The reference derives p0 / p1 from the slice's reference lists; the caller passes the
+ * frames themselves (NULL = none). */
 void Lookahead::getEstimatedPictureCost(Frame* cur, Frame* ref0, Frame* ref1)
 {
     Lowres* frames[2 * (BFRAME_MAX + 2) + 2];
@@ -1536,14 +1568,27 @@ void Lookahead::getEstimatedPictureCost(Frame* cur, Frame* ref0, Frame* ref1)
     }
     else
     {
-        if (!ref0 || !ref1) return;
-        b = cur->m_poc - ref0->m_poc;
-        p1 = b + ref1->m_poc - cur->m_poc;
-        frames[0] = &ref0->m_lowres;
-        frames[b] = &cur->m_lowres;
-        frames[p1] = &ref1->m_lowres;
+        if (!ref1) return;
+        if (ref0)
+        {
+            b = cur->m_poc - ref0->m_poc;
+            p1 = b + ref1->m_poc - cur->m_poc;
+            frames[0] = &ref0->m_lowres;
+            frames[b] = &cur->m_lowres;
+            frames[p1] = &ref1->m_lowres;
+        }
+        else
+        {
+            /* a B slice without a list-0 reference (a RADL leading picture): estimated against itself, :1360-1366 */
+            p0 = b = 0;
+            p1 = ref1->m_poc - cur->m_poc;
+            frames[0] = &cur->m_lowres;
+            frames[p1] = &ref1->m_lowres;
+        }
     }
+    if (b - p0 < 0 || b - p0 >= m_geom.nb || p1 - b < 0 || p1 - b >= m_geom.nb) { fail("getEstimatedPictureCost: references outside the (bframes+2) window"); return; }
     const double t0 = nowSec();
+    cur->m_lowres.rcD0 = b - p0; cur->m_lowres.rcD1 = p1 - b;
     if (m_param.rc.cuTree)
         cur->m_lowres.satdCost = frameCostRecalculate(frames, p0, p1, b);
     else if (m_param.rc.aqMode)
@@ -1551,6 +1596,26 @@ void Lookahead::getEstimatedPictureCost(Frame* cur, Frame* ref0, Frame* ref1)
     else
         cur->m_lowres.satdCost = cur->m_lowres.costEst[b - p0][p1 - b];
     m_timers[8] += nowSec() - t0;
+}
+
+/* The VBV half of getEstimatedPictureCost (slicetype.cpp:1387-1436) for the estimate the last getEstimatedPictureCost of
+ * this frame named: per CTU row the sums the reference adds to m_rowStat[].satdForVbv / intraSatdForVbv, and the scaled
+ * lowresCostForRc / intraCost arrays it leaves in the Lowres (any output may be NULL). */
+bool Lookahead::getVbvRowCosts(Frame* cur, int pirStartCol, int pirEndCol, uint32_t* satdForVbv, uint32_t* intraSatdForVbv,
+                               uint16_t* lowresCostForRc, int32_t* intraCostScaled)
+{
+    const Lowres& l = cur->m_lowres;
+    if (l.rcD0 < 0) { fail("getVbvRowCosts before getEstimatedPictureCost"); return false; }
+    const int cs = l.costStore[l.rcD0][l.rcD1];
+    if (cs < 0) { fail("getVbvRowCosts on an estimate that was never computed"); return false; }
+    const int scale = m_param.maxCUSize / 16;
+    /* :1408-1410: B frames and runs without cuTree read qpAqOffset */
+    int qpSource = 0;
+    if (m_param.rc.aqMode)
+        qpSource = (l.sliceType == TYPE_B || !m_param.rc.cuTree) ? 1 : 2;
+    const bool pir = m_param.bIntraRefresh && l.sliceType == TYPE_P && pirStartCol >= 0;
+    return check(x265cu_vbv_row_costs(m_ctx, l.slot, cs, qpSource, scale, pir ? pirStartCol : -1, pir ? pirEndCol : -1,
+                                      vbvRows(), satdForVbv, intraSatdForVbv, lowresCostForRc, intraCostScaled), "x265cu_vbv_row_costs");
 }
 
 /* -------------------------------------------------------------------------------------------

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <deque>
+#include <map>
 #include <vector>
 #include "x265cu.h"
 
@@ -69,7 +70,8 @@ struct LookaheadParam
     int pendingMax;      /* streaming + weightp: frames that may wait for their pixel sums before addPicture blocks on them */
     int asyncDepth;      /* extra frames of input delay before a decision is taken (0 = the reference's trigger).  The
                             decision analyses the same frames either way; the GPU gets that many frames of slack */
-    int pinHost;         /* page-lock pictures handed to addPicture */
+    int pinHost;         /* page-lock the picture buffers handed to addPicture the first time each is seen (they must then
+                            stay allocated until destroy(); meant for an encoder's recycled PicYuv buffers) */
 };
 void lookaheadParamDefault(LookaheadParam* p);   /* x265_param_default + preset medium, param.cpp:164-349 */
 
@@ -92,6 +94,7 @@ struct Lowres
     int     plannedType[LOOKAHEAD_MAX + 1];
     int64_t plannedSatd[LOOKAHEAD_MAX + 1];
     int     indB;
+    int     rcD0, rcD1;      /* the (b - p0, p1 - b) estimate the last getEstimatedPictureCost read; -1 = none yet */
 
     /* publication state: which device store holds what the reference would hold */
     int     mvStore[2][BFRAME_MAX + 2];                      /* -1 = lowresMvs[l][d][0].x == 0x7FFF */
@@ -141,14 +144,20 @@ public:
     void    destroy();
     void    stopJobs() {}
     /* the reference takes a Frame the encoder filled; here the picture is handed over directly.
-     * Returns NULL when no frame slot is free (caller holds too many unreleased frames). */
+     * sliceType: Lookahead::addPicture's argument (the first-pass type of a 2-pass encode, else AUTO);
+     * sliceTypeReq: x265_picture::sliceType as the application forces it (Frame::m_lowres.sliceTypeReq, encoder.cpp:1714).
+     * Returns NULL (and sets the error string) when no frame slot is free (caller holds too many unreleased frames). */
     Frame*  addPicture(const void* y, const void* u, const void* v, int strideY, int strideC,
-                       int64_t pts, int sliceType);
+                       int64_t pts, int sliceType, int sliceTypeReq = TYPE_AUTO);
     void    flush();
     Frame*  getDecidedPicture();
     /* RateControl's entry point (slicetype.cpp:1327-1439).  The reference derives p0/p1 from the
      * slice's reference lists; the caller passes the POC distances instead (0 = none). */
     void    getEstimatedPictureCost(Frame* curFrame, Frame* ref0, Frame* ref1);
+    /* its VBV half (slicetype.cpp:1387-1436), see lookahead.cpp; arrays of vbvRows() / geometry().ncu entries */
+    bool    getVbvRowCosts(Frame* curFrame, int pirStartCol, int pirEndCol, uint32_t* satdForVbv, uint32_t* intraSatdForVbv,
+                           uint16_t* lowresCostForRc, int32_t* intraCostScaled);
+    int     vbvRows() const { return (m_param.sourceHeight + m_param.maxCUSize - 1) / m_param.maxCUSize; }
     int     findSliceType(int poc);
     void    releaseFrame(Frame* f);        /* encoder is done with the frame (DPB recycle) */
 
@@ -192,6 +201,7 @@ private:
     std::vector<Frame*> m_pool;           /* one per slot */
     std::vector<Frame*> m_resident;       /* frames with live slots, by arrival */
     std::deque<Frame*>  m_pendingSpec;    /* arrived, searches / costs not enqueued yet */
+    std::map<const void*, bool> m_pinned; /* caller buffers page-locked by pinHost (true = registered) */
     int     m_pocNext;
     bool    m_failed; char m_error[256];
 
