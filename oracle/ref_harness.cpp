@@ -141,6 +141,7 @@ struct Handle
     std::vector<Frame*> retired;     /* frames drained from the lookahead; kept alive because
                                         later decisions still reference m_lastNonB */
     double      secondsInLookahead;
+    double      secondsInSnapshot;   /* harness overhead inside put / flush, for callers that time those calls */
 };
 
 void snapshot(Handle* h, Frame* f)
@@ -232,7 +233,11 @@ void drain(Handle* h, bool snap)
         if (!f)
             break;
         if (snap)
+        {
+            double s0 = nowSec();
             snapshot(h, f);
+            h->secondsInSnapshot += nowSec() - s0;
+        }
         else
         {
             FrameSnap* s = new FrameSnap;
@@ -318,7 +323,7 @@ void* ref_la_open(const RefLaConfig* c)
     h->cfg = *c; h->userParam = p;
     h->enc = static_cast<Encoder*>(e);
     h->la = h->enc->m_lookahead;
-    h->pocNext = 0; h->flushed = false; h->secondsInLookahead = 0;
+    h->pocNext = 0; h->flushed = false; h->secondsInLookahead = 0; h->secondsInSnapshot = 0;
     return h;
 }
 
@@ -452,6 +457,21 @@ int ref_la_estimate(void* hv, int idx, int idxRef0, int idxRef1, int pirStartCol
 }
 
 int ref_la_num_out(void* hv) { return (int)((Handle*)hv)->out.size(); }
+double ref_la_snapshot_seconds(void* hv) { return ((Handle*)hv)->secondsInSnapshot; }
+
+/* free the arrays of snapshot `idx` (its scalars stay readable): a long full-size run is compared frame by frame */
+void ref_la_drop(void* hv, int idx)
+{
+    Handle* h = (Handle*)hv;
+    if (idx < 0 || idx >= (int)h->out.size()) return;
+    FrameSnap* s = h->out[idx];
+    FrameSnap* t = new FrameSnap;
+    memset(&t->h, 0, sizeof(t->h));
+    t->h.poc = s->h.poc; t->h.sliceType = s->h.sliceType; t->h.bScenecut = s->h.bScenecut; t->h.bKeyframe = s->h.bKeyframe;
+    t->frame = s->frame;
+    delete s;
+    h->out[idx] = t;
+}
 double ref_la_seconds(void* hv) { return ((Handle*)hv)->secondsInLookahead; }
 
 int ref_la_get(void* hv, int idx, RefLaFrame* out)

@@ -67,6 +67,9 @@ def load(depth):
     lib.ref_la_open.argtypes = [C.POINTER(RefLaConfig)]
     lib.ref_la_put.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.ref_la_put_typed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_la_snapshot_seconds.argtypes = [C.c_void_p]
+    lib.ref_la_snapshot_seconds.restype = C.c_double
+    lib.ref_la_drop.argtypes = [C.c_void_p, C.c_int]
     lib.ref_la_estimate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ref_la_flush.argtypes = [C.c_void_p, C.c_int]
     lib.ref_la_num_out.argtypes = [C.c_void_p]
@@ -79,6 +82,8 @@ def load(depth):
     lib.ref_satd8x8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.ref_sad8x8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.ref_exp2fix8.argtypes = [C.c_double]
+    lib.ref_simd_install.argtypes = [C.c_int]
+    lib.ref_simd_selftest.argtypes = [C.c_int]
     lib.ref_setup_primitives()
     _libs[key] = lib
     return lib
@@ -141,10 +146,17 @@ class RefLookahead:
         if self.lib.ref_la_estimate(self.h, idx, ref0, ref1, pir[0], pir[1]) != 0:
             raise RuntimeError("ref_la_estimate: frame %d or its references are no longer alive" % idx)
 
-    def frame(self, idx):
+    def frame(self, idx, drop=False):
+        """decided frame idx as a dict; drop=True frees the harness' copy afterwards (full-size runs)"""
         f = RefLaFrame()
         self.lib.ref_la_get(self.h, idx, C.byref(f))
-        return self._to_dict(f)
+        d = self._to_dict(f)
+        if drop:
+            self.lib.ref_la_drop(self.h, idx)
+        return d
+
+    def snapshot_seconds(self):
+        return self.lib.ref_la_snapshot_seconds(self.h)
 
     def flush(self, snap=True):
         return self.lib.ref_la_flush(self.h, 1 if snap else 0)
@@ -210,6 +222,17 @@ class RefLookahead:
             self.close()
         except Exception:
             pass
+
+
+def simd_install(depth, on):
+    """install (on=True) / remove the SSE4.1 intrinsics shims (oracle/ref_simd.cpp) in the reference's primitives table;
+    returns True when they are active"""
+    return bool(load(depth).ref_simd_install(1 if on else 0))
+
+
+def simd_selftest(depth, iterations=3000):
+    """mismatches of the shims against the C primitives on the pixelharness buffer recipe (0 = bit-exact, -1 = no SSE4.1)"""
+    return load(depth).ref_simd_selftest(iterations)
 
 
 def mvcost_table(depth, n=4096):

@@ -159,6 +159,31 @@ def test_cuda_speculation_modes_and_async_depth(name, mode, pkg, synth, simdir):
     assert not bad, "\n".join(bad[:10])
 
 
+@pytest.mark.parametrize("name", [c[0] for c in cases.FULL_SIZE])
+def test_baseline_configs_at_full_size_match_live_reference(name, pkg, synth):
+    """BASELINE.json's configurations themselves (2160p main10 rc-lookahead 60 bframes 8 -- the benchmarked one --, 1080p
+    8-bit rc-lookahead 20 bframes 4, 1080p preset-slower depths with weightp on fades / cuts / flashes), full size, against
+    the live unmodified reference: every published field of every decided frame, bit-exact."""
+    case = [c for c in cases.FULL_SIZE if c[0] == name][0]
+    if not refbind.available(case[1]):
+        pytest.skip("oracle/_ref not in this snapshot")
+    bad, n = cases.compare_streaming(pkg, synth, refbind, compare, case, asyncDepth=16)
+    assert not bad, "\n".join(bad[:10])
+    assert n == case[4]
+
+
+def test_config4_4320p_matches_c_oracle(pkg, synth, simdir):
+    """7680x4320 8-bit rc-lookahead 80 bframes 4 (BASELINE configs[3]) on a dozen frames against the C oracle"""
+    name, depth, w, h, n, skw, rkw = cases.FULL_SIZE_ORACLE
+    seq = synth.SynthSequence(w, h, depth=depth, **skw)
+    frames = [seq.frame(i) for i in range(n)]
+    kw = cases.la_kwargs(rkw)
+    want = _as_ref_layout(pkg.run_sequence(pkg.Lookahead(w, h, depth=depth, lib_path=_sim(simdir, depth), **kw), iter(frames), planes=False))
+    got = pkg.run_sequence(pkg.Lookahead(w, h, depth=depth, asyncDepth=8, **kw), iter(frames), planes=False)
+    bad = compare.compare_runs(want, got, check_planes=False)
+    assert not bad, "\n".join(bad[:10])
+
+
 @pytest.mark.parametrize("depth,w,h", [(8, 1920, 1080), (10, 3840, 2160), (8, 7680, 4320)])
 def test_full_size_properties(depth, w, h, pkg, synth, simdir):
     """BASELINE sizes: oracle spot-check of whole frames plus size-independent properties

@@ -167,3 +167,25 @@ def test_lookahead_slices_rules(pkg, synth, simdir):
         if "poolWorkers" not in extra:
             bad = compare.compare_runs(golden_io.load("base8"), got, check_planes=False)
             assert not bad, "\n".join(bad[:10])
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+def test_intrinsics_baseline_shims_are_bit_exact(depth):
+    """oracle/ref_simd.cpp (the asm-class CPU baseline): every SSE4.1 shim against the reference's C primitive on the
+    pixelharness buffer recipe, and a whole lookahead run with the shims installed against one without"""
+    if not refbind.available(depth):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    assert refbind.simd_selftest(depth, 6000) == 0
+    import _pkg
+    synth = _pkg.load_synth()
+    case = cases.get_case("fade8" if depth == 8 else "pool16_10bit")
+    try:
+        plain = cases.run_reference(refbind, synth, case)
+        assert refbind.simd_install(depth, True)
+        shim = cases.run_reference(refbind, synth, case)
+    finally:
+        refbind.simd_install(depth, False)
+    for f in shim:      # give the second reference run the key our own runs carry
+        f["searched"] = f["mvs"][:, :, 0, 0] != 0x7FFF
+    bad = compare.compare_runs(plain, shim, check_planes=True)
+    assert not bad, "\n".join(bad[:10])

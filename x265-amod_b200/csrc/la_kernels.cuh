@@ -375,6 +375,10 @@ __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const 
         qpCuTree[i] = qp_adj;
         invQ[i] = exp2fix8(qp_adj);
     }
+    /* entries the running index never reaches (qg-size 8 with an odd number of 8x8 block rows / columns): the reference
+     * leaves them as its zero-initialised allocation had them unless cuTreeFinish of an earlier tenant of the Lowres wrote
+     * them; a slot is recycled in a different order than the reference's frames, so they are put back to zero here */
+    for (int i = n + blockIdx.x * LA_AQ_THREADS + tid; i < g.ncuFull; i += LA_AQ_CTAS * LA_AQ_THREADS) qpCuTree[i] = 0;
 }
 
 /* qg-size 8: the per-lowres-block scale is the mean of its four 8x8 factors (slicetype.cpp:656-670) */
