@@ -1,0 +1,83 @@
+"""The drop-in itself (VERDICT r01 N1 / SURVEY T3): the reference's own command-line encoder built twice from
+/root/reference by integration/Makefile -- unmodified (CPU lookahead) and with integration/x265_enable_cuda.patch +
+-DENABLE_CUDA=1 (the Lookahead class forwarding to the B200 engine) -- must produce the same frame types, scene cuts,
+I/P cost ratios, QPs and the same BITSTREAM, bit for bit."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "integration", "_build")
+
+
+def _bin(kind, depth):
+    return os.path.join(BUILD, "x265-%s%d" % (kind, depth))
+
+
+def test_integration_patch_and_binaries():
+    """the patch only hooks the public entry points of Lookahead and leaves the class declaration alone; where the
+    reference sources exist the two encoders were built from them (by __graft_entry__.build) and the CUDA one is linked
+    against the product libraries"""
+    patch = open(os.path.join(ROOT, "integration", "x265_enable_cuda.patch")).read()
+    assert "a/source/encoder/slicetype.h" not in patch and "a/source/encoder/encoder.cpp" not in patch
+    for hook in ("cudaLookaheadCreate", "cudaLookaheadAddPicture", "cudaLookaheadGetDecided", "cudaLookaheadEstimatedPictureCost",
+                 "cudaLookaheadFlush", "cudaLookaheadDestroy", "cudaLookaheadFindSliceType", "option(ENABLE_CUDA"):
+        assert hook in patch, hook
+    if not os.path.isdir("/root/reference/source"):
+        pytest.skip("reference sources not on this box")
+    for depth in (8, 10):
+        assert os.path.exists(_bin("cpu", depth)) and os.path.exists(_bin("cuda", depth))
+        needed = subprocess.run(["readelf", "-d", _bin("cuda", depth)], stdout=subprocess.PIPE, text=True).stdout
+        assert "libx265la.so" in needed      # which in turn needs libx265cu.so, the CUDA engine
+        needed = subprocess.run(["readelf", "-d", _bin("cpu", depth)], stdout=subprocess.PIPE, text=True).stdout
+        assert "libx265la.so" not in needed
+
+
+def _encode(binary, y4m, out, extra, env=None):
+    csv = out + ".csv"
+    cmd = [binary, "--input", y4m, "--frame-threads", "1", "--csv", csv, "--csv-log-level", "2", "--log-level", "error",
+           "-o", out] + extra
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=e, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+    rows = []
+    with open(csv) as f:
+        head = [h.strip() for h in f.readline().split(",")]
+        keep = [head.index(k) for k in ("Encode Order", "Type", "POC", "QP", "Bits", "Scenecut", "I/P cost ratio")]
+        for line in f:
+            cells = [c.strip() for c in line.split(",")]
+            if len(cells) > max(keep) and cells[0].isdigit():
+                rows.append([cells[i] for i in keep])
+    return hashlib.md5(open(out, "rb").read()).hexdigest(), rows
+
+
+CLI_CASES = [
+    ("medium_360p", 8, 640, 360, 60, dict(cuts=(33,)), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0"]),
+    ("medium_720p_slices", 8, 1280, 720, 24, dict(cuts=(11,)), ["--preset", "medium", "--pools", "4"]),
+    ("veryfast_nopool", 8, 640, 360, 50, dict(cuts=(20,)), ["--preset", "veryfast", "--pools", "none", "--no-wpp"]),
+    ("vbv_10bit", 10, 640, 360, 50, dict(cuts=(27,)), ["--preset", "fast", "--pools", "4", "--lookahead-slices", "0", "--bitrate", "1500",
+                                                          "--vbv-bufsize", "2000", "--vbv-maxrate", "2000"]),
+    ("b8_la40_fades_10bit", 10, 640, 360, 70, dict(cuts=(), fades=[(20, 12, 0.3), (45, 10, 1.0)]),
+     ["--preset", "medium", "--pools", "16", "--lookahead-slices", "0", "--bframes", "8", "--rc-lookahead", "40", "--weightb"]),
+    ("qg8_cqp", 8, 640, 360, 40, dict(cuts=(19,)), ["--preset", "faster", "--pools", "4", "--qg-size", "8", "--aq-mode", "3", "--crf", "24"]),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [c[0] for c in CLI_CASES])
+def test_x265_cli_with_cuda_lookahead_is_bit_identical(name, synth, tmp_path):
+    name, depth, w, h, n, skw, extra = [c for c in CLI_CASES if c[0] == name][0]
+    if not (os.path.exists(_bin("cpu", depth)) and os.path.exists(_bin("cuda", depth))):
+        pytest.skip("integration/_build not in this snapshot (needs /root/reference at build time)")
+    seq = synth.SynthSequence(w, h, depth=depth, seed=5, n_rects=5, **skw)
+    y4m = str(tmp_path / "in.y4m")
+    synth.write_y4m(y4m, seq, n)
+    md5_cpu, rows_cpu = _encode(_bin("cpu", depth), y4m, str(tmp_path / "cpu.hevc"), extra)
+    md5_gpu, rows_gpu = _encode(_bin("cuda", depth), y4m, str(tmp_path / "gpu.hevc"), extra, env={"X265_CUDA_ASYNC_DEPTH": "8"})
+    assert len(rows_cpu) == n and len(rows_gpu) == n
+    for a, b in zip(rows_cpu, rows_gpu):
+        assert a == b, "csv row differs:\ncpu %s\ngpu %s" % (a, b)
+    assert md5_cpu == md5_gpu, "bitstreams differ although every csv row matches"

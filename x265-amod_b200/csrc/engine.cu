@@ -44,7 +44,7 @@ inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
-enum { LA_NUM_LANES = 16, LA_NUM_BATCHES = 48, LA_MAX_RANKS = 8, LA_CT_RING = 2048 };
+enum { LA_NUM_LANES = 16, LA_NUM_BATCHES = 48, LA_MAX_RANKS = 8, LA_CT_RING = 2048, LA_NUM_PRE = 3 };
 
 /* One asynchronous batch of search / cost jobs (x265cu_batch_begin ... x265cu_batch_end).  Everything a batch's
  * kernels read besides the frame slots is private to it, so batches never wait for each other's buffers. */
@@ -52,7 +52,7 @@ struct Batch
 {
     long long id;                       /* -1 = never used; the object serves ids id, id + LA_NUM_BATCHES, ... */
     cudaStream_t stream;                /* lane id % LA_NUM_LANES */
-    cudaEvent_t begun, searchDone, done;
+    cudaEvent_t begun[LA_NUM_PRE], searchDone, done;
     bool open;
     char* h_stage; char* d_stage;       /* pinned host / device copy of the job arrays */
     size_t stageCap, stageUsed;
@@ -75,7 +75,9 @@ struct x265cu_ctx
     SlotLayout lay;
     cudaStream_t stream;            /* main: weightp scores, cuTree, every D2H */
     cudaStream_t copyStream;        /* picture uploads, so they overlap the kernels of earlier frames */
-    cudaStream_t preStream;         /* pre-lookahead kernels K1-K3 of every uploaded frame */
+    cudaStream_t preStreams[LA_NUM_PRE];    /* pre-lookahead kernels K1-K3: consecutive frames alternate between them, so the one-warp
+                                               sequential AQ mean of a frame overlaps the streaming kernels of the next ones */
+    unsigned preSeq;
     cudaEvent_t mainMark;
     std::vector<char> slotMainTouched;          /* main-stream work read the slot's current tenant */
     cudaStream_t lanes[LA_NUM_LANES];
@@ -162,7 +164,7 @@ struct Prof
 void syncAll(x265cu_ctx* c)
 {
     cudaStreamSynchronize(c->copyStream);
-    cudaStreamSynchronize(c->preStream);
+    for (int i = 0; i < LA_NUM_PRE; i++) cudaStreamSynchronize(c->preStreams[i]);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < LA_NUM_LANES; i++) cudaStreamSynchronize(c->lanes[i]);
 }
@@ -416,8 +418,11 @@ int beginBatch(x265cu_ctx* c)
     b->stream = c->lanes[b->id % LA_NUM_LANES];
     b->stageUsed = 0; b->syncUsed = 0; b->open = true;
     /* the batch reads planes / intra costs / AQ factors of every frame uploaded so far */
-    CK(cudaEventRecord(b->begun, c->preStream));
-    CK(cudaStreamWaitEvent(b->stream, b->begun, 0));
+    for (int i = 0; i < LA_NUM_PRE; i++)
+    {
+        CK(cudaEventRecord(b->begun[i], c->preStreams[i]));
+        CK(cudaStreamWaitEvent(b->stream, b->begun[i], 0));
+    }
     c->cur = b;
     return X265CU_OK;
 }
@@ -534,7 +539,8 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
         c->counters.h2d_bytes += 2ull * g.cW * g.cH * sizeof(P);
     }
     CK(cudaEventRecord(c->slotCopied[slot], c->copyStream));
-    CK(cudaStreamWaitEvent(c->preStream, c->slotCopied[slot], 0));
+    const cudaStream_t ps = c->preStreams[c->preSeq++ % LA_NUM_PRE];
+    CK(cudaStreamWaitEvent(ps, c->slotCopied[slot], 0));
     /* K1-K3 overwrite the slot: every batch that still reads or writes its previous tenant goes first (the copy
      * above only touches the staging planes, which batches never read, so it is not held back) */
     {
@@ -544,7 +550,7 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
             Batch* w = batchOf(c, users[i]);
             if (!w) continue;
             if (w->open) { int st = endBatch(c); if (st) return st; }
-            CK(cudaStreamWaitEvent(c->preStream, w->done, 0));
+            CK(cudaStreamWaitEvent(ps, w->done, 0));
         }
         users.clear();
         std::fill(c->mvWriter.begin() + (size_t)slot * c->geom.n_mv_stores, c->mvWriter.begin() + (size_t)(slot + 1) * c->geom.n_mv_stores, -1LL);
@@ -554,16 +560,16 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     {
         /* ... and whatever the main stream (cuTree, recalc, mirrors) still reads of it */
         CK(cudaEventRecord(c->mainMark, c->stream));
-        CK(cudaStreamWaitEvent(c->preStream, c->mainMark, 0));
+        CK(cudaStreamWaitEvent(ps, c->mainMark, 0));
         c->slotMainTouched[slot] = 0;
     }
     /* stats + rowSatds00 start at zero */
-    CK(cudaMemsetAsync(c->slots[slot] + L.rowSatds00, 0, L.stats + sizeof(FrameStatsDev) - L.rowSatds00, c->preStream));
+    CK(cudaMemsetAsync(c->slots[slot] + L.rowSatds00, 0, L.stats + sizeof(FrameStatsDev) - L.rowSatds00, ps));
     P* planes = slotPtr<P>(c, slot, L.planes);
     {
-        Prof pr(c, X265CU_K_LOWRES, 1, c->preStream);
+        Prof pr(c, X265CU_K_LOWRES, 1, ps);
         const long long threads = (long long)g.tpr * (g.planeLines >> 3) * 16;
-        lowres_kernel<P><<<(unsigned)((threads + 255) / 256), 256, 0, c->preStream>>>(g, dY, planes);
+        lowres_kernel<P><<<(unsigned)((threads + 255) / 256), 256, 0, ps>>>(g, dY, planes);
     }
     FrameStatsDev* stats = slotPtr<FrameStatsDev>(c, slot, L.stats);
     int* invQ = slotInvQ(c, slot);
@@ -571,36 +577,36 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     {
         const bool twoPass = (c->cfg.aq_mode == 2 || c->cfg.aq_mode == 3) && c->cfg.aq_strength != 0;
         const bool qg8 = g.aqBlock == 8;
-        Prof pr(c, X265CU_K_AQ, 2 + 2 * twoPass + qg8, c->preStream);
+        Prof pr(c, X265CU_K_AQ, 2 + 2 * twoPass + qg8, ps);
         unsigned* energy = slotPtr<unsigned>(c, slot, L.energy);
         double* qpCuTree = slotPtr<double>(c, slot, L.qpCuTree);
         double* sums = slotPtr<double>(c, slot, L.aqSums);
         if (qg8)
-            aq_energy8_kernel<P><<<(g.aqW * g.aqH + 31) / 32, 256, 0, c->preStream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
+            aq_energy8_kernel<P><<<(g.aqW * g.aqH + 31) / 32, 256, 0, ps>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
         else
-            aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, c->preStream>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
+            aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, ps>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
         if (twoPass)
         {
-            aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, c->preStream>>>(g, energy, qpCuTree);
-            aq_mean_kernel<<<1, 32, 0, c->preStream>>>(g, qpCuTree, sums);
+            aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, ps>>>(g, energy, qpCuTree);
+            aq_mean_kernel<<<1, 32, 0, ps>>>(g, qpCuTree, sums);
         }
-        aq_finish_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, c->preStream>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
+        aq_finish_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, ps>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
                                                                       sums, slotPtr<double>(c, slot, L.qpAq), qpCuTree,
                                                                       slotPtr<int>(c, slot, L.invQ), stats);
         if (qg8)
-            aq_invq8x8_kernel<<<(g.ncu + 255) / 256, 256, 0, c->preStream>>>(g, slotPtr<int>(c, slot, L.invQ), invQ);
+            aq_invq8x8_kernel<<<(g.ncu + 255) / 256, 256, 0, ps>>>(g, slotPtr<int>(c, slot, L.invQ), invQ);
     }
     {
-        Prof pr(c, X265CU_K_INTRA, 1, c->preStream);
-        intra_kernel<P><<<(g.ncu + 15) / 16, 128, 0, c->preStream>>>(g, planes, c->cfg.need_aq ? invQ : NULL,
+        Prof pr(c, X265CU_K_INTRA, 1, ps);
+        intra_kernel<P><<<(g.ncu + 15) / 16, 128, 0, ps>>>(g, planes, c->cfg.need_aq ? invQ : NULL,
                                                                   slotPtr<int>(c, slot, L.intraCost), slotPtr<unsigned char>(c, slot, L.intraMode),
                                                                   slotPtr<unsigned short>(c, slot, L.lowresCosts00),
                                                                   slotPtr<int>(c, slot, L.rowSatds00), stats);
     }
-    publish_kernel<<<1, 32, 0, c->preStream>>>((const unsigned*)stats, (unsigned*)(c->d_slotStats + slot), (int)(sizeof(FrameStatsDev) / 4));
+    publish_kernel<<<1, 32, 0, ps>>>((const unsigned*)stats, (unsigned*)(c->d_slotStats + slot), (int)(sizeof(FrameStatsDev) / 4));
     c->counters.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->slotConsumed[slot], c->preStream));
+    CK(cudaEventRecord(c->slotConsumed[slot], ps));
     return X265CU_OK;
 }
 
@@ -992,12 +998,12 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
-    c->stream = c->copyStream = c->preStream = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
+    c->stream = c->copyStream = NULL; c->preSeq = 0; for (int i = 0; i < LA_NUM_PRE; i++) c->preStreams[i] = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
     for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
     for (int i = 0; i < LA_NUM_BATCHES; i++)
     {
         Batch& b = c->batches[i];
-        b.id = -1; b.stream = NULL; b.begun = b.searchDone = b.done = NULL; b.open = false;
+        b.id = -1; b.stream = NULL; b.searchDone = b.done = NULL; b.open = false; for (int k = 0; k < LA_NUM_PRE; k++) b.begun[k] = NULL;
         b.h_stage = b.d_stage = NULL; b.stageCap = b.stageUsed = 0; b.d_sync = NULL; b.syncCap = b.syncUsed = 0;
         for (int r = 0; r < LA_MAX_RANKS; r++) { b.xbuf[r] = NULL; b.xcap[r] = 0; }
     }
@@ -1068,14 +1074,17 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
     if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return X265CU_ERR_CUDA; }
-    if (cudaStreamCreateWithPriority(&c->preStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    for (int i = 0; i < LA_NUM_PRE; i++)
+        if (cudaStreamCreateWithPriority(&c->preStreams[i], cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
     if (cudaEventCreateWithFlags(&c->mainMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < LA_NUM_LANES; i++)
         if (cudaStreamCreateWithPriority(&c->lanes[i], cudaStreamNonBlocking, prLeast) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < LA_NUM_BATCHES; i++)
     {
         Batch& b = c->batches[i];
-        if (cudaEventCreateWithFlags(&b.begun, cudaEventDisableTiming) != cudaSuccess ||
+        for (int k = 0; k < LA_NUM_PRE; k++)
+            if (cudaEventCreateWithFlags(&b.begun[k], cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
+        if (
             cudaEventCreateWithFlags(&b.searchDone, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
     }
@@ -1158,7 +1167,7 @@ void x265cu_destroy(x265cu_ctx* c)
         cudaFree(b.d_stage); cudaFree(b.d_sync);
         for (int r = 0; r < LA_MAX_RANKS; r++) cudaFree(b.xbuf[r]);
         if (b.h_stage) cudaFreeHost(b.h_stage);
-        if (b.begun) cudaEventDestroy(b.begun);
+        for (int k = 0; k < LA_NUM_PRE; k++) if (b.begun[k]) cudaEventDestroy(b.begun[k]);
         if (b.searchDone) cudaEventDestroy(b.searchDone);
         if (b.done) cudaEventDestroy(b.done);
     }
@@ -1171,7 +1180,7 @@ void x265cu_destroy(x265cu_ctx* c)
     if (c->tm1) cudaEventDestroy(c->tm1);
     if (c->profBase) cudaEventDestroy(c->profBase);
     for (int i = 0; i < LA_NUM_LANES; i++) if (c->lanes[i]) cudaStreamDestroy(c->lanes[i]);
-    if (c->preStream) cudaStreamDestroy(c->preStream);
+    for (int i = 0; i < LA_NUM_PRE; i++) if (c->preStreams[i]) cudaStreamDestroy(c->preStreams[i]);
     if (c->mainMark) cudaEventDestroy(c->mainMark);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1212,7 +1221,7 @@ int x265cu_sync(x265cu_ctx* c)
     flushCutree(c);
     int st = endBatch(c);
     if (st) return st;
-    CK(cudaStreamSynchronize(c->copyStream)); CK(cudaStreamSynchronize(c->preStream)); CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copyStream)); for (int i = 0; i < LA_NUM_PRE; i++) CK(cudaStreamSynchronize(c->preStreams[i])); CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < LA_NUM_LANES; i++) CK(cudaStreamSynchronize(c->lanes[i]));
     return X265CU_OK;
 }
@@ -1275,7 +1284,7 @@ int x265cu_timer_stop(x265cu_ctx* c, double* ms)
     int st = mainJoinBatches(c);
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream));
-    CK(cudaStreamSynchronize(c->preStream));
+    for (int i = 0; i < LA_NUM_PRE; i++) CK(cudaStreamSynchronize(c->preStreams[i]));
     CK(cudaEventRecord(c->tm1, c->stream));
     CK(cudaEventSynchronize(c->tm1));
     float f = 0;

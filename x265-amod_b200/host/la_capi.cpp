@@ -47,6 +47,7 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     p.pinHost = q->pinHost; p.asyncDepth = q->asyncDepth;
     if (q->pendingMax > 0) p.pendingMax = q->pendingMax;
     p.shardCount = q->shardCount; p.batchMin = q->batchMin; p.gopLookahead = q->gopLookahead; p.radl = q->radl;
+    p.csvLogLevel = q->csvLogLevel; p.numRowsPerSlice = q->numRowsPerSlice;
     if (p.radl && p.bOpenGOP) p.radl = 0;      /* encoder.cpp:4361-4365 */
     if (p.radl > p.bframes) p.radl = p.bframes;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
@@ -106,6 +107,15 @@ int64_t x265la_estimated_picture_cost(void* la, void* frame, void* ref0, void* r
     ((Lookahead*)la)->getEstimatedPictureCost((Frame*)frame, (Frame*)ref0, (Frame*)ref1);
     return ((Frame*)frame)->m_lowres.satdCost;
 }
+
+int64_t x265la_estimated_picture_cost_dist(void* la, void* frame, int32_t d0, int32_t d1)
+{
+    ((Lookahead*)la)->getEstimatedPictureCost((Frame*)frame, d0, d1);
+    return ((Frame*)frame)->m_lowres.satdCost;
+}
+
+int x265la_find_slice_type(void* la, int32_t poc) { return ((Lookahead*)la)->findSliceType(poc); }
+double x265la_frame_ip_cost_ratio(void* /*la*/, void* frame) { return ((Frame*)frame)->m_lowres.ipCostRatio; }
 
 void x265la_release(void* la, void* frame) { ((Lookahead*)la)->releaseFrame((Frame*)frame); }
 

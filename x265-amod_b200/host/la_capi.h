@@ -29,7 +29,10 @@ typedef struct
     int32_t batchMin;                /* LookaheadParam::batchMin; 0 = asyncDepth / 2 */
     int32_t gopLookahead;            /* x265_param::gopLookahead */
     int32_t radl;                    /* x265_param::radl */
-    int32_t reserved[2];
+    int32_t csvLogLevel;             /* x265_param::csvLogLevel: >= 2 makes scenecut() record Lowres::ipCostRatio (slicetype.cpp:2998-3003) */
+    int32_t numRowsPerSlice;         /* > 0: Lookahead::m_numRowsPerSlice as the reference's constructor derived it (it rewrites
+                                        x265_param::lookaheadSlices afterwards, so deriving it twice is not idempotent); 0 = derive
+                                        from lookaheadSlices */
 } x265la_param;
 
 typedef struct
@@ -54,6 +57,11 @@ void  x265la_flush(void* la);
 int   x265la_get_decided(void* la, x265la_frame_info* out);
 /* Lookahead::getEstimatedPictureCost with explicit references (handles, may be NULL) */
 int64_t x265la_estimated_picture_cost(void* la, void* frame, void* ref0, void* ref1);
+/* the same with the POC distances to the list-0 / list-1 reference (0 = none) instead of their handles, for a caller
+ * that has already released the reference frames */
+int64_t x265la_estimated_picture_cost_dist(void* la, void* frame, int32_t d0, int32_t d1);
+int     x265la_find_slice_type(void* la, int32_t poc);      /* Lookahead::findSliceType */
+double  x265la_frame_ip_cost_ratio(void* la, void* frame);  /* Lowres::ipCostRatio */
 /* the VBV half of getEstimatedPictureCost (slicetype.cpp:1387-1436) for the estimate the last
  * x265la_estimated_picture_cost of this frame read: x265la_vbv_rows() row sums, ncu scaled costs (NULL = skip); 0 = ok */
 int   x265la_vbv_rows(void* la);

@@ -126,7 +126,7 @@ bool Lookahead::create()
         if (slices && p.sourceHeight < 720) slices = 0;
         if (slices > 1)
         {
-            int rows = std::min(std::max(m_8x8Height / slices, 10), m_8x8Height);
+            int rows = p.numRowsPerSlice > 0 ? p.numRowsPerSlice : std::min(std::max(m_8x8Height / slices, 10), m_8x8Height);
             if (m_8x8Height / rows > 1) rowsPerSlice = rows;
         }
     }
@@ -509,8 +509,10 @@ void Lookahead::enqueueCosts(int l0kind, bool conditional)
             const int cond = (conditional && b->haveSearch[l0kind][d0] == 1) ? (l0kind + 1) * nb + d0 : -1;
             addCost(b, &p0f->m_lowres, NULL, d0, 0, l0kind, -1, cond);
             const int maxD1 = m_bBatchFrameCosts ? B : B + 1 - d0;
-            for (int d1 = 1; d1 <= maxD1; d1++)
+            for (int d1 = 1; d1 <= B + 1; d1++)
             {
+                /* (d0, d0): the estimate a search batch makes while it searches both lists at distance d0 (:2686-2692) */
+                if (d1 > maxD1 && !(m_bBatchMotionSearch && d1 == d0)) continue;
                 if (!b->haveSearch[l1kind][d1]) continue;
                 Frame* p1f = frameOfPoc(bf->m_poc + d1);
                 if (!p1f) continue;
@@ -550,7 +552,9 @@ void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
             if (!rf) break;
             Lowres* r = &rf->m_lowres;
             addSearch(n, r, firstKind, d);                  /* L0(n,d) */
-            if (B > 0 && d <= B)
+            /* the reference's search batches pair every list-0 search with the list-1 search at the SAME distance
+             * (p1 = b + i, slicetype.cpp:2686-2690), i.e. up to bframes + 1; on demand only distances <= bframes occur */
+            if (B > 0 && (d <= B || m_bBatchMotionSearch))
                 addSearch(r, n, 2 + s3, d);                 /* L1(n-d,d), reference = n */
         }
     }
@@ -1259,6 +1263,12 @@ bool Lookahead::scenecut(Lowres** frames, int p0, int p1, bool bRealScenecut, in
         if (!fluctuate && !noScenecuts)
             m_isSceneTransition = false;
     }
+    if (m_param.csvLogLevel >= 2)      /* :2998-3003 */
+    {
+        int64_t icost = frames[p1]->costEst[0][0];
+        int64_t pcost = frames[p1]->costEst[p1 - p0][0];
+        frames[p1]->ipCostRatio = (double)icost / pcost;
+    }
     if (!frames[p1]->bScenecut)
         return false;
     return scenecutInternal(frames, p0, p1, bRealScenecut);
@@ -1547,54 +1557,52 @@ void Lookahead::vbvLookahead(Lowres** frames, int numFrames, int keyframe)
 }
 
 /* slicetype.cpp:1327-1386.  The reference derives p0 / p1 from the slice's reference lists; the caller passes the
- * frames themselves (NULL = none). */
+ * frames themselves (NULL = none) or their POC distances. */
 void Lookahead::getEstimatedPictureCost(Frame* cur, Frame* ref0, Frame* ref1)
 {
-    Lowres* frames[2 * (BFRAME_MAX + 2) + 2];
-    memset(frames, 0, sizeof(frames));
-    int p0 = 0, p1, b;
-    int type = cur->m_lowres.sliceType;
+    getEstimatedPictureCost(cur, ref0 ? cur->m_poc - ref0->m_poc : 0, ref1 ? ref1->m_poc - cur->m_poc : 0);
+}
+
+void Lookahead::getEstimatedPictureCost(Frame* cur, int dist0, int dist1)
+{
+    int d0, d1;
+    const int type = cur->m_lowres.sliceType;
     if (isTypeI(type))
-    {
-        frames[0] = &cur->m_lowres;
-        b = p1 = 0;
-    }
+        d0 = d1 = 0;
     else if (type == TYPE_P)
     {
-        if (!ref0) return;
-        b = p1 = cur->m_poc - ref0->m_poc;
-        frames[0] = &ref0->m_lowres;
-        frames[b] = &cur->m_lowres;
+        if (dist0 <= 0) return;
+        d0 = dist0; d1 = 0;
     }
     else
     {
-        if (!ref1) return;
-        if (ref0)
-        {
-            b = cur->m_poc - ref0->m_poc;
-            p1 = b + ref1->m_poc - cur->m_poc;
-            frames[0] = &ref0->m_lowres;
-            frames[b] = &cur->m_lowres;
-            frames[p1] = &ref1->m_lowres;
-        }
+        if (dist1 <= 0) return;
+        /* a B slice without a list-0 reference (a RADL leading picture) is estimated against itself, :1360-1366 */
+        d0 = dist0 > 0 ? dist0 : 0;
+        d1 = dist1;
+    }
+    if (d0 >= m_geom.nb || d1 >= m_geom.nb) { fail("getEstimatedPictureCost: references outside the (bframes+2) window"); return; }
+    const double t0 = nowSec();
+    Lowres& l = cur->m_lowres;
+    l.rcD0 = d0; l.rcD1 = d1;
+    if (m_param.rc.cuTree)
+    {
+        /* frameCostRecalculate (:3802-3879) only reads frames[b] */
+        if (l.sliceType == TYPE_B)
+            l.satdCost = l.costEstAq[d0][d1];
         else
         {
-            /* a B slice without a list-0 reference (a RADL leading picture): estimated against itself, :1360-1366 */
-            p0 = b = 0;
-            p1 = ref1->m_poc - cur->m_poc;
-            frames[0] = &cur->m_lowres;
-            frames[p1] = &ref1->m_lowres;
+            int64_t score = 0;
+            const int cs = l.costStore[d0][d1];
+            if (cs < 0) { fail("getEstimatedPictureCost on an estimate that was never computed"); return; }
+            check(x265cu_cost_recalc(m_ctx, l.slot, cs, 1, &score, NULL), "x265cu_cost_recalc");
+            l.satdCost = score;
         }
     }
-    if (b - p0 < 0 || b - p0 >= m_geom.nb || p1 - b < 0 || p1 - b >= m_geom.nb) { fail("getEstimatedPictureCost: references outside the (bframes+2) window"); return; }
-    const double t0 = nowSec();
-    cur->m_lowres.rcD0 = b - p0; cur->m_lowres.rcD1 = p1 - b;
-    if (m_param.rc.cuTree)
-        cur->m_lowres.satdCost = frameCostRecalculate(frames, p0, p1, b);
     else if (m_param.rc.aqMode)
-        cur->m_lowres.satdCost = cur->m_lowres.costEstAq[b - p0][p1 - b];
+        l.satdCost = l.costEstAq[d0][d1];
     else
-        cur->m_lowres.satdCost = cur->m_lowres.costEst[b - p0][p1 - b];
+        l.satdCost = l.costEst[d0][d1];
     m_timers[8] += nowSec() - t0;
 }
 

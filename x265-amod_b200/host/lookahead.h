@@ -70,6 +70,8 @@ struct LookaheadParam
     int pendingMax;      /* streaming + weightp: frames that may wait for their pixel sums before addPicture blocks on them */
     int asyncDepth;      /* extra frames of input delay before a decision is taken (0 = the reference's trigger).  The
                             decision analyses the same frames either way; the GPU gets that many frames of slack */
+    int csvLogLevel;     /* x265_param::csvLogLevel */
+    int numRowsPerSlice; /* > 0: the reference's m_numRowsPerSlice, taken as is (see la_capi.h) */
     int pinHost;         /* page-lock the picture buffers handed to addPicture the first time each is seen (they must then
                             stay allocated until destroy(); meant for an encoder's recycled PicYuv buffers) */
 };
@@ -154,6 +156,7 @@ public:
     /* RateControl's entry point (slicetype.cpp:1327-1439).  The reference derives p0/p1 from the
      * slice's reference lists; the caller passes the POC distances instead (0 = none). */
     void    getEstimatedPictureCost(Frame* curFrame, Frame* ref0, Frame* ref1);
+    void    getEstimatedPictureCost(Frame* curFrame, int d0, int d1);   /* POC distances to the references, 0 = none */
     /* its VBV half (slicetype.cpp:1387-1436), see lookahead.cpp; arrays of vbvRows() / geometry().ncu entries */
     bool    getVbvRowCosts(Frame* curFrame, int pirStartCol, int pirEndCol, uint32_t* satdForVbv, uint32_t* intraSatdForVbv,
                            uint16_t* lowresCostForRc, int32_t* intraCostScaled);
