@@ -225,19 +225,25 @@ class Stream:
         self.pocs = {}
         self.fed = 0
         if self.mirror:
-            ncu, nf, bpp = g.ncu, g.ncu_full, 2 if wl["depth"] > 8 else 1
-            self.b = dict(qpAq=np.zeros(nf, np.float64), qpCt=np.zeros(nf, np.float64), invQ=np.zeros(nf, np.int32),
-                          intra=np.zeros(ncu, np.int32), lc=np.zeros(ncu, np.uint16), rs=np.zeros(g.bh, np.int32),
-                          mv0=np.zeros((ncu, 2), np.int32), mv1=np.zeros((ncu, 2), np.int32),
-                          planes=np.zeros(4 * g.stride * g.plane_lines, np.uint16 if bpp == 2 else np.uint8))
-            b = self.b
-            self.fo = self.pkg.FrameOut()
-            self.fo.qp_aq_offset = b["qpAq"].ctypes.data; self.fo.qp_cutree_offset = b["qpCt"].ctypes.data
-            self.fo.inv_qscale_factor = b["invQ"].ctypes.data; self.fo.intra_cost = b["intra"].ctypes.data
-            self.fo_planes = self.pkg.FrameOut()
-            self.fo_planes.planes = b["planes"].ctypes.data
-            self.bytes_small = b["qpAq"].nbytes + b["qpCt"].nbytes + b["invQ"].nbytes + b["intra"].nbytes
+            # two sets of page-locked destination buffers: the mirror of frame i lands while frame i + 1 is decided
+            ncu, nf, bpp, nb = g.ncu, g.ncu_full, 2 if wl["depth"] > 8 else 1, g.nb
+            self.sets, self.tickets, self.nmir = [], [None, None], 0
+            for _ in range(2):
+                b = dict(qpAq=np.zeros(nf, np.float64), qpCt=np.zeros(nf, np.float64), invQ=np.zeros(nf, np.int32),
+                         intra=np.zeros(ncu, np.int32), lc=np.zeros(ncu, np.uint16), rs=np.zeros(g.bh, np.int32),
+                         mv=np.zeros((2, nb, ncu, 2), np.int32),
+                         planes=np.zeros(4 * g.stride * g.plane_lines, np.uint16 if bpp == 2 else np.uint8))
+                for a in b.values():
+                    self.la.lib.x265la_pin(self.la.h, a.ctypes.data, a.nbytes)
+                m = self.pkg.Mirror()
+                m.intraCost = b["intra"].ctypes.data; m.qpAqOffset = b["qpAq"].ctypes.data; m.qpCuTreeOffset = b["qpCt"].ctypes.data
+                m.invQscaleFactor = b["invQ"].ctypes.data; m.lowresCosts = b["lc"].ctypes.data; m.rowSatds = b["rs"].ctypes.data
+                for l in range(2):
+                    for d in range(1, nb):
+                        m.lowresMvs[l][d] = b["mv"][l, d].ctypes.data
+                self.sets.append((b, m))
         self.weightp = bool(self.la.param.bEnableWeightedPred)
+        self.pub = (C.c_uint32 * 2)()
 
     def feed(self):
         if self.fed >= len(self.pics):
@@ -258,32 +264,40 @@ class Stream:
             old = set(t for _, t in self.tracker.refs)
             r0, r1 = self.tracker.push(info.poc, info.sliceType, info.handle)
             if self.mirror:
-                # what Encoder::encode / RateControl / the frame encoder / weightPrediction read of a decided frame
-                # (SURVEY 8b "output contract"): the same calls the ENABLE_CUDA Lookahead shim makes
-                b = self.b
-                la.estimated_picture_cost(info.handle, r0, r1)
-                la.lib.x265la_frame_fetch(la.h, info.handle, C.byref(self.fo))
-                self.d2h += self.bytes_small
+                # what Encoder::encode / RateControl / the frame encoder / search / weightPrediction read of a decided frame
+                # (SURVEY 8b "output contract"): the same requests the ENABLE_CUDA Lookahead shim makes (integration/)
+                k = self.nmir & 1
+                b, m = self.sets[k]
+                if self.tickets[k] is not None:
+                    la.lib.x265la_mirror_wait(la.h, self.tickets[k])
                 d0 = info.poc - self.pocs[r0] if r0 else 0
                 d1 = self.pocs[r1] - info.poc if r1 else 0
-                la.lib.x265la_frame_costs(la.h, info.handle, d0, d1, b["lc"].ctypes.data, b["rs"].ctypes.data)
-                self.d2h += b["lc"].nbytes + b["rs"].nbytes
-                if r0:
-                    la.lib.x265la_frame_mvs(la.h, info.handle, 0, d0, b["mv0"].ctypes.data, None)
-                    self.d2h += b["mv0"].nbytes
-                if r1:
-                    la.lib.x265la_frame_mvs(la.h, info.handle, 1, d1, b["mv1"].ctypes.data, None)
-                    self.d2h += b["mv1"].nbytes
-                if self.weightp and info.sliceType != self.pkg.TYPE_B and info.sliceType != self.pkg.TYPE_BREF:
-                    la.lib.x265la_frame_fetch(la.h, info.handle, C.byref(self.fo_planes))
-                    self.d2h += b["planes"].nbytes
+                la.lib.x265la_estimated_picture_cost_dist(la.h, info.handle, d0, d1)
+                m.d0, m.d1 = d0, d1
+                isb = info.sliceType in (self.pkg.TYPE_B, self.pkg.TYPE_BREF)
+                m.planes = b["planes"].ctypes.data if (self.weightp and not isb) else None
+                t = C.c_int64(0)
+                if la.lib.x265la_frame_mirror_async(la.h, info.handle, C.byref(m), self.pub, C.byref(t)) != 0:
+                    raise RuntimeError("mirror failed: %s" % la.lib.x265la_last_error(la.h).decode())
+                self.tickets[k] = t.value
+                self.nmir += 1
             live = set(t for _, t in self.tracker.refs)
             for h in old - live:
                 la.release(h)
             if info.handle not in live:
                 la.release(info.handle)
 
+    def finish(self):
+        if self.mirror:
+            for t in self.tickets:
+                if t is not None:
+                    self.la.lib.x265la_mirror_wait(self.la.h, t)
+
     def close(self):
+        if self.mirror:
+            for b, _ in self.sets:
+                for a in b.values():
+                    self.la.lib.x265la_unpin(self.la.h, a.ctypes.data)
         self.la.close()
         self.la = None
 
@@ -318,6 +332,7 @@ def run_step(eng, streams, dist=None, shard=None, profile=True):
     for s in streams:
         s.la.flush()
         s.drain()
+        s.finish()
     ms = 0.0
     for c in ctxs:
         m = C.c_double(0)
@@ -343,7 +358,7 @@ def run_step(eng, streams, dist=None, shard=None, profile=True):
         prof["host"] = host_t
         delta = dict(launches=k1.kernel_launches - k0.kernel_launches, h2d=k1.h2d_bytes - k0.h2d_bytes,
                      d2h=k1.d2h_bytes - k0.d2h_bytes, search_jobs=k1.search_jobs - k0.search_jobs,
-                     cost_jobs=k1.cost_jobs - k0.cost_jobs, d2h_mirror=s.d2h)
+                     cost_jobs=k1.cost_jobs - k0.cost_jobs)
         assert len(s.types) == len(s.pics), (len(s.types), len(s.pics))
         out.append((list(s.types), delta, prof, dict(s.geom)))
         s.close()
@@ -643,9 +658,10 @@ def main():
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * res["bytes_in"] // (1 << 20))},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(res["e2e_delta"]["h2d"]), "d2h_bytes_per_step": int(res["e2e_delta"]["d2h"]),
-                    "d2h": "per decided frame: getEstimatedPictureCost, qpAqOffset, qpCuTreeOffset, invQscaleFactor, intraCost, the coded "
-                           "estimate's lowresCosts + rowSatds, lowresMvs of the coded references; the 4 lowres planes of every non-B "
-                           "frame (weightPrediction.cpp:354-365)",
+                    "d2h": "per decided frame, one asynchronous mirror request into page-locked buffers: getEstimatedPictureCost, qpAqOffset, "
+                           "qpCuTreeOffset, invQscaleFactor, intraCost, the coded estimate's lowresCosts + rowSatds, EVERY published "
+                           "lowresMvs list (search.cpp:1968-1988), the 4 lowres planes of every non-B frame (weightPrediction.cpp:"
+                           "354-365)",
                     "host_memory": "pinned" if res["pinned"] else "pageable (page-locking was refused)",
                     "host_ms_last_step": {k: round(1000.0 * v, 2) for k, v in res["e2e_prof"]["host"].items()}},
             "gpu_launches": int(sum(d["launches"] for d in deltas)),

@@ -232,6 +232,39 @@ int  x265cu_fetch_mvs(x265cu_ctx* ctx, int32_t slot, int32_t store, int32_t* mv_
 int  x265cu_fetch_costs(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, uint16_t* lowres_costs /* ncu */,
                         int32_t* row_satds /* bh */);
 
+/* ---- the host mirror of a decided frame in ONE asynchronous request: everything the main encoder reads of the frame's
+ * Lowres (SURVEY 8b "output contract") goes to the caller's buffers on a dedicated copy stream, behind the work that
+ * produces it (the frame's pre-lookahead, the batches that wrote the stores, the cuTree passes enqueued so far).  The call
+ * returns at once; x265cu_mirror_wait blocks until that request has landed.  Destinations should be page-locked
+ * (x265cu_pin_host) -- pageable ones make the enqueue itself wait for the copies.  At most X265CU_MIRROR_RING requests are in
+ * flight; an older one is waited for when the ring wraps. */
+#define X265CU_MIRROR_MAX_MV 36
+#define X265CU_MIRROR_RING   4
+typedef struct
+{
+    int32_t*  intra_cost;        /* ncu, or NULL */
+    double*   qp_aq_offset;      /* ncu_full */
+    double*   qp_cutree_offset;  /* ncu_full */
+    int32_t*  inv_qscale_factor; /* ncu_full */
+    void*     planes;            /* 4 * stride * plane_lines samples (de-tiled, Lowres::buffer[0]) */
+    int32_t   n_mv;              /* MV stores to mirror, <= X265CU_MIRROR_MAX_MV */
+    int32_t   mv_store[X265CU_MIRROR_MAX_MV];
+    int32_t*  mv_dst[X265CU_MIRROR_MAX_MV];      /* ncu (x, y) pairs each: Lowres::lowresMvs[list][dist] */
+    int32_t   cost_store;        /* cost store to mirror, -1 = none, 0 = the intra estimate */
+    uint16_t* lowres_costs;      /* ncu */
+    int32_t*  row_satds;         /* bh */
+} x265cu_mirror_request;
+int  x265cu_mirror_enqueue(x265cu_ctx* ctx, int32_t slot, const x265cu_mirror_request* req, int64_t* ticket);
+int  x265cu_mirror_wait(x265cu_ctx* ctx, int64_t ticket);
+
+/* frameCostRecalculate (slicetype.cpp:3802-3879) ahead of time: enqueued when the frame's qp offsets are final (the end of the
+ * decision that outputs it), collected by x265cu_cost_recalc_get when RateControl asks -- by then it has long finished, so
+ * getEstimatedPictureCost does not stall behind the cuTree work of later decisions.  The recalculated row sums stay in a
+ * per-slot scratch until _get, which moves them into the cost store's rowSatds (where the reference's call leaves them). */
+int  x265cu_cost_recalc_enqueue(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, int32_t use_cutree_offsets);
+/* synchronises with that one request; returns X265CU_ERR_BAD_ARG when nothing was enqueued for (slot, cost_store) */
+int  x265cu_cost_recalc_get(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, int64_t* score, int32_t* row_satds);
+
 /* wait for everything enqueued on this context */
 int  x265cu_sync(x265cu_ctx* ctx);
 

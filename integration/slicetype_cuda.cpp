@@ -52,9 +52,10 @@ struct CudaState
     std::map<void*, Frame*> frameOf;        /* library frame handle -> encoder Frame */
     std::map<Frame*, void*> handleOf;
     std::vector<void*> unreleased;          /* decided frames whose slot the library still holds for us */
-    std::vector<int32_t> mvTmp;
+    std::map<Frame*, int64_t> mirrorTicket; /* asynchronous mirror of the frame's Lowres still in flight */
+    std::vector<void*> pinned;              /* page-locked Lowres arrays (once per Frame; frames are recycled by the DPB) */
+    std::map<Frame*, bool> pinnedFrame;
     bool weightPlanesP, weightPlanesB;
-    int64_t d2hBytes;
 };
 
 Lock g_stateLock;
@@ -71,6 +72,38 @@ int envInt(const char* name, int dflt)
 {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+void pin(CudaState* st, void* p, size_t bytes)
+{
+    if (p && x265la_pin(st->la, p, bytes) == 0) st->pinned.push_back(p);
+}
+
+/* page-lock the arrays of f's Lowres the mirror writes, so that the copies are truly asynchronous */
+void pinLowres(CudaState* st, Frame* f, int nb)
+{
+    if (st->pinnedFrame.count(f)) return;
+    st->pinnedFrame[f] = true;
+    Lowres& l = f->m_lowres;
+    const size_t ncu = st->geom.ncu, nfull = st->geom.ncu_full;
+    pin(st, l.buffer[0], (size_t)4 * st->geom.stride * st->geom.plane_lines * sizeof(pixel));
+    pin(st, l.intraCost, ncu * sizeof(int32_t));
+    if (l.qpAqOffset && l.invQscaleFactor)
+    {
+        pin(st, l.qpAqOffset, nfull * sizeof(double)); pin(st, l.qpCuTreeOffset, nfull * sizeof(double));
+        pin(st, l.invQscaleFactor, nfull * sizeof(int));
+    }
+    for (int list = 0; list < 2; list++)
+        for (int d = 1; d < nb; d++)
+            pin(st, l.lowresMvs[list][d], ncu * sizeof(MV));
+}
+
+void waitMirror(CudaState* st, Frame* f)
+{
+    std::map<Frame*, int64_t>::iterator it = st->mirrorTicket.find(f);
+    if (it == st->mirrorTicket.end()) return;
+    x265la_mirror_wait(st->la, it->second);
+    st->mirrorTicket.erase(it);
 }
 
 void releaseHandle(CudaState* st, void* h)
@@ -140,11 +173,9 @@ bool cudaLookaheadCreate(Lookahead& self)
     }
     CudaState* st = new CudaState;
     st->la = la;
-    st->d2hBytes = 0;
     x265la_get_geometry(la, &st->geom);
     st->weightPlanesP = !!p->bEnableWeightedPred;
     st->weightPlanesB = !!p->bEnableWeightedBiPred;
-    st->mvTmp.resize((size_t)st->geom.ncu * 2);
     {
         ScopedLock lock(g_stateLock);
         g_state[&self] = st;
@@ -163,6 +194,10 @@ void cudaLookaheadDestroy(Lookahead& self)
         if (it != g_state.end()) { st = it->second; g_state.erase(it); }
     }
     if (!st) return;
+    for (std::map<Frame*, int64_t>::iterator it = st->mirrorTicket.begin(); it != st->mirrorTicket.end(); ++it)
+        x265la_mirror_wait(st->la, it->second);
+    for (size_t i = 0; i < st->pinned.size(); i++)
+        x265la_unpin(st->la, st->pinned[i]);
     x265la_close(st->la);
     delete st;
 }
@@ -275,31 +310,35 @@ Frame* cudaLookaheadGetDecided(Lookahead& self)
         for (int i = 0; i <= X265_LOOKAHEAD_MAX; i++) l.plannedType[i] = pt[i];
         l.indB = indB;
     }
-    /* per-block arrays: what frameencoder.cpp:1456,1559-1560, analysis.cpp:3681 and ratecontrol.cpp read */
-    x265cu_frame_out fo;
-    memset(&fo, 0, sizeof(fo));
-    fo.intra_cost = l.intraCost;
+    /* per-block arrays (frameencoder.cpp:1456,1559-1560, analysis.cpp:3681, ratecontrol.cpp), every lowres MV list the
+     * lookahead published with the sentinel for the rest (search.cpp:1975-1977), and with weightp / weightb the four
+     * lowres planes (weightPrediction.cpp:60-88,354-365): one asynchronous request straight into the Lowres arrays */
+    pinLowres(st, f, nb);
+    x265la_mirror m;
+    memset(&m, 0, sizeof(m));
+    m.intraCost = l.intraCost;
     if (l.qpAqOffset && l.invQscaleFactor)
     {
-        fo.qp_aq_offset = l.qpAqOffset; fo.qp_cutree_offset = l.qpCuTreeOffset; fo.inv_qscale_factor = l.invQscaleFactor;
+        m.qpAqOffset = l.qpAqOffset; m.qpCuTreeOffset = l.qpCuTreeOffset; m.invQscaleFactor = l.invQscaleFactor;
     }
     const bool isB = IS_X265_TYPE_B(l.sliceType);
     if ((st->weightPlanesP && !isB) || st->weightPlanesB)
-        fo.planes = l.buffer[0];            /* the 4 contiguous planes incl. margins, exactly Lowres::buffer[0..3] */
-    if (x265la_frame_fetch(st->la, info.handle, &fo) != 0)
+        m.planes = l.buffer[0];             /* the 4 contiguous planes incl. margins, exactly Lowres::buffer[0..3] */
+    for (int list = 0; list < 2; list++)
+        for (int d = 1; d < nb && d < 18; d++)
+            m.lowresMvs[list][d] = (int32_t*)l.lowresMvs[list][d];      /* MV = { int32 x, y } (common/mv.h:38-47) */
+    m.d0 = -1;
+    uint32_t published[2] = { 0, 0 };
+    int64_t ticket = -1;
+    if (x265la_frame_mirror_async(st->la, info.handle, &m, published, &ticket) != 0)
         x265_log(p, X265_LOG_ERROR, "ENABLE_CUDA lookahead: mirror failed: %s\n", x265la_last_error(st->la));
-    /* lowres MVs: every list the lookahead published, the sentinel for the rest (search.cpp:1975-1977) */
+    else
+        st->mirrorTicket[f] = ticket;
     for (int list = 0; list < 2; list++)
         for (int d = 0; d < nb; d++)
-        {
-            if (d && x265la_frame_mvs(st->la, info.handle, list, d, &st->mvTmp[0], NULL) == 1)
-            {
-                MV* dst = l.lowresMvs[list][d];
-                for (int i = 0; i < ncu; i++) { dst[i].x = st->mvTmp[2 * i]; dst[i].y = st->mvTmp[2 * i + 1]; }
-            }
-            else
+            if (!d || !(published[list] & (1u << d)))
                 l.lowresMvs[list][d][0].x = 0x7FFF;
-        }
+    (void)ncu;
     st->unreleased.push_back(info.handle);
     self.m_inputLock.acquire();
     self.m_inputQueue.remove(*f);
@@ -307,6 +346,7 @@ Frame* cudaLookaheadGetDecided(Lookahead& self)
     self.m_inputCount--;
     if (p->rc.rateControlMode == X265_RC_CQP)      /* Encoder::encode will not call getEstimatedPictureCost (encoder.cpp:2366) */
     {
+        waitMirror(st, f);
         st->handleOf.erase(f);
         releaseHandle(st, info.handle);
     }
@@ -333,6 +373,7 @@ void cudaLookaheadEstimatedPictureCost(Lookahead& self, Frame* cur)
         return;
     }
     void* h = it->second;
+    waitMirror(st, cur);        /* the frame encoder starts reading the Lowres right after this call */
     Slice* slice = cur->m_encData->m_slice;
     const int poc = slice->m_poc;
     int d0 = 0, d1 = 0;

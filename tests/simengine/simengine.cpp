@@ -28,6 +28,7 @@ struct SimSlot
     std::vector<std::vector<int32_t> > rowSatds;
     std::vector<x265cu_cost_result> results;
     x265cu_frame_stats stats;
+    std::vector<int32_t> recalcRows; int64_t recalcScore; int recalcStore;
 };
 
 struct x265cu_ctx
@@ -165,6 +166,7 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     s.costs.assign(ncs, std::vector<uint16_t>()); s.rowSatds.assign(ncs, std::vector<int32_t>());
     s.results.assign(ncs, x265cu_cost_result());
     memset(&s.stats, 0, sizeof(s.stats));
+    s.recalcStore = -1;
     if (c->cfg.need_aq)
         or_aq_frame(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW,
                     c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats, &s.qpAq[0], &s.qpCuTree[0], &s.invQ[0],
@@ -327,6 +329,51 @@ int x265cu_vbv_row_costs(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_
     if (intra) memcpy(intra, &b[0], n_rows * 4);
     if (cost_for_rc) memcpy(cost_for_rc, &rc[0], c->g.ncu * 2);
     if (intra_scaled) memcpy(intra_scaled, &ic[0], c->g.ncu * 4);
+    return 0;
+}
+
+int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost);
+int x265cu_fetch_costs(x265cu_ctx* c, int32_t slot, int32_t store, uint16_t* costs, int32_t* rows);
+int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o);
+
+/* the asynchronous mirror, done on the spot */
+int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_request* q, int64_t* ticket)
+{
+    x265cu_frame_out o;
+    memset(&o, 0, sizeof(o));
+    o.intra_cost = q->intra_cost; o.qp_aq_offset = q->qp_aq_offset; o.qp_cutree_offset = q->qp_cutree_offset;
+    o.inv_qscale_factor = q->inv_qscale_factor; o.planes = q->planes;
+    if (q->cost_store == 0) { o.lowres_costs00 = q->lowres_costs; o.row_satds00 = q->row_satds; }
+    x265cu_fetch_frame(c, slot, &o);
+    for (int i = 0; i < q->n_mv; i++) x265cu_fetch_mvs(c, slot, q->mv_store[i], q->mv_dst[i], NULL);
+    if (q->cost_store >= 2) x265cu_fetch_costs(c, slot, q->cost_store, q->lowres_costs, q->row_satds);
+    static int64_t n = 0;
+    if (ticket) *ticket = n++;
+    return 0;
+}
+int x265cu_mirror_wait(x265cu_ctx*, int64_t) { return 0; }
+
+int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree, int64_t* score, int32_t* rows);
+/* ahead-of-time recalculation: computed at enqueue into a side buffer, published into the store's rowSatds at get */
+int x265cu_cost_recalc_enqueue(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree)
+{
+    SimSlot& s = c->slots[slot];
+    std::vector<int32_t>& rs = cost_store == 0 ? s.rowSatds00 : s.rowSatds[cost_store];
+    std::vector<int32_t> keep(rs);
+    s.recalcRows.resize(c->g.bh);
+    x265cu_cost_recalc(c, slot, cost_store, use_cutree, &s.recalcScore, &s.recalcRows[0]);
+    rs = keep;
+    s.recalcStore = cost_store;
+    return 0;
+}
+int x265cu_cost_recalc_get(x265cu_ctx* c, int32_t slot, int32_t cost_store, int64_t* score, int32_t* rows)
+{
+    SimSlot& s = c->slots[slot];
+    if (s.recalcStore != cost_store) return X265CU_ERR_BAD_ARG;
+    *score = s.recalcScore;
+    if (rows) memcpy(rows, &s.recalcRows[0], c->g.bh * sizeof(int32_t));
+    (cost_store == 0 ? s.rowSatds00 : s.rowSatds[cost_store]) = s.recalcRows;
+    s.recalcStore = -1;
     return 0;
 }
 

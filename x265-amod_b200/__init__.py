@@ -51,6 +51,13 @@ class FrameOut(C.Structure):
                 ("planes", C.c_void_p), ("lowres_costs00", C.c_void_p), ("row_satds00", C.c_void_p)]
 
 
+class Mirror(C.Structure):
+    """x265la_mirror (host/la_capi.h): destinations of the asynchronous host mirror of a decided frame"""
+    _fields_ = [("intraCost", C.c_void_p), ("qpAqOffset", C.c_void_p), ("qpCuTreeOffset", C.c_void_p),
+                ("invQscaleFactor", C.c_void_p), ("planes", C.c_void_p), ("lowresMvs", (C.c_void_p * 18) * 2),
+                ("d0", C.c_int32), ("d1", C.c_int32), ("lowresCosts", C.c_void_p), ("rowSatds", C.c_void_p)]
+
+
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("search_jobs", C.c_uint64), ("cost_jobs", C.c_uint64)]
@@ -89,6 +96,12 @@ def load_lib(path=None):
                                        C.c_int64, C.c_int32, C.c_int32]
     lib.x265la_vbv_rows.argtypes = [C.c_void_p]
     lib.x265la_vbv_row_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4
+    lib.x265la_frame_mirror_async.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Mirror), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]
+    lib.x265la_mirror_wait.argtypes = [C.c_void_p, C.c_int64]
+    lib.x265la_pin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.x265la_unpin.argtypes = [C.c_void_p, C.c_void_p]
+    lib.x265la_estimated_picture_cost_dist.restype = C.c_int64
+    lib.x265la_estimated_picture_cost_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     lib.x265la_frame_planned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.x265la_flush.argtypes = [C.c_void_p]
     lib.x265la_get_decided.argtypes = [C.c_void_p, C.POINTER(FrameInfo)]

@@ -79,6 +79,18 @@ struct x265cu_ctx
                                                sequential AQ mean of a frame overlaps the streaming kernels of the next ones */
     unsigned preSeq;
     cudaEvent_t mainMark;
+    /* host mirrors of decided frames (x265cu_mirror_enqueue): their own high-priority stream, a ring of requests */
+    cudaStream_t mirrorStream;
+    cudaEvent_t mirrorMark;
+    struct MirrorEntry { cudaEvent_t done; char* scratch; size_t cap; long long ticket; } mirror[X265CU_MIRROR_RING];
+    long long nextMirror;
+    std::vector<cudaEvent_t> slotMirrored;      /* per slot: the last mirror request that read it */
+    std::vector<char> slotMirrorTouched;
+    /* cost recalculation ahead of time (x265cu_cost_recalc_enqueue): per slot {score, rows[bh]} in device scratch + event */
+    std::vector<cudaEvent_t> slotRecalc;
+    std::vector<int> slotRecalcStore;           /* cost store the pending request is for, -1 = none */
+    char* d_recalc; char* h_recalc;             /* [slot] x recalcStride: device scratch / mapped host copy */
+    size_t recalcStride;
     std::vector<char> slotMainTouched;          /* main-stream work read the slot's current tenant */
     cudaStream_t lanes[LA_NUM_LANES];
     Batch batches[LA_NUM_BATCHES];
@@ -166,6 +178,7 @@ void syncAll(x265cu_ctx* c)
     cudaStreamSynchronize(c->copyStream);
     for (int i = 0; i < LA_NUM_PRE; i++) cudaStreamSynchronize(c->preStreams[i]);
     cudaStreamSynchronize(c->stream);
+    if (c->mirrorStream) cudaStreamSynchronize(c->mirrorStream);
     for (int i = 0; i < LA_NUM_LANES; i++) cudaStreamSynchronize(c->lanes[i]);
 }
 
@@ -556,6 +569,12 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
         std::fill(c->mvWriter.begin() + (size_t)slot * c->geom.n_mv_stores, c->mvWriter.begin() + (size_t)(slot + 1) * c->geom.n_mv_stores, -1LL);
         std::fill(c->costWriter.begin() + (size_t)slot * c->geom.n_cost_stores, c->costWriter.begin() + (size_t)(slot + 1) * c->geom.n_cost_stores, -1LL);
     }
+    if (c->slotMirrorTouched[slot])
+    {
+        CK(cudaStreamWaitEvent(ps, c->slotMirrored[slot], 0));
+        c->slotMirrorTouched[slot] = 0;
+    }
+    c->slotRecalcStore[slot] = -1;
     if (c->slotMainTouched[slot])
     {
         /* ... and whatever the main stream (cuTree, recalc, mirrors) still reads of it */
@@ -998,6 +1017,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
+    c->mirrorStream = NULL; c->mirrorMark = NULL; c->nextMirror = 0; c->d_recalc = c->h_recalc = NULL; c->recalcStride = 0;
+    for (int i = 0; i < X265CU_MIRROR_RING; i++) { c->mirror[i].done = NULL; c->mirror[i].scratch = NULL; c->mirror[i].cap = 0; c->mirror[i].ticket = -1; }
     c->stream = c->copyStream = NULL; c->preSeq = 0; for (int i = 0; i < LA_NUM_PRE; i++) c->preStreams[i] = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
     for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
     for (int i = 0; i < LA_NUM_BATCHES; i++)
@@ -1077,6 +1098,10 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     for (int i = 0; i < LA_NUM_PRE; i++)
         if (cudaStreamCreateWithPriority(&c->preStreams[i], cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
     if (cudaEventCreateWithFlags(&c->mainMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    if (cudaStreamCreateWithPriority(&c->mirrorStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->mirrorMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
+    for (int i = 0; !rc && i < X265CU_MIRROR_RING; i++)
+        if (cudaEventCreateWithFlags(&c->mirror[i].done, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < LA_NUM_LANES; i++)
         if (cudaStreamCreateWithPriority(&c->lanes[i], cudaStreamNonBlocking, prLeast) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < LA_NUM_BATCHES; i++)
@@ -1105,6 +1130,10 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
         c->slotUsers.push_back(std::vector<long long>());
         c->slotOwner.push_back(0);
         c->slotMainTouched.push_back(0);
+        cudaEvent_t e2, e3;
+        cudaEventCreateWithFlags(&e2, cudaEventDisableTiming); cudaEventCreateWithFlags(&e3, cudaEventDisableTiming);
+        c->slotMirrored.push_back(e2); c->slotMirrorTouched.push_back(0);
+        c->slotRecalc.push_back(e3); c->slotRecalcStore.push_back(-1);
         /* planes must start zeroed: columns past the right margin are never written (K1) */
         if (cudaMemsetAsync(p, 0, L.total, c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
     }
@@ -1125,6 +1154,12 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
             cudaMalloc((void**)&b.d_sync, b.syncCap) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     }
     if (!rc && cfg->need_wp_stats && ensureScratch(c, c->mainScratch, c->stream, 1) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
+    if (!rc)
+    {
+        c->recalcStride = alignUp(8 + (size_t)g.bh * 4, 256);
+        if (cudaMalloc((void**)&c->d_recalc, c->recalcStride * cfg->max_slots) != cudaSuccess ||
+            cudaHostAlloc((void**)&c->h_recalc, c->recalcStride * cfg->max_slots, cudaHostAllocDefault) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+    }
     if (!rc)
     {
         c->resultsCap = (size_t)1 << 20;
@@ -1156,6 +1191,11 @@ void x265cu_destroy(x265cu_ctx* c)
     syncAll(c);
     for (size_t i = 0; i < c->slots.size(); i++) cudaFree(c->slots[i]);
     for (size_t i = 0; i < c->slotCopied.size(); i++) { cudaEventDestroy(c->slotCopied[i]); cudaEventDestroy(c->slotConsumed[i]); }
+    for (size_t i = 0; i < c->slotMirrored.size(); i++) { cudaEventDestroy(c->slotMirrored[i]); cudaEventDestroy(c->slotRecalc[i]); }
+    for (int i = 0; i < X265CU_MIRROR_RING; i++) { if (c->mirror[i].done) cudaEventDestroy(c->mirror[i].done); cudaFree(c->mirror[i].scratch); }
+    if (c->mirrorStream) cudaStreamDestroy(c->mirrorStream);
+    if (c->mirrorMark) cudaEventDestroy(c->mirrorMark);
+    cudaFree(c->d_recalc); if (c->h_recalc) cudaFreeHost(c->h_recalc);
     for (size_t i = 0; i < c->evPool.size(); i++) { cudaEventDestroy(c->evPool[i].a); cudaEventDestroy(c->evPool[i].b); }
     for (size_t i = 0; i < c->mainScratch.size(); i++) cudaFree(c->mainScratch[i]);
     for (int i = 0; i < LA_NUM_BATCHES; i++)
@@ -1223,6 +1263,7 @@ int x265cu_sync(x265cu_ctx* c)
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream)); for (int i = 0; i < LA_NUM_PRE; i++) CK(cudaStreamSynchronize(c->preStreams[i])); CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < LA_NUM_LANES; i++) CK(cudaStreamSynchronize(c->lanes[i]));
+    CK(cudaStreamSynchronize(c->mirrorStream));
     return X265CU_OK;
 }
 
@@ -1285,6 +1326,7 @@ int x265cu_timer_stop(x265cu_ctx* c, double* ms)
     if (st) return st;
     CK(cudaStreamSynchronize(c->copyStream));
     for (int i = 0; i < LA_NUM_PRE; i++) CK(cudaStreamSynchronize(c->preStreams[i]));
+    CK(cudaStreamSynchronize(c->mirrorStream));
     CK(cudaEventRecord(c->tm1, c->stream));
     CK(cudaEventSynchronize(c->tm1));
     float f = 0;
@@ -1617,6 +1659,164 @@ __global__ void unpack_mv_kernel(const int* __restrict__ src, int* __restrict__ 
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const int p = src[i]; dst[2 * i] = (int)(short)(p & 0xffff); dst[2 * i + 1] = p >> 16; }
+}
+
+/* `st` waits for batch `id` (its searches only, or all of it) */
+static int streamWaitBatch(x265cu_ctx* c, cudaStream_t st, long long id, bool searchesOnly)
+{
+    Batch* w = batchOf(c, id);
+    if (!w) return X265CU_OK;
+    if (w->open) { int rc = endBatch(c); if (rc) return rc; }
+    CK(cudaStreamWaitEvent(st, searchesOnly ? w->searchDone : w->done, 0));
+    return X265CU_OK;
+}
+
+struct UnpackTab { const int* src[X265CU_MIRROR_MAX_MV]; int* dst[X265CU_MIRROR_MAX_MV]; };
+__global__ void __launch_bounds__(256) unpack_mvs_kernel(UnpackTab t, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = t.src[blockIdx.y][i];
+    int2 v; v.x = (int)(short)(p & 0xffff); v.y = p >> 16;
+    ((int2*)t.dst[blockIdx.y])[i] = v;
+}
+
+int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_request* q, int64_t* ticket)
+{
+    if (!c || !q) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    flushCutree(c);
+    const Geom& g = c->g;
+    const SlotLayout& L = c->lay;
+    if (!slotOk(c, slot) || q->n_mv < 0 || q->n_mv > X265CU_MIRROR_MAX_MV || q->cost_store == 1 || q->cost_store >= c->geom.n_cost_stores)
+        return X265CU_ERR_BAD_ARG;
+    x265cu_ctx::MirrorEntry& e = c->mirror[c->nextMirror % X265CU_MIRROR_RING];
+    if (e.ticket >= 0) CK(cudaEventSynchronize(e.done));        /* the ring wrapped: that request's scratch is free again */
+    const cudaStream_t ms = c->mirrorStream;
+    /* behind everything the main stream carries so far (cuTree of the decisions taken, cost recalculations) ... */
+    CK(cudaEventRecord(c->mirrorMark, c->stream));
+    CK(cudaStreamWaitEvent(ms, c->mirrorMark, 0));
+    /* ... the frame's own pre-lookahead and the batches that wrote the stores asked for */
+    CK(cudaStreamWaitEvent(ms, c->slotConsumed[slot], 0));
+    int st = X265CU_OK;
+    for (int i = 0; i < q->n_mv && !st; i++)
+    {
+        if (q->mv_store[i] < 0 || q->mv_store[i] >= c->geom.n_mv_stores || !q->mv_dst[i]) return X265CU_ERR_BAD_ARG;
+        st = streamWaitBatch(c, ms, c->mvWriter[(size_t)slot * c->geom.n_mv_stores + q->mv_store[i]], c->nranks <= 1);
+    }
+    if (!st && q->cost_store >= 2) st = streamWaitBatch(c, ms, c->costWriter[(size_t)slot * c->geom.n_cost_stores + q->cost_store], false);
+    if (st) return st;
+    const size_t planeBytes = q->planes ? alignUp((size_t)(4 * g.planeSize) * c->bpp, 256) : 0;
+    const size_t mvBytes = alignUp((size_t)g.ncu * 8, 256);
+    const size_t need = planeBytes + mvBytes * q->n_mv + 256;
+    if (e.cap < need)
+    {
+        cudaFree(e.scratch); e.scratch = NULL; e.cap = 0;
+        CK(cudaMalloc((void**)&e.scratch, need));
+        e.cap = need;
+    }
+#define MIRROR_D2H(dst, src, bytes) do { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ms)); c->counters.d2h_bytes += (bytes); } while (0)
+    if (q->intra_cost) MIRROR_D2H(q->intra_cost, c->slots[slot] + L.intraCost, (size_t)g.ncu * 4);
+    if (q->qp_aq_offset) MIRROR_D2H(q->qp_aq_offset, c->slots[slot] + L.qpAq, (size_t)g.ncuFull * 8);
+    if (q->qp_cutree_offset) MIRROR_D2H(q->qp_cutree_offset, c->slots[slot] + L.qpCuTree, (size_t)g.ncuFull * 8);
+    if (q->inv_qscale_factor)
+    {
+        if (c->cfg.need_aq) MIRROR_D2H(q->inv_qscale_factor, c->slots[slot] + L.invQ, (size_t)g.ncuFull * 4);
+        else for (int i = 0; i < g.ncuFull; i++) q->inv_qscale_factor[i] = 256;
+    }
+    if (q->n_mv)
+    {
+        UnpackTab tab;
+        for (int i = 0; i < q->n_mv; i++)
+        {
+            tab.src[i] = (const int*)mvStorePtr(c, slot, q->mv_store[i]);
+            tab.dst[i] = (int*)(e.scratch + planeBytes + mvBytes * i);
+        }
+        unpack_mvs_kernel<<<dim3((g.ncu + 255) / 256, q->n_mv), 256, 0, ms>>>(tab, g.ncu);
+        c->counters.kernel_launches++;
+        CK(cudaGetLastError());
+        for (int i = 0; i < q->n_mv; i++) MIRROR_D2H(q->mv_dst[i], tab.dst[i], (size_t)g.ncu * 8);
+    }
+    if (q->cost_store >= 0 && (q->lowres_costs || q->row_satds))
+    {
+        const char* cs = q->cost_store == 0 ? NULL : costStorePtr(c, slot, q->cost_store);
+        if (q->lowres_costs) MIRROR_D2H(q->lowres_costs, cs ? cs : c->slots[slot] + L.lowresCosts00, (size_t)g.ncu * 2);
+        if (q->row_satds) MIRROR_D2H(q->row_satds, cs ? cs + L.costRowOff : c->slots[slot] + L.rowSatds00, (size_t)g.bh * 4);
+    }
+    if (q->planes)
+    {
+        const unsigned blocks = (unsigned)((4 * g.planeSize + 255) / 256);
+        if (c->bpp == 1) detile_kernel<uint8_t><<<blocks, 256, 0, ms>>>(g, slotPtr<uint8_t>(c, slot, L.planes), (uint8_t*)e.scratch);
+        else detile_kernel<uint16_t><<<blocks, 256, 0, ms>>>(g, slotPtr<uint16_t>(c, slot, L.planes), (uint16_t*)e.scratch);
+        c->counters.kernel_launches++;
+        CK(cudaGetLastError());
+        MIRROR_D2H(q->planes, e.scratch, (size_t)(4 * g.planeSize) * c->bpp);
+    }
+#undef MIRROR_D2H
+    CK(cudaEventRecord(e.done, ms));
+    CK(cudaEventRecord(c->slotMirrored[slot], ms));
+    c->slotMirrorTouched[slot] = 1;
+    e.ticket = c->nextMirror++;
+    if (ticket) *ticket = e.ticket;
+    return X265CU_OK;
+}
+
+int x265cu_mirror_wait(x265cu_ctx* c, int64_t ticket)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    if (ticket < 0 || ticket >= c->nextMirror) return X265CU_ERR_BAD_ARG;
+    x265cu_ctx::MirrorEntry& e = c->mirror[ticket % X265CU_MIRROR_RING];
+    if (e.ticket != ticket) return X265CU_OK;       /* the ring already moved past it: it was waited for then */
+    CK(cudaEventSynchronize(e.done));
+    return X265CU_OK;
+}
+
+int x265cu_cost_recalc_enqueue(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t use_cutree)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    flushCutree(c);
+    if (!slotOk(c, slot) || cost_store < 0 || cost_store >= c->geom.n_cost_stores || cost_store == 1) return X265CU_ERR_BAD_ARG;
+    const SlotLayout& L = c->lay;
+    const Geom& g = c->g;
+    const unsigned short* costs = cost_store == 0 ? slotPtr<unsigned short>(c, slot, L.lowresCosts00)
+                                                  : (const unsigned short*)costStorePtr(c, slot, cost_store);
+    int st = mainWaitCost(c, slot, cost_store);
+    if (!st) st = mainWaitPre(c, slot);
+    if (st) return st;
+    char* scratch = c->d_recalc + (size_t)slot * c->recalcStride;
+    CK(cudaMemsetAsync(scratch, 0, 8 + (size_t)g.bh * 4, c->stream));
+    {
+        Prof pr(c, X265CU_K_CUTREE, 1);
+        cost_recalc_kernel<<<(g.ncu + 255) / 256, 256, 0, c->stream>>>(g, costs, slotPtr<double>(c, slot, use_cutree ? L.qpCuTree : L.qpAq),
+                                                                      (int*)(scratch + 8), (unsigned long long*)scratch);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_recalc + (size_t)slot * c->recalcStride, scratch, 8 + (size_t)g.bh * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->slotRecalc[slot], c->stream));
+    c->slotRecalcStore[slot] = cost_store;
+    return X265CU_OK;
+}
+
+int x265cu_cost_recalc_get(x265cu_ctx* c, int32_t slot, int32_t cost_store, int64_t* score, int32_t* rows)
+{
+    if (!c || !score) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    if (!slotOk(c, slot) || c->slotRecalcStore[slot] != cost_store) return X265CU_ERR_BAD_ARG;
+    const SlotLayout& L = c->lay;
+    const Geom& g = c->g;
+    CK(cudaEventSynchronize(c->slotRecalc[slot]));
+    const char* h = c->h_recalc + (size_t)slot * c->recalcStride;
+    *score = *(const long long*)h;
+    if (rows) memcpy(rows, h + 8, (size_t)g.bh * 4);
+    c->counters.d2h_bytes += 8 + (size_t)g.bh * 4;
+    /* the reference's call leaves the recalculated row sums in rowSatds[b - p0][p1 - b]: move them there now */
+    int* rs = cost_store == 0 ? slotPtr<int>(c, slot, L.rowSatds00) : (int*)(costStorePtr(c, slot, cost_store) + L.costRowOff);
+    CK(cudaMemcpyAsync(rs, c->d_recalc + (size_t)slot * c->recalcStride + 8, (size_t)g.bh * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->slotMainTouched[slot] = 1;
+    c->slotRecalcStore[slot] = -1;
+    return X265CU_OK;
 }
 
 int x265cu_fetch_frame(x265cu_ctx* c, int32_t slot, const x265cu_frame_out* o)

@@ -167,6 +167,36 @@ int x265la_frame_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t*
 int x265la_frame_costs(void* la, void* frame, int32_t d0, int32_t d1, uint16_t* lowresCosts, int32_t* rowSatds)
 { return ((Lookahead*)la)->fetchCosts((Frame*)frame, d0, d1, lowresCosts, rowSatds) ? 1 : 0; }
 
+int x265la_frame_mirror_async(void* lav, void* frame, const x265la_mirror* m, uint32_t published[2], int64_t* ticket)
+{
+    Lookahead* la = (Lookahead*)lav;
+    Frame* f = (Frame*)frame;
+    const Lowres& l = f->m_lowres;
+    const int nb = la->geometry().nb;
+    x265cu_mirror_request q;
+    memset(&q, 0, sizeof(q));
+    q.intra_cost = m->intraCost; q.qp_aq_offset = m->qpAqOffset; q.qp_cutree_offset = m->qpCuTreeOffset;
+    q.inv_qscale_factor = m->invQscaleFactor; q.planes = m->planes;
+    if (published) published[0] = published[1] = 0;
+    for (int list = 0; list < 2; list++)
+        for (int d = 1; d < nb && d < 18; d++)
+            if (m->lowresMvs[list][d] && l.mvStore[list][d] >= 0 && q.n_mv < X265CU_MIRROR_MAX_MV)
+            {
+                q.mv_store[q.n_mv] = l.mvStore[list][d]; q.mv_dst[q.n_mv] = m->lowresMvs[list][d]; q.n_mv++;
+                if (published) published[list] |= 1u << d;
+            }
+    q.cost_store = -1;
+    if (m->d0 >= 0 && m->d0 < nb && m->d1 >= 0 && m->d1 < nb && l.costStore[m->d0][m->d1] >= 0)
+    {
+        q.cost_store = l.costStore[m->d0][m->d1]; q.lowres_costs = m->lowresCosts; q.row_satds = m->rowSatds;
+    }
+    return la->mirror(f, &q, ticket) ? 0 : -1;
+}
+
+int x265la_mirror_wait(void* la, int64_t ticket) { return x265cu_mirror_wait(((Lookahead*)la)->engine(), ticket); }
+int x265la_pin(void* la, void* ptr, uint64_t bytes) { return x265cu_pin_host(((Lookahead*)la)->engine(), ptr, bytes); }
+int x265la_unpin(void* la, void* ptr) { return x265cu_unpin_host(((Lookahead*)la)->engine(), ptr); }
+
 int x265la_frame_weights(void* lav, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset)
 {
     const Lowres& l = ((Frame*)frame)->m_lowres;

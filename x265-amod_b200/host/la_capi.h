@@ -79,6 +79,21 @@ int   x265la_frame_scalars(void* la, void* frame, int64_t* costEst /* nb*nb */, 
 int   x265la_frame_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t* mvXY, int32_t* mvCosts);  /* 1 ok, 0 unsearched */
 int   x265la_frame_costs(void* la, void* frame, int32_t d0, int32_t d1, uint16_t* lowresCosts, int32_t* rowSatds);
 int   x265la_frame_fetch(void* la, void* frame, const x265cu_frame_out* out);
+/* The host mirror of a decided frame in one asynchronous request (x265cu_mirror_enqueue): every destination is a host array in
+ * the reference's layout, NULL = skip.  lowresMvs[list][dist]: (x, y) int32 pairs = the reference's MV struct; lists the
+ * lookahead never published are skipped and their bit stays clear in published[list] (the caller writes the 0x7FFF sentinel).
+ * (d0, d1) names the estimate whose lowresCosts / rowSatds are wanted, d0 < 0 = none.  Returns 0 and a ticket for
+ * x265la_mirror_wait.  Page-lock the destinations (x265la_pin) or the enqueue itself waits for the copies. */
+typedef struct
+{
+    int32_t*  intraCost; double* qpAqOffset; double* qpCuTreeOffset; int32_t* invQscaleFactor; void* planes;
+    int32_t*  lowresMvs[2][18];
+    int32_t   d0, d1; uint16_t* lowresCosts; int32_t* rowSatds;
+} x265la_mirror;
+int   x265la_frame_mirror_async(void* la, void* frame, const x265la_mirror* m, uint32_t published[2], int64_t* ticket);
+int   x265la_mirror_wait(void* la, int64_t ticket);
+int   x265la_pin(void* la, void* ptr, uint64_t bytes);      /* cudaHostRegister through the engine; 0 = ok */
+int   x265la_unpin(void* la, void* ptr);
 /* weightp analysis outcome per L0 distance: state 0 = not analysed, 1 = no weight, 2 = weighted */
 int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset /* nb each */);
 /* host wall-clock per phase, seconds (see Lookahead::m_timers); reset != 0 clears them */

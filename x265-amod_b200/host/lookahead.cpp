@@ -196,6 +196,7 @@ void Lookahead::initLowres(Frame* f, int poc)
     l.frameNum = poc;
     l.satdCost = -1;
     l.rcD0 = l.rcD1 = -1;
+    l.rcPlanD0 = l.rcPlanD1 = -1;
     for (int i = 0; i < BFRAME_MAX + 2; i++)
         for (int j = 0; j < BFRAME_MAX + 2; j++)
         {
@@ -289,6 +290,15 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     if (m_param.speculate)
     {
         m_pendingSpec.push_back(f);
+        if (m_param.speculate == 1 && m_param.shardCount <= 1 && (int)m_pendingSpec.size() >= m_param.batchMin)
+        {
+            /* per-decision mode, window still filling (or the host far ahead of the GPU): hand the frames whose
+             * pre-lookahead has finished to the GPU in launches of batchMin frames instead of one launch at the first decision */
+            const double t0 = nowSec();
+            drainPending((size_t)m_param.pendingMax, -1);
+            m_timers[7] += nowSec() - t0;
+            if (m_failed) return NULL;
+        }
         if (m_param.speculate >= 2)
         {
             /* streaming: the frame's searches and costs go to the GPU now, long before a decision asks for them.
@@ -592,9 +602,22 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
     /* per-decision mode: unless the window needs one of them now, wait until enough frames have gathered for a launch
      * that fills the GPU (a lowres search is a ~500-step wavefront: small launches spend most of their time ramping
      * up and draining) */
-    if (m_param.speculate == 1 && !m_pendingSpec.empty() && m_pendingSpec.front()->m_poc > mustPoc &&
-        (int)m_pendingSpec.size() < m_param.batchMin)
-        return;
+    if (m_param.speculate == 1 && !m_pendingSpec.empty() && m_pendingSpec.front()->m_poc > mustPoc)
+    {
+        if ((int)m_pendingSpec.size() < m_param.batchMin)
+            return;
+        if (needStats && m_param.shardCount <= 1)
+        {
+            /* ... and with weightp only frames whose pixel sums are on the host (pre-lookahead finished) can be taken without
+             * stalling: wait until batchMin of them are */
+            int ready = 0;
+            for (size_t i = 0; i < m_pendingSpec.size() && ready < m_param.batchMin; i++, ready++)
+                if (!m_pendingSpec[i]->m_lowresInit && x265cu_frame_ready(m_ctx, m_pendingSpec[i]->m_lowres.slot) != 1)
+                    break;
+            if (ready < m_param.batchMin && m_pendingSpec.size() <= keep)
+                return;
+        }
+    }
     while (!m_pendingSpec.empty() && !m_failed)
     {
         Frame* f = m_pendingSpec.front();
@@ -929,6 +952,7 @@ void Lookahead::slicetypeDecide()
         p1 = b = bframes + 1;
         p0 = isTypeI(frames[bframes + 1]->sliceType) ? b : 0;
         singleCost(frames, p0, p1, b);
+        frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
         if (bframes)
         {
             p0 = 0;
@@ -941,6 +965,7 @@ void Lookahead::slicetypeDecide()
                 else
                     p1 = bframes + 1;
                 singleCost(frames, p0, p1, b);
+                frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
                 if (frames[b]->sliceType == TYPE_BREF) { p0 = b; isp0available = true; }
             }
         }
@@ -986,6 +1011,18 @@ void Lookahead::slicetypeDecide()
         frames[j + 1] = NULL;
         slicetypeAnalyse(frames, fr, true);
     }
+    /* The qp offsets of the frames just output are final now (cuTreeFinish ran in the analysis above, or in the keyframe
+     * re-analysis): enqueue the cuTree-adjusted cost rate control will ask for (frameCostRecalculate, :3802-3879), so that
+     * getEstimatedPictureCost finds it done instead of queueing behind the cuTree passes of later decisions */
+    if (p.rc.cuTree && p.rc.rateControlMode != 1)
+        for (int i = 0; i <= bframes && !m_failed; i++)
+        {
+            Lowres& l = list[i]->m_lowres;
+            if (l.sliceType == TYPE_B || l.rcPlanD0 < 0) continue;
+            const int cs = l.costStore[l.rcPlanD0][l.rcPlanD1];
+            if (cs >= 0) check(x265cu_cost_recalc_enqueue(m_ctx, l.slot, cs, 1), "x265cu_cost_recalc_enqueue");
+            else l.rcPlanD0 = l.rcPlanD1 = -1;
+        }
     m_timers[4] += nowSec() - tAnalyse;
     /* the pictures that were still uploading when this decision started have landed by now: hand them to the GPU
      * before returning to the caller instead of at the next decision */
@@ -1595,7 +1632,13 @@ void Lookahead::getEstimatedPictureCost(Frame* cur, int dist0, int dist1)
             int64_t score = 0;
             const int cs = l.costStore[d0][d1];
             if (cs < 0) { fail("getEstimatedPictureCost on an estimate that was never computed"); return; }
-            check(x265cu_cost_recalc(m_ctx, l.slot, cs, 1, &score, NULL), "x265cu_cost_recalc");
+            if (l.rcPlanD0 == d0 && l.rcPlanD1 == d1)
+            {
+                check(x265cu_cost_recalc_get(m_ctx, l.slot, cs, &score, NULL), "x265cu_cost_recalc_get");
+                l.rcPlanD0 = l.rcPlanD1 = -1;
+            }
+            else
+                check(x265cu_cost_recalc(m_ctx, l.slot, cs, 1, &score, NULL), "x265cu_cost_recalc");
             l.satdCost = score;
         }
     }
@@ -1657,6 +1700,14 @@ bool Lookahead::fetchCosts(Frame* f, int d0, int d1, uint16_t* lowresCosts, int3
         return check(x265cu_fetch_frame(m_ctx, f->m_lowres.slot, &o), "x265cu_fetch_frame");
     }
     return check(x265cu_fetch_costs(m_ctx, f->m_lowres.slot, cs, lowresCosts, rowSatds), "x265cu_fetch_costs");
+}
+
+bool Lookahead::mirror(Frame* f, const x265cu_mirror_request* req, int64_t* ticket)
+{
+    const double t0 = nowSec();
+    const bool ok = check(x265cu_mirror_enqueue(m_ctx, f->m_lowres.slot, req, ticket), "x265cu_mirror_enqueue");
+    m_timers[9] += nowSec() - t0;
+    return ok;
 }
 
 bool Lookahead::fetchFrame(Frame* f, const x265cu_frame_out* out)

@@ -97,6 +97,8 @@ struct Lowres
     int64_t plannedSatd[LOOKAHEAD_MAX + 1];
     int     indB;
     int     rcD0, rcD1;      /* the (b - p0, p1 - b) estimate the last getEstimatedPictureCost read; -1 = none yet */
+    int     rcPlanD0, rcPlanD1;  /* the estimate slicetypeDecide pre-computed for rate control (slicetype.cpp:2378-2427) and whose
+                                    cuTree-adjusted cost was enqueued ahead of time; -1 = none */
 
     /* publication state: which device store holds what the reference would hold */
     int     mvStore[2][BFRAME_MAX + 2];                      /* -1 = lowresMvs[l][d][0].x == 0x7FFF */
@@ -168,6 +170,7 @@ public:
     bool    fetchMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t* mvCosts);  /* false + x=0x7FFF if unsearched */
     bool    fetchCosts(Frame* f, int d0, int d1, uint16_t* lowresCosts, int32_t* rowSatds);
     bool    fetchFrame(Frame* f, const x265cu_frame_out* out);
+    bool    mirror(Frame* f, const x265cu_mirror_request* req, int64_t* ticket);   /* asynchronous, x265cu_mirror_enqueue */
 
     const x265cu_geometry& geometry() const { return m_geom; }
     x265cu_ctx* engine() { return m_ctx; }
