@@ -542,9 +542,10 @@ def main():
     ap.add_argument("--workload", default="2160p-main10", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end measurement (the line then repeats `value` there and says so)")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (other BASELINE configs)")
     ap.add_argument("--c-primitives", action="store_true", help="--impl reference: time the plain C primitives instead of the intrinsics shims")
-    ap.add_argument("--async-depth", type=int, default=32,
+    ap.add_argument("--async-depth", type=int, default=64,
                     help="extra frames of input delay (LookaheadParam::asyncDepth): same decisions, GPU slack")
     ap.add_argument("--speculate", type=int, default=1)
     ap.add_argument("--shard", default="streams", choices=["streams", "window"],
@@ -656,7 +657,7 @@ def main():
                        "lookahead_slices": 0, "pool_workers": cores, "async_depth": args.async_depth, "speculate": args.speculate,
                        "streams": world, "parallelism": "independent stream per GPU" if world > 1 else "1 GPU",
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * res["bytes_in"] // (1 << 20))},
-            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3),
+            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3), "skipped": bool(args.no_e2e),
                     "h2d_bytes_per_step": int(res["e2e_delta"]["h2d"]), "d2h_bytes_per_step": int(res["e2e_delta"]["d2h"]),
                     "d2h": "per decided frame, one asynchronous mirror request into page-locked buffers: getEstimatedPictureCost, qpAqOffset, "
                            "qpCuTreeOffset, invQscaleFactor, intraCost, the coded estimate's lowresCosts + rowSatds, EVERY published "
@@ -743,11 +744,13 @@ def measure_workload_ranked(pkg, eng, wl, args, device, cores, dist, reduce_max,
     e2e_kw = dict(la_kw, extraSlots=12)
     run_step(eng, [Stream(pkg, wl, host, e2e_kw, True)], dist=dist)
     e_times = []
-    for _ in range(args.steps):
+    for _ in range(0 if args.no_e2e else args.steps):
         ms, wall, out = run_step(eng, [Stream(pkg, wl, host, e2e_kw, True)], dist=dist)
         types, delta, prof, _ = out[0]
         assert types == types0, "decisions differ between device-resident and host-fed runs"
         e_times.append(reduce_max(ms))
+    if args.no_e2e:
+        e_times = list(res["times"])
     res.update(e2e_times=e_times, e2e_delta=delta, e2e_prof=prof, pinned=pinned_ok[0])
     del host
     if with_cpu:

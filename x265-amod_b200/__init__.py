@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.join(HERE, "lib")
+# X265CU_LIBDIR: another build of the two libraries (kernel tuning variants, tools/build_variants.sh)
+LIBDIR = os.environ.get("X265CU_LIBDIR") or os.path.join(HERE, "lib")
 
 TYPE_AUTO, TYPE_IDR, TYPE_I, TYPE_P, TYPE_BREF, TYPE_B = 0, 1, 2, 3, 4, 5
 TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "b", 5: "B"}

@@ -533,8 +533,8 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     CK(cudaStreamWaitEvent(c->copyStream, c->slotConsumed[slot], 0));
     /* cudaMemcpyDefault: the picture may live in host memory (pageable or pinned) or already in HBM */
     /* a contiguous plane goes as one linear copy (one DMA descriptor instead of one per row) */
-    if (sy == g.picW) CK(cudaMemcpyAsync(dY, y, (size_t)g.picW * g.picH * sizeof(P), cudaMemcpyDefault, c->copyStream));
-    else CK(cudaMemcpy2DAsync(dY, g.picW * sizeof(P), y, (size_t)sy * sizeof(P), g.picW * sizeof(P), g.picH, cudaMemcpyDefault, c->copyStream));
+    if (sy == g.picW && g.srcPitch == g.picW) CK(cudaMemcpyAsync(dY, y, (size_t)g.picW * g.picH * sizeof(P), cudaMemcpyDefault, c->copyStream));
+    else CK(cudaMemcpy2DAsync(dY, g.srcPitch * sizeof(P), y, (size_t)sy * sizeof(P), g.picW * sizeof(P), g.picH, cudaMemcpyDefault, c->copyStream));
     c->counters.h2d_bytes += (uint64_t)g.picW * g.picH * sizeof(P);
     const bool chroma = u && v;
     if (chroma && c->cfg.need_aq)
@@ -585,25 +585,27 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     /* stats + rowSatds00 start at zero */
     CK(cudaMemsetAsync(c->slots[slot] + L.rowSatds00, 0, L.stats + sizeof(FrameStatsDev) - L.rowSatds00, ps));
     P* planes = slotPtr<P>(c, slot, L.planes);
-    {
-        Prof pr(c, X265CU_K_LOWRES, 1, ps);
-        const long long threads = (long long)g.tpr * (g.planeLines >> 3) * 16;
-        lowres_kernel<P><<<(unsigned)((threads + 255) / 256), 256, 0, ps>>>(g, dY, planes);
-    }
     FrameStatsDev* stats = slotPtr<FrameStatsDev>(c, slot, L.stats);
     int* invQ = slotInvQ(c, slot);
+    const bool qg8 = g.aqBlock == 8;
+    unsigned* energy = slotPtr<unsigned>(c, slot, L.energy);
+    {
+        /* K1 + K2a fused: lowres planes and (qg-size > 8) the 16x16 AC energies / weightp sums in one pass over the luma */
+        Prof pr(c, X265CU_K_LOWRES, 2, ps);
+        const dim3 grid((g.bw + LA_LR_TILES - 1) / LA_LR_TILES, g.bh);
+        lowres_fused_kernel<P><<<grid, 32 * LA_LR_TILES, 0, ps>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, planes, energy, stats,
+                                                                  c->cfg.need_aq && !qg8);
+        const long long tileRows = 4LL * g.tpr * g.planeLines;
+        extend_border_kernel<P><<<(unsigned)((tileRows + 255) / 256), 256, 0, ps>>>(g, planes);
+    }
     if (c->cfg.need_aq)
     {
         const bool twoPass = (c->cfg.aq_mode == 2 || c->cfg.aq_mode == 3) && c->cfg.aq_strength != 0;
-        const bool qg8 = g.aqBlock == 8;
-        Prof pr(c, X265CU_K_AQ, 2 + 2 * twoPass + qg8, ps);
-        unsigned* energy = slotPtr<unsigned>(c, slot, L.energy);
+        Prof pr(c, X265CU_K_AQ, 1 + 2 * twoPass + 2 * qg8, ps);
         double* qpCuTree = slotPtr<double>(c, slot, L.qpCuTree);
         double* sums = slotPtr<double>(c, slot, L.aqSums);
         if (qg8)
             aq_energy8_kernel<P><<<(g.aqW * g.aqH + 31) / 32, 256, 0, ps>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
-        else
-            aq_energy_kernel<P><<<(g.ncu + 7) / 8, 256, 0, ps>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
         if (twoPass)
         {
             aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, ps>>>(g, energy, qpCuTree);
@@ -1035,6 +1037,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     /* geometry: Lowres::create (lowres.cpp:72-97) */
     Geom& g = c->g;
     g.picW = cfg->width; g.picH = cfg->height; g.cW = (cfg->width + 1) / 2; g.cH = (cfg->height + 1) / 2;
+    g.srcPitch = (g.picW + 15) / 16 * 16;
     const int lw = cfg->width / 2, lh = cfg->height / 2;
     g.mx = cfg->max_cu_size + 32; g.my = cfg->max_cu_size + 16;
     g.stride = lw + 2 * g.mx;
@@ -1061,7 +1064,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     SlotLayout& L = c->lay;
     size_t o = 0;
 #define SECTION(name, bytes) L.name = o; o = alignUp(o + (bytes), 256)
-    SECTION(srcY, (size_t)g.picW * g.picH * c->bpp + 64);
+    SECTION(srcY, (size_t)g.srcPitch * g.picH * c->bpp + 1024);     /* + slack: K1's row copies may run past the last row's end */
     SECTION(srcU, (size_t)g.cW * g.cH * c->bpp + 64);
     SECTION(srcV, (size_t)g.cW * g.cH * c->bpp + 64);
     SECTION(planes, (size_t)(4 * g.planeSize) * c->bpp + 256);

@@ -33,6 +33,8 @@ namespace la {
 struct Geom
 {
     int picW, picH, cW, cH;     /* full-res luma / chroma size */
+    int srcPitch;               /* samples per row of the staged full-res luma: picW rounded up to 16 (rows 16-byte aligned for
+                                   the bulk copies of K1); the chroma planes are packed at cW */
     int w, h, bw, bh, ncu;      /* lowres plane size and 8x8 grid */
     int mx, my, stride, planeLines;
     long long planeSize, padOffset;

@@ -23,83 +23,7 @@ struct CostResultDev            /* mirrors x265cu_cost_result */
     int intraMbs, reserved;
 };
 
-/* ------------------------------------------------------------------------------------------
- * K1: downscale to the four half-pel planes and write the WHOLE padded plane (margins included)
- * in one pass.  frame_init_lowres_core (pixel.cpp:605-628) + 4x extendPicBorder (lowres.cpp:
- * 373-376, pixel.cpp:1044-1058).  Margin samples replicate the edge sample, which is the same as
- * evaluating the filter at the clamped lowres coordinate; columns past the right margin (stride
- * alignment) stay 0 exactly as in the reference's zero-initialised buffer.  The source is read
- * with replicate clamping = PicYuv's padding (picyuv.cpp:261-285).
- * One thread = 4 consecutive output samples of all 4 planes: coalesced vector stores.
- * HBM-bound: reads F (full-res luma), writes 4 planes.
- * ------------------------------------------------------------------------------------------ */
-template <typename P> struct Vec4;
-template <> struct Vec4<uint8_t>  { typedef uchar4 T; };
-template <> struct Vec4<uint16_t> { typedef ushort4 T; };
-
-/* 16 consecutive threads write one whole 8x8 tile (thread = one row half of 4 samples), so the
- * stores of a warp are two contiguous tiles per plane. */
-template <typename P>
-__global__ void __launch_bounds__(256) lowres_kernel(Geom g, const P* __restrict__ src, P* __restrict__ buf)
-{
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long tile = t >> 4;
-    const int sub = (int)(t & 15);
-    if (tile >= (long long)g.tpr * (g.planeLines >> 3)) return;
-    const int x4 = (int)(tile % g.tpr) * 8 + (sub & 1) * 4;
-    const int py = (int)(tile / g.tpr) * 8 + (sub >> 1);
-    typename Vec4<P>::T o0, o1, o2, o3;
-    P* op[4] = { (P*)&o0, (P*)&o1, (P*)&o2, (P*)&o3 };
-    const int ly = min(max(py - g.my, 0), g.h - 1);
-    const int r0 = min(2 * ly, g.picH - 1), r1 = min(2 * ly + 1, g.picH - 1), r2 = min(2 * ly + 2, g.picH - 1);
-    const P* s0 = src + (long long)r0 * g.picW;
-    const P* s1 = src + (long long)r1 * g.picW;
-    const P* s2 = src + (long long)r2 * g.picW;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-    {
-        const int pxx = x4 + i;
-        if (pxx >= 2 * g.mx + g.w)
-        {
-            op[0][i] = op[1][i] = op[2][i] = op[3][i] = 0;
-            continue;
-        }
-        const int lx = min(max(pxx - g.mx, 0), g.w - 1);
-        const int c0 = min(2 * lx, g.picW - 1), c1 = min(2 * lx + 1, g.picW - 1), c2 = min(2 * lx + 2, g.picW - 1);
-        const int a00 = __ldg(s0 + c0), a01 = __ldg(s0 + c1), a02 = __ldg(s0 + c2);
-        const int a10 = __ldg(s1 + c0), a11 = __ldg(s1 + c1), a12 = __ldg(s1 + c2);
-        const int a20 = __ldg(s2 + c0), a21 = __ldg(s2 + c1), a22 = __ldg(s2 + c2);
-#define LA_FILTER(a, b, c, d) ((((a + b + 1) >> 1) + ((c + d + 1) >> 1) + 1) >> 1)
-        op[0][i] = (P)LA_FILTER(a00, a10, a01, a11);
-        op[1][i] = (P)LA_FILTER(a01, a11, a02, a12);
-        op[2][i] = (P)LA_FILTER(a10, a20, a11, a21);
-        op[3][i] = (P)LA_FILTER(a11, a21, a12, a22);
-#undef LA_FILTER
-    }
-    const long long o = tileOff(x4, py, g.tpr);
-    *(typename Vec4<P>::T*)(buf + o) = o0;
-    *(typename Vec4<P>::T*)(buf + g.planeSize + o) = o1;
-    *(typename Vec4<P>::T*)(buf + 2 * g.planeSize + o) = o2;
-    *(typename Vec4<P>::T*)(buf + 3 * g.planeSize + o) = o3;
-}
-
-/* tiled -> pitched copy of the four planes, for the host mirror of Lowres::buffer[0..3] */
-template <typename P>
-__global__ void __launch_bounds__(256) detile_kernel(Geom g, const P* __restrict__ tiled, P* __restrict__ linear)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 4 * g.planeSize) return;
-    const int pl = (int)(i / g.planeSize);
-    const long long o = i % g.planeSize;
-    const int Y = (int)(o / g.stride), X = (int)(o % g.stride);
-    linear[i] = tiled[pl * g.planeSize + tileOff(X, Y, g.tpr)];
-}
-
-/* ------------------------------------------------------------------------------------------
- * K2a: per-16x16 AC energy of Y + the two co-located 8x8 chroma blocks, and the frame sums for
- * weightp.  acEnergyCu / acEnergyPlane / acEnergyVar / pixel_var (slicetype.cpp:49-84,264-283,
- * pixel.cpp:720-737).  One warp per 16x16 block.  HBM-bound: reads 1.5 F.
- * ------------------------------------------------------------------------------------------ */
+/* sums / sums of squares for the AC energies (pixel_var, pixel.cpp:720-737) */
 template <typename P>
 __device__ __forceinline__ void warpVar(const P* __restrict__ p, int stride, int W, int H, int bx, int by, int size,
                                         unsigned& sum, unsigned& sqr)
@@ -146,80 +70,271 @@ __device__ __forceinline__ void sumSqr8(const uint16_t* p, unsigned& sum, unsign
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * K1 (+ K2a): ONE streaming pass over the full-res luma produces the four half-pel lowres planes
+ * (frame_init_lowres_core, pixel.cpp:605-628) AND the 16x16 AC energies + weightp sums of calcAdaptiveQuantFrame
+ * (acEnergyCu / acEnergyPlane / pixel_var, slicetype.cpp:49-84,264-283, pixel.cpp:720-737), so the picture is read from
+ * HBM once.  HBM-bound: reads F (+ 0.5 F chroma for the energies), writes 4 P.
+ *
+ * A CTA owns LA_LR_TILES lowres tiles side by side (64 x 8 lowres samples = 128 x 16 source samples = exactly the
+ * 16x16 AQ blocks of those tiles) and stages its 17 source rows x 129 columns in shared memory with one BULK ASYNC COPY per
+ * row (cp.async.bulk global -> shared, completion on an mbarrier: SASS UBLKCP), issued by one thread; nobody touches
+ * global memory for luma afterwards.  Replicate clamping = PicYuv's padding (picyuv.cpp:261-285) is done once per tile:
+ * vertically by pointing the copy of a row beyond the picture at the last row, horizontally by a fix-up of the staged
+ * columns in the right-most CTAs only.  A warp owns a tile: lane (y, q) produces samples 2q, 2q+1 of row y of all four planes
+ * from packed shared-memory words -- FILTER(a,b,c,d) = avg(avg(a,b), avg(c,d)) with avg = (x + y + 1) >> 1 is two packed
+ * average steps -- and the warp's 32 words are one contiguous tile in the tiled plane layout (la_device.cuh): full-line
+ * stores.  The same lane holds a 2 x 4 piece of the tile's 16x16 source block, so the block's sum / sum of squares are a
+ * warp reduction of values already in registers.  The plane margins are written by extend_border_kernel.
+ * ------------------------------------------------------------------------------------------ */
+template <typename P> struct Vec4;
+template <> struct Vec4<uint8_t>  { typedef uchar4 T; };
+template <> struct Vec4<uint16_t> { typedef ushort4 T; };
+
+#define LA_LR_TILES 8
+#define LA_LR_ROW_SAMPLES 144           /* 129 needed; 144 samples = 144 / 288 bytes, a multiple of 16 for both sample sizes */
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t avgPacked(uint32_t a, uint32_t b, uint8_t)  { return __vavgu4(a, b); }
+/* 16-bit samples below 2^15: the two halves cannot carry into each other */
+__device__ __forceinline__ uint32_t avgPacked(uint32_t a, uint32_t b, uint16_t) { return ((a + b + 0x00010001u) >> 1) & 0x7fff7fffu; }
+
 template <typename P>
-__global__ void __launch_bounds__(256) aq_energy_kernel(Geom g, const P* __restrict__ y, const P* __restrict__ u,
-                                                        const P* __restrict__ v, unsigned* __restrict__ energy,
-                                                        FrameStatsDev* stats)
+__global__ void __launch_bounds__(32 * LA_LR_TILES) lowres_fused_kernel(Geom g, const P* __restrict__ srcY, const P* __restrict__ srcU,
+                                                                        const P* __restrict__ srcV, P* __restrict__ planes,
+                                                                        unsigned* __restrict__ energy, FrameStatsDev* stats, int doEnergy)
 {
+    constexpr int SPP = (int)sizeof(P);
+    constexpr int ROW_BYTES = LA_LR_ROW_SAMPLES * SPP;
+    __shared__ __align__(128) unsigned char s_src[17 * ROW_BYTES];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ unsigned long long s_acc[6];
-    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int blk = blockIdx.x * 8 + warp;
-    /* rows of the packed picture are 16-byte aligned (8-byte for 8-bit chroma rows): whole-row vector loads */
-    const bool vecOk = ((g.picW * (int)sizeof(P)) & 15) == 0 && ((g.cW * (int)sizeof(P)) & (8 * (int)sizeof(P) - 1)) == 0;
-    if (blk < g.ncu)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ty = blockIdx.y;                      /* lowres tile row = 16 source rows */
+    const int c0 = blockIdx.x * 16 * LA_LR_TILES;   /* first source column of this CTA */
+    const int copySamples = min(LA_LR_ROW_SAMPLES, g.srcPitch - c0);       /* a multiple of 16 samples */
+    const uint32_t bar = smemAddr(&s_bar);
+    if (tid == 0)
     {
-        const int bx = (blk % g.bw) * 16, by = (blk / g.bw) * 16;
-        unsigned sum, sqr, e;
-        if (vecOk && bx + 16 <= g.picW && by + 16 <= g.picH)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 6) s_acc[tid] = 0;
+    __syncthreads();
+    if (tid == 0)
+    {
+        const uint32_t bytes = (uint32_t)(copySamples * SPP);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 17u) : "memory");
+#pragma unroll 1
+        for (int r = 0; r < 17; r++)
         {
-            /* interior block: lane = (row, half row) of the 16x16 luma block; lanes 0-7 / 8-15 = rows of the U / V 8x8 */
+            const P* src = srcY + (long long)min(16 * ty + r, g.picH - 1) * g.srcPitch + c0;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smemAddr(s_src + r * ROW_BYTES)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        }
+    }
+    /* everybody waits for the 17 rows (phase 0 of the barrier) */
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    /* columns at and beyond the picture's right edge replicate its last column (right-most CTAs only) */
+    const int valid = g.picW - c0;
+    if (valid < 16 * LA_LR_TILES + 1)
+    {
+        P* sp = (P*)s_src;
+        for (int i = tid; i < 17 * LA_LR_ROW_SAMPLES; i += 32 * LA_LR_TILES)
+        {
+            const int r = i / LA_LR_ROW_SAMPLES, x = i % LA_LR_ROW_SAMPLES;
+            if (x >= valid && x <= 16 * LA_LR_TILES) sp[r * LA_LR_ROW_SAMPLES + x] = sp[r * LA_LR_ROW_SAMPLES + valid - 1];
+        }
+        __syncthreads();
+    }
+    const int tx = blockIdx.x * LA_LR_TILES + warp;
+    if (tx < g.bw)
+    {
+        const int y = lane >> 2, q = lane & 3;
+        /* this lane's 3 source rows x 5 samples, starting at sample 16 * warp + 4 q of staged rows 2y .. 2y + 2 */
+        const unsigned char* base = s_src + (2 * y) * ROW_BYTES + (16 * warp + 4 * q) * SPP;
+        uint32_t o0, o1, o2, o3;        /* this lane's two samples of the planes (0,0), (h,0), (0,v), (h,v) */
+        unsigned sum, sqr;
+        if (SPP == 2)
+        {
+            uint32_t r[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                const uint2 v = *(const uint2*)(base + k * ROW_BYTES);
+                r[k][0] = v.x; r[k][1] = v.y; r[k][2] = *(const unsigned short*)(base + k * ROW_BYTES + 8);
+            }
+            uint32_t A[2][3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) { A[0][j] = avgPacked(r[0][j], r[1][j], (P)0); A[1][j] = avgPacked(r[1][j], r[2][j], (P)0); }
+            uint32_t t[2][2];
+#pragma unroll
+            for (int v = 0; v < 2; v++)
+            {
+                t[v][0] = avgPacked(A[v][0], __funnelshift_r(A[v][0], A[v][1], 16), (P)0);
+                t[v][1] = avgPacked(A[v][1], __funnelshift_r(A[v][1], A[v][2], 16), (P)0);
+            }
+            o0 = __byte_perm(t[0][0], t[0][1], 0x5410); o1 = __byte_perm(t[0][0], t[0][1], 0x7632);
+            o2 = __byte_perm(t[1][0], t[1][1], 0x5410); o3 = __byte_perm(t[1][0], t[1][1], 0x7632);
             sum = 0; sqr = 0;
-            sumSqr8(y + (long long)(by + (lane >> 1)) * g.picW + bx + (lane & 1) * 8, sum, sqr);
-            unsigned cs = 0, cq = 0;
-            if (u && lane < 16)
-                sumSqr8((lane < 8 ? u : v) + (long long)((by >> 1) + (lane & 7)) * g.cW + (bx >> 1), cs, cq);
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                {
+                    const unsigned lo = r[k][j] & 0xffffu, hi = r[k][j] >> 16;
+                    sum += lo + hi; sqr += lo * lo + hi * hi;
+                }
+        }
+        else
+        {
+            uint32_t r[3][2];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                r[k][0] = *(const uint32_t*)(base + k * ROW_BYTES);
+                r[k][1] = *(const unsigned char*)(base + k * ROW_BYTES + 4);
+            }
+            uint32_t t[2];
+#pragma unroll
+            for (int v = 0; v < 2; v++)
+            {
+                const uint32_t A0 = avgPacked(r[v][0], r[v + 1][0], (P)0), A1 = avgPacked(r[v][1], r[v + 1][1], (P)0);
+                t[v] = avgPacked(A0, __funnelshift_r(A0, A1, 8), (P)0);
+            }
+            o0 = __byte_perm(t[0], 0, 0x0020); o1 = __byte_perm(t[0], 0, 0x0031);
+            o2 = __byte_perm(t[1], 0, 0x0020); o3 = __byte_perm(t[1], 0, 0x0031);
+            sum = __vsadu4(r[0][0], 0) + __vsadu4(r[1][0], 0);
+            sqr = __dp4a(r[0][0], r[0][0], __dp4a(r[1][0], r[1][0], 0u));
+        }
+        /* the warp's 32 x 2 samples are one whole tile of each plane, contiguous in the tiled layout */
+        const long long tileBase = tileOff(g.mx + 8 * tx, g.my + 8 * ty, g.tpr);
+        if (SPP == 2)
+        {
+            uint32_t* d = (uint32_t*)(planes + tileBase) + lane;
+            const long long ps = g.planeSize >> 1;      /* plane stride in 32-bit words */
+            d[0] = o0; d[ps] = o1; d[2 * ps] = o2; d[3 * ps] = o3;
+        }
+        else
+        {
+            unsigned short* d = (unsigned short*)(planes + tileBase) + lane;
+            const long long ps = g.planeSize >> 1;      /* plane stride in 16-bit units */
+            d[0] = (unsigned short)o0; d[ps] = (unsigned short)o1; d[2 * ps] = (unsigned short)o2; d[3 * ps] = (unsigned short)o3;
+        }
+        if (doEnergy)
+        {
 #pragma unroll
             for (int o = 16; o; o >>= 1)
             {
                 sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 sqr += __shfl_xor_sync(0xffffffffu, sqr, o);
             }
-#pragma unroll
-            for (int o = 4; o; o >>= 1)     /* inside each 8-lane group */
-            {
-                cs += __shfl_xor_sync(0xffffffffu, cs, o);
-                cq += __shfl_xor_sync(0xffffffffu, cq, o);
-            }
-            const unsigned vs = __shfl_sync(0xffffffffu, cs, 8), vq = __shfl_sync(0xffffffffu, cq, 8);
-            e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
+            unsigned e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
             if (lane == 0) { atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr); }
-            if (u)
+            if (srcU)
             {
-                e += cq - (unsigned)(((unsigned long long)cs * cs) >> 6);
+                /* the co-located 8x8 chroma blocks: lanes 0-7 / 8-15 = rows of the U / V block */
+                const int bx = 8 * tx, by = 8 * ty;
+                const bool vecOk = ((g.cW * SPP) & (8 * SPP - 1)) == 0 && bx + 8 <= g.cW && by + 8 <= g.cH;
+                unsigned us, uq, vs, vq;
+                if (vecOk)
+                {
+                    unsigned cs = 0, cq = 0;
+                    if (lane < 16) sumSqr8((lane < 8 ? srcU : srcV) + (long long)(by + (lane & 7)) * g.cW + bx, cs, cq);
+#pragma unroll
+                    for (int o = 4; o; o >>= 1)
+                    {
+                        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                        cq += __shfl_xor_sync(0xffffffffu, cq, o);
+                    }
+                    us = __shfl_sync(0xffffffffu, cs, 0); uq = __shfl_sync(0xffffffffu, cq, 0);
+                    vs = __shfl_sync(0xffffffffu, cs, 8); vq = __shfl_sync(0xffffffffu, cq, 8);
+                }
+                else
+                {
+                    warpVar(srcU, g.cW, g.cW, g.cH, bx, by, 8, us, uq);
+                    warpVar(srcV, g.cW, g.cW, g.cH, bx, by, 8, vs, vq);
+                }
+                e += uq - (unsigned)(((unsigned long long)us * us) >> 6);
                 e += vq - (unsigned)(((unsigned long long)vs * vs) >> 6);
                 if (lane == 0)
                 {
-                    atomicAdd(&s_acc[1], (unsigned long long)cs); atomicAdd(&s_acc[4], (unsigned long long)cq);
+                    atomicAdd(&s_acc[1], (unsigned long long)us); atomicAdd(&s_acc[4], (unsigned long long)uq);
                     atomicAdd(&s_acc[2], (unsigned long long)vs); atomicAdd(&s_acc[5], (unsigned long long)vq);
                 }
             }
+            if (lane == 0) energy[ty * g.bw + tx] = e;
+        }
+    }
+    if (doEnergy)
+    {
+        __syncthreads();
+        if (tid < 3) atomicAdd(&stats->wp_sum[tid], s_acc[tid]);
+        else if (tid < 6) atomicAdd(&stats->wp_ssd[tid - 3], s_acc[tid]);
+    }
+}
+
+/* The plane margins: 4 x extendPicBorder (lowres.cpp:373-376, pixel.cpp:1044-1058) -- every margin sample replicates the
+ * nearest interior sample; columns past the right margin (stride alignment) are 0 like the reference's zero-initialised
+ * buffer.  One thread = one tile row (8 samples = one 16 / 8-byte store), threads in memory order. */
+template <typename P>
+__global__ void __launch_bounds__(256) extend_border_kernel(Geom g, P* __restrict__ planes)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long perPlane = (long long)g.tpr * g.planeLines;
+    if (idx >= 4 * perPlane) return;
+    const int pl = (int)(idx / perPlane);
+    const long long o = idx % perPlane;
+    const int tile = (int)(o >> 3), r = (int)(o & 7);
+    const int X0 = (tile % g.tpr) * 8, Y = (tile / g.tpr) * 8 + r;
+    if (X0 >= g.mx && X0 < g.mx + g.w && Y >= g.my && Y < g.my + g.h) return;     /* interior: written by K1 */
+    P* plane = planes + pl * g.planeSize;
+    typedef typename Vec4<P>::T V4;
+    V4 a, b;
+    P* pa = (P*)&a; P* pb = (P*)&b;
+    if (X0 >= 2 * g.mx + g.w)
+    {
+#pragma unroll
+        for (int i = 0; i < 4; i++) pa[i] = pb[i] = 0;
+    }
+    else
+    {
+        const int cy = min(max(Y, g.my), g.my + g.h - 1);
+        if (X0 >= g.mx && X0 < g.mx + g.w)
+        {
+            const V4* s = (const V4*)(plane + tileOff(X0, cy, g.tpr));
+            a = s[0]; b = s[1];
         }
         else
         {
-            /* picture edge: replicate-clamped samples (PicYuv padding, picyuv.cpp:261-285) */
-            warpVar(y, g.picW, g.picW, g.picH, bx, by, 16, sum, sqr);
-            e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
-            if (lane == 0) { atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr); }
-            if (u)
-            {
-                warpVar(u, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
-                e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
-                if (lane == 0) { atomicAdd(&s_acc[1], (unsigned long long)sum); atomicAdd(&s_acc[4], (unsigned long long)sqr); }
-                warpVar(v, g.cW, g.cW, g.cH, bx >> 1, by >> 1, 8, sum, sqr);
-                e += sqr - (unsigned)(((unsigned long long)sum * sum) >> 6);
-                if (lane == 0) { atomicAdd(&s_acc[2], (unsigned long long)sum); atomicAdd(&s_acc[5], (unsigned long long)sqr); }
-            }
+            const P v = plane[tileOff(X0 < g.mx ? g.mx : g.mx + g.w - 1, cy, g.tpr)];
+#pragma unroll
+            for (int i = 0; i < 4; i++) pa[i] = pb[i] = v;
         }
-        if (lane == 0) energy[blk] = e;
     }
-    __syncthreads();
-    if (threadIdx.x < 3) atomicAdd(&stats->wp_sum[threadIdx.x], s_acc[threadIdx.x]);
-    else if (threadIdx.x < 6) atomicAdd(&stats->wp_ssd[threadIdx.x - 3], s_acc[threadIdx.x]);
+    V4* d = (V4*)(plane + (o << 3));
+    d[0] = a; d[1] = b;
 }
 
-/* qg-size 8: the same for 8x8 luma blocks + the co-located 4x4 chroma blocks (slicetype.cpp:64-68,79-80: var shifts
+/* tiled -> pitched copy of the four planes, for the host mirror of Lowres::buffer[0..3] */
+template <typename P>
+__global__ void __launch_bounds__(256) detile_kernel(Geom g, const P* __restrict__ tiled, P* __restrict__ linear)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * g.planeSize) return;
+    const int pl = (int)(i / g.planeSize);
+    const long long o = i % g.planeSize;
+    const int Y = (int)(o / g.stride), X = (int)(o % g.stride);
+    linear[i] = tiled[pl * g.planeSize + tileOff(X, Y, g.tpr)];
+}
+
+/* K2a for qg-size 8: the AC energies of 8x8 luma blocks + the co-located 4x4 chroma blocks (slicetype.cpp:64-68,79-80: var shifts
  * 6 / 4).  One 8-lane group per block: lane r sums luma row r, lanes 0-3 / 4-7 a row of the U / V block.  Blocks are
  * numbered by the reference's running index (aqW per row).  Samples are replicate-clamped like PicYuv's padding. */
 template <typename P>
@@ -238,7 +353,7 @@ __global__ void __launch_bounds__(256) aq_energy8_kernel(Geom g, const P* __rest
     const int bx = (blk % g.aqW) * 8, by = (blk / g.aqW) * 8;
     unsigned sum = 0, sqr = 0;
     {
-        const P* row = y + (long long)min(by + r, g.picH - 1) * g.picW;
+        const P* row = y + (long long)min(by + r, g.picH - 1) * g.srcPitch;
 #pragma unroll
         for (int i = 0; i < 8; i++) { const unsigned s = row[min(bx + i, g.picW - 1)]; sum += s; sqr += s * s; }
     }
@@ -629,13 +744,29 @@ __device__ LA_ME_FN int sadFpelFn(Row<P> fenc, const P* plane0, int tpr, int X, 
 /* three of them at once (independent loads in flight together); offsets packed as (d + 8) nibbles x0 y0 x1 y1 x2 y2 */
 #define LA_PK3(x0, y0, x1, y1, x2, y2) \
     (((x0) + 8) | (((y0) + 8) << 4) | (((x1) + 8) << 8) | (((y1) + 8) << 12) | (((x2) + 8) << 16) | (((y2) + 8) << 20))
+#ifndef LA_SAD3_LOOP
+#define LA_SAD3_LOOP 0
+#endif
+#ifndef LA_MVP_LOOP
+#define LA_MVP_LOOP 0
+#endif
 template <typename P>
 __device__ LA_ME_FN int3 sad3FpelFn(Row<P> fenc, const P* plane0, int tpr, int X, int Yr, int pk)
 {
+#if LA_SAD3_LOOP
+    /* one copy of the row fetch + SAD in the instruction stream instead of three (the kernel's SASS does not fit the
+     * instruction cache: "no instruction" is its largest stall) */
+    int p[3];
+#pragma unroll 1
+    for (int i = 0; i < 3; i++, pk >>= 8)
+        p[i] = groupSum(sadRow(fenc, loadRowT(plane0, tpr, X + ((pk & 15) - 8), Yr + (((pk >> 4) & 15) - 8))));
+    return make_int3(p[0], p[1], p[2]);
+#else
     const int p0 = sadRow(fenc, loadRowT(plane0, tpr, X + ((pk & 15) - 8), Yr + (((pk >> 4) & 15) - 8)));
     const int p1 = sadRow(fenc, loadRowT(plane0, tpr, X + (((pk >> 8) & 15) - 8), Yr + (((pk >> 12) & 15) - 8)));
     const int p2 = sadRow(fenc, loadRowT(plane0, tpr, X + (((pk >> 16) & 15) - 8), Yr + (((pk >> 20) & 15) - 8)));
     return make_int3(groupSum(p0), groupSum(p1), groupSum(p2));
+#endif
 }
 
 /* lowresQPelCost (lowres.h:98-124): SAD or SATD of the motion-compensated block at quarter-pel (qx, qy) */
@@ -896,6 +1027,39 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
         }
         MV2 mvp = { 0, 0 };
         int skipCost = 0x7fffffff;
+#if LA_MVP_LOOP
+        {
+            /* the same, as a real loop: one copy of the quarter-pel SATD in the instruction stream instead of four */
+            int mvpcost = LA_COST_MAX;
+            int c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll 1
+            for (int i = 0; i < 4; i++)
+            {
+                const int ci = i == 0 ? cand[0] : i == 1 ? cand[1] : i == 2 ? cand[2] : cand[3];
+                const bool vi = i == 0 ? valid[0] : i == 1 ? valid[1] : i == 2 ? valid[2] : valid[3];
+                int dup = -1;
+                if (i > 0 && valid[0] && cand[0] == ci) dup = 0;
+                else if (i > 1 && valid[1] && cand[1] == ci) dup = 1;
+                else if (i > 2 && valid[2] && cand[2] == ci) dup = 2;
+                const bool need = vi && dup < 0;
+                int cost = 0;
+                if (__any_sync(LA_FULL, need))
+                {
+                    const MV2 zero = { 0, 0 };
+                    const MV2 c = need ? unpackMv(ci) : zero;
+                    cost = m.qpelSatd(c.x, c.y);
+                }
+                if (dup == 0) cost = c0; else if (dup == 1) cost = c1; else if (dup == 2) cost = c2;
+                if (i == 0) c0 = cost; else if (i == 1) c1 = cost; else if (i == 2) c2 = cost;
+                if (vi)
+                {
+                    if (cost < mvpcost) { mvpcost = cost; mvp = unpackMv(ci); }
+                    if (!(mvp.x | mvp.y) && J.bidir)
+                        skipCost = cost;
+                }
+            }
+        }
+#else
         {
             int mvpcost = LA_COST_MAX;
             int costs[4];
@@ -927,6 +1091,7 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
                 }
             }
         }
+#endif
         const MV2 mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
         const MV2 mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
         MV2 best;
