@@ -686,6 +686,17 @@ def main():
         except Exception as e:      # pragma: no cover
             others["ladder-2160p-1080p-720p"] = {"error": repr(e)}
         del frames
+        if world > 1 and left() > 90:
+            # BASELINE configs[3]: ONE 4320p stream over all the GPUs of the job (strong scaling; the 1-GPU figure is the
+            # "4320p-8bit" entry of the N = 1 run)
+            try:
+                w4 = dict(WORKLOADS["4320p-8bit"])
+                f4 = gen_frames(w4, w4["frames"], 0)
+                others["4320p-window-shard"] = window_shard_line(pkg, eng, shard, dist, w4, f4, args, rank, world, local_rank, cores,
+                                                                 reduce_max, steps=3, warmup=2)
+                del f4
+            except Exception as e:      # pragma: no cover
+                others["4320p-window-shard"] = {"error": repr(e)}
         if world == 1:
             for name in ("1080p-8bit", "1080p-slower-weightp", "4320p-8bit"):
                 need = 75 if name == "4320p-8bit" else 30
@@ -777,25 +788,27 @@ def measure_workload_ranked(pkg, eng, wl, args, device, cores, dist, reduce_max,
     return res
 
 
-def window_shard_line(pkg, eng, shard, dist, wl, frames, args, rank, world, local_rank, cores, reduce_max):
+def window_shard_line(pkg, eng, shard, dist, wl, frames, args, rank, world, local_rank, cores, reduce_max, steps=None, warmup=None):
     """ONE stream over the GPUs of the job (SURVEY 8e level 2, strong scaling): --shard window"""
     import torch
     F = wl["frames"]
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     la_kw = dict(wl["la"], asyncDepth=args.async_depth, speculate=args.speculate, pendingMax=args.pending_max or max(8, args.async_depth),
                  batchMin=args.batch_min, device=local_rank, poolWorkers=cores, shardCount=world)
     exchange = shard.make_exchange(dist, pkg.EXCHANGE_FN, cuda=True)
     dev = [tuple(to_t(a).cuda() for a in f) for f in frames]
     torch.cuda.synchronize()
     sh = (rank, world, exchange)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         run_step(eng, [Stream(pkg, wl, dev, la_kw, False)], dist=dist, shard=sh)
     times, types0 = [], None
-    for _ in range(args.steps):
+    for _ in range(steps):
         ms, wall, out = run_step(eng, [Stream(pkg, wl, dev, la_kw, False)], dist=dist, shard=sh)
         times.append(reduce_max(ms)); types0 = out[0][0]
     ms = float(np.mean(times))
     return {"metric": "lookahead_frames_per_s", "value": round(F / (ms / 1000.0), 2), "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong",
+            "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u16" if wl["depth"] > 8 else "u8", "data": "synthetic",
             "config": {"workload": wl["text"], "frames_per_step": F, "pool_workers": cores,
                        "parallelism": "one stream, searches / estimates split by source frame over %d GPUs" % world},

@@ -115,6 +115,7 @@ struct x265cu_ctx
     std::vector<int> slotOwner;
     std::vector<std::pair<char*, size_t> > xpool;    /* free exchange buffers */
     int searchWorkers;              /* worker warps per search job; 0 = default (env X265CU_SEARCH_WORKERS, for tuning) */
+    int searchSmem;                 /* dynamic shared memory per search CTA (env X265CU_SEARCH_SMEM, bytes): residency cap */
     bool profile;
     double profMs[X265CU_K_COUNT], profBusy[X265CU_K_COUNT];
     uint64_t profN[X265CU_K_COUNT];
@@ -196,6 +197,17 @@ void resolveProfile(x265cu_ctx* c)
         {
             c->profMs[c->evPool[i].kind] += t1 - t0;
             iv[c->evPool[i].kind].push_back(std::make_pair(t0, t1));
+        }
+    }
+    if (const char* path = getenv("X265CU_TIMELINE"))
+    {
+        /* tuning aid: every profiled launch bracket as "family,start_ms,end_ms" (ms since the context was created) */
+        if (FILE* f = fopen(path, "a"))
+        {
+            for (int k = 0; k < X265CU_K_COUNT; k++)
+                for (size_t i = 0; i < iv[k].size(); i++) fprintf(f, "%d,%.4f,%.4f\n", k, iv[k][i].first, iv[k][i].second);
+            fprintf(f, "-1,0,0\n");
+            fclose(f);
         }
     }
     for (int k = 0; k < X265CU_K_COUNT; k++)
@@ -743,7 +755,9 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
         /* workers per job: a job's strips start 8 steps apart and run ~bw steps, so beyond ~bw/8 of them some only
          * sit resident waiting for their turn; that matters when the launch is too small to oversubscribe the GPU */
         const int workers = std::max(1, std::min(nstrips, c->searchWorkers > 0 ? c->searchWorkers : (nstrips + 1) / 2));
-        search_kernel<P><<<n * workers, 32, 0, b->stream>>>(g, (const SearchJobDev<P>*)dst, nstrips, n,
+        /* searchSmem: bytes of (unused) dynamic shared memory per one-warp CTA -- caps how many search warps an SM holds,
+         * so that the short high-priority kernels (pre-lookahead, cuTree, recalc) always find room beside them */
+        search_kernel<P><<<n * workers, 32, c->searchSmem, b->stream>>>(g, (const SearchJobDev<P>*)dst, nstrips, n,
                                                            c->d_mvcost + c->cfg.mvcost_half, dsync, dsync + 1, c->d_executed);
     }
     CK(cudaGetLastError());
@@ -1017,6 +1031,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     c->d_results = NULL; c->resultsCap = 0; c->h_slotStats = NULL; c->d_slotStats = NULL; c->h_mapped = NULL; c->d_mapped = NULL; c->mappedCap = 0;
     c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
+    c->searchSmem = getenv("X265CU_SEARCH_SMEM") ? atoi(getenv("X265CU_SEARCH_SMEM")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
     c->mirrorStream = NULL; c->mirrorMark = NULL; c->nextMirror = 0; c->d_recalc = c->h_recalc = NULL; c->recalcStride = 0;
