@@ -29,6 +29,10 @@ N > 1 (torchrun): every rank runs an independent stream on its own GPU (lookahea
 streams shard with no data-path collective); value = total frames / max-over-ranks step time; scaling "weak".
 """
 import argparse
+import os
+# 22 CUDA streams per lookahead context (16 batch lanes, 3 pre-lookahead, main, mirror, copy): give them their own hardware
+# queues instead of the default 8, or unrelated streams falsely serialise behind each other's event waits
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import ctypes as C
 import json
 import os
@@ -220,6 +224,9 @@ class Stream:
         g = self.la.geom
         self.geom = dict(ncu=g.ncu, bw=g.bw, bh=g.bh, low_w=g.low_width, low_h=g.low_height, ncu_full=g.ncu_full,
                          stride=g.stride, plane_lines=g.plane_lines)
+        sm = (C.c_int32 * 2)()
+        self.pkg.load_engine().x265cu_sm_partition(C.c_void_p(self.la.engine()), C.byref(sm, 0), C.byref(sm, 4))
+        self.geom["sm_partition"] = [sm[0], sm[1]]
         self.types, self.d2h = [], 0
         self.tracker = self.pkg.RefTracker()
         self.pocs = {}
@@ -655,6 +662,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u16" if depth > 8 else "u8", "data": "synthetic",
             "config": {"workload": wl["text"], "frames_per_step": F, "resolution": "%dx%d" % (W, H), "bit_depth": depth,
                        "lookahead_slices": 0, "pool_workers": cores, "async_depth": args.async_depth, "speculate": args.speculate,
+                       "sm_partition": "%d SMs for cuTree / recalc / mirrors, %d for the search and cost batches (CUDA green contexts)"
+                                       % tuple(geom["sm_partition"]) if geom.get("sm_partition", [0, 0])[0] else "none",
                        "streams": world, "parallelism": "independent stream per GPU" if world > 1 else "1 GPU",
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * res["bytes_in"] // (1 << 20))},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3), "skipped": bool(args.no_e2e),

@@ -80,6 +80,10 @@ int  x265cu_device_count(void);
 int  x265cu_create(const x265cu_config* cfg, x265cu_ctx** out);
 void x265cu_destroy(x265cu_ctx* ctx);
 int  x265cu_get_geometry(const x265cu_ctx* ctx, x265cu_geometry* out);
+/* SMs of the two partitions the engine runs on (CUDA green contexts): `small_sms` for the short latency-critical kernels the
+ * host waits for (cuTree, cost recalculation, weightp scores, mirrors), `large_sms` for the search / cost batches; 0 / 0 when
+ * the device is not partitioned (driver without green contexts, or X265CU_GREEN=0 in the environment) */
+int  x265cu_sm_partition(const x265cu_ctx* ctx, int32_t* small_sms, int32_t* large_sms);
 const char* x265cu_strerror(int status);
 const char* x265cu_last_error(const x265cu_ctx* ctx);
 

@@ -114,6 +114,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 
 void x265cu_destroy(x265cu_ctx* c) { delete c; }
 int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* g) { *g = c->geom; return 0; }
+int x265cu_sm_partition(const x265cu_ctx*, int32_t* a, int32_t* b) { if (a) *a = 0; if (b) *b = 0; return 0; }
 int x265cu_pin_host(x265cu_ctx*, void*, uint64_t) { return 0; }
 int x265cu_unpin_host(x265cu_ctx*, void*) { return 0; }
 int x265cu_sync(x265cu_ctx*) { return 0; }

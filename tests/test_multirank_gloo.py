@@ -116,7 +116,8 @@ def test_two_ranks_shard_one_stream(case_name, extra, simdir):
     jobs = []
     for rank, blob, nsearch, ncost in res:
         got = pickle.loads(blob)
-        bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1))
+        bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1),
+                                   decision_rank=rank == 0)
         assert not bad, "rank %d:\n%s" % (rank, "\n".join(bad[:10]))
         jobs.append((nsearch, ncost))
     # the work really was split: neither rank did (nearly) all of it

@@ -21,6 +21,7 @@
  */
 #include "x265cu.h"
 #include "la_kernels.cuh"
+#include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -124,6 +125,12 @@ struct x265cu_ctx
     size_t evUsed;
     cudaEvent_t profBase;           /* origin of the busy-interval timestamps */
     cudaEvent_t tm0, tm1;           /* x265cu_timer_* */
+    /* SM partitioning (CUDA green contexts): the latency-critical short kernels the host waits for (cuTree, cost
+     * recalculation, weightp scores, the mirror's unpack / de-tile) get a small SM partition of their own, the search / cost
+     * lanes the rest.  Without it a 256-thread cuTree CTA queues for milliseconds until enough of the long-lived one-warp search
+     * CTAs of ONE SM have retired (28 of them hold every register of an SM).  NULL = not in use (API missing, or X265CU_GREEN=0). */
+    void* greenSmall; void* greenLarge;
+    int greenSmallSMs, greenLargeSMs;
     char err[256];
 };
 
@@ -244,6 +251,50 @@ DeviceScope::DeviceScope(const x265cu_ctx* c) : prev(-1), want(c ? c->cfg.device
 template <typename T> T* slotPtr(x265cu_ctx* c, int slot, size_t off) { return (T*)(c->slots[slot] + off); }
 /* the per-lowres-block AQ scale the block kernels read: invQscaleFactor, or invQscaleFactor8x8 with qg-size 8 */
 int* slotInvQ(x265cu_ctx* c, int slot) { return slotPtr<int>(c, slot, c->g.aqBlock == 8 ? c->lay.invQ8 : c->lay.invQ); }
+
+/* Green contexts through cudaGetDriverEntryPoint: no link-time dependency on libcuda (the library must load on a box
+ * without a driver, where x265cu_create then fails with X265CU_ERR_NO_DEVICE).  Returns false when the partitioning is
+ * unavailable or refused; the caller then creates ordinary priority streams. */
+bool makeGreenStreams(x265cu_ctx* c, int smallSMs, int prGreatest, int prLeast)
+{
+    typedef CUresult (*GetRes)(CUdevice, CUdevResource*, CUdevResourceType);
+    typedef CUresult (*Split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+    typedef CUresult (*GenDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+    typedef CUresult (*GreenCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*GreenStream)(CUstream*, CUgreenCtx, unsigned int, int);
+    typedef CUresult (*DevGet)(CUdevice*, int);
+    void *fGetRes = NULL, *fSplit = NULL, *fGen = NULL, *fCreate = NULL, *fStream = NULL, *fDev = NULL;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuDeviceGetDevResource", &fGetRes, cudaEnableDefault, &q) != cudaSuccess || !fGetRes ||
+        cudaGetDriverEntryPoint("cuDevSmResourceSplitByCount", &fSplit, cudaEnableDefault, &q) != cudaSuccess || !fSplit ||
+        cudaGetDriverEntryPoint("cuDevResourceGenerateDesc", &fGen, cudaEnableDefault, &q) != cudaSuccess || !fGen ||
+        cudaGetDriverEntryPoint("cuGreenCtxCreate", &fCreate, cudaEnableDefault, &q) != cudaSuccess || !fCreate ||
+        cudaGetDriverEntryPoint("cuGreenCtxStreamCreate", &fStream, cudaEnableDefault, &q) != cudaSuccess || !fStream ||
+        cudaGetDriverEntryPoint("cuDeviceGet", &fDev, cudaEnableDefault, &q) != cudaSuccess || !fDev)
+    { cudaGetLastError(); return false; }
+    CUdevice dev;
+    if (((DevGet)fDev)(&dev, c->cfg.device) != CUDA_SUCCESS) return false;
+    CUdevResource all, small, rest;
+    if (((GetRes)fGetRes)(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned int groups = 1;
+    if (((Split)fSplit)(&small, &groups, &all, &rest, 0, (unsigned)smallSMs) != CUDA_SUCCESS || groups != 1) return false;
+    if (small.sm.smCount < 8 || rest.sm.smCount < 64) return false;
+    CUdevResourceDesc dSmall, dRest;
+    if (((GenDesc)fGen)(&dSmall, &small, 1) != CUDA_SUCCESS || ((GenDesc)fGen)(&dRest, &rest, 1) != CUDA_SUCCESS) return false;
+    CUgreenCtx gS = NULL, gL = NULL;
+    if (((GreenCreate)fCreate)(&gS, dSmall, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (((GreenCreate)fCreate)(&gL, dRest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    CUstream sMain = NULL, sMirror = NULL, lanes[LA_NUM_LANES];
+    if (((GreenStream)fStream)(&sMain, gS, CU_STREAM_NON_BLOCKING, prGreatest) != CUDA_SUCCESS ||
+        ((GreenStream)fStream)(&sMirror, gS, CU_STREAM_NON_BLOCKING, prGreatest) != CUDA_SUCCESS) return false;
+    for (int i = 0; i < LA_NUM_LANES; i++)
+        if (((GreenStream)fStream)(&lanes[i], gL, CU_STREAM_NON_BLOCKING, prLeast) != CUDA_SUCCESS) return false;
+    c->stream = (cudaStream_t)sMain; c->mirrorStream = (cudaStream_t)sMirror;
+    for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = (cudaStream_t)lanes[i];
+    c->greenSmall = gS; c->greenLarge = gL;
+    c->greenSmallSMs = (int)small.sm.smCount; c->greenLargeSMs = (int)rest.sm.smCount;
+    return true;
+}
 
 int ensureDev(x265cu_ctx* c, char** p, size_t* cap, size_t need)
 {
@@ -1111,17 +1162,28 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
      * leave the short pre-lookahead / cuTree kernels (which the host waits for) queueing for a free SM slot */
     int prLeast = 0, prGreatest = 0;
     cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
-    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
+    c->greenSmall = c->greenLarge = NULL; c->greenSmallSMs = c->greenLargeSMs = 0;
+    {
+        const char* e = getenv("X265CU_GREEN");
+        const int want = e ? atoi(e) : 16;      /* SMs of the small partition; 0 = no partitioning */
+        if (want > 0 && !makeGreenStreams(c, want, prGreatest, prLeast))
+        {
+            c->greenSmall = c->greenLarge = NULL;
+            c->stream = c->mirrorStream = NULL;
+            for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
+        }
+    }
+    if (!c->stream && cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) { delete c; return X265CU_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return X265CU_ERR_CUDA; }
     for (int i = 0; i < LA_NUM_PRE; i++)
         if (cudaStreamCreateWithPriority(&c->preStreams[i], cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
     if (cudaEventCreateWithFlags(&c->mainMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
-    if (cudaStreamCreateWithPriority(&c->mirrorStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess ||
+    if ((!c->mirrorStream && cudaStreamCreateWithPriority(&c->mirrorStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) ||
         cudaEventCreateWithFlags(&c->mirrorMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < X265CU_MIRROR_RING; i++)
         if (cudaEventCreateWithFlags(&c->mirror[i].done, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < LA_NUM_LANES; i++)
-        if (cudaStreamCreateWithPriority(&c->lanes[i], cudaStreamNonBlocking, prLeast) != cudaSuccess) rc = X265CU_ERR_CUDA;
+        if (!c->lanes[i] && cudaStreamCreateWithPriority(&c->lanes[i], cudaStreamNonBlocking, prLeast) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < LA_NUM_BATCHES; i++)
     {
         Batch& b = c->batches[i];
@@ -1242,7 +1304,26 @@ void x265cu_destroy(x265cu_ctx* c)
     if (c->mainMark) cudaEventDestroy(c->mainMark);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->greenSmall || c->greenLarge)
+    {
+        typedef CUresult (*GreenDestroy)(CUgreenCtx);
+        void* f = NULL;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &f, cudaEnableDefault, &q) == cudaSuccess && f)
+        {
+            if (c->greenSmall) ((GreenDestroy)f)((CUgreenCtx)c->greenSmall);
+            if (c->greenLarge) ((GreenDestroy)f)((CUgreenCtx)c->greenLarge);
+        }
+    }
     delete c;
+}
+
+int x265cu_sm_partition(const x265cu_ctx* c, int32_t* small_sms, int32_t* large_sms)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    if (small_sms) *small_sms = c->greenSmallSMs;
+    if (large_sms) *large_sms = c->greenLargeSMs;
+    return X265CU_OK;
 }
 
 int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* out) { if (!c || !out) return X265CU_ERR_BAD_ARG; *out = c->geom; return X265CU_OK; }

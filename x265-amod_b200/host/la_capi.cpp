@@ -78,7 +78,10 @@ int x265la_get_geometry(void* la, x265cu_geometry* g) { *g = ((Lookahead*)la)->g
 const char* x265la_last_error(void* la) { return ((Lookahead*)la)->lastError(); }
 x265cu_ctx* x265la_engine(void* la) { return ((Lookahead*)la)->engine(); }
 int x265la_shard_config(void* la, int32_t rank, int32_t nranks, x265cu_exchange_fn fn, void* user)
-{ return x265cu_shard_config(((Lookahead*)la)->engine(), rank, nranks, fn, user); }
+{
+    ((Lookahead*)la)->setShardRank(rank);
+    return x265cu_shard_config(((Lookahead*)la)->engine(), rank, nranks, fn, user);
+}
 
 void* x265la_add_picture(void* la, const void* y, const void* u, const void* v, int32_t strideY, int32_t strideC,
                          int64_t pts, int32_t sliceType, int32_t sliceTypeReq)

@@ -62,7 +62,7 @@ void lookaheadParamDefault(LookaheadParam* p)
 Lookahead::Lookahead(const LookaheadParam& param)
     : m_param(param), m_filled(false), m_inputCount(0), m_lastNonB(NULL), m_lastNonBFrame(NULL),
       m_isSceneTransition(false), m_extendGopBoundary(false), m_rowsPerSlice(0), m_dualSlicing(false), m_inBatch(false),
-      m_costVariants(2), m_ctx(NULL), m_pocNext(0), m_failed(false)
+      m_costVariants(2), m_ctx(NULL), m_pocNext(0), m_shardRank(0), m_failed(false)
 {
     m_error[0] = 0;
     memset(m_timers, 0, sizeof(m_timers));
@@ -1014,7 +1014,7 @@ void Lookahead::slicetypeDecide()
     /* The qp offsets of the frames just output are final now (cuTreeFinish ran in the analysis above, or in the keyframe
      * re-analysis): enqueue the cuTree-adjusted cost rate control will ask for (frameCostRecalculate, :3802-3879), so that
      * getEstimatedPictureCost finds it done instead of queueing behind the cuTree passes of later decisions */
-    if (p.rc.cuTree && p.rc.rateControlMode != 1)
+    if (p.rc.cuTree && p.rc.rateControlMode != 1 && !(p.shardCount > 1 && m_shardRank > 0))
         for (int i = 0; i <= bframes && !m_failed; i++)
         {
             Lowres& l = list[i]->m_lowres;
@@ -1401,6 +1401,8 @@ int64_t Lookahead::slicetypePathCost(Lowres** frames, char* path, int64_t thresh
 void Lookahead::cuTree(Lowres** frames, int numframes, bool bIntra)
 {
     const LookaheadParam& p = m_param;
+    if (m_param.shardCount > 1 && m_shardRank > 0)
+        return;     /* not the decision rank: its qp offsets are never read */
     int idx = !bIntra;
     int lastnonb, curnonb = 1;
     int bframes = 0;
@@ -1505,6 +1507,8 @@ int64_t Lookahead::frameCostRecalculate(Lowres** frames, int p0, int p1, int b)
 {
     if (frames[b]->sliceType == TYPE_B)
         return frames[b]->costEstAq[b - p0][p1 - b];
+    if (m_param.shardCount > 1 && m_shardRank > 0)
+        return 0;   /* planned costs are only read on the decision rank */
     int64_t score = 0;
     int cs = frames[b]->costStore[b - p0][p1 - b];
     if (cs < 0) { fail("frameCostRecalculate on an estimate that was never computed"); return 0; }

@@ -172,6 +172,9 @@ public:
     bool    fetchFrame(Frame* f, const x265cu_frame_out* out);
     bool    mirror(Frame* f, const x265cu_mirror_request* req, int64_t* ticket);   /* asynchronous, x265cu_mirror_enqueue */
 
+    /* sharded stream: this instance's rank.  Every rank takes the same slice-type decisions; only rank 0 is the decision rank
+     * whose output is used, so only it runs cuTree and the rate-control costs (qp offsets never feed back into decisions) */
+    void    setShardRank(int rank) { m_shardRank = rank; }
     const x265cu_geometry& geometry() const { return m_geom; }
     x265cu_ctx* engine() { return m_ctx; }
     const char* lastError() const { return m_error; }
@@ -209,6 +212,7 @@ private:
     std::deque<Frame*>  m_pendingSpec;    /* arrived, searches / costs not enqueued yet */
     std::map<const void*, bool> m_pinned; /* caller buffers page-locked by pinHost (true = registered) */
     int     m_pocNext;
+    int     m_shardRank;
     bool    m_failed; char m_error[256];
 
     /* decision logic (same names as the reference) */
