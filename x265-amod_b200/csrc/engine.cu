@@ -82,6 +82,8 @@ struct x265cu_ctx
     cudaEvent_t mainMark;
     /* host mirrors of decided frames (x265cu_mirror_enqueue): their own high-priority stream, a ring of requests */
     cudaStream_t mirrorStream;
+    cudaStream_t gatherStream;      /* the small synchronous gathers of the decision path (cost sums, skip flags): ordered only after the
+                                       batches that produced them, NOT after the cuTree backlog of earlier decisions on the main stream */
     cudaEvent_t mirrorMark;
     struct MirrorEntry { cudaEvent_t done; char* scratch; size_t cap; long long ticket; } mirror[X265CU_MIRROR_RING];
     long long nextMirror;
@@ -187,6 +189,7 @@ void syncAll(x265cu_ctx* c)
     for (int i = 0; i < LA_NUM_PRE; i++) cudaStreamSynchronize(c->preStreams[i]);
     cudaStreamSynchronize(c->stream);
     if (c->mirrorStream) cudaStreamSynchronize(c->mirrorStream);
+    if (c->gatherStream) cudaStreamSynchronize(c->gatherStream);
     for (int i = 0; i < LA_NUM_LANES; i++) cudaStreamSynchronize(c->lanes[i]);
 }
 
@@ -289,7 +292,9 @@ bool makeGreenStreams(x265cu_ctx* c, int smallSMs, int prGreatest, int prLeast)
         ((GreenStream)fStream)(&sMirror, gS, CU_STREAM_NON_BLOCKING, prGreatest) != CUDA_SUCCESS) return false;
     for (int i = 0; i < LA_NUM_LANES; i++)
         if (((GreenStream)fStream)(&lanes[i], gL, CU_STREAM_NON_BLOCKING, prLeast) != CUDA_SUCCESS) return false;
-    c->stream = (cudaStream_t)sMain; c->mirrorStream = (cudaStream_t)sMirror;
+    CUstream sGather = NULL;
+    if (((GreenStream)fStream)(&sGather, gS, CU_STREAM_NON_BLOCKING, prGreatest) != CUDA_SUCCESS) return false;
+    c->stream = (cudaStream_t)sMain; c->mirrorStream = (cudaStream_t)sMirror; c->gatherStream = (cudaStream_t)sGather;
     for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = (cudaStream_t)lanes[i];
     c->greenSmall = gS; c->greenLarge = gL;
     c->greenSmallSMs = (int)small.sm.smCount; c->greenLargeSMs = (int)rest.sm.smCount;
@@ -330,7 +335,7 @@ __global__ void gather_small_kernel(const unsigned* const* __restrict__ srcs, in
 int ensureMapped(x265cu_ctx* c, size_t need)
 {
     if (c->mappedCap >= need) return X265CU_OK;
-    if (c->h_mapped) { cudaStreamSynchronize(c->stream); cudaFreeHost(c->h_mapped); c->h_mapped = NULL; c->mappedCap = 0; }
+    if (c->h_mapped) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->gatherStream); cudaFreeHost(c->h_mapped); c->h_mapped = NULL; c->mappedCap = 0; }
     const size_t n = alignUp(need * 2, 4096);
     CK(cudaHostAlloc((void**)&c->h_mapped, n, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&c->d_mapped, c->h_mapped, 0));
@@ -346,11 +351,11 @@ int gatherSmall(x265cu_ctx* c, const std::vector<const void*>& srcs, int wordsEa
     int st = ensureMapped(c, tabBytes + outBytes);
     if (st) return st;
     memcpy(c->h_mapped, &srcs[0], n * sizeof(void*));
-    gather_small_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const unsigned* const*)c->d_mapped, wordsEach,
-                                                                             (unsigned*)(c->d_mapped + tabBytes), (int)n);
+    gather_small_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->gatherStream>>>((const unsigned* const*)c->d_mapped, wordsEach,
+                                                                                   (unsigned*)(c->d_mapped + tabBytes), (int)n);
     c->counters.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->gatherStream));
     memcpy(dst, c->h_mapped + tabBytes, outBytes);
     c->counters.d2h_bytes += outBytes;
     return X265CU_OK;
@@ -555,6 +560,16 @@ int mainWaitBatch(x265cu_ctx* c, long long id, bool searchesOnly)
     CK(cudaStreamWaitEvent(c->stream, searchesOnly ? w->searchDone : w->done, 0));
     return X265CU_OK;
 }
+/* `st` waits for batch `id` (its searches only, or all of it) */
+int streamWaitBatch(x265cu_ctx* c, cudaStream_t st, long long id, bool searchesOnly)
+{
+    Batch* w = batchOf(c, id);
+    if (!w) return X265CU_OK;
+    if (w->open) { int rc = endBatch(c); if (rc) return rc; }
+    CK(cudaStreamWaitEvent(st, searchesOnly ? w->searchDone : w->done, 0));
+    return X265CU_OK;
+}
+
 int mainWaitMv(x265cu_ctx* c, int slot, int store)
 {
     /* sharded stream: the MVs of a frame another rank owns arrive with the exchange at the end of the batch */
@@ -1085,7 +1100,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     c->searchSmem = getenv("X265CU_SEARCH_SMEM") ? atoi(getenv("X265CU_SEARCH_SMEM")) : 0;
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
-    c->mirrorStream = NULL; c->mirrorMark = NULL; c->nextMirror = 0; c->d_recalc = c->h_recalc = NULL; c->recalcStride = 0;
+    c->mirrorStream = NULL; c->gatherStream = NULL; c->mirrorMark = NULL; c->nextMirror = 0; c->d_recalc = c->h_recalc = NULL; c->recalcStride = 0;
     for (int i = 0; i < X265CU_MIRROR_RING; i++) { c->mirror[i].done = NULL; c->mirror[i].scratch = NULL; c->mirror[i].cap = 0; c->mirror[i].ticket = -1; }
     c->stream = c->copyStream = NULL; c->preSeq = 0; for (int i = 0; i < LA_NUM_PRE; i++) c->preStreams[i] = NULL; c->profBase = c->tm0 = c->tm1 = c->mainMark = NULL;
     for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
@@ -1169,7 +1184,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
         if (want > 0 && !makeGreenStreams(c, want, prGreatest, prLeast))
         {
             c->greenSmall = c->greenLarge = NULL;
-            c->stream = c->mirrorStream = NULL;
+            c->stream = c->mirrorStream = c->gatherStream = NULL;
             for (int i = 0; i < LA_NUM_LANES; i++) c->lanes[i] = NULL;
         }
     }
@@ -1178,7 +1193,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     for (int i = 0; i < LA_NUM_PRE; i++)
         if (cudaStreamCreateWithPriority(&c->preStreams[i], cudaStreamNonBlocking, prGreatest) != cudaSuccess) rc = X265CU_ERR_CUDA;
     if (cudaEventCreateWithFlags(&c->mainMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
-    if ((!c->mirrorStream && cudaStreamCreateWithPriority(&c->mirrorStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) ||
+    if ((!c->gatherStream && cudaStreamCreateWithPriority(&c->gatherStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) ||
+        (!c->mirrorStream && cudaStreamCreateWithPriority(&c->mirrorStream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) ||
         cudaEventCreateWithFlags(&c->mirrorMark, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
     for (int i = 0; !rc && i < X265CU_MIRROR_RING; i++)
         if (cudaEventCreateWithFlags(&c->mirror[i].done, cudaEventDisableTiming) != cudaSuccess) rc = X265CU_ERR_CUDA;
@@ -1274,6 +1290,7 @@ void x265cu_destroy(x265cu_ctx* c)
     for (size_t i = 0; i < c->slotMirrored.size(); i++) { cudaEventDestroy(c->slotMirrored[i]); cudaEventDestroy(c->slotRecalc[i]); }
     for (int i = 0; i < X265CU_MIRROR_RING; i++) { if (c->mirror[i].done) cudaEventDestroy(c->mirror[i].done); cudaFree(c->mirror[i].scratch); }
     if (c->mirrorStream) cudaStreamDestroy(c->mirrorStream);
+    if (c->gatherStream) cudaStreamDestroy(c->gatherStream);
     if (c->mirrorMark) cudaEventDestroy(c->mirrorMark);
     cudaFree(c->d_recalc); if (c->h_recalc) cudaFreeHost(c->h_recalc);
     for (size_t i = 0; i < c->evPool.size(); i++) { cudaEventDestroy(c->evPool[i].a); cudaEventDestroy(c->evPool[i].b); }
@@ -1375,6 +1392,21 @@ int x265cu_batch_begin(x265cu_ctx* c, int64_t* batch_id)
     int st = beginBatch(c);
     if (!st && batch_id) *batch_id = c->cur->id;
     return st;
+}
+
+int x265cu_batches_in_flight(x265cu_ctx* c)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    /* newest first, one lane's worth: the answer the caller acts on is "none", and a busy GPU says otherwise at the first query */
+    int n = 0;
+    for (long long id = c->nextBatch - 1; id >= 0 && id >= c->nextBatch - LA_NUM_LANES && !n; id--)
+    {
+        const Batch* b = batchOf(c, id);
+        if (b && (b->open || cudaEventQuery(b->done) == cudaErrorNotReady)) n++;
+    }
+    cudaGetLastError();
+    return n;
 }
 
 int x265cu_batch_end(x265cu_ctx* c)
@@ -1539,7 +1571,8 @@ int x265cu_search_flags_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i]) || stores[i] < 0 || stores[i] >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
-        int st = mainWaitMv(c, slots[i], stores[i]);
+        /* (sharded stream: the flag of a frame another rank owns arrives with the exchange at the end of the batch) */
+        int st = streamWaitBatch(c, c->gatherStream, c->mvWriter[(size_t)slots[i] * c->geom.n_mv_stores + stores[i]], c->nranks <= 1);
         if (st) return st;
         srcs[i] = mvStorePtr(c, slots[i], stores[i]) + (size_t)c->g.ncu * 8;
     }
@@ -1566,7 +1599,7 @@ int x265cu_cost_results_get(x265cu_ctx* c, const int32_t* slots, const int32_t* 
     for (int i = 0; i < n; i++)
     {
         if (!slotOk(c, slots[i]) || outs[i] < 0 || outs[i] >= c->geom.n_cost_stores) return X265CU_ERR_BAD_ARG;
-        int st = mainWaitCost(c, slots[i], outs[i]);
+        int st = outs[i] < 2 ? X265CU_OK : streamWaitBatch(c, c->gatherStream, c->costWriter[(size_t)slots[i] * c->geom.n_cost_stores + outs[i]], false);
         if (st) return st;
         srcs[i] = costStorePtr(c, slots[i], outs[i]) + c->lay.costResOff;
     }
@@ -1758,16 +1791,6 @@ __global__ void unpack_mv_kernel(const int* __restrict__ src, int* __restrict__ 
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const int p = src[i]; dst[2 * i] = (int)(short)(p & 0xffff); dst[2 * i + 1] = p >> 16; }
-}
-
-/* `st` waits for batch `id` (its searches only, or all of it) */
-static int streamWaitBatch(x265cu_ctx* c, cudaStream_t st, long long id, bool searchesOnly)
-{
-    Batch* w = batchOf(c, id);
-    if (!w) return X265CU_OK;
-    if (w->open) { int rc = endBatch(c); if (rc) return rc; }
-    CK(cudaStreamWaitEvent(st, searchesOnly ? w->searchDone : w->done, 0));
-    return X265CU_OK;
 }
 
 struct UnpackTab { const int* src[X265CU_MIRROR_MAX_MV]; int* dst[X265CU_MIRROR_MAX_MV]; };

@@ -290,7 +290,7 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     if (m_param.speculate)
     {
         m_pendingSpec.push_back(f);
-        if (m_param.speculate == 1 && m_param.shardCount <= 1 && (int)m_pendingSpec.size() >= m_param.batchMin)
+        if (m_param.speculate == 1 && m_param.shardCount <= 1 && (int)m_pendingSpec.size() >= std::min(m_param.batchMin, 4))
         {
             /* per-decision mode, window still filling (or the host far ahead of the GPU): hand the frames whose
              * pre-lookahead has finished to the GPU in launches of batchMin frames instead of one launch at the first decision */
@@ -604,17 +604,23 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
      * up and draining) */
     if (m_param.speculate == 1 && !m_pendingSpec.empty() && m_pendingSpec.front()->m_poc > mustPoc)
     {
-        if ((int)m_pendingSpec.size() < m_param.batchMin)
+        /* ... unless the GPU has nothing left to do (pictures arrive slower than it consumes them): then a smaller launch
+         * now beats a full one later.  A sharded stream must batch the same frames on every rank, so it never asks. */
+        const int minFrames = std::min(m_param.batchMin, 4);
+        const bool idle = m_param.shardCount <= 1 && (int)m_pendingSpec.size() >= minFrames && (int)m_pendingSpec.size() < m_param.batchMin &&
+                          x265cu_batches_in_flight(m_ctx) == 0;
+        const int want = idle ? minFrames : m_param.batchMin;
+        if ((int)m_pendingSpec.size() < want)
             return;
         if (needStats && m_param.shardCount <= 1)
         {
             /* ... and with weightp only frames whose pixel sums are on the host (pre-lookahead finished) can be taken without
-             * stalling: wait until batchMin of them are */
+             * stalling: wait until enough of them are */
             int ready = 0;
-            for (size_t i = 0; i < m_pendingSpec.size() && ready < m_param.batchMin; i++, ready++)
+            for (size_t i = 0; i < m_pendingSpec.size() && ready < want; i++, ready++)
                 if (!m_pendingSpec[i]->m_lowresInit && x265cu_frame_ready(m_ctx, m_pendingSpec[i]->m_lowres.slot) != 1)
                     break;
-            if (ready < m_param.batchMin && m_pendingSpec.size() <= keep)
+            if (ready < want && m_pendingSpec.size() <= keep)
                 return;
         }
     }
