@@ -234,8 +234,8 @@ class Stream:
         if self.mirror:
             # two sets of page-locked destination buffers: the mirror of frame i lands while frame i + 1 is decided
             ncu, nf, bpp, nb = g.ncu, g.ncu_full, 2 if wl["depth"] > 8 else 1, g.nb
-            self.sets, self.tickets, self.nmir = [], [None, None], 0
-            for _ in range(2):
+            self.sets, self.tickets, self.nmir = [], [None] * 4, 0
+            for _ in range(4):
                 b = dict(qpAq=np.zeros(nf, np.float64), qpCt=np.zeros(nf, np.float64), invQ=np.zeros(nf, np.int32),
                          intra=np.zeros(ncu, np.int32), lc=np.zeros(ncu, np.uint16), rs=np.zeros(g.bh, np.int32),
                          mv=np.zeros((2, nb, ncu, 2), np.int32),
@@ -260,9 +260,10 @@ class Stream:
         self.fed += 1
         return True
 
-    def drain(self):
+    def drain(self, limit=1 << 30):
+        """take up to `limit` decided frames (Encoder::encode takes one per picture it adds, encoder.cpp:2130)"""
         la = self.la
-        while True:
+        for _ in range(limit):
             info = la.get_decided()
             if info is None:
                 return
@@ -273,7 +274,7 @@ class Stream:
             if self.mirror:
                 # what Encoder::encode / RateControl / the frame encoder / search / weightPrediction read of a decided frame
                 # (SURVEY 8b "output contract"): the same requests the ENABLE_CUDA Lookahead shim makes (integration/)
-                k = self.nmir & 1
+                k = self.nmir & 3
                 b, m = self.sets[k]
                 if self.tickets[k] is not None:
                     la.lib.x265la_mirror_wait(la.h, self.tickets[k])
@@ -335,7 +336,7 @@ def run_step(eng, streams, dist=None, shard=None, profile=True):
         for s in streams:
             if s.feed():
                 more = True
-                s.drain()
+                s.drain(1)
     for s in streams:
         s.la.flush()
         s.drain()
@@ -658,8 +659,8 @@ def main():
                         "(SURVEY 8d); the HBM fraction is the conservative checkable figure, profiles/ holds the pipe utilisation"}
 
     line = {"metric": "lookahead_frames_per_s", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u16" if depth > 8 else "u8", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "ms_steps": [round(t, 1) for t in res["times"]],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if depth > 8 else "u8", "data": "synthetic",
             "config": {"workload": wl["text"], "frames_per_step": F, "resolution": "%dx%d" % (W, H), "bit_depth": depth,
                        "lookahead_slices": 0, "pool_workers": cores, "async_depth": args.async_depth, "speculate": args.speculate,
                        "sm_partition": "%d SMs for cuTree / recalc / mirrors, %d for the search and cost batches (CUDA green contexts)"
@@ -667,6 +668,7 @@ def main():
                        "streams": world, "parallelism": "independent stream per GPU" if world > 1 else "1 GPU",
                        "l2_policy": "inputs larger than L2: %d MB of pictures per step vs 126 MB L2" % (F * res["bytes_in"] // (1 << 20))},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "ms_per_step": round(e2e_ms, 3), "skipped": bool(args.no_e2e),
+                    "ms_steps": [round(t, 1) for t in res["e2e_times"]],
                     "h2d_bytes_per_step": int(res["e2e_delta"]["h2d"]), "d2h_bytes_per_step": int(res["e2e_delta"]["d2h"]),
                     "d2h": "per decided frame, one asynchronous mirror request into page-locked buffers: getEstimatedPictureCost, qpAqOffset, "
                            "qpCuTreeOffset, invQscaleFactor, intraCost, the coded estimate's lowresCosts + rowSatds, EVERY published "

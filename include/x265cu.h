@@ -246,7 +246,7 @@ int  x265cu_fetch_costs(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, uint1
  * (x265cu_pin_host) -- pageable ones make the enqueue itself wait for the copies.  At most X265CU_MIRROR_RING requests are in
  * flight; an older one is waited for when the ring wraps. */
 #define X265CU_MIRROR_MAX_MV 36
-#define X265CU_MIRROR_RING   4
+#define X265CU_MIRROR_RING   8
 typedef struct
 {
     int32_t*  intra_cost;        /* ncu, or NULL */

@@ -118,6 +118,7 @@ struct x265cu_ctx
     std::vector<int> slotOwner;
     std::vector<std::pair<char*, size_t> > xpool;    /* free exchange buffers */
     int searchWorkers;              /* worker warps per search job; 0 = default (env X265CU_SEARCH_WORKERS, for tuning) */
+    int numSMs;
     int searchSmem;                 /* dynamic shared memory per search CTA (env X265CU_SEARCH_SMEM, bytes): residency cap */
     bool profile;
     double profMs[X265CU_K_COUNT], profBusy[X265CU_K_COUNT];
@@ -617,15 +618,15 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     const bool chroma = u && v;
     if (chroma && c->cfg.need_aq)
     {
-        if (sc == g.cW)
+        if (sc == g.cW && g.srcPitchC == g.cW)
         {
             CK(cudaMemcpyAsync(dU, u, (size_t)g.cW * g.cH * sizeof(P), cudaMemcpyDefault, c->copyStream));
             CK(cudaMemcpyAsync(dV, v, (size_t)g.cW * g.cH * sizeof(P), cudaMemcpyDefault, c->copyStream));
         }
         else
         {
-            CK(cudaMemcpy2DAsync(dU, g.cW * sizeof(P), u, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
-            CK(cudaMemcpy2DAsync(dV, g.cW * sizeof(P), v, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
+            CK(cudaMemcpy2DAsync(dU, g.srcPitchC * sizeof(P), u, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
+            CK(cudaMemcpy2DAsync(dV, g.srcPitchC * sizeof(P), v, (size_t)sc * sizeof(P), g.cW * sizeof(P), g.cH, cudaMemcpyDefault, c->copyStream));
         }
         c->counters.h2d_bytes += 2ull * g.cW * g.cH * sizeof(P);
     }
@@ -670,7 +671,9 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     {
         /* K1 + K2a fused: lowres planes and (qg-size > 8) the 16x16 AC energies / weightp sums in one pass over the luma */
         Prof pr(c, X265CU_K_LOWRES, 2, ps);
-        const dim3 grid((g.bw + LA_LR_TILES - 1) / LA_LR_TILES, g.bh);
+        /* persistent CTAs: LA_LR_CTAS_PER_SM per SM, each walking groups of LA_LR_TILES tiles with a ring of staged copies */
+        const int groups = (g.bw + LA_LR_TILES - 1) / LA_LR_TILES * g.bh;
+        const int grid = std::min(groups, c->numSMs * LA_LR_CTAS_PER_SM);
         lowres_fused_kernel<P><<<grid, 32 * LA_LR_TILES, 0, ps>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, planes, energy, stats,
                                                                   c->cfg.need_aq && !qg8);
         const long long tileRows = 4LL * g.tpr * g.planeLines;
@@ -1098,6 +1101,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->searchSmem = getenv("X265CU_SEARCH_SMEM") ? atoi(getenv("X265CU_SEARCH_SMEM")) : 0;
+    c->numSMs = 148;
+    cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, cfg->device);
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
     c->rank = 0; c->nranks = 1; c->exchange = NULL; c->exchangeUser = NULL;
     c->mirrorStream = NULL; c->gatherStream = NULL; c->mirrorMark = NULL; c->nextMirror = 0; c->d_recalc = c->h_recalc = NULL; c->recalcStride = 0;
@@ -1118,7 +1123,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     /* geometry: Lowres::create (lowres.cpp:72-97) */
     Geom& g = c->g;
     g.picW = cfg->width; g.picH = cfg->height; g.cW = (cfg->width + 1) / 2; g.cH = (cfg->height + 1) / 2;
-    g.srcPitch = (g.picW + 15) / 16 * 16;
+    g.srcPitch = (g.picW + 15) / 16 * 16; g.srcPitchC = (g.cW + 15) / 16 * 16;
     const int lw = cfg->width / 2, lh = cfg->height / 2;
     g.mx = cfg->max_cu_size + 32; g.my = cfg->max_cu_size + 16;
     g.stride = lw + 2 * g.mx;
@@ -1146,8 +1151,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     size_t o = 0;
 #define SECTION(name, bytes) L.name = o; o = alignUp(o + (bytes), 256)
     SECTION(srcY, (size_t)g.srcPitch * g.picH * c->bpp + 1024);     /* + slack: K1's row copies may run past the last row's end */
-    SECTION(srcU, (size_t)g.cW * g.cH * c->bpp + 64);
-    SECTION(srcV, (size_t)g.cW * g.cH * c->bpp + 64);
+    SECTION(srcU, (size_t)g.srcPitchC * g.cH * c->bpp + 512);
+    SECTION(srcV, (size_t)g.srcPitchC * g.cH * c->bpp + 512);
     SECTION(planes, (size_t)(4 * g.planeSize) * c->bpp + 256);
     SECTION(intraCost, (size_t)g.ncu * 4);
     SECTION(intraMode, (size_t)g.ncu);

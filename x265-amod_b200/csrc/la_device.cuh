@@ -33,8 +33,8 @@ namespace la {
 struct Geom
 {
     int picW, picH, cW, cH;     /* full-res luma / chroma size */
-    int srcPitch;               /* samples per row of the staged full-res luma: picW rounded up to 16 (rows 16-byte aligned for
-                                   the bulk copies of K1); the chroma planes are packed at cW */
+    int srcPitch, srcPitchC;    /* samples per row of the staged full-res luma / chroma planes: picW / cW rounded up to 16, so
+                                   that every row starts 16-byte aligned for the bulk copies of K1 */
     int w, h, bw, bh, ncu;      /* lowres plane size and 8x8 grid */
     int mx, my, stride, planeLines;
     long long planeSize, padOffset;

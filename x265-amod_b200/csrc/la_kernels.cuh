@@ -23,69 +23,25 @@ struct CostResultDev            /* mirrors x265cu_cost_result */
     int intraMbs, reserved;
 };
 
-/* sums / sums of squares for the AC energies (pixel_var, pixel.cpp:720-737) */
-template <typename P>
-__device__ __forceinline__ void warpVar(const P* __restrict__ p, int stride, int W, int H, int bx, int by, int size,
-                                        unsigned& sum, unsigned& sqr)
-{
-    sum = 0; sqr = 0;
-    const int lane = threadIdx.x & 31;
-    const int n = size * size;
-    for (int i = lane; i < n; i += 32)
-    {
-        const int x = min(bx + (i % size), W - 1), y = min(by + (i / size), H - 1);
-        const unsigned v = __ldg(p + (long long)y * stride + x);
-        sum += v; sqr += v * v;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1)
-    {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sqr += __shfl_xor_sync(0xffffffffu, sqr, o);
-    }
-}
-
-/* 8 consecutive samples with one vector load (the caller guarantees the alignment), summed and square-summed */
-__device__ __forceinline__ void sumSqr8(const uint8_t* p, unsigned& sum, unsigned& sqr)
-{
-    const uint2 v = __ldg((const uint2*)p);
-    const unsigned w[2] = { v.x, v.y };
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-    {
-        sum += __vsadu4(w[i], 0);
-        sqr = __dp4a(w[i], w[i], sqr);
-    }
-}
-__device__ __forceinline__ void sumSqr8(const uint16_t* p, unsigned& sum, unsigned& sqr)
-{
-    const uint4 v = __ldg((const uint4*)p);
-    const unsigned w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-    {
-        const unsigned lo = w[i] & 0xffffu, hi = w[i] >> 16;
-        sum += lo + hi;
-        sqr += lo * lo + hi * hi;
-    }
-}
-
 /* ------------------------------------------------------------------------------------------
- * K1 (+ K2a): ONE streaming pass over the full-res luma produces the four half-pel lowres planes
+ * K1 (+ K2a): ONE streaming pass over the full-res picture produces the four half-pel lowres planes
  * (frame_init_lowres_core, pixel.cpp:605-628) AND the 16x16 AC energies + weightp sums of calcAdaptiveQuantFrame
  * (acEnergyCu / acEnergyPlane / pixel_var, slicetype.cpp:49-84,264-283, pixel.cpp:720-737), so the picture is read from
- * HBM once.  HBM-bound: reads F (+ 0.5 F chroma for the energies), writes 4 P.
+ * HBM once.  HBM-bound: reads 1.5 F, writes 4 P.
  *
- * A CTA owns LA_LR_TILES lowres tiles side by side (64 x 8 lowres samples = 128 x 16 source samples = exactly the
- * 16x16 AQ blocks of those tiles) and stages its 17 source rows x 129 columns in shared memory with one BULK ASYNC COPY per
- * row (cp.async.bulk global -> shared, completion on an mbarrier: SASS UBLKCP), issued by one thread; nobody touches
- * global memory for luma afterwards.  Replicate clamping = PicYuv's padding (picyuv.cpp:261-285) is done once per tile:
- * vertically by pointing the copy of a row beyond the picture at the last row, horizontally by a fix-up of the staged
- * columns in the right-most CTAs only.  A warp owns a tile: lane (y, q) produces samples 2q, 2q+1 of row y of all four planes
- * from packed shared-memory words -- FILTER(a,b,c,d) = avg(avg(a,b), avg(c,d)) with avg = (x + y + 1) >> 1 is two packed
- * average steps -- and the warp's 32 words are one contiguous tile in the tiled plane layout (la_device.cuh): full-line
- * stores.  The same lane holds a 2 x 4 piece of the tile's 16x16 source block, so the block's sum / sum of squares are a
- * warp reduction of values already in registers.  The plane margins are written by extend_border_kernel.
+ * Persistent CTAs, one per SM slot, walk the frame in GROUPS of LA_LR_TILES lowres tiles side by side (64 x 8 lowres
+ * samples = 128 x 16 luma samples = exactly the 16x16 AQ blocks of those tiles, + their 64 x 8 U and V samples).  A group's
+ * 17 luma rows x 129 columns and 2 x 8 chroma rows are staged in shared memory by BULK ASYNC COPIES (cp.async.bulk global ->
+ * shared, one per row, completion counted on an mbarrier: SASS UBLKCP), issued by one thread LA_LR_STAGES groups ahead of
+ * the group being processed: a ring of stages keeps several KB per CTA in flight, which is what a streaming kernel needs to
+ * fill HBM, and nobody touches global memory for pixels afterwards.  Replicate clamping = PicYuv's padding (picyuv.cpp:
+ * 261-285) is done once per group: vertically by pointing the copy of a row beyond the picture at the last row, horizontally
+ * by a fix-up of the staged columns in the right-most groups only.  A warp owns a tile: lane (y, q) produces samples 2q, 2q+1
+ * of row y of all four planes from packed shared-memory words -- FILTER(a,b,c,d) = avg(avg(a,b), avg(c,d)) with
+ * avg = (x + y + 1) >> 1 is two packed average steps -- and the warp's 32 words are one contiguous tile of the tiled plane
+ * layout (la_device.cuh): full-line stores.  The same lane holds a 2 x 4 piece of the tile's 16x16 source block, so the
+ * block's sum / sum of squares are a warp reduction of values already in registers; lanes 0-15 add a staged chroma row each.
+ * The plane margins are written by extend_border_kernel.
  * ------------------------------------------------------------------------------------------ */
 template <typename P> struct Vec4;
 template <> struct Vec4<uint8_t>  { typedef uchar4 T; };
@@ -93,6 +49,9 @@ template <> struct Vec4<uint16_t> { typedef ushort4 T; };
 
 #define LA_LR_TILES 8
 #define LA_LR_ROW_SAMPLES 144           /* 129 needed; 144 samples = 144 / 288 bytes, a multiple of 16 for both sample sizes */
+#define LA_LR_CROW_SAMPLES 64           /* chroma samples per staged row: 8 per tile */
+#define LA_LR_STAGES 3
+#define LA_LR_CTAS_PER_SM 5
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,176 +59,243 @@ __device__ __forceinline__ uint32_t avgPacked(uint32_t a, uint32_t b, uint8_t)  
 /* 16-bit samples below 2^15: the two halves cannot carry into each other */
 __device__ __forceinline__ uint32_t avgPacked(uint32_t a, uint32_t b, uint16_t) { return ((a + b + 0x00010001u) >> 1) & 0x7fff7fffu; }
 
+/* sum / sum of squares of 8 staged samples at p (16-byte aligned for 16-bit samples, 8-byte for 8-bit) */
+__device__ __forceinline__ void sumSqr8s(const uint8_t* p, unsigned& sum, unsigned& sqr)
+{
+    const uint2 v = *(const uint2*)p;
+    sum = __vsadu4(v.x, 0) + __vsadu4(v.y, 0);
+    sqr = __dp4a(v.x, v.x, __dp4a(v.y, v.y, 0u));
+}
+__device__ __forceinline__ void sumSqr8s(const uint16_t* p, unsigned& sum, unsigned& sqr)
+{
+    const uint4 v = *(const uint4*)p;
+    const unsigned w[4] = { v.x, v.y, v.z, v.w };
+    sum = 0; sqr = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const unsigned lo = w[i] & 0xffffu, hi = w[i] >> 16;
+        sum += lo + hi; sqr += lo * lo + hi * hi;
+    }
+}
+
 template <typename P>
-__global__ void __launch_bounds__(32 * LA_LR_TILES) lowres_fused_kernel(Geom g, const P* __restrict__ srcY, const P* __restrict__ srcU,
-                                                                        const P* __restrict__ srcV, P* __restrict__ planes,
-                                                                        unsigned* __restrict__ energy, FrameStatsDev* stats, int doEnergy)
+__global__ void __launch_bounds__(32 * LA_LR_TILES, LA_LR_CTAS_PER_SM)
+lowres_fused_kernel(Geom g, const P* __restrict__ srcY, const P* __restrict__ srcU, const P* __restrict__ srcV, P* __restrict__ planes,
+                    unsigned* __restrict__ energy, FrameStatsDev* stats, int doEnergy)
 {
     constexpr int SPP = (int)sizeof(P);
     constexpr int ROW_BYTES = LA_LR_ROW_SAMPLES * SPP;
-    __shared__ __align__(128) unsigned char s_src[17 * ROW_BYTES];
-    __shared__ __align__(8) unsigned long long s_bar;
+    constexpr int CROW_BYTES = LA_LR_CROW_SAMPLES * SPP;
+    constexpr int STAGE_BYTES = 17 * ROW_BYTES + 16 * CROW_BYTES;
+    __shared__ __align__(128) unsigned char s_stage[LA_LR_STAGES][STAGE_BYTES];
+    __shared__ __align__(8) unsigned long long s_bar[LA_LR_STAGES];
     __shared__ unsigned long long s_acc[6];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ty = blockIdx.y;                      /* lowres tile row = 16 source rows */
-    const int c0 = blockIdx.x * 16 * LA_LR_TILES;   /* first source column of this CTA */
-    const int copySamples = min(LA_LR_ROW_SAMPLES, g.srcPitch - c0);       /* a multiple of 16 samples */
-    const uint32_t bar = smemAddr(&s_bar);
-    if (tid == 0)
+    const int groupsX = (g.bw + LA_LR_TILES - 1) / LA_LR_TILES;
+    const int total = groupsX * g.bh;
+    const bool chroma = doEnergy && srcU != NULL;
+
+    /* one thread arms stage `st` for group `gid` and issues its row copies */
+    auto issue = [&](int gid, int st)
     {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (tid < 6) s_acc[tid] = 0;
-    __syncthreads();
-    if (tid == 0)
-    {
-        const uint32_t bytes = (uint32_t)(copySamples * SPP);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 17u) : "memory");
+        const int gx = gid % groupsX, ty = gid / groupsX;
+        const int c0 = gx * 16 * LA_LR_TILES;
+        const uint32_t bar = smemAddr(&s_bar[st]);
+        const uint32_t lumaBytes = (uint32_t)(min(LA_LR_ROW_SAMPLES, g.srcPitch - c0) * SPP);
+        const int cc0 = gx * LA_LR_CROW_SAMPLES;
+        const uint32_t chromaBytes = chroma ? (uint32_t)(min(LA_LR_CROW_SAMPLES, g.srcPitchC - cc0) * SPP) : 0u;
+        /* the stage was read (and, at the picture's right edge, patched) through the generic proxy: order that before the
+         * asynchronous proxy writes into it again */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(lumaBytes * 17u + chromaBytes * 16u) : "memory");
+        unsigned char* dst = s_stage[st];
 #pragma unroll 1
         for (int r = 0; r < 17; r++)
         {
             const P* src = srcY + (long long)min(16 * ty + r, g.picH - 1) * g.srcPitch + c0;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smemAddr(s_src + r * ROW_BYTES)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                         ::"r"(smemAddr(dst + r * ROW_BYTES)), "l"(src), "r"(lumaBytes), "r"(bar) : "memory");
         }
-    }
-    /* everybody waits for the 17 rows (phase 0 of the barrier) */
-    {
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(bar) : "memory");
-    }
-    /* columns at and beyond the picture's right edge replicate its last column (right-most CTAs only) */
-    const int valid = g.picW - c0;
-    if (valid < 16 * LA_LR_TILES + 1)
-    {
-        P* sp = (P*)s_src;
-        for (int i = tid; i < 17 * LA_LR_ROW_SAMPLES; i += 32 * LA_LR_TILES)
+        if (chroma)
         {
-            const int r = i / LA_LR_ROW_SAMPLES, x = i % LA_LR_ROW_SAMPLES;
-            if (x >= valid && x <= 16 * LA_LR_TILES) sp[r * LA_LR_ROW_SAMPLES + x] = sp[r * LA_LR_ROW_SAMPLES + valid - 1];
+#pragma unroll 1
+            for (int r = 0; r < 16; r++)
+            {
+                const P* src = (r < 8 ? srcU : srcV) + (long long)min(8 * ty + (r & 7), g.cH - 1) * g.srcPitchC + cc0;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smemAddr(dst + 17 * ROW_BYTES + r * CROW_BYTES)), "l"(src), "r"(chromaBytes), "r"(bar) : "memory");
+            }
         }
-        __syncthreads();
-    }
-    const int tx = blockIdx.x * LA_LR_TILES + warp;
-    if (tx < g.bw)
+    };
+
+    if (tid == 0)
     {
-        const int y = lane >> 2, q = lane & 3;
-        /* this lane's 3 source rows x 5 samples, starting at sample 16 * warp + 4 q of staged rows 2y .. 2y + 2 */
-        const unsigned char* base = s_src + (2 * y) * ROW_BYTES + (16 * warp + 4 * q) * SPP;
-        uint32_t o0, o1, o2, o3;        /* this lane's two samples of the planes (0,0), (h,0), (0,v), (h,v) */
-        unsigned sum, sqr;
-        if (SPP == 2)
+#pragma unroll
+        for (int st = 0; st < LA_LR_STAGES; st++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&s_bar[st])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 6) s_acc[tid] = 0;
+    __syncthreads();
+    if (tid == 0)
+        for (int st = 0; st < LA_LR_STAGES; st++)
         {
-            uint32_t r[3][3];
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-            {
-                const uint2 v = *(const uint2*)(base + k * ROW_BYTES);
-                r[k][0] = v.x; r[k][1] = v.y; r[k][2] = *(const unsigned short*)(base + k * ROW_BYTES + 8);
-            }
-            uint32_t A[2][3];
-#pragma unroll
-            for (int j = 0; j < 3; j++) { A[0][j] = avgPacked(r[0][j], r[1][j], (P)0); A[1][j] = avgPacked(r[1][j], r[2][j], (P)0); }
-            uint32_t t[2][2];
-#pragma unroll
-            for (int v = 0; v < 2; v++)
-            {
-                t[v][0] = avgPacked(A[v][0], __funnelshift_r(A[v][0], A[v][1], 16), (P)0);
-                t[v][1] = avgPacked(A[v][1], __funnelshift_r(A[v][1], A[v][2], 16), (P)0);
-            }
-            o0 = __byte_perm(t[0][0], t[0][1], 0x5410); o1 = __byte_perm(t[0][0], t[0][1], 0x7632);
-            o2 = __byte_perm(t[1][0], t[1][1], 0x5410); o3 = __byte_perm(t[1][0], t[1][1], 0x7632);
-            sum = 0; sqr = 0;
-#pragma unroll
-            for (int k = 0; k < 2; k++)
-#pragma unroll
-                for (int j = 0; j < 2; j++)
+            const int gid = blockIdx.x + st * gridDim.x;
+            if (gid < total) issue(gid, st);
+        }
+
+    int it = 0;
+    for (int gid = blockIdx.x; gid < total; gid += gridDim.x, it++)
+    {
+        const int st = it % LA_LR_STAGES;
+        const uint32_t parity = (uint32_t)((it / LA_LR_STAGES) & 1);
+        {
+            const uint32_t bar = smemAddr(&s_bar[st]);
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+        const int gx = gid % groupsX, ty = gid / groupsX;
+        unsigned char* s_src = s_stage[st];
+        /* columns at and beyond the picture's right edge replicate its last column (right-most groups only) */
+        const int valid = g.picW - gx * 16 * LA_LR_TILES;
+        const int cvalid = g.cW - gx * LA_LR_CROW_SAMPLES;
+        if (valid < 16 * LA_LR_TILES + 1 || (chroma && cvalid < LA_LR_CROW_SAMPLES))
+        {
+            P* sp = (P*)s_src;
+            if (valid < 16 * LA_LR_TILES + 1)
+                for (int i = tid; i < 17 * LA_LR_ROW_SAMPLES; i += 32 * LA_LR_TILES)
                 {
-                    const unsigned lo = r[k][j] & 0xffffu, hi = r[k][j] >> 16;
-                    sum += lo + hi; sqr += lo * lo + hi * hi;
+                    const int r = i / LA_LR_ROW_SAMPLES, x = i % LA_LR_ROW_SAMPLES;
+                    if (x >= valid && x <= 16 * LA_LR_TILES) sp[r * LA_LR_ROW_SAMPLES + x] = sp[r * LA_LR_ROW_SAMPLES + valid - 1];
                 }
-        }
-        else
-        {
-            uint32_t r[3][2];
-#pragma unroll
-            for (int k = 0; k < 3; k++)
+            if (chroma && cvalid < LA_LR_CROW_SAMPLES)
             {
-                r[k][0] = *(const uint32_t*)(base + k * ROW_BYTES);
-                r[k][1] = *(const unsigned char*)(base + k * ROW_BYTES + 4);
-            }
-            uint32_t t[2];
-#pragma unroll
-            for (int v = 0; v < 2; v++)
-            {
-                const uint32_t A0 = avgPacked(r[v][0], r[v + 1][0], (P)0), A1 = avgPacked(r[v][1], r[v + 1][1], (P)0);
-                t[v] = avgPacked(A0, __funnelshift_r(A0, A1, 8), (P)0);
-            }
-            o0 = __byte_perm(t[0], 0, 0x0020); o1 = __byte_perm(t[0], 0, 0x0031);
-            o2 = __byte_perm(t[1], 0, 0x0020); o3 = __byte_perm(t[1], 0, 0x0031);
-            sum = __vsadu4(r[0][0], 0) + __vsadu4(r[1][0], 0);
-            sqr = __dp4a(r[0][0], r[0][0], __dp4a(r[1][0], r[1][0], 0u));
-        }
-        /* the warp's 32 x 2 samples are one whole tile of each plane, contiguous in the tiled layout */
-        const long long tileBase = tileOff(g.mx + 8 * tx, g.my + 8 * ty, g.tpr);
-        if (SPP == 2)
-        {
-            uint32_t* d = (uint32_t*)(planes + tileBase) + lane;
-            const long long ps = g.planeSize >> 1;      /* plane stride in 32-bit words */
-            d[0] = o0; d[ps] = o1; d[2 * ps] = o2; d[3 * ps] = o3;
-        }
-        else
-        {
-            unsigned short* d = (unsigned short*)(planes + tileBase) + lane;
-            const long long ps = g.planeSize >> 1;      /* plane stride in 16-bit units */
-            d[0] = (unsigned short)o0; d[ps] = (unsigned short)o1; d[2 * ps] = (unsigned short)o2; d[3 * ps] = (unsigned short)o3;
-        }
-        if (doEnergy)
-        {
-#pragma unroll
-            for (int o = 16; o; o >>= 1)
-            {
-                sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                sqr += __shfl_xor_sync(0xffffffffu, sqr, o);
-            }
-            unsigned e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
-            if (lane == 0) { atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr); }
-            if (srcU)
-            {
-                /* the co-located 8x8 chroma blocks: lanes 0-7 / 8-15 = rows of the U / V block */
-                const int bx = 8 * tx, by = 8 * ty;
-                const bool vecOk = ((g.cW * SPP) & (8 * SPP - 1)) == 0 && bx + 8 <= g.cW && by + 8 <= g.cH;
-                unsigned us, uq, vs, vq;
-                if (vecOk)
+                P* cp = (P*)(s_src + 17 * ROW_BYTES);
+                for (int i = tid; i < 16 * LA_LR_CROW_SAMPLES; i += 32 * LA_LR_TILES)
                 {
-                    unsigned cs = 0, cq = 0;
-                    if (lane < 16) sumSqr8((lane < 8 ? srcU : srcV) + (long long)(by + (lane & 7)) * g.cW + bx, cs, cq);
+                    const int r = i / LA_LR_CROW_SAMPLES, x = i % LA_LR_CROW_SAMPLES;
+                    if (x >= cvalid) cp[r * LA_LR_CROW_SAMPLES + x] = cp[r * LA_LR_CROW_SAMPLES + cvalid - 1];
+                }
+            }
+            __syncthreads();
+        }
+        const int tx = gx * LA_LR_TILES + warp;
+        if (tx < g.bw)
+        {
+            const int y = lane >> 2, q = lane & 3;
+            /* this lane's 3 source rows x 5 samples, starting at sample 16 * warp + 4 q of staged rows 2y .. 2y + 2 */
+            const unsigned char* base = s_src + (2 * y) * ROW_BYTES + (16 * warp + 4 * q) * SPP;
+            uint32_t o0, o1, o2, o3;        /* this lane's two samples of the planes (0,0), (h,0), (0,v), (h,v) */
+            unsigned sum, sqr;
+            if (SPP == 2)
+            {
+                uint32_t r[3][3];
 #pragma unroll
-                    for (int o = 4; o; o >>= 1)
+                for (int k = 0; k < 3; k++)
+                {
+                    const uint2 v = *(const uint2*)(base + k * ROW_BYTES);
+                    r[k][0] = v.x; r[k][1] = v.y; r[k][2] = *(const unsigned short*)(base + k * ROW_BYTES + 8);
+                }
+                uint32_t A[2][3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) { A[0][j] = avgPacked(r[0][j], r[1][j], (P)0); A[1][j] = avgPacked(r[1][j], r[2][j], (P)0); }
+                uint32_t t[2][2];
+#pragma unroll
+                for (int v = 0; v < 2; v++)
+                {
+                    t[v][0] = avgPacked(A[v][0], __funnelshift_r(A[v][0], A[v][1], 16), (P)0);
+                    t[v][1] = avgPacked(A[v][1], __funnelshift_r(A[v][1], A[v][2], 16), (P)0);
+                }
+                o0 = __byte_perm(t[0][0], t[0][1], 0x5410); o1 = __byte_perm(t[0][0], t[0][1], 0x7632);
+                o2 = __byte_perm(t[1][0], t[1][1], 0x5410); o3 = __byte_perm(t[1][0], t[1][1], 0x7632);
+                sum = 0; sqr = 0;
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
                     {
-                        cs += __shfl_xor_sync(0xffffffffu, cs, o);
-                        cq += __shfl_xor_sync(0xffffffffu, cq, o);
+                        const unsigned lo = r[k][j] & 0xffffu, hi = r[k][j] >> 16;
+                        sum += lo + hi; sqr += lo * lo + hi * hi;
                     }
-                    us = __shfl_sync(0xffffffffu, cs, 0); uq = __shfl_sync(0xffffffffu, cq, 0);
-                    vs = __shfl_sync(0xffffffffu, cs, 8); vq = __shfl_sync(0xffffffffu, cq, 8);
-                }
-                else
+            }
+            else
+            {
+                uint32_t r[3][2];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
                 {
-                    warpVar(srcU, g.cW, g.cW, g.cH, bx, by, 8, us, uq);
-                    warpVar(srcV, g.cW, g.cW, g.cH, bx, by, 8, vs, vq);
+                    r[k][0] = *(const uint32_t*)(base + k * ROW_BYTES);
+                    r[k][1] = *(const unsigned char*)(base + k * ROW_BYTES + 4);
                 }
-                e += uq - (unsigned)(((unsigned long long)us * us) >> 6);
-                e += vq - (unsigned)(((unsigned long long)vs * vs) >> 6);
+                uint32_t t[2];
+#pragma unroll
+                for (int v = 0; v < 2; v++)
+                {
+                    const uint32_t A0 = avgPacked(r[v][0], r[v + 1][0], (P)0), A1 = avgPacked(r[v][1], r[v + 1][1], (P)0);
+                    t[v] = avgPacked(A0, __funnelshift_r(A0, A1, 8), (P)0);
+                }
+                o0 = __byte_perm(t[0], 0, 0x0020); o1 = __byte_perm(t[0], 0, 0x0031);
+                o2 = __byte_perm(t[1], 0, 0x0020); o3 = __byte_perm(t[1], 0, 0x0031);
+                sum = __vsadu4(r[0][0], 0) + __vsadu4(r[1][0], 0);
+                sqr = __dp4a(r[0][0], r[0][0], __dp4a(r[1][0], r[1][0], 0u));
+            }
+            /* the warp's 32 x 2 samples are one whole tile of each plane, contiguous in the tiled layout */
+            const long long tileBase = tileOff(g.mx + 8 * tx, g.my + 8 * ty, g.tpr);
+            if (SPP == 2)
+            {
+                uint32_t* d = (uint32_t*)(planes + tileBase) + lane;
+                const long long ps = g.planeSize >> 1;      /* plane stride in 32-bit words */
+                d[0] = o0; d[ps] = o1; d[2 * ps] = o2; d[3 * ps] = o3;
+            }
+            else
+            {
+                unsigned short* d = (unsigned short*)(planes + tileBase) + lane;
+                const long long ps = g.planeSize >> 1;      /* plane stride in 16-bit units */
+                d[0] = (unsigned short)o0; d[ps] = (unsigned short)o1; d[2 * ps] = (unsigned short)o2; d[3 * ps] = (unsigned short)o3;
+            }
+            if (doEnergy)
+            {
+                /* lanes 0-7 / 8-15 add a row of the tile's co-located 8x8 U / V block */
+                unsigned cs = 0, cq = 0;
+                if (chroma && lane < 16)
+                    sumSqr8s((const P*)(s_src + 17 * ROW_BYTES + lane * CROW_BYTES) + 8 * warp, cs, cq);
+#pragma unroll
+                for (int o = 16; o; o >>= 1)
+                {
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    sqr += __shfl_xor_sync(0xffffffffu, sqr, o);
+                }
+#pragma unroll
+                for (int o = 4; o; o >>= 1)
+                {
+                    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                    cq += __shfl_xor_sync(0xffffffffu, cq, o);
+                }
+                const unsigned us = __shfl_sync(0xffffffffu, cs, 0), uq = __shfl_sync(0xffffffffu, cq, 0);
+                const unsigned vs = __shfl_sync(0xffffffffu, cs, 8), vq = __shfl_sync(0xffffffffu, cq, 8);
                 if (lane == 0)
                 {
-                    atomicAdd(&s_acc[1], (unsigned long long)us); atomicAdd(&s_acc[4], (unsigned long long)uq);
-                    atomicAdd(&s_acc[2], (unsigned long long)vs); atomicAdd(&s_acc[5], (unsigned long long)vq);
+                    unsigned e = sqr - (unsigned)(((unsigned long long)sum * sum) >> 8);
+                    atomicAdd(&s_acc[0], (unsigned long long)sum); atomicAdd(&s_acc[3], (unsigned long long)sqr);
+                    if (chroma)
+                    {
+                        e += uq - (unsigned)(((unsigned long long)us * us) >> 6);
+                        e += vq - (unsigned)(((unsigned long long)vs * vs) >> 6);
+                        atomicAdd(&s_acc[1], (unsigned long long)us); atomicAdd(&s_acc[4], (unsigned long long)uq);
+                        atomicAdd(&s_acc[2], (unsigned long long)vs); atomicAdd(&s_acc[5], (unsigned long long)vq);
+                    }
+                    energy[ty * g.bw + tx] = e;
                 }
             }
-            if (lane == 0) energy[ty * g.bw + tx] = e;
+        }
+        __syncthreads();        /* everybody is done with this stage: refill it LA_LR_STAGES groups ahead */
+        if (tid == 0)
+        {
+            const int next = gid + LA_LR_STAGES * gridDim.x;
+            if (next < total) issue(next, st);
         }
     }
     if (doEnergy)
@@ -360,7 +386,7 @@ __global__ void __launch_bounds__(256) aq_energy8_kernel(Geom g, const P* __rest
     unsigned cs = 0, cq = 0;
     if (u)
     {
-        const P* row = ((r < 4) ? u : v) + (long long)min((by >> 1) + (r & 3), g.cH - 1) * g.cW;
+        const P* row = ((r < 4) ? u : v) + (long long)min((by >> 1) + (r & 3), g.cH - 1) * g.srcPitchC;
 #pragma unroll
         for (int i = 0; i < 4; i++) { const unsigned s = row[min((bx >> 1) + i, g.cW - 1)]; cs += s; cq += s * s; }
     }

@@ -147,7 +147,7 @@ bool Lookahead::create()
     memset(&cfg, 0, sizeof(cfg));
     cfg.width = p.sourceWidth; cfg.height = p.sourceHeight; cfg.depth = p.internalBitDepth;
     cfg.max_cu_size = p.maxCUSize; cfg.bframes = p.bframes;
-    cfg.max_slots = std::max(1, p.lookaheadDepth) + 2 * (p.bframes + 2) + 4 + p.extraSlots + std::max(0, p.asyncDepth);
+    cfg.max_slots = std::max(1, p.lookaheadDepth) + 3 * (p.bframes + 2) + 4 + p.extraSlots + std::max(0, p.asyncDepth);
     cfg.qg_size = p.rc.qgSize; cfg.aq_mode = p.rc.aqMode; cfg.aq_strength = p.rc.aqStrength;
     cfg.need_aq = m_bAdaptiveQuant; cfg.need_wp_stats = p.bEnableWeightedPred || p.bEnableWeightedBiPred;
     cfg.lambda = lookaheadLambda(p.internalBitDepth);
@@ -320,7 +320,12 @@ Frame* Lookahead::getDecidedPicture()
 {
     if (!m_filled || m_failed)
         return NULL;
-    if (m_outputQueue.empty() && (int)m_inputQueue.size() >= m_fullQueueSize && !m_inputQueue.empty())
+    /* The reference decides as soon as the input queue is full (a pool worker runs slicetypeDecide the moment addPicture
+     * fills it, slicetype.cpp:1231-1243), so its output queue usually holds the mini-GOP decided one step earlier.  Same
+     * here: decide while at most one mini-GOP is left in the output queue.  A caller that takes one decided frame per
+     * picture it adds (Encoder::encode) then reads a frame's rate-control cost and mirrors one mini-GOP after its decision,
+     * when the cuTree pass that produces them has long finished on the GPU, instead of waiting for it. */
+    if ((int)m_outputQueue.size() <= m_param.bframes + 1 && (int)m_inputQueue.size() >= m_fullQueueSize && !m_inputQueue.empty())
         slicetypeDecide();
     if (m_outputQueue.empty() || m_failed)
         return NULL;
