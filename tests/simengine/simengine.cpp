@@ -131,7 +131,11 @@ int x265cu_shard_config(x265cu_ctx* c, int32_t rank, int32_t nranks, x265cu_exch
     return 0;
 }
 int x265cu_slot_owner(x265cu_ctx* c, int32_t slot, int32_t owner) { c->owner[slot] = owner; return 0; }
-int x265cu_frame_ready(x265cu_ctx*, int32_t slot) { return (slot % 3) != 1; }   /* exercise both answers */
+int x265cu_frame_ready(x265cu_ctx*, int32_t slot)
+{
+    if (getenv("X265CU_FRAME_READY_NEVER")) return 0;    /* same test hook as the engine: every pair takes the assumed-weights path */
+    return (slot % 3) != 1;     /* exercise both answers */
+}
 int x265cu_profile_get_busy(x265cu_ctx*, double* ms) { for (int i = 0; i < X265CU_K_COUNT; i++) ms[i] = 0; return 0; }
 int x265cu_profile_enable(x265cu_ctx*, int32_t) { return 0; }
 int x265cu_profile_get(x265cu_ctx*, double* ms, uint64_t* n, int32_t) { for (int i = 0; i < X265CU_K_COUNT; i++) { ms[i] = 0; n[i] = 0; } return 0; }

@@ -287,3 +287,35 @@ def test_cuda_tiny_sequences(nframes, extra, pkg, synth, simdir):
             want = _as_ref_layout(cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, 8), planes=False))
         bad = compare.compare_runs(want, got, check_planes=False)
         assert not bad, "\n".join(bad[:10])
+
+
+_ASSUMED_WEIGHTS_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests")); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+import _pkg, cases, compare, golden_io, refbind
+pkg = _pkg.load_pkg(); synth = _pkg.load_synth()
+case = cases.get_case({name!r})
+want = cases.run_reference(refbind, synth, case, planes=False) if refbind.available(case[1]) else golden_io.load({name!r})
+got = cases.run_ours(pkg, synth, case, planes=False, speculate={spec}, asyncDepth={depth})
+bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1))
+print("\n".join(bad[:10]))
+sys.exit(1 if bad else 0)
+"""
+
+
+@pytest.mark.parametrize("name", ["fade8", "fade10", "fade_weightb_pool"])
+@pytest.mark.parametrize("mode", [(1, 12), (2, 6)])
+def test_cuda_weights_assumed_then_redone(name, mode):
+    """Batches are cut without waiting for the pixel sums weightp needs: a pair whose sums are still in flight is enqueued
+    unweighted and settled later (Lookahead::verifyWeights), its searches and costs redone on the weighted reference when the
+    analysis asks for weights.  X265CU_FRAME_READY_NEVER makes every frame look in flight, so the fade sequences take that path
+    for every pair (a fresh process: the engine reads the variable once)."""
+    import subprocess
+    import sys
+    if name != "fade8" and not refbind.available(cases.get_case(name)[1]):
+        pytest.skip("needs the live reference")
+    env = dict(os.environ, X265CU_FRAME_READY_NEVER="1", X265LA_DEBUG_WEIGHTS="1")
+    r = subprocess.run([sys.executable, "-c", _ASSUMED_WEIGHTS_SCRIPT.format(root=ROOT, name=name, spec=mode[0], depth=mode[1])],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr[-2000:]
+    assert "verifyWeights: redo" in r.stderr, "the fade never took the redo path"

@@ -1,6 +1,8 @@
 """CPU suite (no GPU): the C oracle + the PRODUCT's host decision logic, run through the CPU
 sim-engine (tests/simengine), must reproduce the unmodified reference bit for bit -- against the
 committed golden fixtures always, and against the live reference build (oracle/_ref) when present."""
+import os
+
 import numpy as np
 import pytest
 
@@ -188,4 +190,20 @@ def test_intrinsics_baseline_shims_are_bit_exact(depth):
     for f in shim:      # give the second reference run the key our own runs carry
         f["searched"] = f["mvs"][:, :, 0, 0] != 0x7FFF
     bad = compare.compare_runs(plain, shim, check_planes=True)
+    assert not bad, "\n".join(bad[:10])
+
+
+@pytest.mark.parametrize("name", ["fade8", "fade10", "fade_weightb_pool"])
+@pytest.mark.parametrize("mode", [(1, 12), (2, 6), (1, 0)])
+def test_weights_assumed_then_redone(name, mode, pkg, synth, simdir, monkeypatch):
+    """Lookahead::verifyWeights: with every frame's pixel sums reported "still in flight" all weightp pairs are enqueued
+    unweighted, settled when a decision needs them, and the fades' searches and costs redone on the weighted reference"""
+    monkeypatch.setenv("X265CU_FRAME_READY_NEVER", "1")
+    case = cases.get_case(name)
+    if not refbind.available(case[1]):
+        pytest.skip("needs the live reference")
+    want = cases.run_reference(refbind, synth, case, planes=False)
+    got = cases.run_ours(pkg, synth, case, lib_path=os.path.join(simdir, "libx265la_sim%d.so" % case[1]), planes=False,
+                         speculate=mode[0], asyncDepth=mode[1])
+    bad = compare.compare_runs(want, got, check_planes=False, cutree=case[6].get("cuTree", 1), weightp=case[6].get("weightp", 1))
     assert not bad, "\n".join(bad[:10])

@@ -32,6 +32,21 @@
 
 using namespace la;
 
+#include <chrono>
+/* host-side stopwatch for tuning (X265CU_HOST_TIMING=1 prints the totals when a context is destroyed) */
+enum { HT_UPLOAD, HT_BATCH_BEGIN, HT_SEARCH_ENQ, HT_COST_ENQ, HT_BATCH_END, HT_GATHER, HT_MIRROR_RINGWAIT, HT_MIRROR_MALLOC, HT_MIRROR_REST,
+       HT_STATS_WAIT, HT_RECALC_GET, HT_CUTREE, HT_WEIGHT, HT_COUNT };
+static const char* const g_htNames[HT_COUNT] = { "upload", "batch_begin", "search_enqueue", "cost_enqueue", "batch_end", "gather", "mirror_ringwait",
+                                                 "mirror_malloc", "mirror_rest", "stats_wait", "recalc_get", "cutree", "weight" };
+static double g_ht[HT_COUNT];
+static unsigned long long g_htN[HT_COUNT];
+struct HostTimer
+{
+    int k; std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(int kind) : k(kind), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() { g_ht[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); g_htN[k]++; }
+};
+
 namespace {
 
 struct SlotLayout
@@ -60,7 +75,8 @@ struct Batch
     int* d_sync; size_t syncCap, syncUsed;      /* ticket counter + per-(job, strip) progress of every search call */
     std::vector<char*> weightScratch;   /* 4 weighted planes each */
     std::vector<void*> retiredDev, retiredHost; /* outgrown buffers, freed when the object is reused */
-    std::vector<long long> waited;      /* batches this one already waits for */
+    std::vector<long long> waited;      /* batches whose searches this one already waits for */
+    std::vector<long long> waitedDone;  /* batches this one waits for entirely */
     /* sharded stream: stores written in this batch (by their owners), exchanged at batch_end */
     struct Seg { char* ptr; size_t bytes; int root; };
     std::vector<Seg> segs;
@@ -347,6 +363,7 @@ int ensureMapped(x265cu_ctx* c, size_t need)
 /* wordsEach words from each of srcs[0..n) into dst (host), through one kernel on the main stream; synchronises */
 int gatherSmall(x265cu_ctx* c, const std::vector<const void*>& srcs, int wordsEach, void* dst)
 {
+    HostTimer ht(HT_GATHER);
     const size_t n = srcs.size();
     const size_t tabBytes = alignUp(n * sizeof(void*), 256), outBytes = n * wordsEach * sizeof(unsigned);
     int st = ensureMapped(c, tabBytes + outBytes);
@@ -468,6 +485,7 @@ int exchangeBatch(x265cu_ctx* c, Batch* b)
 int endBatch(x265cu_ctx* c)
 {
     if (!c->cur) return X265CU_OK;
+    HostTimer ht(HT_BATCH_END);
     Batch* b = c->cur;
     c->cur = NULL;
     b->open = false;
@@ -479,6 +497,7 @@ int endBatch(x265cu_ctx* c)
 
 int beginBatch(x265cu_ctx* c)
 {
+    HostTimer ht(HT_BATCH_BEGIN);
     int st = endBatch(c);
     if (st) return st;
     if (c->nranks > 1)
@@ -495,7 +514,7 @@ int beginBatch(x265cu_ctx* c)
     xbufGiveBack(c, b);
     for (size_t i = 0; i < b->retiredDev.size(); i++) cudaFree(b->retiredDev[i]);
     for (size_t i = 0; i < b->retiredHost.size(); i++) cudaFreeHost(b->retiredHost[i]);
-    b->retiredDev.clear(); b->retiredHost.clear(); b->waited.clear();
+    b->retiredDev.clear(); b->retiredHost.clear(); b->waited.clear(); b->waitedDone.clear();
     b->id = c->nextBatch++;
     b->stream = c->lanes[b->id % LA_NUM_LANES];
     b->stageUsed = 0; b->syncUsed = 0; b->open = true;
@@ -552,6 +571,19 @@ int batchWaitSearches(x265cu_ctx* c, Batch* b, long long id)
     return X265CU_OK;
 }
 
+/* The batch is about to overwrite a store that batch `id` wrote (a search redone with weights after it had been enqueued
+ * assuming none, Lookahead::verifyWeights): everything of that batch -- its writers and the cost jobs reading the store --
+ * goes first.  Rare (fades); the stores of a recycled slot are reset by the upload, which orders the tenants itself. */
+int batchWaitDone(x265cu_ctx* c, Batch* b, long long id)
+{
+    if (id < 0 || id == b->id) return X265CU_OK;
+    if (std::find(b->waitedDone.begin(), b->waitedDone.end(), id) != b->waitedDone.end()) return X265CU_OK;
+    b->waitedDone.push_back(id);
+    Batch* w = batchOf(c, id);
+    if (w && !w->open) CK(cudaStreamWaitEvent(b->stream, w->done, 0));
+    return X265CU_OK;
+}
+
 /* the main stream waits for batch `id` (its searches only, or all of it) */
 int mainWaitBatch(x265cu_ctx* c, long long id, bool searchesOnly)
 {
@@ -603,6 +635,7 @@ char* costStorePtr(x265cu_ctx* c, int slot, int store) { return c->slots[slot] +
 template <typename P>
 int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v, int sy, int sc)
 {
+    HostTimer ht(HT_UPLOAD);
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
     P* dY = slotPtr<P>(c, slot, L.srcY);
@@ -742,6 +775,7 @@ int ensureScratch(x265cu_ctx* c, std::vector<char*>& scratch, cudaStream_t strea
 template <typename P>
 int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
 {
+    HostTimer ht(HT_SEARCH_ENQ);
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
     const bool implicit = !c->cur;
@@ -763,6 +797,8 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
         { snprintf(c->err, sizeof(c->err), "search job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
         char* ms = mvStorePtr(c, j.fenc_slot, j.store);
         touchSlot(c, j.fenc_slot, b->id); touchSlot(c, j.ref_slot, b->id);
+        st = batchWaitDone(c, b, c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.store]);
+        if (st) return st;
         c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.store] = b->id;
         if (c->nranks > 1)
         {
@@ -838,6 +874,7 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
 template <typename P>
 int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
 {
+    HostTimer ht(HT_COST_ENQ);
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
     const bool implicit = !c->cur;
@@ -868,6 +905,8 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         { snprintf(c->err, sizeof(c->err), "cost job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
         char* cs = costStorePtr(c, j.b_slot, j.out);
         touchSlot(c, j.b_slot, b->id); touchSlot(c, j.p0_slot, b->id); touchSlot(c, j.p1_slot, b->id);
+        st = batchWaitDone(c, b, c->costWriter[(size_t)j.b_slot * c->geom.n_cost_stores + j.out]);
+        if (st) return st;
         c->costWriter[(size_t)j.b_slot * c->geom.n_cost_stores + j.out] = b->id;
         if (c->nranks > 1)
         {
@@ -967,6 +1006,7 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
 template <typename P>
 int weightCostT(x265cu_ctx* c, const x265cu_wcost_job* jobs, int n, uint32_t* costs)
 {
+    HostTimer ht(HT_WEIGHT);
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
     int st = ensureDev(c, &c->d_results, &c->resultsCap, n * sizeof(unsigned));
@@ -1286,6 +1326,12 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
 
 void x265cu_destroy(x265cu_ctx* c)
 {
+    if (c && getenv("X265CU_HOST_TIMING"))
+    {
+        fprintf(stderr, "x265cu host timing (ms, calls):");
+        for (int i = 0; i < HT_COUNT; i++) { fprintf(stderr, " %s %.1f/%llu", g_htNames[i], g_ht[i] * 1e3, g_htN[i]); g_ht[i] = 0; g_htN[i] = 0; }
+        fprintf(stderr, "\n");
+    }
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c) return;
@@ -1531,6 +1577,10 @@ int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
     if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     if (!c || !slotOk(c, slot)) return X265CU_ERR_BAD_ARG;
+    /* test hook: every frame "still in flight", so that callers exercise the paths they take behind a busy GPU
+     * (Lookahead::verifyWeights: weights assumed, settled later, searches redone) on sequences too short to get there */
+    static const bool never = getenv("X265CU_FRAME_READY_NEVER") != NULL;
+    if (never) return 0;
     const cudaError_t e = cudaEventQuery(c->slotConsumed[slot]);
     if (e == cudaSuccess) return 1;
     if (e == cudaErrorNotReady) return 0;
@@ -1543,6 +1593,7 @@ int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265c
     if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     flushCutree(c);
+    HostTimer ht(HT_STATS_WAIT);
     /* the statistics were published into mapped host memory by the frame's own pre-lookahead: wait for that only */
     for (int i = 0; i < n; i++)
     {
@@ -1649,6 +1700,7 @@ int x265cu_cutree_propagate(x265cu_ctx* c, int32_t bs, int32_t p0s, int32_t p1s,
         l0 < 0 || l0 >= c->geom.n_mv_stores || l1 >= c->geom.n_mv_stores)
         return X265CU_ERR_BAD_ARG;
     const SlotLayout& L = c->lay;
+    HostTimer ht(HT_CUTREE);
     int st = mainWaitCost(c, bs, cost_store);
     if (!st) st = mainWaitMv(c, bs, l0);
     if (!st) st = mainWaitMv(c, bs, l1);
@@ -1818,7 +1870,8 @@ int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_reque
     if (!slotOk(c, slot) || q->n_mv < 0 || q->n_mv > X265CU_MIRROR_MAX_MV || q->cost_store == 1 || q->cost_store >= c->geom.n_cost_stores)
         return X265CU_ERR_BAD_ARG;
     x265cu_ctx::MirrorEntry& e = c->mirror[c->nextMirror % X265CU_MIRROR_RING];
-    if (e.ticket >= 0) CK(cudaEventSynchronize(e.done));        /* the ring wrapped: that request's scratch is free again */
+    if (e.ticket >= 0) { HostTimer ht(HT_MIRROR_RINGWAIT); CK(cudaEventSynchronize(e.done)); }  /* the ring wrapped: that request's scratch is free again */
+    HostTimer htRest(HT_MIRROR_REST);
     const cudaStream_t ms = c->mirrorStream;
     /* behind everything the main stream carries so far (cuTree of the decisions taken, cost recalculations) ... */
     CK(cudaEventRecord(c->mirrorMark, c->stream));
@@ -1838,6 +1891,7 @@ int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_reque
     const size_t need = planeBytes + mvBytes * q->n_mv + 256;
     if (e.cap < need)
     {
+        HostTimer ht(HT_MIRROR_MALLOC);
         cudaFree(e.scratch); e.scratch = NULL; e.cap = 0;
         CK(cudaMalloc((void**)&e.scratch, need));
         e.cap = need;
@@ -1931,6 +1985,7 @@ int x265cu_cost_recalc_get(x265cu_ctx* c, int32_t slot, int32_t cost_store, int6
     if (!c || !score) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     if (!slotOk(c, slot) || c->slotRecalcStore[slot] != cost_store) return X265CU_ERR_BAD_ARG;
+    HostTimer ht(HT_RECALC_GET);
     const SlotLayout& L = c->lay;
     const Geom& g = c->g;
     CK(cudaEventSynchronize(c->slotRecalc[slot]));

@@ -993,7 +993,7 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
     const SearchJobDev<P> J = jobs[job];
     if (J.cond && __ldcg(J.cond) == 0) continue;    /* the variant this job would compute is not needed */
     /* strip 0 owns the lowest ticket of its job and every other strip waits on its progress chain */
-    if (strip == 0 && lane == 0) { *J.flagOut = 0; atomicAdd(executed, 1ull); }
+    if (strip == 0 && lane == 0) { atomicExch(J.flagOut, 0); atomicAdd(executed, 1ull); }
     const int rowsInStrip = min(LA_STRIP_ROWS, bh - strip * LA_STRIP_ROWS);
     const bool rowOk = grp < rowsInStrip;
     const int cuY = rowOk ? bh - 1 - strip * LA_STRIP_ROWS - grp : 0;
@@ -1013,6 +1013,7 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
     m.rb.plane0 = J.ref0;
     int h0 = 0, h1 = 0, h2 = 0;     /* this group's results of the last three steps (packed MVs) */
     int seen = 0;                   /* progress of the strip below as last observed (warp-uniform) */
+    bool flagSet = false;
 
     for (int s = 0; s < steps; s++)
     {
@@ -1133,7 +1134,7 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
         h2 = h1; h1 = h0; h0 = packed;
         if (r == 0 && act)
         {
-            if (skipped) *J.flagOut = 1;
+            if (skipped && !flagSet) { atomicOr(J.flagOut, 1); flagSet = true; }    /* once per strip and row */
             __stcg(J.mvOut + cu, packed);
             J.costOut[cu] = fencCost;
             if (grp == rowsInStrip - 1)

@@ -175,7 +175,7 @@ bool Lookahead::create()
 void Lookahead::destroy()
 {
     for (size_t i = 0; i < m_pool.size(); i++) delete m_pool[i];
-    m_pool.clear(); m_inputQueue.clear(); m_outputQueue.clear(); m_resident.clear(); m_pendingSpec.clear();
+    m_pool.clear(); m_inputQueue.clear(); m_outputQueue.clear(); m_resident.clear(); m_pendingSpec.clear(); m_unverified.clear();
     if (m_ctx)
     {
         x265cu_sync(m_ctx);
@@ -544,7 +544,7 @@ void Lookahead::enqueueCosts(int l0kind, bool conditional)
  * always computed; the P-context variant and the costs that read it are enqueued as CONDITIONAL jobs which the
  * device skips when the B-context search never applied the zero-MV skip rule (the two variants are then the same
  * search and the host aliases them once it has read the flag, resolveAlias). */
-void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
+void Lookahead::speculateFrames(const std::vector<Frame*>& fresh, int onlyDist)
 {
     if (fresh.empty() || m_failed) return;
     const int B = m_param.bframes, nb = m_geom.nb;
@@ -565,6 +565,7 @@ void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
         {
             Frame* rf = frameOfPoc(fn->m_poc - d);
             if (!rf) break;
+            if (onlyDist && d != onlyDist) continue;        /* verifyWeights redoes one L0 distance of a frame */
             Lowres* r = &rf->m_lowres;
             addSearch(n, r, firstKind, d);                  /* L0(n,d) */
             /* the reference's search batches pair every list-0 search with the list-1 search at the SAME distance
@@ -584,6 +585,7 @@ void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
             {
                 Frame* rf = frameOfPoc(fn->m_poc - d);
                 if (!rf) break;
+                if (onlyDist && d != onlyDist) continue;
                 addSearch(&fn->m_lowres, &rf->m_lowres, s3, d, (1 + s3) * nb + d);
             }
         }
@@ -594,16 +596,22 @@ void Lookahead::speculateFrames(const std::vector<Frame*>& fresh)
     m_timers[2] += nowSec() - t0;
 }
 
-/* Speculate the frames that arrived but were not processed yet, oldest first.  Frames up to mustPoc are needed now
- * and are taken unconditionally.  Newer ones are taken too -- the GPU works on them while the host decides from the
- * results of earlier batches -- but with weightp a frame's pixel sums must be on the host first, so a newer frame is
- * only taken if its pre-lookahead has already finished (or more than `keep` frames are waiting): the caller never
- * stalls on the GPU for work nobody needs yet.  Scheduling only: what is computed does not depend on when.
+/* Speculate the frames that arrived but were not processed yet, oldest first.  Frames up to mustPoc are needed now;
+ * newer ones are taken too -- the GPU works on them while the host decides from the results of earlier batches.
+ * Nothing here waits for the GPU on behalf of a frame nobody needs yet.  In particular weightp: whether an L0 search runs
+ * on a weighted reference is decided on the host from the pixel sums of the two frames (weightsAnalyse), and those
+ * only exist once the frame's pre-lookahead has run -- which, behind a saturated search launch, is milliseconds
+ * away.  A pair whose sums are not on the host yet is therefore enqueued ASSUMING no weight (weightState 3) and
+ * verified later (verifyWeights); outside fades the assumption always holds.  Waiting for the sums instead (the first
+ * version did) serialised the whole pipeline: batch k+1 could only be cut after the search launch of batch k had
+ * drained.  Scheduling only: what is computed does not depend on when.
  * streaming mode: one batch per frame; otherwise one batch for all of them */
 void Lookahead::drainPending(size_t keep, int mustPoc)
 {
     std::vector<Frame*> group;
     const bool needStats = m_param.bEnableWeightedPred != 0;
+    const bool sharded = m_param.shardCount > 1;
+    (void)keep;
     /* per-decision mode: unless the window needs one of them now, wait until enough frames have gathered for a launch
      * that fills the GPU (a lowres search is a ~500-step wavefront: small launches spend most of their time ramping
      * up and draining) */
@@ -612,32 +620,21 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
         /* ... unless the GPU has nothing left to do (pictures arrive slower than it consumes them): then a smaller launch
          * now beats a full one later.  A sharded stream must batch the same frames on every rank, so it never asks. */
         const int minFrames = std::min(m_param.batchMin, 4);
-        const bool idle = m_param.shardCount <= 1 && (int)m_pendingSpec.size() >= minFrames && (int)m_pendingSpec.size() < m_param.batchMin &&
+        const bool idle = !sharded && (int)m_pendingSpec.size() >= minFrames && (int)m_pendingSpec.size() < m_param.batchMin &&
                           x265cu_batches_in_flight(m_ctx) == 0;
         const int want = idle ? minFrames : m_param.batchMin;
         if ((int)m_pendingSpec.size() < want)
             return;
-        if (needStats && m_param.shardCount <= 1)
-        {
-            /* ... and with weightp only frames whose pixel sums are on the host (pre-lookahead finished) can be taken without
-             * stalling: wait until enough of them are */
-            int ready = 0;
-            for (size_t i = 0; i < m_pendingSpec.size() && ready < want; i++, ready++)
-                if (!m_pendingSpec[i]->m_lowresInit && x265cu_frame_ready(m_ctx, m_pendingSpec[i]->m_lowres.slot) != 1)
-                    break;
-            if (ready < want && m_pendingSpec.size() <= keep)
-                return;
-        }
     }
+    /* weights assumed earlier whose pixel sums have arrived in the meantime: settle them first, so a search that does
+     * need weights is redone before more work piles up behind the wrong one */
+    if (needStats && !sharded) verifyWeights(mustPoc);
     while (!m_pendingSpec.empty() && !m_failed)
     {
         Frame* f = m_pendingSpec.front();
         /* (a sharded stream must batch the same frames on every rank, so it never looks at the clock: it leaves the
-         * two newest frames, whose pre-lookahead is probably still running, for the next batch) */
-        if (f->m_poc > mustPoc && m_param.shardCount > 1 && needStats && f->m_poc > m_pocNext - 3)
-            break;
-        if (f->m_poc > mustPoc && m_pendingSpec.size() <= keep && needStats && !f->m_lowresInit &&
-            m_param.shardCount <= 1 && x265cu_frame_ready(m_ctx, f->m_lowres.slot) != 1)
+         * two newest frames, whose pre-lookahead is probably still running, for the next batch and waits for the sums) */
+        if (f->m_poc > mustPoc && sharded && needStats && f->m_poc > m_pocNext - 3)
             break;
         m_pendingSpec.pop_front();
         group.push_back(f);
@@ -645,9 +642,21 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
     if (group.empty()) return;
     if (needStats)
     {
+        /* the pixel sums of the group's frames and of the references they pair with: waited for where a decision needs the
+         * frame now (or the stream is sharded), otherwise taken only if they are already there */
         std::vector<Frame*> pre;
         for (size_t i = 0; i < group.size(); i++)
-            if (!group[i]->m_lowresInit) pre.push_back(group[i]);
+        {
+            const bool must = sharded || group[i]->m_poc <= mustPoc;
+            for (int d = 0; d <= m_param.bframes + 1; d++)
+            {
+                Frame* x = d ? frameOfPoc(group[i]->m_poc - d) : group[i];
+                if (!x) break;
+                if (x->m_lowresInit || std::find(pre.begin(), pre.end(), x) != pre.end()) continue;
+                if (must || x265cu_frame_ready(m_ctx, x->m_lowres.slot) == 1)
+                    pre.push_back(x);
+            }
+        }
         const double t0 = nowSec();
         preLookahead(pre);
         m_timers[0] += nowSec() - t0;
@@ -659,7 +668,13 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
             {
                 Frame* r = frameOfPoc(group[i]->m_poc - d);
                 if (!r) break;
-                pairs.push_back(std::make_pair(&group[i]->m_lowres, &r->m_lowres));
+                if (group[i]->m_lowresInit && r->m_lowresInit)
+                    pairs.push_back(std::make_pair(&group[i]->m_lowres, &r->m_lowres));
+                else if (!group[i]->m_lowres.weightState[d])
+                {
+                    group[i]->m_lowres.weightState[d] = 3;
+                    m_unverified.push_back(std::make_pair(group[i], d));
+                }
             }
         weightsAnalyseBatch(pairs);
         m_timers[1] += nowSec() - t1;
@@ -669,6 +684,86 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
             speculateFrames(std::vector<Frame*>(1, group[i]));
     else
         speculateFrames(group);
+}
+
+/* Settle the weightp assumptions of drainPending: every (frame, L0 distance) enqueued without weights because the pixel
+ * sums of the pair were still on their way.  A pair is analysed as soon as both frames' sums are on the host (taken
+ * without waiting when their pre-lookahead has finished; waited for when the frame is <= mustPoc, i.e. a decision is about to
+ * read its results).  weightsAnalyse's answer is "no weight" outside fades and nothing else happens; otherwise the L0
+ * searches of that distance and every cost that read them are enqueued again, this time on the weighted reference
+ * (the engine orders the new batch behind the old writers and readers of those stores).  No result of such a frame has
+ * been read by the host before this point: results are only fetched for frames <= maxPoc of a decision, after this ran. */
+void Lookahead::verifyWeights(int mustPoc)
+{
+    if (m_unverified.empty() || m_failed) return;
+    std::vector<Frame*> need;
+    for (size_t i = 0; i < m_unverified.size(); i++)
+    {
+        Frame* f = m_unverified[i].first;
+        Frame* pair[2] = { f, frameOfPoc(f->m_poc - m_unverified[i].second) };
+        for (int k = 0; k < 2; k++)
+        {
+            Frame* x = pair[k];
+            if (!x || x->m_lowresInit || std::find(need.begin(), need.end(), x) != need.end()) continue;
+            if (f->m_poc <= mustPoc || x265cu_frame_ready(m_ctx, x->m_lowres.slot) == 1)
+                need.push_back(x);
+        }
+    }
+    if (!need.empty())
+    {
+        const double t0 = nowSec();
+        preLookahead(need);
+        m_timers[0] += nowSec() - t0;
+        if (m_failed) return;
+    }
+    const double t1 = nowSec();
+    std::vector<std::pair<Frame*, int> > later, checked;
+    std::vector<std::pair<Lowres*, Lowres*> > pairs;
+    for (size_t i = 0; i < m_unverified.size(); i++)
+    {
+        Frame* f = m_unverified[i].first;
+        const int d = m_unverified[i].second;
+        Frame* r = frameOfPoc(f->m_poc - d);
+        if (!r)
+        {
+            /* cannot happen: the reference frame of an undecided frame is still resident */
+            fail("verifyWeights: reference frame gone");
+            return;
+        }
+        if (f->m_lowresInit && r->m_lowresInit)
+        {
+            f->m_lowres.weightState[d] = 0;
+            pairs.push_back(std::make_pair(&f->m_lowres, &r->m_lowres));
+            checked.push_back(m_unverified[i]);
+        }
+        else
+            later.push_back(m_unverified[i]);
+    }
+    m_unverified.swap(later);
+    weightsAnalyseBatch(pairs);
+    m_timers[1] += nowSec() - t1;
+    if (m_failed) return;
+    const int nb = m_geom.nb;
+    for (size_t i = 0; i < checked.size() && !m_failed; i++)
+    {
+        Frame* f = checked[i].first;
+        const int d = checked[i].second;
+        Lowres& n = f->m_lowres;
+        if (n.weightState[d] != 2) continue;
+        /* the assumption was wrong: forget the L0 searches of this distance (both contexts, both slicednesses) and every
+         * cost that read them, and enqueue them again */
+        for (int kind = 0; kind < 6; kind++)
+            if (kind % 3 < 2) n.haveSearch[kind][d] = 0;
+        for (int s2 = 0; s2 < 2; s2++) { n.flagFetched[s2][d] = 0; n.l0Alias[s2][d] = 0; }
+        for (int d1 = 0; d1 < nb; d1++)
+            for (int v = 0; v < 8; v++)
+            {
+                if (n.resultFetched[d][d1][v]) { fail("verifyWeights: a result of an unverified search was already read"); return; }
+                n.haveCost[d][d1][v] = 0;
+            }
+        if (getenv("X265LA_DEBUG_WEIGHTS")) fprintf(stderr, "verifyWeights: redo poc %d d %d\n", f->m_poc, d);
+        speculateFrames(std::vector<Frame*>(1, f), d);
+    }
 }
 
 /* the skip flags of the B-context L0 searches of `who` that the host has not looked at yet: decides, per (frame,
@@ -871,6 +966,8 @@ void Lookahead::slicetypeDecide()
         preLookahead(still);
         m_timers[0] += nowSec() - t0;
     }
+    if (m_failed) return;
+    verifyWeights(maxPoc);      /* weights assumed for frames this decision reads are settled (and redone) first */
     if (m_failed) return;
     if (m_param.speculate)
     {

@@ -103,7 +103,8 @@ struct Lowres
     /* publication state: which device store holds what the reference would hold */
     int     mvStore[2][BFRAME_MAX + 2];                      /* -1 = lowresMvs[l][d][0].x == 0x7FFF */
     int     costStore[BFRAME_MAX + 2][BFRAME_MAX + 2];       /* -1 = never computed */
-    /* weightp state per L0 distance: 0 unknown, 1 analysed/no weight, 2 weighted */
+    /* weightp state per L0 distance: 0 unknown, 1 analysed/no weight, 2 weighted, 3 = searches and costs were enqueued
+     * ASSUMING no weight because the pixel sums of the pair were not on the host yet (Lookahead::verifyWeights) */
     int     weightState[BFRAME_MAX + 2];
     int     wScale[BFRAME_MAX + 2], wDenom[BFRAME_MAX + 2], wOffset[BFRAME_MAX + 2];
 
@@ -210,6 +211,7 @@ private:
     std::vector<Frame*> m_pool;           /* one per slot */
     std::vector<Frame*> m_resident;       /* frames with live slots, by arrival */
     std::deque<Frame*>  m_pendingSpec;    /* arrived, searches / costs not enqueued yet */
+    std::vector<std::pair<Frame*, int> > m_unverified;   /* (frame, L0 distance) in weightState 3 */
     std::map<const void*, bool> m_pinned; /* caller buffers page-locked by pinHost (true = registered) */
     int     m_pocNext;
     int     m_shardRank;
@@ -237,7 +239,8 @@ private:
 
     /* device orchestration */
     void    preLookahead(const std::vector<Frame*>& fr);
-    void    speculateFrames(const std::vector<Frame*>& fresh);
+    void    speculateFrames(const std::vector<Frame*>& fresh, int onlyDist = 0);
+    void    verifyWeights(int mustPoc);
     void    drainPending(size_t keep, int mustPoc);
     void    resolveAlias(const std::vector<Lowres*>& who);
     void    enqueueCosts(int l0kind, bool conditional);
