@@ -122,8 +122,8 @@ int  x265cu_frame_stats_get(x265cu_ctx* ctx, const int32_t* slots, int32_t n, x2
  * own.  Nothing here blocks the caller. */
 int  x265cu_batch_begin(x265cu_ctx* ctx, int64_t* batch_id /* may be NULL */);
 int  x265cu_batch_end(x265cu_ctx* ctx);
-/* batches still open or running (never blocks; >= 0, or a negative status): lets the caller launch a smaller batch early when
- * the GPU would otherwise sit idle waiting for a full one (pictures arriving slower than the GPU consumes them) */
+/* batches still open or running, counted up to 2 (never blocks; 0, 1, 2, or a negative status): lets the caller launch a smaller
+ * batch early when the GPU would otherwise run dry waiting for a full one (it should hold the batch it works on and one behind it) */
 int  x265cu_batches_in_flight(x265cu_ctx* ctx);
 
 /* ---- one stream sharded over several GPUs (SURVEY 8e level 2): every (frame, list, distance) search and every

@@ -123,7 +123,7 @@ int x265cu_timer_stop(x265cu_ctx*, double* ms) { *ms = 0; return 0; }
 int x265cu_get_counters(x265cu_ctx* c, x265cu_counters* o) { *o = c->counters; return 0; }
 int x265cu_batch_begin(x265cu_ctx*, int64_t* id) { static int64_t n = 0; if (id) *id = n++; return 0; }
 int x265cu_batch_end(x265cu_ctx*) { return 0; }
-int x265cu_batches_in_flight(x265cu_ctx*) { static int n = 0; return (n++ % 3) == 0 ? 0 : 1; }    /* exercise both answers */
+int x265cu_batches_in_flight(x265cu_ctx*) { static int n = 0; return n++ % 3; }    /* exercise every answer (0, 1, 2) */
 int x265cu_shard_config(x265cu_ctx* c, int32_t rank, int32_t nranks, x265cu_exchange_fn fn, void* user)
 {
     if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks || (nranks > 1 && !fn)) return X265CU_ERR_BAD_ARG;

@@ -111,6 +111,9 @@ struct x265cu_ctx
     char* d_recalc; char* h_recalc;             /* [slot] x recalcStride: device scratch / mapped host copy */
     size_t recalcStride;
     std::vector<char> slotMainTouched;          /* main-stream work read the slot's current tenant */
+    std::vector<cudaEvent_t> slotMainWrote;     /* per slot: the last main-stream kernel that wrote arrays a mirror reads (cuTreeFinish,
+                                                   the synchronous cost recalculation) */
+    std::vector<char> slotMainWroteSet;
     cudaStream_t lanes[LA_NUM_LANES];
     Batch batches[LA_NUM_BATCHES];
     long long nextBatch;
@@ -136,6 +139,10 @@ struct x265cu_ctx
     int searchWorkers;              /* worker warps per search job; 0 = default (env X265CU_SEARCH_WORKERS, for tuning) */
     int numSMs;
     int searchSmem;                 /* dynamic shared memory per search CTA (env X265CU_SEARCH_SMEM, bytes): residency cap */
+    int searchLanes;                /* lanes per 8x8 block in the search kernel: 4 (default; two rows per lane, strips of 8 block rows) or
+                                       8 (one row per lane, strips of 4; env X265CU_SEARCH_LANES, kept for A/B measurements) */
+    int searchOneShot;              /* one ticket per search CTA instead of persistent workers (env X265CU_SEARCH_ONESHOT) */
+    long long bigSearch[2];         /* the two most recent batches with a large search launch (see searchBatchT), -1 = none */
     bool profile;
     double profMs[X265CU_K_COUNT], profBusy[X265CU_K_COUNT];
     uint64_t profN[X265CU_K_COUNT];
@@ -687,6 +694,7 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
         c->slotMirrorTouched[slot] = 0;
     }
     c->slotRecalcStore[slot] = -1;
+    c->slotMainWroteSet[slot] = 0;
     if (c->slotMainTouched[slot])
     {
         /* ... and whatever the main stream (cuTree, recalc, mirrors) still reads of it */
@@ -848,22 +856,38 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
         CK(cudaEventRecord(b->searchDone, b->stream));
         return implicit ? endBatch(c) : X265CU_OK;
     }
-    const int nstrips = (g.bh + LA_STRIP_ROWS - 1) / LA_STRIP_ROWS;      /* strips of 4 rows, one warp each */
+    const int stripRows = 32 / c->searchLanes;
+    const int nstrips = (g.bh + stripRows - 1) / stripRows;      /* strips of 4 or 8 block rows, one warp each */
     c->searchEnq += n;
     int* dsync;
     st = batchSync(c, b, (size_t)(1 + n * nstrips), &dsync);
     if (st) return st;
     CK(cudaMemcpyAsync(dst, hst, n * sizeof(SearchJobDev<P>), cudaMemcpyHostToDevice, b->stream));
     CK(cudaMemsetAsync(dsync, 0, (size_t)(1 + n * nstrips) * sizeof(int), b->stream));
+    if (n >= 64 && c->bigSearch[1] != b->id)
+    {
+        /* Large search launches of different batches run on different lanes with equal priority; left alone, the launches of
+         * several queued batches share the GPU evenly and all finish late together -- the host, which needs the OLDEST batch
+         * first, then waits for the sum of them.  At most two overlap (the second ramps up while the first drains): a large
+         * launch starts after the one two before it has finished.  Small (on-demand) launches are never held back. */
+        Batch* w = batchOf(c, c->bigSearch[0]);
+        if (w && !w->open) CK(cudaStreamWaitEvent(b->stream, w->searchDone, 0));
+        c->bigSearch[0] = c->bigSearch[1]; c->bigSearch[1] = b->id;
+    }
     {
         Prof pr(c, X265CU_K_SEARCH, 1, b->stream);
         /* workers per job: a job's strips start 8 steps apart and run ~bw steps, so beyond ~bw/8 of them some only
          * sit resident waiting for their turn; that matters when the launch is too small to oversubscribe the GPU */
-        const int workers = std::max(1, std::min(nstrips, c->searchWorkers > 0 ? c->searchWorkers : (nstrips + 1) / 2));
+        const int workers = c->searchOneShot ? nstrips
+                                             : std::max(1, std::min(nstrips, c->searchWorkers > 0 ? c->searchWorkers : (nstrips + 1) / 2));
         /* searchSmem: bytes of (unused) dynamic shared memory per one-warp CTA -- caps how many search warps an SM holds,
          * so that the short high-priority kernels (pre-lookahead, cuTree, recalc) always find room beside them */
-        search_kernel<P><<<n * workers, 32, c->searchSmem, b->stream>>>(g, (const SearchJobDev<P>*)dst, nstrips, n,
-                                                           c->d_mvcost + c->cfg.mvcost_half, dsync, dsync + 1, c->d_executed);
+        if (c->searchLanes == 8)
+            search_kernel<P, 8><<<n * workers, 32, c->searchSmem, b->stream>>>(g, (const SearchJobDev<P>*)dst, nstrips, n,
+                                                           c->d_mvcost + c->cfg.mvcost_half, dsync, dsync + 1, c->d_executed, c->searchOneShot);
+        else
+            search_kernel<P, 4><<<n * workers, 32, c->searchSmem, b->stream>>>(g, (const SearchJobDev<P>*)dst, nstrips, n,
+                                                           c->d_mvcost + c->cfg.mvcost_half, dsync, dsync + 1, c->d_executed, c->searchOneShot);
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(b->searchDone, b->stream));
@@ -1141,6 +1165,9 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->searchSmem = getenv("X265CU_SEARCH_SMEM") ? atoi(getenv("X265CU_SEARCH_SMEM")) : 0;
+    c->searchLanes = getenv("X265CU_SEARCH_LANES") && atoi(getenv("X265CU_SEARCH_LANES")) == 8 ? 8 : 4;
+    c->searchOneShot = getenv("X265CU_SEARCH_ONESHOT") ? atoi(getenv("X265CU_SEARCH_ONESHOT")) : 0;
+    c->bigSearch[0] = c->bigSearch[1] = -1;
     c->numSMs = 148;
     cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, cfg->device);
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
@@ -1275,6 +1302,9 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
         cudaEventCreateWithFlags(&e2, cudaEventDisableTiming); cudaEventCreateWithFlags(&e3, cudaEventDisableTiming);
         c->slotMirrored.push_back(e2); c->slotMirrorTouched.push_back(0);
         c->slotRecalc.push_back(e3); c->slotRecalcStore.push_back(-1);
+        cudaEvent_t e4;
+        cudaEventCreateWithFlags(&e4, cudaEventDisableTiming);
+        c->slotMainWrote.push_back(e4); c->slotMainWroteSet.push_back(0);
         /* planes must start zeroed: columns past the right margin are never written (K1) */
         if (cudaMemsetAsync(p, 0, L.total, c->stream) != cudaSuccess) rc = X265CU_ERR_CUDA;
     }
@@ -1339,6 +1369,7 @@ void x265cu_destroy(x265cu_ctx* c)
     for (size_t i = 0; i < c->slots.size(); i++) cudaFree(c->slots[i]);
     for (size_t i = 0; i < c->slotCopied.size(); i++) { cudaEventDestroy(c->slotCopied[i]); cudaEventDestroy(c->slotConsumed[i]); }
     for (size_t i = 0; i < c->slotMirrored.size(); i++) { cudaEventDestroy(c->slotMirrored[i]); cudaEventDestroy(c->slotRecalc[i]); }
+    for (size_t i = 0; i < c->slotMainWrote.size(); i++) cudaEventDestroy(c->slotMainWrote[i]);
     for (int i = 0; i < X265CU_MIRROR_RING; i++) { if (c->mirror[i].done) cudaEventDestroy(c->mirror[i].done); cudaFree(c->mirror[i].scratch); }
     if (c->mirrorStream) cudaStreamDestroy(c->mirrorStream);
     if (c->gatherStream) cudaStreamDestroy(c->gatherStream);
@@ -1449,9 +1480,9 @@ int x265cu_batches_in_flight(x265cu_ctx* c)
 {
     if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
-    /* newest first, one lane's worth: the answer the caller acts on is "none", and a busy GPU says otherwise at the first query */
+    /* newest first, one lane's worth: the answer the caller acts on is "fewer than two", so counting stops there */
     int n = 0;
-    for (long long id = c->nextBatch - 1; id >= 0 && id >= c->nextBatch - LA_NUM_LANES && !n; id--)
+    for (long long id = c->nextBatch - 1; id >= 0 && id >= c->nextBatch - LA_NUM_LANES && n < 2; id--)
     {
         const Batch* b = batchOf(c, id);
         if (b && (b->open || cudaEventQuery(b->done) == cudaErrorNotReady)) n++;
@@ -1752,6 +1783,8 @@ int x265cu_cutree_finish(x265cu_ctx* c, int32_t slot, int32_t fps_fix8, double w
         c->g, slotPtr<int>(c, slot, L.intraCost), slotInvQ(c, slot), slotPtr<int>(c, slot, L.propagate),
         slotPtr<double>(c, slot, L.qpAq), slotPtr<double>(c, slot, L.qpCuTree), fps_fix8, weightdelta, strength);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->slotMainWrote[slot], c->stream));
+    c->slotMainWroteSet[slot] = 1;
     return X265CU_OK;
 }
 
@@ -1779,6 +1812,8 @@ int x265cu_cost_recalc(x265cu_ctx* c, int32_t slot, int32_t cost_store, int32_t 
                                                                       rs, (unsigned long long*)c->d_results);
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->slotMainWrote[slot], c->stream));
+    c->slotMainWroteSet[slot] = 1;
     st = ensureMapped(c, 8 + (size_t)g.bh * 4);
     if (st) return st;
     publish_kernel<<<1, 32, 0, c->stream>>>((const unsigned*)c->d_results, (unsigned*)c->d_mapped, 2);
@@ -1873,9 +1908,11 @@ int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_reque
     if (e.ticket >= 0) { HostTimer ht(HT_MIRROR_RINGWAIT); CK(cudaEventSynchronize(e.done)); }  /* the ring wrapped: that request's scratch is free again */
     HostTimer htRest(HT_MIRROR_REST);
     const cudaStream_t ms = c->mirrorStream;
-    /* behind everything the main stream carries so far (cuTree of the decisions taken, cost recalculations) ... */
-    CK(cudaEventRecord(c->mirrorMark, c->stream));
-    CK(cudaStreamWaitEvent(ms, c->mirrorMark, 0));
+    /* behind the main-stream kernels that wrote what is copied here: the last cuTreeFinish (qpCuTreeOffset) / synchronous cost
+     * recalculation (rowSatds) enqueued for THIS slot -- not behind the whole main stream: by the time the encoder takes a
+     * decided frame the next decision's cuTree is already queued there, waiting for the newest batch, and a mirror ordered
+     * behind it stalled the caller (and with it the feed of new pictures) for a whole batch */
+    if (c->slotMainWroteSet[slot]) CK(cudaStreamWaitEvent(ms, c->slotMainWrote[slot], 0));
     /* ... the frame's own pre-lookahead and the batches that wrote the stores asked for */
     CK(cudaStreamWaitEvent(ms, c->slotConsumed[slot], 0));
     int st = X265CU_OK;

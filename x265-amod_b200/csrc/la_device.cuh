@@ -263,6 +263,73 @@ __device__ __forceinline__ int groupSatdRows(const Row<P>& a, const Row<P>& b)
     return groupSatdH(toH(a), toH(b));
 }
 
+/* ---- the same primitives for the FOUR-lanes-per-block decomposition of the motion search: lane l of a 4-lane group owns
+ * rows 2l and 2l+1 of the 8x8 block, a warp works on 8 blocks.  Everything that is uniform inside a group (addresses, mv
+ * costs, comparisons, the search's control flow) is then executed once per 4 lanes instead of once per 8, and the first
+ * vertical Hadamard stage pairs the lane's own two rows in registers instead of going through a shuffle: ncu had the
+ * 8-lane search kernel on the ALU pipe (59-65 % busy, the top pipe) with one third of its instructions group-uniform. */
+
+/* this lane's share (two rows) of an 8x8 SAD */
+__device__ __forceinline__ int sadRows2(const Row<uint8_t>& fa, const Row<uint8_t>& fb, const Row<uint8_t>& pa, const Row<uint8_t>& pb)
+{
+    return (int)(__vsadu4(fa.v[0], pa.v[0]) + __vsadu4(fa.v[1], pa.v[1]) + __vsadu4(fb.v[0], pb.v[0]) + __vsadu4(fb.v[1], pb.v[1]));
+}
+__device__ __forceinline__ int sadRows2(const Row<uint16_t>& fa, const Row<uint16_t>& fb, const Row<uint16_t>& pa, const Row<uint16_t>& pb)
+{
+    /* eight packed |a-b| pairs; each 16-bit lane sums to at most 8 * 1023 */
+    const uint32_t s = absdiffU16x2(fa.v[0], pa.v[0]) + absdiffU16x2(fa.v[1], pa.v[1]) + absdiffU16x2(fa.v[2], pa.v[2]) + absdiffU16x2(fa.v[3], pa.v[3]) +
+                       absdiffU16x2(fb.v[0], pb.v[0]) + absdiffU16x2(fb.v[1], pb.v[1]) + absdiffU16x2(fb.v[2], pb.v[2]) + absdiffU16x2(fb.v[3], pb.v[3]);
+    return (int)((s & 0xffffu) + (s >> 16));
+}
+
+/* sum over the 4 lanes of a group; the whole warp must call it converged */
+__device__ __forceinline__ int group4Sum(int v)
+{
+    v += __shfl_xor_sync(LA_FULL, v, 1);
+    v += __shfl_xor_sync(LA_FULL, v, 2);
+    return v;
+}
+
+/* horizontal half of the SWAR Hadamard of one row (both 4x4 blocks of the row at once) */
+__device__ __forceinline__ void hadamardRowH(const RowH& a, const RowH& b, uint32_t p[4])
+{
+    const uint32_t d0 = a.v[0] - b.v[0], d1 = a.v[1] - b.v[1], d2 = a.v[2] - b.v[2], d3 = a.v[3] - b.v[3];
+    const uint32_t a0 = d0 + d1, a1 = d0 - d1, a2 = d2 + d3, a3 = d2 - d3;
+    p[0] = a0 + a2; p[1] = a1 + a3; p[2] = a0 - a2; p[3] = a1 - a3;
+}
+
+/* 8x8 SATD (two 8x4 SATDs, pixel.cpp:239-297) of each 4-lane group's block; lane l holds rows 2l (a0 / b0) and 2l+1
+ * (a1 / b1) of both operands in RowH order, so lanes 0-1 hold the upper 8x4 and lanes 2-3 the lower.  Vertical
+ * butterflies: rows (2l, 2l+1) in registers, then one xor-1 shuffle stage.  A lane accumulates 8 of the 16 coefficients
+ * of each of its two 4x4 blocks per SWAR half: sum |c| <= 4 * sqrt(16 * 16 * 1023^2) = 65472 < 2^16 (Cauchy-Schwarz over
+ * the whole 4x4 block), so one 32-bit accumulator holds both halves.  Every lane returns the total. */
+__device__ __forceinline__ int group4SatdH(const RowH& a0, const RowH& b0, const RowH& a1, const RowH& b1)
+{
+    uint32_t p0[4], p1[4];
+    hadamardRowH(a0, b0, p0);
+    hadamardRowH(a1, b1, p1);
+    const bool odd = threadIdx.x & 1;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const uint32_t s = p0[i] + p1[i], d = p0[i] - p1[i];
+        const uint32_t ts = __shfl_xor_sync(LA_FULL, s, 1), td = __shfl_xor_sync(LA_FULL, d, 1);
+        const uint32_t qs = odd ? ts - s : s + ts;
+        const uint32_t qd = odd ? td - d : d + td;
+        sum += abs2(qs) + abs2(qd);
+    }
+    int t = (int)((sum & 0xffffu) + (sum >> 16));
+    t += __shfl_xor_sync(LA_FULL, t, 1);
+    return (t >> 1) + (__shfl_xor_sync(LA_FULL, t, 2) >> 1);
+}
+
+template <typename P>
+__device__ __forceinline__ int group4SatdRows(const Row<P>& fa, const Row<P>& fb, const Row<P>& pa, const Row<P>& pb)
+{
+    return group4SatdH(toH(fa), toH(pa), toH(fb), toH(pb));
+}
+
 /* the four tiled half-pel planes of one frame and the origin of the group's block in buffer coordinates */
 template <typename P>
 struct RefBlock

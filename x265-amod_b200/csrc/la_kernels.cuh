@@ -725,7 +725,10 @@ __global__ void __launch_bounds__(128) intra_kernel(Geom g, const P* __restrict_
  * The search is data dependent (MVP choice, hexagon iterations, early exits); it is written with per-group
  * predicates and warp-votes so the warp never diverges, which keeps every shuffle on the full mask.
  * ------------------------------------------------------------------------------------------ */
-#define LA_STRIP_ROWS 4
+#define LA_STRIP_ROWS 4             /* 8-lane decomposition; the 4-lane one has 8 */
+#ifndef LA_SEARCH4_MIN_CTAS
+#define LA_SEARCH4_MIN_CTAS 20      /* 4-lane decomposition: two rows per lane want ~96 registers */
+#endif
 #ifndef LA_SEARCH_MIN_CTAS
 #define LA_SEARCH_MIN_CTAS 28       /* resident one-warp CTAs per SM the register allocation must allow: 72 registers, no spills;
                                        32 (64 registers) spills and measured 3 % slower; 28 also leaves block slots for the short
@@ -815,6 +818,8 @@ struct MeCtx
     int mvpx, mvpy;
     int r;
 
+    __device__ __forceinline__ void init(int lane) { r = lane & 7; }
+    __device__ __forceinline__ void loadFenc(const P* fenc0) { fenc = loadRowAligned(fenc0, rb.tpr, rb.X0, rb.Y0 + r); }
     __device__ __forceinline__ int mvc(int qx, int qy) const
     {
         return (int)(unsigned short)(__ldg(mvcost + (qx - mvpx)) + __ldg(mvcost + (qy - mvpy)));
@@ -825,13 +830,86 @@ struct MeCtx
     __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return qpelCostFn<P>(fenc, rb.plane0, rb.planeSize, rb.tpr, rb.X0, rb.Y0, r, qx, qy, true); }
 };
 
+/* ---- the same evaluators for the 4-lanes-per-block decomposition (la_device.cuh): the lane owns rows r and r + 1 ---- */
+template <typename P>
+__device__ __forceinline__ int sadFpelFn4(Row<P> fa, Row<P> fb, const P* plane0, int tpr, int X, int Yr)
+{
+    return group4Sum(sadRows2(fa, fb, loadRowT(plane0, tpr, X, Yr), loadRowT(plane0, tpr, X, Yr + 1)));
+}
+
+template <typename P>
+__device__ __forceinline__ int3 sad3FpelFn4(Row<P> fa, Row<P> fb, const P* plane0, int tpr, int X, int Yr, int pk)
+{
+    const int x0 = X + ((pk & 15) - 8), y0 = Yr + (((pk >> 4) & 15) - 8);
+    const int x1 = X + (((pk >> 8) & 15) - 8), y1 = Yr + (((pk >> 12) & 15) - 8);
+    const int x2 = X + (((pk >> 16) & 15) - 8), y2 = Yr + (((pk >> 20) & 15) - 8);
+    const int p0 = sadRows2(fa, fb, loadRowT(plane0, tpr, x0, y0), loadRowT(plane0, tpr, x0, y0 + 1));
+    const int p1 = sadRows2(fa, fb, loadRowT(plane0, tpr, x1, y1), loadRowT(plane0, tpr, x1, y1 + 1));
+    const int p2 = sadRows2(fa, fb, loadRowT(plane0, tpr, x2, y2), loadRowT(plane0, tpr, x2, y2 + 1));
+    /* a whole 8x8 SAD is at most 64 * 1023 < 2^16: two of the three sums share one register through the reduction */
+    const int w = group4Sum(p0 | (p1 << 16));
+    return make_int3(w & 0xffff, (int)((unsigned)w >> 16), group4Sum(p2));
+}
+
+template <typename P>
+__device__ __forceinline__ int qpelCostFn4(Row<P> fa, Row<P> fb, const P* plane0, long long planeSize, int tpr, int X0, int Y0, int r2,
+                                          int qx, int qy, bool satd)
+{
+    /* ReferencePlanes::lowresMC (lowres.h:71-96), two rows */
+    const int hA = (qy & 2) | ((qx & 2) >> 1);
+    const P* pA = plane0 + hA * planeSize;
+    const int xa = X0 + (qx >> 2), ya = Y0 + (qy >> 2) + r2;
+    Row<P> a0 = loadRowT(pA, tpr, xa, ya), a1 = loadRowT(pA, tpr, xa, ya + 1);
+    if (__any_sync(LA_FULL, (qx | qy) & 1))
+    {
+        const int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
+        const int hB = (qy2 & 2) | ((qx2 & 2) >> 1);
+        const P* pB = plane0 + hB * planeSize;
+        const int xb = X0 + (qx2 >> 2), yb = Y0 + (qy2 >> 2) + r2;
+        /* for a half/full-pel vector B == A and the rounded average returns A unchanged */
+        a0 = avgRow(a0, loadRowT(pB, tpr, xb, yb));
+        a1 = avgRow(a1, loadRowT(pB, tpr, xb, yb + 1));
+    }
+    if (satd) return group4SatdRows(fa, fb, a0, a1);      /* uniform */
+    return group4Sum(sadRows2(fa, fb, a0, a1));
+}
+
+template <typename P>
+struct MeCtx4
+{
+    Row<P> fa, fb;                  /* rows r and r + 1 of the source block */
+    RefBlock<P> rb;
+    const unsigned short* mvcost;   /* centre */
+    int mvpx, mvpy;
+    int r;                          /* first of this lane's two rows: 0, 2, 4, 6 */
+
+    __device__ __forceinline__ void init(int lane) { r = (lane & 3) * 2; }
+    __device__ __forceinline__ void loadFenc(const P* fenc0)
+    {
+        fa = loadRowAligned(fenc0, rb.tpr, rb.X0, rb.Y0 + r);
+        fb = loadRowAligned(fenc0, rb.tpr, rb.X0, rb.Y0 + r + 1);
+    }
+    __device__ __forceinline__ int mvc(int qx, int qy) const
+    {
+        return (int)(unsigned short)(__ldg(mvcost + (qx - mvpx)) + __ldg(mvcost + (qy - mvpy)));
+    }
+    __device__ __forceinline__ int sadFpel(int x, int y) const { return sadFpelFn4<P>(fa, fb, rb.plane0, rb.tpr, rb.X0 + x, rb.Y0 + y + r); }
+    __device__ __forceinline__ int3 sad3Fpel(int x, int y, int pk) const { return sad3FpelFn4<P>(fa, fb, rb.plane0, rb.tpr, rb.X0 + x, rb.Y0 + y + r, pk); }
+    __device__ __forceinline__ int qpelSad(int qx, int qy) const { return qpelCostFn4<P>(fa, fb, rb.plane0, rb.planeSize, rb.tpr, rb.X0, rb.Y0, r, qx, qy, false); }
+    __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return qpelCostFn4<P>(fa, fb, rb.plane0, rb.planeSize, rb.tpr, rb.X0, rb.Y0, r, qx, qy, true); }
+};
+
+template <typename P, int LPB> struct MeSel;
+template <typename P> struct MeSel<P, 8> { typedef MeCtx<P> T; };
+template <typename P> struct MeSel<P, 4> { typedef MeCtx4<P> T; };
+
 __device__ const signed char c_hex2[8][2] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };
 __device__ const unsigned char c_mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };
 __device__ const signed char c_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };
 
 /* The whole warp calls this converged; every value is uniform inside an 8-lane group. */
-template <typename P>
-__device__ __forceinline__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& out)
+template <typename Ctx>
+__device__ __forceinline__ int motionEstimate(Ctx& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, MV2& out)
 {
     const int merange = 16;
     m.mvpx = qmvp.x; m.mvpy = qmvp.y;
@@ -967,16 +1045,18 @@ __device__ __forceinline__ int motionEstimate(MeCtx<P>& m, MV2 mvmin, MV2 mvmax,
 __device__ __forceinline__ MV2 unpackMv(int p) { MV2 m = { (int)(short)(p & 0xffff), p >> 16 }; return m; }
 __device__ __forceinline__ int packMv(MV2 m) { return (m.x & 0xffff) | (m.y << 16); }
 
-template <typename P>
-__global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nstrips, int njobs,
-                                                    const unsigned short* __restrict__ mvcost,
-                                                    int* ticketCounter, int* progress, unsigned long long* executed)
+template <typename P, int LPB>
+__global__ void __launch_bounds__(32, LPB == 8 ? LA_SEARCH_MIN_CTAS : LA_SEARCH4_MIN_CTAS)
+search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nstrips, int njobs, const unsigned short* __restrict__ mvcost,
+              int* ticketCounter, int* progress, unsigned long long* executed, int oneShot)
 {
+    /* LPB lanes per block: 8 (one row per lane, 4 block rows per strip) or 4 (two rows per lane, 8 block rows per strip) */
+    const int STRIP_ROWS = 32 / LPB;
     const int lane = threadIdx.x;
-    const int grp = lane >> 3, r = lane & 7;
+    const int grp = lane / LPB, r = lane % LPB;
     const int bw = g.bw, bh = g.bh;
-    MeCtx<P> m;
-    m.mvcost = mvcost; m.r = r;
+    typename MeSel<P, LPB>::T m;
+    m.mvcost = mvcost; m.init(lane);
     m.rb.planeSize = g.planeSize; m.rb.tpr = g.tpr;
     /* A warp is a worker: it takes strips from the ticket counter until none are left.  The grid may hold fewer
      * warps than strips (engine.cu sizes it); a warp that finishes a strip picks up the next one, whose
@@ -994,9 +1074,9 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
     if (J.cond && __ldcg(J.cond) == 0) continue;    /* the variant this job would compute is not needed */
     /* strip 0 owns the lowest ticket of its job and every other strip waits on its progress chain */
     if (strip == 0 && lane == 0) { atomicExch(J.flagOut, 0); atomicAdd(executed, 1ull); }
-    const int rowsInStrip = min(LA_STRIP_ROWS, bh - strip * LA_STRIP_ROWS);
+    const int rowsInStrip = min(STRIP_ROWS, bh - strip * STRIP_ROWS);
     const bool rowOk = grp < rowsInStrip;
-    const int cuY = rowOk ? bh - 1 - strip * LA_STRIP_ROWS - grp : 0;
+    const int cuY = rowOk ? bh - 1 - strip * STRIP_ROWS - grp : 0;
     /* the first row a search visits takes no predictors from below: the frame's bottom row, or with cooperative
      * slices (slicetype.cpp:3957-3968) the bottom row of each slice, the last slice running to the frame's end */
     bool lastRow = cuY == bh - 1;
@@ -1023,7 +1103,7 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
         const int cuX = bw - 1 - k;
         const int cu = cuX + cuY * bw;
         m.rb.X0 = g.mx + 8 * cuX; m.rb.Y0 = g.my + 8 * cuY;
-        m.fenc = loadRowAligned(J.fenc0, g.tpr, m.rb.X0, m.rb.Y0 + r);
+        m.loadFenc(J.fenc0);
 
         /* reverse-order MV predictors (slicetype.cpp:4131-4141): right, below, below-left, below-right */
         int cand[4]; bool valid[4];
@@ -1032,9 +1112,9 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
         valid[1] = act && !lastRow; valid[2] = act && !lastRow && cuX > 0; valid[3] = act && !lastRow && cuX < bw - 1;
         cand[0] = h0;
         /* the row below lives in the group below: it finished columns cuX-1, cuX, cuX+1 one, two and three steps ago */
-        cand[2] = __shfl_up_sync(LA_FULL, h0, 8);
-        cand[1] = __shfl_up_sync(LA_FULL, h1, 8);
-        cand[3] = __shfl_up_sync(LA_FULL, h2, 8);
+        cand[2] = __shfl_up_sync(LA_FULL, h0, LPB);
+        cand[1] = __shfl_up_sync(LA_FULL, h1, LPB);
+        cand[3] = __shfl_up_sync(LA_FULL, h2, LPB);
         if (strip > 0 && s < bw)
         {
             /* row below group 0 belongs to the strip below: wait until it has finished column cuX-1 */
@@ -1142,6 +1222,10 @@ __global__ void __launch_bounds__(32, LA_SEARCH_MIN_CTAS) search_kernel(Geom g, 
         }
     }
     __syncwarp();
+    /* one ticket per CTA (the grid then holds one CTA per ticket): a warp slot is given back after every strip, so pending
+     * CTAs of higher-priority streams (pre-lookahead of the next frames, cuTree) get onto the SMs while a long search
+     * launch is running instead of behind it */
+    if (oneShot) return;
     }
 }
 
@@ -1515,8 +1599,23 @@ __global__ void __launch_bounds__(128) block_metrics_kernel(const P* __restrict_
     const int iRaw = blockIdx.x * 16 + grp;
     const int i = min(iRaw, n - 1);
     const Row<P> ra = loadRowPitched(a + (long long)i * 64 + r * 8), rb = loadRowPitched(b + (long long)i * 64 + r * 8);
-    const int sad = groupSum(sadRow(ra, rb));
-    const int satd = groupSatdRows(ra, rb);
+    int sad = groupSum(sadRow(ra, rb));
+    int satd = groupSatdRows(ra, rb);
+    /* the same blocks through the 4-lanes-per-block primitives of the search kernel (two rows per lane); a disagreement
+     * between the two decompositions is reported as -1, which no oracle value equals */
+    __shared__ int s4[2][16];
+    {
+        const int g4 = (threadIdx.x >> 2) & 15, r2 = (threadIdx.x & 3) * 2;
+        const int i4 = min(blockIdx.x * 16 + g4, n - 1);
+        const Row<P> fa = loadRowPitched(a + (long long)i4 * 64 + r2 * 8), fb = loadRowPitched(a + (long long)i4 * 64 + r2 * 8 + 8);
+        const Row<P> pa = loadRowPitched(b + (long long)i4 * 64 + r2 * 8), pb = loadRowPitched(b + (long long)i4 * 64 + r2 * 8 + 8);
+        const int sad4 = group4Sum(sadRows2(fa, fb, pa, pb));
+        const int satd4 = group4SatdRows(fa, fb, pa, pb);
+        if (threadIdx.x < 64 && (threadIdx.x & 3) == 0) { s4[0][g4] = sad4; s4[1][g4] = satd4; }
+    }
+    __syncthreads();
+    if (s4[0][grp] != sad) sad = -1;
+    if (s4[1][grp] != satd) satd = -1;
     if (r == 0 && iRaw < n) { sadOut[i] = sad; satdOut[i] = satd; }
 }
 

@@ -290,7 +290,7 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     if (m_param.speculate)
     {
         m_pendingSpec.push_back(f);
-        if (m_param.speculate == 1 && m_param.shardCount <= 1 && (int)m_pendingSpec.size() >= std::min(m_param.batchMin, 4))
+        if (m_param.speculate == 1 && m_param.shardCount <= 1 && (int)m_pendingSpec.size() >= std::min(m_param.batchMin, 8))
         {
             /* per-decision mode, window still filling (or the host far ahead of the GPU): hand the frames whose
              * pre-lookahead has finished to the GPU in launches of batchMin frames instead of one launch at the first decision */
@@ -617,12 +617,13 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
      * up and draining) */
     if (m_param.speculate == 1 && !m_pendingSpec.empty() && m_pendingSpec.front()->m_poc > mustPoc)
     {
-        /* ... unless the GPU has nothing left to do (pictures arrive slower than it consumes them): then a smaller launch
-         * now beats a full one later.  A sharded stream must batch the same frames on every rank, so it never asks. */
-        const int minFrames = std::min(m_param.batchMin, 4);
-        const bool idle = !sharded && (int)m_pendingSpec.size() >= minFrames && (int)m_pendingSpec.size() < m_param.batchMin &&
-                          x265cu_batches_in_flight(m_ctx) == 0;
-        const int want = idle ? minFrames : m_param.batchMin;
+        /* ... unless the GPU is about to run dry: it should always hold the batch it is working on AND one queued behind
+         * it (whose search launch ramps up while the first one drains), so with fewer than two in flight a smaller launch now
+         * beats a full one later.  A sharded stream must batch the same frames on every rank, so it never asks. */
+        const int minFrames = std::min(m_param.batchMin, 8);
+        const bool hungry = !sharded && (int)m_pendingSpec.size() >= minFrames && (int)m_pendingSpec.size() < m_param.batchMin &&
+                            x265cu_batches_in_flight(m_ctx) < 2;
+        const int want = hungry ? minFrames : m_param.batchMin;
         if ((int)m_pendingSpec.size() < want)
             return;
     }
