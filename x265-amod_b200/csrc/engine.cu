@@ -103,6 +103,7 @@ struct x265cu_ctx
     cudaEvent_t mirrorMark;
     struct MirrorEntry { cudaEvent_t done; char* scratch; size_t cap; long long ticket; } mirror[X265CU_MIRROR_RING];
     long long nextMirror;
+    std::map<void*, void*> mappedCache;         /* host pointer -> device address of page-locked memory (NULL: not page-locked) */
     std::vector<cudaEvent_t> slotMirrored;      /* per slot: the last mirror request that read it */
     std::vector<char> slotMirrorTouched;
     /* cost recalculation ahead of time (x265cu_cost_recalc_enqueue): per slot {score, rows[bh]} in device scratch + event */
@@ -142,6 +143,7 @@ struct x265cu_ctx
     int searchLanes;                /* lanes per 8x8 block in the search kernel: 4 (default; two rows per lane, strips of 8 block rows) or
                                        8 (one row per lane, strips of 4; env X265CU_SEARCH_LANES, kept for A/B measurements) */
     int searchOneShot;              /* one ticket per search CTA instead of persistent workers (env X265CU_SEARCH_ONESHOT) */
+    int costLanes;                  /* lanes per block in the grouped cost kernel: 4 (default) or 8 (env X265CU_COST_LANES, for A/B) */
     long long bigSearch[2];         /* the two most recent batches with a large search launch (see searchBatchT), -1 = none */
     bool profile;
     double profMs[X265CU_K_COUNT], profBusy[X265CU_K_COUNT];
@@ -1018,8 +1020,9 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         const int ng = (int)groups.size();
         for (int base = 0; base < ng; base += 65535)
         {
-            dim3 gg((g.ncu + 15) / 16, (unsigned)((ng - base) < 65535 ? (ng - base) : 65535));
-            cost_group_kernel<P><<<gg, 128, 0, b->stream>>>(g, (const CostGroupDev<P>*)dgr + base);
+            const unsigned ny = (unsigned)((ng - base) < 65535 ? (ng - base) : 65535);
+            if (c->costLanes == 8) cost_group_kernel<P><<<dim3((g.ncu + 15) / 16, ny), 128, 0, b->stream>>>(g, (const CostGroupDev<P>*)dgr + base);
+            else cost_group_kernel4<P><<<dim3((g.ncu + 31) / 32, ny), 128, 0, b->stream>>>(g, (const CostGroupDev<P>*)dgr + base);
         }
     }
     CK(cudaGetLastError());
@@ -1165,9 +1168,10 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
     c->searchSmem = getenv("X265CU_SEARCH_SMEM") ? atoi(getenv("X265CU_SEARCH_SMEM")) : 0;
-    c->searchLanes = getenv("X265CU_SEARCH_LANES") && atoi(getenv("X265CU_SEARCH_LANES")) == 8 ? 8 : 4;
+    c->searchLanes = getenv("X265CU_SEARCH_LANES") && atoi(getenv("X265CU_SEARCH_LANES")) == 4 ? 4 : 8;
     c->searchOneShot = getenv("X265CU_SEARCH_ONESHOT") ? atoi(getenv("X265CU_SEARCH_ONESHOT")) : 0;
     c->bigSearch[0] = c->bigSearch[1] = -1;
+    c->costLanes = getenv("X265CU_COST_LANES") && atoi(getenv("X265CU_COST_LANES")) == 8 ? 8 : 4;
     c->numSMs = 148;
     cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, cfg->device);
     c->profile = false; c->evUsed = 0; c->nextBatch = 0; c->cur = NULL; c->searchEnq = c->costEnq = 0;
@@ -1431,7 +1435,8 @@ int x265cu_pin_host(x265cu_ctx* c, void* ptr, uint64_t bytes)
 {
     if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
-    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    c->mappedCache.clear();
     return X265CU_OK;
 }
 int x265cu_unpin_host(x265cu_ctx* c, void* ptr)
@@ -1439,6 +1444,7 @@ int x265cu_unpin_host(x265cu_ctx* c, void* ptr)
     if (!c) return X265CU_ERR_BAD_ARG;
     DeviceScope deviceScope(c);
     CK(cudaHostUnregister(ptr));
+    c->mappedCache.clear();
     return X265CU_OK;
 }
 
@@ -1895,6 +1901,45 @@ __global__ void __launch_bounds__(256) unpack_mvs_kernel(UnpackTab t, int n)
     ((int2*)t.dst[blockIdx.y])[i] = v;
 }
 
+/* The small arrays of a mirror request in ONE launch: the kernel stores straight into the caller's page-locked arrays (registered
+ * host memory is mapped into the device's address space), so a request costs one kernel launch instead of ~30 cudaMemcpyAsync
+ * calls of 130-260 KB each -- measured 0.5-0.8 ms of host time per decided frame, the largest single item of the end-to-end
+ * run.  kind 0: copy 32-bit words; kind 1: packed (int16, int16) MVs -> (int32, int32) pairs (Lowres::lowresMvs). */
+struct MirrorSeg { const unsigned* src; unsigned* dst; unsigned words; unsigned kind; };
+enum { LA_MIRROR_SEGS = X265CU_MIRROR_MAX_MV + 8 };
+struct MirrorTab { MirrorSeg s[LA_MIRROR_SEGS]; };
+__global__ void __launch_bounds__(256) mirror_scatter_kernel(MirrorTab t)
+{
+    const MirrorSeg sg = t.s[blockIdx.y];
+    if (sg.kind == 0)
+    {
+        /* 16 bytes per thread where source, destination and length allow (all device arrays are 256-byte aligned) */
+        const unsigned n4 = ((((size_t)sg.dst | (size_t)sg.src) & 15) == 0) ? sg.words >> 2 : 0;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+            ((uint4*)sg.dst)[i] = ((const uint4*)sg.src)[i];
+        for (unsigned i = n4 * 4 + blockIdx.x * blockDim.x + threadIdx.x; i < sg.words; i += gridDim.x * blockDim.x)
+            sg.dst[i] = sg.src[i];
+    }
+    else
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.words; i += gridDim.x * blockDim.x)
+        {
+            const int p = (int)sg.src[i];
+            uint2 v; v.x = (unsigned)(int)(short)(p & 0xffff); v.y = (unsigned)(p >> 16);
+            ((uint2*)sg.dst)[i] = v;
+        }
+}
+
+/* device address of a host pointer inside a page-locked (registered) range, or NULL; looked up once per pointer */
+static void* mappedPtr(x265cu_ctx* c, void* host)
+{
+    std::map<void*, void*>::iterator it = c->mappedCache.find(host);
+    if (it != c->mappedCache.end()) return it->second;
+    void* dev = NULL;
+    if (cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) { cudaGetLastError(); dev = NULL; }
+    c->mappedCache[host] = dev;
+    return dev;
+}
+
 int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_request* q, int64_t* ticket)
 {
     if (!c || !q) return X265CU_ERR_BAD_ARG;
@@ -1916,24 +1961,88 @@ int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_reque
     /* ... the frame's own pre-lookahead and the batches that wrote the stores asked for */
     CK(cudaStreamWaitEvent(ms, c->slotConsumed[slot], 0));
     int st = X265CU_OK;
+    long long waitedFor[X265CU_MIRROR_MAX_MV]; int nWaited = 0;     /* most stores of a frame were written by the same few batches */
     for (int i = 0; i < q->n_mv && !st; i++)
     {
         if (q->mv_store[i] < 0 || q->mv_store[i] >= c->geom.n_mv_stores || !q->mv_dst[i]) return X265CU_ERR_BAD_ARG;
-        st = streamWaitBatch(c, ms, c->mvWriter[(size_t)slot * c->geom.n_mv_stores + q->mv_store[i]], c->nranks <= 1);
+        const long long w = c->mvWriter[(size_t)slot * c->geom.n_mv_stores + q->mv_store[i]];
+        bool seen = false;
+        for (int k = 0; k < nWaited; k++) seen |= waitedFor[k] == w;
+        if (seen) continue;
+        waitedFor[nWaited++] = w;
+        st = streamWaitBatch(c, ms, w, c->nranks <= 1);
     }
     if (!st && q->cost_store >= 2) st = streamWaitBatch(c, ms, c->costWriter[(size_t)slot * c->geom.n_cost_stores + q->cost_store], false);
     if (st) return st;
+    /* fast path: every small destination array is page-locked => one scatter kernel writes them all */
+    bool direct = getenv("X265CU_MIRROR_MEMCPY") == NULL;
+    MirrorTab tab; int nseg = 0; size_t segBytes = 0; unsigned maxWords = 0;
+    if (direct)
+    {
+        struct Add
+        {
+            static bool seg(x265cu_ctx* c, MirrorTab& t, int& n, size_t& bytes, unsigned& maxWords, const void* src, void* hostDst, size_t words, unsigned kind)
+            {
+                if (!hostDst) return true;
+                void* d = mappedPtr(c, hostDst);
+                if (!d || n >= LA_MIRROR_SEGS) return false;
+                t.s[n].src = (const unsigned*)src; t.s[n].dst = (unsigned*)d; t.s[n].words = (unsigned)words; t.s[n].kind = kind;
+                n++; bytes += words * (kind ? 8 : 4); maxWords = std::max(maxWords, (unsigned)words);
+                return true;
+            }
+        };
+        direct = Add::seg(c, tab, nseg, segBytes, maxWords, c->slots[slot] + L.intraCost, q->intra_cost, g.ncu, 0) &&
+                 Add::seg(c, tab, nseg, segBytes, maxWords, c->slots[slot] + L.qpAq, q->qp_aq_offset, (size_t)g.ncuFull * 2, 0) &&
+                 Add::seg(c, tab, nseg, segBytes, maxWords, c->slots[slot] + L.qpCuTree, q->qp_cutree_offset, (size_t)g.ncuFull * 2, 0) &&
+                 (!c->cfg.need_aq || Add::seg(c, tab, nseg, segBytes, maxWords, c->slots[slot] + L.invQ, q->inv_qscale_factor, g.ncuFull, 0));
+        for (int i = 0; direct && i < q->n_mv; i++)
+            direct = Add::seg(c, tab, nseg, segBytes, maxWords, mvStorePtr(c, slot, q->mv_store[i]), q->mv_dst[i], g.ncu, 1);
+        if (direct && q->cost_store >= 0 && (q->lowres_costs || q->row_satds))
+        {
+            const char* cs = q->cost_store == 0 ? NULL : costStorePtr(c, slot, q->cost_store);
+            /* lowresCosts are 16-bit: whole words only when the block count is even, else that one array goes the slow way */
+            if (q->lowres_costs && (g.ncu & 1)) direct = false;
+            direct = direct && Add::seg(c, tab, nseg, segBytes, maxWords, cs ? cs : c->slots[slot] + L.lowresCosts00, q->lowres_costs, g.ncu / 2, 0) &&
+                     Add::seg(c, tab, nseg, segBytes, maxWords, cs ? cs + L.costRowOff : c->slots[slot] + L.rowSatds00, q->row_satds, g.bh, 0);
+        }
+    }
     const size_t planeBytes = q->planes ? alignUp((size_t)(4 * g.planeSize) * c->bpp, 256) : 0;
     const size_t mvBytes = alignUp((size_t)g.ncu * 8, 256);
-    const size_t need = planeBytes + mvBytes * q->n_mv + 256;
+    const size_t need = planeBytes + (direct ? 0 : mvBytes * q->n_mv) + 256;
     if (e.cap < need)
     {
+        /* cudaFree / cudaMalloc wait for the whole device: with several batches queued that is tens of milliseconds per call
+         * (measured: 23 calls, 175 - 1100 ms per 300-frame step while the ring entries grew one request at a time).  So the
+         * first request that needs scratch sizes EVERY ring entry for the largest request there can be, once. */
         HostTimer ht(HT_MIRROR_MALLOC);
-        cudaFree(e.scratch); e.scratch = NULL; e.cap = 0;
-        CK(cudaMalloc((void**)&e.scratch, need));
-        e.cap = need;
+        const size_t full = alignUp((size_t)(4 * g.planeSize) * c->bpp, 256) + mvBytes * X265CU_MIRROR_MAX_MV + 256;
+        for (int i = 0; i < X265CU_MIRROR_RING; i++)
+        {
+            x265cu_ctx::MirrorEntry& m = c->mirror[i];
+            if (m.cap >= full) continue;
+            if (m.ticket >= 0) CK(cudaEventSynchronize(m.done));
+            if (m.scratch) cudaFree(m.scratch);
+            m.scratch = NULL; m.cap = 0;
+            CK(cudaMalloc((void**)&m.scratch, full));
+            m.cap = full;
+        }
     }
 #define MIRROR_D2H(dst, src, bytes) do { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ms)); c->counters.d2h_bytes += (bytes); } while (0)
+    if (direct)
+    {
+        if (q->inv_qscale_factor && !c->cfg.need_aq) for (int i = 0; i < g.ncuFull; i++) q->inv_qscale_factor[i] = 256;
+        if (nseg)
+        {
+            for (int i = nseg; i < LA_MIRROR_SEGS; i++) tab.s[i].words = 0;
+            const unsigned gx = std::max(1u, std::min(64u, (maxWords / 4 + 255) / 256));
+            mirror_scatter_kernel<<<dim3(gx, nseg), 256, 0, ms>>>(tab);
+            c->counters.kernel_launches++;
+            c->counters.d2h_bytes += segBytes;
+            CK(cudaGetLastError());
+        }
+    }
+    else
+    {
     if (q->intra_cost) MIRROR_D2H(q->intra_cost, c->slots[slot] + L.intraCost, (size_t)g.ncu * 4);
     if (q->qp_aq_offset) MIRROR_D2H(q->qp_aq_offset, c->slots[slot] + L.qpAq, (size_t)g.ncuFull * 8);
     if (q->qp_cutree_offset) MIRROR_D2H(q->qp_cutree_offset, c->slots[slot] + L.qpCuTree, (size_t)g.ncuFull * 8);
@@ -1960,6 +2069,7 @@ int x265cu_mirror_enqueue(x265cu_ctx* c, int32_t slot, const x265cu_mirror_reque
         const char* cs = q->cost_store == 0 ? NULL : costStorePtr(c, slot, q->cost_store);
         if (q->lowres_costs) MIRROR_D2H(q->lowres_costs, cs ? cs : c->slots[slot] + L.lowresCosts00, (size_t)g.ncu * 2);
         if (q->row_satds) MIRROR_D2H(q->row_satds, cs ? cs + L.costRowOff : c->slots[slot] + L.rowSatds00, (size_t)g.bh * 4);
+    }
     }
     if (q->planes)
     {

@@ -191,8 +191,14 @@ __device__ __forceinline__ void diffRow(const Row<P>& a, const Row<P>& b, int d[
 }
 
 /* sum over the 8 lanes of a group; the whole warp must call it converged */
+#ifndef LA_REDUX
+#define LA_REDUX 0      /* 1: REDUX.SUM over the group's 8 lanes instead of three shuffle + add stages (tuning variant) */
+#endif
 __device__ __forceinline__ int groupSum(int v)
 {
+#if LA_REDUX
+    return (int)__reduce_add_sync(0xffu << (threadIdx.x & 24), (unsigned)v);
+#endif
     v += __shfl_xor_sync(LA_FULL, v, 1);
     v += __shfl_xor_sync(LA_FULL, v, 2);
     v += __shfl_xor_sync(LA_FULL, v, 4);
