@@ -33,6 +33,7 @@
 using namespace la;
 
 #include <chrono>
+#include <mutex>
 /* host-side stopwatch for tuning (X265CU_HOST_TIMING=1 prints the totals when a context is destroyed) */
 enum { HT_UPLOAD, HT_BATCH_BEGIN, HT_SEARCH_ENQ, HT_COST_ENQ, HT_BATCH_END, HT_GATHER, HT_MIRROR_RINGWAIT, HT_MIRROR_MALLOC, HT_MIRROR_REST,
        HT_STATS_WAIT, HT_RECALC_GET, HT_CUTREE, HT_WEIGHT, HT_COUNT };
@@ -181,6 +182,9 @@ struct DeviceScope
     ~DeviceScope() { if (prev != want && prev >= 0) cudaSetDevice(prev); }
 };
 
+static std::mutex g_evMutex;
+static std::map<int, std::vector<std::pair<cudaEvent_t, cudaEvent_t> > > g_evFree;     /* per device: timing event pairs not in use */
+
 /* Brackets the launches of one kernel family with a pair of CUDA events on the launching stream.
  * Nothing blocks here; the pairs are resolved when the caller asks for the totals. */
 struct Prof
@@ -194,8 +198,16 @@ struct Prof
         {
             if (c->evUsed == c->evPool.size())
             {
+                /* timing events are recycled across contexts of the same device (a bench step opens a new context and
+                 * brackets ~2000 launches: 4000 cudaEventCreate calls per step otherwise) */
                 x265cu_ctx::EvPair e;
-                cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.kind = 0;
+                e.a = e.b = NULL; e.kind = 0;
+                {
+                    std::lock_guard<std::mutex> lock(g_evMutex);
+                    std::vector<std::pair<cudaEvent_t, cudaEvent_t> >& fr = g_evFree[c->cfg.device];
+                    if (!fr.empty()) { e.a = fr.back().first; e.b = fr.back().second; fr.pop_back(); }
+                }
+                if (!e.a) { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
                 c->evPool.push_back(e);
             }
             idx = (int)c->evUsed++;
@@ -388,6 +400,49 @@ int gatherSmall(x265cu_ctx* c, const std::vector<const void*>& srcs, int wordsEa
     return X265CU_OK;
 }
 
+/* Small host <-> device transfers on the paths the GPU waits for go through a KERNEL that reads / writes mapped page-locked host
+ * memory, never through cudaMemcpyAsync: the copy engines are FIFO across streams, and in an end-to-end run the H2D engine
+ * is saturated by picture uploads (25 MB every 0.46 ms at 2160p main10) -- a 36 KB job array queued behind them held the
+ * first search launch of a stream back by 60 ms (every picture of the window fill went first), and the 0.5 KB result of a
+ * cost recalculation waited 0.4 ms behind a 21 MB plane mirror on the D2H engine.  Also zeroes `zeroWords` words at `zero`. */
+struct StageSeg { const uint4* src; uint4* dst; unsigned n16; unsigned pad; };
+struct StageTab { StageSeg s[3]; unsigned* zero; unsigned zeroWords; };
+__global__ void __launch_bounds__(256) stage_kernel(StageTab t)
+{
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        for (unsigned i = tid; i < t.s[k].n16; i += nth) t.s[k].dst[i] = t.s[k].src[i];
+    for (unsigned i = tid; i < t.zeroWords; i += nth) t.zero[i] = 0;
+}
+
+/* device-visible address of page-locked host memory allocated by this library */
+static void* hostAlias(void* h)
+{
+    void* d = NULL;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return d;
+}
+
+/* up to three (dst, src, bytes) copies -- bytes a multiple of 16, both ends 16-byte aligned; the host side of each must be
+ * page-locked memory of this library -- and one zero fill, as one launch on `stream` */
+int stageLaunch(x265cu_ctx* c, cudaStream_t stream, void* dst0, const void* src0, size_t bytes0, void* dst1, const void* src1, size_t bytes1,
+                unsigned* zero, size_t zeroWords)
+{
+    StageTab t;
+    memset(&t, 0, sizeof(t));
+    t.s[0].dst = (uint4*)dst0; t.s[0].src = (const uint4*)src0; t.s[0].n16 = (unsigned)(bytes0 / 16);
+    t.s[1].dst = (uint4*)dst1; t.s[1].src = (const uint4*)src1; t.s[1].n16 = (unsigned)(bytes1 / 16);
+    t.zero = zero; t.zeroWords = (unsigned)zeroWords;
+    const size_t work = std::max(std::max(bytes0, bytes1) / 16, zeroWords);
+    if (!work) return X265CU_OK;
+    const unsigned grid = (unsigned)std::max((size_t)1, std::min((size_t)64, (work + 255) / 256));
+    stage_kernel<<<grid, 256, 0, stream>>>(t);
+    c->counters.kernel_launches++;
+    CK(cudaGetLastError());
+    return X265CU_OK;
+}
+
 /* ---------------------------------------------------------------- batches */
 
 Batch* batchOf(x265cu_ctx* c, long long id)
@@ -546,7 +601,7 @@ int batchStage(x265cu_ctx* c, Batch* b, size_t bytes, char** h, char** d)
         if (b->h_stage) { b->retiredHost.push_back(b->h_stage); b->retiredDev.push_back(b->d_stage); }
         b->h_stage = NULL; b->d_stage = NULL; b->stageUsed = 0;
         b->stageCap = alignUp(std::max(bytes * 2, b->stageCap * 2), 4096);
-        CK(cudaMallocHost((void**)&b->h_stage, b->stageCap));
+        CK(cudaHostAlloc((void**)&b->h_stage, b->stageCap, cudaHostAllocMapped));
         CK(cudaMalloc((void**)&b->d_stage, b->stageCap));
     }
     *h = b->h_stage + b->stageUsed; *d = b->d_stage + b->stageUsed;
@@ -864,8 +919,12 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
     int* dsync;
     st = batchSync(c, b, (size_t)(1 + n * nstrips), &dsync);
     if (st) return st;
-    CK(cudaMemcpyAsync(dst, hst, n * sizeof(SearchJobDev<P>), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaMemsetAsync(dsync, 0, (size_t)(1 + n * nstrips) * sizeof(int), b->stream));
+    {
+        void* hAlias = hostAlias(hst);
+        if (!hAlias) { snprintf(c->err, sizeof(c->err), "job staging memory is not device-visible"); return X265CU_ERR_CUDA; }
+        st = stageLaunch(c, b->stream, dst, hAlias, alignUp(n * sizeof(SearchJobDev<P>), 16), NULL, NULL, 0, (unsigned*)dsync, (size_t)(1 + n * nstrips));
+        if (st) return st;
+    }
     if (n >= 64 && c->bigSearch[1] != b->id)
     {
         /* Large search launches of different batches run on different lanes with equal priority; left alone, the launches of
@@ -1005,9 +1064,15 @@ int costBatchT(x265cu_ctx* c, const x265cu_cost_job* jobs, int n)
         st = batchStage(c, b, groups.size() * sizeof(CostGroupDev<P>), &hgr, &dgr);
         if (st) return st;
         memcpy(hgr, &groups[0], groups.size() * sizeof(CostGroupDev<P>));
-        CK(cudaMemcpyAsync(dgr, hgr, groups.size() * sizeof(CostGroupDev<P>), cudaMemcpyHostToDevice, b->stream));
     }
-    CK(cudaMemcpyAsync(dst, hst, n * sizeof(CostJobDev<P>), cudaMemcpyHostToDevice, b->stream));
+    {
+        void* hAlias = hostAlias(hst);
+        void* gAlias = hgr ? hostAlias(hgr) : NULL;
+        if (!hAlias || (hgr && !gAlias)) { snprintf(c->err, sizeof(c->err), "job staging memory is not device-visible"); return X265CU_ERR_CUDA; }
+        st = stageLaunch(c, b->stream, dst, hAlias, alignUp(n * sizeof(CostJobDev<P>), 16), dgr, gAlias,
+                         alignUp(groups.size() * sizeof(CostGroupDev<P>), 16), NULL, 0);
+        if (st) return st;
+    }
     {
         Prof pr(c, X265CU_K_COST, 1 + (nP > 0) + (n > nP), b->stream);
         for (int base = 0; base < n; base += 65535)
@@ -1325,7 +1390,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
         const size_t perFrameSync = 3 * B1 * nstripsEst * sizeof(int) + 64;
         b.stageCap = alignUp(std::max((size_t)256 << 10, perFrameStage * 96), 4096);
         b.syncCap = alignUp(std::max((size_t)64 << 10, perFrameSync * 96), 4096);
-        if (cudaMallocHost((void**)&b.h_stage, b.stageCap) != cudaSuccess || cudaMalloc((void**)&b.d_stage, b.stageCap) != cudaSuccess ||
+        if (cudaHostAlloc((void**)&b.h_stage, b.stageCap, cudaHostAllocMapped) != cudaSuccess || cudaMalloc((void**)&b.d_stage, b.stageCap) != cudaSuccess ||
             cudaMalloc((void**)&b.d_sync, b.syncCap) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     }
     if (!rc && cfg->need_wp_stats && ensureScratch(c, c->mainScratch, c->stream, 1) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
@@ -1333,7 +1398,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     {
         c->recalcStride = alignUp(8 + (size_t)g.bh * 4, 256);
         if (cudaMalloc((void**)&c->d_recalc, c->recalcStride * cfg->max_slots) != cudaSuccess ||
-            cudaHostAlloc((void**)&c->h_recalc, c->recalcStride * cfg->max_slots, cudaHostAllocDefault) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+            cudaHostAlloc((void**)&c->h_recalc, c->recalcStride * cfg->max_slots, cudaHostAllocMapped) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     }
     if (!rc)
     {
@@ -1379,7 +1444,15 @@ void x265cu_destroy(x265cu_ctx* c)
     if (c->gatherStream) cudaStreamDestroy(c->gatherStream);
     if (c->mirrorMark) cudaEventDestroy(c->mirrorMark);
     cudaFree(c->d_recalc); if (c->h_recalc) cudaFreeHost(c->h_recalc);
-    for (size_t i = 0; i < c->evPool.size(); i++) { cudaEventDestroy(c->evPool[i].a); cudaEventDestroy(c->evPool[i].b); }
+    {
+        std::lock_guard<std::mutex> lock(g_evMutex);
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t> >& fr = g_evFree[c->cfg.device];
+        for (size_t i = 0; i < c->evPool.size(); i++)
+        {
+            if (fr.size() < 16384) fr.push_back(std::make_pair(c->evPool[i].a, c->evPool[i].b));
+            else { cudaEventDestroy(c->evPool[i].a); cudaEventDestroy(c->evPool[i].b); }
+        }
+    }
     for (size_t i = 0; i < c->mainScratch.size(); i++) cudaFree(c->mainScratch[i]);
     for (int i = 0; i < LA_NUM_BATCHES; i++)
     {
@@ -2121,7 +2194,12 @@ int x265cu_cost_recalc_enqueue(x265cu_ctx* c, int32_t slot, int32_t cost_store, 
                                                                       (int*)(scratch + 8), (unsigned long long*)scratch);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_recalc + (size_t)slot * c->recalcStride, scratch, 8 + (size_t)g.bh * 4, cudaMemcpyDeviceToHost, c->stream));
+    {
+        void* hAlias = hostAlias(c->h_recalc + (size_t)slot * c->recalcStride);
+        if (!hAlias) { snprintf(c->err, sizeof(c->err), "recalc result memory is not device-visible"); return X265CU_ERR_CUDA; }
+        st = stageLaunch(c, c->stream, hAlias, scratch, alignUp(8 + (size_t)g.bh * 4, 16), NULL, NULL, 0, NULL, 0);
+        if (st) return st;
+    }
     CK(cudaEventRecord(c->slotRecalc[slot], c->stream));
     c->slotRecalcStore[slot] = cost_store;
     return X265CU_OK;
