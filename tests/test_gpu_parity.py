@@ -263,7 +263,8 @@ def test_cuda_one_stream_sharded_over_two_gpus(case_name, pkg, synth):
         assert p.exitcode == 0
     case = cases.get_case(case_name)
     if refbind.available(case[1]):
-        want = cases.run_reference(refbind, synth, case, planes=False)
+        # the shard workers run no getEstimatedPictureCost (rate control belongs to the decision rank's caller): the same here
+        want = cases.run_reference(refbind, synth, case, planes=False, estimate=False)
     else:
         want = golden_io.load(case_name)
     for rank, blob in res:
