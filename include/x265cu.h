@@ -60,7 +60,9 @@ typedef struct
     int32_t mv_store_kinds;     /* MV stores per slot = this * (bframes+2); 0 = 3 (L0 in P context, L0 in B context, L1).
                                    6 when sliced and unsliced variants of a search can both be needed */
     int32_t cost_variants;      /* cost stores per slot = this * (bframes+2)^2; 0 = 2 */
-    int32_t reserved[5];
+    int32_t fade_stats;         /* x265_param::bEnableFades: Lowres::frameVariance per frame and the second acEnergyCu pass'
+                                   side effect on wp_ssd / wp_sum (slicetype.cpp:697-712).  Needs need_aq, qg-size > 8 */
+    int32_t reserved[4];
 } x265cu_config;
 
 /* derived geometry, as Lowres::create computes it */
@@ -106,6 +108,7 @@ typedef struct
     int64_t  cost_est_aq;   /* Lowres::costEstAq[0][0] */
     uint64_t wp_ssd[3];     /* Lowres::wp_ssd (finalised, slicetype.cpp:681-694) */
     uint64_t wp_sum[3];     /* Lowres::wp_sum */
+    double   frame_variance;/* Lowres::frameVariance (x265cu_config::fade_stats), else 0 */
 } x265cu_frame_stats;
 /* 1 when the pre-lookahead of the frame in `slot` has finished (x265cu_frame_stats_get would not wait), 0 when it is
  * still running, negative on error.  Never blocks. */

@@ -130,7 +130,7 @@ bool cudaLookaheadCreate(Lookahead& self)
     else if (p->bAQMotion) why = "--aq-motion";
     else if (p->bEnableTemporalSubLayers > 2) why = "--temporal-layers > 2";
     else if (p->analysisLoad || p->bAnalysisType == AVC_INFO) why = "--analysis-load";
-    else if (p->bEnableFades) why = "--fades";
+    else if (p->bEnableFades && p->rc.qgSize == 8) why = "--fades with --qg-size 8";
     else if (p->bDynamicRefine) why = "--dynamic-refine";
     else if (p->rc.bStatRead && p->rc.cuTree) why = "2-pass cutree";
     else if (p->internalCsp != X265_CSP_I420 && p->internalCsp != X265_CSP_I400) why = "chroma formats other than 4:2:0 / 4:0:0";
@@ -157,6 +157,7 @@ bool cudaLookaheadCreate(Lookahead& self)
     q.rateControlMode = p->rc.rateControlMode;
     q.poolWorkers = self.m_pool ? self.m_pool->m_numWorkers : 0;
     q.gopLookahead = p->gopLookahead; q.radl = p->radl; q.csvLogLevel = p->csvLogLevel;
+    q.bEnableFades = p->bEnableFades;
     q.device = envInt("X265_CUDA_DEVICE", 0);
     /* extra frames of input delay that keep the GPU busy while the host decides (same decisions, LookaheadParam::asyncDepth) */
     q.asyncDepth = envInt("X265_CUDA_ASYNC_DEPTH", 16);
@@ -286,6 +287,12 @@ Frame* cudaLookaheadGetDecided(Lookahead& self)
     l.sliceType = info.sliceType; l.bScenecut = !!info.bScenecut; l.bKeyframe = !!info.bKeyframe;
     l.bLastMiniGopBFrame = !!info.bLastMiniGopBFrame; l.leadingBframes = info.leadingBframes;
     l.ipCostRatio = x265la_frame_ip_cost_ratio(st->la, info.handle);
+    if (p->bEnableFades)
+    {
+        int32_t fadeEnd = 0; double variance = 0;
+        x265la_frame_fade(st->la, info.handle, &fadeEnd, &variance);
+        l.bIsFadeEnd = !!fadeEnd; l.frameVariance = variance;     /* ratecontrol.cpp:1416 reads bIsFadeEnd */
+    }
     f->m_reorderedPts = info.reorderedPts;
 
     std::vector<int64_t> ce(nb * nb), cea(nb * nb);

@@ -267,6 +267,36 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
     free(energy);
 }
 
+/* --fades: the tail of calcAdaptiveQuantFrame (encoder/slicetype.cpp:697-712).  A second acEnergyCu pass over the picture
+ * fills blockVariance and sums it into frameVariance: the row sum is never reset between rows, its division by maxCol is an
+ * integer one, and maxCol / maxRow are the values the weightp block above left behind (the size rounded to 16, :683-684) when
+ * weightp is on.  acEnergyVar's side effect (:54-55) adds every block's sum / ssd to wp_sum / wp_ssd once more, after they
+ * were finalised.  Call after or_aq_frame. */
+double or_fade_variance(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v, int strideC,
+                        int bWeightP, uint64_t wp_ssd[3], uint64_t wp_sum[3])
+{
+    const int W = g->picW, H = g->picH;
+    const int qg8 = g->qg8, incr = qg8 ? 8 : 16;
+    const int maxCol = bWeightP ? ((W + 8) >> 4) << 4 : W, maxRow = bWeightP ? ((H + 8) >> 4) << 4 : H;
+    uint64_t rowVariance = 0;
+    double frameVariance = 0;
+    for (int by = 0; by < maxRow; by += incr)
+    {
+        for (int bx = 0; bx < maxCol; bx += incr)
+        {
+            uint32_t e = block_energy(y, strideY, W, H, bx, by, incr, qg8 ? 6 : 8, &wp_sum[0], &wp_ssd[0]);
+            if (u && v)
+            {
+                e += block_energy(u, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, incr / 2, qg8 ? 4 : 6, &wp_sum[1], &wp_ssd[1]);
+                e += block_energy(v, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, incr / 2, qg8 ? 4 : 6, &wp_sum[2], &wp_ssd[2]);
+            }
+            rowVariance += e;
+        }
+        frameVariance += (double)(rowVariance / (uint64_t)maxCol);
+    }
+    return frameVariance / maxRow;
+}
+
 /* ------------------------------------------------------------------ intra */
 
 /* common/constants.cpp:561-567 */

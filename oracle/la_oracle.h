@@ -71,6 +71,11 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
                  double* qpAqOffset, double* qpCuTreeOffset, int32_t* invQscaleFactor,
                  uint32_t* blockEnergy /* ncu or NULL */, uint64_t wp_ssd[3], uint64_t wp_sum[3]);
 
+/* --fades, the tail of calcAdaptiveQuantFrame (encoder/slicetype.cpp:697-712): returns Lowres::frameVariance and applies the
+ * second acEnergyCu pass' side effect to wp_ssd / wp_sum; call after or_aq_frame */
+double or_fade_variance(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v, int strideC,
+                        int bWeightP, uint64_t wp_ssd[3], uint64_t wp_sum[3]);
+
 /* lowresIntraEstimate (encoder/slicetype.cpp:715-824) */
 void or_intra_estimate(const or_geom* g, const or_pixel* plane0 /* lowresPlane[0] */,
                        const int32_t* invQscaleFactor /* may be NULL */,

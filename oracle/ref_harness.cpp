@@ -70,7 +70,8 @@ struct RefLaConfig
     int32_t radl;                   /* --radl */
     int32_t keepFrames;             /* drained frames kept alive (0 = just what the lookahead itself still references);
                                        ref_la_estimate needs a frame and its references alive */
-    int32_t reserved[4];
+    int32_t fades;                  /* --fades (x265_param::bEnableFades) */
+    int32_t reserved[3];
 };
 
 struct RefLaFrame
@@ -107,6 +108,8 @@ struct RefLaFrame
     const uint16_t* lowresCostForRc;/* ncu, after the in-place scaling of slicetype.cpp:1411-1428 */
     const int32_t*  intraCostForRc; /* ncu, Lowres::intraCost after the same */
     const int32_t*  estRowSatds;    /* bh: rowSatds of the coded estimate after frameCostRecalculate */
+    int32_t bIsFadeEnd, pad0;       /* Lowres::bIsFadeEnd (--fades) */
+    double  frameVariance;          /* Lowres::frameVariance (--fades) */
 };
 
 } // extern "C"
@@ -154,6 +157,7 @@ void snapshot(Handle* h, Frame* f)
     s->h.poc = f->m_poc; s->h.sliceType = l.sliceType; s->h.bScenecut = l.bScenecut;
     s->h.bKeyframe = l.bKeyframe; s->h.bLastMiniGopBFrame = l.bLastMiniGopBFrame;
     s->h.leadingBframes = l.leadingBframes;
+    s->h.bIsFadeEnd = l.bIsFadeEnd; s->h.frameVariance = h->enc->m_param->bEnableFades ? l.frameVariance : 0;
     s->h.bw = bw; s->h.bh = bh; s->h.nb = nb;
     s->h.stride = (int)l.lumaStride;
     s->h.planeLines = (int)((l.buffer[1] - l.buffer[0]) / l.lumaStride);
@@ -302,6 +306,7 @@ void* ref_la_open(const RefLaConfig* c)
     p->bIntraRefresh = c->bIntraRefresh;
     p->gopLookahead = c->gopLookahead;
     p->radl = c->radl;
+    p->bEnableFades = c->fades;
     if (c->vbvBufferSize)
     {
         p->rc.rateControlMode = X265_RC_ABR;

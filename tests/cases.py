@@ -38,6 +38,14 @@ CASES = [
     ("fade_weightb_pool", 10, 320, 192, 60, dict(cuts=(), fades=[(15, 14, 0.25)]), dict(bframes=4, lookaheadDepth=12, weightb=1, poolThreads=16)),
     ("hd_ragged_slices", 8, 1368, 768, 20, dict(cuts=(9,)), dict(bframes=3, lookaheadDepth=10, poolThreads=8, lookaheadSlices=8)),
     ("keymin", 8, 320, 192, 50, dict(cuts=(8, 15, 22)), dict(bframes=3, lookaheadDepth=10, keyframeMax=30, keyframeMin=12)),
+    # --fades: a fade-in of at least one second ends in a keyframe (bIsFadeEnd); frameVariance and the second acEnergyCu pass'
+    # side effect on the weightp sums (slicetype.cpp:697-712, 1861-1906, 1972)
+    ("fadein8", 8, 320, 192, 70, dict(cuts=(), envelope=[(0, 1.0), (6, 1.0), (12, 0.12), (16, 0.12), (32, 1.0), (44, 1.0), (47, 0.3), (62, 1.0)]),
+     dict(bframes=4, lookaheadDepth=12, fades=1, fpsNum=10)),
+    ("fadein10_sd", 10, 640, 360, 60, dict(cuts=(48,), envelope=[(0, 0.1), (3, 0.1), (20, 1.0), (30, 1.0), (34, 0.5), (46, 0.9)]),
+     dict(bframes=3, lookaheadDepth=15, fades=1, fpsNum=8, weightb=1)),
+    ("fadein_nowp_ragged", 8, 328, 184, 60, dict(cuts=(), envelope=[(0, 1.0), (5, 0.2), (8, 0.2), (24, 1.0)]),
+     dict(bframes=4, lookaheadDepth=12, fades=1, fpsNum=10, weightp=0)),
     # --radl: leading B pictures in front of the scene-cut IDRs of a closed GOP
     ("radl2", 8, 320, 192, 50, dict(cuts=(14, 31)), dict(bframes=3, lookaheadDepth=12, bOpenGOP=0, radl=2, keyframeMax=60, keyframeMin=4)),
     # slice types forced by the application (IDR, P, B runs, I) in the middle of automatic decisions
@@ -82,7 +90,8 @@ REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive
               bOpenGOP="bOpenGOP", aqMode="aqMode", aqStrength="aqStrength", cuTree="cuTree", qCompress="qCompress",
               weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
               scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
-              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh", radl="radl")
+              poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh", radl="radl",
+              fades="bEnableFades", fpsNum="fpsNum", fpsDenom="fpsDenom")
 
 
 def la_kwargs(refkw):

@@ -44,6 +44,11 @@ def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutr
             not np.array_equal(ref["propagateCost"], got["propagateCost"]):
         n = int(np.sum(ref["propagateCost"] != got["propagateCost"]))
         bad.append(tag + "propagateCost differs in %d blocks" % n)
+    if "bIsFadeEnd" in ref and "bIsFadeEnd" in got:
+        if int(ref["bIsFadeEnd"]) != int(got["bIsFadeEnd"]):
+            bad.append(tag + "bIsFadeEnd ref=%d got=%d" % (ref["bIsFadeEnd"], got["bIsFadeEnd"]))
+        if ref.get("frameVariance", 0) != got.get("frameVariance", 0):
+            bad.append(tag + "frameVariance ref=%r got=%r" % (ref.get("frameVariance"), got.get("frameVariance")))
     if weightp:
         if not np.array_equal(ref["wp_ssd"], got["wp_ssd"]) or not np.array_equal(ref["wp_sum"], got["wp_sum"]):
             bad.append(tag + "wp stats ref=%s/%s got=%s/%s" % (ref["wp_ssd"], ref["wp_sum"], got["wp_ssd"], got["wp_sum"]))

@@ -177,6 +177,9 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
         or_aq_frame(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW,
                     c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats, &s.qpAq[0], &s.qpCuTree[0], &s.invQ[0],
                     NULL, s.stats.wp_ssd, s.stats.wp_sum);
+    if (c->cfg.need_aq && c->cfg.fade_stats)
+        s.stats.frame_variance = or_fade_variance(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW,
+                                                  c->cfg.need_wp_stats, s.stats.wp_ssd, s.stats.wp_sum);
     if (c->cfg.need_aq && g.qg8) or_invq8x8(&g, &s.invQ[0], &s.invQ8[0]);
     or_intra_estimate(&g, &s.planes[g.padOffset], c->cfg.need_aq ? (g.qg8 ? &s.invQ8[0] : &s.invQ[0]) : NULL, &s.intraCost[0], &s.intraMode[0],
                       &s.lowresCosts00[0], &s.rowSatds00[0], &s.stats.cost_est, &s.stats.cost_est_aq);

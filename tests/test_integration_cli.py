@@ -63,6 +63,9 @@ CLI_CASES = [
     ("b8_la40_fades_10bit", 10, 640, 360, 70, dict(cuts=(), fades=[(20, 12, 0.3), (45, 10, 1.0)]),
      ["--preset", "medium", "--pools", "16", "--lookahead-slices", "0", "--bframes", "8", "--rc-lookahead", "40", "--weightb"]),
     ("qg8_cqp", 8, 640, 360, 40, dict(cuts=(19,)), ["--preset", "faster", "--pools", "4", "--qg-size", "8", "--aq-mode", "3", "--crf", "24"]),
+    # --fades (10 fps, so that the 16-frame fade-ins last "at least one second"): the frame that ends a fade-in becomes a keyframe
+    ("fades_10fps", 8, 640, 360, 70, dict(cuts=(), envelope=[(0, 1.0), (6, 1.0), (12, 0.12), (16, 0.12), (32, 1.0), (44, 1.0), (47, 0.3), (62, 1.0)]),
+     ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--fades"]),
 ]
 
 
@@ -74,7 +77,7 @@ def test_x265_cli_with_cuda_lookahead_is_bit_identical(name, synth, tmp_path):
         pytest.skip("integration/_build not in this snapshot (needs /root/reference at build time)")
     seq = synth.SynthSequence(w, h, depth=depth, seed=5, n_rects=5, **skw)
     y4m = str(tmp_path / "in.y4m")
-    synth.write_y4m(y4m, seq, n)
+    synth.write_y4m(y4m, seq, n, fps=(10, 1) if "--fades" in extra else (30, 1))
     md5_cpu, rows_cpu = _encode(_bin("cpu", depth), y4m, str(tmp_path / "cpu.hevc"), extra)
     md5_gpu, rows_gpu = _encode(_bin("cuda", depth), y4m, str(tmp_path / "gpu.hevc"), extra, env={"X265_CUDA_ASYNC_DEPTH": "8"})
     assert len(rows_cpu) == n and len(rows_gpu) == n

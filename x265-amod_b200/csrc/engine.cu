@@ -429,6 +429,16 @@ static void* hostAlias(void* h)
 int stageLaunch(x265cu_ctx* c, cudaStream_t stream, void* dst0, const void* src0, size_t bytes0, void* dst1, const void* src1, size_t bytes1,
                 unsigned* zero, size_t zeroWords)
 {
+    /* X265CU_STAGE_MEMCPY=1: the same through the copy engines (ncu cannot replay a kernel that reads mapped host memory --
+     * "Failed to prepare kernel for profiling" --, so the ncu launch lists under profiles/ are taken with this set) */
+    static const bool viaMemcpy = getenv("X265CU_STAGE_MEMCPY") != NULL;
+    if (viaMemcpy)
+    {
+        if (bytes0) CK(cudaMemcpyAsync(dst0, src0, bytes0, cudaMemcpyDefault, stream));
+        if (bytes1) CK(cudaMemcpyAsync(dst1, src1, bytes1, cudaMemcpyDefault, stream));
+        if (zeroWords) CK(cudaMemsetAsync(zero, 0, zeroWords * 4, stream));
+        return X265CU_OK;
+    }
     StageTab t;
     memset(&t, 0, sizeof(t));
     t.s[0].dst = (uint4*)dst0; t.s[0].src = (const uint4*)src0; t.s[0].n16 = (unsigned)(bytes0 / 16);
@@ -791,7 +801,7 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
             aq_mean_kernel<<<1, 32, 0, ps>>>(g, qpCuTree, sums);
         }
         aq_finish_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, ps>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
-                                                                      sums, slotPtr<double>(c, slot, L.qpAq), qpCuTree,
+                                                                      c->cfg.fade_stats, sums, slotPtr<double>(c, slot, L.qpAq), qpCuTree,
                                                                       slotPtr<int>(c, slot, L.invQ), stats);
         if (qg8)
             aq_invq8x8_kernel<<<(g.ncu + 255) / 256, 256, 0, ps>>>(g, slotPtr<int>(c, slot, L.invQ), invQ);
@@ -1221,6 +1231,17 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     *out = NULL;
     if (cfg->qg_size != 8 && cfg->qg_size != 16 && cfg->qg_size != 32 && cfg->qg_size != 64) return X265CU_ERR_BAD_ARG;
     if (cfg->depth != 8 && cfg->depth != 10) return X265CU_ERR_UNSUPPORTED;     /* SWAR SATD range, la_device.cuh */
+    if (cfg->fade_stats)
+    {
+        /* --fades: the second acEnergyCu pass (slicetype.cpp:697-712) walks the picture ROUNDED to 16 when weightp is on
+         * (:683-684).  Supported where that is the AQ grid itself: 16x16 AQ blocks, and either no weightp or a size whose
+         * remainder modulo 16 is 0 or >= 8 (1080, 2160, 720, 360, ...); anything else would need per-block sums of a sub-grid */
+        const bool wp = cfg->need_wp_stats != 0;
+        const int rw = cfg->width & 15, rh = cfg->height & 15;
+        if (!cfg->need_aq || cfg->qg_size == 8 || (wp && ((rw > 0 && rw < 8) || (rh > 0 && rh < 8))) ||
+            (cfg->height + 15) / 16 + 1 > LA_FADE_MAX_ROWS)
+            return X265CU_ERR_UNSUPPORTED;
+    }
     if (cfg->width < 16 || cfg->height < 16 || cfg->bframes < 0 || cfg->bframes > 16 || cfg->max_slots < 1 || !cfg->mvcost)
         return X265CU_ERR_BAD_ARG;
     int ndev = 0;
@@ -1712,6 +1733,7 @@ int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265c
         const FrameStatsDev* s = c->h_slotStats + slots[i];
         out[i].cost_est = s->costEst; out[i].cost_est_aq = s->costEstAq;
         for (int k = 0; k < 3; k++) { out[i].wp_ssd[k] = s->wp_ssd[k]; out[i].wp_sum[k] = s->wp_sum[k]; }
+        out[i].frame_variance = c->cfg.fade_stats ? s->frameVariance : 0;
     }
     c->counters.d2h_bytes += (n > 0 ? n : 0) * sizeof(FrameStatsDev);
     return X265CU_OK;

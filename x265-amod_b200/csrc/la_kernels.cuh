@@ -15,6 +15,7 @@ struct FrameStatsDev            /* mirrors x265cu_frame_stats */
 {
     long long costEst, costEstAq;
     unsigned long long wp_ssd[3], wp_sum[3];
+    double frameVariance;
 };
 
 struct CostResultDev            /* mirrors x265cu_cost_result */
@@ -460,15 +461,40 @@ __global__ void __launch_bounds__(32) aq_mean_kernel(Geom g, const double* __res
     if (lane == 0) { sums[0] = a; sums[1] = b; }
 }
 
+#define LA_FADE_MAX_ROWS 1024
 __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const unsigned* __restrict__ energy, int aqMode,
-                                                                  double aqStrength, int bWeightP, const double* __restrict__ sums,
+                                                                  double aqStrength, int bWeightP, int bFades, const double* __restrict__ sums,
                                                                   double* __restrict__ qpAq, double* __restrict__ qpCuTree,
                                                                   int* __restrict__ invQ, FrameStatsDev* stats)
 {
     const int tid = threadIdx.x, n = g.aqW * g.aqH;
     const bool qg8 = g.aqBlock == 8;
     const float modeOneConst = qg8 ? 11.427f : 14.427f, modeTwoConst = qg8 ? 8.f : 11.f;     /* :459-472 */
-    if (blockIdx.x == 0 && tid == 0 && bWeightP)
+    if (blockIdx.x == 0 && bFades)
+    {
+        /* --fades, slicetype.cpp:697-712: frameVariance = sum over block rows of (RUNNING sum of the block variances / maxCol),
+         * divided by maxRow -- the row sum is never reset and the division is an integer one, as in the reference.  With
+         * weightp the loop bounds are the picture size ROUNDED to 16 (the weightp block above it reassigns maxCol / maxRow,
+         * :683-684): a subset of the AQ grid (x265cu_create only accepts sizes for which it is the whole grid) */
+        __shared__ unsigned long long s_row[LA_FADE_MAX_ROWS];
+        const int maxCol = bWeightP ? ((g.picW + 8) >> 4) << 4 : g.picW, maxRow = bWeightP ? ((g.picH + 8) >> 4) << 4 : g.picH;
+        const int nCols = (maxCol + g.aqBlock - 1) / g.aqBlock, nRows = (maxRow + g.aqBlock - 1) / g.aqBlock;
+        for (int r = tid; r < nRows; r += LA_AQ_THREADS)
+        {
+            unsigned long long a = 0;
+            for (int cc = 0; cc < nCols; cc++) a += energy[r * g.aqW + cc];
+            s_row[r] = a;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            unsigned long long run = 0;
+            double fv = 0;
+            for (int r = 0; r < nRows; r++) { run += s_row[r]; fv = __dadd_rn(fv, (double)(run / (unsigned long long)maxCol)); }
+            stats->frameVariance = __ddiv_rn(fv, (double)maxRow);
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0 && (bWeightP || bFades))
     {
         const int maxCol = ((g.picW + 8) >> 4) << 4, maxRow = ((g.picH + 8) >> 4) << 4;
         const int wd[3] = { maxCol, maxCol >> 1, maxCol >> 1 }, ht[3] = { maxRow, maxRow >> 1, maxRow >> 1 };
@@ -476,7 +502,12 @@ __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const 
         {
             const unsigned long long sum = stats->wp_sum[i], ssd = stats->wp_ssd[i];
             const unsigned long long area = (unsigned long long)(wd[i] * ht[i]);
-            stats->wp_ssd[i] = ssd - (sum * sum + area / 2) / area;
+            unsigned long long fsum = sum, fssd = ssd;
+            if (bWeightP) fssd = ssd - (sum * sum + area / 2) / area;
+            /* --fades runs acEnergyCu over every block a second time, and acEnergyVar adds each block's sum / ssd to
+             * wp_sum / wp_ssd again -- after they were finalised (slicetype.cpp:54-55, 703) */
+            if (bFades) { fsum += sum; fssd += ssd; }
+            stats->wp_sum[i] = fsum; stats->wp_ssd[i] = fssd;
         }
     }
     if (aqMode == 0 || aqStrength == 0)

@@ -48,6 +48,7 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     if (q->pendingMax > 0) p.pendingMax = q->pendingMax;
     p.shardCount = q->shardCount; p.batchMin = q->batchMin; p.gopLookahead = q->gopLookahead; p.radl = q->radl;
     p.csvLogLevel = q->csvLogLevel; p.numRowsPerSlice = q->numRowsPerSlice;
+    p.bEnableFades = q->bEnableFades;
     if (p.radl && p.bOpenGOP) p.radl = 0;      /* encoder.cpp:4361-4365 */
     if (p.radl > p.bframes) p.radl = p.bframes;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
@@ -161,6 +162,14 @@ int x265la_frame_scalars(void* lav, void* frame, int64_t* costEst, int64_t* cost
         if (wdelta) wdelta[i] = l.weightedCostDelta[i];
     }
     for (int k = 0; k < 3; k++) { if (wp_ssd) wp_ssd[k] = l.wp_ssd[k]; if (wp_sum) wp_sum[k] = l.wp_sum[k]; }
+    return 0;
+}
+
+int x265la_frame_fade(void*, void* frame, int32_t* bIsFadeEnd, double* frameVariance)
+{
+    const Lowres& l = ((Frame*)frame)->m_lowres;
+    if (bIsFadeEnd) *bIsFadeEnd = l.bIsFadeEnd;
+    if (frameVariance) *frameVariance = l.frameVariance;
     return 0;
 }
 

@@ -33,6 +33,7 @@ typedef struct
     int32_t numRowsPerSlice;         /* > 0: Lookahead::m_numRowsPerSlice as the reference's constructor derived it (it rewrites
                                         x265_param::lookaheadSlices afterwards, so deriving it twice is not idempotent); 0 = derive
                                         from lookaheadSlices */
+    int32_t bEnableFades;            /* x265_param::bEnableFades (--fades) */
 } x265la_param;
 
 typedef struct
@@ -94,6 +95,8 @@ int   x265la_frame_mirror_async(void* la, void* frame, const x265la_mirror* m, u
 int   x265la_mirror_wait(void* la, int64_t ticket);
 int   x265la_pin(void* la, void* ptr, uint64_t bytes);      /* cudaHostRegister through the engine; 0 = ok */
 int   x265la_unpin(void* la, void* ptr);
+/* --fades: Lowres::bIsFadeEnd (rate control resets on it, ratecontrol.cpp:1416) and Lowres::frameVariance */
+int   x265la_frame_fade(void* la, void* frame, int32_t* bIsFadeEnd, double* frameVariance);
 /* weightp analysis outcome per L0 distance: state 0 = not analysed, 1 = no weight, 2 = weighted */
 int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset /* nb each */);
 /* host wall-clock per phase, seconds (see Lookahead::m_timers); reset != 0 clears them */

@@ -7,7 +7,8 @@
  *
  * Not supported (create() fails with an error string rather than silently diverging):
  * --hme, --hist-scenecut, aq-mode 4/5, hevc-aq, aq-motion,
- * zones, temporal sub-layers, analysis load, fades, chunked encodes.
+ * zones, temporal sub-layers, analysis load, chunked encodes; --fades only with 16x16 AQ blocks and picture sizes whose
+ * remainder modulo 16 is 0 or >= 8 (x265cu_create refuses the rest).
  */
 #include "lookahead.h"
 #include <math.h>
@@ -81,6 +82,8 @@ Lookahead::Lookahead(const LookaheadParam& param)
     if (m_param.gopLookahead && m_param.gopLookahead > m_param.lookaheadDepth - m_param.bframes - 2)   /* :1060-1064 */
         m_param.gopLookahead = std::max(0, m_param.lookaheadDepth - m_param.bframes - 2);
     m_lastKeyframe = -m_param.keyframeMax;
+    m_isFadeIn = false; m_fadeCount = 0; m_fadeStart = -1;      /* slicetype.cpp:1002-1004 */
+    for (int i = 0; i < BFRAME_MAX + 4; i++) m_frameVariance[i] = -1;
     /* asyncDepth extra frames of input delay: the decision only ever analyses the first rc-lookahead frames of the
      * queue (slicetype.cpp:1821-1827, 2609-2616), so the results are the same, but the GPU always holds that many
      * frames of searches in flight beyond the window being decided */
@@ -150,6 +153,7 @@ bool Lookahead::create()
     cfg.max_slots = std::max(1, p.lookaheadDepth) + 3 * (p.bframes + 2) + 4 + p.extraSlots + std::max(0, p.asyncDepth);
     cfg.qg_size = p.rc.qgSize; cfg.aq_mode = p.rc.aqMode; cfg.aq_strength = p.rc.aqStrength;
     cfg.need_aq = m_bAdaptiveQuant; cfg.need_wp_stats = p.bEnableWeightedPred || p.bEnableWeightedBiPred;
+    cfg.fade_stats = p.bEnableFades;
     cfg.lambda = lookaheadLambda(p.internalBitDepth);
     cfg.mvcost = &m_mvcost[0]; cfg.mvcost_half = half;
     cfg.device = p.device;
@@ -366,6 +370,7 @@ void Lookahead::preLookahead(const std::vector<Frame*>& fr)
         l.rowSatdsValid[0][0] = true;
         l.costStore[0][0] = 0;
         for (int k = 0; k < 3; k++) { l.wp_ssd[k] = st[i].wp_ssd[k]; l.wp_sum[k] = st[i].wp_sum[k]; }
+        l.frameVariance = st[i].frame_variance;
         l.statsFetched = true;
         fr[i]->m_lowresInit = true;
     }
@@ -984,6 +989,57 @@ void Lookahead::slicetypeDecide()
     const double tAnalyse = nowSec();
 
     const LookaheadParam& p = m_param;
+    if (p.bEnableFades)
+    {
+        /* slicetype.cpp:1861-1906, as is: the frame variances of the mini-GOP candidates in a ring of BFRAME_MAX + 4 entries
+         * indexed by POC; a run of non-decreasing variances is a fade-in, and the frame where a fade-in of at least one
+         * second stops is marked bIsFadeEnd (coded as a keyframe below; rate control resets on it, ratecontrol.cpp:1416).
+         * The walk does not wrap when the candidates straddle the end of the ring (k starts above its end value): kept */
+        int j, endIndex = 0;
+        const int length = BFRAME_MAX + 4;
+        for (j = 0; j < length; j++)
+            m_frameVariance[j] = -1;
+        for (j = 0; list[j] != NULL; j++)
+            m_frameVariance[list[j]->m_poc % length] = list[j]->m_lowres.frameVariance;
+        for (int k = list[0]->m_poc % length; k <= list[j - 1]->m_poc % length; k++)
+        {
+            if (m_frameVariance[k] == -1)
+                break;
+            if ((k > 0 && m_frameVariance[k] >= m_frameVariance[k - 1]) ||
+                (k == 0 && m_frameVariance[k] >= m_frameVariance[length - 1]))
+            {
+                m_isFadeIn = true;
+                if (m_fadeCount == 0 && m_fadeStart == -1)
+                {
+                    for (int temp = list[0]->m_poc; temp <= list[j - 1]->m_poc; temp++)
+                        if (k == temp % length)
+                        {
+                            m_fadeStart = temp ? temp - 1 : 0;
+                            break;
+                        }
+                }
+                m_fadeCount = list[endIndex]->m_poc > m_fadeStart ? list[endIndex]->m_poc - m_fadeStart : 0;
+                endIndex++;
+            }
+            else
+            {
+                if (m_isFadeIn && m_fadeCount >= p.fpsNum / p.fpsDenom)
+                {
+                    for (int temp = 0; list[temp] != NULL; temp++)
+                        if (list[temp]->m_poc == m_fadeStart + (int)m_fadeCount)
+                        {
+                            list[temp]->m_lowres.bIsFadeEnd = true;
+                            break;
+                        }
+                }
+                m_isFadeIn = false;
+                m_fadeCount = 0;
+                m_fadeStart = -1;
+            }
+            if (k == length - 1)
+                k = -1;
+        }
+    }
     if (m_lastNonB && ((p.bFrameAdaptive && p.bframes) || p.rc.cuTree || p.scenecutThreshold ||
                        (p.lookaheadDepth && p.rc.vbvBufferSize)))
         slicetypeAnalyse(frames, fr, false);
@@ -1010,6 +1066,8 @@ void Lookahead::slicetypeDecide()
             if (warn)
                 frm.sliceType = p.bOpenGOP && m_lastKeyframe >= 0 ? TYPE_I : TYPE_IDR;
         }
+        if (frm.bIsFadeEnd)         /* :1972 */
+            frm.sliceType = p.bOpenGOP && m_lastKeyframe >= 0 ? TYPE_I : TYPE_IDR;
         if (frm.sliceType == TYPE_I && frm.frameNum - m_lastKeyframe >= p.keyframeMin)
         {
             if (p.bOpenGOP) { m_lastKeyframe = frm.frameNum; frm.bKeyframe = true; }

@@ -46,6 +46,7 @@ struct LookaheadParam
     int radl;            /* --radl: leading pictures kept in front of a scene-cut IDR of a closed GOP */
     int gopLookahead;    /* --gop-lookahead: a keyframe due at the GOP boundary may wait this many frames for a scene cut */
     int bEnableWeightedPred, bEnableWeightedBiPred;
+    int bEnableFades;    /* --fades: mark the frame that ends a fade-in and code it as a keyframe (slicetype.cpp:1861-1906, 1972) */
     int lookaheadSlices;
     int maxNumReferences;
     struct
@@ -92,6 +93,7 @@ struct Lowres
     int     intraMbs[BFRAME_MAX + 2];
     int64_t satdCost;
     uint64_t wp_ssd[3], wp_sum[3];
+    double  frameVariance;       /* --fades (slicetype.cpp:697-712) */
     double  weightedCostDelta[BFRAME_MAX + 2];
     int     plannedType[LOOKAHEAD_MAX + 1];
     int64_t plannedSatd[LOOKAHEAD_MAX + 1];
@@ -197,6 +199,11 @@ private:
     Lowres* m_lastNonB; Frame* m_lastNonBFrame;
     int     m_8x8Width, m_8x8Height, m_8x8Blocks, m_cuCount;
     int     m_lastKeyframe, m_fullQueueSize;
+    /* --fades state (slicetype.h:190-196) */
+    double  m_frameVariance[BFRAME_MAX + 4];
+    bool    m_isFadeIn;
+    uint64_t m_fadeCount;
+    int     m_fadeStart;
     bool    m_isSceneTransition, m_bBatchMotionSearch, m_bBatchFrameCosts, m_bAdaptiveQuant, m_extendGopBoundary;
     double  m_cuTreeStrength;
     int     m_rowsPerSlice;        /* cooperative search slices (slicetype.cpp:1047-1059); 0 = none */

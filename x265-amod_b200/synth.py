@@ -15,13 +15,15 @@ def _box_blur(a, k):
 
 class SynthSequence:
     def __init__(self, width, height, depth=8, seed=1, cuts=(), fades=(), flashes=(),
-                 n_rects=6, noise=3, chroma_noise=True, static=False, pan=(4, 2)):
+                 n_rects=6, noise=3, chroma_noise=True, static=False, pan=(4, 2), envelope=()):
         """cuts: frame indices where a new scene starts; fades: (start, length, to_level 0..1);
         flashes: (frame, length).  static=True gives a motionless scene (exercises the
-        B-frame zero-MV skip rule)."""
+        B-frame zero-MV skip rule).  envelope: (frame, level) points of a piecewise-linear luminance envelope
+        (fade-ins as well as fade-outs), applied on top of `fades`."""
         self.w, self.h, self.depth, self.seed = width, height, depth, seed
         self.cuts = sorted(cuts)
         self.fades, self.flashes = list(fades), list(flashes)
+        self.envelope = sorted(envelope)
         self.noise, self.static, self.pan = noise, static, pan
         self.maxv = (1 << depth) - 1
         rng = np.random.default_rng(seed)
@@ -82,6 +84,8 @@ class SynthSequence:
                 lum = 1.0 + (lvl - 1.0) * (i - fs + 1) / fl
             elif i >= fs + fl:
                 lum = lvl
+        if self.envelope:
+            lum *= float(np.interp(i, [p[0] for p in self.envelope], [p[1] for p in self.envelope]))
         if lum != 1.0:
             y = np.floor(y * lum + 0.5).astype(np.int64)
         for (ff, fl) in self.flashes:
