@@ -157,7 +157,7 @@ bool cudaLookaheadCreate(Lookahead& self)
     q.rateControlMode = p->rc.rateControlMode;
     q.poolWorkers = self.m_pool ? self.m_pool->m_numWorkers : 0;
     q.gopLookahead = p->gopLookahead; q.radl = p->radl; q.csvLogLevel = p->csvLogLevel;
-    q.bEnableFades = p->bEnableFades;
+    q.bEnableFades = p->bEnableFades; q.bEnableTemporalSubLayers = p->bEnableTemporalSubLayers;
     q.device = envInt("X265_CUDA_DEVICE", 0);
     /* extra frames of input delay that keep the GPU busy while the host decides (same decisions, LookaheadParam::asyncDepth) */
     q.asyncDepth = envInt("X265_CUDA_ASYNC_DEPTH", 16);

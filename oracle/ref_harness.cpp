@@ -71,7 +71,8 @@ struct RefLaConfig
     int32_t keepFrames;             /* drained frames kept alive (0 = just what the lookahead itself still references);
                                        ref_la_estimate needs a frame and its references alive */
     int32_t fades;                  /* --fades (x265_param::bEnableFades) */
-    int32_t reserved[3];
+    int32_t temporalLayers;         /* --temporal-layers (x265_param::bEnableTemporalSubLayers) */
+    int32_t reserved[2];
 };
 
 struct RefLaFrame
@@ -307,6 +308,7 @@ void* ref_la_open(const RefLaConfig* c)
     p->gopLookahead = c->gopLookahead;
     p->radl = c->radl;
     p->bEnableFades = c->fades;
+    p->bEnableTemporalSubLayers = c->temporalLayers;
     if (c->vbvBufferSize)
     {
         p->rc.rateControlMode = X265_RC_ABR;

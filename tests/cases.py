@@ -46,6 +46,9 @@ CASES = [
      dict(bframes=3, lookaheadDepth=15, fades=1, fpsNum=8, weightb=1)),
     ("fadein_nowp_ragged", 8, 328, 184, 60, dict(cuts=(), envelope=[(0, 1.0), (5, 0.2), (8, 0.2), (24, 1.0)]),
      dict(bframes=4, lookaheadDepth=12, fades=1, fpsNum=10, weightp=0)),
+    # --temporal-layers 2: B-refs placed recursively over the mini-GOP, their costs pre-computed by compCostBref
+    ("temporal2", 8, 320, 192, 60, dict(cuts=(31,), static=True, noise=2), dict(bframes=7, lookaheadDepth=20, temporalLayers=2)),
+    ("temporal2_pool", 10, 320, 192, 50, dict(cuts=(24,)), dict(bframes=5, lookaheadDepth=16, temporalLayers=2, poolThreads=16)),
     # --radl: leading B pictures in front of the scene-cut IDRs of a closed GOP
     ("radl2", 8, 320, 192, 50, dict(cuts=(14, 31)), dict(bframes=3, lookaheadDepth=12, bOpenGOP=0, radl=2, keyframeMax=60, keyframeMin=4)),
     # slice types forced by the application (IDR, P, B runs, I) in the middle of automatic decisions
@@ -91,7 +94,7 @@ REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive
               weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
               scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
               poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh", radl="radl",
-              fades="bEnableFades", fpsNum="fpsNum", fpsDenom="fpsDenom")
+              fades="bEnableFades", fpsNum="fpsNum", fpsDenom="fpsDenom", temporalLayers="bEnableTemporalSubLayers")
 
 
 def la_kwargs(refkw):

@@ -37,7 +37,8 @@ class LaParam(C.Structure):
                 ("rateControlMode", C.c_int32), ("poolWorkers", C.c_int32), ("device", C.c_int32),
                 ("extraSlots", C.c_int32), ("speculate", C.c_int32), ("pinHost", C.c_int32),
                 ("asyncDepth", C.c_int32), ("pendingMax", C.c_int32), ("shardCount", C.c_int32), ("batchMin", C.c_int32), ("gopLookahead", C.c_int32), ("radl", C.c_int32),
-                ("csvLogLevel", C.c_int32), ("numRowsPerSlice", C.c_int32), ("bEnableFades", C.c_int32)]
+                ("csvLogLevel", C.c_int32), ("numRowsPerSlice", C.c_int32), ("bEnableFades", C.c_int32),
+                ("bEnableTemporalSubLayers", C.c_int32)]
 
 
 class FrameInfo(C.Structure):
@@ -152,7 +153,7 @@ def make_param(width, height, depth=8, **kw):
              keyframeMax=250, keyframeMin=0, bOpenGOP=1, bIntraRefresh=0, bEnableWeightedPred=1,
              bEnableWeightedBiPred=0, lookaheadSlices=0, maxNumReferences=3, aqMode=2, aqStrength=1.0,
              cuTree=1, qCompress=0.6, qgSize=32, vbvBufferSize=0, vbvMaxBitrate=0, rateControlMode=2,
-             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0, shardCount=0, batchMin=0, gopLookahead=0, radl=0, csvLogLevel=0, numRowsPerSlice=0, bEnableFades=0)
+             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0, shardCount=0, batchMin=0, gopLookahead=0, radl=0, csvLogLevel=0, numRowsPerSlice=0, bEnableFades=0, bEnableTemporalSubLayers=0)
     d.update(kw)
     lib_defaults.sourceWidth, lib_defaults.sourceHeight = width, height
     for k, v in d.items():

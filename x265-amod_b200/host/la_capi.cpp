@@ -48,7 +48,7 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     if (q->pendingMax > 0) p.pendingMax = q->pendingMax;
     p.shardCount = q->shardCount; p.batchMin = q->batchMin; p.gopLookahead = q->gopLookahead; p.radl = q->radl;
     p.csvLogLevel = q->csvLogLevel; p.numRowsPerSlice = q->numRowsPerSlice;
-    p.bEnableFades = q->bEnableFades;
+    p.bEnableFades = q->bEnableFades; p.bEnableTemporalSubLayers = q->bEnableTemporalSubLayers;
     if (p.radl && p.bOpenGOP) p.radl = 0;      /* encoder.cpp:4361-4365 */
     if (p.radl > p.bframes) p.radl = p.bframes;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params

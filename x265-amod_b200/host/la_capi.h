@@ -34,6 +34,7 @@ typedef struct
                                         x265_param::lookaheadSlices afterwards, so deriving it twice is not idempotent); 0 = derive
                                         from lookaheadSlices */
     int32_t bEnableFades;            /* x265_param::bEnableFades (--fades) */
+    int32_t bEnableTemporalSubLayers;/* x265_param::bEnableTemporalSubLayers (--temporal-layers): 0-2 */
 } x265la_param;
 
 typedef struct

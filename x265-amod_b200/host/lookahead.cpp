@@ -138,6 +138,7 @@ bool Lookahead::create()
     m_costVariants = m_dualSlicing ? 8 : 2;
     if (p.rc.qgSize != 8 && p.rc.qgSize != 16 && p.rc.qgSize != 32 && p.rc.qgSize != 64) { fail("qg-size must be 8, 16, 32 or 64"); return false; }
     if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
+    if (p.bEnableTemporalSubLayers > 2) { fail("more than two temporal layers are not supported by the GPU lookahead"); return false; }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
     if (p.lookaheadDepth && p.lookaheadDepth <= p.bframes) { fail("rc-lookahead must exceed bframes"); return false; }
     if (p.lookaheadDepth > LOOKAHEAD_MAX) { fail("rc-lookahead too large"); return false; }
@@ -920,11 +921,36 @@ int64_t Lookahead::estimateFrameCost(Lowres** frames, int p0, int p1, int b, boo
  * slicetypeDecide (slicetype.cpp:1802-2508; non-temporal-layer, non-analysis-load branches)
  * ------------------------------------------------------------------------------------------- */
 
-void Lookahead::placeBref(Frame** list, int start, int end, int /*num*/, int* brefs)   /* :1755-1777 */
+void Lookahead::placeBref(Frame** list, int start, int end, int num, int* brefs)   /* :1755-1777 */
 {
     int avg = (start + end) / 2;
+    if (m_param.bEnableTemporalSubLayers < 2)
+    {
+        list[avg]->m_lowres.sliceType = TYPE_BREF;
+        (*brefs)++;
+        return;
+    }
+    if (num <= 2)
+        return;
     list[avg]->m_lowres.sliceType = TYPE_BREF;
     (*brefs)++;
+    placeBref(list, start, avg, avg - start, brefs);
+    placeBref(list, avg + 1, end, end - avg, brefs);
+}
+
+/* :1780-1799 -- with two temporal layers the costs rate control will ask for are those of the B-ref hierarchy */
+void Lookahead::compCostBref(Lowres** frames, int start, int end, int num)
+{
+    int avg = (start + end) / 2;
+    if (num <= 2)
+    {
+        for (int i = start; i < end; i++)
+            singleCost(frames, start, end + 1, i + 1);
+        return;
+    }
+    singleCost(frames, start, end + 1, avg + 1);
+    compCostBref(frames, start, avg, avg - start);
+    compCostBref(frames, avg + 1, end, end - avg);
 }
 
 void Lookahead::slicetypeDecide()
@@ -1120,7 +1146,9 @@ void Lookahead::slicetypeDecide()
         p0 = isTypeI(frames[bframes + 1]->sliceType) ? b : 0;
         singleCost(frames, p0, p1, b);
         frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
-        if (bframes)
+        if (p.bEnableTemporalSubLayers > 1 && bframes)
+            compCostBref(frames, 0, bframes, bframes + 1);
+        else if (bframes)
         {
             p0 = 0;
             bool isp0available = frames[bframes + 1]->sliceType != TYPE_IDR;

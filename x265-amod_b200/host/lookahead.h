@@ -46,6 +46,8 @@ struct LookaheadParam
     int radl;            /* --radl: leading pictures kept in front of a scene-cut IDR of a closed GOP */
     int gopLookahead;    /* --gop-lookahead: a keyframe due at the GOP boundary may wait this many frames for a scene cut */
     int bEnableWeightedPred, bEnableWeightedBiPred;
+    int bEnableTemporalSubLayers;   /* --temporal-layers: 0 / 1, or 2 (B-refs placed recursively, their costs pre-computed by
+                                       compCostBref, slicetype.cpp:1755-1799); > 2 is refused */
     int bEnableFades;    /* --fades: mark the frame that ends a fade-in and code it as a keyframe (slicetype.cpp:1861-1906, 1972) */
     int lookaheadSlices;
     int maxNumReferences;
@@ -238,7 +240,7 @@ private:
     void    vbvLookahead(Lowres** frames, int numFrames, int keyframe);
     int64_t vbvFrameCost(Lowres** frames, int p0, int p1, int b);
     void    placeBref(Frame** list, int start, int end, int num, int* brefs);
-    void    compCostBref(Lowres** frames, int start, int end, int num);
+    void    compCostBref(Lowres** frames, int start, int end, int num);   /* :1780-1799 */
 
     /* CostEstimateGroup (slicetype.h:261-326) folded in */
     int64_t singleCost(Lowres** frames, int p0, int p1, int b, bool bIntraPenalty = false);
