@@ -62,7 +62,9 @@ typedef struct
     int32_t cost_variants;      /* cost stores per slot = this * (bframes+2)^2; 0 = 2 */
     int32_t fade_stats;         /* x265_param::bEnableFades: Lowres::frameVariance per frame and the second acEnergyCu pass'
                                    side effect on wp_ssd / wp_sum (slicetype.cpp:697-712).  Needs need_aq, qg-size > 8 */
-    int32_t reserved[4];
+    int32_t hist_stats;         /* x265_param::bHistBasedSceneCut: the per-frame picture statistics of collectPictureStatistics
+                                   (slicetype.cpp:1441-1724), read back with x265cu_frame_hist_get.  8-bit only */
+    int32_t reserved[3];
 } x265cu_config;
 
 /* derived geometry, as Lowres::create computes it */
@@ -110,6 +112,19 @@ typedef struct
     uint64_t wp_sum[3];     /* Lowres::wp_sum */
     double   frame_variance;/* Lowres::frameVariance (x265cu_config::fade_stats), else 0 */
 } x265cu_frame_stats;
+/* --hist-scenecut: Lowres::picHistogram / averageIntensityPerSegment / averageIntensity / picAvgVariance{,Cb,Cr} of one frame
+ * (x265cu_config::hist_stats).  Synchronises with the frame's pre-lookahead only. */
+typedef struct
+{
+    uint32_t histogram[4][4][3][256];       /* [segment x][segment y][plane][bin] */
+    uint8_t  avg_intensity_seg[4][4][3];
+    uint8_t  avg_intensity[3];
+    uint8_t  pad0;
+    uint16_t pic_avg_variance[3];
+    uint16_t pad1;
+} x265cu_hist_stats;
+int  x265cu_frame_hist_get(x265cu_ctx* ctx, int32_t slot, x265cu_hist_stats* out);
+
 /* 1 when the pre-lookahead of the frame in `slot` has finished (x265cu_frame_stats_get would not wait), 0 when it is
  * still running, negative on error.  Never blocks. */
 int  x265cu_frame_ready(x265cu_ctx* ctx, int32_t slot);

@@ -124,7 +124,7 @@ bool cudaLookaheadCreate(Lookahead& self)
     x265_param* p = self.m_param;
     const char* why = NULL;
     if (p->bEnableHME) why = "--hme";
-    else if (p->bHistBasedSceneCut) why = "--hist-scenecut";
+    else if (p->bHistBasedSceneCut && X265_DEPTH != 8) why = "--hist-scenecut at high bit depth";
     else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED) why = "--aq-mode 4/5";
     else if (p->rc.hevcAq) why = "--hevc-aq";
     else if (p->bAQMotion) why = "--aq-motion";
@@ -158,6 +158,7 @@ bool cudaLookaheadCreate(Lookahead& self)
     q.poolWorkers = self.m_pool ? self.m_pool->m_numWorkers : 0;
     q.gopLookahead = p->gopLookahead; q.radl = p->radl; q.csvLogLevel = p->csvLogLevel;
     q.bEnableFades = p->bEnableFades; q.bEnableTemporalSubLayers = p->bEnableTemporalSubLayers;
+    q.bHistBasedSceneCut = p->bHistBasedSceneCut;
     q.device = envInt("X265_CUDA_DEVICE", 0);
     /* extra frames of input delay that keep the GPU busy while the host decides (same decisions, LookaheadParam::asyncDepth) */
     q.asyncDepth = envInt("X265_CUDA_ASYNC_DEPTH", 16);

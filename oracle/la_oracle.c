@@ -297,6 +297,118 @@ double or_fade_variance(const or_geom* g, const or_pixel* y, int strideY, const 
     return frameVariance / maxRow;
 }
 
+/* ------------------------------------------------------------------ --hist-scenecut picture statistics */
+
+/* pixel_var<N> + acEnergyVarHist (pixel.cpp:720-737, slicetype.cpp:90-96) on a block inside the (replicate-padded) picture */
+static uint32_t hist_block_var(const or_pixel* p, int stride, int W, int H, int bx, int by, int size, int shift)
+{
+    uint32_t sum = 0, sqr = 0;
+    for (int yy = 0; yy < size; yy++)
+        for (int xx = 0; xx < size; xx++)
+        {
+            uint32_t v = (uint32_t)src_at(p, stride, W, H, bx + xx, by + yy);
+            sum += v; sqr += v * v;
+        }
+    return sqr - (uint32_t)(((uint64_t)sum * sum) >> shift);
+}
+
+/* LookaheadTLD::calculateHistogram (slicetype.cpp:1549-1571) */
+static uint64_t hist_accumulate(const or_pixel* src, uint32_t width, uint32_t height, int stride, int dsFactor, uint32_t* histogram)
+{
+    uint64_t sum = 0;
+    for (uint32_t vy = 0; vy < height; vy += dsFactor)
+    {
+        for (uint32_t hx = 0; hx < width; hx += dsFactor)
+        {
+            ++histogram[src[hx] & 255];     /* 8-bit samples; the mask only keeps a (refused) high-bit-depth build in bounds */
+            sum += src[hx];
+        }
+        src += (stride << (dsFactor >> 1));
+    }
+    return sum;
+}
+
+void or_hist_stats(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v, int strideC,
+                   const or_pixel* plane0, or_hist_stats_t* out)
+{
+    const int W = g->picW, H = g->picH;
+    memset(out, 0, sizeof(*out));
+    /* quarter-sampled luma: frame_lowres_core on lowresPlane[0] (lowres.cpp:35-51, 392-402) */
+    const int qW = W / 4, qH = H / 4;
+    or_pixel* q = (or_pixel*)malloc(sizeof(or_pixel) * (size_t)(qW > 0 ? qW : 1) * (size_t)(qH > 0 ? qH : 1));
+    for (int yy = 0; yy < qH; yy++)
+        for (int xx = 0; xx < qW; xx++)
+        {
+            const or_pixel* s0 = plane0 + (int64_t)(2 * yy) * g->stride, *s1 = s0 + g->stride;
+            q[yy * qW + xx] = (or_pixel)OR_FILTER(s0[2 * xx], s1[2 * xx], s0[2 * xx + 1], s1[2 * xx + 1]);
+        }
+    uint64_t sumLuma = 0, sumCb = 0, sumCr = 0;
+    {   /* computeIntensityHistogramBinsLuma (:1649-1694) */
+        const uint32_t segW = (uint32_t)qW / 4, segH = (uint32_t)qH / 4;
+        for (uint32_t wi = 0; wi < 4; wi++)
+            for (uint32_t hi = 0; hi < 4; hi++)
+            {
+                uint32_t* hist = out->histogram[wi][hi][0];
+                for (int b = 0; b < 256; b++) hist[b] = 1;
+                const uint32_t offW = wi == 3 ? (uint32_t)qW - 4 * segW : 0, offH = hi == 3 ? (uint32_t)qH - 4 * segH : 0;
+                const uint64_t sum = hist_accumulate(q + wi * segW + (int64_t)(hi * segH) * qW, segW + offW, segH + offH, qW, 1, hist);
+                /* (the rounding term multiplies two WIDTHS in the reference, :1683) */
+                out->avgIntensitySeg[wi][hi][0] = (uint8_t)((sum + (((segW + offW) * (segW + offH)) >> 1)) / ((segW + offW) * (segH + offH)));
+                sumLuma += sum << 4;
+                for (int b = 0; b < 256; b++) hist[b] <<= 4;
+            }
+    }
+    {   /* computeIntensityHistogramBinsChroma (:1576-1644) */
+        const uint32_t segW = (uint32_t)W / 4, segH = (uint32_t)H / 4;
+        const int dsFactor = 4;
+        for (uint32_t wi = 0; wi < 4; wi++)
+            for (uint32_t hi = 0; hi < 4; hi++)
+            {
+                const uint32_t offW = wi == 3 ? (uint32_t)W - 4 * segW : 0, offH = hi == 3 ? (uint32_t)H - 4 * segH : 0;
+                for (int pl = 1; pl <= 2; pl++)
+                {
+                    uint32_t* hist = out->histogram[wi][hi][pl];
+                    for (int b = 0; b < 256; b++) hist[b] = 1;
+                    const or_pixel* src = (pl == 1 ? u : v) + ((wi * segW) >> 1) + (int64_t)((hi * segH) >> 1) * strideC;
+                    uint64_t sum = hist_accumulate(src, (segW + offW) >> 1, (segH + offH) >> 1, strideC, dsFactor, hist);
+                    sum <<= dsFactor;
+                    if (pl == 1) sumCb += sum; else sumCr += sum;
+                    /* (the V divisor adds the HEIGHT offset to the width in the reference, :1632) */
+                    const uint32_t den = pl == 1 ? ((segW + offW) * (segH + offH)) >> 2 : ((segW + offH) * (segH + offH)) >> 2;
+                    out->avgIntensitySeg[wi][hi][pl] = (uint8_t)((sum + (((segW + offW) * (segH + offH)) >> 3)) / den);
+                    for (int b = 0; b < 256; b++) hist[b] <<= dsFactor;
+                }
+            }
+    }
+    /* collectPictureStatistics (:1698-1724) */
+    out->avgIntensity[0] = (uint8_t)((sumLuma + (((uint64_t)W * H) >> 1)) / ((uint64_t)W * H));
+    out->avgIntensity[1] = (uint8_t)((sumCb + (((uint64_t)W * H) >> 3)) / (((uint64_t)W * H) >> 2));
+    out->avgIntensity[2] = (uint8_t)((sumCr + (((uint64_t)W * H) >> 3)) / (((uint64_t)W * H) >> 2));
+    {   /* computePictureStatistics (:1457-1544): per block row the variances are summed, divided by the width and CUT to 16 bits */
+        uint64_t tot = 0;
+        for (int by = 0; by < H; by += 8)
+        {
+            uint64_t row = 0;
+            for (int bx = 0; bx < W; bx += 8) row += hist_block_var(y, strideY, W, H, bx, by, 8, 6);
+            tot += (uint16_t)(row / (uint64_t)W);
+        }
+        out->picAvgVariance[0] = (uint16_t)(tot / (uint64_t)H);
+        const int cW = W >> 1, cH = H >> 1;
+        for (int pl = 1; pl <= 2; pl++)
+        {
+            tot = 0;
+            for (int by = 0; by < cH; by += 4)
+            {
+                uint64_t row = 0;
+                for (int bx = 0; bx < cW; bx += 4) row += hist_block_var(pl == 1 ? u : v, strideC, (W + 1) >> 1, (H + 1) >> 1, bx, by, 4, 4);
+                tot += (uint16_t)(row / (uint64_t)cW);
+            }
+            out->picAvgVariance[pl] = (uint16_t)(tot / (uint64_t)cH);
+        }
+    }
+    free(q);
+}
+
 /* ------------------------------------------------------------------ intra */
 
 /* common/constants.cpp:561-567 */

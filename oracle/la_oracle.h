@@ -76,6 +76,21 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
 double or_fade_variance(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v, int strideC,
                         int bWeightP, uint64_t wp_ssd[3], uint64_t wp_sum[3]);
 
+/* --hist-scenecut: the per-frame picture statistics of LookaheadTLD::collectPictureStatistics (encoder/slicetype.cpp:1441-1724)
+ * over the quarter-sampled luma (common/lowres.cpp:35-51, 392-402) and the full-res chroma.  8-bit only: the reference
+ * indexes 256 bins with the sample value.  Same layout as x265cu_hist_stats (include/x265cu.h). */
+typedef struct
+{
+    uint32_t histogram[4][4][3][256];   /* Lowres::picHistogram[segment x][segment y][plane][bin] */
+    uint8_t  avgIntensitySeg[4][4][3];  /* Lowres::averageIntensityPerSegment (the values are uint8_t casts) */
+    uint8_t  avgIntensity[3];
+    uint8_t  pad0;
+    uint16_t picAvgVariance[3];         /* picAvgVariance, picAvgVarianceCb, picAvgVarianceCr */
+    uint16_t pad1;
+} or_hist_stats_t;
+void or_hist_stats(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v, int strideC,
+                   const or_pixel* plane0 /* lowresPlane[0] */, or_hist_stats_t* out);
+
 /* lowresIntraEstimate (encoder/slicetype.cpp:715-824) */
 void or_intra_estimate(const or_geom* g, const or_pixel* plane0 /* lowresPlane[0] */,
                        const int32_t* invQscaleFactor /* may be NULL */,

@@ -72,7 +72,8 @@ struct RefLaConfig
                                        ref_la_estimate needs a frame and its references alive */
     int32_t fades;                  /* --fades (x265_param::bEnableFades) */
     int32_t temporalLayers;         /* --temporal-layers (x265_param::bEnableTemporalSubLayers) */
-    int32_t reserved[2];
+    int32_t histScenecut;           /* --hist-scenecut (x265_param::bHistBasedSceneCut) */
+    int32_t reserved[1];
 };
 
 struct RefLaFrame
@@ -111,6 +112,9 @@ struct RefLaFrame
     const int32_t*  estRowSatds;    /* bh: rowSatds of the coded estimate after frameCostRecalculate */
     int32_t bIsFadeEnd, pad0;       /* Lowres::bIsFadeEnd (--fades) */
     double  frameVariance;          /* Lowres::frameVariance (--fades) */
+    /* --hist-scenecut: Lowres::picAvgVariance{,Cb,Cr}, averageIntensity[3], and a checksum of picHistogram + averageIntensityPerSegment */
+    int32_t histVar[3], histAvg[3];
+    uint64_t histCheck;
 };
 
 } // extern "C"
@@ -159,6 +163,20 @@ void snapshot(Handle* h, Frame* f)
     s->h.bKeyframe = l.bKeyframe; s->h.bLastMiniGopBFrame = l.bLastMiniGopBFrame;
     s->h.leadingBframes = l.leadingBframes;
     s->h.bIsFadeEnd = l.bIsFadeEnd; s->h.frameVariance = h->enc->m_param->bEnableFades ? l.frameVariance : 0;
+    if (h->enc->m_param->bHistBasedSceneCut && l.picHistogram)
+    {
+        s->h.histVar[0] = l.picAvgVariance; s->h.histVar[1] = l.picAvgVarianceCb; s->h.histVar[2] = l.picAvgVarianceCr;
+        uint64_t ck = 0;
+        for (int i = 0; i < 3; i++) s->h.histAvg[i] = l.averageIntensity[i];
+        for (int wi = 0; wi < 4; wi++)
+            for (int hi = 0; hi < 4; hi++)
+                for (int pl = 0; pl < 3; pl++)
+                {
+                    ck = ck * 1000003u + (uint8_t)l.averageIntensityPerSegment[wi][hi][pl];
+                    for (int b = 0; b < 256; b++) ck = ck * 1000003u + l.picHistogram[wi][hi][pl][b];
+                }
+        s->h.histCheck = ck;
+    }
     s->h.bw = bw; s->h.bh = bh; s->h.nb = nb;
     s->h.stride = (int)l.lumaStride;
     s->h.planeLines = (int)((l.buffer[1] - l.buffer[0]) / l.lumaStride);
@@ -309,6 +327,7 @@ void* ref_la_open(const RefLaConfig* c)
     p->radl = c->radl;
     p->bEnableFades = c->fades;
     p->bEnableTemporalSubLayers = c->temporalLayers;
+    p->bHistBasedSceneCut = c->histScenecut;
     if (c->vbvBufferSize)
     {
         p->rc.rateControlMode = X265_RC_ABR;

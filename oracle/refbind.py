@@ -20,7 +20,7 @@ class RefLaConfig(C.Structure):
                 ("scenecutBias", C.c_double), ("vbvBufferSize", C.c_int32), ("vbvMaxBitrate", C.c_int32),
                 ("bitrate", C.c_int32), ("dumpPlanes", C.c_int32), ("bIntraRefresh", C.c_int32),
                 ("gopLookahead", C.c_int32), ("radl", C.c_int32), ("keepFrames", C.c_int32),
-                ("fades", C.c_int32), ("temporalLayers", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("fades", C.c_int32), ("temporalLayers", C.c_int32), ("histScenecut", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class RefLaFrame(C.Structure):
@@ -38,14 +38,15 @@ class RefLaFrame(C.Structure):
                 ("estimated", C.c_int32), ("vbvRows", C.c_int32), ("estSatdCost", C.c_int64),
                 ("satdForVbv", C.c_void_p), ("intraSatdForVbv", C.c_void_p), ("lowresCostForRc", C.c_void_p),
                 ("intraCostForRc", C.c_void_p), ("estRowSatds", C.c_void_p),
-                ("bIsFadeEnd", C.c_int32), ("pad0", C.c_int32), ("frameVariance", C.c_double)]
+                ("bIsFadeEnd", C.c_int32), ("pad0", C.c_int32), ("frameVariance", C.c_double),
+                ("histVar", C.c_int32 * 3), ("histAvg", C.c_int32 * 3), ("histCheck", C.c_uint64)]
 
 
 DEFAULTS = dict(fpsNum=30, fpsDenom=1, bframes=4, lookaheadDepth=20, bFrameAdaptive=2, bBPyramid=1,
                 scenecutThreshold=40, keyframeMax=250, keyframeMin=0, bOpenGOP=1, aqMode=2, aqStrength=1.0,
                 cuTree=1, qCompress=0.6, weightp=1, weightb=0, poolThreads=0, lookaheadSlices=0, qgSize=32,
                 bFrameBias=0, scenecutBias=5.0, vbvBufferSize=0, vbvMaxBitrate=0, bitrate=0, dumpPlanes=0,
-                bIntraRefresh=0, gopLookahead=0, radl=0, keepFrames=0, fades=0, temporalLayers=0)
+                bIntraRefresh=0, gopLookahead=0, radl=0, keepFrames=0, fades=0, temporalLayers=0, histScenecut=0)
 
 
 def lib_path(depth):
@@ -182,7 +183,8 @@ class RefLookahead:
                  bLastMiniGopBFrame=f.bLastMiniGopBFrame, leadingBframes=f.leadingBframes,
                  bw=bw, bh=bh, nb=nb, stride=f.stride, planeLines=f.planeLines, satdCost=f.satdCost,
                  wp_ssd=np.array(list(f.wp_ssd), np.uint64), wp_sum=np.array(list(f.wp_sum), np.uint64),
-                 bIsFadeEnd=f.bIsFadeEnd, frameVariance=f.frameVariance)
+                 bIsFadeEnd=f.bIsFadeEnd, frameVariance=f.frameVariance,
+                 histVar=list(f.histVar), histAvg=list(f.histAvg), histCheck=int(f.histCheck))
         if not nb:
             return d
         d["costEst"] = _arr(f.costEst, np.int64, nb * nb).reshape(nb, nb)

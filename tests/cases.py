@@ -46,6 +46,15 @@ CASES = [
      dict(bframes=3, lookaheadDepth=15, fades=1, fpsNum=8, weightb=1)),
     ("fadein_nowp_ragged", 8, 328, 184, 60, dict(cuts=(), envelope=[(0, 1.0), (5, 0.2), (8, 0.2), (24, 1.0)]),
      dict(bframes=4, lookaheadDepth=12, fades=1, fpsNum=10, weightp=0)),
+    # --hist-scenecut (8-bit): scene cuts from per-segment histogram differences; hard cuts, a flash and a fade
+    ("histcut8", 8, 640, 360, 70, dict(cuts=(17, 41), flashes=[(29, 1)],
+                                        envelope=[(0, 1.0), (16, 1.0), (17, 0.5), (40, 0.5), (41, 0.95), (52, 0.95), (60, 0.3), (69, 0.3)]),
+     dict(bframes=4, lookaheadDepth=16, histScenecut=1)),
+    ("histcut8_ragged_nob", 8, 328, 184, 50, dict(cuts=(12, 30), envelope=[(0, 0.6), (11, 0.6), (12, 1.0), (29, 1.0), (30, 0.45), (49, 0.45)]),
+     dict(bframes=0, lookaheadDepth=10, histScenecut=1)),
+    ("histcut8_b8_pool", 8, 640, 360, 60, dict(cuts=(9, 22, 23, 44), envelope=[(0, 1.0), (8, 1.0), (9, 0.5), (21, 0.5), (22, 1.0), (22.5, 1.0), (23, 0.4),
+                                                                               (43, 0.4), (44, 0.9), (59, 0.9)]),
+     dict(bframes=8, lookaheadDepth=25, histScenecut=1, poolThreads=16)),
     # --temporal-layers 2: B-refs placed recursively over the mini-GOP, their costs pre-computed by compCostBref
     ("temporal2", 8, 320, 192, 60, dict(cuts=(31,), static=True, noise=2), dict(bframes=7, lookaheadDepth=20, temporalLayers=2)),
     ("temporal2_pool", 10, 320, 192, 50, dict(cuts=(24,)), dict(bframes=5, lookaheadDepth=16, temporalLayers=2, poolThreads=16)),
@@ -94,7 +103,7 @@ REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive
               weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
               scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
               poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh", radl="radl",
-              fades="bEnableFades", fpsNum="fpsNum", fpsDenom="fpsDenom", temporalLayers="bEnableTemporalSubLayers")
+              fades="bEnableFades", fpsNum="fpsNum", fpsDenom="fpsDenom", temporalLayers="bEnableTemporalSubLayers", histScenecut="bHistBasedSceneCut")
 
 
 def la_kwargs(refkw):

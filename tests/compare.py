@@ -49,6 +49,10 @@ def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutr
             bad.append(tag + "bIsFadeEnd ref=%d got=%d" % (ref["bIsFadeEnd"], got["bIsFadeEnd"]))
         if ref.get("frameVariance", 0) != got.get("frameVariance", 0):
             bad.append(tag + "frameVariance ref=%r got=%r" % (ref.get("frameVariance"), got.get("frameVariance")))
+    if "histCheck" in got and ref.get("histCheck"):
+        for k in ("histVar", "histAvg", "histCheck"):
+            if ref[k] != got[k]:
+                bad.append(tag + "%s ref=%s got=%s" % (k, ref[k], got[k]))
     if weightp:
         if not np.array_equal(ref["wp_ssd"], got["wp_ssd"]) or not np.array_equal(ref["wp_sum"], got["wp_sum"]):
             bad.append(tag + "wp stats ref=%s/%s got=%s/%s" % (ref["wp_ssd"], ref["wp_sum"], got["wp_ssd"], got["wp_sum"]))

@@ -27,6 +27,7 @@ struct SimSlot
     std::vector<std::vector<uint16_t> > costs;                /* per cost store */
     std::vector<std::vector<int32_t> > rowSatds;
     std::vector<x265cu_cost_result> results;
+    std::vector<x265cu_hist_stats> hist;                        /* 0 or 1 entries (--hist-scenecut) */
     x265cu_frame_stats stats;
     std::vector<int32_t> recalcRows; int64_t recalcScore; int recalcStore;
 };
@@ -92,6 +93,7 @@ const char* x265cu_last_error(const x265cu_ctx*) { return ""; }
 int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 {
     if (cfg->depth != or_depth()) return X265CU_ERR_BAD_ARG;
+    if (cfg->hist_stats && cfg->depth != 8) return X265CU_ERR_UNSUPPORTED;
     x265cu_ctx* c = new x265cu_ctx;
     c->cfg = *cfg;
     or_geom_init(&c->g, cfg->width, cfg->height, cfg->max_cu_size);
@@ -180,10 +182,24 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     if (c->cfg.need_aq && c->cfg.fade_stats)
         s.stats.frame_variance = or_fade_variance(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW,
                                                   c->cfg.need_wp_stats, s.stats.wp_ssd, s.stats.wp_sum);
+    if (c->cfg.hist_stats)
+    {
+        static_assert(sizeof(or_hist_stats_t) == sizeof(x265cu_hist_stats), "same layout");
+        s.hist.resize(1);
+        or_hist_stats(&g, &s.y[0], W, s.u.empty() ? NULL : &s.u[0], s.v.empty() ? NULL : &s.v[0], CW, &s.planes[g.padOffset],
+                      (or_hist_stats_t*)&s.hist[0]);
+    }
     if (c->cfg.need_aq && g.qg8) or_invq8x8(&g, &s.invQ[0], &s.invQ8[0]);
     or_intra_estimate(&g, &s.planes[g.padOffset], c->cfg.need_aq ? (g.qg8 ? &s.invQ8[0] : &s.invQ[0]) : NULL, &s.intraCost[0], &s.intraMode[0],
                       &s.lowresCosts00[0], &s.rowSatds00[0], &s.stats.cost_est, &s.stats.cost_est_aq);
     c->counters.h2d_bytes += (uint64_t)W * H * sizeof(or_pixel) * 3 / 2;
+    return 0;
+}
+
+int x265cu_frame_hist_get(x265cu_ctx* c, int32_t slot, x265cu_hist_stats* out)
+{
+    if (!c->cfg.hist_stats || c->slots[slot].hist.empty()) return X265CU_ERR_BAD_ARG;
+    *out = c->slots[slot].hist[0];
     return 0;
 }
 

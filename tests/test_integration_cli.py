@@ -66,6 +66,11 @@ CLI_CASES = [
     # --fades (10 fps, so that the 16-frame fade-ins last "at least one second"): the frame that ends a fade-in becomes a keyframe
     ("fades_10fps", 8, 640, 360, 70, dict(cuts=(), envelope=[(0, 1.0), (6, 1.0), (12, 0.12), (16, 0.12), (32, 1.0), (44, 1.0), (47, 0.3), (62, 1.0)]),
      ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--fades"]),
+    # --hist-scenecut (8-bit) and two temporal layers
+    ("hist_scenecut", 8, 640, 360, 60, dict(cuts=(17, 41), envelope=[(0, 1.0), (16, 1.0), (17, 0.5), (40, 0.5), (41, 0.95), (59, 0.95)]),
+     ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--hist-scenecut"]),
+    ("temporal_layers_2", 8, 640, 360, 50, dict(cuts=(23,)),
+     ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--bframes", "7", "--temporal-layers", "2"]),
 ]
 
 

@@ -38,7 +38,7 @@ class LaParam(C.Structure):
                 ("extraSlots", C.c_int32), ("speculate", C.c_int32), ("pinHost", C.c_int32),
                 ("asyncDepth", C.c_int32), ("pendingMax", C.c_int32), ("shardCount", C.c_int32), ("batchMin", C.c_int32), ("gopLookahead", C.c_int32), ("radl", C.c_int32),
                 ("csvLogLevel", C.c_int32), ("numRowsPerSlice", C.c_int32), ("bEnableFades", C.c_int32),
-                ("bEnableTemporalSubLayers", C.c_int32)]
+                ("bEnableTemporalSubLayers", C.c_int32), ("bHistBasedSceneCut", C.c_int32)]
 
 
 class FrameInfo(C.Structure):
@@ -116,6 +116,7 @@ def load_lib(path=None):
     lib.x265la_frame_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FrameOut)]
     lib.x265la_frame_weights.argtypes = [C.c_void_p] * 6
     lib.x265la_frame_fade.argtypes = [C.c_void_p] * 4
+    lib.x265la_frame_hist.argtypes = [C.c_void_p] * 5
     lib.x265la_get_timers.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int32]
     lib.x265la_engine.restype = C.c_void_p
     lib.x265la_engine.argtypes = [C.c_void_p]
@@ -153,7 +154,7 @@ def make_param(width, height, depth=8, **kw):
              keyframeMax=250, keyframeMin=0, bOpenGOP=1, bIntraRefresh=0, bEnableWeightedPred=1,
              bEnableWeightedBiPred=0, lookaheadSlices=0, maxNumReferences=3, aqMode=2, aqStrength=1.0,
              cuTree=1, qCompress=0.6, qgSize=32, vbvBufferSize=0, vbvMaxBitrate=0, rateControlMode=2,
-             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0, shardCount=0, batchMin=0, gopLookahead=0, radl=0, csvLogLevel=0, numRowsPerSlice=0, bEnableFades=0, bEnableTemporalSubLayers=0)
+             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0, shardCount=0, batchMin=0, gopLookahead=0, radl=0, csvLogLevel=0, numRowsPerSlice=0, bEnableFades=0, bEnableTemporalSubLayers=0, bHistBasedSceneCut=0)
     d.update(kw)
     lib_defaults.sourceWidth, lib_defaults.sourceHeight = width, height
     for k, v in d.items():
@@ -260,6 +261,9 @@ class Lookahead:
         fe = C.c_int32(0); fv = C.c_double(0)
         self.lib.x265la_frame_fade(self.h, hnd, C.byref(fe), C.byref(fv))
         d.update(bIsFadeEnd=fe.value, frameVariance=fv.value)
+        hv = (C.c_int32 * 3)(); ha = (C.c_int32 * 3)(); hc = C.c_uint64(0)
+        if self.lib.x265la_frame_hist(self.h, hnd, hv, ha, C.byref(hc)) == 0:
+            d.update(histVar=list(hv), histAvg=list(ha), histCheck=int(hc.value))
         ps = np.zeros(251, np.int64); pt = np.zeros(251, np.int32); ib = C.c_int32(0)
         self.lib.x265la_frame_planned(self.h, hnd, ps.ctypes.data, pt.ctypes.data, 251, C.byref(ib))
         d.update(plannedSatd=ps, plannedType=pt, indB=ib.value)

@@ -32,6 +32,9 @@
 
 using namespace la;
 
+static_assert(sizeof(HistStatsDev) == sizeof(x265cu_hist_stats), "HistStatsDev mirrors x265cu_hist_stats");
+static_assert(sizeof(FrameStatsDev) == sizeof(x265cu_frame_stats), "FrameStatsDev mirrors x265cu_frame_stats");
+
 #include <chrono>
 #include <mutex>
 /* host-side stopwatch for tuning (X265CU_HOST_TIMING=1 prints the totals when a context is destroyed) */
@@ -127,6 +130,7 @@ struct x265cu_ctx
     unsigned short* d_mvcost;       /* whole table; centre at +mvcost_half */
     unsigned long long* d_executed; /* [0] search jobs, [1] cost jobs that passed their condition */
     char* d_results; size_t resultsCap;
+    HistAcc* d_histAcc; HistStatsDev* h_hist; HistStatsDev* d_hist;   /* --hist-scenecut: per-slot accumulators, per-slot results in mapped host memory */
     FrameStatsDev* h_slotStats; FrameStatsDev* d_slotStats;   /* mapped host memory: every slot's statistics, written by K3's epilogue */
     char* h_mapped; char* d_mapped; size_t mappedCap;         /* mapped host memory for the small gathers */
     CutreeJobDev* h_ctJobs; CutreeJobDev* d_ctJobs;           /* mapped ring of batched cuTree propagate jobs */
@@ -813,6 +817,19 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
                                                                   slotPtr<unsigned short>(c, slot, L.lowresCosts00),
                                                                   slotPtr<int>(c, slot, L.rowSatds00), stats);
     }
+    if (c->cfg.hist_stats)
+    {
+        /* --hist-scenecut picture statistics (8-bit only, checked at create) */
+        HistAcc* acc = c->d_histAcc + slot;
+        int hst = stageLaunch(c, ps, NULL, NULL, 0, NULL, NULL, 0, (unsigned*)acc, sizeof(HistAcc) / 4);
+        if (hst) return hst;
+        Prof pr(c, X265CU_K_AQ, 4, ps);
+        const uint8_t* y8 = (const uint8_t*)dY; const uint8_t* u8 = (const uint8_t*)dU; const uint8_t* v8 = (const uint8_t*)dV;
+        hist_luma_kernel<<<dim3(16, LA_HIST_CHUNKS), 256, 0, ps>>>(g, (const uint8_t*)planes, acc);
+        hist_chroma_kernel<<<dim3(16, 2), 256, 0, ps>>>(g, u8, v8, acc);
+        hist_var_kernel<<<(g.picH + 7) / 8 + 2 * (((g.picH >> 1) + 3) / 4), 256, 0, ps>>>(g, y8, u8, v8, acc);
+        hist_finish_kernel<<<1, 256, 0, ps>>>(g, acc, c->d_hist + slot);
+    }
     publish_kernel<<<1, 32, 0, ps>>>((const unsigned*)stats, (unsigned*)(c->d_slotStats + slot), (int)(sizeof(FrameStatsDev) / 4));
     c->counters.kernel_launches++;
     CK(cudaGetLastError());
@@ -1231,6 +1248,8 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     *out = NULL;
     if (cfg->qg_size != 8 && cfg->qg_size != 16 && cfg->qg_size != 32 && cfg->qg_size != 64) return X265CU_ERR_BAD_ARG;
     if (cfg->depth != 8 && cfg->depth != 10) return X265CU_ERR_UNSUPPORTED;     /* SWAR SATD range, la_device.cuh */
+    if (cfg->hist_stats && (cfg->depth != 8 || cfg->width < 64 || cfg->height < 64))
+        return X265CU_ERR_UNSUPPORTED;      /* the reference indexes 256 histogram bins with the sample value */
     if (cfg->fade_stats)
     {
         /* --fades: the second acEnergyCu pass (slicetype.cpp:697-712) walks the picture ROUNDED to 16 when weightp is on
@@ -1250,6 +1269,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     x265cu_ctx* c = new (std::nothrow) x265cu_ctx();
     if (!c) return X265CU_ERR_NO_MEMORY;
     c->cfg = *cfg; c->err[0] = 0; c->d_mvcost = NULL; c->d_executed = NULL;
+    c->d_histAcc = NULL; c->h_hist = NULL; c->d_hist = NULL;
     c->d_results = NULL; c->resultsCap = 0; c->h_slotStats = NULL; c->d_slotStats = NULL; c->h_mapped = NULL; c->d_mapped = NULL; c->mappedCap = 0;
     c->h_ctJobs = NULL; c->d_ctJobs = NULL; c->ctRingPos = 0; c->ctPending = 0;
     c->searchWorkers = getenv("X265CU_SEARCH_WORKERS") ? atoi(getenv("X265CU_SEARCH_WORKERS")) : 0;
@@ -1415,6 +1435,12 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
             cudaMalloc((void**)&b.d_sync, b.syncCap) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
     }
     if (!rc && cfg->need_wp_stats && ensureScratch(c, c->mainScratch, c->stream, 1) != X265CU_OK) rc = X265CU_ERR_NO_MEMORY;
+    if (!rc && cfg->hist_stats)
+    {
+        if (cudaMalloc((void**)&c->d_histAcc, (size_t)cfg->max_slots * sizeof(HistAcc)) != cudaSuccess ||
+            cudaHostAlloc((void**)&c->h_hist, (size_t)cfg->max_slots * sizeof(HistStatsDev), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&c->d_hist, c->h_hist, 0) != cudaSuccess) rc = X265CU_ERR_NO_MEMORY;
+    }
     if (!rc)
     {
         c->recalcStride = alignUp(8 + (size_t)g.bh * 4, 256);
@@ -1491,6 +1517,7 @@ void x265cu_destroy(x265cu_ctx* c)
     for (size_t i = 0; i < c->xpool.size(); i++) cudaFree(c->xpool[i].first);
     cudaFree(c->d_mvcost); cudaFree(c->d_executed); cudaFree(c->d_results);
     if (c->h_slotStats) cudaFreeHost(c->h_slotStats);
+    cudaFree(c->d_histAcc); if (c->h_hist) cudaFreeHost(c->h_hist);
     if (c->h_mapped) cudaFreeHost(c->h_mapped);
     if (c->h_ctJobs) cudaFreeHost(c->h_ctJobs);
     if (c->tm0) cudaEventDestroy(c->tm0);
@@ -1717,6 +1744,17 @@ int x265cu_frame_ready(x265cu_ctx* c, int32_t slot)
     if (e == cudaErrorNotReady) return 0;
     cudaOk(c, e, "cudaEventQuery");
     return X265CU_ERR_CUDA;
+}
+
+int x265cu_frame_hist_get(x265cu_ctx* c, int32_t slot, x265cu_hist_stats* out)
+{
+    if (!c || !out) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    if (!slotOk(c, slot) || !c->cfg.hist_stats) return X265CU_ERR_BAD_ARG;
+    CK(cudaEventSynchronize(c->slotConsumed[slot]));
+    memcpy(out, c->h_hist + slot, sizeof(*out));
+    c->counters.d2h_bytes += sizeof(*out);
+    return X265CU_OK;
 }
 
 int x265cu_frame_stats_get(x265cu_ctx* c, const int32_t* slots, int32_t n, x265cu_frame_stats* out)

@@ -1756,6 +1756,173 @@ __global__ void __launch_bounds__(128) cost_group_kernel4(Geom g, const CostGrou
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * --hist-scenecut: LookaheadTLD::collectPictureStatistics (slicetype.cpp:1441-1724) per frame.  8-bit only (the reference
+ * indexes its 256 bins with the sample value).  Accumulators per slot: counts[16][3][256] (u32), sums[16][3] (u64),
+ * varTot[3] (u64), zeroed before the first kernel; hist_finish_kernel turns them into x265cu_hist_stats in mapped host memory.
+ * Segment index = wi * 4 + hi (picHistogram[wi][hi]).
+ * ------------------------------------------------------------------------------------------ */
+struct HistAcc
+{
+    unsigned counts[16][3][256];
+    unsigned long long sums[16][3];
+    unsigned long long varTot[3];
+};
+
+struct HistStatsDev     /* mirrors x265cu_hist_stats */
+{
+    unsigned histogram[4][4][3][256];
+    unsigned char avgIntensitySeg[4][4][3];
+    unsigned char avgIntensity[3];
+    unsigned char pad0;
+    unsigned short picAvgVariance[3];
+    unsigned short pad1;
+};
+
+/* luma: histogram of the quarter-sampled picture, frame_lowres_core applied to lowresPlane[0] (lowres.cpp:35-51, 392-402),
+ * computed on the fly from the tiled plane.  grid (16 segments, LA_HIST_CHUNKS row chunks) */
+#define LA_HIST_CHUNKS 8
+__global__ void __launch_bounds__(256) hist_luma_kernel(Geom g, const uint8_t* __restrict__ plane0, HistAcc* acc)
+{
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_sum;
+    const int seg = blockIdx.x, wi = seg >> 2, hi = seg & 3;
+    const int qW = g.picW / 4, qH = g.picH / 4, segW = qW / 4, segH = qH / 4;
+    const int w = segW + (wi == 3 ? qW - 4 * segW : 0), h = segH + (hi == 3 ? qH - 4 * segH : 0);
+    const int x0 = wi * segW, y0 = hi * segH;
+    s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const int rows = (h + LA_HIST_CHUNKS - 1) / LA_HIST_CHUNKS;
+    const int r0 = blockIdx.y * rows, r1 = min(h, r0 + rows);
+    unsigned long long sum = 0;
+    for (int r = r0; r < r1; r++)
+        for (int c = threadIdx.x; c < w; c += 256)
+        {
+            const int X = g.mx + 2 * (x0 + c), Y = g.my + 2 * (y0 + r);
+            const int a = plane0[tileOff(X, Y, g.tpr)], b = plane0[tileOff(X, Y + 1, g.tpr)];
+            const int cc = plane0[tileOff(X + 1, Y, g.tpr)], d = plane0[tileOff(X + 1, Y + 1, g.tpr)];
+            const int v = (((a + b + 1) >> 1) + ((cc + d + 1) >> 1) + 1) >> 1;
+            atomicAdd(&s_hist[v], 1u);
+            sum += (unsigned)v;
+        }
+    atomicAdd(&s_sum, sum);
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&acc->counts[seg][0][threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x == 0 && s_sum) atomicAdd(&acc->sums[seg][0], s_sum);
+}
+
+/* chroma: every 4th sample of every 4th row of the segment (calculateHistogram with dsFactor 4).  grid (16 segments, 2 planes) */
+__global__ void __launch_bounds__(256) hist_chroma_kernel(Geom g, const uint8_t* __restrict__ u, const uint8_t* __restrict__ v, HistAcc* acc)
+{
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_sum;
+    const int seg = blockIdx.x, wi = seg >> 2, hi = seg & 3, pl = 1 + blockIdx.y;
+    const uint8_t* src = pl == 1 ? u : v;
+    const int segW = g.picW / 4, segH = g.picH / 4;
+    const int w = (segW + (wi == 3 ? g.picW - 4 * segW : 0)) >> 1, h = (segH + (hi == 3 ? g.picH - 4 * segH : 0)) >> 1;
+    const int x0 = (wi * segW) >> 1, y0 = (hi * segH) >> 1;
+    s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const int nx = (w + 3) / 4, ny = (h + 3) / 4;
+    unsigned long long sum = 0;
+    for (int i = threadIdx.x; i < nx * ny; i += 256)
+    {
+        const int c = (i % nx) * 4, r = (i / nx) * 4;
+        const int vv = src[(long long)(y0 + r) * g.srcPitchC + x0 + c];
+        atomicAdd(&s_hist[vv], 1u);
+        sum += (unsigned)vv;
+    }
+    atomicAdd(&s_sum, sum);
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&acc->counts[seg][pl][threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x == 0) atomicAdd(&acc->sums[seg][pl], s_sum);
+}
+
+/* computePictureStatistics (:1457-1544): one CTA per block row of a plane; the row's block variances are summed, divided by the
+ * plane width and CUT to 16 bits before they are added up.  Blocks read the picture with replicate clamping (PicYuv's padding).
+ * grid = luma rows of 8 + 2 x chroma rows of 4 */
+__global__ void __launch_bounds__(256) hist_var_kernel(Geom g, const uint8_t* __restrict__ y, const uint8_t* __restrict__ u,
+                                                        const uint8_t* __restrict__ v, HistAcc* acc)
+{
+    __shared__ unsigned long long s_row;
+    const int lumaRows = (g.picH + 7) / 8, cH = g.picH >> 1, cW = g.picW >> 1, chromaRows = (cH + 3) / 4;
+    int pl, row;
+    if ((int)blockIdx.x < lumaRows) { pl = 0; row = blockIdx.x; }
+    else { pl = 1 + ((int)blockIdx.x - lumaRows) / chromaRows; row = ((int)blockIdx.x - lumaRows) % chromaRows; }
+    const uint8_t* src = pl == 0 ? y : pl == 1 ? u : v;
+    const int pitch = pl == 0 ? g.srcPitch : g.srcPitchC;
+    const int size = pl == 0 ? 8 : 4, shift = pl == 0 ? 6 : 4;
+    const int planeW = pl == 0 ? g.picW : g.cW, planeH = pl == 0 ? g.picH : g.cH;       /* clamp limits */
+    const int loopW = pl == 0 ? g.picW : cW;                                            /* maxCol / maxColChroma */
+    if (threadIdx.x == 0) s_row = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    const int nblk = (loopW + size - 1) / size;
+    for (int b = threadIdx.x; b < nblk; b += 256)
+    {
+        unsigned sum = 0, sqr = 0;
+        for (int yy = 0; yy < size; yy++)
+        {
+            const int Y = min(row * size + yy, planeH - 1);
+            for (int xx = 0; xx < size; xx++)
+            {
+                const unsigned px = src[(long long)Y * pitch + min(b * size + xx, planeW - 1)];
+                sum += px; sqr += px * px;
+            }
+        }
+        mine += sqr - (unsigned)(((unsigned long long)sum * sum) >> shift);
+    }
+    atomicAdd(&s_row, mine);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        atomicAdd(&acc->varTot[pl], (unsigned long long)(unsigned short)(s_row / (unsigned long long)loopW));
+}
+
+/* the reference's final arithmetic, quirks included (slicetype.cpp:1604-1607, 1630-1633, 1683, 1715-1719) */
+__global__ void __launch_bounds__(256) hist_finish_kernel(Geom g, const HistAcc* __restrict__ acc, HistStatsDev* out)
+{
+    const unsigned W = g.picW, H = g.picH;
+    for (int i = threadIdx.x; i < 16 * 3 * 256; i += 256)
+    {
+        const int seg = i / 768, pl = (i / 256) % 3, bin = i & 255;
+        out->histogram[seg >> 2][seg & 3][pl][bin] = (1u + acc->counts[seg][pl][bin]) << 4;
+    }
+    if (threadIdx.x < 16)
+    {
+        const int seg = threadIdx.x, wi = seg >> 2, hi = seg & 3;
+        {
+            const unsigned qW = W / 4, qH = H / 4, segW = qW / 4, segH = qH / 4;
+            const unsigned offW = wi == 3 ? qW - 4 * segW : 0, offH = hi == 3 ? qH - 4 * segH : 0;
+            const unsigned long long sum = acc->sums[seg][0];
+            out->avgIntensitySeg[wi][hi][0] = (unsigned char)((sum + (((segW + offW) * (segW + offH)) >> 1)) / ((segW + offW) * (segH + offH)));
+        }
+        const unsigned segW = W / 4, segH = H / 4;
+        const unsigned offW = wi == 3 ? W - 4 * segW : 0, offH = hi == 3 ? H - 4 * segH : 0;
+        for (int pl = 1; pl <= 2; pl++)
+        {
+            const unsigned long long sum = acc->sums[seg][pl] << 4;
+            const unsigned den = pl == 1 ? ((segW + offW) * (segH + offH)) >> 2 : ((segW + offH) * (segH + offH)) >> 2;
+            out->avgIntensitySeg[wi][hi][pl] = (unsigned char)((sum + (((segW + offW) * (segH + offH)) >> 3)) / den);
+        }
+    }
+    if (threadIdx.x == 0)
+    {
+        unsigned long long s0 = 0, s1 = 0, s2 = 0;
+        for (int seg = 0; seg < 16; seg++) { s0 += acc->sums[seg][0] << 4; s1 += acc->sums[seg][1] << 4; s2 += acc->sums[seg][2] << 4; }
+        const unsigned long long area = (unsigned long long)W * H;
+        out->avgIntensity[0] = (unsigned char)((s0 + (area >> 1)) / area);
+        out->avgIntensity[1] = (unsigned char)((s1 + (area >> 3)) / (area >> 2));
+        out->avgIntensity[2] = (unsigned char)((s2 + (area >> 3)) / (area >> 2));
+        out->picAvgVariance[0] = (unsigned short)(acc->varTot[0] / (unsigned long long)H);
+        out->picAvgVariance[1] = (unsigned short)(acc->varTot[1] / (unsigned long long)(H >> 1));
+        out->picAvgVariance[2] = (unsigned short)(acc->varTot[2] / (unsigned long long)(H >> 1));
+        out->pad0 = 0; out->pad1 = 0;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * K6: weighted prediction.  weight_pp_c over whole padded planes (pixel.cpp:518-541 as called
  * from slicetype.cpp:833-842, 966-976) and weightCostLuma's whole-frame score (:845-858).

@@ -49,6 +49,7 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     p.shardCount = q->shardCount; p.batchMin = q->batchMin; p.gopLookahead = q->gopLookahead; p.radl = q->radl;
     p.csvLogLevel = q->csvLogLevel; p.numRowsPerSlice = q->numRowsPerSlice;
     p.bEnableFades = q->bEnableFades; p.bEnableTemporalSubLayers = q->bEnableTemporalSubLayers;
+    p.bHistBasedSceneCut = q->bHistBasedSceneCut;
     if (p.radl && p.bOpenGOP) p.radl = 0;      /* encoder.cpp:4361-4365 */
     if (p.radl > p.bframes) p.radl = p.bframes;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
@@ -162,6 +163,23 @@ int x265la_frame_scalars(void* lav, void* frame, int64_t* costEst, int64_t* cost
         if (wdelta) wdelta[i] = l.weightedCostDelta[i];
     }
     for (int k = 0; k < 3; k++) { if (wp_ssd) wp_ssd[k] = l.wp_ssd[k]; if (wp_sum) wp_sum[k] = l.wp_sum[k]; }
+    return 0;
+}
+
+int x265la_frame_hist(void*, void* frame, int32_t* variance, int32_t* intensity, uint64_t* checksum)
+{
+    const Lowres& l = ((Frame*)frame)->m_lowres;
+    if (!l.hist) return -1;
+    uint64_t ck = 0;
+    for (int i = 0; i < 3; i++) { variance[i] = l.hist->pic_avg_variance[i]; intensity[i] = l.hist->avg_intensity[i]; }
+    for (int wi = 0; wi < 4; wi++)
+        for (int hi = 0; hi < 4; hi++)
+            for (int pl = 0; pl < 3; pl++)
+            {
+                ck = ck * 1000003u + l.hist->avg_intensity_seg[wi][hi][pl];
+                for (int b = 0; b < 256; b++) ck = ck * 1000003u + l.hist->histogram[wi][hi][pl][b];
+            }
+    *checksum = ck;
     return 0;
 }
 

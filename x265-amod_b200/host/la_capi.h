@@ -35,6 +35,7 @@ typedef struct
                                         from lookaheadSlices */
     int32_t bEnableFades;            /* x265_param::bEnableFades (--fades) */
     int32_t bEnableTemporalSubLayers;/* x265_param::bEnableTemporalSubLayers (--temporal-layers): 0-2 */
+    int32_t bHistBasedSceneCut;      /* x265_param::bHistBasedSceneCut (--hist-scenecut), 8-bit only */
 } x265la_param;
 
 typedef struct
@@ -98,6 +99,9 @@ int   x265la_pin(void* la, void* ptr, uint64_t bytes);      /* cudaHostRegister 
 int   x265la_unpin(void* la, void* ptr);
 /* --fades: Lowres::bIsFadeEnd (rate control resets on it, ratecontrol.cpp:1416) and Lowres::frameVariance */
 int   x265la_frame_fade(void* la, void* frame, int32_t* bIsFadeEnd, double* frameVariance);
+/* --hist-scenecut: Lowres::picAvgVariance{,Cb,Cr}, averageIntensity[3] and a checksum over picHistogram + averageIntensityPerSegment
+ * (tests compare it with the same checksum of the reference's arrays); returns 0 when the frame has such statistics */
+int   x265la_frame_hist(void* la, void* frame, int32_t* variance /* 3 */, int32_t* intensity /* 3 */, uint64_t* checksum);
 /* weightp analysis outcome per L0 distance: state 0 = not analysed, 1 = no weight, 2 = weighted */
 int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset /* nb each */);
 /* host wall-clock per phase, seconds (see Lookahead::m_timers); reset != 0 clears them */

@@ -83,6 +83,11 @@ Lookahead::Lookahead(const LookaheadParam& param)
         m_param.gopLookahead = std::max(0, m_param.lookaheadDepth - m_param.bframes - 2);
     m_lastKeyframe = -m_param.keyframeMax;
     m_isFadeIn = false; m_fadeCount = 0; m_fadeStart = -1;      /* slicetype.cpp:1002-1004 */
+    memset(m_accHistDiffRunningAvg, 0, sizeof(m_accHistDiffRunningAvg));        /* :1065-1095 */
+    memset(m_accHistDiffRunningAvgCb, 0, sizeof(m_accHistDiffRunningAvgCb));
+    memset(m_accHistDiffRunningAvgCr, 0, sizeof(m_accHistDiffRunningAvgCr));
+    m_resetRunningAvg = true;
+    m_segmentCountThreshold = (uint32_t)(((float)((4 * 4) * 50) / 100) + 0.5);
     for (int i = 0; i < BFRAME_MAX + 4; i++) m_frameVariance[i] = -1;
     /* asyncDepth extra frames of input delay: the decision only ever analyses the first rc-lookahead frames of the
      * queue (slicetype.cpp:1821-1827, 2609-2616), so the results are the same, but the GPU always holds that many
@@ -138,6 +143,7 @@ bool Lookahead::create()
     m_costVariants = m_dualSlicing ? 8 : 2;
     if (p.rc.qgSize != 8 && p.rc.qgSize != 16 && p.rc.qgSize != 32 && p.rc.qgSize != 64) { fail("qg-size must be 8, 16, 32 or 64"); return false; }
     if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
+    if (p.bHistBasedSceneCut && p.internalBitDepth != 8) { fail("--hist-scenecut is 8-bit only (the reference indexes 256 bins with the sample value)"); return false; }
     if (p.bEnableTemporalSubLayers > 2) { fail("more than two temporal layers are not supported by the GPU lookahead"); return false; }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
     if (p.lookaheadDepth && p.lookaheadDepth <= p.bframes) { fail("rc-lookahead must exceed bframes"); return false; }
@@ -154,7 +160,7 @@ bool Lookahead::create()
     cfg.max_slots = std::max(1, p.lookaheadDepth) + 3 * (p.bframes + 2) + 4 + p.extraSlots + std::max(0, p.asyncDepth);
     cfg.qg_size = p.rc.qgSize; cfg.aq_mode = p.rc.aqMode; cfg.aq_strength = p.rc.aqStrength;
     cfg.need_aq = m_bAdaptiveQuant; cfg.need_wp_stats = p.bEnableWeightedPred || p.bEnableWeightedBiPred;
-    cfg.fade_stats = p.bEnableFades;
+    cfg.fade_stats = p.bEnableFades; cfg.hist_stats = p.bHistBasedSceneCut;
     cfg.lambda = lookaheadLambda(p.internalBitDepth);
     cfg.mvcost = &m_mvcost[0]; cfg.mvcost_half = half;
     cfg.device = p.device;
@@ -372,6 +378,13 @@ void Lookahead::preLookahead(const std::vector<Frame*>& fr)
         l.costStore[0][0] = 0;
         for (int k = 0; k < 3; k++) { l.wp_ssd[k] = st[i].wp_ssd[k]; l.wp_sum[k] = st[i].wp_sum[k]; }
         l.frameVariance = st[i].frame_variance;
+        if (m_param.bHistBasedSceneCut)
+        {
+            fr[i]->m_hist.resize(1);
+            if (!check(x265cu_frame_hist_get(m_ctx, l.slot, &fr[i]->m_hist[0]), "x265cu_frame_hist_get")) return;
+            l.hist = &fr[i]->m_hist[0];
+            l.bHistScenecutAnalyzed = false;        /* collectPictureStatistics, :1723 */
+        }
         l.statsFetched = true;
         fr[i]->m_lowresInit = true;
     }
@@ -1066,7 +1079,7 @@ void Lookahead::slicetypeDecide()
                 k = -1;
         }
     }
-    if (m_lastNonB && ((p.bFrameAdaptive && p.bframes) || p.rc.cuTree || p.scenecutThreshold ||
+    if (m_lastNonB && ((p.bFrameAdaptive && p.bframes) || p.rc.cuTree || p.scenecutThreshold || p.bHistBasedSceneCut ||
                        (p.lookaheadDepth && p.rc.vbvBufferSize)))
         slicetypeAnalyse(frames, fr, false);
     if (m_failed) return;
@@ -1308,7 +1321,8 @@ void Lookahead::slicetypeAnalyse(Lowres** frames, Frame** fr, bool bKeyframe)
     }
 
     int numBFrames = 0, numAnalyzed = numFrames;
-    bool isScenecut = scenecut(frames, 0, 1, true, origNumFrames);
+    bool isScenecut = p.bHistBasedSceneCut ? histBasedScenecut(frames, 0, 1, origNumFrames)      /* :2742-2745 */
+                                           : scenecut(frames, 0, 1, true, origNumFrames);
     if (p.scenecutThreshold && isScenecut)
     {
         frames[1]->sliceType = TYPE_I;
@@ -1507,6 +1521,121 @@ bool Lookahead::scenecut(Lowres** frames, int p0, int p1, bool bRealScenecut, in
 }
 
 /* slicetype.cpp:3016-3055 */
+/* slicetype.cpp:3057-3188, as is -- including the segment size that keeps growing by the last segment's remainder from one
+ * segment to the next (it only feeds the thresholds) */
+bool Lookahead::detectHistBasedSceneChange(Lowres** frames, int p0, int p1, int p2)
+{
+    enum { PICTURE_DIFF_VARIANCE_TH = 390, PICTURE_VARIANCE_TH = 1500, LOW_VAR_SCENE_CHANGE_TH = 2250, HIGH_VAR_SCENE_CHANGE_TH = 3500,
+           PICTURE_DIFF_VARIANCE_CHROMA_TH = 10, PICTURE_VARIANCE_CHROMA_TH = 20, LOW_VAR_SCENE_CHANGE_CHROMA_TH = 2250 / 4,
+           HIGH_VAR_SCENE_CHANGE_CHROMA_TH = 3500 / 4, FADE_TH = 4, INTENSITY_CHANGE_TH = 4 };       /* slicetype.h:49-61 */
+    const double FLASH_TH = 1.5;
+    Lowres* previousFrame = frames[p0];
+    Lowres* currentFrame = frames[p1];
+    Lowres* futureFrame = frames[p2];
+    currentFrame->bHistScenecutAnalyzed = true;
+    if (!previousFrame->hist || !currentFrame->hist || !futureFrame->hist) { fail("hist-scenecut statistics missing"); return false; }
+    const x265cu_hist_stats &prev = *previousFrame->hist, &cur = *currentFrame->hist, &fut = *futureFrame->hist;
+
+    uint8_t absIntDiffFuturePast = 0, absIntDiffFuturePresent = 0, absIntDiffPresentPast = 0;
+    uint32_t abruptChangeCount = 0, sceneChangeCount = 0;
+    uint32_t segmentWidth = (uint32_t)m_param.sourceWidth / 4, segmentHeight = (uint32_t)m_param.sourceHeight / 4;
+#define LA_NUM64(w, h) (((w) * (h)) >> (6 << 1))     /* NUM64x64INPIC, MAX_LOG2_CU_SIZE = 6 */
+    for (uint32_t wi = 0; wi < 4; wi++)
+    {
+        for (uint32_t hi = 0; hi < 4; hi++)
+        {
+            bool isAbruptChange = false, isSceneChange = false;
+            uint32_t accHistDiff = 0, accHistDiffCb = 0, accHistDiffCr = 0;
+            uint32_t segmentWidthOffset = wi == 3 ? (uint32_t)m_param.sourceWidth - 4 * segmentWidth : 0;
+            uint32_t segmentHeightOffset = hi == 3 ? (uint32_t)m_param.sourceHeight - 4 * segmentHeight : 0;
+            segmentWidth += segmentWidthOffset;
+            segmentHeight += segmentHeightOffset;
+
+            const int64_t dv = std::abs((int64_t)cur.pic_avg_variance[0] - (int64_t)prev.pic_avg_variance[0]);
+            uint32_t segmentThreshHold = (dv > PICTURE_DIFF_VARIANCE_TH &&
+                                          (cur.pic_avg_variance[0] > PICTURE_VARIANCE_TH || prev.pic_avg_variance[0] > PICTURE_VARIANCE_TH))
+                                         ? HIGH_VAR_SCENE_CHANGE_TH * LA_NUM64(segmentWidth, segmentHeight)
+                                         : LOW_VAR_SCENE_CHANGE_TH * LA_NUM64(segmentWidth, segmentHeight);
+            const int64_t dvb = std::abs((int64_t)cur.pic_avg_variance[1] - (int64_t)prev.pic_avg_variance[1]);
+            uint32_t segmentThreshHoldCb = (dvb > PICTURE_DIFF_VARIANCE_CHROMA_TH &&
+                                            (cur.pic_avg_variance[1] > PICTURE_VARIANCE_CHROMA_TH || prev.pic_avg_variance[1] > PICTURE_VARIANCE_CHROMA_TH))
+                                           ? HIGH_VAR_SCENE_CHANGE_CHROMA_TH * LA_NUM64(segmentWidth, segmentHeight)
+                                           : LOW_VAR_SCENE_CHANGE_CHROMA_TH * LA_NUM64(segmentWidth, segmentHeight);
+            const int64_t dvr = std::abs((int64_t)cur.pic_avg_variance[2] - (int64_t)prev.pic_avg_variance[2]);
+            uint32_t segmentThreshHoldCr = (dvr > PICTURE_DIFF_VARIANCE_CHROMA_TH &&
+                                            (cur.pic_avg_variance[2] > PICTURE_VARIANCE_CHROMA_TH || prev.pic_avg_variance[2] > PICTURE_VARIANCE_CHROMA_TH))
+                                           ? HIGH_VAR_SCENE_CHANGE_CHROMA_TH * LA_NUM64(segmentWidth, segmentHeight)
+                                           : LOW_VAR_SCENE_CHANGE_CHROMA_TH * LA_NUM64(segmentWidth, segmentHeight);
+
+            for (uint32_t bin = 0; bin < 256; ++bin)
+            {
+                accHistDiff += (uint32_t)std::abs((int32_t)cur.histogram[wi][hi][0][bin] - (int32_t)prev.histogram[wi][hi][0][bin]);
+                accHistDiffCb += (uint32_t)std::abs((int32_t)cur.histogram[wi][hi][1][bin] - (int32_t)prev.histogram[wi][hi][1][bin]);
+                accHistDiffCr += (uint32_t)std::abs((int32_t)cur.histogram[wi][hi][2][bin] - (int32_t)prev.histogram[wi][hi][2][bin]);
+            }
+            if (m_resetRunningAvg)
+            {
+                m_accHistDiffRunningAvg[wi][hi] = accHistDiff;
+                m_accHistDiffRunningAvgCb[wi][hi] = accHistDiffCb;
+                m_accHistDiffRunningAvgCr[wi][hi] = accHistDiffCr;
+            }
+            uint32_t accHistDiffError = (uint32_t)std::abs((int32_t)m_accHistDiffRunningAvg[wi][hi] - (int32_t)accHistDiff);
+            uint32_t accHistDiffErrorCb = (uint32_t)std::abs((int32_t)m_accHistDiffRunningAvgCb[wi][hi] - (int32_t)accHistDiffCb);
+            uint32_t accHistDiffErrorCr = (uint32_t)std::abs((int32_t)m_accHistDiffRunningAvgCr[wi][hi] - (int32_t)accHistDiffCr);
+
+            if ((accHistDiffError > segmentThreshHold && accHistDiff >= accHistDiffError) ||
+                (accHistDiffErrorCb > segmentThreshHoldCb && accHistDiffCb >= accHistDiffErrorCb) ||
+                (accHistDiffErrorCr > segmentThreshHoldCr && accHistDiffCr >= accHistDiffErrorCr))
+                isAbruptChange = true;
+
+            if (isAbruptChange)
+            {
+                absIntDiffFuturePast = (uint8_t)std::abs((int16_t)fut.avg_intensity_seg[wi][hi][0] - (int16_t)prev.avg_intensity_seg[wi][hi][0]);
+                absIntDiffFuturePresent = (uint8_t)std::abs((int16_t)fut.avg_intensity_seg[wi][hi][0] - (int16_t)cur.avg_intensity_seg[wi][hi][0]);
+                absIntDiffPresentPast = (uint8_t)std::abs((int16_t)cur.avg_intensity_seg[wi][hi][0] - (int16_t)prev.avg_intensity_seg[wi][hi][0]);
+                if (absIntDiffFuturePresent >= FLASH_TH * absIntDiffFuturePast && absIntDiffPresentPast >= FLASH_TH * absIntDiffFuturePast)
+                    ;   /* flash */
+                else if (absIntDiffFuturePresent < FADE_TH && absIntDiffPresentPast < FADE_TH)
+                    ;   /* fade */
+                else if (std::abs(absIntDiffFuturePresent - absIntDiffPresentPast) < INTENSITY_CHANGE_TH &&
+                         absIntDiffFuturePresent + absIntDiffPresentPast >= absIntDiffFuturePast)
+                    ;   /* intensity change */
+                else
+                    isSceneChange = true;
+            }
+            else
+                m_accHistDiffRunningAvg[wi][hi] = (3 * m_accHistDiffRunningAvg[wi][hi] + accHistDiff) / 4;
+
+            abruptChangeCount += isAbruptChange;
+            sceneChangeCount += isSceneChange;
+        }
+    }
+#undef LA_NUM64
+    m_resetRunningAvg = abruptChangeCount >= m_segmentCountThreshold;
+    return sceneChangeCount >= m_segmentCountThreshold;
+}
+
+/* slicetype.cpp:3190-3216 */
+bool Lookahead::histBasedScenecut(Lowres** frames, int p0, int p1, int numFrames)
+{
+    /* Only do analysis during a normal scenecut check. */
+    if (m_param.bframes)
+    {
+        int origmaxp1 = p0 + 1;
+        /* Look ahead to avoid coding short flashes as scenecuts. */
+        origmaxp1 += m_param.bframes;
+        int maxp1 = std::min(origmaxp1, numFrames);
+        for (int cp1 = p0; cp1 < maxp1; cp1++)
+        {
+            if (frames[cp1 + 1]->bHistScenecutAnalyzed == true)
+                continue;
+            if (frames[cp1 + 2] != NULL && detectHistBasedSceneChange(frames, cp1, cp1 + 1, cp1 + 2))
+                frames[cp1 + 1]->bScenecut = true;
+        }
+    }
+    return frames[p1]->bScenecut;
+}
+
 bool Lookahead::scenecutInternal(Lowres** frames, int p0, int p1, bool bRealScenecut)
 {
     Lowres* frame = frames[p1];

@@ -48,6 +48,8 @@ struct LookaheadParam
     int bEnableWeightedPred, bEnableWeightedBiPred;
     int bEnableTemporalSubLayers;   /* --temporal-layers: 0 / 1, or 2 (B-refs placed recursively, their costs pre-computed by
                                        compCostBref, slicetype.cpp:1755-1799); > 2 is refused */
+    int bHistBasedSceneCut;         /* --hist-scenecut (8-bit only): scene cuts from per-segment histogram differences instead of
+                                       the cost-based test (slicetype.cpp:3057-3216) */
     int bEnableFades;    /* --fades: mark the frame that ends a fade-in and code it as a keyframe (slicetype.cpp:1861-1906, 1972) */
     int lookaheadSlices;
     int maxNumReferences;
@@ -96,6 +98,9 @@ struct Lowres
     int64_t satdCost;
     uint64_t wp_ssd[3], wp_sum[3];
     double  frameVariance;       /* --fades (slicetype.cpp:697-712) */
+    /* --hist-scenecut: the picture statistics (collectPictureStatistics); hist points into Frame::m_hist */
+    const x265cu_hist_stats* hist;
+    bool    bHistScenecutAnalyzed;
     double  weightedCostDelta[BFRAME_MAX + 2];
     int     plannedType[LOOKAHEAD_MAX + 1];
     int64_t plannedSatd[LOOKAHEAD_MAX + 1];
@@ -138,6 +143,7 @@ struct Frame
     bool     m_released;      /* caller is done with it */
     bool     m_inUse;
     const void* m_planes[3];  /* caller's picture (valid until the frame's upload completed) */
+    std::vector<x265cu_hist_stats> m_hist;   /* 0 or 1 entries (--hist-scenecut) */
     int      m_strideY, m_strideC;
     Lookahead* m_owner;
 };
@@ -201,6 +207,12 @@ private:
     Lowres* m_lastNonB; Frame* m_lastNonBFrame;
     int     m_8x8Width, m_8x8Height, m_8x8Blocks, m_cuCount;
     int     m_lastKeyframe, m_fullQueueSize;
+    /* --hist-scenecut state (slicetype.h:196-203) */
+    uint32_t m_accHistDiffRunningAvg[4][4], m_accHistDiffRunningAvgCb[4][4], m_accHistDiffRunningAvgCr[4][4];
+    bool    m_resetRunningAvg;
+    uint32_t m_segmentCountThreshold;
+    bool    histBasedScenecut(Lowres** frames, int p0, int p1, int numFrames);
+    bool    detectHistBasedSceneChange(Lowres** frames, int p0, int p1, int p2);
     /* --fades state (slicetype.h:190-196) */
     double  m_frameVariance[BFRAME_MAX + 4];
     bool    m_isFadeIn;
