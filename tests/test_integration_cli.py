@@ -86,6 +86,12 @@ def test_x265_cli_with_cuda_lookahead_is_bit_identical(name, synth, tmp_path):
     md5_cpu, rows_cpu = _encode(_bin("cpu", depth), y4m, str(tmp_path / "cpu.hevc"), extra)
     md5_gpu, rows_gpu = _encode(_bin("cuda", depth), y4m, str(tmp_path / "gpu.hevc"), extra, env={"X265_CUDA_ASYNC_DEPTH": "8"})
     assert len(rows_cpu) == n and len(rows_gpu) == n
+    # Lowres::ipCostRatio is only ever written by Lookahead::scenecut (slicetype.cpp:2998-3003) and never reset when a Frame is
+    # recycled (lowres.cpp:337-365): with --hist-scenecut the first-frame check goes through histBasedScenecut instead, and the
+    # CSV column of most frames shows whatever an EARLIER frame left in the recycled object.  Not reproducible, not compared.
+    skip_ratio = "--hist-scenecut" in extra
     for a, b in zip(rows_cpu, rows_gpu):
+        if skip_ratio:
+            a, b = a[:6] + a[7:], b[:6] + b[7:]
         assert a == b, "csv row differs:\ncpu %s\ngpu %s" % (a, b)
     assert md5_cpu == md5_gpu, "bitstreams differ although every csv row matches"
