@@ -73,7 +73,7 @@ struct RefLaConfig
     int32_t fades;                  /* --fades (x265_param::bEnableFades) */
     int32_t temporalLayers;         /* --temporal-layers (x265_param::bEnableTemporalSubLayers) */
     int32_t histScenecut;           /* --hist-scenecut (x265_param::bHistBasedSceneCut) */
-    int32_t reserved[1];
+    int32_t csp400;                 /* 1 = 4:0:0 (x265_param::internalCsp = X265_CSP_I400): pictures carry no chroma */
 };
 
 struct RefLaFrame
@@ -300,7 +300,7 @@ void* ref_la_open(const RefLaConfig* c)
     PARAM_NS::x265_param_default_preset(p, "medium", NULL);
     p->sourceWidth = c->width; p->sourceHeight = c->height;
     p->fpsNum = c->fpsNum; p->fpsDenom = c->fpsDenom;
-    p->internalCsp = X265_CSP_I420;
+    p->internalCsp = c->csp400 ? X265_CSP_I400 : X265_CSP_I420;
     p->internalBitDepth = X265_DEPTH;
     p->sourceBitDepth = X265_DEPTH;
     p->logLevel = getenv("REF_LA_LOG") ? atoi(getenv("REF_LA_LOG")) : X265_LOG_NONE;
@@ -388,8 +388,8 @@ int ref_la_put_typed(void* hv, const void* y, const void* u, const void* v, int 
     x265_picture pic;
     x265_picture_init(p, &pic);
     pic.bitDepth = X265_DEPTH;
-    pic.colorSpace = X265_CSP_I420;
-    pic.planes[0] = (void*)y; pic.planes[1] = (void*)u; pic.planes[2] = (void*)v;
+    pic.colorSpace = h->cfg.csp400 ? X265_CSP_I400 : X265_CSP_I420;
+    pic.planes[0] = (void*)y; pic.planes[1] = h->cfg.csp400 ? NULL : (void*)u; pic.planes[2] = h->cfg.csp400 ? NULL : (void*)v;
     pic.stride[0] = strideY * (int)sizeof(pixel);
     pic.stride[1] = pic.stride[2] = strideC * (int)sizeof(pixel);
     /* conformance-window padding exactly as Encoder::encode passes it (encoder.cpp:1645) */

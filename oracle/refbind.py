@@ -20,7 +20,7 @@ class RefLaConfig(C.Structure):
                 ("scenecutBias", C.c_double), ("vbvBufferSize", C.c_int32), ("vbvMaxBitrate", C.c_int32),
                 ("bitrate", C.c_int32), ("dumpPlanes", C.c_int32), ("bIntraRefresh", C.c_int32),
                 ("gopLookahead", C.c_int32), ("radl", C.c_int32), ("keepFrames", C.c_int32),
-                ("fades", C.c_int32), ("temporalLayers", C.c_int32), ("histScenecut", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("fades", C.c_int32), ("temporalLayers", C.c_int32), ("histScenecut", C.c_int32), ("csp400", C.c_int32)]
 
 
 class RefLaFrame(C.Structure):
@@ -46,7 +46,7 @@ DEFAULTS = dict(fpsNum=30, fpsDenom=1, bframes=4, lookaheadDepth=20, bFrameAdapt
                 scenecutThreshold=40, keyframeMax=250, keyframeMin=0, bOpenGOP=1, aqMode=2, aqStrength=1.0,
                 cuTree=1, qCompress=0.6, weightp=1, weightb=0, poolThreads=0, lookaheadSlices=0, qgSize=32,
                 bFrameBias=0, scenecutBias=5.0, vbvBufferSize=0, vbvMaxBitrate=0, bitrate=0, dumpPlanes=0,
-                bIntraRefresh=0, gopLookahead=0, radl=0, keepFrames=0, fades=0, temporalLayers=0, histScenecut=0)
+                bIntraRefresh=0, gopLookahead=0, radl=0, keepFrames=0, fades=0, temporalLayers=0, histScenecut=0, csp400=0)
 
 
 def lib_path(depth):

@@ -55,6 +55,9 @@ CASES = [
     ("histcut8_b8_pool", 8, 640, 360, 60, dict(cuts=(9, 22, 23, 44), envelope=[(0, 1.0), (8, 1.0), (9, 0.5), (21, 0.5), (22, 1.0), (22.5, 1.0), (23, 0.4),
                                                                                (43, 0.4), (44, 0.9), (59, 0.9)]),
      dict(bframes=8, lookaheadDepth=25, histScenecut=1, poolThreads=16)),
+    # 4:0:0 (X265_CSP_I400): no chroma in the AQ energies, the weightp sums or the uploads
+    ("mono400", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, csp400=1)),
+    ("mono400_10_fade", 10, 320, 192, 50, dict(cuts=(), fades=[(15, 12, 0.3)]), dict(bframes=4, lookaheadDepth=12, csp400=1, aqMode=3)),
     # --temporal-layers 2: B-refs placed recursively over the mini-GOP, their costs pre-computed by compCostBref
     ("temporal2", 8, 320, 192, 60, dict(cuts=(31,), static=True, noise=2), dict(bframes=7, lookaheadDepth=20, temporalLayers=2)),
     ("temporal2_pool", 10, 320, 192, 50, dict(cuts=(24,)), dict(bframes=5, lookaheadDepth=16, temporalLayers=2, poolThreads=16)),
@@ -175,7 +178,8 @@ def run_ours(pkg, synth, case, lib_path=None, planes=True, **extra):
     kw = la_kwargs(rkw)
     kw.update(extra)
     la = pkg.Lookahead(w, h, depth=depth, lib_path=lib_path, **kw)
-    out = pkg.run_sequence(la, (seq.frame(i) for i in range(n)), planes=planes, slice_types=FORCED.get(name),
+    mono = bool(rkw.get("csp400"))      # 4:0:0: the pictures carry no chroma planes
+    out = pkg.run_sequence(la, ((seq.frame(i)[0], None, None) if mono else seq.frame(i) for i in range(n)), planes=planes, slice_types=FORCED.get(name),
                            pass2_types=PASS2.get(name), estimate_cost=name in ESTIMATE, pir=PIR.get(name, (-1, -1)))
     la.close()
     return out
