@@ -82,6 +82,7 @@ Lookahead::Lookahead(const LookaheadParam& param)
     if (m_param.gopLookahead && m_param.gopLookahead > m_param.lookaheadDepth - m_param.bframes - 2)   /* :1060-1064 */
         m_param.gopLookahead = std::max(0, m_param.lookaheadDepth - m_param.bframes - 2);
     m_lastKeyframe = -m_param.keyframeMax;
+    m_shardDecouple = getenv("X265LA_SHARD_DECOUPLE") != NULL && atoi(getenv("X265LA_SHARD_DECOUPLE")) != 0;   /* opt-in: green on the gloo ranks, not yet timed on 2 GPUs */
     m_isFadeIn = false; m_fadeCount = 0; m_fadeStart = -1;      /* slicetype.cpp:1002-1004 */
     memset(m_accHistDiffRunningAvg, 0, sizeof(m_accHistDiffRunningAvg));        /* :1065-1095 */
     memset(m_accHistDiffRunningAvgCb, 0, sizeof(m_accHistDiffRunningAvgCb));
@@ -648,13 +649,14 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
     }
     /* weights assumed earlier whose pixel sums have arrived in the meantime: settle them first, so a search that does
      * need weights is redone before more work piles up behind the wrong one */
-    if (needStats && !sharded) verifyWeights(mustPoc);
+    const bool lockstep = sharded && !m_shardDecouple;      /* the first sharded pipeline: wait for every frame's sums before batching it */
+    if (needStats && !lockstep) verifyWeights(mustPoc);
     while (!m_pendingSpec.empty() && !m_failed)
     {
         Frame* f = m_pendingSpec.front();
         /* (a sharded stream must batch the same frames on every rank, so it never looks at the clock: it leaves the
          * two newest frames, whose pre-lookahead is probably still running, for the next batch and waits for the sums) */
-        if (f->m_poc > mustPoc && sharded && needStats && f->m_poc > m_pocNext - 3)
+        if (f->m_poc > mustPoc && lockstep && needStats && f->m_poc > m_pocNext - 3)
             break;
         m_pendingSpec.pop_front();
         group.push_back(f);
@@ -667,13 +669,14 @@ void Lookahead::drainPending(size_t keep, int mustPoc)
         std::vector<Frame*> pre;
         for (size_t i = 0; i < group.size(); i++)
         {
-            const bool must = sharded || group[i]->m_poc <= mustPoc;
+            const bool must = lockstep || group[i]->m_poc <= mustPoc;
             for (int d = 0; d <= m_param.bframes + 1; d++)
             {
                 Frame* x = d ? frameOfPoc(group[i]->m_poc - d) : group[i];
                 if (!x) break;
                 if (x->m_lowresInit || std::find(pre.begin(), pre.end(), x) != pre.end()) continue;
-                if (must || x265cu_frame_ready(m_ctx, x->m_lowres.slot) == 1)
+                /* (a sharded stream never asks the clock: ranks must make identical choices) */
+                if (must || (!sharded && x265cu_frame_ready(m_ctx, x->m_lowres.slot) == 1))
                     pre.push_back(x);
             }
         }
@@ -725,7 +728,9 @@ void Lookahead::verifyWeights(int mustPoc)
         {
             Frame* x = pair[k];
             if (!x || x->m_lowresInit || std::find(need.begin(), need.end(), x) != need.end()) continue;
-            if (f->m_poc <= mustPoc || x265cu_frame_ready(m_ctx, x->m_lowres.slot) == 1)
+            /* a sharded stream settles every assumption made by EARLIER batches at every call (their sums are at most one search
+             * launch away), identically on all ranks; an unsharded one takes what has arrived */
+            if (f->m_poc <= mustPoc || m_param.shardCount > 1 || x265cu_frame_ready(m_ctx, x->m_lowres.slot) == 1)
                 need.push_back(x);
         }
     }

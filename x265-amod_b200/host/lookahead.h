@@ -236,6 +236,8 @@ private:
     std::map<const void*, bool> m_pinned; /* caller buffers page-locked by pinHost (true = registered) */
     int     m_pocNext;
     int     m_shardRank;
+    bool    m_shardDecouple;       /* sharded stream: cut batches without waiting for the pixel sums, like the unsharded path, but
+                                      settle the assumed weights at fixed points only (every rank must cut identical batches) */
     bool    m_failed; char m_error[256];
 
     /* decision logic (same names as the reference) */
