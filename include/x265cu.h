@@ -31,7 +31,7 @@ extern "C" {
 #define X265CU_ERR_BAD_ARG     -2
 #define X265CU_ERR_NO_MEMORY   -3
 #define X265CU_ERR_CUDA        -4   /* a CUDA call or kernel failed; see x265cu_last_error */
-#define X265CU_ERR_UNSUPPORTED -5   /* configuration outside the hot path (12-bit, HME, ...) */
+#define X265CU_ERR_UNSUPPORTED -5   /* configuration outside the hot path (12-bit, star / full search under --hme, ...) */
 
 typedef struct x265cu_ctx x265cu_ctx;
 
@@ -64,7 +64,13 @@ typedef struct
                                    side effect on wp_ssd / wp_sum (slicetype.cpp:697-712).  Needs need_aq, qg-size > 8 */
     int32_t hist_stats;         /* x265_param::bHistBasedSceneCut: the per-frame picture statistics of collectPictureStatistics
                                    (slicetype.cpp:1441-1724), read back with x265cu_frame_hist_get.  8-bit only */
-    int32_t reserved[3];
+    int32_t hme;                /* x265_param::bEnableHME (--hme): every search job first searches the 1/16-resolution planes
+                                   (lowres.cpp:378-388) on the m_4x4 block grid and feeds twice that vector to the lowres search as one
+                                   more predictor (slicetype.cpp:4040-4048, 4142-4145).  The level-0 results stay on the device */
+    int32_t hme_search[2];      /* x265_param::hmeSearchMethod[0..1] (level 2 is the main encoder's): X265_DIA_SEARCH (0),
+                                   X265_HEX_SEARCH (1) or X265_UMH_SEARCH (2); others are refused */
+    int32_t hme_range[2];       /* x265_param::hmeRange[0..1] */
+    int32_t reserved[2];
 } x265cu_config;
 
 /* derived geometry, as Lowres::create computes it */
@@ -256,6 +262,10 @@ int  x265cu_fetch_mvs(x265cu_ctx* ctx, int32_t slot, int32_t store, int32_t* mv_
                       int32_t* mv_costs /* ncu */);
 int  x265cu_fetch_costs(x265cu_ctx* ctx, int32_t slot, int32_t cost_store, uint16_t* lowres_costs /* ncu */,
                         int32_t* row_satds /* bh */);
+/* --hme: the level-0 results behind MV store `store` (Lowres::lowerResMvs / lowerResMvCosts of that list and distance): bw4 * bh4
+ * (x, y) pairs and costs, bw4 / bh4 = ((width / 4) + 7) >> 3, ((height / 4) + 7) >> 3.  The main encoder never reads them; the
+ * parity tests do */
+int  x265cu_fetch_hme_mvs(x265cu_ctx* ctx, int32_t slot, int32_t store, int32_t* mv_xy, int32_t* mv_costs);
 
 /* ---- the host mirror of a decided frame in ONE asynchronous request: everything the main encoder reads of the frame's
  * Lowres (SURVEY 8b "output contract") goes to the caller's buffers on a dedicated copy stream, behind the work that

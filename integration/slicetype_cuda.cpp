@@ -123,7 +123,7 @@ bool cudaLookaheadCreate(Lookahead& self)
 {
     x265_param* p = self.m_param;
     const char* why = NULL;
-    if (p->bEnableHME) why = "--hme";
+    if (p->bEnableHME && (p->hmeSearchMethod[0] > X265_UMH_SEARCH || p->hmeSearchMethod[1] > X265_UMH_SEARCH)) why = "--hme-search star / sea / full at levels 0 and 1";
     else if (p->bHistBasedSceneCut && X265_DEPTH != 8) why = "--hist-scenecut at high bit depth";
     else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED) why = "--aq-mode 4/5";
     else if (p->rc.hevcAq) why = "--hevc-aq";
@@ -159,6 +159,8 @@ bool cudaLookaheadCreate(Lookahead& self)
     q.gopLookahead = p->gopLookahead; q.radl = p->radl; q.csvLogLevel = p->csvLogLevel;
     q.bEnableFades = p->bEnableFades; q.bEnableTemporalSubLayers = p->bEnableTemporalSubLayers;
     q.bHistBasedSceneCut = p->bHistBasedSceneCut;
+    q.bEnableHME = p->bEnableHME;
+    for (int i = 0; i < 2; i++) { q.hmeSearchMethod[i] = p->hmeSearchMethod[i]; q.hmeRange[i] = p->hmeRange[i]; }
     q.device = envInt("X265_CUDA_DEVICE", 0);
     /* extra frames of input delay that keep the GPU busy while the host decides (same decisions, LookaheadParam::asyncDepth) */
     q.asyncDepth = envInt("X265_CUDA_ASYNC_DEPTH", 16);

@@ -30,6 +30,15 @@ void or_geom_init(or_geom* g, int picW, int picH, int maxCUSize)
     g->planeSize = (int64_t)g->stride * g->planeLines;
     g->padOffset = (int64_t)g->stride * g->my + g->mx;
     g->rowsPerSlice = 0; g->qg8 = 0;
+    /* --hme, level 0: the 1/16-resolution planes live in buffers of half the size, addressed with half the stride and
+     * extended by half the margins (common/lowres.cpp:165-183, 378-388); the level-0 block grid comes from the SOURCE
+     * size (encoder/slicetype.cpp:998-999) */
+    g->w4 = g->w / 2; g->h4 = g->h / 2;
+    g->bw4 = ((picW / 4) + 7) >> 3; g->bh4 = ((picH / 4) + 7) >> 3;
+    g->mx4 = g->mx / 2; g->my4 = g->my / 2;
+    g->stride4 = g->stride / 2;
+    g->planeSize4 = g->planeSize / 2;
+    g->padOffset4 = g->padOffset / 2;
 }
 
 /* common/constants.cpp:34-90: lambda = 2^(qp/6 - 2) * 2^(depth-8); X265_LOOKAHEAD_QP = 12 + 6*(depth-8)
@@ -155,6 +164,47 @@ void or_lowres_init(const or_geom* g, const or_pixel* srcY, int srcStride, or_pi
         or_pixel* bot = p - g->mx + (g->h - 1) * st;
         for (int y = 0; y < g->my; y++)
             memcpy(bot + (y + 1) * st, bot, st * sizeof(or_pixel));
+    }
+}
+
+/* --hme: Lowres::init's second call of the downscale primitive, lowresPlane[0] -> the four 1/16-resolution planes, and their
+ * border extension by half the margins (common/lowres.cpp:378-388, pixel.cpp:605-628).  `plane0` is lowresPlane[0] (margins
+ * already extended: the filter reads one column / row beyond the plane); `buf4` is 4 * planeSize4 pixels, zeroed by the caller. */
+void or_lowerres_init(const or_geom* g, const or_pixel* plane0, or_pixel* buf4)
+{
+    or_pixel* pl[4];
+    for (int i = 0; i < 4; i++) pl[i] = buf4 + i * g->planeSize4 + g->padOffset4;
+    const int st = g->stride, st4 = g->stride4;
+    for (int y = 0; y < g->h4; y++)
+    {
+        const or_pixel* s0 = plane0 + (int64_t)2 * y * st;
+        const or_pixel* s1 = s0 + st;
+        const or_pixel* s2 = s1 + st;
+        for (int x = 0; x < g->w4; x++)
+        {
+            pl[0][y * st4 + x] = (or_pixel)OR_FILTER(s0[2 * x], s1[2 * x], s0[2 * x + 1], s1[2 * x + 1]);
+            pl[1][y * st4 + x] = (or_pixel)OR_FILTER(s0[2 * x + 1], s1[2 * x + 1], s0[2 * x + 2], s1[2 * x + 2]);
+            pl[2][y * st4 + x] = (or_pixel)OR_FILTER(s1[2 * x], s2[2 * x], s1[2 * x + 1], s2[2 * x + 1]);
+            pl[3][y * st4 + x] = (or_pixel)OR_FILTER(s1[2 * x + 1], s2[2 * x + 1], s1[2 * x + 2], s2[2 * x + 2]);
+        }
+    }
+    for (int i = 0; i < 4; i++)
+    {
+        or_pixel* p = pl[i];
+        for (int y = 0; y < g->h4; y++)
+            for (int x = 0; x < g->mx4; x++)
+            {
+                p[y * st4 - g->mx4 + x] = p[y * st4];
+                p[y * st4 + g->w4 + x] = p[y * st4 + g->w4 - 1];
+            }
+        /* extendPicBorder copies (width + 2 * marginX) pixels per row above / below (pixel.cpp:1044-1058 via picyuv) */
+        const int rowLen = g->w4 + 2 * g->mx4;
+        or_pixel* top = p - g->mx4;
+        for (int y = 0; y < g->my4; y++)
+            memcpy(top - (y + 1) * st4, top, rowLen * sizeof(or_pixel));
+        or_pixel* bot = p - g->mx4 + (g->h4 - 1) * st4;
+        for (int y = 0; y < g->my4; y++)
+            memcpy(bot + (y + 1) * st4, bot, rowLen * sizeof(or_pixel));
     }
 }
 
@@ -628,11 +678,20 @@ static const or_mv hex2[8] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -
 static const uint8_t mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };                                               /* motion.cpp:65 */
 static const or_mv square1[9] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} }; /* :66 */
 
-/* MotionEstimate::motionEstimate, lowres path: HEX search + lowres subpel, merange 16, subpelRefine 1
- * (encoder/motion.cpp:764-821, 870-969, 1473-1528) */
-static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv* out)
+static const or_mv hex4[16] = { {0, -4}, {0, 4}, {-2, -3}, {2, -3}, {-4, -2}, {4, -2}, {-4, -1}, {4, -1},
+                                 {-4, 0}, {4, 0}, {-4, 1}, {4, 1}, {-4, 2}, {4, 2}, {-2, 3}, {2, 3} };                    /* motion.cpp:67-73 */
+
+#define OR_DIA_SEARCH 0
+#define OR_HEX_SEARCH 1
+#define OR_UMH_SEARCH 2
+
+static inline int in_range(or_mv v, or_mv lo, or_mv hi) { return v.x >= lo.x && v.x <= hi.x && v.y >= lo.y && v.y <= hi.y; }   /* mv.h:104 */
+
+/* MotionEstimate::motionEstimate, lowres path (numCandidates 0, subpelRefine 1): the integer search `method` (DIA / HEX / UMH,
+ * encoder/motion.cpp:842-1160) over `merange`, then the lowres subpel refinement (:1473-1528).  Without --hme the lookahead
+ * always runs HEX over 16 (slicetype.cpp:4096,4170). */
+static int motion_estimate_ex(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, int merange, int method, or_mv* out)
 {
-    const int merange = 16;
     m->mvp = qmvp;
     or_mv qmin = { mvmin.x << 2, mvmin.y << 2 }, qmax = { mvmax.x << 2, mvmax.y << 2 };
     or_mv pmv = { imax(imin(qmvp.x, qmax.x), qmin.x), imax(imin(qmvp.y, qmax.y), qmin.y) };
@@ -652,8 +711,140 @@ static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv
             bmv.y = imax(imin(0, mvmax.y), mvmin.y);
         }
     }
+    pmv.x = (pmv.x + 2) >> 2; pmv.y = (pmv.y + 2) >> 2;      /* motion.cpp:839 */
+    int hexRefine = method == OR_HEX_SEARCH;
 #define YOK(dy) ((bmv.y + (dy) >= mvmin.y) & (bmv.y + (dy) <= mvmax.y))
 #define COSTAT(dx, dy) (sad_fpel(m, bmv.x + (dx), bmv.y + (dy)) + mvcost_q(m, (bmv.x + (dx)) << 2, (bmv.y + (dy)) << 2))
+    if (method == OR_DIA_SEARCH)
+    {   /* diamond, radius 1 (motion.cpp:845-868) */
+        bcost <<= 4;
+        int i = merange;
+        do
+        {
+            int c0 = COSTAT(0, -1), c1 = COSTAT(0, 1), c2 = COSTAT(-1, 0), c3 = COSTAT(1, 0);
+            if (YOK(-1)) { if ((c0 << 4) + 1 < bcost) bcost = (c0 << 4) + 1; }
+            if (YOK(1))  { if ((c1 << 4) + 3 < bcost) bcost = (c1 << 4) + 3; }
+            if ((c2 << 4) + 4 < bcost) bcost = (c2 << 4) + 4;
+            if ((c3 << 4) + 12 < bcost) bcost = (c3 << 4) + 12;
+            if (!(bcost & 15))
+                break;
+            bmv.x -= (int32_t)((uint32_t)bcost << 28) >> 30;
+            bmv.y -= (int32_t)((uint32_t)bcost << 30) >> 30;
+            bcost &= ~15;
+        }
+        while (--i && in_range(bmv, mvmin, mvmax));
+        bcost >>= 4;
+    }
+    else if (method == OR_UMH_SEARCH)
+    {   /* uneven multi-hexagon (motion.cpp:971-1160), numCandidates == 0 */
+        or_mv omv = bmv;
+        int ucost1, ucost2, cross_start = 1;
+        /* COST_MV / COST_MV_X4 (motion.cpp:263-269, 309-330): the latter measures around omv and range-checks y only */
+#define COST_MV(mx, my) { int cost_ = sad_fpel(m, (mx), (my)) + mvcost_q(m, (mx) << 2, (my) << 2); \
+                          if (cost_ < bcost) { bcost = cost_; bmv.x = (mx); bmv.y = (my); } }
+#define COST_MV_1(dx, dy) { int cost_ = sad_fpel(m, omv.x + (dx), omv.y + (dy)) + mvcost_q(m, (omv.x + (dx)) << 2, (omv.y + (dy)) << 2); \
+                            if ((omv.y + (dy) >= mvmin.y) & (omv.y + (dy) <= mvmax.y)) \
+                                if (cost_ < bcost) { bcost = cost_; bmv.x = omv.x + (dx); bmv.y = omv.y + (dy); } }
+#define COST_MV_X4(x0, y0, x1, y1, x2, y2, x3, y3) { COST_MV_1(x0, y0) COST_MV_1(x1, y1) COST_MV_1(x2, y2) COST_MV_1(x3, y3) }
+#define DIA1_ITER(mx, my) { omv.x = (mx); omv.y = (my); COST_MV_X4(0, -1, 0, 1, -1, 0, 1, 0) }
+#define CROSS(start, x_max, y_max) \
+        { \
+            int i_ = (start); \
+            if ((x_max) <= imin(mvmax.x - omv.x, omv.x - mvmin.x)) \
+                for (; i_ < (x_max) - 2; i_ += 4) \
+                    COST_MV_X4(i_, 0, -i_, 0, i_ + 2, 0, -i_ - 2, 0) \
+            for (; i_ < (x_max); i_ += 2) \
+            { \
+                if (omv.x + i_ <= mvmax.x) COST_MV(omv.x + i_, omv.y) \
+                if (omv.x - i_ >= mvmin.x) COST_MV(omv.x - i_, omv.y) \
+            } \
+            i_ = (start); \
+            if ((y_max) <= imin(mvmax.y - omv.y, omv.y - mvmin.y)) \
+                for (; i_ < (y_max) - 2; i_ += 4) \
+                    COST_MV_X4(0, i_, 0, -i_, 0, i_ + 2, 0, -i_ - 2) \
+            for (; i_ < (y_max); i_ += 2) \
+            { \
+                if (omv.y + i_ <= mvmax.y) COST_MV(omv.x, omv.y + i_) \
+                if (omv.y - i_ >= mvmin.y) COST_MV(omv.x, omv.y - i_) \
+            } \
+        }
+#define SAD_THRESH(v) (bcost < (((v) >> 4) * 4))      /* sizeScale[LUMA_8x8] = (8 * 8) >> 4 (motion.cpp:61,126) */
+        do
+        {
+            ucost1 = bcost;
+            DIA1_ITER(pmv.x, pmv.y)
+            if (pmv.x | pmv.y)
+                DIA1_ITER(0, 0)
+            ucost2 = bcost;
+            if ((bmv.x | bmv.y) && (bmv.x != pmv.x || bmv.y != pmv.y))
+                DIA1_ITER(bmv.x, bmv.y)
+            if (bcost == ucost2)
+                cross_start = 3;
+            omv = bmv;
+            if (bcost == ucost2 && SAD_THRESH(2000))
+            {
+                COST_MV_X4(0, -2, -1, -1, 1, -1, -2, 0)
+                COST_MV_X4(2, 0, -1, 1, 1, 1, 0, 2)
+                if (bcost == ucost1 && SAD_THRESH(500))
+                    break;
+                if (bcost == ucost2)
+                {
+                    const int range = (int16_t)(merange >> 1) | 1;
+                    CROSS(3, range, range)
+                    COST_MV_X4(-1, -2, 1, -2, -2, -1, 2, -1)
+                    COST_MV_X4(-2, 1, 2, 1, -1, 2, 1, 2)
+                    if (bcost == ucost2)
+                        break;
+                    cross_start = range + 2;
+                }
+            }
+            CROSS(cross_start, merange, merange >> 1)
+            COST_MV_X4(-2, -2, -2, 2, 2, -2, 2, 2)
+            /* hexagon grid, motion.cpp:1075-1154 */
+            omv = bmv;
+            int i = 1;
+            do
+            {
+                if (4 * i > imin(imin(mvmax.x - omv.x, omv.x - mvmin.x), imin(mvmax.y - omv.y, omv.y - mvmin.y)))
+                {
+                    for (int j = 0; j < 16; j++)
+                    {
+                        or_mv mv = { omv.x + hex4[j].x * i, omv.y + hex4[j].y * i };
+                        if (in_range(mv, mvmin, mvmax))
+                            COST_MV(mv.x, mv.y)
+                    }
+                }
+                else
+                {
+                    /* all 16 points are measured; MIN_MV tests the UNSCALED y offset against the range (motion.cpp:1100) */
+                    int best = -1;
+                    for (int k = 0; k < 16; k++)
+                    {
+                        const int mx = omv.x + hex4[k].x * i, my = omv.y + hex4[k].y * i;
+                        const int cost = sad_fpel(m, mx, my) + mvcost_q(m, mx << 2, my << 2);
+                        if ((omv.y + hex4[k].y >= mvmin.y) & (omv.y + hex4[k].y <= mvmax.y))
+                            if (cost < bcost) { bcost = cost; best = k; }
+                    }
+                    if (best >= 0)
+                    {
+                        bmv.x = omv.x + i * hex4[best].x;
+                        bmv.y = omv.y + i * hex4[best].y;
+                    }
+                }
+            }
+            while (++i <= merange >> 2);
+            if (in_range(bmv, mvmin, mvmax))
+                hexRefine = 1;          /* goto me_hex2 */
+        }
+        while (0);
+#undef COST_MV
+#undef COST_MV_1
+#undef COST_MV_X4
+#undef DIA1_ITER
+#undef CROSS
+#undef SAD_THRESH
+    }
+    if (hexRefine)
     {
         int c0 = COSTAT(-2, 0), c1 = COSTAT(-1, 2), c2 = COSTAT(1, 2);
         bcost <<= 3;
@@ -687,10 +878,9 @@ static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv
             }
         }
         bcost >>= 3;
-    }
-    {   /* square refine, motion.cpp:950-967 */
-        int dir = 0;
-        int c0 = COSTAT(0, -1), c1 = COSTAT(0, 1), c2 = COSTAT(-1, 0), c3 = COSTAT(1, 0);
+        /* square refine, motion.cpp:950-967 */
+        int dir = 0, c3;
+        c0 = COSTAT(0, -1); c1 = COSTAT(0, 1); c2 = COSTAT(-1, 0); c3 = COSTAT(1, 0);
         if (YOK(-1)) { if (c0 < bcost) { bcost = c0; dir = 1; } }
         if (YOK(1))  { if (c1 < bcost) { bcost = c1; dir = 2; } }
         if (c2 < bcost) { bcost = c2; dir = 3; }
@@ -733,6 +923,11 @@ static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv
     }
     *out = bmv;
     return bcost;
+}
+
+static int motion_estimate(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, or_mv* out)
+{
+    return motion_estimate_ex(m, mvmin, mvmax, qmvp, 16, OR_HEX_SEARCH, out);
 }
 
 /* is cuY the first row a search visits in its slice?  Whole frame: the bottom row (slicetype.cpp:4050-4059);
@@ -795,6 +990,80 @@ void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel
             }
             or_mv best;
             int fencCost = motion_estimate(&m, mvmin, mvmax, mvp, &best);
+            if (skipCost < 64 && skipCost < fencCost && bBidir)
+            {
+                fencCost = skipCost;
+                best.x = best.y = 0;
+                skips++;
+            }
+            mvs[2 * cuXY] = best.x; mvs[2 * cuXY + 1] = best.y;
+            mvCosts[cuXY] = fencCost;
+        }
+    }
+    if (skipCount) *skipCount = skips;
+}
+
+/* --hme: the search half of estimateCUCost for one level (slicetype.cpp:3942-3955, 4040-4048, 4083-4183) */
+void or_search_list_hme(const or_geom* g, int level, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
+                        const uint16_t* mvcost, int bBidir, int method, int merange,
+                        const int32_t* hmeMvs, const int32_t* hmeMvCosts,
+                        int32_t* mvs, int32_t* mvCosts, int32_t* skipCount)
+{
+    int skips = 0;
+    or_me m;
+    const int hme = level == 0;
+    const int bw = hme ? g->bw4 : g->bw, bh = hme ? g->bh4 : g->bh;
+    const int stride = hme ? g->stride4 : g->stride;
+    m.g = g; m.stride = stride; m.mvcost = mvcost;
+    /* No cooperative slices here: with them the reference's level-1 search of one slice reads level-0 vectors that another
+     * slice's worker may not have written yet (the two levels are cut at different rows, :3942-3968) -- uninitialised
+     * vectors, observed to crash the reference.  The GPU path refuses --hme together with active lookahead slices. */
+    for (int cuY = bh - 1; cuY >= 0; cuY--)
+    {
+        const int lastRow = cuY == bh - 1;
+        for (int cuX = bw - 1; cuX >= 0; cuX--)
+        {
+            const int cuXY = cuX + cuY * bw;
+            const int cuXY_4x4 = (cuX / 2) + (cuY / 2) * bw / 2;       /* :4088, as written */
+            const int64_t pel = 8 * cuX + (int64_t)8 * cuY * stride;
+            for (int y = 0; y < 8; y++) memcpy(m.fenc + 8 * y, fencPlane0 + pel + (int64_t)y * stride, 8 * sizeof(or_pixel));
+            for (int i = 0; i < 4; i++) m.ref[i] = refPlanes[i] + pel;
+            or_mv mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
+            or_mv mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
+
+            or_mv mvc[5]; int numc = 0;
+#define MVC(idx) { mvc[numc].x = mvs[2 * (idx)]; mvc[numc].y = mvs[2 * (idx) + 1]; numc++; }
+            if (cuX < bw - 1) MVC(cuXY + 1);
+            if (!lastRow)
+            {
+                MVC(cuXY + bw);
+                if (cuX > 0) MVC(cuXY + bw - 1);
+                if (cuX < bw - 1) MVC(cuXY + bw + 1);
+            }
+#undef MVC
+            if (!hme && hmeMvs && hmeMvCosts[cuXY_4x4] > 0)
+            {
+                mvc[numc].x = hmeMvs[2 * cuXY_4x4] * 2; mvc[numc].y = hmeMvs[2 * cuXY_4x4 + 1] * 2;
+                numc++;
+            }
+            or_mv mvp = { 0, 0 };
+            int skipCost = 0x7fffffff;
+            if (numc)
+            {
+                int mvpcost = OR_COST_MAX;
+                or_pixel buf[64];
+                for (int i = 0; i < numc; i++)
+                {
+                    int st;
+                    const or_pixel* src = lowres_mc(&m, mvc[i].x, mvc[i].y, buf, &st);
+                    int cost = or_satd8x8(m.fenc, 8, src, st);
+                    if (cost < mvpcost) { mvpcost = cost; mvp = mvc[i]; }
+                    if (!(mvp.x | mvp.y) && bBidir)
+                        skipCost = cost;
+                }
+            }
+            or_mv best;
+            int fencCost = motion_estimate_ex(&m, mvmin, mvmax, mvp, merange, method, &best);
             if (skipCost < 64 && skipCost < fencCost && bBidir)
             {
                 fencCost = skipCost;

@@ -44,6 +44,13 @@ typedef struct
     int32_t rowsPerSlice;   /* Lookahead::m_numRowsPerSlice when the searches run as cooperative slices
                                (slicetype.cpp:1047-1059, 3957-3968); 0 = whole frame */
     int32_t qg8;            /* 1 = qg-size 8: AQ on 8x8 full-res blocks, 4 * ncu qp-offset entries (lowres.cpp:86-89) */
+    /* --hme level 0: the 1/16-resolution planes (lowres.cpp:165-183, 378-388) and their block grid (slicetype.cpp:998-999) */
+    int32_t w4, h4;         /* plane size: w / 2, h / 2 */
+    int32_t bw4, bh4;       /* Lookahead::m_4x4Width / m_4x4Height */
+    int32_t mx4, my4;       /* margins: mx / 2, my / 2 */
+    int32_t stride4;        /* stride / 2 */
+    int64_t planeSize4;     /* planeSize / 2 */
+    int64_t padOffset4;     /* padOffset / 2 */
 } or_geom;
 
 int  or_depth(void);
@@ -105,6 +112,20 @@ void or_intra_estimate(const or_geom* g, const or_pixel* plane0 /* lowresPlane[0
 void or_search_list(const or_geom* g, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
                     const uint16_t* mvcost /* centre */, int bBidir,
                     int32_t* mvs /* ncu*2 */, int32_t* mvCosts /* ncu */, int32_t* skipCount /* may be NULL */);
+
+/* --hme (x265_param::bEnableHME): the four 1/16-resolution planes of a frame from its lowresPlane[0] (lowres.cpp:378-388) */
+void or_lowerres_init(const or_geom* g, const or_pixel* plane0 /* lowresPlane[0], borders extended */, or_pixel* buf4 /* 4 * planeSize4, zeroed */);
+
+/* The same search with --hme: `level` 0 searches the 1/16-resolution planes on the m_4x4 grid (fencPlane0 / refPlanes are then
+ * lowerResPlane[0..3], never weighted, slicetype.cpp:4083-4094), level 1 is the ordinary lowres search with one more predictor,
+ * twice the level-0 vector of the block's 16x16 parent when that search cost more than zero (:4142-4145; hmeMvs / hmeMvCosts =
+ * the level-0 results of the same list and distance).  `method` is X265_DIA_SEARCH (0), X265_HEX_SEARCH (1) or X265_UMH_SEARCH (2)
+ * (hmeSearchMethod[level], motion.cpp:842), `merange` hmeRange[level] (:4170).  Whole-frame searches only: with cooperative
+ * slices the reference's two levels race (see la_oracle.c). */
+void or_search_list_hme(const or_geom* g, int level, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
+                        const uint16_t* mvcost /* centre */, int bBidir, int method, int merange,
+                        const int32_t* hmeMvs /* level 1: bw4*bh4*2 */, const int32_t* hmeMvCosts,
+                        int32_t* mvs, int32_t* mvCosts, int32_t* skipCount /* may be NULL */);
 
 /* Cost half of estimateCUCost + the sums of estimateFrameCost (slicetype.cpp:4187-4248,
  * 4050-4067).  For a P estimate pass ref1Planes = NULL. */

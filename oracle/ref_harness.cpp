@@ -74,6 +74,9 @@ struct RefLaConfig
     int32_t temporalLayers;         /* --temporal-layers (x265_param::bEnableTemporalSubLayers) */
     int32_t histScenecut;           /* --hist-scenecut (x265_param::bHistBasedSceneCut) */
     int32_t csp400;                 /* 1 = 4:0:0 (x265_param::internalCsp = X265_CSP_I400): pictures carry no chroma */
+    int32_t hme;                    /* --hme (x265_param::bEnableHME; the encoder turns it off below 540 lines) */
+    int32_t hmeSearch0, hmeSearch1; /* --hme-search levels 0 and 1 (level 2 is the main encoder's) */
+    int32_t hmeRange0, hmeRange1;   /* --hme-range levels 0 and 1 */
 };
 
 struct RefLaFrame
@@ -115,6 +118,10 @@ struct RefLaFrame
     /* --hist-scenecut: Lowres::picAvgVariance{,Cb,Cr}, averageIntensity[3], and a checksum of picHistogram + averageIntensityPerSegment */
     int32_t histVar[3], histAvg[3];
     uint64_t histCheck;
+    /* --hme: Lowres::lowerResMvs / lowerResMvCosts (the level-0 searches), else NULL */
+    int32_t bw4, bh4;
+    const int32_t*  lowerMvs;       /* 2*nb*ncu4*2 (x,y) */
+    const int32_t*  lowerMvCosts;   /* 2*nb*ncu4 */
 };
 
 } // extern "C"
@@ -134,6 +141,7 @@ struct FrameSnap
     std::vector<int32_t> plannedType, intraCostForRc, estRowSatds;
     std::vector<uint32_t> satdForVbv, intraSatdForVbv;
     std::vector<uint16_t> lowresCostForRc;
+    std::vector<int32_t> lowerMvs, lowerMvCosts;
     Frame* frame;                    /* NULL once the frame was destroyed */
 };
 
@@ -204,6 +212,23 @@ void snapshot(Handle* h, Frame* f)
             }
             s->mvCosts.insert(s->mvCosts.end(), l.lowresMvCosts[list][i], l.lowresMvCosts[list][i] + ncu);
         }
+    if (h->enc->m_param->bEnableHME)
+    {
+        const int bw4 = ((l.width / 2) + X265_LOWRES_CU_SIZE - 1) >> X265_LOWRES_CU_BITS;     /* lowres.cpp:205-207 */
+        const int bh4 = ((l.lines / 2) + X265_LOWRES_CU_SIZE - 1) >> X265_LOWRES_CU_BITS;
+        s->h.bw4 = bw4; s->h.bh4 = bh4;
+        for (int list = 0; list < 2; list++)
+            for (int i = 0; i < nb; i++)
+            {
+                for (int c = 0; c < bw4 * bh4; c++)
+                {
+                    s->lowerMvs.push_back(l.lowerResMvs[list][i][c].x);
+                    s->lowerMvs.push_back(l.lowerResMvs[list][i][c].y);
+                }
+                s->lowerMvCosts.insert(s->lowerMvCosts.end(), l.lowerResMvCosts[list][i], l.lowerResMvCosts[list][i] + bw4 * bh4);
+            }
+        s->h.lowerMvs = s->lowerMvs.data(); s->h.lowerMvCosts = s->lowerMvCosts.data();
+    }
     s->intraCost.assign(l.intraCost, l.intraCost + ncu);
     s->intraMode.assign(l.intraMode, l.intraMode + ncu);
     const int ncuFull = h->enc->m_param->rc.qgSize == 8 ? 4 * ncu : ncu;      /* lowres.cpp:89 */
@@ -328,6 +353,12 @@ void* ref_la_open(const RefLaConfig* c)
     p->bEnableFades = c->fades;
     p->bEnableTemporalSubLayers = c->temporalLayers;
     p->bHistBasedSceneCut = c->histScenecut;
+    if (c->hme)
+    {
+        p->bEnableHME = 1;
+        p->hmeSearchMethod[0] = c->hmeSearch0; p->hmeSearchMethod[1] = c->hmeSearch1;
+        p->hmeRange[0] = c->hmeRange0; p->hmeRange[1] = c->hmeRange1;
+    }
     if (c->vbvBufferSize)
     {
         p->rc.rateControlMode = X265_RC_ABR;

@@ -20,7 +20,9 @@ class RefLaConfig(C.Structure):
                 ("scenecutBias", C.c_double), ("vbvBufferSize", C.c_int32), ("vbvMaxBitrate", C.c_int32),
                 ("bitrate", C.c_int32), ("dumpPlanes", C.c_int32), ("bIntraRefresh", C.c_int32),
                 ("gopLookahead", C.c_int32), ("radl", C.c_int32), ("keepFrames", C.c_int32),
-                ("fades", C.c_int32), ("temporalLayers", C.c_int32), ("histScenecut", C.c_int32), ("csp400", C.c_int32)]
+                ("fades", C.c_int32), ("temporalLayers", C.c_int32), ("histScenecut", C.c_int32), ("csp400", C.c_int32),
+                ("hme", C.c_int32), ("hmeSearch0", C.c_int32), ("hmeSearch1", C.c_int32), ("hmeRange0", C.c_int32),
+                ("hmeRange1", C.c_int32)]
 
 
 class RefLaFrame(C.Structure):
@@ -39,14 +41,16 @@ class RefLaFrame(C.Structure):
                 ("satdForVbv", C.c_void_p), ("intraSatdForVbv", C.c_void_p), ("lowresCostForRc", C.c_void_p),
                 ("intraCostForRc", C.c_void_p), ("estRowSatds", C.c_void_p),
                 ("bIsFadeEnd", C.c_int32), ("pad0", C.c_int32), ("frameVariance", C.c_double),
-                ("histVar", C.c_int32 * 3), ("histAvg", C.c_int32 * 3), ("histCheck", C.c_uint64)]
+                ("histVar", C.c_int32 * 3), ("histAvg", C.c_int32 * 3), ("histCheck", C.c_uint64),
+                ("bw4", C.c_int32), ("bh4", C.c_int32), ("lowerMvs", C.c_void_p), ("lowerMvCosts", C.c_void_p)]
 
 
 DEFAULTS = dict(fpsNum=30, fpsDenom=1, bframes=4, lookaheadDepth=20, bFrameAdaptive=2, bBPyramid=1,
                 scenecutThreshold=40, keyframeMax=250, keyframeMin=0, bOpenGOP=1, aqMode=2, aqStrength=1.0,
                 cuTree=1, qCompress=0.6, weightp=1, weightb=0, poolThreads=0, lookaheadSlices=0, qgSize=32,
                 bFrameBias=0, scenecutBias=5.0, vbvBufferSize=0, vbvMaxBitrate=0, bitrate=0, dumpPlanes=0,
-                bIntraRefresh=0, gopLookahead=0, radl=0, keepFrames=0, fades=0, temporalLayers=0, histScenecut=0, csp400=0)
+                bIntraRefresh=0, gopLookahead=0, radl=0, keepFrames=0, fades=0, temporalLayers=0, histScenecut=0, csp400=0,
+                hme=0, hmeSearch0=1, hmeSearch1=2, hmeRange0=16, hmeRange1=32)
 
 
 def lib_path(depth):
@@ -211,6 +215,11 @@ class RefLookahead:
                             rowSatds=_arr(f.estRowSatds, np.int32, bh))
         d["propagateCost"] = _arr(f.propagateCost, np.uint16, ncu)
         d["weightedCostDelta"] = _arr(f.weightedCostDelta, np.float64, nb)
+        if f.lowerMvs:
+            n4 = f.bw4 * f.bh4
+            d["bw4"], d["bh4"] = f.bw4, f.bh4
+            d["lowerMvs"] = _arr(f.lowerMvs, np.int32, 2 * nb * n4 * 2).reshape(2, nb, n4, 2)
+            d["lowerMvCosts"] = _arr(f.lowerMvCosts, np.int32, 2 * nb * n4).reshape(2, nb, n4)
         if f.planes:
             dt = np.uint8 if self.depth == 8 else np.uint16
             d["planes"] = _arr(f.planes, dt, 4 * f.stride * f.planeLines).reshape(4, f.planeLines, f.stride)

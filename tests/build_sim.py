@@ -27,7 +27,8 @@ def build(force=False):
     oc = os.path.join(ROOT, "oracle", "la_oracle.c")
     oh = os.path.join(ROOT, "oracle", "la_oracle.h")
     host_srcs = [os.path.join(HOST, f) for f in ("lookahead.cpp", "la_capi.cpp")]
-    host_hdrs = [os.path.join(HOST, f) for f in ("lookahead.h", "la_capi.h")] + [os.path.join(ROOT, "include", "x265cu.h")]
+    host_hdrs = [os.path.join(HOST, f) for f in ("lookahead.h", "la_capi.h")] + [os.path.join(ROOT, "include", "x265cu.h"),
+                 os.path.join(ROOT, "x265-amod_b200", "csrc", "la_me_generic.cuh")]
     sim = os.path.join(ROOT, "tests", "simengine", "simengine.cpp")
     for d in (8, 10):
         lib = os.path.join(OUT, "liboracle%d.so" % d)
@@ -37,7 +38,7 @@ def build(force=False):
         lib = os.path.join(OUT, "libx265la_sim%d.so" % d)
         if force or _stale(lib, [oc, oh, sim] + host_srcs + host_hdrs):
             _run(["gcc", "-O2", "-std=c99", "-fPIC", "-c", "-DOR_DEPTH=%d" % d, "-o", obj, oc])
-            _run(["g++", "-O2", "-std=c++11", "-fPIC", "-shared", "-DOR_DEPTH=%d" % d,
+            _run(["g++", "-O2", "-std=c++11", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-DOR_DEPTH=%d" % d,
                   "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"), "-I" + HOST,
                   "-o", lib, sim, obj] + host_srcs + ["-lm"])
     return OUT

@@ -87,6 +87,14 @@ CASES = [
     ("qg8", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=8)),
     ("qg8_ragged10", 10, 328, 184, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=8, aqMode=3)),
     ("qg8_aq1_vbv", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, qgSize=8, aqMode=1, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
+    # --hme (>= 540 lines): every search first runs on the 1/16-resolution planes (level 0), twice its vector is one more predictor
+    # of the lowres search (level 1); per-level search method (hex / umh / dia) and range
+    ("hme_default", 8, 960, 544, 16, dict(cuts=(9,)), dict(bframes=3, lookaheadDepth=8, hme=1)),
+    ("hme_hexhex10", 10, 960, 540, 14, dict(cuts=(6,)), dict(bframes=2, lookaheadDepth=6, hme=1, hmeSearch0=1, hmeSearch1=1, hmeRange0=12, hmeRange1=24)),
+    ("hme_umhdia_pool_fade", 8, 1024, 576, 20, dict(cuts=(), fades=[(5, 8, 0.3)]),
+     dict(bframes=4, lookaheadDepth=10, hme=1, hmeSearch0=2, hmeSearch1=0, hmeRange0=20, hmeRange1=16, poolThreads=16, weightb=1)),
+    # short enough to commit as a golden fixture
+    ("hme_golden", 8, 960, 544, 8, dict(cuts=(4,)), dict(bframes=2, lookaheadDepth=5, hme=1)),
     ("vbv_nocutree", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
 ]
 
@@ -98,7 +106,7 @@ ESTIMATE = ["base8", "base10", "vbv", "radl2", "nocutree", "plain", "intrarefres
 PIR = {"intrarefresh": (2, 3)}
 
 # subset small enough to commit as golden fixtures and to run in the quick CPU suite
-GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob", "slices_golden"]
+GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob", "slices_golden", "hme_golden"]
 
 REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive="bFrameAdaptive", bBPyramid="bBPyramid",
               scenecutThreshold="scenecutThreshold", keyframeMax="keyframeMax", keyframeMin="keyframeMin",
@@ -106,13 +114,16 @@ REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive
               weightp="bEnableWeightedPred", weightb="bEnableWeightedBiPred", qgSize="qgSize", bFrameBias="bFrameBias",
               scenecutBias="scenecutBias", vbvBufferSize="vbvBufferSize", vbvMaxBitrate="vbvMaxBitrate",
               poolThreads="poolWorkers", lookaheadSlices="lookaheadSlices", gopLookahead="gopLookahead", bIntraRefresh="bIntraRefresh", radl="radl",
-              fades="bEnableFades", fpsNum="fpsNum", fpsDenom="fpsDenom", temporalLayers="bEnableTemporalSubLayers", histScenecut="bHistBasedSceneCut")
+              fades="bEnableFades", fpsNum="fpsNum", fpsDenom="fpsDenom", temporalLayers="bEnableTemporalSubLayers", histScenecut="bHistBasedSceneCut", hme="bEnableHME")
 
 
 def la_kwargs(refkw):
     kw = {REF2LA[k]: v for k, v in refkw.items() if k in REF2LA}
     if "bitrate" in refkw:
         kw["rateControlMode"] = 0
+    if refkw.get("hme"):
+        kw["hmeSearchMethod"] = (refkw.get("hmeSearch0", 1), refkw.get("hmeSearch1", 2))
+        kw["hmeRange"] = (refkw.get("hmeRange0", 16), refkw.get("hmeRange1", 32))
     return kw
 
 

@@ -69,6 +69,13 @@ def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutr
                 if not np.array_equal(ref["mvCosts"][l, d], got["mvCosts"][l, d]):
                     n = int(np.sum(ref["mvCosts"][l, d] != got["mvCosts"][l, d]))
                     bad.append(tag + "lowresMvCosts[%d][%d] differ in %d blocks" % (l, d, n))
+                if "lowerMvs" in ref and "lowerMvs" in got:     # --hme: the level-0 search behind it
+                    if not np.array_equal(ref["lowerMvs"][l, d], got["lowerMvs"][l, d]):
+                        n = int(np.sum(np.any(ref["lowerMvs"][l, d] != got["lowerMvs"][l, d], axis=1)))
+                        bad.append(tag + "lowerResMvs[%d][%d] differ in %d blocks" % (l, d, n))
+                    if not np.array_equal(ref["lowerMvCosts"][l, d], got["lowerMvCosts"][l, d]):
+                        n = int(np.sum(ref["lowerMvCosts"][l, d] != got["lowerMvCosts"][l, d]))
+                        bad.append(tag + "lowerResMvCosts[%d][%d] differ in %d blocks" % (l, d, n))
     for i in range(nb):
         for j in range(nb):
             ref_done = ref["rowSatds"][i, j, 0] != -1 and ref["costEst"][i, j] >= 0

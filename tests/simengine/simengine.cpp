@@ -13,11 +13,93 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+/* the PRODUCT's generic search source (dia / hex / umh + subpel), compiled for the CPU with a scalar evaluator: with
+ * X265SIM_GENERIC_ME=1 in the environment the --hme searches below run through it instead of the oracle's restatement, so
+ * the text the CUDA kernel compiles is itself checked against the reference (control flow and arithmetic; the warp-level
+ * evaluators are checked on the GPU) */
+#include "../../x265-amod_b200/csrc/la_me_generic.cuh"
+
+namespace {
+struct CpuMeCtx
+{
+    or_pixel fenc[64];
+    const or_pixel* ref[4];
+    int stride;
+    const uint16_t* mvcost;
+    int mvpx, mvpy;
+    int mvc(int qx, int qy) const { return (uint16_t)(mvcost[qx - mvpx] + mvcost[qy - mvpy]); }
+    int sadFpel(int x, int y) const { return or_sad8x8(fenc, 8, ref[0] + x + (int64_t)y * stride, stride); }
+    const or_pixel* mc(int qx, int qy, or_pixel* buf, int* st) const      /* lowres.h:71-96 */
+    {
+        const int hA = (qy & 2) | ((qx & 2) >> 1);
+        const or_pixel* a = ref[hA] + (qx >> 2) + (int64_t)(qy >> 2) * stride;
+        if (!((qx | qy) & 1)) { *st = stride; return a; }
+        const int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
+        const int hB = (qy2 & 2) | ((qx2 & 2) >> 1);
+        const or_pixel* b = ref[hB] + (qx2 >> 2) + (int64_t)(qy2 >> 2) * stride;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++)
+                buf[y * 8 + x] = (or_pixel)((a[y * stride + x] + b[y * stride + x] + 1) >> 1);
+        *st = 8;
+        return buf;
+    }
+    int qpelSad(int qx, int qy) const { or_pixel buf[64]; int st; const or_pixel* p = mc(qx, qy, buf, &st); return or_sad8x8(fenc, 8, p, st); }
+    int qpelSatd(int qx, int qy) const { or_pixel buf[64]; int st; const or_pixel* p = mc(qx, qy, buf, &st); return or_satd8x8(fenc, 8, p, st); }
+};
+
+/* same contract as or_search_list_hme (oracle/la_oracle.h), the per-block search done by la::motionEstimateG */
+void genericSearchList(const or_geom* g, int level, const or_pixel* fencPlane0, const or_pixel* const refPlanes[4],
+                       const uint16_t* mvcost, int bBidir, int method, int merange, const int32_t* hmeMvs, const int32_t* hmeMvCosts,
+                       int32_t* mvs, int32_t* mvCosts, int32_t* skipCount)
+{
+    const bool hme = level == 0;
+    const int bw = hme ? g->bw4 : g->bw, bh = hme ? g->bh4 : g->bh, stride = hme ? g->stride4 : g->stride;
+    int skips = 0;
+    CpuMeCtx m;
+    m.stride = stride; m.mvcost = mvcost;
+    for (int cuY = bh - 1; cuY >= 0; cuY--)
+        for (int cuX = bw - 1; cuX >= 0; cuX--)
+        {
+            const int cu = cuX + cuY * bw;
+            const int64_t pel = 8 * cuX + (int64_t)8 * cuY * stride;
+            for (int y = 0; y < 8; y++) memcpy(m.fenc + 8 * y, fencPlane0 + pel + (int64_t)y * stride, 8 * sizeof(or_pixel));
+            for (int i = 0; i < 4; i++) m.ref[i] = refPlanes[i] + pel;
+            const la::MV2 mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 }, mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
+            la::MV2 cand[5]; int numc = 0;
+            const bool lastRow = cuY == bh - 1;
+            if (cuX < bw - 1) { cand[numc].x = mvs[2 * (cu + 1)]; cand[numc].y = mvs[2 * (cu + 1) + 1]; numc++; }
+            if (!lastRow)
+            {
+                cand[numc].x = mvs[2 * (cu + bw)]; cand[numc].y = mvs[2 * (cu + bw) + 1]; numc++;
+                if (cuX > 0) { cand[numc].x = mvs[2 * (cu + bw - 1)]; cand[numc].y = mvs[2 * (cu + bw - 1) + 1]; numc++; }
+                if (cuX < bw - 1) { cand[numc].x = mvs[2 * (cu + bw + 1)]; cand[numc].y = mvs[2 * (cu + bw + 1) + 1]; numc++; }
+            }
+            const int cu4 = (cuX / 2) + (cuY / 2) * bw / 2;
+            if (!hme && hmeMvs && hmeMvCosts[cu4] > 0) { cand[numc].x = hmeMvs[2 * cu4] * 2; cand[numc].y = hmeMvs[2 * cu4 + 1] * 2; numc++; }
+            la::MV2 mvp = { 0, 0 };
+            int skipCost = 0x7fffffff, mvpcost = 1 << 28;
+            for (int i = 0; i < numc; i++)
+            {
+                const int cost = m.qpelSatd(cand[i].x, cand[i].y);
+                if (cost < mvpcost) { mvpcost = cost; mvp = cand[i]; }
+                if (!(mvp.x | mvp.y) && bBidir) skipCost = cost;
+            }
+            la::MV2 best;
+            int fencCost = la::motionEstimateG(m, mvmin, mvmax, mvp, merange, method, best);
+            if (skipCost < 64 && skipCost < fencCost && bBidir) { fencCost = skipCost; best.x = best.y = 0; skips++; }
+            mvs[2 * cu] = best.x; mvs[2 * cu + 1] = best.y;
+            mvCosts[cu] = fencCost;
+        }
+    if (skipCount) *skipCount = skips;
+}
+} // namespace
 
 struct SimSlot
 {
     std::vector<or_pixel> y, u, v;
     std::vector<or_pixel> planes;
+    std::vector<or_pixel> planes4;                              /* --hme: the four 1/16-resolution planes */
+    std::vector<std::vector<int32_t> > mvs4, mvCosts4;          /* --hme: level-0 results per MV store */
     std::vector<int32_t> intraCost, invQ, invQ8, rowSatds00;
     std::vector<uint8_t> intraMode;
     std::vector<uint16_t> lowresCosts00, propagate;
@@ -94,6 +176,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
 {
     if (cfg->depth != or_depth()) return X265CU_ERR_BAD_ARG;
     if (cfg->hist_stats && cfg->depth != 8) return X265CU_ERR_UNSUPPORTED;
+    if (cfg->hme && (cfg->hme_search[0] < 0 || cfg->hme_search[0] > 2 || cfg->hme_search[1] < 0 || cfg->hme_search[1] > 2)) return X265CU_ERR_UNSUPPORTED;
     x265cu_ctx* c = new x265cu_ctx;
     c->cfg = *cfg;
     or_geom_init(&c->g, cfg->width, cfg->height, cfg->max_cu_size);
@@ -161,6 +244,11 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     else { s.u.clear(); s.v.clear(); }
     s.planes.assign((size_t)(4 * g.planeSize), 0);
     or_lowres_init(&g, &s.y[0], W, &s.planes[0]);
+    if (c->cfg.hme)
+    {
+        s.planes4.assign((size_t)(4 * g.planeSize4), 0);
+        or_lowerres_init(&g, &s.planes[g.padOffset], &s.planes4[0]);
+    }
     const int ncu = g.ncu, nb = c->geom.nb;
     /* the qp-offset arrays are allocated zeroed once per Lowres in the reference (lowres.cpp:98-106) and entries the
      * running AQ index never reaches stay zero */
@@ -171,6 +259,7 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     const int nmv = c->geom.n_mv_stores, ncs = c->geom.n_cost_stores;
     s.mvs.assign(nmv, std::vector<int32_t>()); s.mvCosts.assign(nmv, std::vector<int32_t>());
     s.skipFlag.assign(nmv, 0);
+    s.mvs4.assign(nmv, std::vector<int32_t>()); s.mvCosts4.assign(nmv, std::vector<int32_t>());
     s.costs.assign(ncs, std::vector<uint16_t>()); s.rowSatds.assign(ncs, std::vector<int32_t>());
     s.results.assign(ncs, x265cu_cost_result());
     memset(&s.stats, 0, sizeof(s.stats));
@@ -240,6 +329,26 @@ int x265cu_search_batch(x265cu_ctx* c, const x265cu_search_job* jobs, int32_t n)
         f.mvs[j.store].assign(2 * g.ncu, 0); f.mvCosts[j.store].assign(g.ncu, 0);
         or_geom gj = g;
         gj.rowsPerSlice = j.sliced ? c->cfg.rows_per_slice : 0;
+        if (c->cfg.hme)
+        {
+            /* level 0 on the 1/16-resolution planes (never weighted), then level 1 fed with its vectors; a skip at either
+             * level makes the B-context search differ from the P-context one (x265cu_search_job::cond_store) */
+            const int n4 = g.bw4 * g.bh4;
+            f.mvs4[j.store].assign(2 * n4, 0); f.mvCosts4[j.store].assign(n4, 0);
+            const or_pixel* rp4[4];
+            for (int k = 0; k < 4; k++) rp4[k] = &r.planes4[(size_t)(k * g.planeSize4 + g.padOffset4)];
+            int32_t skips0 = 0, skips1 = 0;
+            static const bool generic = getenv("X265SIM_GENERIC_ME") && atoi(getenv("X265SIM_GENERIC_ME"));
+            void (*searchList)(const or_geom*, int, const or_pixel*, const or_pixel* const*, const uint16_t*, int, int, int, const int32_t*,
+                               const int32_t*, int32_t*, int32_t*, int32_t*) = generic ? genericSearchList : or_search_list_hme;
+            searchList(&gj, 0, &f.planes4[g.padOffset4], rp4, &c->mvcost[c->cfg.mvcost_half], j.bidir_ctx,
+                               c->cfg.hme_search[0], c->cfg.hme_range[0], NULL, NULL, &f.mvs4[j.store][0], &f.mvCosts4[j.store][0], &skips0);
+            searchList(&gj, 1, &f.planes[g.padOffset], rp, &c->mvcost[c->cfg.mvcost_half], j.bidir_ctx,
+                               c->cfg.hme_search[1], c->cfg.hme_range[1], &f.mvs4[j.store][0], &f.mvCosts4[j.store][0],
+                               &f.mvs[j.store][0], &f.mvCosts[j.store][0], &skips1);
+            f.skipFlag[j.store] = skips0 + skips1;
+        }
+        else
         or_search_list(&gj, &f.planes[g.padOffset], rp, &c->mvcost[c->cfg.mvcost_half], j.bidir_ctx,
                        &f.mvs[j.store][0], &f.mvCosts[j.store][0], &f.skipFlag[j.store]);
         c->counters.kernel_launches++;
@@ -428,6 +537,16 @@ int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, in
     if (s.mvs[store].empty()) return X265CU_ERR_BAD_ARG;
     if (mv) memcpy(mv, &s.mvs[store][0], c->g.ncu * 8);
     if (cost) memcpy(cost, &s.mvCosts[store][0], c->g.ncu * 4);
+    return 0;
+}
+
+int x265cu_fetch_hme_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost)
+{
+    SimSlot& s = c->slots[slot];
+    if (!c->cfg.hme || s.mvs4[store].empty()) return X265CU_ERR_BAD_ARG;
+    const int n4 = c->g.bw4 * c->g.bh4;
+    if (mv) memcpy(mv, &s.mvs4[store][0], n4 * 8);
+    if (cost) memcpy(cost, &s.mvCosts4[store][0], n4 * 4);
     return 0;
 }
 

@@ -69,6 +69,8 @@ CLI_CASES = [
     # --hist-scenecut (8-bit) and two temporal layers
     ("hist_scenecut", 8, 640, 360, 60, dict(cuts=(17, 41), envelope=[(0, 1.0), (16, 1.0), (17, 0.5), (40, 0.5), (41, 0.95), (59, 0.95)]),
      ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--hist-scenecut"]),
+    # --hme: the lookahead's level-0 / level-1 searches on the GPU (hex, umh), the main encoder's level 2 fed by the mirrored lowres MVs
+    ("hme_544p", 8, 960, 544, 24, dict(cuts=(11,)), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--hme"]),
     ("temporal_layers_2", 8, 640, 360, 50, dict(cuts=(23,)),
      ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--bframes", "7", "--temporal-layers", "2"]),
 ]

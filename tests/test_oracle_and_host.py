@@ -45,6 +45,32 @@ def test_sim_pipeline_matches_live_reference(name, pkg, synth, simdir):
     assert not bad, "\n".join(bad[:10])
 
 
+@pytest.mark.parametrize("name", ["hme_default", "hme_hexhex10", "hme_umhdia_pool_fade"])
+def test_generic_search_source_on_cpu(name):
+    """--hme: the source text of the product's dia / hex / umh searches (csrc/la_me_generic.cuh, what search_hme_kernel compiles)
+    built for the CPU with a scalar evaluator reproduces the live reference (the warp-level evaluators are the GPU suite's job)"""
+    import subprocess
+    import sys
+    if not refbind.available(cases.get_case(name)[1]):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "hme_generic_check.py"), name], env=dict(os.environ, X265SIM_GENERIC_ME="1"),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_hme_refusals(pkg, simdir):
+    """--hme outside what is built fails loudly at create: star / sea / full at levels 0-1, and active lookahead slices (where the
+    reference's two levels race on uninitialised vectors)"""
+    sim = _sim(simdir, 8)
+    with pytest.raises(RuntimeError, match="hme-search"):
+        pkg.Lookahead(960, 544, depth=8, lib_path=sim, bEnableHME=1, hmeSearchMethod=(3, 2))
+    with pytest.raises(RuntimeError, match="lookahead slices"):
+        pkg.Lookahead(1280, 720, depth=8, lib_path=sim, bEnableHME=1, poolWorkers=8, lookaheadSlices=4)
+    # below 540 lines the encoder itself turns --hme off (encoder.cpp:4400-4407): accepted, and plain searches run
+    pkg.Lookahead(320, 192, depth=8, lib_path=sim, bEnableHME=1).close()
+
+
 def test_speculation_off_gives_same_results(pkg, synth, simdir):
     case = cases.get_case("base8")
     a = cases.run_ours(pkg, synth, case, lib_path=_sim(simdir, 8), speculate=1)

@@ -38,7 +38,8 @@ class LaParam(C.Structure):
                 ("extraSlots", C.c_int32), ("speculate", C.c_int32), ("pinHost", C.c_int32),
                 ("asyncDepth", C.c_int32), ("pendingMax", C.c_int32), ("shardCount", C.c_int32), ("batchMin", C.c_int32), ("gopLookahead", C.c_int32), ("radl", C.c_int32),
                 ("csvLogLevel", C.c_int32), ("numRowsPerSlice", C.c_int32), ("bEnableFades", C.c_int32),
-                ("bEnableTemporalSubLayers", C.c_int32), ("bHistBasedSceneCut", C.c_int32)]
+                ("bEnableTemporalSubLayers", C.c_int32), ("bHistBasedSceneCut", C.c_int32),
+                ("bEnableHME", C.c_int32), ("hmeSearchMethod", C.c_int32 * 2), ("hmeRange", C.c_int32 * 2)]
 
 
 class FrameInfo(C.Structure):
@@ -112,6 +113,7 @@ def load_lib(path=None):
     lib.x265la_release.argtypes = [C.c_void_p, C.c_void_p]
     lib.x265la_frame_scalars.argtypes = [C.c_void_p] * 9
     lib.x265la_frame_mvs.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.x265la_frame_hme_mvs.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.x265la_frame_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.x265la_frame_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FrameOut)]
     lib.x265la_frame_weights.argtypes = [C.c_void_p] * 6
@@ -154,10 +156,13 @@ def make_param(width, height, depth=8, **kw):
              keyframeMax=250, keyframeMin=0, bOpenGOP=1, bIntraRefresh=0, bEnableWeightedPred=1,
              bEnableWeightedBiPred=0, lookaheadSlices=0, maxNumReferences=3, aqMode=2, aqStrength=1.0,
              cuTree=1, qCompress=0.6, qgSize=32, vbvBufferSize=0, vbvMaxBitrate=0, rateControlMode=2,
-             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0, shardCount=0, batchMin=0, gopLookahead=0, radl=0, csvLogLevel=0, numRowsPerSlice=0, bEnableFades=0, bEnableTemporalSubLayers=0, bHistBasedSceneCut=0)
+             poolWorkers=0, device=0, extraSlots=8, speculate=1, pinHost=0, asyncDepth=0, pendingMax=0, shardCount=0, batchMin=0, gopLookahead=0, radl=0, csvLogLevel=0, numRowsPerSlice=0, bEnableFades=0, bEnableTemporalSubLayers=0, bHistBasedSceneCut=0,
+             bEnableHME=0, hmeSearchMethod=(1, 2), hmeRange=(16, 32))
     d.update(kw)
     lib_defaults.sourceWidth, lib_defaults.sourceHeight = width, height
     for k, v in d.items():
+        if isinstance(v, (tuple, list)):
+            v = (C.c_int32 * len(v))(*v)
         setattr(lib_defaults, k, v)
     return lib_defaults
 
@@ -255,6 +260,15 @@ class Lookahead:
             for i in range(nb):
                 searched[l, i] = bool(self.lib.x265la_frame_mvs(self.h, hnd, l, i, mvs[l, i].ctypes.data, mvc[l, i].ctypes.data))
         d.update(mvs=mvs, mvCosts=mvc, searched=searched)
+        if self.param.bEnableHME and self.param.sourceHeight >= 540:
+            # level-0 results of --hme behind every published search (Lowres::lowerResMvs / lowerResMvCosts)
+            n4 = (((self.param.sourceWidth // 4) + 7) >> 3) * (((self.param.sourceHeight // 4) + 7) >> 3)
+            lm = np.zeros((2, nb, n4, 2), np.int32); lmc = np.zeros((2, nb, n4), np.int32)
+            for l in range(2):
+                for i in range(nb):
+                    if searched[l, i]:
+                        self.lib.x265la_frame_hme_mvs(self.h, hnd, l, i, lm[l, i].ctypes.data, lmc[l, i].ctypes.data)
+            d.update(lowerMvs=lm, lowerMvCosts=lmc)
         ws = np.zeros((4, nb), np.int32)
         self.lib.x265la_frame_weights(self.h, hnd, ws[0].ctypes.data, ws[1].ctypes.data, ws[2].ctypes.data, ws[3].ctypes.data)
         d.update(weightState=ws[0], weightParams=ws[1:].T.copy())

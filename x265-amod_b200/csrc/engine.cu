@@ -56,8 +56,8 @@ namespace {
 struct SlotLayout
 {
     size_t srcY, srcU, srcV, planes, intraCost, intraMode, invQ, invQ8, qpAq, qpCuTree, propagate, energy, aqSums,
-           lowresCosts00, rowSatds00, stats, mvStores, costStores, total;
-    size_t mvStoreStride, costStoreStride, costRowOff, costResOff;
+           lowresCosts00, rowSatds00, stats, mvStores, costStores, planes4, mvStores4, total;
+    size_t mvStoreStride, costStoreStride, costRowOff, costResOff, mvStore4Stride;
 };
 
 inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -91,6 +91,7 @@ struct x265cu_ctx
 {
     x265cu_config cfg;
     Geom g;
+    Geom g4;                        /* --hme: geometry of the 1/16-resolution planes and their block grid (level 0) */
     x265cu_geometry geom;
     int bpp;
     SlotLayout lay;
@@ -791,6 +792,17 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
         const long long tileRows = 4LL * g.tpr * g.planeLines;
         extend_border_kernel<P><<<(unsigned)((tileRows + 255) / 256), 256, 0, ps>>>(g, planes);
     }
+    if (c->cfg.hme)
+    {
+        /* the 1/16-resolution planes of HME level 0 from the finished lowresPlane[0] (lowres.cpp:378-388) */
+        const Geom& g4 = c->g4;
+        Prof pr(c, X265CU_K_LOWRES, 2, ps);
+        P* planes4 = slotPtr<P>(c, slot, L.planes4);
+        const long long n4 = (long long)((g4.w + 7) & ~7) * g4.h;
+        lowerres_kernel<P><<<(unsigned)((n4 + 255) / 256), 256, 0, ps>>>(g, g4, planes, planes4);
+        const long long tileRows4 = 4LL * g4.tpr * g4.planeLines;
+        extend_border_kernel<P><<<(unsigned)((tileRows4 + 255) / 256), 256, 0, ps>>>(g4, planes4);
+    }
     if (c->cfg.need_aq)
     {
         const bool twoPass = (c->cfg.aq_mode == 2 || c->cfg.aq_mode == 3) && c->cfg.aq_strength != 0;
@@ -864,9 +876,12 @@ int ensureScratch(x265cu_ctx* c, std::vector<char*>& scratch, cudaStream_t strea
     return X265CU_OK;
 }
 
+template <typename P> int searchBatchHmeT(x265cu_ctx* c, const x265cu_search_job* jobs, int n);
+
 template <typename P>
 int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
 {
+    if (c->cfg.hme) return searchBatchHmeT<P>(c, jobs, n);
     HostTimer ht(HT_SEARCH_ENQ);
     const Geom& g = c->g;
     const SlotLayout& L = c->lay;
@@ -976,6 +991,120 @@ int searchBatchT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
         else
             search_kernel<P, 4><<<n * workers, 32, c->searchSmem, b->stream>>>(g, (const SearchJobDev<P>*)dst, nstrips, n,
                                                            c->d_mvcost + c->cfg.mvcost_half, dsync, dsync + 1, c->d_executed, c->searchOneShot);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->searchDone, b->stream));
+    if (implicit) return endBatch(c);
+    return X265CU_OK;
+}
+
+/* --hme: every search job is two launches of search_hme_kernel on the batch's stream -- level 0 on the 1/16-resolution planes
+ * into the slot's level-0 store of the same index, then level 1 (the lowres search proper) reading it.  Bookkeeping (writer
+ * table, slot users, shard segments, weighted copies, conditions) is that of searchBatchT. */
+template <typename P>
+int searchBatchHmeT(x265cu_ctx* c, const x265cu_search_job* jobs, int n)
+{
+    HostTimer ht(HT_SEARCH_ENQ);
+    const Geom& g = c->g;
+    const Geom& g4 = c->g4;
+    const SlotLayout& L = c->lay;
+    const bool implicit = !c->cur;
+    if (implicit) { int st = beginBatch(c); if (st) return st; }
+    Batch* b = c->cur;
+    char *hst, *dst;
+    int st = batchStage(c, b, 2 * alignUp((size_t)n * sizeof(SearchJobHme<P>), 16), &hst, &dst);
+    if (st) return st;
+    std::vector<SearchJobHme<P> > lv0, lv1;
+    std::map<std::vector<int>, int> wmap;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_search_job& j = jobs[i];
+        if (!slotOk(c, j.fenc_slot) || !slotOk(c, j.ref_slot) || j.store < 0 || j.store >= c->geom.n_mv_stores ||
+            j.cond_store >= c->geom.n_mv_stores || j.sliced)
+        { snprintf(c->err, sizeof(c->err), "search job %d: bad slot/store", i); return X265CU_ERR_BAD_ARG; }
+        char* ms = mvStorePtr(c, j.fenc_slot, j.store);
+        touchSlot(c, j.fenc_slot, b->id); touchSlot(c, j.ref_slot, b->id);
+        st = batchWaitDone(c, b, c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.store]);
+        if (st) return st;
+        c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.store] = b->id;
+        if (c->nranks > 1)
+        {
+            Batch::Seg sg = { ms, (size_t)g.ncu * 8 + 4, c->slotOwner[j.fenc_slot] };
+            b->segs.push_back(sg);
+            if (sg.root != c->rank) continue;
+        }
+        const P* refBuf = slotPtr<P>(c, j.ref_slot, L.planes);
+        if (j.weighted)
+        {
+            std::vector<int> key(4);
+            key[0] = j.ref_slot; key[1] = j.w_scale; key[2] = j.w_denom; key[3] = j.w_offset;
+            std::map<std::vector<int>, int>::iterator it = wmap.find(key);
+            int idx;
+            if (it == wmap.end())
+            {
+                idx = (int)wmap.size();
+                wmap[key] = idx;
+                st = ensureScratch(c, b->weightScratch, b->stream, idx + 1);
+                if (st) return st;
+                st = weightPlanes<P>(c, b->stream, refBuf, (P*)b->weightScratch[idx], 4, j.w_scale, j.w_denom, j.w_offset);
+                if (st) return st;
+            }
+            else
+                idx = it->second;
+            refBuf = (const P*)b->weightScratch[idx];
+        }
+        int* ms4 = (int*)(c->slots[j.fenc_slot] + L.mvStores4 + (size_t)j.store * L.mvStore4Stride);
+        SearchJobHme<P> D0, D1;
+        D0.fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes4);
+        D0.ref0 = slotPtr<P>(c, j.ref_slot, L.planes4);         /* never the weighted reference (slicetype.cpp:4083) */
+        D0.mvOut = ms4; D0.costOut = ms4 + g4.ncu;
+        D0.flagOut = (int*)ms + 2 * g.ncu;
+        D0.cond = NULL;
+        if (j.cond_store >= 0)
+        {
+            D0.cond = (const int*)mvStorePtr(c, j.fenc_slot, j.cond_store) + 2 * g.ncu;
+            st = batchWaitSearches(c, b, c->mvWriter[(size_t)j.fenc_slot * c->geom.n_mv_stores + j.cond_store]);
+            if (st) return st;
+        }
+        D0.hmeMv = NULL; D0.hmeCost = NULL;
+        D0.bidir = j.bidir_ctx; D0.pad = 0;
+        D1 = D0;
+        D1.fenc0 = slotPtr<P>(c, j.fenc_slot, L.planes);
+        D1.ref0 = refBuf;
+        D1.mvOut = (int*)ms; D1.costOut = (int*)ms + g.ncu;
+        D1.hmeMv = ms4; D1.hmeCost = ms4 + g4.ncu;
+        lv0.push_back(D0); lv1.push_back(D1);
+    }
+    n = (int)lv0.size();
+    if (!n)
+    {
+        CK(cudaEventRecord(b->searchDone, b->stream));
+        return implicit ? endBatch(c) : X265CU_OK;
+    }
+    const size_t half = alignUp((size_t)n * sizeof(SearchJobHme<P>), 16);
+    memcpy(hst, &lv0[0], (size_t)n * sizeof(SearchJobHme<P>));
+    memcpy(hst + half, &lv1[0], (size_t)n * sizeof(SearchJobHme<P>));
+    const int nstrips0 = (g4.bh + 3) / 4, nstrips1 = (g.bh + 3) / 4;
+    c->searchEnq += n;
+    int* dsync;
+    const size_t sync0 = 1 + (size_t)n * nstrips0, sync1 = 1 + (size_t)n * nstrips1;
+    st = batchSync(c, b, sync0 + sync1, &dsync);
+    if (st) return st;
+    {
+        void* hAlias = hostAlias(hst);
+        if (!hAlias) { snprintf(c->err, sizeof(c->err), "job staging memory is not device-visible"); return X265CU_ERR_CUDA; }
+        st = stageLaunch(c, b->stream, dst, hAlias, half + alignUp((size_t)n * sizeof(SearchJobHme<P>), 16), NULL, NULL, 0, (unsigned*)dsync, sync0 + sync1);
+        if (st) return st;
+    }
+    {
+        Prof pr(c, X265CU_K_SEARCH, 2, b->stream);
+        const unsigned short* mvc = c->d_mvcost + c->cfg.mvcost_half;
+        search_hme_kernel<P><<<n * std::max(1, (nstrips0 + 1) / 2), 32, 0, b->stream>>>(g4, (const SearchJobHme<P>*)dst, nstrips0, n, mvc,
+                                                                                         dsync, dsync + 1, c->d_executed, 0,
+                                                                                         c->cfg.hme_search[0], c->cfg.hme_range[0]);
+        search_hme_kernel<P><<<n * std::max(1, (nstrips1 + 1) / 2), 32, 0, b->stream>>>(g, (const SearchJobHme<P>*)(dst + half), nstrips1, n, mvc,
+                                                                                         dsync + sync0, dsync + sync0 + 1, c->d_executed, 1,
+                                                                                         c->cfg.hme_search[1], c->cfg.hme_range[1]);
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(b->searchDone, b->stream));
@@ -1261,6 +1390,15 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
             (cfg->height + 15) / 16 + 1 > LA_FADE_MAX_ROWS)
             return X265CU_ERR_UNSUPPORTED;
     }
+    if (cfg->hme)
+    {
+        /* dia / hex / umh only (la_me_generic.cuh).  No cooperative slices: the reference's two levels race there (its level-1
+         * slices read level-0 vectors other workers may not have written).  CTU >= 32: the level-0 margins (half the lowres
+         * ones) must be whole tiles and cover what a search can reach */
+        for (int i = 0; i < 2; i++)
+            if (cfg->hme_search[i] < 0 || cfg->hme_search[i] > 2 || cfg->hme_range[i] < 4 || cfg->hme_range[i] > 256) return X265CU_ERR_UNSUPPORTED;
+        if (cfg->rows_per_slice > 0 || cfg->max_cu_size < 32 || cfg->width < 64 || cfg->height < 64) return X265CU_ERR_UNSUPPORTED;
+    }
     if (cfg->width < 16 || cfg->height < 16 || cfg->bframes < 0 || cfg->bframes > 16 || cfg->max_slots < 1 || !cfg->mvcost)
         return X265CU_ERR_BAD_ARG;
     int ndev = 0;
@@ -1317,6 +1455,19 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     g.aqBlock = cfg->qg_size == 8 ? 8 : 16;
     g.aqW = (g.picW + g.aqBlock - 1) / g.aqBlock; g.aqH = (g.picH + g.aqBlock - 1) / g.aqBlock;
     g.ncuFull = cfg->qg_size == 8 ? 4 * g.ncu : g.ncu;
+    /* --hme level 0 (lowres.cpp:165-183, 378-388; slicetype.cpp:998-999): planes of w / 2 x h / 2 samples with half the
+     * margins; the buffer is a little larger than the reference's (whole tiles, and room for the clamped loads) */
+    Geom& g4 = c->g4;
+    g4 = g;
+    g4.w = g.w / 2; g4.h = g.h / 2;
+    g4.bw = ((cfg->width / 4) + 7) >> 3; g4.bh = ((cfg->height / 4) + 7) >> 3; g4.ncu = g4.bw * g4.bh;
+    g4.mx = g.mx / 2; g4.my = g.my / 2;
+    g4.stride = (std::max(g4.w, 8 * g4.bw) + 2 * g4.mx + 16 + 7) & ~7;
+    g4.planeLines = (std::max(g4.h, 8 * g4.bh) + 2 * g4.my + 16 + 7) & ~7;
+    g4.planeSize = (long long)g4.stride * g4.planeLines;
+    g4.padOffset = (long long)g4.stride * g4.my + g4.mx;
+    g4.tpr = g4.stride / 8;
+    g4.rowsPerSlice = 0;
     x265cu_geometry& G = c->geom;
     G.low_width = g.w; G.low_height = g.h; G.bw = g.bw; G.bh = g.bh; G.ncu = g.ncu; G.stride = g.stride;
     G.plane_lines = g.planeLines; G.margin_x = g.mx; G.margin_y = g.my; G.nb = g.nb;
@@ -1351,6 +1502,13 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     L.costResOff = L.costRowOff + alignUp((size_t)g.bh * 4, 16);
     L.costStoreStride = alignUp(L.costResOff + sizeof(CostResultDev), 256);
     SECTION(costStores, L.costStoreStride * G.n_cost_stores);
+    L.mvStore4Stride = alignUp((size_t)g4.ncu * 8, 256);        /* level-0 packed MVs + costs of one (list, distance) */
+    if (cfg->hme)
+    {
+        SECTION(planes4, (size_t)(4 * g4.planeSize) * c->bpp + 256);
+        SECTION(mvStores4, L.mvStore4Stride * G.n_mv_stores);
+    }
+    else { L.planes4 = L.mvStores4 = 0; }
 #undef SECTION
     L.total = o;
 
@@ -2356,6 +2514,30 @@ int x265cu_fetch_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, in
         st = d2h(c, mv, c->d_results, (size_t)g.ncu * 8);
     }
     if (cost && !st) st = d2h(c, cost, st0 + g.ncu, (size_t)g.ncu * 4);
+    if (st) return st;
+    CK(cudaStreamSynchronize(c->stream));
+    return X265CU_OK;
+}
+
+int x265cu_fetch_hme_mvs(x265cu_ctx* c, int32_t slot, int32_t store, int32_t* mv, int32_t* cost)
+{
+    if (!c) return X265CU_ERR_BAD_ARG;
+    DeviceScope deviceScope(c);
+    flushCutree(c);
+    if (!c->cfg.hme || !slotOk(c, slot) || store < 0 || store >= c->geom.n_mv_stores) return X265CU_ERR_BAD_ARG;
+    const int n4 = c->g4.ncu;
+    const int* st0 = (const int*)(c->slots[slot] + c->lay.mvStores4 + (size_t)store * c->lay.mvStore4Stride);
+    int st = mainWaitMv(c, slot, store);
+    if (st) return st;
+    if (mv)
+    {
+        st = ensureDev(c, &c->d_results, &c->resultsCap, (size_t)n4 * 8);
+        if (st) return st;
+        unpack_mv_kernel<<<(n4 + 255) / 256, 256, 0, c->stream>>>(st0, (int*)c->d_results, n4);
+        c->counters.kernel_launches++;
+        st = d2h(c, mv, c->d_results, (size_t)n4 * 8);
+    }
+    if (cost && !st) st = d2h(c, cost, st0 + n4, (size_t)n4 * 4);
     if (st) return st;
     CK(cudaStreamSynchronize(c->stream));
     return X265CU_OK;

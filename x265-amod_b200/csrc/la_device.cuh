@@ -269,6 +269,38 @@ __device__ __forceinline__ int groupSatdRows(const Row<P>& a, const Row<P>& b)
     return groupSatdH(toH(a), toH(b));
 }
 
+/* The same two reductions with an explicit lane mask (the 8 lanes of ONE group): the four groups of a warp may then run
+ * different control flow -- the generic searches of --hme (la_me_generic.cuh) are plain sequential code per block, not the
+ * warp-wide lockstep of the default search */
+__device__ __forceinline__ int groupSumM(int v, unsigned mask)
+{
+    v += __shfl_xor_sync(mask, v, 1);
+    v += __shfl_xor_sync(mask, v, 2);
+    v += __shfl_xor_sync(mask, v, 4);
+    return v;
+}
+__device__ __forceinline__ int groupSatdHM(const RowH& a, const RowH& b, unsigned mask)
+{
+    const uint32_t d0 = a.v[0] - b.v[0], d1 = a.v[1] - b.v[1], d2 = a.v[2] - b.v[2], d3 = a.v[3] - b.v[3];
+    const uint32_t a0 = d0 + d1, a1 = d0 - d1, a2 = d2 + d3, a3 = d2 - d3;
+    uint32_t p[4] = { a0 + a2, a1 + a3, a0 - a2, a1 - a3 };
+    const bool odd1 = threadIdx.x & 1, odd2 = threadIdx.x & 2;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        uint32_t t = __shfl_xor_sync(mask, p[i], 1);
+        uint32_t q = odd1 ? t - p[i] : p[i] + t;
+        t = __shfl_xor_sync(mask, q, 2);
+        q = odd2 ? t - q : q + t;
+        sum += abs2(q);
+    }
+    int s = (int)((sum & 0xffffu) + (sum >> 16));
+    s += __shfl_xor_sync(mask, s, 1);
+    s += __shfl_xor_sync(mask, s, 2);
+    return (s >> 1) + (__shfl_xor_sync(mask, s, 4) >> 1);
+}
+
 /* ---- the same primitives for the FOUR-lanes-per-block decomposition of the motion search: lane l of a 4-lane group owns
  * rows 2l and 2l+1 of the 8x8 block, a warp works on 8 blocks.  Everything that is uniform inside a group (addresses, mv
  * costs, comparisons, the search's control flow) is then executed once per 4 lanes instead of once per 8, and the first

@@ -4,6 +4,7 @@
  * x86-64 (no FMA) build. */
 #pragma once
 #include "la_device.cuh"
+#include "la_me_generic.cuh"
 
 namespace la {
 
@@ -779,7 +780,7 @@ struct SearchJobDev
     int      sliced;        /* search as cooperative slices of g.rowsPerSlice rows */
 };
 
-struct MV2 { int x, y; };
+/* (struct MV2 lives in la_me_generic.cuh) */
 
 /* The candidate evaluators of the search.  Inlined at each of their ~25 call sites the kernel is 75 KB of SASS, and ncu
  * at full occupancy shows "no instruction" as the largest warp stall (4.2 of 13 stalled warps per issue slot).  Built as
@@ -1506,6 +1507,232 @@ search_kernel(Geom g, const SearchJobDev<P>* __restrict__ jobs, int nstrips, int
      * CTAs of higher-priority streams (pre-lookahead of the next frames, cuTree) get onto the SMs while a long search
      * launch is running instead of behind it */
     if (oneShot) return;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * --hme (x265_param::bEnableHME): hierarchical motion estimation, the two levels the lookahead runs.
+ *
+ *   lowerres_kernel   Lowres::init's second downscale (lowres.cpp:378-388): lowresPlane[0] -> the four 1/16-resolution
+ *                     planes, tiled like the lowres planes, in a buffer of their own geometry (Geom `g4`: w / 2 x h / 2
+ *                     samples, half the margins); extend_border_kernel<P>(g4, ...) then fills their margins
+ *   search_hme_kernel level 0 = the search of search_kernel on those planes over the m_4x4 block grid (slicetype.cpp:
+ *                     4040-4048), level 1 = the lowres search with one more predictor, twice the level-0 vector of the
+ *                     block's parent (:4142-4145).  Per level: search method dia / hex / umh and range (:4094-4096,
+ *                     4170; motion.cpp:842) -- la_me_generic.cuh
+ *
+ * Same strips, tickets and progress chain as search_kernel.  Inside a wavefront step the four 8-lane groups of the warp
+ * run their block's search INDEPENDENTLY (shuffles name the group's lanes only; idle groups skip the step): UMH is
+ * data-dependent sequential control flow per block, not something four blocks can do in lockstep.  The warp reconverges
+ * at the end of every step for the predictor hand-over.  This is a correctness-first path: the default configuration
+ * (no --hme) never launches it.
+ * ------------------------------------------------------------------------------------------ */
+template <typename P>
+__global__ void __launch_bounds__(256) lowerres_kernel(Geom g, Geom g4, const P* __restrict__ planes, P* __restrict__ planes4)
+{
+    /* one thread per sample of the tile-aligned interior: columns past w4 (w4 is a multiple of 4, tiles are 8 wide)
+     * replicate the last sample like the margin the border kernel would have written there */
+    const int wT = (g4.w + 7) & ~7;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)wT * g4.h) return;
+    const int y = (int)(idx / wT), xo = (int)(idx % wT);
+    const int x = min(xo, g4.w - 1);
+    int a[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            a[j][i] = planes[tileOff(g.mx + 2 * x + i, g.my + 2 * y + j, g.tpr)];
+#define LA_F4(p, q, r, s) ((((p + q + 1) >> 1) + ((r + s + 1) >> 1) + 1) >> 1)       /* pixel.cpp:605-628 */
+    const long long o = tileOff(g4.mx + xo, g4.my + y, g4.tpr);
+    planes4[o]                     = (P)LA_F4(a[0][0], a[1][0], a[0][1], a[1][1]);
+    planes4[o + g4.planeSize]      = (P)LA_F4(a[0][1], a[1][1], a[0][2], a[1][2]);
+    planes4[o + 2 * g4.planeSize]  = (P)LA_F4(a[1][0], a[2][0], a[1][1], a[2][1]);
+    planes4[o + 3 * g4.planeSize]  = (P)LA_F4(a[1][1], a[2][1], a[1][2], a[2][2]);
+#undef LA_F4
+}
+
+template <typename P>
+struct SearchJobHme
+{
+    const P* fenc0;         /* tiled plane-0 buffer of this level of the frame being searched */
+    const P* ref0;          /* ... of the reference (level 1: possibly the weighted copy; level 0: never weighted, slicetype.cpp:4083) */
+    int*     mvOut;         /* this level's packed MVs */
+    int*     costOut;
+    int*     flagOut;       /* the job's skip flag, shared by both levels: level 0 clears it, either level sets it */
+    const int* cond;        /* as SearchJobDev::cond */
+    const int* hmeMv;       /* level 1: the level-0 results of the same (frame, list, distance); level 0: NULL */
+    const int* hmeCost;
+    int      bidir;
+    int      pad;
+};
+
+/* candidate evaluators of ONE 8-lane group (see la_me_generic.cuh for the interface).  Loads are clamped to the plane
+ * buffer: the extra predictor of level 1 comes from another block's level-0 search and is followed unchecked by the
+ * reference (it reads whatever lies outside its margins there); vectors inside the margins are not affected */
+template <typename P>
+struct MeCtxG
+{
+    Row<P> fenc;
+    const P* plane0; long long planeSize; int tpr;
+    int X0, Y0, maxX, maxY;
+    const unsigned short* mvcost;   /* centre */
+    int mvpx, mvpy;
+    int r;
+    unsigned mask;
+
+    __device__ __forceinline__ Row<P> row(int pl, int X, int Y) const
+    {
+        return loadRowT(plane0 + pl * planeSize, tpr, min(max(X, 0), maxX), min(max(Y, 0), maxY));
+    }
+    __device__ __forceinline__ int mvc(int qx, int qy) const
+    {
+        return (int)(unsigned short)(__ldg(mvcost + (qx - mvpx)) + __ldg(mvcost + (qy - mvpy)));
+    }
+    __device__ __forceinline__ int sadFpel(int x, int y) const { return groupSumM(sadRow(fenc, row(0, X0 + x, Y0 + y + r)), mask); }
+    __device__ __forceinline__ Row<P> mc(int qx, int qy) const      /* lowres.h:71-96; (qx, qy) is uniform inside the group */
+    {
+        const int hA = (qy & 2) | ((qx & 2) >> 1);
+        const Row<P> A = row(hA, X0 + (qx >> 2), Y0 + (qy >> 2) + r);
+        if (!((qx | qy) & 1)) return A;
+        const int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
+        const int hB = (qy2 & 2) | ((qx2 & 2) >> 1);
+        return avgRow(A, row(hB, X0 + (qx2 >> 2), Y0 + (qy2 >> 2) + r));
+    }
+    __device__ __forceinline__ int qpelSad(int qx, int qy) const { return groupSumM(sadRow(fenc, mc(qx, qy)), mask); }
+    __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return groupSatdHM(toH(fenc), toH(mc(qx, qy)), mask); }
+};
+
+template <typename P>
+__global__ void __launch_bounds__(32, 16)
+search_hme_kernel(Geom g /* geometry of this level */, const SearchJobHme<P>* __restrict__ jobs, int nstrips, int njobs,
+                  const unsigned short* __restrict__ mvcost, int* ticketCounter, int* progress, unsigned long long* executed,
+                  int level, int method, int merange)
+{
+    const int STRIP_ROWS = 4;
+    const int lane = threadIdx.x;
+    const int grp = lane >> 3, r = lane & 7;
+    const int bw = g.bw, bh = g.bh;
+    MeCtxG<P> m;
+    m.mvcost = mvcost; m.r = r; m.mask = 0xffu << (grp * 8);
+    m.planeSize = g.planeSize; m.tpr = g.tpr;
+    m.maxX = g.tpr * 8 - 16; m.maxY = g.planeLines - 1;
+    for (;;)
+    {
+        int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(ticketCounter, 1);
+        ticket = __shfl_sync(LA_FULL, ticket, 0);
+        if (ticket >= nstrips * njobs) return;
+        const int strip = ticket / njobs, job = ticket % njobs;
+        const SearchJobHme<P> J = jobs[job];
+        if (J.cond && __ldcg(J.cond) == 0) continue;
+        if (strip == 0 && lane == 0)
+        {
+            if (level == 0) atomicExch(J.flagOut, 0);
+            else atomicAdd(executed, 1ull);
+        }
+        const int rowsInStrip = min(STRIP_ROWS, bh - strip * STRIP_ROWS);
+        const bool rowOk = grp < rowsInStrip;
+        const int cuY = rowOk ? bh - 1 - strip * STRIP_ROWS - grp : 0;
+        const bool lastRow = cuY == bh - 1;         /* no cooperative slices with --hme (refused at create) */
+        const int steps = bw + 2 * (rowsInStrip - 1);
+        int* myProgress = progress + job * nstrips + strip;
+        const int* belowProgress = myProgress - 1;
+        const int* belowRow = J.mvOut + min(cuY + 1, bh - 1) * bw;
+        m.plane0 = J.ref0;
+        int h0 = 0, h1 = 0, h2 = 0;
+        int seen = 0;
+        bool flagSet = false;
+
+        for (int s = 0; s < steps; s++)
+        {
+            const int kRaw = s - 2 * grp;
+            const bool act = rowOk && kRaw >= 0 && kRaw < bw;
+            const int k = min(max(kRaw, 0), bw - 1);
+            const int cuX = bw - 1 - k;
+            const int cu = cuX + cuY * bw;
+            /* reverse-order MV predictors (slicetype.cpp:4131-4141): right, below, below-left, below-right */
+            int cand[5]; bool valid[5];
+            valid[0] = act && cuX < bw - 1;
+            valid[1] = act && !lastRow; valid[2] = act && !lastRow && cuX > 0; valid[3] = act && !lastRow && cuX < bw - 1;
+            cand[0] = h0;
+            cand[2] = __shfl_up_sync(LA_FULL, h0, 8);
+            cand[1] = __shfl_up_sync(LA_FULL, h1, 8);
+            cand[3] = __shfl_up_sync(LA_FULL, h2, 8);
+            if (strip > 0 && s < bw)
+            {
+                const int need = min(bw, s + 2);
+                if (seen < need)
+                {
+                    if (lane == 0)
+                        while ((seen = ldRelaxed(belowProgress)) < need) __nanosleep(400);
+                    seen = __shfl_sync(LA_FULL, seen, 0);
+                }
+                if (grp == 0)
+                {
+                    cand[1] = __ldcg(belowRow + cuX);
+                    cand[2] = __ldcg(belowRow + max(cuX - 1, 0));
+                    cand[3] = __ldcg(belowRow + min(cuX + 1, bw - 1));
+                }
+            }
+            valid[4] = false; cand[4] = 0;
+            if (act && J.hmeMv)
+            {
+                /* the level-0 block this block is read from, exactly as indexed at slicetype.cpp:4088 */
+                const int cu4 = (cuX / 2) + (cuY / 2) * bw / 2;
+                if (__ldg(J.hmeCost + cu4) > 0)
+                {
+                    const MV2 v = unpackMv(__ldg(J.hmeMv + cu4));
+                    const MV2 v2 = { v.x * 2, v.y * 2 };
+                    cand[4] = packMv(v2); valid[4] = true;
+                }
+            }
+            int packed = 0;
+            if (act)
+            {   /* from here to the end of the branch only this group's lanes take part */
+                m.X0 = g.mx + 8 * cuX; m.Y0 = g.my + 8 * cuY;
+                m.fenc = loadRowAligned(J.fenc0, g.tpr, m.X0, m.Y0 + r);
+                const MV2 mvmin = { -cuX * 8 - 8, -cuY * 8 - 8 };
+                const MV2 mvmax = { (bw - cuX - 1) * 8 + 8, (bh - cuY - 1) * 8 + 8 };
+                MV2 mvp = { 0, 0 };
+                int skipCost = 0x7fffffff, mvpcost = LA_COST_MAX;
+#pragma unroll 1
+                for (int i = 0; i < 5; i++)
+                {
+                    const int ci = i == 0 ? cand[0] : i == 1 ? cand[1] : i == 2 ? cand[2] : i == 3 ? cand[3] : cand[4];
+                    const bool vi = i == 0 ? valid[0] : i == 1 ? valid[1] : i == 2 ? valid[2] : i == 3 ? valid[3] : valid[4];
+                    if (!vi) continue;
+                    const MV2 c = unpackMv(ci);
+                    const int cost = m.qpelSatd(c.x, c.y);
+                    if (cost < mvpcost) { mvpcost = cost; mvp = c; }
+                    if (!(mvp.x | mvp.y) && J.bidir)
+                        skipCost = cost;
+                }
+                MV2 best;
+                int fencCost = motionEstimateG(m, mvmin, mvmax, mvp, merange, method, best);
+                bool skipped = false;
+                if (skipCost < 64 && skipCost < fencCost && J.bidir)
+                {
+                    fencCost = skipCost;
+                    best.x = best.y = 0;
+                    skipped = true;
+                }
+                packed = packMv(best);
+                if (r == 0)
+                {
+                    if (skipped && !flagSet) { atomicOr(J.flagOut, 1); flagSet = true; }
+                    __stcg(J.mvOut + cu, packed);
+                    J.costOut[cu] = fencCost;
+                    if (grp == rowsInStrip - 1)
+                        stRelease(myProgress, k + 1);
+                }
+            }
+            __syncwarp();
+            /* every group shifts at every step, idle or not: the row above reads (h0, h1, h2) as "columns cuX-1, cuX, cuX+1 of
+             * the row below", which keeps sliding for two steps after that row has finished */
+            h2 = h1; h1 = h0; h0 = packed;
+        }
+        __syncwarp();
     }
 }
 

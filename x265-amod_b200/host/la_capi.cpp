@@ -25,6 +25,7 @@ void x265la_param_default(x265la_param* q)
     q->extraSlots = p.extraSlots; q->speculate = p.speculate; q->asyncDepth = p.asyncDepth;
     q->pendingMax = p.pendingMax; q->batchMin = p.batchMin; q->gopLookahead = p.gopLookahead; q->radl = p.radl;
     q->bFrameBias = p.bFrameBias; q->bIntraRefresh = p.bIntraRefresh; q->lookaheadSlices = p.lookaheadSlices;
+    for (int i = 0; i < 2; i++) { q->hmeSearchMethod[i] = p.hmeSearchMethod[i]; q->hmeRange[i] = p.hmeRange[i]; }
 }
 
 void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
@@ -50,6 +51,8 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
     p.csvLogLevel = q->csvLogLevel; p.numRowsPerSlice = q->numRowsPerSlice;
     p.bEnableFades = q->bEnableFades; p.bEnableTemporalSubLayers = q->bEnableTemporalSubLayers;
     p.bHistBasedSceneCut = q->bHistBasedSceneCut;
+    p.bEnableHME = q->bEnableHME && q->sourceHeight >= 540;      /* encoder.cpp:4400-4407 */
+    for (int i = 0; i < 2; i++) { p.hmeSearchMethod[i] = q->hmeSearchMethod[i]; p.hmeRange[i] = q->hmeRange[i]; }
     if (p.radl && p.bOpenGOP) p.radl = 0;      /* encoder.cpp:4361-4365 */
     if (p.radl > p.bframes) p.radl = p.bframes;
     /* the adjustments Encoder::configure makes before the Lookahead sees the params
@@ -193,6 +196,9 @@ int x265la_frame_fade(void*, void* frame, int32_t* bIsFadeEnd, double* frameVari
 
 int x265la_frame_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t* mvXY, int32_t* mvCosts)
 { return ((Lookahead*)la)->fetchMvs((Frame*)frame, list, dist, mvXY, mvCosts) ? 1 : 0; }
+
+int x265la_frame_hme_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t* mvXY, int32_t* mvCosts)
+{ return ((Lookahead*)la)->fetchHmeMvs((Frame*)frame, list, dist, mvXY, mvCosts) ? 1 : 0; }
 
 int x265la_frame_costs(void* la, void* frame, int32_t d0, int32_t d1, uint16_t* lowresCosts, int32_t* rowSatds)
 { return ((Lookahead*)la)->fetchCosts((Frame*)frame, d0, d1, lowresCosts, rowSatds) ? 1 : 0; }

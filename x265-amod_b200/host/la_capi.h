@@ -36,6 +36,9 @@ typedef struct
     int32_t bEnableFades;            /* x265_param::bEnableFades (--fades) */
     int32_t bEnableTemporalSubLayers;/* x265_param::bEnableTemporalSubLayers (--temporal-layers): 0-2 */
     int32_t bHistBasedSceneCut;      /* x265_param::bHistBasedSceneCut (--hist-scenecut), 8-bit only */
+    int32_t bEnableHME;              /* x265_param::bEnableHME (--hme); like the encoder, ignored below 540 lines (encoder.cpp:4400-4407) */
+    int32_t hmeSearchMethod[2];      /* x265_param::hmeSearchMethod[0..1]: dia (0), hex (1) or umh (2) */
+    int32_t hmeRange[2];             /* x265_param::hmeRange[0..1] */
 } x265la_param;
 
 typedef struct
@@ -80,6 +83,8 @@ int   x265la_frame_scalars(void* la, void* frame, int64_t* costEst /* nb*nb */, 
                            int32_t* intraMbs /* nb */, int32_t* rowSatdsValid /* nb*nb */,
                            uint64_t* wp_ssd /* 3 */, uint64_t* wp_sum /* 3 */, double* weightedCostDelta /* nb */);
 int   x265la_frame_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t* mvXY, int32_t* mvCosts);  /* 1 ok, 0 unsearched */
+/* --hme: the level-0 vectors / costs (Lowres::lowerResMvs / lowerResMvCosts) of a published search; 1 ok, 0 none */
+int   x265la_frame_hme_mvs(void* la, void* frame, int32_t list, int32_t dist, int32_t* mvXY, int32_t* mvCosts);
 int   x265la_frame_costs(void* la, void* frame, int32_t d0, int32_t d1, uint16_t* lowresCosts, int32_t* rowSatds);
 int   x265la_frame_fetch(void* la, void* frame, const x265cu_frame_out* out);
 /* The host mirror of a decided frame in one asynchronous request (x265cu_mirror_enqueue): every destination is a host array in

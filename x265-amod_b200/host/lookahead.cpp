@@ -58,6 +58,7 @@ void lookaheadParamDefault(LookaheadParam* p)
     p->rc.aqMode = 2; p->rc.aqStrength = 1.0; p->rc.cuTree = 1; p->rc.qCompress = 0.6; p->rc.qgSize = 32;
     p->rc.rateControlMode = 2 /* X265_RC_CRF */;
     p->extraSlots = 8; p->speculate = 1; p->asyncDepth = 0; p->pendingMax = 8;
+    p->hmeSearchMethod[0] = 1; p->hmeSearchMethod[1] = 2; p->hmeRange[0] = 16; p->hmeRange[1] = 32;      /* param.cpp:226-230 */
 }
 
 Lookahead::Lookahead(const LookaheadParam& param)
@@ -146,6 +147,19 @@ bool Lookahead::create()
     if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
     if (p.bHistBasedSceneCut && p.internalBitDepth != 8) { fail("--hist-scenecut is 8-bit only (the reference indexes 256 bins with the sample value)"); return false; }
     if (p.bEnableTemporalSubLayers > 2) { fail("more than two temporal layers are not supported by the GPU lookahead"); return false; }
+    if (p.bEnableHME && rowsPerSlice > 0)
+    {
+        /* the reference cuts the two levels into slices at different rows (slicetype.cpp:3942-3968): a slice's lowres search
+         * reads level-0 vectors another worker may not have written yet (uninitialised memory; it crashes the reference here) */
+        fail("--hme with active lookahead slices is undefined in the reference (its two levels race); use --lookahead-slices 0");
+        return false;
+    }
+    if (p.bEnableHME)
+        for (int i = 0; i < 2; i++)
+        {
+            if (p.hmeSearchMethod[i] < 0 || p.hmeSearchMethod[i] > 2) { fail("--hme-search: only dia, hex and umh are supported for levels 0 and 1 by the GPU lookahead"); return false; }
+            if (p.hmeRange[i] < 4 || p.hmeRange[i] > 256) { fail("--hme-range of levels 0 and 1 must be 4..256"); return false; }
+        }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
     if (p.lookaheadDepth && p.lookaheadDepth <= p.bframes) { fail("rc-lookahead must exceed bframes"); return false; }
     if (p.lookaheadDepth > LOOKAHEAD_MAX) { fail("rc-lookahead too large"); return false; }
@@ -162,6 +176,8 @@ bool Lookahead::create()
     cfg.qg_size = p.rc.qgSize; cfg.aq_mode = p.rc.aqMode; cfg.aq_strength = p.rc.aqStrength;
     cfg.need_aq = m_bAdaptiveQuant; cfg.need_wp_stats = p.bEnableWeightedPred || p.bEnableWeightedBiPred;
     cfg.fade_stats = p.bEnableFades; cfg.hist_stats = p.bHistBasedSceneCut;
+    cfg.hme = p.bEnableHME;
+    for (int i = 0; i < 2; i++) { cfg.hme_search[i] = p.hmeSearchMethod[i]; cfg.hme_range[i] = p.hmeRange[i]; }
     cfg.lambda = lookaheadLambda(p.internalBitDepth);
     cfg.mvcost = &m_mvcost[0]; cfg.mvcost_half = half;
     cfg.device = p.device;
@@ -2015,6 +2031,13 @@ bool Lookahead::fetchMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t* m
         return false;
     }
     return check(x265cu_fetch_mvs(m_ctx, f->m_lowres.slot, store, mvXY, mvCosts), "x265cu_fetch_mvs");
+}
+
+bool Lookahead::fetchHmeMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t* mvCosts)
+{
+    const int store = f->m_lowres.mvStore[list][dist];
+    if (store < 0 || !m_param.bEnableHME) return false;
+    return check(x265cu_fetch_hme_mvs(m_ctx, f->m_lowres.slot, store, mvXY, mvCosts), "x265cu_fetch_hme_mvs");
 }
 
 bool Lookahead::fetchCosts(Frame* f, int d0, int d1, uint16_t* lowresCosts, int32_t* rowSatds)

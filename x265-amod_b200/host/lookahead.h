@@ -50,6 +50,9 @@ struct LookaheadParam
                                        compCostBref, slicetype.cpp:1755-1799); > 2 is refused */
     int bHistBasedSceneCut;         /* --hist-scenecut (8-bit only): scene cuts from per-segment histogram differences instead of
                                        the cost-based test (slicetype.cpp:3057-3216) */
+    int bEnableHME;      /* --hme: hierarchical motion estimation, levels 0 (1/16 resolution) and 1 (lowres) of the lookahead's searches
+                            (slicetype.cpp:4040-4048, 4083-4183); level 2 is the main encoder's */
+    int hmeSearchMethod[2], hmeRange[2];    /* per level: X265_DIA/HEX/UMH_SEARCH (0 / 1 / 2; star, sea and full are refused) and range */
     int bEnableFades;    /* --fades: mark the frame that ends a fade-in and code it as a keyframe (slicetype.cpp:1861-1906, 1972) */
     int lookaheadSlices;
     int maxNumReferences;
@@ -179,6 +182,8 @@ public:
 
     /* host mirrors of device-resident Lowres arrays, in the reference's layout */
     bool    fetchMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t* mvCosts);  /* false + x=0x7FFF if unsearched */
+    /* --hme: Lowres::lowerResMvs / lowerResMvCosts[list][dist] (the level-0 search behind a published lowres search) */
+    bool fetchHmeMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t* mvCosts);
     bool    fetchCosts(Frame* f, int d0, int d1, uint16_t* lowresCosts, int32_t* rowSatds);
     bool    fetchFrame(Frame* f, const x265cu_frame_out* out);
     bool    mirror(Frame* f, const x265cu_mirror_request* req, int64_t* ticket);   /* asynchronous, x265cu_mirror_enqueue */
