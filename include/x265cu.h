@@ -46,7 +46,8 @@ typedef struct
     int32_t max_slots;          /* frame slots resident in HBM */
     int32_t qg_size;            /* x265_param::rc.qgSize: 8, 16, 32 or 64.  8 = AQ on 8x8 full-res blocks: the qp-offset arrays
                                    hold ncu_full = 4 * ncu entries, addressed like the reference (lowres.h:98-106) */
-    int32_t aq_mode;            /* x265_param::rc.aqMode 0..3 */
+    int32_t aq_mode;            /* x265_param::rc.aqMode 0..5 (4 / 5 = edge: Gaussian + gradient edge map of the luma, slicetype.cpp:98-258;
+                                   not together with fade_stats) */
     double  aq_strength;        /* x265_param::rc.aqStrength */
     int32_t need_aq;            /* Lookahead::m_bAdaptiveQuant (slicetype.cpp:1013-1017) */
     int32_t need_wp_stats;      /* bEnableWeightedPred || bEnableWeightedBiPred */

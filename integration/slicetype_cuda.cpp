@@ -125,7 +125,8 @@ bool cudaLookaheadCreate(Lookahead& self)
     const char* why = NULL;
     if (p->bEnableHME && (p->hmeSearchMethod[0] > X265_UMH_SEARCH || p->hmeSearchMethod[1] > X265_UMH_SEARCH)) why = "--hme-search star / sea / full at levels 0 and 1";
     else if (p->bHistBasedSceneCut && X265_DEPTH != 8) why = "--hist-scenecut at high bit depth";
-    else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED) why = "--aq-mode 4/5";
+    else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED && p->recursionSkipMode == EDGE_BASED_RSKIP) why = "--aq-mode 4/5 with --rskip 2 (the encoder reads the lookahead's full-resolution edge picture)";
+    else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED && p->bEnableFades) why = "--aq-mode 4/5 with --fades";
     else if (p->rc.hevcAq) why = "--hevc-aq";
     else if (p->bAQMotion) why = "--aq-motion";
     else if (p->bEnableTemporalSubLayers > 2) why = "--temporal-layers > 2";

@@ -226,7 +226,69 @@ static uint32_t block_energy(const or_pixel* p, int stride, int W, int H, int bx
     return sqr - (uint32_t)(((uint64_t)sum * sum) >> shift);
 }
 
-/* encoder/slicetype.cpp:452-713, qg-size > 8 */
+/* aq-mode 4 / 5: edgeFilter + computeEdge (encoder/slicetype.cpp:98-223) over the luma plane.  edge / theta are W x H (the
+ * reference's buffers are zero outside the picture; callers treat anything outside as 0).  Gaussian 5x5 (integer, / 159) inside a
+ * 2-sample border, the border keeps the source; Sobel-like gradients on that inside a 1-sample border: edge = white (the
+ * largest sample value) where sqrtf(gH^2 + gV^2) >= EDGE_THRESHOLD else 0, the border keeps the SOURCE sample; theta = the
+ * gradient angle in whole degrees 0..180, 0 on the border. */
+static void edge_filter(const or_pixel* y, int strideY, int W, int H, or_pixel* edge, or_pixel* theta)
+{
+    or_pixel* gauss = (or_pixel*)malloc(sizeof(or_pixel) * (size_t)W * H);
+    for (int r = 0; r < H; r++)
+        for (int c = 0; c < W; c++)
+        {
+            const or_pixel* s = y + (int64_t)r * strideY + c;
+            int v = s[0];
+            if (r >= 2 && c >= 2 && r < H - 2 && c < W - 2)
+            {
+                static const int k[5][5] = { {2, 4, 5, 4, 2}, {4, 9, 12, 9, 4}, {5, 12, 15, 12, 5}, {4, 9, 12, 9, 4}, {2, 4, 5, 4, 2} };
+                int acc = 0;
+                for (int j = -2; j <= 2; j++)
+                    for (int i = -2; i <= 2; i++)
+                        acc += k[j + 2][i + 2] * s[(int64_t)j * strideY + i];
+                v = (or_pixel)(acc / 159);
+            }
+            gauss[(size_t)r * W + c] = (or_pixel)v;
+            edge[(size_t)r * W + c] = s[0];
+            theta[(size_t)r * W + c] = 0;
+        }
+    const float threshold = (float)OR_MAXV;      /* EDGE_THRESHOLD, slicetype.h:64-69 */
+    for (int r = 1; r < H - 1; r++)
+        for (int c = 1; c < W - 1; c++)
+        {
+            const or_pixel* p = gauss + (size_t)r * W + c;
+            const float gH = (float)(-3 * p[-W - 1] + 3 * p[-W + 1] - 10 * p[-1] + 10 * p[1] - 3 * p[W - 1] + 3 * p[W + 1]);
+            const float gV = (float)(-3 * p[-W - 1] - 10 * p[-W] - 3 * p[-W + 1] + 3 * p[W - 1] + 10 * p[W] + 3 * p[W + 1]);
+            const float mag = sqrtf(gH * gH + gV * gV);
+            const float radians = (float)atan2(gV, gH);
+            float th = (float)((radians * 180) / 3.14159265);        /* PI, slicetype.h:70 */
+            if (th < 0) th = 180 + th;
+            theta[(size_t)r * W + c] = (or_pixel)th;
+            edge[(size_t)r * W + c] = (or_pixel)(mag >= threshold ? OR_MAXV : 0);
+        }
+    free(gauss);
+}
+
+/* LookaheadTLD::edgeDensityCu (slicetype.cpp:236-258): variance of the edge image's block and the block's mean angle; like
+ * every acEnergyVar call it adds the block's sum / sum of squares to the weightp statistics of plane 0 (:54-55) */
+static uint32_t edge_density(const or_pixel* edge, const or_pixel* theta, int W, int H, int bx, int by, int size, int shift,
+                             uint32_t* avgAngle, uint64_t* wpSum, uint64_t* wpSsd)
+{
+    uint32_t sum = 0, sqr = 0, ang = 0;
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++)
+        {
+            if (bx + x >= W || by + y >= H) continue;       /* the reference's buffers are zeroed outside the picture (:170-172) */
+            const uint32_t v = edge[(size_t)(by + y) * W + bx + x];
+            sum += v; sqr += v * v;
+            ang += theta[(size_t)(by + y) * W + bx + x];
+        }
+    *avgAngle = ang / (uint32_t)(size * size);
+    *wpSum += sum; *wpSsd += sqr;
+    return sqr - (uint32_t)(((uint64_t)sum * sum) >> shift);
+}
+
+/* encoder/slicetype.cpp:452-713 */
 void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v,
                  int strideC, int aqMode, double aqStrength, int bWeightP,
                  double* qpAqOffset, double* qpCuTreeOffset, int32_t* invQscaleFactor,
@@ -242,6 +304,15 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
     for (int i = 0; i < 3; i++) wp_ssd[i] = wp_sum[i] = 0;
     const int visited = ((W + incr - 1) / incr) * ((H + incr - 1) / incr);
     uint32_t* energy = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(visited > blockCount ? visited : blockCount));
+    const int edgeAq = (aqMode == 4 || aqMode == 5) && aqStrength != 0;
+    or_pixel *edge = NULL, *theta = NULL;
+    uint8_t* inclined = NULL;
+    if (edgeAq)
+    {
+        edge = (or_pixel*)malloc(sizeof(or_pixel) * (size_t)W * H); theta = (or_pixel*)malloc(sizeof(or_pixel) * (size_t)W * H);
+        inclined = (uint8_t*)calloc((size_t)(visited > blockCount ? visited : blockCount), 1);
+        edge_filter(y, strideY, W, H, edge, theta);
+    }
     int n = 0;
     for (int by = 0; by < H; by += incr)
         for (int bx = 0; bx < W; bx += incr, n++)
@@ -252,8 +323,20 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
                 e += block_energy(u, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, incr / 2, qg8 ? 4 : 6, &wp_sum[1], &wp_ssd[1]);
                 e += block_energy(v, strideC, (W + 1) >> 1, (H + 1) >> 1, bx >> 1, by >> 1, incr / 2, qg8 ? 4 : 6, &wp_sum[2], &wp_ssd[2]);
             }
-            energy[n] = e;
             if (blockEnergy) blockEnergy[n] = e;
+            if (edgeAq)
+            {
+                /* :568-585: a block with edges takes its edge density instead of its energy, and is marked when the mean
+                 * gradient angle lies within 15 degrees of a diagonal (EDGE_INCLINATION 45) */
+                uint32_t avgAngle = 0;
+                const uint32_t density = edge_density(edge, theta, W, H, bx, by, incr, qg8 ? 6 : 8, &avgAngle, &wp_sum[0], &wp_ssd[0]);
+                if (density)
+                {
+                    e = density;
+                    inclined[n] = (avgAngle >= 30 && avgAngle <= 60) || (avgAngle >= 120 && avgAngle <= 150);
+                }
+            }
+            energy[n] = e;
         }
 
     if (aqMode == 0 || aqStrength == 0)
@@ -264,7 +347,7 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
     else
     {
         double avg_adj_pow2 = 0, avg_adj = 0, qp_adj = 0, bias_strength = 0, strength = 0;
-        if (aqMode == 2 || aqMode == 3)
+        if (aqMode == 2 || aqMode == 3 || aqMode == 4 || aqMode == 5)
         {
             double bit_depth_correction = 1.f / (1 << (2 * (OR_DEPTH - 8)));
             for (int i = 0; i < visited; i++)
@@ -294,6 +377,24 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
                 qp_adj = qpCuTreeOffset[i];
                 qp_adj = strength * (qp_adj - avg_adj);
             }
+            else if (aqMode == 4)
+            {
+                qp_adj = qpCuTreeOffset[i];
+                if (inclined[i] && (qp_adj - avg_adj > 0))
+                    qp_adj = ((strength + 0.5 /* AQ_EDGE_BIAS */) * (qp_adj - avg_adj));
+                else
+                    qp_adj = strength * (qp_adj - avg_adj);
+            }
+            else if (aqMode == 5)
+            {
+                qp_adj = qpCuTreeOffset[i];
+                double dark_bias = bias_strength * (1.f - modeTwoConst / (qp_adj * qp_adj)) / 10.f;
+                if (inclined[i] && (qp_adj - avg_adj > 0))
+                    qp_adj = ((strength + 0.5) * (qp_adj - avg_adj));
+                else
+                    qp_adj = strength * (qp_adj - avg_adj);
+                qp_adj += dark_bias;
+            }
             else
             {
                 uint32_t e = energy[i] > 1 ? energy[i] : 1;
@@ -314,7 +415,7 @@ void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixe
             wp_ssd[i] = ssd - (sum * sum + (uint64_t)(wd[i] * ht[i]) / 2) / (uint64_t)(wd[i] * ht[i]);
         }
     }
-    free(energy);
+    free(energy); free(edge); free(theta); free(inclined);
 }
 
 /* --fades: the tail of calcAdaptiveQuantFrame (encoder/slicetype.cpp:697-712).  A second acEnergyCu pass over the picture

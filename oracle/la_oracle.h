@@ -70,7 +70,7 @@ int  or_satd8x8(const or_pixel* a, int sa, const or_pixel* b, int sb);  /* pixel
  * what PicYuv::copyFromPicture's padding (picyuv.cpp:261-285,480-512) amounts to. */
 void or_lowres_init(const or_geom* g, const or_pixel* srcY, int srcStride, or_pixel* buf);
 
-/* calcAdaptiveQuantFrame, aq-mode 0..3 (encoder/slicetype.cpp:452-713); g->qg8 selects 8x8 blocks, in which case the
+/* calcAdaptiveQuantFrame, aq-mode 0..5 (encoder/slicetype.cpp:452-713; modes 4 / 5 with edgeFilter / edgeDensityCu, :98-258); g->qg8 selects 8x8 blocks, in which case the
  * three output arrays hold 4 * ncu entries (+ a row of slack for the running index) and must come in zeroed.
  * Chroma may be NULL (treated as 4:0:0). */
 void or_aq_frame(const or_geom* g, const or_pixel* y, int strideY, const or_pixel* u, const or_pixel* v,

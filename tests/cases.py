@@ -93,6 +93,10 @@ CASES = [
     ("hme_hexhex10", 10, 960, 540, 14, dict(cuts=(6,)), dict(bframes=2, lookaheadDepth=6, hme=1, hmeSearch0=1, hmeSearch1=1, hmeRange0=12, hmeRange1=24)),
     ("hme_umhdia_pool_fade", 8, 1024, 576, 20, dict(cuts=(), fades=[(5, 8, 0.3)]),
      dict(bframes=4, lookaheadDepth=10, hme=1, hmeSearch0=2, hmeSearch1=0, hmeRange0=20, hmeRange1=16, poolThreads=16, weightb=1)),
+    # aq-mode 4 / 5 (edge): Gaussian + gradient edge map of the full-res luma, per-block edge density and mean gradient angle
+    ("aq4_edge", 8, 320, 192, 30, dict(cuts=(15,)), dict(bframes=3, lookaheadDepth=10, aqMode=4)),
+    ("aq5_edge10_ragged", 10, 328, 184, 30, dict(cuts=(15,)), dict(bframes=3, lookaheadDepth=10, aqMode=5, aqStrength=1.3)),
+    ("aq4_qg8_sd", 8, 640, 360, 24, dict(cuts=(11,)), dict(bframes=4, lookaheadDepth=12, aqMode=4, qgSize=8, poolThreads=16)),
     # short enough to commit as a golden fixture
     ("hme_golden", 8, 960, 544, 8, dict(cuts=(4,)), dict(bframes=2, lookaheadDepth=5, hme=1)),
     ("vbv_nocutree", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),

@@ -71,6 +71,8 @@ CLI_CASES = [
      ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--hist-scenecut"]),
     # --hme: the lookahead's level-0 / level-1 searches on the GPU (hex, umh), the main encoder's level 2 fed by the mirrored lowres MVs
     ("hme_544p", 8, 960, 544, 24, dict(cuts=(11,)), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--hme"]),
+    # aq-mode 4 (edge): the qp offsets the frame encoder quantises with come from the GPU's edge map
+    ("aq4_edge", 8, 640, 360, 40, dict(cuts=(19,)), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--aq-mode", "4"]),
     ("temporal_layers_2", 8, 640, 360, 50, dict(cuts=(23,)),
      ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--bframes", "7", "--temporal-layers", "2"]),
 ]

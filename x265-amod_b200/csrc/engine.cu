@@ -55,7 +55,7 @@ namespace {
 
 struct SlotLayout
 {
-    size_t srcY, srcU, srcV, planes, intraCost, intraMode, invQ, invQ8, qpAq, qpCuTree, propagate, energy, aqSums,
+    size_t srcY, srcU, srcV, planes, intraCost, intraMode, invQ, invQ8, qpAq, qpCuTree, propagate, energy, edge, aqSums,
            lowresCosts00, rowSatds00, stats, mvStores, costStores, planes4, mvStores4, total;
     size_t mvStoreStride, costStoreStride, costRowOff, costResOff, mvStore4Stride;
 };
@@ -805,20 +805,24 @@ int uploadT(x265cu_ctx* c, int slot, const void* y, const void* u, const void* v
     }
     if (c->cfg.need_aq)
     {
-        const bool twoPass = (c->cfg.aq_mode == 2 || c->cfg.aq_mode == 3) && c->cfg.aq_strength != 0;
-        Prof pr(c, X265CU_K_AQ, 1 + 2 * twoPass + 2 * qg8, ps);
+        const bool twoPass = c->cfg.aq_mode >= 2 && c->cfg.aq_strength != 0;
+        const bool edgeAq = c->cfg.aq_mode > 3 && c->cfg.aq_strength != 0;
+        unsigned* edge = edgeAq ? slotPtr<unsigned>(c, slot, L.edge) : NULL;
+        Prof pr(c, X265CU_K_AQ, 1 + 2 * twoPass + 2 * qg8 + edgeAq, ps);
         double* qpCuTree = slotPtr<double>(c, slot, L.qpCuTree);
         double* sums = slotPtr<double>(c, slot, L.aqSums);
         if (qg8)
             aq_energy8_kernel<P><<<(g.aqW * g.aqH + 31) / 32, 256, 0, ps>>>(g, dY, chroma ? dU : NULL, chroma ? dV : NULL, energy, stats);
+        if (edgeAq)
+            aq_edge_kernel<P><<<((g.picW + 15) >> 4) * ((g.picH + 15) >> 4), 256, 0, ps>>>(g, dY, edge, stats);
         if (twoPass)
         {
-            aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, ps>>>(g, energy, qpCuTree);
+            aq_pow_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, ps>>>(g, energy, edge, qpCuTree);
             aq_mean_kernel<<<1, 32, 0, ps>>>(g, qpCuTree, sums);
         }
         aq_finish_kernel<<<LA_AQ_CTAS, LA_AQ_THREADS, 0, ps>>>(g, energy, c->cfg.aq_mode, c->cfg.aq_strength, c->cfg.need_wp_stats,
                                                                       c->cfg.fade_stats, sums, slotPtr<double>(c, slot, L.qpAq), qpCuTree,
-                                                                      slotPtr<int>(c, slot, L.invQ), stats);
+                                                                      slotPtr<int>(c, slot, L.invQ), stats, edge);
         if (qg8)
             aq_invq8x8_kernel<<<(g.ncu + 255) / 256, 256, 0, ps>>>(g, slotPtr<int>(c, slot, L.invQ), invQ);
     }
@@ -1399,6 +1403,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
             if (cfg->hme_search[i] < 0 || cfg->hme_search[i] > 2 || cfg->hme_range[i] < 4 || cfg->hme_range[i] > 256) return X265CU_ERR_UNSUPPORTED;
         if (cfg->rows_per_slice > 0 || cfg->max_cu_size < 32 || cfg->width < 64 || cfg->height < 64) return X265CU_ERR_UNSUPPORTED;
     }
+    if (cfg->aq_mode < 0 || cfg->aq_mode > 5 || (cfg->aq_mode > 3 && cfg->fade_stats)) return X265CU_ERR_UNSUPPORTED;
     if (cfg->width < 16 || cfg->height < 16 || cfg->bframes < 0 || cfg->bframes > 16 || cfg->max_slots < 1 || !cfg->mvcost)
         return X265CU_ERR_BAD_ARG;
     int ndev = 0;
@@ -1492,6 +1497,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     SECTION(qpCuTree, nAq * 8);
     SECTION(propagate, (size_t)g.ncu * 4);
     SECTION(energy, nAq * 4);
+    SECTION(edge, cfg->aq_mode > 3 ? nAq * 4 : 0);
     SECTION(aqSums, 16);
     SECTION(lowresCosts00, (size_t)g.ncu * 2);
     L.rowSatds00 = o; o += alignUp((size_t)g.bh * 4, 16);

@@ -425,16 +425,116 @@ __global__ void __launch_bounds__(256) aq_energy8_kernel(Geom g, const P* __rest
  *                    2160p frame, on one warp, off the critical path of the search batches;
  *   aq_finish_kernel : the per-block finish, LA_AQ_CTAS CTAs.
  * n = blocks visited (aqW * aqH, the running index); the means divide by g.ncuFull (:569-570). */
+/* aq-mode 4 / 5 (X265_AQ_EDGE / _BIASED): edgeFilter + computeEdge + edgeDensityCu (slicetype.cpp:98-258) in one pass, nothing
+ * kept at full resolution.  One CTA = one 16x16 region of the luma plane = one AQ block (qg-size > 8) or four (qg-size 8):
+ * stage the source with a 3-sample halo, 5x5 Gaussian (integer, / 159; the 2-sample picture border keeps the source) for the
+ * region + 1, Sobel-like gradients of that (the 1-sample picture border keeps the SOURCE in the edge image and angle 0),
+ * then the block sums.  The edge test sqrtf(gH^2 + gV^2) >= EDGE_THRESHOLD is decided in integers (the squares near the
+ * threshold are far below 2^24, so the reference's float arithmetic is exact there); the angle goes through the same
+ * float / double steps as the reference's (atan2 in double, rounded to float, * 180 / PI in double with its truncated PI,
+ * rounded to float, truncated to a sample).  Outside the picture both images are 0 (the reference clears its buffers).
+ * Output per block: the edge density (variance of the edge image, < 2^31) | mean angle within 15 degrees of a diagonal << 31.
+ * Like every acEnergyVar call, the block's sum / sum of squares also goes to the weightp statistics of plane 0 (:54-55). */
+template <typename P>
+__global__ void __launch_bounds__(256) aq_edge_kernel(Geom g, const P* __restrict__ y, unsigned* __restrict__ edgeOut, FrameStatsDev* stats)
+{
+    __shared__ int s_src[22][23];
+    __shared__ int s_g[18][19];
+    __shared__ unsigned s_acc[4][3];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int regW = (g.picW + 15) >> 4;
+    const int rx = blockIdx.x % regW, ry = blockIdx.x / regW;
+    const int X0 = rx * 16, Y0 = ry * 16, W = g.picW, H = g.picH;
+    if (tid < 12) s_acc[tid / 3][tid % 3] = 0;
+    for (int i = tid; i < 22 * 22; i += 256)
+    {
+        const int r = i / 22, c = i % 22;
+        const int R = Y0 - 3 + r, C = X0 - 3 + c;
+        s_src[r][c] = (R >= 0 && C >= 0 && R < H && C < W) ? (int)y[(long long)R * g.srcPitch + C] : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < 18 * 18; i += 256)
+    {
+        const int r = i / 18, c = i % 18;
+        const int R = Y0 - 1 + r, C = X0 - 1 + c;
+        int v = s_src[r + 2][c + 2];
+        if (R >= 2 && C >= 2 && R < H - 2 && C < W - 2)
+        {
+            const int (*s)[23] = (const int (*)[23])&s_src[r][c];      /* rows r .. r + 4 = R - 2 .. R + 2 */
+            const int acc = 2 * s[0][0] + 4 * s[0][1] + 5 * s[0][2] + 4 * s[0][3] + 2 * s[0][4] +
+                            4 * s[1][0] + 9 * s[1][1] + 12 * s[1][2] + 9 * s[1][3] + 4 * s[1][4] +
+                            5 * s[2][0] + 12 * s[2][1] + 15 * s[2][2] + 12 * s[2][3] + 5 * s[2][4] +
+                            4 * s[3][0] + 9 * s[3][1] + 12 * s[3][2] + 9 * s[3][3] + 4 * s[3][4] +
+                            2 * s[4][0] + 4 * s[4][1] + 5 * s[4][2] + 4 * s[4][3] + 2 * s[4][4];
+            v = acc / 159;
+        }
+        s_g[r][c] = v;
+    }
+    __syncthreads();
+    const int R = Y0 + ty, C = X0 + tx;
+    unsigned e = 0, th = 0;
+    if (R < H && C < W)
+    {
+        if (R >= 1 && C >= 1 && R < H - 1 && C < W - 1)
+        {
+            const int (*p)[19] = (const int (*)[19])&s_g[ty][tx];      /* p[1][1] is the sample itself */
+            const int gH = -3 * p[0][0] + 3 * p[0][2] - 10 * p[1][0] + 10 * p[1][2] - 3 * p[2][0] + 3 * p[2][2];
+            const int gV = -3 * p[0][0] - 10 * p[0][1] - 3 * p[0][2] + 3 * p[2][0] + 10 * p[2][1] + 3 * p[2][2];
+            const int maxv = (1 << g.depth) - 1;
+            /* |g| <= 32 * 1023: the sum of squares fits 64 bits trivially; float rounding cannot move it across maxv^2 < 2^24 */
+            e = ((long long)gH * gH + (long long)gV * gV >= (long long)maxv * maxv) ? (unsigned)maxv : 0u;
+            const float radians = (float)atan2((double)gV, (double)gH);
+            float theta = (float)__ddiv_rn(__dmul_rn((double)radians, 180.0), 3.14159265);
+            if (theta < 0) theta = __fadd_rn(180.f, theta);
+            th = (unsigned)(int)theta;
+        }
+        else
+            e = (unsigned)s_src[ty + 3][tx + 3];
+    }
+    const bool qg8 = g.aqBlock == 8;
+    const int lane = tid & 31;
+    /* a warp holds rows 2w and 2w + 1 of the region: one AQ block (16x16), or with 8x8 blocks the left half in lanes with
+     * bit 3 clear and the right half in the others */
+    const unsigned mask = qg8 ? ((lane & 8) ? 0xff00ff00u : 0x00ff00ffu) : 0xffffffffu;
+    const unsigned sSum = __reduce_add_sync(mask, e), sSqr = __reduce_add_sync(mask, e * e), sAng = __reduce_add_sync(mask, th);
+    const int q = qg8 ? ((ty >> 3) * 2 + ((tx >> 3) & 1)) : 0;
+    if ((lane & (qg8 ? 23 : 31)) == 0)
+    {
+        atomicAdd(&s_acc[q][0], sSum); atomicAdd(&s_acc[q][1], sSqr); atomicAdd(&s_acc[q][2], sAng);
+    }
+    __syncthreads();
+    if (tid < (qg8 ? 4 : 1))
+    {
+        const int bx = qg8 ? 2 * rx + (tid & 1) : rx, by = qg8 ? 2 * ry + (tid >> 1) : ry;
+        if (bx < g.aqW && by < g.aqH)
+        {
+            const unsigned sum = s_acc[tid][0], sqr = s_acc[tid][1];
+            const unsigned density = sqr - (unsigned)(((unsigned long long)sum * sum) >> (qg8 ? 6 : 8));
+            const unsigned avgAngle = s_acc[tid][2] / (unsigned)(g.aqBlock * g.aqBlock);
+            const bool inclined = density && ((avgAngle >= 30 && avgAngle <= 60) || (avgAngle >= 120 && avgAngle <= 150));
+            edgeOut[by * g.aqW + bx] = density | (inclined ? 0x80000000u : 0u);
+            atomicAdd(&stats->wp_sum[0], (unsigned long long)sum);
+            atomicAdd(&stats->wp_ssd[0], (unsigned long long)sqr);
+        }
+    }
+}
+
 #define LA_AQ_CTAS 64
 #define LA_AQ_THREADS 256
 
 __global__ void __launch_bounds__(LA_AQ_THREADS) aq_pow_kernel(Geom g, const unsigned* __restrict__ energy,
+                                                               const unsigned* __restrict__ edge /* aq-mode 4 / 5, else NULL */,
                                                                double* __restrict__ qpCuTree)
 {
     const int n = g.aqW * g.aqH;
     const double bdc = (double)(1.f / (1 << (2 * (g.depth - 8))));
     for (int i = blockIdx.x * LA_AQ_THREADS + threadIdx.x; i < n; i += LA_AQ_CTAS * LA_AQ_THREADS)
-        qpCuTree[i] = pow(__dadd_rn(__dmul_rn((double)energy[i], bdc), 1.0), 0.1);
+    {
+        unsigned e = energy[i];
+        /* a block with edges takes its edge density instead of its energy (slicetype.cpp:568-585) */
+        if (edge && (edge[i] & 0x7fffffffu)) e = edge[i] & 0x7fffffffu;
+        qpCuTree[i] = pow(__dadd_rn(__dmul_rn((double)e, bdc), 1.0), 0.1);
+    }
 }
 
 __global__ void __launch_bounds__(32) aq_mean_kernel(Geom g, const double* __restrict__ qpAdj, double* __restrict__ sums)
@@ -466,7 +566,8 @@ __global__ void __launch_bounds__(32) aq_mean_kernel(Geom g, const double* __res
 __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const unsigned* __restrict__ energy, int aqMode,
                                                                   double aqStrength, int bWeightP, int bFades, const double* __restrict__ sums,
                                                                   double* __restrict__ qpAq, double* __restrict__ qpCuTree,
-                                                                  int* __restrict__ invQ, FrameStatsDev* stats)
+                                                                  int* __restrict__ invQ, FrameStatsDev* stats,
+                                                                  const unsigned* __restrict__ edge /* aq-mode 4 / 5, else NULL */)
 {
     const int tid = threadIdx.x, n = g.aqW * g.aqH;
     const bool qg8 = g.aqBlock == 8;
@@ -518,7 +619,7 @@ __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const 
         return;
     }
     double strength, avg_adj = 0, bias_strength = 0;
-    if (aqMode == 2 || aqMode == 3)
+    if (aqMode >= 2)
     {
         const double mean = __ddiv_rn(sums[0], (double)g.ncuFull), mean2 = __ddiv_rn(sums[1], (double)g.ncuFull);
         strength = __dmul_rn(aqStrength, mean);
@@ -538,6 +639,20 @@ __global__ void __launch_bounds__(LA_AQ_THREADS) aq_finish_kernel(Geom g, const 
         }
         else if (aqMode == 2)
             qp_adj = __dmul_rn(strength, __dadd_rn(qpCuTree[i], -avg_adj));
+        else if (aqMode == 4 || aqMode == 5)
+        {
+            /* slicetype.cpp:612-630: blocks whose mean gradient angle is near a diagonal and that lie above the mean get a
+             * steeper slope (AQ_EDGE_BIAS 0.5); mode 5 adds a tenth of mode 3's dark bias */
+            const double q = qpCuTree[i];
+            const double d = __dadd_rn(q, -avg_adj);
+            const bool inclined = (edge[i] >> 31) != 0;
+            qp_adj = (inclined && d > 0) ? __dmul_rn(__dadd_rn(strength, 0.5), d) : __dmul_rn(strength, d);
+            if (aqMode == 5)
+            {
+                const double dark = __ddiv_rn(__dmul_rn(bias_strength, __dadd_rn(1.0, -__ddiv_rn((double)modeTwoConst, __dmul_rn(q, q)))), (double)10.f);
+                qp_adj = __dadd_rn(qp_adj, dark);
+            }
+        }
         else
         {
             const unsigned e = energy[i] > 1 ? energy[i] : 1;

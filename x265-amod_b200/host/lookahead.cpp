@@ -144,7 +144,14 @@ bool Lookahead::create()
     m_dualSlicing = rowsPerSlice > 0 && m_bBatchMotionSearch;
     m_costVariants = m_dualSlicing ? 8 : 2;
     if (p.rc.qgSize != 8 && p.rc.qgSize != 16 && p.rc.qgSize != 32 && p.rc.qgSize != 64) { fail("qg-size must be 8, 16, 32 or 64"); return false; }
-    if (p.rc.aqMode > 3) { fail("aq-mode 4/5 (edge) is not supported by the GPU lookahead"); return false; }
+    if (p.rc.aqMode < 0 || p.rc.aqMode > 5) { fail("aq-mode must be 0..5"); return false; }
+    if (p.rc.aqMode > 3 && p.bEnableFades)
+    {
+        /* the second acEnergyCu pass of --fades adds the luma sums to the weightp statistics once more, but not the edge image's
+         * (slicetype.cpp:54-55, 568-573, 703): the statistics kernels keep one sum per plane */
+        fail("--fades with aq-mode 4/5 (edge) is not supported by the GPU lookahead");
+        return false;
+    }
     if (p.bHistBasedSceneCut && p.internalBitDepth != 8) { fail("--hist-scenecut is 8-bit only (the reference indexes 256 bins with the sample value)"); return false; }
     if (p.bEnableTemporalSubLayers > 2) { fail("more than two temporal layers are not supported by the GPU lookahead"); return false; }
     if (p.bEnableHME && rowsPerSlice > 0)
