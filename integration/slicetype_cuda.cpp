@@ -129,7 +129,6 @@ bool cudaLookaheadCreate(Lookahead& self)
     else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED && p->bEnableFades) why = "--aq-mode 4/5 with --fades";
     else if (p->rc.hevcAq) why = "--hevc-aq";
     else if (p->bAQMotion) why = "--aq-motion";
-    else if (p->bEnableTemporalSubLayers > 2) why = "--temporal-layers > 2";
     else if (p->analysisLoad || p->bAnalysisType == AVC_INFO) why = "--analysis-load";
     else if (p->bEnableFades && p->rc.qgSize == 8) why = "--fades with --qg-size 8";
     else if (p->bDynamicRefine) why = "--dynamic-refine";
@@ -298,6 +297,13 @@ Frame* cudaLookaheadGetDecided(Lookahead& self)
         l.bIsFadeEnd = !!fadeEnd; l.frameVariance = variance;     /* ratecontrol.cpp:1416 reads bIsFadeEnd */
     }
     f->m_reorderedPts = info.reorderedPts;
+    if (p->bEnableTemporalSubLayers > 2)
+    {
+        /* where in which random-access structure the frame sits, and its temporal layer (slicetype.cpp:2133-2320; the DPB
+         * derives the reference picture sets from them) */
+        f->m_gopOffset = info.gopOffset; f->m_tempLayer = (int8_t)info.tempLayer;
+        if (info.gopIdWritten) f->m_gopId = (int8_t)info.gopId;
+    }
 
     std::vector<int64_t> ce(nb * nb), cea(nb * nb);
     std::vector<int32_t> mbs(nb), valid(nb * nb);

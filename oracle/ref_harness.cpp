@@ -122,6 +122,8 @@ struct RefLaFrame
     int32_t bw4, bh4;
     const int32_t*  lowerMvs;       /* 2*nb*ncu4*2 (x,y) */
     const int32_t*  lowerMvCosts;   /* 2*nb*ncu4 */
+    /* --temporal-layers 3..5: Frame::m_gopOffset / m_gopId / m_tempLayer as the decision left them */
+    int32_t gopOffset, gopId, tempLayer, pad1;
 };
 
 } // extern "C"
@@ -185,6 +187,7 @@ void snapshot(Handle* h, Frame* f)
                 }
         s->h.histCheck = ck;
     }
+    s->h.gopOffset = f->m_gopOffset; s->h.gopId = f->m_gopId; s->h.tempLayer = f->m_tempLayer;
     s->h.bw = bw; s->h.bh = bh; s->h.nb = nb;
     s->h.stride = (int)l.lumaStride;
     s->h.planeLines = (int)((l.buffer[1] - l.buffer[0]) / l.lumaStride);

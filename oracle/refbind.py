@@ -42,7 +42,8 @@ class RefLaFrame(C.Structure):
                 ("intraCostForRc", C.c_void_p), ("estRowSatds", C.c_void_p),
                 ("bIsFadeEnd", C.c_int32), ("pad0", C.c_int32), ("frameVariance", C.c_double),
                 ("histVar", C.c_int32 * 3), ("histAvg", C.c_int32 * 3), ("histCheck", C.c_uint64),
-                ("bw4", C.c_int32), ("bh4", C.c_int32), ("lowerMvs", C.c_void_p), ("lowerMvCosts", C.c_void_p)]
+                ("bw4", C.c_int32), ("bh4", C.c_int32), ("lowerMvs", C.c_void_p), ("lowerMvCosts", C.c_void_p),
+                ("gopOffset", C.c_int32), ("gopId", C.c_int32), ("tempLayer", C.c_int32), ("pad1", C.c_int32)]
 
 
 DEFAULTS = dict(fpsNum=30, fpsDenom=1, bframes=4, lookaheadDepth=20, bFrameAdaptive=2, bBPyramid=1,
@@ -189,6 +190,8 @@ class RefLookahead:
                  wp_ssd=np.array(list(f.wp_ssd), np.uint64), wp_sum=np.array(list(f.wp_sum), np.uint64),
                  bIsFadeEnd=f.bIsFadeEnd, frameVariance=f.frameVariance,
                  histVar=list(f.histVar), histAvg=list(f.histAvg), histCheck=int(f.histCheck))
+        if self.cfg.temporalLayers > 2:     # otherwise nothing ever writes them (Frame's constructor leaves m_gopOffset / m_gopId alone)
+            d.update(gopOffset=f.gopOffset, gopId=f.gopId, tempLayer=f.tempLayer)
         if not nb:
             return d
         d["costEst"] = _arr(f.costEst, np.int64, nb * nb).reshape(nb, nb)

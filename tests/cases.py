@@ -61,6 +61,13 @@ CASES = [
     # --temporal-layers 2: B-refs placed recursively over the mini-GOP, their costs pre-computed by compCostBref
     ("temporal2", 8, 320, 192, 60, dict(cuts=(31,), static=True, noise=2), dict(bframes=7, lookaheadDepth=20, temporalLayers=2)),
     ("temporal2_pool", 10, 320, 192, 50, dict(cuts=(24,)), dict(bframes=5, lookaheadDepth=16, temporalLayers=2, poolThreads=16)),
+    # --temporal-layers 3 / 4 / 5: fixed random-access mini-GOPs of 4 / 8 / 16 pictures (Encoder::configure sets bframes 3 / 7 / 15 and
+    # b-adapt 0), coded in hierarchical order; scene cuts and the end of the stream split a mini-GOP into smaller structures
+    ("temporal3", 8, 320, 192, 45, dict(cuts=(14, 30)), dict(bframes=3, lookaheadDepth=12, bFrameAdaptive=0, temporalLayers=3)),
+    ("temporal4_pool", 10, 320, 192, 50, dict(cuts=(21,)), dict(bframes=7, lookaheadDepth=20, bFrameAdaptive=0, temporalLayers=4, poolThreads=16)),
+    ("temporal5_nopyramid_vbv", 8, 320, 192, 60, dict(cuts=(37,), static=True, noise=2),
+     dict(bframes=15, lookaheadDepth=30, bFrameAdaptive=0, temporalLayers=5, bBPyramid=0, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),
+    ("temporal5", 8, 320, 192, 70, dict(cuts=(13, 41, 52)), dict(bframes=15, lookaheadDepth=35, bFrameAdaptive=0, temporalLayers=5)),
     # --radl: leading B pictures in front of the scene-cut IDRs of a closed GOP
     ("radl2", 8, 320, 192, 50, dict(cuts=(14, 31)), dict(bframes=3, lookaheadDepth=12, bOpenGOP=0, radl=2, keyframeMax=60, keyframeMin=4)),
     # slice types forced by the application (IDR, P, B runs, I) in the middle of automatic decisions

@@ -40,10 +40,17 @@ def compare_frames(ref, got, check_planes=False, qp_tol=1e-3, weightp=True, cutr
     # ... and a frame whose type the application forced (Lowres::sliceTypeReq) is analysed as AUTO: when the analysis made it
     # a B frame and slicetypeDecide then imposes P on it (slicetype.cpp:1938), cuTree only ever cleared its first row and
     # the rest is whatever the malloc'ed (lowres.cpp: CHECKED_MALLOC, not zeroed) array held.
-    if cutree and decision_rank and ref["sliceType"] in (1, 2, 3) and ref["poc"] not in skip_propagate and \
+    # ... and with --temporal-layers 3..5 the P that closes a sub-structure of a SPLIT mini-GOP (slicetype.cpp:2084-2090) was a B
+    # frame to the analysis and to cuTree, too
+    split_p = "gopIdTop" in got and got["gopId"] != got["gopIdTop"]
+    if cutree and decision_rank and ref["sliceType"] in (1, 2, 3) and ref["poc"] not in skip_propagate and not split_p and \
             not np.array_equal(ref["propagateCost"], got["propagateCost"]):
         n = int(np.sum(ref["propagateCost"] != got["propagateCost"]))
         bad.append(tag + "propagateCost differs in %d blocks" % n)
+    if "tempLayer" in got and "tempLayer" in ref:       # --temporal-layers 3..5: what the DPB reads of the decision
+        for k in ("tempLayer", "gopOffset") + (("gopId",) if got["gopId"] is not None else ()):
+            if int(ref[k]) != int(got[k]):
+                bad.append(tag + "%s ref=%d got=%d" % (k, ref[k], got[k]))
     if "bIsFadeEnd" in ref and "bIsFadeEnd" in got:
         if int(ref["bIsFadeEnd"]) != int(got["bIsFadeEnd"]):
             bad.append(tag + "bIsFadeEnd ref=%d got=%d" % (ref["bIsFadeEnd"], got["bIsFadeEnd"]))

@@ -75,6 +75,13 @@ CLI_CASES = [
     ("aq4_edge", 8, 640, 360, 40, dict(cuts=(19,)), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--aq-mode", "4"]),
     ("temporal_layers_2", 8, 640, 360, 50, dict(cuts=(23,)),
      ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--bframes", "7", "--temporal-layers", "2"]),
+    # 3 and 5 temporal layers: random-access mini-GOPs of 4 / 16 pictures, split at the scene cuts and at the end of the stream; the DPB
+    # builds its reference picture sets from the positions / layers the GPU lookahead hands back
+    ("temporal_layers_3", 8, 640, 360, 46, dict(cuts=(14, 30)), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--temporal-layers", "3"]),
+    ("temporal_layers_5", 10, 640, 360, 70, dict(cuts=(13, 41, 52)),
+     ["--preset", "medium", "--pools", "16", "--lookahead-slices", "0", "--rc-lookahead", "35", "--temporal-layers", "5"]),
+    # --lookahead-threads: the lookahead gets a pool of its own, whose size selects the reference's batch modes
+    ("lookahead_threads", 8, 640, 360, 50, dict(cuts=(23,)), ["--preset", "medium", "--pools", "8", "--lookahead-threads", "2", "--lookahead-slices", "0"]),
 ]
 
 

@@ -45,7 +45,8 @@ class LaParam(C.Structure):
 class FrameInfo(C.Structure):
     _fields_ = [("poc", C.c_int32), ("sliceType", C.c_int32), ("bScenecut", C.c_int32), ("bKeyframe", C.c_int32),
                 ("bLastMiniGopBFrame", C.c_int32), ("leadingBframes", C.c_int32),
-                ("pts", C.c_int64), ("reorderedPts", C.c_int64), ("satdCost", C.c_int64), ("handle", C.c_void_p)]
+                ("pts", C.c_int64), ("reorderedPts", C.c_int64), ("satdCost", C.c_int64), ("handle", C.c_void_p),
+                ("gopOffset", C.c_int32), ("gopId", C.c_int32), ("tempLayer", C.c_int32), ("gopIdWritten", C.c_int32)]
 
 
 class FrameOut(C.Structure):
@@ -247,6 +248,9 @@ class Lookahead:
         d = dict(poc=info.poc, sliceType=info.sliceType, bScenecut=info.bScenecut, bKeyframe=info.bKeyframe,
                  bLastMiniGopBFrame=info.bLastMiniGopBFrame, leadingBframes=info.leadingBframes,
                  bw=g.bw, bh=bh, nb=nb, stride=g.stride, planeLines=g.plane_lines)
+        if self.param.bEnableTemporalSubLayers > 2:
+            d.update(gopOffset=info.gopOffset, tempLayer=info.tempLayer, gopId=info.gopId if info.gopIdWritten else None,
+                     gopIdTop=self.param.bEnableTemporalSubLayers - 3)
         costEst = np.zeros((nb, nb), np.int64); costEstAq = np.zeros((nb, nb), np.int64)
         intraMbs = np.zeros(nb, np.int32); valid = np.zeros((nb, nb), np.int32)
         ssd = np.zeros(3, np.uint64); sm = np.zeros(3, np.uint64); wd = np.zeros(nb, np.float64)

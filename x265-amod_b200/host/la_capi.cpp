@@ -106,6 +106,7 @@ int x265la_get_decided(void* lav, x265la_frame_info* out)
     out->poc = f->m_poc; out->sliceType = l.sliceType; out->bScenecut = l.bScenecut; out->bKeyframe = l.bKeyframe;
     out->bLastMiniGopBFrame = l.bLastMiniGopBFrame; out->leadingBframes = l.leadingBframes;
     out->pts = f->m_pts; out->reorderedPts = f->m_reorderedPts; out->satdCost = l.satdCost;
+    out->gopOffset = f->m_gopOffset; out->gopId = f->m_gopId; out->tempLayer = f->m_tempLayer; out->gopIdWritten = f->m_gopIdSet;
     out->handle = f;
     return 1;
 }

@@ -46,6 +46,9 @@ typedef struct
     int32_t poc, sliceType, bScenecut, bKeyframe, bLastMiniGopBFrame, leadingBframes;
     int64_t pts, reorderedPts, satdCost;
     void*   handle;                  /* pass to the x265la_frame_* calls and x265la_release */
+    /* --temporal-layers 3..5: Frame::m_gopOffset / m_gopId / m_tempLayer as slicetypeDecide left them (slicetype.cpp:2133-2320);
+     * gopIdWritten == 0: the reference did not touch m_gopId of this frame (the caller's Frame keeps what it held) */
+    int32_t gopOffset, gopId, tempLayer, gopIdWritten;
 } x265la_frame_info;
 
 void  x265la_param_default(x265la_param* p);

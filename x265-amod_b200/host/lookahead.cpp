@@ -153,7 +153,14 @@ bool Lookahead::create()
         return false;
     }
     if (p.bHistBasedSceneCut && p.internalBitDepth != 8) { fail("--hist-scenecut is 8-bit only (the reference indexes 256 bins with the sample value)"); return false; }
-    if (p.bEnableTemporalSubLayers > 2) { fail("more than two temporal layers are not supported by the GPU lookahead"); return false; }
+    if (p.bEnableTemporalSubLayers > 5) { fail("temporal-layers must be 0..5"); return false; }
+    if (p.bEnableTemporalSubLayers > 2)
+    {
+        /* Encoder::configure (encoder.cpp:3914-3943) has fixed the mini-GOP to 3 / 7 / 15 B frames and turned b-adapt off */
+        static const int tlBframes[6] = { 0, 0, 0, 3, 7, 15 };
+        if (p.bframes != tlBframes[p.bEnableTemporalSubLayers] || p.bFrameAdaptive) { fail("temporal-layers 3..5 need bframes 3 / 7 / 15 and b-adapt 0 (Encoder::configure sets them)"); return false; }
+        if (!p.lookaheadDepth) { fail("temporal-layers 3..5 with rc-lookahead 0 is not supported"); return false; }
+    }
     if (p.bEnableHME && rowsPerSlice > 0)
     {
         /* the reference cuts the two levels into slices at different rows (slicetype.cpp:3942-3968): a slice's lowres search
@@ -290,6 +297,7 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
     }
     f->m_inUse = true; f->m_released = false; f->m_speculated = false; f->m_lowresInit = false;
     f->m_poc = m_pocNext++; f->m_pts = pts; f->m_reorderedPts = 0;
+    f->m_gopOffset = 0; f->m_gopId = 0; f->m_tempLayer = 0; f->m_gopIdSet = false;
     f->m_planes[0] = y; f->m_planes[1] = u; f->m_planes[2] = v; f->m_strideY = strideY; f->m_strideC = strideC;
     initLowres(f, f->m_poc);
     /* Encoder::encode (encoder.cpp:1713-1714, 1863): the type an application forces through x265_picture::sliceType goes
@@ -994,6 +1002,155 @@ void Lookahead::compCostBref(Lowres** frames, int start, int end, int num)
     compCostBref(frames, avg + 1, end, end - avg);
 }
 
+/* x265_gop_ra (x265.h:771-...): the random-access sub-GOPs of 4 / 8 / 16 pictures in coded order, { POC offset, temporal layer } */
+static const signed char s_gopRaLength[3] = { 4, 8, 16 };
+static const signed char s_gopRa[3][16][2] = {
+    { {4, 0}, {2, 1}, {1, 2}, {3, 2} },
+    { {8, 0}, {4, 1}, {2, 2}, {1, 3}, {3, 3}, {6, 2}, {5, 3}, {7, 3} },
+    { {16, 0}, {8, 1}, {4, 2}, {2, 3}, {1, 4}, {3, 4}, {6, 3}, {5, 4}, {7, 4}, {12, 2}, {10, 3}, {9, 4}, {11, 4}, {14, 3}, {13, 4}, {15, 4} } };
+
+/* The tail of slicetypeDecide with more than two temporal layers (slicetype.cpp:2061-2325): bframes is 3 / 7 / 15 and
+ * b-adapt is off (Encoder::configure, encoder.cpp:3933-3943).  A complete mini-GOP leaves in the coded order of its
+ * random-access structure, every frame tagged with its position, structure and temporal layer (the DPB builds the
+ * reference picture sets from those); a partial one (scene cut, keyframe, end of stream) is split into the largest
+ * smaller structures that fit, each closed by its own P, and a rest of up to three frames coded B-refs first. */
+void Lookahead::decideTemporalLayers(Frame** list, Lowres** frames, Frame** fr, int bframes, int brefs, int& maxSearch)
+{
+    const LookaheadParam& p = m_param;
+    const int topGop = p.bEnableTemporalSubLayers - 3;     /* Lookahead::m_gopId, :1097-1114 */
+    (void)fr;
+    /* close frames list[from .. last] as a sub mini-GOP: types, B-refs, the costs rate control will ask for */
+    struct Close
+    {
+        static void run(Lookahead& la, Frame** list, Lowres** frames, int from, int last, bool bref, int* brefs)
+        {
+            Lowres& l = list[last]->m_lowres;
+            if (!isTypeI(l.sliceType)) l.sliceType = TYPE_P;
+            if (last) list[last - 1]->m_lowres.bLastMiniGopBFrame = true;
+            l.leadingBframes = last;            /* the index in the whole list, as the reference writes it */
+            la.m_lastNonB = &l; la.m_lastNonBFrame = list[last];
+            if (bref) la.placeBref(list, from, last, last + 1, brefs);
+            if (la.m_param.rc.rateControlMode != 1 /* X265_RC_CQP */)
+            {
+                const int b = last + 1, p1 = b;
+                const int p0 = isTypeI(frames[last + 1]->sliceType) ? b : from;
+                la.singleCost(frames, p0, p1, b);
+                frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
+                if (last) la.compCostBref(frames, from, last, last + 1);
+            }
+        }
+    };
+    if (bframes < p.bframes)
+    {
+        int leftOver = bframes + 1;
+        int gopId = topGop - 1;
+        int gopLen = gopId >= 0 ? s_gopRaLength[gopId] : 0;
+        int listReset = 0;
+        while (gopId >= 0 && leftOver > 3 && !m_failed)
+        {
+            if (leftOver < gopLen)
+            {
+                gopId--;
+                gopLen = gopId >= 0 ? s_gopRaLength[gopId] : 0;
+                continue;
+            }
+            const int newbFrames = listReset + gopLen - 1;
+            Close::run(*this, list, frames, listReset, newbFrames, p.bBPyramid && newbFrames, &brefs);
+            if (m_failed) return;
+            int64_t pts[BFRAME_MAX + 1];
+            for (int i = 0; i < gopLen; i++)
+            {
+                pts[i] = m_inputQueue.front()->m_pts;
+                m_inputQueue.pop_front();
+                maxSearch--;
+            }
+            int idx = 0;
+            list[newbFrames]->m_reorderedPts = pts[idx++];
+            list[newbFrames]->m_gopOffset = 0; list[newbFrames]->m_gopId = gopId; list[newbFrames]->m_gopIdSet = true; list[newbFrames]->m_tempLayer = s_gopRa[gopId][0][1];
+            m_outputQueue.push_back(list[newbFrames]);
+            for (int j = 1; j < gopLen; j++)
+            {
+                Frame* f = list[listReset + s_gopRa[gopId][j][0] - 1];
+                f->m_gopOffset = j;
+                list[bframes]->m_gopId = gopId; list[bframes]->m_gopIdSet = true;     /* sic (:2152): the LAST frame of the list is tagged, not this one */
+                f->m_tempLayer = s_gopRa[gopId][j][1];
+                f->m_reorderedPts = pts[idx++];
+                m_outputQueue.push_back(f);
+            }
+            listReset += gopLen;
+            leftOver -= gopLen;
+            gopId--;
+            gopLen = gopId >= 0 ? s_gopRaLength[gopId] : 0;
+        }
+        if (leftOver > 0 && leftOver < 4)
+        {
+            const int newbFrames = listReset + leftOver - 1;
+            Close::run(*this, list, frames, listReset, newbFrames, p.bBPyramid && (newbFrames - listReset) > 1, &brefs);
+            if (m_failed) return;
+            int64_t pts[BFRAME_MAX + 1];
+            for (int i = 0; i < leftOver; i++)
+            {
+                pts[i] = m_inputQueue.front()->m_pts;
+                m_inputQueue.pop_front();
+                maxSearch--;
+            }
+            int idx = 0;
+            list[newbFrames]->m_reorderedPts = pts[idx++];
+            list[newbFrames]->m_gopOffset = 0; list[newbFrames]->m_gopId = -1; list[newbFrames]->m_gopIdSet = true; list[newbFrames]->m_tempLayer = 0;
+            m_outputQueue.push_back(list[newbFrames]);
+            if (brefs)
+                for (int i = listReset; i < newbFrames; i++)
+                    if (list[i]->m_lowres.sliceType == TYPE_BREF)
+                    {
+                        list[i]->m_reorderedPts = pts[idx++];
+                        list[i]->m_gopOffset = 0; list[i]->m_gopId = -1; list[i]->m_gopIdSet = true; list[i]->m_tempLayer = 0;
+                        m_outputQueue.push_back(list[i]);
+                    }
+            for (int i = listReset; i < newbFrames; i++)
+                if (list[i]->m_lowres.sliceType != TYPE_BREF)
+                {
+                    list[i]->m_reorderedPts = pts[idx++];
+                    list[i]->m_gopOffset = 0; list[i]->m_gopId = -1; list[i]->m_gopIdSet = true; list[i]->m_tempLayer = 1;
+                    m_outputQueue.push_back(list[i]);
+                }
+        }
+        return;
+    }
+    /* the complete mini-GOP */
+    list[bframes - 1]->m_lowres.bLastMiniGopBFrame = true;
+    list[bframes]->m_lowres.leadingBframes = bframes;
+    m_lastNonB = &list[bframes]->m_lowres; m_lastNonBFrame = list[bframes];
+    if (p.bBPyramid && !brefs)
+        placeBref(list, 0, bframes, bframes + 1, &brefs);
+    if (p.rc.rateControlMode != 1)
+    {
+        const int b = bframes + 1, p1 = b;
+        const int p0 = isTypeI(frames[bframes + 1]->sliceType) ? b : 0;
+        singleCost(frames, p0, p1, b);
+        frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
+        compCostBref(frames, 0, bframes, bframes + 1);
+    }
+    if (m_failed) return;
+    int64_t pts[BFRAME_MAX + 1];
+    for (int i = 0; i <= bframes; i++)
+    {
+        pts[i] = m_inputQueue.front()->m_pts;
+        m_inputQueue.pop_front();
+        maxSearch--;
+    }
+    int idx = 0;
+    list[bframes]->m_reorderedPts = pts[idx++];
+    list[bframes]->m_gopOffset = 0; list[bframes]->m_gopId = topGop; list[bframes]->m_gopIdSet = true; list[bframes]->m_tempLayer = s_gopRa[topGop][0][1];
+    m_outputQueue.push_back(list[bframes]);
+    for (int j = 1; j <= bframes; j++)
+    {
+        Frame* f = list[s_gopRa[topGop][j][0] - 1];
+        f->m_gopOffset = j; f->m_gopId = topGop; f->m_gopIdSet = true; f->m_tempLayer = s_gopRa[topGop][j][1];
+        f->m_reorderedPts = pts[idx++];
+        m_outputQueue.push_back(f);
+    }
+}
+
 void Lookahead::slicetypeDecide()
 {
     Lowres* frames[LOOKAHEAD_MAX + BFRAME_MAX + 4];
@@ -1169,69 +1326,75 @@ void Lookahead::slicetypeDecide()
         else if (!isTypeB(frm.sliceType)) break;
     }
 
-    if (bframes) list[bframes - 1]->m_lowres.bLastMiniGopBFrame = true;
-    list[bframes]->m_lowres.leadingBframes = bframes;
-    m_lastNonB = &list[bframes]->m_lowres;
-    m_lastNonBFrame = list[bframes];
-
-    if (p.bBPyramid && bframes > 1 && !brefs)
-        placeBref(list, 0, bframes, bframes + 1, &brefs);
-
-    /* costs RateControl will ask for (slicetype.cpp:2378-2427) */
-    if (p.rc.rateControlMode != 1 /* X265_RC_CQP */)
+    if (p.bEnableTemporalSubLayers > 2)
+        decideTemporalLayers(list, frames, fr, bframes, brefs, maxSearch);      /* :2061-2325 */
+    else
     {
-        int p0, p1, b;
-        if (!maxSearch)
-            for (int i = 0; i <= bframes; i++) { frames[i + 1] = &list[i]->m_lowres; fr[i + 1] = list[i]; }
-        p1 = b = bframes + 1;
-        p0 = isTypeI(frames[bframes + 1]->sliceType) ? b : 0;
-        singleCost(frames, p0, p1, b);
-        frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
-        if (p.bEnableTemporalSubLayers > 1 && bframes)
-            compCostBref(frames, 0, bframes, bframes + 1);
-        else if (bframes)
+        if (bframes) list[bframes - 1]->m_lowres.bLastMiniGopBFrame = true;
+        list[bframes]->m_lowres.leadingBframes = bframes;
+        m_lastNonB = &list[bframes]->m_lowres;
+        m_lastNonBFrame = list[bframes];
+
+        if (p.bBPyramid && bframes > 1 && !brefs)
+            placeBref(list, 0, bframes, bframes + 1, &brefs);
+
+        /* costs RateControl will ask for (slicetype.cpp:2378-2427) */
+        if (p.rc.rateControlMode != 1 /* X265_RC_CQP */)
         {
-            p0 = 0;
-            bool isp0available = frames[bframes + 1]->sliceType != TYPE_IDR;
-            for (b = 1; b <= bframes; b++)
+            int p0, p1, b;
+            if (!maxSearch)
+                for (int i = 0; i <= bframes; i++) { frames[i + 1] = &list[i]->m_lowres; fr[i + 1] = list[i]; }
+            p1 = b = bframes + 1;
+            p0 = isTypeI(frames[bframes + 1]->sliceType) ? b : 0;
+            singleCost(frames, p0, p1, b);
+            frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
+            if (p.bEnableTemporalSubLayers > 1 && bframes)
+                compCostBref(frames, 0, bframes, bframes + 1);
+            else if (bframes)
             {
-                if (!isp0available) p0 = b;
-                if (frames[b]->sliceType == TYPE_B)
-                    for (p1 = b; frames[p1]->sliceType == TYPE_B; p1++) ;
-                else
-                    p1 = bframes + 1;
-                singleCost(frames, p0, p1, b);
-                frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
-                if (frames[b]->sliceType == TYPE_BREF) { p0 = b; isp0available = true; }
+                p0 = 0;
+                bool isp0available = frames[bframes + 1]->sliceType != TYPE_IDR;
+                for (b = 1; b <= bframes; b++)
+                {
+                    if (!isp0available) p0 = b;
+                    if (frames[b]->sliceType == TYPE_B)
+                        for (p1 = b; frames[p1]->sliceType == TYPE_B; p1++) ;
+                    else
+                        p1 = bframes + 1;
+                    singleCost(frames, p0, p1, b);
+                    frames[b]->rcPlanD0 = b - p0; frames[b]->rcPlanD1 = p1 - b;
+                    if (frames[b]->sliceType == TYPE_BREF) { p0 = b; isp0available = true; }
+                }
             }
         }
-    }
-    if (m_failed) return;
+        if (m_failed) return;
 
-    /* move the mini-GOP to the output queue in coded order (:2429-2472) */
-    int64_t pts[BFRAME_MAX + 1];
-    for (int i = 0; i <= bframes; i++)
-    {
-        pts[i] = m_inputQueue.front()->m_pts;
-        m_inputQueue.pop_front();
-        maxSearch--;
-    }
-    int idx = 0;
-    list[bframes]->m_reorderedPts = pts[idx++];
-    m_outputQueue.push_back(list[bframes]);
-    if (brefs)
+        /* move the mini-GOP to the output queue in coded order (:2429-2472) */
+        int64_t pts[BFRAME_MAX + 1];
+        for (int i = 0; i <= bframes; i++)
+        {
+            pts[i] = m_inputQueue.front()->m_pts;
+            m_inputQueue.pop_front();
+            maxSearch--;
+        }
+        int idx = 0;
+        list[bframes]->m_reorderedPts = pts[idx++];
+        m_outputQueue.push_back(list[bframes]);
+        if (brefs)
+            for (int i = 0; i < bframes; i++)
+                if (list[i]->m_lowres.sliceType == TYPE_BREF)
+                {
+                    list[i]->m_reorderedPts = pts[idx++];
+                    m_outputQueue.push_back(list[i]);
+                }
         for (int i = 0; i < bframes; i++)
-            if (list[i]->m_lowres.sliceType == TYPE_BREF)
+            if (list[i]->m_lowres.sliceType != TYPE_BREF)
             {
                 list[i]->m_reorderedPts = pts[idx++];
                 m_outputQueue.push_back(list[i]);
             }
-    for (int i = 0; i < bframes; i++)
-        if (list[i]->m_lowres.sliceType != TYPE_BREF)
-        {
-            list[i]->m_reorderedPts = pts[idx++];
-            m_outputQueue.push_back(list[i]);
-        }
+    }
+    if (m_failed) return;
 
     /* keyframe re-analysis for cuTree / VBV (:2475-2504) */
     bool isKeyFrameAnalyse = p.rc.cuTree || (p.rc.vbvBufferSize && p.lookaheadDepth);

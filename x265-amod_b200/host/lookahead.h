@@ -47,7 +47,8 @@ struct LookaheadParam
     int gopLookahead;    /* --gop-lookahead: a keyframe due at the GOP boundary may wait this many frames for a scene cut */
     int bEnableWeightedPred, bEnableWeightedBiPred;
     int bEnableTemporalSubLayers;   /* --temporal-layers: 0 / 1, or 2 (B-refs placed recursively, their costs pre-computed by
-                                       compCostBref, slicetype.cpp:1755-1799); > 2 is refused */
+                                       compCostBref, slicetype.cpp:1755-1799), or 3 / 4 / 5 (fixed random-access mini-GOPs of
+                                       4 / 8 / 16 pictures, :2061-2325; Encoder::configure then sets bframes 3 / 7 / 15, b-adapt 0) */
     int bHistBasedSceneCut;         /* --hist-scenecut (8-bit only): scene cuts from per-segment histogram differences instead of
                                        the cost-based test (slicetype.cpp:3057-3216) */
     int bEnableHME;      /* --hme: hierarchical motion estimation, levels 0 (1/16 resolution) and 1 (lowres) of the lookahead's searches
@@ -140,6 +141,9 @@ struct Frame
 {
     int      m_poc;
     int64_t  m_pts, m_reorderedPts;
+    bool     m_gopIdSet;      /* this decision wrote m_gopId (the reference leaves it alone for the B frames of a split mini-GOP, :2152) */
+    int      m_gopOffset, m_gopId, m_tempLayer;     /* Frame::m_gopOffset / m_gopId / m_tempLayer (--temporal-layers 3..5: position in the
+                                                       random-access structure, which structure, temporal layer; the DPB reads them) */
     Lowres   m_lowres;
     bool     m_lowresInit;
     bool     m_speculated;
@@ -260,6 +264,7 @@ private:
     int64_t vbvFrameCost(Lowres** frames, int p0, int p1, int b);
     void    placeBref(Frame** list, int start, int end, int num, int* brefs);
     void    compCostBref(Lowres** frames, int start, int end, int num);   /* :1780-1799 */
+    void    decideTemporalLayers(Frame** list, Lowres** frames, Frame** fr, int bframes, int brefs, int& maxSearch);   /* :2061-2325 */
 
     /* CostEstimateGroup (slicetype.h:261-326) folded in */
     int64_t singleCost(Lowres** frames, int p0, int p1, int b, bool bIntraPenalty = false);
