@@ -69,6 +69,11 @@ WORKLOADS = {
     "4320p-8bit": dict(width=7680, height=4320, depth=8, frames=160, cpu_frames=24, seed=4,
                        la=dict(bframes=4, lookaheadDepth=80, bFrameAdaptive=2),
                        text="4320p 8-bit --rc-lookahead 80 --bframes 4 (BASELINE configs[3])"),
+    # --hme on BASELINE configs[0]: levels 0 (hex) and 1 (umh) of the hierarchical search on the GPU (a correctness-first
+    # path -- the four blocks of a warp search independently); measured so that the cost of the option is on record
+    "1080p-8bit-hme": dict(width=1920, height=1080, depth=8, frames=120, cpu_frames=40, seed=1,
+                           la=dict(bframes=4, lookaheadDepth=20, bFrameAdaptive=2, bEnableHME=1),
+                           text="1080p 8-bit preset medium --rc-lookahead 20 --bframes 4 --b-adapt 2 --hme (hex, umh; ranges 16, 32)"),
     "360p-smoke": dict(width=640, height=360, depth=8, frames=60, cpu_frames=60, seed=1,
                        la=dict(bframes=4, lookaheadDepth=20, bFrameAdaptive=2), text="640x360 smoke"),
 }
@@ -164,7 +169,7 @@ def run_reference_sample(wl, frames, threads, simd=True, snap=False):
 
 def ref_kwargs(la):
     """our LaParam names -> the reference harness' (oracle/refbind.py)"""
-    m = dict(bEnableWeightedPred="weightp", bEnableWeightedBiPred="weightb")
+    m = dict(bEnableWeightedPred="weightp", bEnableWeightedBiPred="weightb", bEnableHME="hme")
     return {m.get(k, k): v for k, v in la.items()}
 
 
@@ -709,7 +714,7 @@ def main():
             except Exception as e:      # pragma: no cover
                 others["4320p-window-shard"] = {"error": repr(e)}
         if world == 1:
-            for name in ("1080p-8bit", "1080p-slower-weightp", "4320p-8bit"):
+            for name in ("1080p-8bit", "1080p-slower-weightp", "4320p-8bit", "1080p-8bit-hme"):
                 need = 75 if name == "4320p-8bit" else 30
                 if left() < need:
                     others[name] = {"skipped": "time budget of the default run (%.0f s left, %d s needed)" % (left(), need)}

@@ -215,6 +215,8 @@ FULL_SIZE = [
     ("cfg1_1080p_8bit", 8, 1920, 1080, 100, dict(cuts=(53,), n_rects=6, seed=1), dict(bframes=4, lookaheadDepth=20, poolThreads=16)),
     ("cfg3_1080p_slower_weightp", 8, 1920, 1080, 90, dict(cuts=(13, 37, 64), fades=[(20, 12, 0.35), (70, 10, 1.0)], flashes=[(50, 1)], n_rects=6, seed=3),
      dict(bframes=8, lookaheadDepth=40, poolThreads=16, weightp=1)),
+    # --hme at a BASELINE size: level-0 (hex) and level-1 (umh) vectors and costs of every published search included
+    ("cfg1_1080p_8bit_hme", 8, 1920, 1080, 40, dict(cuts=(21,), n_rects=6, seed=1), dict(bframes=4, lookaheadDepth=20, poolThreads=16, hme=1)),
 ]
 # config 4 (7680x4320, rc-lookahead 80): against the C oracle through the sim engine on a dozen frames
 FULL_SIZE_ORACLE = ("cfg4_4320p_8bit", 8, 7680, 4320, 12, dict(cuts=(7,), n_rects=4, seed=4), dict(bframes=4, lookaheadDepth=80))
