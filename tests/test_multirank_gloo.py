@@ -93,7 +93,7 @@ def _shard_worker(rank, world, port, simdir, q, case_name, extra):
 
 
 @pytest.mark.parametrize("case_name,extra,world", [("base8", {}, 2), ("static_noise", dict(asyncDepth=5), 2), ("fade8", dict(speculate=2), 2),
-                                                   ("base8", dict(asyncDepth=6), 4), ("fade8", {}, 3)])
+                                                   ("base8", dict(asyncDepth=6), 4), ("fade8", {}, 3), ("hme_golden", {}, 2)])
 def test_two_ranks_shard_one_stream(case_name, extra, world, simdir):
     """SURVEY 8e level 2: one stream, searches / estimates split by source frame over two ranks, stores exchanged after
     every batch (gloo here, NCCL on the GPU box).  Both ranks must publish exactly what a single rank publishes (the
@@ -108,7 +108,21 @@ def test_two_ranks_shard_one_stream(case_name, extra, world, simdir):
     procs = [ctx.Process(target=_shard_worker, args=(r, world, port, simdir, q, case_name, extra)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in procs)
+    res = []
+    import queue as _queue
+    import time as _time
+    t0 = _time.time()
+    while len(res) < len(procs):
+        try:
+            res.append(q.get(timeout=2))
+        except _queue.Empty:
+            dead = [p.exitcode for p in procs if not p.is_alive() and p.exitcode]
+            if dead or _time.time() - t0 > 600:       # a rank failed: do not wait for the collective's timeout on the others
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                raise AssertionError("a rank failed (exit codes %s)" % dead)
+    res.sort()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -264,7 +264,7 @@ class Lookahead:
             for i in range(nb):
                 searched[l, i] = bool(self.lib.x265la_frame_mvs(self.h, hnd, l, i, mvs[l, i].ctypes.data, mvc[l, i].ctypes.data))
         d.update(mvs=mvs, mvCosts=mvc, searched=searched)
-        if self.param.bEnableHME and self.param.sourceHeight >= 540:
+        if self.param.bEnableHME and self.param.sourceHeight >= 540 and self.param.shardCount <= 1:
             # level-0 results of --hme behind every published search (Lowres::lowerResMvs / lowerResMvCosts)
             n4 = (((self.param.sourceWidth // 4) + 7) >> 3) * (((self.param.sourceHeight // 4) + 7) >> 3)
             lm = np.zeros((2, nb, n4, 2), np.int32); lmc = np.zeros((2, nb, n4), np.int32)

@@ -2207,6 +2207,8 @@ bool Lookahead::fetchHmeMvs(Frame* f, int list, int dist, int32_t* mvXY, int32_t
 {
     const int store = f->m_lowres.mvStore[list][dist];
     if (store < 0 || !m_param.bEnableHME) return false;
+    /* a sharded stream exchanges the lowres results only: the level-0 vectors stay on the rank that searched the frame */
+    if (m_param.shardCount > 1 && f->m_poc % m_param.shardCount != m_shardRank) return false;
     return check(x265cu_fetch_hme_mvs(m_ctx, f->m_lowres.slot, store, mvXY, mvCosts), "x265cu_fetch_hme_mvs");
 }
 
