@@ -785,8 +785,158 @@ static const or_mv hex4[16] = { {0, -4}, {0, 4}, {-2, -3}, {2, -3}, {-4, -2}, {4
 #define OR_DIA_SEARCH 0
 #define OR_HEX_SEARCH 1
 #define OR_UMH_SEARCH 2
+#define OR_STAR_SEARCH 3
+
+/* offsets for the two-point search around a distance-1 result (motion.cpp:74-84) */
+static const or_mv star_offsets[16] = { {-1, 0}, {0, -1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {-1, -1},
+                                        {1, -1}, {1, 1}, {-1, 0}, {0, 1}, {-1, 1}, {1, 1}, {1, 0}, {0, 1} };
 
 static inline int in_range(or_mv v, or_mv lo, or_mv hi) { return v.x >= lo.x && v.x <= hi.x && v.y >= lo.y && v.y <= hi.y; }   /* mv.h:104 */
+
+/* MotionEstimate::StarPatternSearch (motion.cpp:387-630): a growing star around the entry point (which stays the centre);
+ * every point either measured unconditionally (the whole star lies inside the range) or behind the reference's own,
+ * partial, range tests */
+typedef struct { int bcost; or_mv bmv; int point, dist; } or_star;
+
+static void star_pt(or_me* m, or_star* s, int mx, int my, int point, int dist)
+{
+    int cost = sad_fpel(m, mx, my) + mvcost_q(m, mx << 2, my << 2);
+    if (cost < s->bcost) { s->bcost = cost; s->bmv.x = mx; s->bmv.y = my; s->point = point; s->dist = dist; }
+}
+
+static void star_pattern(or_me* m, or_mv mvmin, or_mv mvmax, or_star* s, int earlyExitIters, int merange)
+{
+    const or_mv o = s->bmv;
+    int saved = s->bcost, rounds = 0;
+    for (int dist = 1; dist <= 8; dist <<= 1)
+    {
+        const int top = o.y - dist, bottom = o.y + dist, left = o.x - dist, right = o.x + dist;
+        const int top2 = o.y - (dist >> 1), bottom2 = o.y + (dist >> 1), left2 = o.x - (dist >> 1), right2 = o.x + (dist >> 1);
+        const int in = top >= mvmin.y && left >= mvmin.x && right <= mvmax.x && bottom <= mvmax.y;
+        saved = s->bcost;
+        if (dist == 1)
+        {
+            if (in || top >= mvmin.y) star_pt(m, s, o.x, top, 2, dist);
+            if (in || left >= mvmin.x) star_pt(m, s, left, o.y, 4, dist);
+            if (in || right <= mvmax.x) star_pt(m, s, right, o.y, 5, dist);
+            if (in || bottom <= mvmax.y) star_pt(m, s, o.x, bottom, 7, dist);
+        }
+        else
+        {
+            if (in || top >= mvmin.y) star_pt(m, s, o.x, top, 2, dist);
+            if (in || top2 >= mvmin.y)
+            {
+                if (in || left2 >= mvmin.x) star_pt(m, s, left2, top2, 1, dist >> 1);
+                if (in || right2 <= mvmax.x) star_pt(m, s, right2, top2, 3, dist >> 1);
+            }
+            if (in || left >= mvmin.x) star_pt(m, s, left, o.y, 4, dist);
+            if (in || right <= mvmax.x) star_pt(m, s, right, o.y, 5, dist);
+            if (in || bottom2 <= mvmax.y)
+            {
+                if (in || left2 >= mvmin.x) star_pt(m, s, left2, bottom2, 6, dist >> 1);
+                if (in || right2 <= mvmax.x) star_pt(m, s, right2, bottom2, 8, dist >> 1);
+            }
+            if (in || bottom <= mvmax.y) star_pt(m, s, o.x, bottom, 7, dist);
+        }
+        if (s->bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+    for (int dist = 16; dist <= (int16_t)merange; dist <<= 1)
+    {
+        const int top = o.y - dist, bottom = o.y + dist, left = o.x - dist, right = o.x + dist;
+        const int in = top >= mvmin.y && left >= mvmin.x && right <= mvmax.x && bottom <= mvmax.y;
+        saved = s->bcost;
+        if (in || top >= mvmin.y) star_pt(m, s, o.x, top, 0, dist);
+        if (in || left >= mvmin.x) star_pt(m, s, left, o.y, 0, dist);
+        if (in || right <= mvmax.x) star_pt(m, s, right, o.y, 0, dist);
+        if (in || bottom <= mvmax.y) star_pt(m, s, o.x, bottom, 0, dist);
+        for (int index = 1; index < 4; index++)
+        {
+            const int yT = top + (dist >> 2) * index, yB = bottom - (dist >> 2) * index;
+            const int xL = o.x - (dist >> 2) * index, xR = o.x + (dist >> 2) * index;
+            if (in || yT >= mvmin.y)
+            {
+                if (in || xL >= mvmin.x) star_pt(m, s, xL, yT, 0, dist);
+                if (in || xR <= mvmax.x) star_pt(m, s, xR, yT, 0, dist);
+            }
+            if (in || yB <= mvmax.y)
+            {
+                if (in || xL >= mvmin.x) star_pt(m, s, xL, yB, 0, dist);
+                if (in || xR <= mvmax.x) star_pt(m, s, xR, yB, 0, dist);
+            }
+        }
+        if (s->bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+}
+
+static void star_two_points(or_me* m, or_mv mvmin, or_mv mvmax, or_star* s)
+{
+    const or_mv c = s->bmv;
+    for (int k = 0; k < 2; k++)
+    {
+        or_mv v = { c.x + star_offsets[(s->point - 1) * 2 + k].x, c.y + star_offsets[(s->point - 1) * 2 + k].y };
+        if (in_range(v, mvmin, mvmax))
+        {
+            int cost = sad_fpel(m, v.x, v.y) + mvcost_q(m, v.x << 2, v.y << 2);
+            if (cost < s->bcost) { s->bcost = cost; s->bmv = v; }
+        }
+    }
+}
+
+/* X265_STAR_SEARCH (motion.cpp:1157-1264) */
+static void star_search(or_me* m, or_mv mvmin, or_mv mvmax, int merange, int* bcost, or_mv* bmv)
+{
+    or_star s = { *bcost, *bmv, 0, 0 };
+    star_pattern(m, mvmin, mvmax, &s, 3, merange);
+    int stop = 0;
+    if (s.dist == 1)
+    {
+        if (!s.point) stop = 1;
+        else
+        {
+            int saved = s.bcost;
+            star_two_points(m, mvmin, mvmax, &s);
+            if (s.bcost == saved) stop = 1;
+        }
+    }
+    if (!stop)
+    {
+        if (s.dist > 5)     /* RasterDistance */
+            for (int y = mvmin.y; y <= mvmax.y; y += 5)
+                for (int x = mvmin.x; x <= mvmax.x; x += 5)
+                {
+                    if (x + 15 <= mvmax.x)
+                    {
+                        for (int k = 0; k < 4; k++)
+                        {
+                            /* the fourth of a group is charged mvcost(tmv << 3) (:1219, sic) */
+                            int sh = k == 3 ? 3 : 2, xk = x + 5 * k;
+                            int cost = sad_fpel(m, xk, y) + mvcost_q(m, xk << sh, y << sh);
+                            if (cost < s.bcost) { s.bcost = cost; s.bmv.x = xk; s.bmv.y = y; }
+                        }
+                        x += 15;
+                    }
+                    else
+                    {
+                        int cost = sad_fpel(m, x, y) + mvcost_q(m, x << 2, y << 2);
+                        if (cost < s.bcost) { s.bcost = cost; s.bmv.x = x; s.bmv.y = y; }
+                    }
+                }
+        while (s.dist > 0)
+        {
+            s.dist = 0; s.point = 0;
+            star_pattern(m, mvmin, mvmax, &s, 32, merange);
+            if (s.dist == 1)
+            {
+                if (s.point) star_two_points(m, mvmin, mvmax, &s);
+                break;
+            }
+        }
+    }
+    *bcost = s.bcost; *bmv = s.bmv;
+}
+
 
 /* MotionEstimate::motionEstimate, lowres path (numCandidates 0, subpelRefine 1): the integer search `method` (DIA / HEX / UMH,
  * encoder/motion.cpp:842-1160) over `merange`, then the lowres subpel refinement (:1473-1528).  Without --hme the lookahead
@@ -945,6 +1095,8 @@ static int motion_estimate_ex(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, in
 #undef CROSS
 #undef SAD_THRESH
     }
+    else if (method == OR_STAR_SEARCH)
+        star_search(m, mvmin, mvmax, merange, &bcost, &bmv);
     if (hexRefine)
     {
         int c0 = COSTAT(-2, 0), c1 = COSTAT(-1, 2), c2 = COSTAT(1, 2);

@@ -1,9 +1,10 @@
 /* la_me_generic.cuh -- the integer motion searches --hme selects per level (dia / hex / umh) + the lowres subpel refinement,
- * written against a small evaluator interface instead of the warp-wide lockstep of the default search (la_kernels.cuh
+ * and star; sea and full are not built), written against a small evaluator interface instead of the warp-wide lockstep of the default search (la_kernels.cuh
  * motionEstimate, which stays as it is: HEX over 16 is all the lookahead runs without --hme).
  *
  * Reference semantics: MotionEstimate::motionEstimate with numCandidates == 0, subpelRefine 1, a lowres reference
- * (source/encoder/motion.cpp:764-868 prologue + DIA, :870-969 HEX + square refine, :971-1160 UMH, :1473-1528 subpel).
+ * (source/encoder/motion.cpp:764-868 prologue + DIA, :870-969 HEX + square refine, :971-1160 UMH, :387-630 + :1157-1264 STAR,
+ * :1473-1528 subpel).
  *
  * `Ctx` provides
  *     int  sadFpel(int x, int y)          SAD of the source block against the reference block displaced by (x, y) full pels
@@ -29,13 +30,17 @@ namespace la {
 
 struct MV2 { int x, y; };
 
-enum { LA_DIA_SEARCH = 0, LA_HEX_SEARCH = 1, LA_UMH_SEARCH = 2 };     /* X265_DIA/HEX/UMH_SEARCH, x265.h */
+enum { LA_DIA_SEARCH = 0, LA_HEX_SEARCH = 1, LA_UMH_SEARCH = 2, LA_STAR_SEARCH = 3 };     /* X265_DIA/HEX/UMH/STAR_SEARCH, x265.h */
 
 LA_CONST_TABLE signed char g_hex2[8][2] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };    /* motion.cpp:64 */
 LA_CONST_TABLE unsigned char g_mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };                                                 /* :65 */
 LA_CONST_TABLE signed char g_square1[9][2] = { {0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1} };   /* :66 */
 LA_CONST_TABLE signed char g_hex4[16][2] = { {0, -4}, {0, 4}, {-2, -3}, {2, -3}, {-4, -2}, {4, -2}, {-4, -1}, {4, -1},
                                              {-4, 0}, {4, 0}, {-4, 1}, {4, 1}, {-4, 2}, {4, 2}, {-2, 3}, {2, 3} };      /* :67-73 */
+
+/* the two outer neighbours of each of the 8 points around the centre (motion.cpp:74-84) */
+LA_CONST_TABLE signed char g_starOffsets[16][2] = { {-1, 0}, {0, -1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {-1, -1},
+                                                    {1, -1}, {1, 1}, {-1, 0}, {0, 1}, {-1, 1}, {1, 1}, {1, 0}, {0, 1} };
 
 LA_HD int gmin(int a, int b) { return a < b ? a : b; }
 LA_HD int gmax(int a, int b) { return a > b ? a : b; }
@@ -175,6 +180,170 @@ LA_HD bool gUmh(Ctx& m, MV2 mvmin, MV2 mvmax, MV2 pmv /* full-pel */, int merang
     return gInRange(bmv, mvmin, mvmax);
 }
 
+/* ---- STAR (adapted from HM; motion.cpp:387-630 StarPatternSearch, :1157-1264) ---- */
+struct StarState { int bcost; MV2 bmv; int pointNr, distance; };
+
+/* COST_MV_PT_DIST (motion.cpp:249-261) */
+template <typename Ctx>
+LA_HD void gStarPt(Ctx& m, int mx, int my, int point, int dist, StarState& s)
+{
+    const int cost = m.sadFpel(mx, my) + m.mvc(mx << 2, my << 2);
+    if (cost < s.bcost) { s.bcost = cost; s.bmv.x = mx; s.bmv.y = my; s.pointNr = point; s.distance = dist; }
+}
+
+template <typename Ctx>
+LA_HD void gStarPattern(Ctx& m, MV2 mvmin, MV2 mvmax, StarState& s, int earlyExitIters, int merange)
+{
+    const MV2 omv = s.bmv;
+    int saved = s.bcost, rounds = 0;
+    {
+        const int top = omv.y - 1, bottom = omv.y + 1, left = omv.x - 1, right = omv.x + 1;
+        const bool inside = top >= mvmin.y && left >= mvmin.x && right <= mvmax.x && bottom <= mvmax.y;
+        if (inside || top >= mvmin.y)    gStarPt(m, omv.x, top, 2, 1, s);
+        if (inside || left >= mvmin.x)   gStarPt(m, left, omv.y, 4, 1, s);
+        if (inside || right <= mvmax.x)  gStarPt(m, right, omv.y, 5, 1, s);
+        if (inside || bottom <= mvmax.y) gStarPt(m, omv.x, bottom, 7, 1, s);
+        if (s.bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+#pragma unroll 1
+    for (int dist = 2; dist <= 8; dist <<= 1)
+    {
+        const int h = dist >> 1;
+        const int top = omv.y - dist, bottom = omv.y + dist, left = omv.x - dist, right = omv.x + dist;
+        const int top2 = omv.y - h, bottom2 = omv.y + h, left2 = omv.x - h, right2 = omv.x + h;
+        saved = s.bcost;
+        if (top >= mvmin.y && left >= mvmin.x && right <= mvmax.x && bottom <= mvmax.y)
+        {
+            gStarPt(m, omv.x, top, 2, dist, s);
+            gStarPt(m, left2, top2, 1, h, s);
+            gStarPt(m, right2, top2, 3, h, s);
+            gStarPt(m, left, omv.y, 4, dist, s);
+            gStarPt(m, right, omv.y, 5, dist, s);
+            gStarPt(m, left2, bottom2, 6, h, s);
+            gStarPt(m, right2, bottom2, 8, h, s);
+            gStarPt(m, omv.x, bottom, 7, dist, s);
+        }
+        else
+        {
+            if (top >= mvmin.y) gStarPt(m, omv.x, top, 2, dist, s);
+            if (top2 >= mvmin.y)
+            {
+                if (left2 >= mvmin.x) gStarPt(m, left2, top2, 1, h, s);
+                if (right2 <= mvmax.x) gStarPt(m, right2, top2, 3, h, s);
+            }
+            if (left >= mvmin.x) gStarPt(m, left, omv.y, 4, dist, s);
+            if (right <= mvmax.x) gStarPt(m, right, omv.y, 5, dist, s);
+            if (bottom2 <= mvmax.y)
+            {
+                if (left2 >= mvmin.x) gStarPt(m, left2, bottom2, 6, h, s);
+                if (right2 <= mvmax.x) gStarPt(m, right2, bottom2, 8, h, s);
+            }
+            if (bottom <= mvmax.y) gStarPt(m, omv.x, bottom, 7, dist, s);
+        }
+        if (s.bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+#pragma unroll 1
+    for (int dist = 16; dist <= (int)(short)merange; dist <<= 1)
+    {
+        const int q = dist >> 2;
+        const int top = omv.y - dist, bottom = omv.y + dist, left = omv.x - dist, right = omv.x + dist;
+        saved = s.bcost;
+        const bool inside = top >= mvmin.y && left >= mvmin.x && right <= mvmax.x && bottom <= mvmax.y;
+        if (inside || top >= mvmin.y)    gStarPt(m, omv.x, top, 0, dist, s);
+        if (inside || left >= mvmin.x)   gStarPt(m, left, omv.y, 0, dist, s);
+        if (inside || right <= mvmax.x)  gStarPt(m, right, omv.y, 0, dist, s);
+        if (inside || bottom <= mvmax.y) gStarPt(m, omv.x, bottom, 0, dist, s);
+#pragma unroll 1
+        for (int index = 1; index < 4; index++)
+        {
+            const int posYT = top + q * index, posYB = bottom - q * index, posXL = omv.x - q * index, posXR = omv.x + q * index;
+            if (inside || posYT >= mvmin.y)
+            {
+                if (inside || posXL >= mvmin.x) gStarPt(m, posXL, posYT, 0, dist, s);
+                if (inside || posXR <= mvmax.x) gStarPt(m, posXR, posYT, 0, dist, s);
+            }
+            if (inside || posYB <= mvmax.y)
+            {
+                if (inside || posXL >= mvmin.x) gStarPt(m, posXL, posYB, 0, dist, s);
+                if (inside || posXR <= mvmax.x) gStarPt(m, posXR, posYB, 0, dist, s);
+            }
+        }
+        if (s.bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+}
+
+/* the two points next to point `pointNr` of a distance-1 result (motion.cpp:1166-1189) */
+template <typename Ctx>
+LA_HD void gStarTwoPoints(Ctx& m, MV2 mvmin, MV2 mvmax, StarState& s)
+{
+    const MV2 c = s.bmv;
+    const MV2 mv1 = { c.x + g_starOffsets[(s.pointNr - 1) * 2][0], c.y + g_starOffsets[(s.pointNr - 1) * 2][1] };
+    const MV2 mv2 = { c.x + g_starOffsets[(s.pointNr - 1) * 2 + 1][0], c.y + g_starOffsets[(s.pointNr - 1) * 2 + 1][1] };
+    if (gInRange(mv1, mvmin, mvmax)) gCostMv(m, mv1.x, mv1.y, s.bcost, s.bmv);
+    if (gInRange(mv2, mvmin, mvmax)) gCostMv(m, mv2.x, mv2.y, s.bcost, s.bmv);
+}
+
+template <typename Ctx>
+LA_HD void gStar(Ctx& m, MV2 mvmin, MV2 mvmax, int merange, int& bcost, MV2& bmv)
+{
+    StarState s = { bcost, bmv, 0, 0 };
+    gStarPattern(m, mvmin, mvmax, s, 3, merange);
+    bool done = false;
+    if (s.distance == 1)
+    {
+        if (s.pointNr)
+        {
+            const int saved = s.bcost;
+            gStarTwoPoints(m, mvmin, mvmax, s);
+            done = s.bcost == saved;
+        }
+        else
+            done = true;
+    }
+    if (!done)
+    {
+        if (s.distance > 5)
+        {
+            /* raster refinement over the WHOLE vector range in steps of 5 (motion.cpp:1192-1228).  Four columns at a time
+             * while they fit; the cost of the fourth is charged for the vector shifted by 3 bits instead of 2 -- the
+             * reference's typo (:1219), part of its results */
+#pragma unroll 1
+            for (int y = mvmin.y; y <= mvmax.y; y += 5)
+#pragma unroll 1
+                for (int x = mvmin.x; x <= mvmax.x; x += 5)
+                {
+                    if (x + 15 <= mvmax.x)
+                    {
+#pragma unroll 1
+                        for (int k = 0; k < 4; k++)
+                        {
+                            const int xk = x + 5 * k, sh = k == 3 ? 3 : 2;
+                            const int cost = m.sadFpel(xk, y) + m.mvc(xk << sh, y << sh);
+                            if (cost < s.bcost) { s.bcost = cost; s.bmv.x = xk; s.bmv.y = y; }
+                        }
+                        x += 15;
+                    }
+                    else
+                        gCostMv(m, x, y, s.bcost, s.bmv);
+                }
+        }
+        while (s.distance > 0)
+        {
+            s.distance = 0; s.pointNr = 0;
+            gStarPattern(m, mvmin, mvmax, s, 32, merange);
+            if (s.distance == 1)
+            {
+                if (s.pointNr) gStarTwoPoints(m, mvmin, mvmax, s);
+                break;
+            }
+        }
+    }
+    bcost = s.bcost; bmv = s.bmv;
+}
+
 template <typename Ctx>
 LA_HD int motionEstimateG(Ctx& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, int merange, int method, MV2& out)
 {
@@ -223,6 +392,8 @@ LA_HD int motionEstimateG(Ctx& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, int merange, i
     }
     else if (method == LA_UMH_SEARCH)
         hexRefine = gUmh(m, mvmin, mvmax, pmv, merange, bcost, bmv);
+    else if (method == LA_STAR_SEARCH)
+        gStar(m, mvmin, mvmax, merange, bcost, bmv);
     if (hexRefine)
     {   /* hexagon, radius 2 (motion.cpp:892-946), then the square refinement (:950-967) */
         int c0 = LA_GCOST(-2, 0), c1 = LA_GCOST(-1, 2), c2 = LA_GCOST(1, 2);

@@ -171,7 +171,7 @@ bool Lookahead::create()
     if (p.bEnableHME)
         for (int i = 0; i < 2; i++)
         {
-            if (p.hmeSearchMethod[i] < 0 || p.hmeSearchMethod[i] > 2) { fail("--hme-search: only dia, hex and umh are supported for levels 0 and 1 by the GPU lookahead"); return false; }
+            if (p.hmeSearchMethod[i] < 0 || p.hmeSearchMethod[i] > 3) { fail("--hme-search: only dia, hex, umh and star are supported for levels 0 and 1 by the GPU lookahead"); return false; }
             if (p.hmeRange[i] < 4 || p.hmeRange[i] > 256) { fail("--hme-range of levels 0 and 1 must be 4..256"); return false; }
         }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }
@@ -179,7 +179,9 @@ bool Lookahead::create()
     if (p.lookaheadDepth > LOOKAHEAD_MAX) { fail("rc-lookahead too large"); return false; }
 
     const int lowW = 8 * m_8x8Width;
-    const int half = std::min(2 * 32768, 4 * (lowW + 8 * m_8x8Height) * 2 + 4096);
+    int half = std::min(2 * 32768, 4 * (lowW + 8 * m_8x8Height) * 2 + 4096);
+    if (p.bEnableHME)   /* the star search's raster pass charges one candidate in four for the vector shifted by 3 bits (motion.cpp:1219) */
+        half = std::min(2 * 32768, std::max(half, 12 * (std::max(lowW, 8 * m_8x8Height) + 16) + 1024));
     buildMvCostTable(m_mvcost, half, p.internalBitDepth);
 
     x265cu_config cfg;
