@@ -69,7 +69,7 @@ typedef struct
                                    (lowres.cpp:378-388) on the m_4x4 block grid and feeds twice that vector to the lowres search as one
                                    more predictor (slicetype.cpp:4040-4048, 4142-4145).  The level-0 results stay on the device */
     int32_t hme_search[2];      /* x265_param::hmeSearchMethod[0..1] (level 2 is the main encoder's): X265_DIA_SEARCH (0),
-                                   X265_HEX_SEARCH (1), X265_UMH_SEARCH (2) or X265_STAR_SEARCH (3); sea / full are refused */
+                                   X265_HEX_SEARCH (1), X265_UMH_SEARCH (2), X265_STAR_SEARCH (3) or X265_FULL_SEARCH (5); X265_SEA (4) is refused */
     int32_t hme_range[2];       /* x265_param::hmeRange[0..1] */
     int32_t reserved[2];
 } x265cu_config;

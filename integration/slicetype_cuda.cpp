@@ -123,7 +123,7 @@ bool cudaLookaheadCreate(Lookahead& self)
 {
     x265_param* p = self.m_param;
     const char* why = NULL;
-    if (p->bEnableHME && (p->hmeSearchMethod[0] > X265_STAR_SEARCH || p->hmeSearchMethod[1] > X265_STAR_SEARCH)) why = "--hme-search sea / full at levels 0 and 1";
+    if (p->bEnableHME && (p->hmeSearchMethod[0] == X265_SEA || p->hmeSearchMethod[1] == X265_SEA)) why = "--hme-search sea at levels 0 and 1";
     else if (p->bHistBasedSceneCut && X265_DEPTH != 8) why = "--hist-scenecut at high bit depth";
     else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED && p->recursionSkipMode == EDGE_BASED_RSKIP) why = "--aq-mode 4/5 with --rskip 2 (the encoder reads the lookahead's full-resolution edge picture)";
     else if (p->rc.aqMode > X265_AQ_AUTO_VARIANCE_BIASED && p->bEnableFades) why = "--aq-mode 4/5 with --fades";

@@ -786,6 +786,7 @@ static const or_mv hex4[16] = { {0, -4}, {0, 4}, {-2, -3}, {2, -3}, {-4, -2}, {4
 #define OR_HEX_SEARCH 1
 #define OR_UMH_SEARCH 2
 #define OR_STAR_SEARCH 3
+#define OR_FULL_SEARCH 5
 
 /* offsets for the two-point search around a distance-1 result (motion.cpp:74-84) */
 static const or_mv star_offsets[16] = { {-1, 0}, {0, -1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {-1, -1},
@@ -1097,6 +1098,16 @@ static int motion_estimate_ex(or_me* m, or_mv mvmin, or_mv mvmax, or_mv qmvp, in
     }
     else if (method == OR_STAR_SEARCH)
         star_search(m, mvmin, mvmax, merange, &bcost, &bmv);
+    else if (method == OR_FULL_SEARCH)
+    {   /* motion.cpp:1421-1466 with ref->isHMELowres: every vector of the range cut to [-merange, merange], raster order */
+        const int r = abs(merange);
+        for (int y = imax(mvmin.y, -r); y <= imin(mvmax.y, r); y++)
+            for (int x = imax(mvmin.x, -r); x <= imin(mvmax.x, r); x++)
+            {
+                int cost = sad_fpel(m, x, y) + mvcost_q(m, x << 2, y << 2);
+                if (cost < bcost) { bcost = cost; bmv.x = x; bmv.y = y; }
+            }
+    }
     if (hexRefine)
     {
         int c0 = COSTAT(-2, 0), c1 = COSTAT(-1, 2), c2 = COSTAT(1, 2);

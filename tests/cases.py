@@ -105,6 +105,7 @@ CASES = [
     ("aq5_edge10_ragged", 10, 328, 184, 30, dict(cuts=(15,)), dict(bframes=3, lookaheadDepth=10, aqMode=5, aqStrength=1.3)),
     ("aq4_qg8_sd", 8, 640, 360, 24, dict(cuts=(11,)), dict(bframes=4, lookaheadDepth=12, aqMode=4, qgSize=8, poolThreads=16)),
     ("hme_star", 8, 960, 544, 14, dict(cuts=(7,), n_rects=8), dict(bframes=3, lookaheadDepth=8, hme=1, hmeSearch0=3, hmeSearch1=3, hmeRange0=16, hmeRange1=32)),
+    ("hme_fullhex", 8, 960, 544, 10, dict(cuts=(5,)), dict(bframes=2, lookaheadDepth=6, hme=1, hmeSearch0=5, hmeSearch1=1, hmeRange0=8, hmeRange1=16)),
     ("hme_hexstar10_pool", 10, 960, 540, 12, dict(cuts=(5,)), dict(bframes=2, lookaheadDepth=6, hme=1, hmeSearch0=1, hmeSearch1=3, hmeRange1=16, poolThreads=16)),
     # short enough to commit as a golden fixture
     ("hme_golden", 8, 960, 544, 8, dict(cuts=(4,)), dict(bframes=2, lookaheadDepth=5, hme=1)),

@@ -177,7 +177,7 @@ int x265cu_create(const x265cu_config* cfg, x265cu_ctx** out)
     if (cfg->depth != or_depth()) return X265CU_ERR_BAD_ARG;
     if (cfg->hist_stats && cfg->depth != 8) return X265CU_ERR_UNSUPPORTED;
     if (cfg->aq_mode > 3 && cfg->fade_stats) return X265CU_ERR_UNSUPPORTED;
-    if (cfg->hme && (cfg->hme_search[0] < 0 || cfg->hme_search[0] > 3 || cfg->hme_search[1] < 0 || cfg->hme_search[1] > 3)) return X265CU_ERR_UNSUPPORTED;
+    if (cfg->hme && (cfg->hme_search[0] < 0 || cfg->hme_search[0] > 5 || cfg->hme_search[0] == 4 || cfg->hme_search[1] < 0 || cfg->hme_search[1] > 5 || cfg->hme_search[1] == 4)) return X265CU_ERR_UNSUPPORTED;
     x265cu_ctx* c = new x265cu_ctx;
     c->cfg = *cfg;
     or_geom_init(&c->g, cfg->width, cfg->height, cfg->max_cu_size);

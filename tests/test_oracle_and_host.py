@@ -45,7 +45,7 @@ def test_sim_pipeline_matches_live_reference(name, pkg, synth, simdir):
     assert not bad, "\n".join(bad[:10])
 
 
-@pytest.mark.parametrize("name", ["hme_default", "hme_hexhex10", "hme_umhdia_pool_fade", "hme_star"])
+@pytest.mark.parametrize("name", ["hme_default", "hme_hexhex10", "hme_umhdia_pool_fade", "hme_star", "hme_fullhex"])
 def test_generic_search_source_on_cpu(name):
     """--hme: the source text of the product's dia / hex / umh searches (csrc/la_me_generic.cuh, what search_hme_kernel compiles)
     built for the CPU with a scalar evaluator reproduces the live reference (the warp-level evaluators are the GPU suite's job)"""
@@ -64,7 +64,7 @@ def test_hme_refusals(pkg, simdir):
     reference's two levels race on uninitialised vectors)"""
     sim = _sim(simdir, 8)
     with pytest.raises(RuntimeError, match="hme-search"):
-        pkg.Lookahead(960, 544, depth=8, lib_path=sim, bEnableHME=1, hmeSearchMethod=(5, 2))
+        pkg.Lookahead(960, 544, depth=8, lib_path=sim, bEnableHME=1, hmeSearchMethod=(4, 2))
     with pytest.raises(RuntimeError, match="lookahead slices"):
         pkg.Lookahead(1280, 720, depth=8, lib_path=sim, bEnableHME=1, poolWorkers=8, lookaheadSlices=4)
     with pytest.raises(RuntimeError, match="fades"):

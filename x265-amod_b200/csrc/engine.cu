@@ -1396,11 +1396,11 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     }
     if (cfg->hme)
     {
-        /* dia / hex / umh / star only (la_me_generic.cuh).  No cooperative slices: the reference's two levels race there (its level-1
+        /* dia / hex / umh / star / full, not sea (la_me_generic.cuh).  No cooperative slices: the reference's two levels race there (its level-1
          * slices read level-0 vectors other workers may not have written).  CTU >= 32: the level-0 margins (half the lowres
          * ones) must be whole tiles and cover what a search can reach */
         for (int i = 0; i < 2; i++)
-            if (cfg->hme_search[i] < 0 || cfg->hme_search[i] > 3 || cfg->hme_range[i] < 4 || cfg->hme_range[i] > 256) return X265CU_ERR_UNSUPPORTED;
+            if (cfg->hme_search[i] < 0 || cfg->hme_search[i] > 5 || cfg->hme_search[i] == 4 || cfg->hme_range[i] < 4 || cfg->hme_range[i] > 256) return X265CU_ERR_UNSUPPORTED;
         if (cfg->rows_per_slice > 0 || cfg->max_cu_size < 32 || cfg->width < 64 || cfg->height < 64) return X265CU_ERR_UNSUPPORTED;
     }
     if (cfg->aq_mode < 0 || cfg->aq_mode > 5 || (cfg->aq_mode > 3 && cfg->fade_stats)) return X265CU_ERR_UNSUPPORTED;

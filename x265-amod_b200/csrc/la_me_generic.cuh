@@ -1,5 +1,5 @@
 /* la_me_generic.cuh -- the integer motion searches --hme selects per level (dia / hex / umh) + the lowres subpel refinement,
- * and star; sea and full are not built), written against a small evaluator interface instead of the warp-wide lockstep of the default search (la_kernels.cuh
+ * star and full; sea is not built), written against a small evaluator interface instead of the warp-wide lockstep of the default search (la_kernels.cuh
  * motionEstimate, which stays as it is: HEX over 16 is all the lookahead runs without --hme).
  *
  * Reference semantics: MotionEstimate::motionEstimate with numCandidates == 0, subpelRefine 1, a lowres reference
@@ -30,7 +30,7 @@ namespace la {
 
 struct MV2 { int x, y; };
 
-enum { LA_DIA_SEARCH = 0, LA_HEX_SEARCH = 1, LA_UMH_SEARCH = 2, LA_STAR_SEARCH = 3 };     /* X265_DIA/HEX/UMH/STAR_SEARCH, x265.h */
+enum { LA_DIA_SEARCH = 0, LA_HEX_SEARCH = 1, LA_UMH_SEARCH = 2, LA_STAR_SEARCH = 3, LA_FULL_SEARCH = 5 };     /* X265_*_SEARCH, x265.h (4 = SEA: not built) */
 
 LA_CONST_TABLE signed char g_hex2[8][2] = { {-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0} };    /* motion.cpp:64 */
 LA_CONST_TABLE unsigned char g_mod6m1[8] = { 5, 0, 1, 2, 3, 4, 5, 0 };                                                 /* :65 */
@@ -394,6 +394,16 @@ LA_HD int motionEstimateG(Ctx& m, MV2 mvmin, MV2 mvmax, MV2 qmvp, int merange, i
         hexRefine = gUmh(m, mvmin, mvmax, pmv, merange, bcost, bmv);
     else if (method == LA_STAR_SEARCH)
         gStar(m, mvmin, mvmax, merange, bcost, bmv);
+    else if (method == LA_FULL_SEARCH)
+    {   /* exhaustive (motion.cpp:1421-1466); under --hme the rectangle is the vector range cut to +-merange around ZERO */
+        const int r = merange < 0 ? -merange : merange;
+        const int y0 = gmax(mvmin.y, -r), y1 = gmin(mvmax.y, r), x0 = gmax(mvmin.x, -r), x1 = gmin(mvmax.x, r);
+#pragma unroll 1
+        for (int y = y0; y <= y1; y++)
+#pragma unroll 1
+            for (int x = x0; x <= x1; x++)
+                gCostMv(m, x, y, bcost, bmv);
+    }
     if (hexRefine)
     {   /* hexagon, radius 2 (motion.cpp:892-946), then the square refinement (:950-967) */
         int c0 = LA_GCOST(-2, 0), c1 = LA_GCOST(-1, 2), c2 = LA_GCOST(1, 2);

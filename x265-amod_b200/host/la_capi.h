@@ -37,7 +37,7 @@ typedef struct
     int32_t bEnableTemporalSubLayers;/* x265_param::bEnableTemporalSubLayers (--temporal-layers): 0-2 */
     int32_t bHistBasedSceneCut;      /* x265_param::bHistBasedSceneCut (--hist-scenecut), 8-bit only */
     int32_t bEnableHME;              /* x265_param::bEnableHME (--hme); like the encoder, ignored below 540 lines (encoder.cpp:4400-4407) */
-    int32_t hmeSearchMethod[2];      /* x265_param::hmeSearchMethod[0..1]: dia (0), hex (1), umh (2) or star (3) */
+    int32_t hmeSearchMethod[2];      /* x265_param::hmeSearchMethod[0..1]: dia (0), hex (1), umh (2), star (3) or full (5) */
     int32_t hmeRange[2];             /* x265_param::hmeRange[0..1] */
 } x265la_param;
 

@@ -171,7 +171,7 @@ bool Lookahead::create()
     if (p.bEnableHME)
         for (int i = 0; i < 2; i++)
         {
-            if (p.hmeSearchMethod[i] < 0 || p.hmeSearchMethod[i] > 3) { fail("--hme-search: only dia, hex, umh and star are supported for levels 0 and 1 by the GPU lookahead"); return false; }
+            if (p.hmeSearchMethod[i] < 0 || p.hmeSearchMethod[i] > 5 || p.hmeSearchMethod[i] == 4) { fail("--hme-search: sea is not supported for levels 0 and 1 by the GPU lookahead (dia, hex, umh, star, full are)"); return false; }
             if (p.hmeRange[i] < 4 || p.hmeRange[i] > 256) { fail("--hme-range of levels 0 and 1 must be 4..256"); return false; }
         }
     if (p.bframes > BFRAME_MAX || p.bframes < 0) { fail("bframes out of range"); return false; }

@@ -53,7 +53,7 @@ struct LookaheadParam
                                        the cost-based test (slicetype.cpp:3057-3216) */
     int bEnableHME;      /* --hme: hierarchical motion estimation, levels 0 (1/16 resolution) and 1 (lowres) of the lookahead's searches
                             (slicetype.cpp:4040-4048, 4083-4183); level 2 is the main encoder's */
-    int hmeSearchMethod[2], hmeRange[2];    /* per level: X265_DIA/HEX/UMH/STAR_SEARCH (0..3; sea and full are refused) and range */
+    int hmeSearchMethod[2], hmeRange[2];    /* per level: X265_DIA/HEX/UMH/STAR/FULL_SEARCH (0..3, 5; sea is refused) and range */
     int bEnableFades;    /* --fades: mark the frame that ends a fade-in and code it as a keyframe (slicetype.cpp:1861-1906, 1972) */
     int lookaheadSlices;
     int maxNumReferences;
