@@ -219,6 +219,9 @@ FULL_SIZE = [
     ("cfg3_1080p_slower_weightp", 8, 1920, 1080, 90, dict(cuts=(13, 37, 64), fades=[(20, 12, 0.35), (70, 10, 1.0)], flashes=[(50, 1)], n_rects=6, seed=3),
      dict(bframes=8, lookaheadDepth=40, poolThreads=16, weightp=1)),
     # --hme at a BASELINE size: level-0 (hex) and level-1 (umh) vectors and costs of every published search included
+    # aq-mode 4 (edge map of the full-res luma) + three temporal layers (random-access mini-GOPs of 4, split at the cut) at a BASELINE size
+    ("cfg1_1080p_8bit_aq4_tl3", 8, 1920, 1080, 38, dict(cuts=(18,), n_rects=6, seed=5),
+     dict(bframes=3, lookaheadDepth=20, bFrameAdaptive=0, temporalLayers=3, aqMode=4, poolThreads=16)),
     ("cfg1_1080p_8bit_hme", 8, 1920, 1080, 40, dict(cuts=(21,), n_rects=6, seed=1), dict(bframes=4, lookaheadDepth=20, poolThreads=16, hme=1)),
 ]
 # config 4 (7680x4320, rc-lookahead 80): against the C oracle through the sim engine on a dozen frames
