@@ -120,7 +120,7 @@ ESTIMATE = ["base8", "base10", "vbv", "radl2", "nocutree", "plain", "intrarefres
 PIR = {"intrarefresh": (2, 3)}
 
 # subset small enough to commit as golden fixtures and to run in the quick CPU suite
-GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob", "slices_golden", "hme_golden"]
+GOLDEN = ["base8", "base10", "pool16", "fade8", "static_noise", "ragged", "nob", "slices_golden", "hme_golden", "aq4_edge", "temporal3"]
 
 REF2LA = dict(bframes="bframes", lookaheadDepth="lookaheadDepth", bFrameAdaptive="bFrameAdaptive", bBPyramid="bBPyramid",
               scenecutThreshold="scenecutThreshold", keyframeMax="keyframeMax", keyframeMin="keyframeMin",
