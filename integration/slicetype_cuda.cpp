@@ -134,7 +134,6 @@ bool cudaLookaheadCreate(Lookahead& self)
     else if (p->bDynamicRefine) why = "--dynamic-refine";
     else if (p->rc.bStatRead && p->rc.cuTree) why = "2-pass cutree";
     else if (p->internalCsp != X265_CSP_I420 && p->internalCsp != X265_CSP_I400) why = "chroma formats other than 4:2:0 / 4:0:0";
-    else if (X265_DEPTH > 10) why = "12-bit";
     if (why)
     {
         x265_log(p, X265_LOG_ERROR, "ENABLE_CUDA lookahead: %s is not supported by the GPU path (no CPU fallback)\n", why);

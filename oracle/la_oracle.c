@@ -252,7 +252,9 @@ static void edge_filter(const or_pixel* y, int strideY, int W, int H, or_pixel* 
             edge[(size_t)r * W + c] = s[0];
             theta[(size_t)r * W + c] = 0;
         }
-    const float threshold = (float)OR_MAXV;      /* EDGE_THRESHOLD, slicetype.h:64-69 */
+    /* EDGE_THRESHOLD (slicetype.h:64-69): 255 for 8-bit, 1023 for EVERY high bit depth; it is also the white sample */
+    const int white = OR_DEPTH > 8 ? 1023 : 255;
+    const float threshold = (float)white;
     for (int r = 1; r < H - 1; r++)
         for (int c = 1; c < W - 1; c++)
         {
@@ -264,7 +266,7 @@ static void edge_filter(const or_pixel* y, int strideY, int W, int H, or_pixel* 
             float th = (float)((radians * 180) / 3.14159265);        /* PI, slicetype.h:70 */
             if (th < 0) th = 180 + th;
             theta[(size_t)r * W + c] = (or_pixel)th;
-            edge[(size_t)r * W + c] = (or_pixel)(mag >= threshold ? OR_MAXV : 0);
+            edge[(size_t)r * W + c] = (or_pixel)(mag >= threshold ? white : 0);
         }
     free(gauss);
 }

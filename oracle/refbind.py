@@ -55,7 +55,7 @@ DEFAULTS = dict(fpsNum=30, fpsDenom=1, bframes=4, lookaheadDepth=20, bFrameAdapt
 
 
 def lib_path(depth):
-    return os.path.join(HERE, "_ref", "libx265ref%d.so" % (8 if depth == 8 else 10))
+    return os.path.join(HERE, "_ref", "libx265ref%d.so" % (depth if depth in (8, 10, 12) else 10))
 
 
 def available(depth=8):
@@ -66,7 +66,7 @@ _libs = {}
 
 
 def load(depth):
-    key = 8 if depth == 8 else 10
+    key = depth if depth in (8, 10, 12) else 10
     if key in _libs:
         return _libs[key]
     lib = C.CDLL(lib_path(depth), mode=C.RTLD_LOCAL)

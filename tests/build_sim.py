@@ -30,7 +30,7 @@ def build(force=False):
     host_hdrs = [os.path.join(HOST, f) for f in ("lookahead.h", "la_capi.h")] + [os.path.join(ROOT, "include", "x265cu.h"),
                  os.path.join(ROOT, "x265-amod_b200", "csrc", "la_me_generic.cuh")]
     sim = os.path.join(ROOT, "tests", "simengine", "simengine.cpp")
-    for d in (8, 10):
+    for d in (8, 10, 12):
         lib = os.path.join(OUT, "liboracle%d.so" % d)
         if force or _stale(lib, [oc, oh]):
             _run(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-DOR_DEPTH=%d" % d, "-o", lib, oc, "-lm"])

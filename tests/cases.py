@@ -107,6 +107,10 @@ CASES = [
     ("hme_star", 8, 960, 544, 14, dict(cuts=(7,), n_rects=8), dict(bframes=3, lookaheadDepth=8, hme=1, hmeSearch0=3, hmeSearch1=3, hmeRange0=16, hmeRange1=32)),
     ("hme_fullhex", 8, 960, 544, 10, dict(cuts=(5,)), dict(bframes=2, lookaheadDepth=6, hme=1, hmeSearch0=5, hmeSearch1=1, hmeRange0=8, hmeRange1=16)),
     ("hme_hexstar10_pool", 10, 960, 540, 12, dict(cuts=(5,)), dict(bframes=2, lookaheadDepth=6, hme=1, hmeSearch0=1, hmeSearch1=3, hmeRange1=16, poolThreads=16)),
+    # 12-bit (main12): 16-bit samples whose SATD coefficients no longer fit the packed 16-bit lanes of the 8 / 10-bit kernels
+    ("base12", 12, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10)),
+    ("fade12_pool_weightb", 12, 320, 192, 50, dict(cuts=(), fades=[(15, 12, 0.3), (35, 9, 1.0)]), dict(bframes=4, lookaheadDepth=12, poolThreads=16, weightb=1, aqMode=3)),
+    ("hme12_aq4", 12, 960, 544, 12, dict(cuts=(6,)), dict(bframes=2, lookaheadDepth=6, hme=1, aqMode=4)),
     # short enough to commit as a golden fixture
     ("hme_golden", 8, 960, 544, 8, dict(cuts=(4,)), dict(bframes=2, lookaheadDepth=5, hme=1)),
     ("vbv_nocutree", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0, vbvBufferSize=2000, vbvMaxBitrate=2000, bitrate=1500)),

@@ -35,7 +35,7 @@ def _as_ref_layout(frames):
     return frames
 
 
-@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("depth", [8, 10, 12])
 def test_block_metrics_vs_oracle(depth, pkg, simdir):
     """T1: SAD/SATD kernels on the reference's pixelharness recipe (random / min / max buffers)"""
     la = pkg.Lookahead(320, 192, depth=depth)
@@ -59,7 +59,7 @@ def test_block_metrics_vs_oracle(depth, pkg, simdir):
     la.close()
 
 
-@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("depth", [8, 10, 12])
 def test_tiled_motion_compensation_vs_oracle(depth, pkg, synth, simdir):
     """T1: the tiled row fetch + lowresMC + SAD/SATD (lowresQPelCost, lowres.h:98-124) for random blocks and
     quarter-pel vectors, including vectors that reach into the plane margins"""

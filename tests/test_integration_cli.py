@@ -27,7 +27,7 @@ def test_integration_patch_and_binaries():
         assert hook in patch, hook
     if not os.path.isdir("/root/reference/source"):
         pytest.skip("reference sources not on this box")
-    for depth in (8, 10):
+    for depth in (8, 10, 12):
         assert os.path.exists(_bin("cpu", depth)) and os.path.exists(_bin("cuda", depth))
         needed = subprocess.run(["readelf", "-d", _bin("cuda", depth)], stdout=subprocess.PIPE, text=True).stdout
         assert "libx265la.so" in needed      # which in turn needs libx265cu.so, the CUDA engine
@@ -80,6 +80,8 @@ CLI_CASES = [
     ("temporal_layers_3", 8, 640, 360, 46, dict(cuts=(14, 30)), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--temporal-layers", "3"]),
     ("temporal_layers_5", 10, 640, 360, 70, dict(cuts=(13, 41, 52)),
      ["--preset", "medium", "--pools", "16", "--lookahead-slices", "0", "--rc-lookahead", "35", "--temporal-layers", "5"]),
+    # main12: the 12-bit build of the encoder (16-bit samples, 32-bit SATD butterflies on the GPU)
+    ("main12_weightb", 12, 640, 360, 40, dict(cuts=(), fades=[(12, 10, 0.3)]), ["--preset", "medium", "--pools", "4", "--lookahead-slices", "0", "--weightb"]),
     # --lookahead-threads: the lookahead gets a pool of its own, whose size selects the reference's batch modes
     ("lookahead_threads", 8, 640, 360, 50, dict(cuts=(23,)), ["--preset", "medium", "--pools", "8", "--lookahead-threads", "2", "--lookahead-slices", "0"]),
 ]

@@ -1335,7 +1335,7 @@ int mcMetricsT(x265cu_ctx* c, int fencSlot, int refSlot, const int32_t* cuIdx, c
     return X265CU_OK;
 }
 
-#define DISPATCH(fn, ...) (c->bpp == 1 ? fn<uint8_t>(__VA_ARGS__) : fn<uint16_t>(__VA_ARGS__))
+#define DISPATCH(fn, ...) (c->bpp == 1 ? fn<uint8_t>(__VA_ARGS__) : c->cfg.depth > 10 ? fn<px12>(__VA_ARGS__) : fn<uint16_t>(__VA_ARGS__))
 
 } // namespace
 
@@ -1380,7 +1380,7 @@ static int createImpl(const x265cu_config* cfg, x265cu_ctx** out)
     if (!cfg || !out) return X265CU_ERR_BAD_ARG;
     *out = NULL;
     if (cfg->qg_size != 8 && cfg->qg_size != 16 && cfg->qg_size != 32 && cfg->qg_size != 64) return X265CU_ERR_BAD_ARG;
-    if (cfg->depth != 8 && cfg->depth != 10) return X265CU_ERR_UNSUPPORTED;     /* SWAR SATD range, la_device.cuh */
+    if (cfg->depth != 8 && cfg->depth != 10 && cfg->depth != 12) return X265CU_ERR_UNSUPPORTED;     /* 12-bit: la_device.cuh px12 */
     if (cfg->hist_stats && (cfg->depth != 8 || cfg->width < 64 || cfg->height < 64))
         return X265CU_ERR_UNSUPPORTED;      /* the reference indexes 256 histogram bins with the sample value */
     if (cfg->fade_stats)

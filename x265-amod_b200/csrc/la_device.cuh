@@ -59,6 +59,25 @@ template <typename P> struct Row;
 template <> struct Row<uint8_t>  { uint32_t v[2]; };
 template <> struct Row<uint16_t> { uint32_t v[4]; };
 
+/* 12-bit samples.  Same storage as the 10-bit ones (uint16_t) but a type of its own, so that every kernel template gets a separate
+ * instantiation for them and the one primitive that differs -- the SATD, whose 4x4 Hadamard coefficients reach 16 * 4095 and no
+ * longer fit the packed signed 16-bit lanes of the 8 / 10-bit version -- can be selected by type (groupSatdRows<px12> below)
+ * without a run-time branch in the 8 / 10-bit kernels.  Everything else (loads, SAD, averaging, packing) is the uint16_t code. */
+struct px12
+{
+    uint16_t v;
+    px12() = default;
+    __host__ __device__ __forceinline__ px12(int x) : v((uint16_t)x) {}
+    __host__ __device__ __forceinline__ operator int() const { return v; }
+};
+using ::__ldg;
+__device__ __forceinline__ px12 __ldg(const px12* p) { return px12((int)::__ldg((const uint16_t*)p)); }
+template <> struct Row<px12> : Row<uint16_t>
+{
+    __device__ __forceinline__ Row() {}
+    __device__ __forceinline__ Row(const Row<uint16_t>& b) : Row<uint16_t>(b) {}
+};
+
 /* 8 samples of row Y starting at column X of a tiled plane: two aligned vector loads + funnel shift */
 __device__ __forceinline__ Row<uint8_t> loadRowT(const uint8_t* plane, int tpr, int X, int Y)
 {
@@ -114,6 +133,9 @@ __device__ __forceinline__ Row<uint16_t> loadRowAligned(const uint16_t* plane, i
     return r;
 }
 
+__device__ __forceinline__ Row<px12> loadRowT(const px12* plane, int tpr, int X, int Y) { return loadRowT((const uint16_t*)plane, tpr, X, Y); }
+__device__ __forceinline__ Row<px12> loadRowAligned(const px12* plane, int tpr, int X, int Y) { return loadRowAligned((const uint16_t*)plane, tpr, X, Y); }
+
 /* pitched (ordinary) memory: 8 samples at an arbitrary sample address (used by the unit-test kernel) */
 __device__ __forceinline__ Row<uint8_t> loadRowPitched(const uint8_t* p)
 {
@@ -129,6 +151,8 @@ __device__ __forceinline__ Row<uint16_t> loadRowPitched(const uint16_t* p)
     for (int i = 0; i < 8; i++) r.v[i >> 1] |= (uint32_t)p[i] << ((i & 1) * 16);
     return r;
 }
+
+__device__ __forceinline__ Row<px12> loadRowPitched(const px12* p) { return loadRowPitched((const uint16_t*)p); }
 
 /* (a + b + 1) >> 1 per sample: pixelavg_pp */
 __device__ __forceinline__ Row<uint8_t> avgRow(const Row<uint8_t>& a, const Row<uint8_t>& b)
@@ -301,6 +325,59 @@ __device__ __forceinline__ int groupSatdHM(const RowH& a, const RowH& b, unsigne
     return (s >> 1) + (__shfl_xor_sync(mask, s, 4) >> 1);
 }
 
+/* ---- 12-bit SATD: the same two 8x4 SATDs with every butterfly in 32-bit integers (|d| <= 4095, coefficients up to 65520) ---- */
+__device__ __forceinline__ void hadamardRowWide(const int d[8], int h[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; k += 4)
+    {
+        const int a0 = d[k] + d[k + 1], a1 = d[k] - d[k + 1], a2 = d[k + 2] + d[k + 3], a3 = d[k + 2] - d[k + 3];
+        h[k] = a0 + a2; h[k + 1] = a1 + a3; h[k + 2] = a0 - a2; h[k + 3] = a1 - a3;
+    }
+}
+/* 8 lanes per block, lane r holds row r (groupSatdH / groupSatdHM for wide samples); `mask` names the lanes taking part */
+__device__ __forceinline__ int groupSatdWide(const int d[8], unsigned mask)
+{
+    int h[8];
+    hadamardRowWide(d, h);
+    const bool odd1 = threadIdx.x & 1, odd2 = threadIdx.x & 2;
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        int t = __shfl_xor_sync(mask, h[i], 1);
+        int q = odd1 ? t - h[i] : h[i] + t;
+        t = __shfl_xor_sync(mask, q, 2);
+        q = odd2 ? t - q : q + t;
+        sum += abs(q);
+    }
+    int s = sum;
+    s += __shfl_xor_sync(mask, s, 1);
+    s += __shfl_xor_sync(mask, s, 2);
+    return (s >> 1) + (__shfl_xor_sync(mask, s, 4) >> 1);
+}
+template <>
+__device__ __forceinline__ int groupSatdRows<px12>(const Row<px12>& a, const Row<px12>& b)
+{
+    int d[8];
+    diffRow(a, b, d);
+    return groupSatdWide(d, LA_FULL);
+}
+
+/* the 8-lane SATD with an explicit lane mask, by sample type (the --hme search kernel) */
+template <typename P>
+__device__ __forceinline__ int groupSatdRowsM(const Row<P>& a, const Row<P>& b, unsigned mask)
+{
+    return groupSatdHM(toH(a), toH(b), mask);
+}
+template <>
+__device__ __forceinline__ int groupSatdRowsM<px12>(const Row<px12>& a, const Row<px12>& b, unsigned mask)
+{
+    int d[8];
+    diffRow(a, b, d);
+    return groupSatdWide(d, mask);
+}
+
 /* ---- the same primitives for the FOUR-lanes-per-block decomposition of the motion search: lane l of a 4-lane group owns
  * rows 2l and 2l+1 of the 8x8 block, a warp works on 8 blocks.  Everything that is uniform inside a group (addresses, mv
  * costs, comparisons, the search's control flow) is then executed once per 4 lanes instead of once per 8, and the first
@@ -366,6 +443,28 @@ template <typename P>
 __device__ __forceinline__ int group4SatdRows(const Row<P>& fa, const Row<P>& fb, const Row<P>& pa, const Row<P>& pb)
 {
     return group4SatdH(toH(fa), toH(pa), toH(fb), toH(pb));
+}
+/* 12-bit: 32-bit butterflies (see groupSatdWide); rows 2l / 2l+1 pair inside the lane, then one shuffle stage */
+template <>
+__device__ __forceinline__ int group4SatdRows<px12>(const Row<px12>& fa, const Row<px12>& fb, const Row<px12>& pa, const Row<px12>& pb)
+{
+    int d0[8], d1[8], h0[8], h1[8];
+    diffRow(fa, pa, d0);
+    diffRow(fb, pb, d1);
+    hadamardRowWide(d0, h0);
+    hadamardRowWide(d1, h1);
+    const bool odd = threadIdx.x & 1;
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        const int s = h0[i] + h1[i], d = h0[i] - h1[i];
+        const int ts = __shfl_xor_sync(LA_FULL, s, 1), td = __shfl_xor_sync(LA_FULL, d, 1);
+        sum += abs(odd ? ts - s : s + ts) + abs(odd ? td - d : d + td);
+    }
+    int t = sum;
+    t += __shfl_xor_sync(LA_FULL, t, 1);
+    return (t >> 1) + (__shfl_xor_sync(LA_FULL, t, 2) >> 1);
 }
 
 /* the four tiled half-pel planes of one frame and the origin of the group's block in buffer coordinates */

@@ -48,6 +48,7 @@ struct CostResultDev            /* mirrors x265cu_cost_result */
 template <typename P> struct Vec4;
 template <> struct Vec4<uint8_t>  { typedef uchar4 T; };
 template <> struct Vec4<uint16_t> { typedef ushort4 T; };
+template <> struct Vec4<px12>     { typedef ushort4 T; };
 
 #define LA_LR_TILES 8
 #define LA_LR_ROW_SAMPLES 144           /* 129 needed; 144 samples = 144 / 288 bytes, a multiple of 16 for both sample sizes */
@@ -60,7 +61,10 @@ __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint32_t avgPacked(uint32_t a, uint32_t b, uint8_t)  { return __vavgu4(a, b); }
 /* 16-bit samples below 2^15: the two halves cannot carry into each other */
 __device__ __forceinline__ uint32_t avgPacked(uint32_t a, uint32_t b, uint16_t) { return ((a + b + 0x00010001u) >> 1) & 0x7fff7fffu; }
+__device__ __forceinline__ uint32_t avgPacked(uint32_t a, uint32_t b, px12) { return ((a + b + 0x00010001u) >> 1) & 0x7fff7fffu; }
 
+__device__ __forceinline__ void sumSqr8s(const uint16_t* p, unsigned& sum, unsigned& sqr);
+__device__ __forceinline__ void sumSqr8s(const px12* p, unsigned& sum, unsigned& sqr) { sumSqr8s((const uint16_t*)p, sum, sqr); }
 /* sum / sum of squares of 8 staged samples at p (16-byte aligned for 16-bit samples, 8-byte for 8-bit) */
 __device__ __forceinline__ void sumSqr8s(const uint8_t* p, unsigned& sum, unsigned& sqr)
 {
@@ -480,8 +484,8 @@ __global__ void __launch_bounds__(256) aq_edge_kernel(Geom g, const P* __restric
             const int (*p)[19] = (const int (*)[19])&s_g[ty][tx];      /* p[1][1] is the sample itself */
             const int gH = -3 * p[0][0] + 3 * p[0][2] - 10 * p[1][0] + 10 * p[1][2] - 3 * p[2][0] + 3 * p[2][2];
             const int gV = -3 * p[0][0] - 10 * p[0][1] - 3 * p[0][2] + 3 * p[2][0] + 10 * p[2][1] + 3 * p[2][2];
-            const int maxv = (1 << g.depth) - 1;
-            /* |g| <= 32 * 1023: the sum of squares fits 64 bits trivially; float rounding cannot move it across maxv^2 < 2^24 */
+            const int maxv = g.depth > 8 ? 1023 : 255;     /* EDGE_THRESHOLD (slicetype.h:64-69): 1023 for every high bit depth */
+            /* |g| <= 32 * 4095: the sum of squares fits 64 bits trivially; float rounding cannot move it across maxv^2 < 2^24 */
             e = ((long long)gH * gH + (long long)gV * gV >= (long long)maxv * maxv) ? (unsigned)maxv : 0u;
             const float radians = (float)atan2((double)gV, (double)gH);
             float theta = (float)__ddiv_rn(__dmul_rn((double)radians, 180.0), 3.14159265);
@@ -1715,7 +1719,7 @@ struct MeCtxG
         return avgRow(A, row(hB, X0 + (qx2 >> 2), Y0 + (qy2 >> 2) + r));
     }
     __device__ __forceinline__ int qpelSad(int qx, int qy) const { return groupSumM(sadRow(fenc, mc(qx, qy)), mask); }
-    __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return groupSatdHM(toH(fenc), toH(mc(qx, qy)), mask); }
+    __device__ __forceinline__ int qpelSatd(int qx, int qy) const { return groupSatdRowsM<P>(fenc, mc(qx, qy), mask); }
 };
 
 template <typename P>
