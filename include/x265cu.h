@@ -31,7 +31,7 @@ extern "C" {
 #define X265CU_ERR_BAD_ARG     -2
 #define X265CU_ERR_NO_MEMORY   -3
 #define X265CU_ERR_CUDA        -4   /* a CUDA call or kernel failed; see x265cu_last_error */
-#define X265CU_ERR_UNSUPPORTED -5   /* configuration outside the hot path (12-bit, star / full search under --hme, ...) */
+#define X265CU_ERR_UNSUPPORTED -5   /* configuration outside the hot path (sea search under --hme, --fades with aq-mode 4 / 5, ...) */
 
 typedef struct x265cu_ctx x265cu_ctx;
 
@@ -40,7 +40,7 @@ typedef struct x265cu_ctx x265cu_ctx;
 typedef struct
 {
     int32_t width, height;      /* x265_param::sourceWidth/Height after Encoder::configure padding */
-    int32_t depth;              /* X265_DEPTH: 8, 10 or 12 */
+    int32_t depth;              /* X265_DEPTH: 8, 10 or 12 (planes are uint8_t for 8, uint16_t otherwise) */
     int32_t max_cu_size;        /* x265_param::maxCUSize (plane margins, picyuv.cpp:87-88) */
     int32_t bframes;            /* x265_param::bframes; per-frame arrays are (bframes+2) wide */
     int32_t max_slots;          /* frame slots resident in HBM */
