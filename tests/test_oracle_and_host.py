@@ -69,8 +69,10 @@ def test_hme_refusals(pkg, simdir):
         pkg.Lookahead(1280, 720, depth=8, lib_path=sim, bEnableHME=1, poolWorkers=8, lookaheadSlices=4)
     with pytest.raises(RuntimeError, match="fades"):
         pkg.Lookahead(320, 192, depth=8, lib_path=sim, aqMode=4, bEnableFades=1)
-    with pytest.raises(RuntimeError, match="temporal-layers"):      # Encoder::configure would have set bframes 7 and b-adapt 0
-        pkg.Lookahead(320, 192, depth=8, lib_path=sim, bEnableTemporalSubLayers=4, bframes=4)
+    # like Encoder::configure (encoder.cpp:3914-3943) the C surface fixes bframes 7 / b-adapt 0 for four temporal layers
+    la = pkg.Lookahead(320, 192, depth=8, lib_path=sim, bEnableTemporalSubLayers=4, bframes=4)
+    assert la.geom.nb == 9
+    la.close()
     # below 540 lines the encoder itself turns --hme off (encoder.cpp:4400-4407): accepted, and plain searches run
     pkg.Lookahead(320, 192, depth=8, lib_path=sim, bEnableHME=1).close()
 

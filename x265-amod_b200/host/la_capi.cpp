@@ -59,6 +59,16 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
      * (encoder.cpp:3511-3516,3730-3753): cuTree needs AQ; strength 0 without cuTree disables AQ */
     if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }
     if (p.rc.aqStrength == 0 && p.rc.cuTree == 0) p.rc.aqMode = 0;
+    /* temporal layers (encoder.cpp:3914-3943): 1 is not a mode, more than 5 become 5, 3..5 fix the mini-GOP and turn b-adapt off */
+    if (p.bEnableTemporalSubLayers > 2 && !p.bframes) p.bEnableTemporalSubLayers = 0;
+    if (p.bEnableTemporalSubLayers == 1) p.bEnableTemporalSubLayers = 0;
+    if (p.bEnableTemporalSubLayers > 5) p.bEnableTemporalSubLayers = 5;
+    if (p.bEnableTemporalSubLayers > 2)
+    {
+        static const int tlBframes[6] = { 0, 0, 0, 3, 7, 15 };
+        p.bframes = tlBframes[p.bEnableTemporalSubLayers];
+        p.bFrameAdaptive = 0;
+    }
     if (!p.bframes) p.bBPyramid = 0;
     if (p.bIntraRefresh)        /* encoder.cpp:3761-3779 */
     {
