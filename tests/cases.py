@@ -13,6 +13,14 @@ CASES = [
     ("badapt0", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=4, lookaheadDepth=12, bFrameAdaptive=0)),
     ("nocutree", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0)),
     ("plain", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, cuTree=0, aqMode=0, weightp=0)),
+    # aq-mode 0 without cuTree but with weightp: the qp arrays exist (weightp needs the pixel sums) and nothing ever writes them, so
+    # invQscaleFactor stays 0 and every AQ-scaled cost (costEstAq, rowSatds) is 0 in the reference (slicetype.cpp:487-511, 4226-4229)
+    ("aq0_weightp", 8, 320, 192, 40, dict(cuts=(20,), fades=[(5, 8, 0.3)]), dict(bframes=3, lookaheadDepth=10, cuTree=0, aqMode=0, weightp=1)),
+    ("aq0_strength0_weightb10", 10, 328, 184, 30, dict(cuts=(14,)), dict(bframes=4, lookaheadDepth=12, cuTree=0, aqMode=2, aqStrength=0.0, weightp=0, weightb=1, qgSize=16)),
+    # rc-lookahead barely above bframes with weightp: a frame is speculated against references the decisions have already passed and
+    # released before the assumed weights are settled (found by tools/fuzz_host_vs_reference.py)
+    ("shallow_la_weightp", 8, 256, 144, 36, dict(cuts=(), fades=[(6, 10, 0.3)]), dict(bframes=4, lookaheadDepth=5, weightp=1, bFrameBias=30)),
+    ("shallow_la_b7_nopyramid10", 10, 256, 144, 40, dict(cuts=(19,)), dict(bframes=7, lookaheadDepth=9, bBPyramid=0, weightp=1, weightb=1, keyframeMax=25, poolThreads=2)),
     ("aq1", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, aqMode=1)),
     ("aq3", 10, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, aqMode=3)),
     ("closedgop", 8, 320, 192, 40, dict(cuts=(20,)), dict(bframes=3, lookaheadDepth=10, bBPyramid=0, bOpenGOP=0, keyframeMax=24, keyframeMin=2)),

@@ -230,6 +230,7 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
 {
     SimSlot& s = c->slots[slot];
     const or_geom& g = c->g;
+    if (c->cfg.hist_stats && (!u || !v)) return X265CU_ERR_BAD_ARG;     /* as the engine: the statistics read chroma */
     const int W = g.picW, H = g.picH, CW = (W + 1) / 2, CH = (H + 1) / 2;
     s.y.resize((size_t)W * H);
     for (int r = 0; r < H; r++) memcpy(&s.y[(size_t)r * W], (const or_pixel*)y + (size_t)r * sy, W * sizeof(or_pixel));
@@ -254,7 +255,9 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     /* the qp-offset arrays are allocated zeroed once per Lowres in the reference (lowres.cpp:98-106) and entries the
      * running AQ index never reaches stay zero */
     const size_t nAq = (size_t)c->geom.ncu_full + 2 * g.bw + 2 + (g.qg8 ? ((g.picW + 7) / 8) * ((g.picH + 7) / 8) : 0);
-    s.intraCost.assign(ncu, 0); s.invQ.assign(nAq, g.qg8 ? 0 : 256); s.invQ8.assign(ncu, 256); s.intraMode.assign(ncu, 0);
+    /* (with aq-mode 0 but weightp on, the arrays exist and nothing ever writes them: invQscaleFactor stays 0 and every AQ-scaled
+     * cost is 0 in the reference, slicetype.cpp:487-511, 4226-4229) */
+    s.intraCost.assign(ncu, 0); s.invQ.assign(nAq, 0); s.invQ8.assign(ncu, g.qg8 && c->cfg.aq_mode ? 256 : 0); s.intraMode.assign(ncu, 0);
     s.lowresCosts00.assign(ncu, 0); s.rowSatds00.assign(g.bh, 0); s.propagate.assign(ncu, 0);
     s.qpAq.assign(nAq, 0.0); s.qpCuTree.assign(nAq, 0.0);
     const int nmv = c->geom.n_mv_stores, ncs = c->geom.n_cost_stores;

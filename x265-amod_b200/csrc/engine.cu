@@ -1891,6 +1891,12 @@ int x265cu_frame_upload(x265cu_ctx* c, int32_t slot, const void* y, const void* 
     DeviceScope deviceScope(c);
     flushCutree(c);
     if (!c || !slotOk(c, slot) || !y) return X265CU_ERR_BAD_ARG;
+    if (c->cfg.hist_stats && (!u || !v))
+    {
+        /* --hist-scenecut reads the chroma planes (slicetype.cpp:1560-1640); on a 4:0:0 picture the reference dereferences NULL there */
+        snprintf(c->err, sizeof(c->err), "hist-scenecut statistics need chroma planes (4:0:0 picture)");
+        return X265CU_ERR_BAD_ARG;
+    }
     return DISPATCH(uploadT, c, slot, y, u, v, sy, sc);
 }
 

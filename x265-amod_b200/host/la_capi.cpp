@@ -59,6 +59,9 @@ void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
      * (encoder.cpp:3511-3516,3730-3753): cuTree needs AQ; strength 0 without cuTree disables AQ */
     if (p.rc.aqMode == 0 && p.rc.cuTree) { p.rc.aqMode = 1; p.rc.aqStrength = 0.0; }
     if (p.rc.aqStrength == 0 && p.rc.cuTree == 0) p.rc.aqMode = 0;
+    /* without AQ and VBV the quantisation group is the CTU (encoder.cpp:4108-4123) */
+    if (!(p.rc.aqMode || (p.rc.vbvBufferSize > 0 && p.rc.vbvMaxBitrate > 0))) p.rc.qgSize = p.maxCUSize;
+    else if (p.rc.qgSize > p.maxCUSize) p.rc.qgSize = p.maxCUSize;
     /* temporal layers (encoder.cpp:3914-3943): 1 is not a mode, more than 5 become 5, 3..5 fix the mini-GOP and turn b-adapt off */
     if (p.bEnableTemporalSubLayers > 2 && !p.bframes) p.bEnableTemporalSubLayers = 0;
     if (p.bEnableTemporalSubLayers == 1) p.bEnableTemporalSubLayers = 0;
