@@ -45,14 +45,17 @@ void or_geom_init(or_geom* g, int picW, int picH, int maxCUSize)
  * (common/common.h:209-213) -> 1, 16, 256 for 8/10/12 bit */
 int or_lookahead_lambda(void) { return 1 << (2 * (OR_DEPTH - 8)); }
 
-/* encoder/bitcost.cpp:46-54 (cost row) and :98-113 (bit sizes, float arithmetic) */
+/* encoder/bitcost.cpp:46-54 (cost row) and :98-113 (bit sizes: the C `log` of a float argument, i.e. double arithmetic up to
+ * the store into the float array) */
 void or_build_mvcost(uint16_t* table, int half)
 {
     double lambda = (double)or_lookahead_lambda();
-    float log2_2 = 2.0f / logf(2.0f);
+    float log2_2 = (float)(2.0f / log((double)2.0f));
     for (int i = 0; i <= half; i++)
     {
-        float bits = i ? logf((float)(i + 1)) * log2_2 + 1.718f : 0.718f;
+        float argument = (float)(i + 1);
+        double value = log((double)argument) * log2_2 + 1.718f;
+        float bits = i ? (float)value : 0.718f;
         double c = bits * lambda + 0.5f;
         if (c > (double)((1 << 15) - 1)) c = (double)((1 << 15) - 1);
         table[half + i] = table[half - i] = (uint16_t)c;

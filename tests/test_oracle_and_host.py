@@ -110,22 +110,28 @@ def test_coverage_of_special_paths(pkg, synth, simdir):
     assert 2 in types, "scene cut not detected"
 
 
-@pytest.mark.parametrize("depth", [8, 10])
-def test_mvcost_table_and_lambda(depth):
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_mvcost_table_and_lambda(depth, pkg, simdir):
+    """BitCost's row for the lookahead QP: the oracle's AND the product's table (x265la_mvcost_table) against the reference's own, over
+    the whole index range a 4320p search can reach (at 12 bits, lambda 256, a float-logf pipeline is off by one in 15 entries)"""
     if not refbind.available(depth):
         pytest.skip("oracle/_ref not built")
     import ctypes as C, os
     lib = C.CDLL(os.path.join(os.path.dirname(__file__), "_build", "liboracle%d.so" % depth))
-    n = 20000
+    n = 60000
     qp, ref = refbind.mvcost_table(depth, n)
     tab = np.zeros(2 * n + 1, np.uint16)
     lib.or_build_mvcost(tab.ctypes.data_as(C.c_void_p), n)
     assert np.array_equal(tab, ref)
+    host = C.CDLL(_sim(simdir, depth))      # the product's host library (linked against the sim engine here)
+    tab2 = np.zeros(2 * n + 1, np.uint16)
+    host.x265la_mvcost_table(depth, n, tab2.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(tab2, ref)
     assert lib.or_lookahead_lambda() == refbind.load(depth).ref_lookahead_lambda()
     assert qp == 12 + 6 * (depth - 8)
 
 
-@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("depth", [8, 10, 12])
 def test_oracle_block_primitives_vs_reference(depth, simdir):
     """the reference's own pixelharness recipe: random, all-min and all-max buffers"""
     if not refbind.available(depth):

@@ -28,6 +28,13 @@ void x265la_param_default(x265la_param* q)
     for (int i = 0; i < 2; i++) { q->hmeSearchMethod[i] = p.hmeSearchMethod[i]; q->hmeRange[i] = p.hmeRange[i]; }
 }
 
+void x265la_mvcost_table(int32_t depth, int32_t half, uint16_t* table)
+{
+    std::vector<uint16_t> t;
+    buildMvCostTable(t, half, depth);
+    memcpy(table, &t[0], t.size() * sizeof(uint16_t));
+}
+
 void* x265la_open(const x265la_param* q, char* err, int32_t errLen)
 {
     LookaheadParam p;

@@ -114,6 +114,9 @@ int   x265la_frame_hist(void* la, void* frame, int32_t* variance /* 3 */, int32_
 int   x265la_frame_weights(void* la, void* frame, int32_t* state, int32_t* scale, int32_t* denom, int32_t* offset /* nb each */);
 /* host wall-clock per phase, seconds (see Lookahead::m_timers); reset != 0 clears them */
 int   x265la_get_timers(void* la, double* t /* 10 */, int32_t reset);
+/* the BitCost row of the lookahead QP as the host library builds it (bitcost.cpp:46-54, 98-113): entries [-half, +half], centre
+ * at table[half].  For tests, and for a caller that wants to compare it with the encoder's own */
+void  x265la_mvcost_table(int32_t depth, int32_t half, uint16_t* table);
 x265cu_ctx* x265la_engine(void* la);
 /* sharded stream: x265cu_shard_config on this Lookahead's engine (open it with x265la_param::shardCount = nranks) */
 int   x265la_shard_config(void* la, int32_t rank, int32_t nranks, x265cu_exchange_fn exchange, void* user);

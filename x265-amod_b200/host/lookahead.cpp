@@ -30,16 +30,19 @@ static inline double clipDuration(double f) { return f < 0.01 ? 0.01 : (f > 1.0 
 /* x265_lambda_tab[X265_LOOKAHEAD_QP] (constants.cpp:34-90, common.h:209-213): exactly 1, 16, 256 */
 int lookaheadLambda(int depth) { return 1 << (2 * (depth - 8)); }
 
-/* The BitCost row the lookahead's MotionEstimate uses (bitcost.cpp:30-54, 98-113).  Built on the
- * host in float exactly like the reference and uploaded; the device never recomputes it. */
+/* The BitCost row the lookahead's MotionEstimate uses (bitcost.cpp:30-54, 98-113).  Built on the host like the reference and
+ * uploaded; the device never recomputes it.  The reference writes `log((float)(i + 1)) * log2_2 + 1.718f` with <math.h>'s
+ * log: the DOUBLE log of the float argument, times the float constant, plus the float constant, all in double, rounded to
+ * float ONCE when it is stored in s_bitsizes.  (A float logf pipeline gives the same table for 8 and 10 bits but 15 entries
+ * of +-60000 off by one at 12 bits, where lambda is 256 -- found by tools/fuzz_host_vs_reference.py.) */
 void buildMvCostTable(std::vector<uint16_t>& table, int half, int depth)
 {
     table.assign(2 * (size_t)half + 1, 0);
     const double lambda = (double)lookaheadLambda(depth);
-    const float log2_2 = 2.0f / logf(2.0f);
+    const float log2_2 = (float)(2.0 / log(2.0));
     for (int i = 0; i <= half; i++)
     {
-        float bits = i ? logf((float)(i + 1)) * log2_2 + 1.718f : 0.718f;
+        float bits = i ? (float)(log((double)(float)(i + 1)) * (double)log2_2 + (double)1.718f) : 0.718f;
         double c = bits * lambda + 0.5f;
         if (c > 32767.0) c = 32767.0;
         table[half + i] = table[half - i] = (uint16_t)c;
@@ -325,6 +328,12 @@ Frame* Lookahead::addPicture(const void* y, const void* u, const void* v, int st
                 /* best effort: a refusal (locked-memory limit) only costs speed */
                 m_pinned[ptr[i]] = x265cu_pin_host(m_ctx, const_cast<void*>(ptr[i]), len[i]) == X265CU_OK;
             }
+    }
+    if (m_param.bHistBasedSceneCut && (!u || !v))
+    {
+        /* its picture statistics read the chroma planes (slicetype.cpp:1560-1640); the reference dereferences NULL on a 4:0:0 picture */
+        fail("--hist-scenecut needs chroma planes (4:0:0 picture)");
+        return NULL;
     }
     /* the device starts the frame's pre-lookahead now; results are collected in slicetypeDecide */
     if (!check(x265cu_frame_upload(m_ctx, f->m_lowres.slot, y, u, v, strideY, strideC), "x265cu_frame_upload"))
