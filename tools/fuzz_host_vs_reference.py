@@ -67,8 +67,13 @@ def run_one(pkg, synth, simdir, seed):
     name, depth, w, h, n, skw, la = case
     if not refbind.available(depth):
         return 2
+    # one case in three also drives Lookahead::getEstimatedPictureCost (+ the VBV row sums) on every decided frame, like Encoder::encode
+    # (not with temporal layers: RefTracker models the nearest references, not the layered reference picture sets)
+    estimate = seed % 3 == 0 and not la.get("temporalLayers", 0) and not la.get("radl") and not la.get("bIntraRefresh")
+    if estimate:
+        cases.ESTIMATE.append(name)
     try:
-        want = cases.run_reference(refbind, synth, case, estimate=False)
+        want = cases.run_reference(refbind, synth, case, estimate=estimate)
     except Exception as e:      # the reference refused the combination
         print(name, "reference refused:", repr(e)[:100]); return 2
     try:

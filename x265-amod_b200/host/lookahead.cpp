@@ -2163,7 +2163,16 @@ void Lookahead::getEstimatedPictureCost(Frame* cur, int dist0, int dist1)
         {
             int64_t score = 0;
             const int cs = l.costStore[d0][d1];
-            if (cs < 0) { fail("getEstimatedPictureCost on an estimate that was never computed"); return; }
+            if (cs < 0)
+            {
+                /* rate control names references the lookahead never estimated this frame against.  The reference re-sums whatever its
+                 * lowresCosts array of that pair holds (never-written memory); here the call reports it and the stream goes on */
+                snprintf(m_error, sizeof(m_error), "getEstimatedPictureCost(%d, %d) of poc %d: that estimate was never computed", d0, d1, cur->m_poc);
+                l.satdCost = l.costEst[d0][d1];
+                l.rcD0 = l.rcD1 = -1;
+                m_timers[8] += nowSec() - t0;
+                return;
+            }
             if (l.rcPlanD0 == d0 && l.rcPlanD1 == d1)
             {
                 check(x265cu_cost_recalc_get(m_ctx, l.slot, cs, &score, NULL), "x265cu_cost_recalc_get");
@@ -2188,9 +2197,14 @@ bool Lookahead::getVbvRowCosts(Frame* cur, int pirStartCol, int pirEndCol, uint3
                                uint16_t* lowresCostForRc, int32_t* intraCostScaled)
 {
     const Lowres& l = cur->m_lowres;
-    if (l.rcD0 < 0) { fail("getVbvRowCosts before getEstimatedPictureCost"); return false; }
+    if (l.rcD0 < 0) { snprintf(m_error, sizeof(m_error), "getVbvRowCosts of poc %d without a usable getEstimatedPictureCost before it", cur->m_poc); return false; }
     const int cs = l.costStore[l.rcD0][l.rcD1];
-    if (cs < 0) { fail("getVbvRowCosts on an estimate that was never computed"); return false; }
+    if (cs < 0)
+    {
+        /* as above: not fatal.  The row sums stay what the caller initialised them to */
+        snprintf(m_error, sizeof(m_error), "getVbvRowCosts(%d, %d) of poc %d: that estimate was never computed", l.rcD0, l.rcD1, cur->m_poc);
+        return false;
+    }
     const int scale = m_param.maxCUSize / 16;
     /* :1408-1410: B frames and runs without cuTree read qpAqOffset */
     int qpSource = 0;
