@@ -43,6 +43,10 @@ def random_case(seed):
         la["gopLookahead"] = int(r.integers(1, 6))
     if r.integers(6) == 0 and la["aqMode"] < 4 and la["qgSize"] != 8 and (la["aqMode"] or la["weightp"] or la["weightb"]):
         la.update(fades=1, fpsNum=int(r.choice([8, 10, 25])))
+    if la.get("fades") and la["lookaheadDepth"] < la["bframes"] + 2:
+        # the fade detector walks the first bframes + 2 frames of the input queue at every decision (slicetype.cpp:1861-1906): with a
+        # shorter rc-lookahead, how many it finds depends on WHEN a pool worker got to run slicetypeDecide -- timing, not parameters
+        la["lookaheadDepth"] = la["bframes"] + 2
     if r.integers(6) == 0 and depth == 8 and w >= 256:
         la["histScenecut"] = 1
     if r.integers(8) == 0:
