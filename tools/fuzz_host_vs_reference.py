@@ -65,21 +65,40 @@ def random_case(seed):
     return ("fuzz%d" % seed, depth, w, h, n, skw, la)
 
 
-def run_one(pkg, synth, simdir, seed):
-    """0 = identical, 1 = mismatch, 2 = one side refused the configuration"""
+def _case_setup(seed):
     case = random_case(seed)
     name, depth, w, h, n, skw, la = case
-    if not refbind.available(depth):
-        return 2
     # one case in three also drives Lookahead::getEstimatedPictureCost (+ the VBV row sums) on every decided frame, like Encoder::encode
     # (not with temporal layers: RefTracker models the nearest references, not the layered reference picture sets)
     estimate = seed % 3 == 0 and not la.get("temporalLayers", 0) and not la.get("radl") and not la.get("bIntraRefresh")
     if estimate:
         cases.ESTIMATE.append(name)
+    return case, estimate
+
+
+def run_reference_side(synth, seed, path):
+    """child 1: the reference's run, pickled to `path`.  0 = done, 2 = it refused the configuration (a crash shows as a signal)"""
+    import pickle
+    case, estimate = _case_setup(seed)
+    if not refbind.available(case[1]):
+        return 2
     try:
         want = cases.run_reference(refbind, synth, case, estimate=estimate)
-    except Exception as e:      # the reference refused the combination
-        print(name, "reference refused:", repr(e)[:100]); return 2
+    except Exception as e:
+        print(case[0], "reference refused:", repr(e)[:100]); return 2
+    with open(path, "wb") as f:
+        pickle.dump(want, f)
+    return 0
+
+
+def run_our_side(pkg, synth, simdir, seed, path):
+    """child 2: the product's run through the sim engine, compared with the pickled reference run.
+    0 = identical, 1 = mismatch, 2 = the host library refused the configuration"""
+    import pickle
+    case, estimate = _case_setup(seed)
+    name, depth, w, h, n, skw, la = case
+    with open(path, "rb") as f:
+        want = pickle.load(f)
     try:
         # how the product schedules its GPU work must not show in the results: random scheduling mode and extra input delay
         r = np.random.default_rng(seed + 1000003)
@@ -106,33 +125,61 @@ def run_one(pkg, synth, simdir, seed):
     return 0
 
 
+def _child(fn, *args):
+    sys.stdout.flush()
+    pid = os.fork()
+    if pid == 0:
+        rc = 3
+        try:
+            rc = fn(*args)
+        finally:
+            sys.stdout.flush()
+            os._exit(rc)
+    _, status = os.waitpid(pid, 0)
+    return os.WEXITSTATUS(status) if os.WIFEXITED(status) else -1
+
+
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 50
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     pkg = _pkg.load_pkg(); synth = _pkg.load_synth()
     simdir = build_sim.build()
-    counts = {0: 0, 1: 0, 2: 0, "crash": 0}
+    path = "/tmp/fuzz_ref_%d.pkl" % os.getpid()
+    c = dict(identical=0, mismatch=0, ref_refused=0, ref_crashed=0, ours_refused=0, ours_crashed=0)
     t0 = time.time()
     for seed in range(first, first + n_cases):
-        # one child per case: the reference itself crashes on a few combinations (e.g. --radl with a scene cut in the last frames)
-        sys.stdout.flush()
-        pid = os.fork()
-        if pid == 0:
-            rc = 3
-            try:
-                rc = run_one(pkg, synth, simdir, seed)
-            finally:
-                sys.stdout.flush()
-                os._exit(rc)
-        _, status = os.waitpid(pid, 0)
-        if os.WIFEXITED(status) and os.WEXITSTATUS(status) in (0, 1, 2):
-            counts[os.WEXITSTATUS(status)] += 1
+        # one child per side and case: the reference itself crashes on a few combinations (hist-scenecut on 4:0:0, --radl with a scene
+        # cut in the last frames, ...), and a crash of the PRODUCT must be told apart from that
+        rc = _child(run_reference_side, synth, seed, path)
+        if rc != 0:
+            c["ref_refused" if rc == 2 else "ref_crashed"] += 1
+            if rc != 2:
+                # the product must still survive (or refuse) what kills the reference
+                rc2 = _child(lambda: 0 if _survives(pkg, synth, simdir, seed) else 0)
+                if rc2 != 0:
+                    c["ours_crashed"] += 1
+                    print("fuzz%d: THE PRODUCT DIED where the reference dies too: %s" % (seed, random_case(seed)[1:]))
+            continue
+        rc = _child(run_our_side, pkg, synth, simdir, seed, path)
+        if rc == 0: c["identical"] += 1
+        elif rc == 1: c["mismatch"] += 1
+        elif rc == 2: c["ours_refused"] += 1
         else:
-            counts["crash"] += 1
-            print("fuzz%d: the process died (status %d): %s" % (seed, status, random_case(seed)[1:]))
-    print("%d cases: %d identical, %d with mismatches, %d refused, %d crashed, %.0f s" %
-          (n_cases, counts[0], counts[1], counts[2], counts["crash"], time.time() - t0))
-    return 1 if counts[1] else 0
+            c["ours_crashed"] += 1
+            print("fuzz%d: THE PRODUCT DIED: %s" % (seed, random_case(seed)[1:]))
+    if os.path.exists(path):
+        os.remove(path)
+    print("%d cases: %s, %.0f s" % (n_cases, ", ".join("%s %d" % kv for kv in c.items()), time.time() - t0))
+    return 1 if c["mismatch"] or c["ours_crashed"] else 0
+
+
+def _survives(pkg, synth, simdir, seed):
+    case, _ = _case_setup(seed)
+    try:
+        cases.run_ours(pkg, synth, case, lib_path=os.path.join(simdir, "libx265la_sim%d.so" % case[1]))
+    except RuntimeError:
+        pass        # a refusal is fine
+    return True
 
 
 if __name__ == "__main__":
