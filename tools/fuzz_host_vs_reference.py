@@ -1,6 +1,6 @@
 """Randomised parity sweep of the PRODUCT's host logic (through the CPU sim engine) against the live unmodified reference:
 seeded random lookahead configurations on small synthetic sequences, every published field compared (tests/compare.py).
-CPU only; needs oracle/_ref.   python tools/fuzz_host_vs_reference.py [n_cases] [first_seed]"""
+CPU only; needs oracle/_ref.   python tools/fuzz_host_vs_reference.py [n_cases] [first_seed]   or   ... seeds 3,17,254"""
 import os
 import sys
 import time
@@ -140,14 +140,19 @@ def _child(fn, *args):
 
 
 def main():
-    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 50
-    first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    if len(sys.argv) > 2 and sys.argv[1] == "seeds":
+        seeds = [int(x) for x in sys.argv[2].split(",")]
+    else:
+        n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+        first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+        seeds = list(range(first, first + n_cases))
+    n_cases = len(seeds)
     pkg = _pkg.load_pkg(); synth = _pkg.load_synth()
     simdir = build_sim.build()
     path = "/tmp/fuzz_ref_%d.pkl" % os.getpid()
     c = dict(identical=0, mismatch=0, ref_refused=0, ref_crashed=0, ours_refused=0, ours_crashed=0)
     t0 = time.time()
-    for seed in range(first, first + n_cases):
+    for seed in seeds:
         # one child per side and case: the reference itself crashes on a few combinations (hist-scenecut on 4:0:0, --radl with a scene
         # cut in the last frames, ...), and a crash of the PRODUCT must be told apart from that
         rc = _child(run_reference_side, synth, seed, path)
