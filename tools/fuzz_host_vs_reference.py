@@ -53,6 +53,25 @@ def random_case(seed):
         la["bIntraRefresh"] = 1
     if r.integers(8) == 0:
         la["csp400"] = 1
+    if seed >= 1000000:
+        # "big" seeds: pictures tall enough for cooperative lookahead slices (>= 720 lines, with a pool) or --hme (>= 540 lines), short
+        big = int(r.integers(3))
+        n = int(r.integers(9, 17))
+        la["lookaheadDepth"] = min(la["lookaheadDepth"], la["bframes"] + 8)
+        for k in ("histScenecut", "fades", "fpsNum", "csp400"):
+            la.pop(k, None)
+        if la["temporalLayers"] > 2:
+            la["temporalLayers"] = 0; la["bFrameAdaptive"] = int(r.integers(3)); la["bframes"] = min(la["bframes"], 4)
+            la["lookaheadDepth"] = la["bframes"] + int(r.integers(2, 8))
+        if big == 0:
+            w, h = 1280, 720
+            la["poolThreads"] = int(r.choice([2, 4, 8, 16])); la["lookaheadSlices"] = int(r.choice([2, 3, 4, 8]))
+        elif big == 1:
+            w, h = 960, 544
+            la.update(hme=1, hmeSearch0=int(r.choice([0, 1, 2, 3])), hmeSearch1=int(r.choice([0, 1, 2, 2, 3])),
+                      hmeRange0=int(r.choice([8, 16, 24])), hmeRange1=int(r.choice([16, 32])))
+        else:
+            w, h = 1024, 576
     cuts = tuple(sorted(set(int(x) for x in r.integers(3, n, int(r.integers(0, 3))))))
     skw = dict(cuts=cuts)
     kind = int(r.integers(5))
