@@ -92,6 +92,11 @@ def _case_setup(seed):
     estimate = seed % 3 == 0 and not la.get("temporalLayers", 0) and not la.get("radl") and not la.get("bIntraRefresh")
     if estimate:
         cases.ESTIMATE.append(name)
+    if seed % 7 == 3 and not la.get("temporalLayers", 0):
+        # slice types forced by the application (x265_picture::sliceType -> Lowres::sliceTypeReq) on a few frames
+        r = np.random.default_rng(seed + 77)
+        pocs = sorted(set(int(x) for x in r.integers(2, n - 1, int(r.integers(1, 5)))))
+        cases.FORCED[name] = {p: int(r.choice([1, 2, 3, 3, 5, 5])) for p in pocs}
     return case, estimate
 
 
@@ -126,7 +131,7 @@ def run_our_side(pkg, synth, simdir, seed, path):
     except RuntimeError as e:
         print(name, "REFUSED by the host library:", str(e)[:160], la); return 2
     bad = compare.compare_runs(want, got, check_planes=True, cutree=la.get("cuTree", 1), weightp=la.get("weightp", 1) or la.get("weightb", 0),
-                               vbv=bool(la.get("vbvBufferSize")))
+                               vbv=bool(la.get("vbvBufferSize")), skip_propagate=tuple(cases.FORCED.get(name, {})))
     # a B frame of the analysis that slicetypeDecide turns into the P in front of an IDR (closed GOP, slicetype.cpp:2012-2016) was
     # a B frame to cuTree: its propagateCost is whatever the allocation held, like that of a forced-type frame (compare.py)
     idr_pocs = set(f["poc"] for f in want if f["sliceType"] == 1)
