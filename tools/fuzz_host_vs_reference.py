@@ -17,6 +17,13 @@ import compare
 import refbind
 
 
+def _engine_lib(simdir, depth):
+    """the CPU sim engine, or with FUZZ_ENGINE=cuda the real library on a GPU box (lib_path None = x265-amod_b200/lib)"""
+    if os.environ.get("FUZZ_ENGINE") == "cuda":
+        return None
+    return os.path.join(simdir, "libx265la_sim%d.so" % depth)
+
+
 def random_case(seed):
     r = np.random.default_rng(seed)
     depth = int(r.choice([8, 8, 10, 12]))
@@ -127,7 +134,7 @@ def run_our_side(pkg, synth, simdir, seed, path):
         # how the product schedules its GPU work must not show in the results: random scheduling mode and extra input delay
         r = np.random.default_rng(seed + 1000003)
         extra = dict(speculate=int(r.choice([0, 1, 1, 2])), asyncDepth=int(r.choice([0, 0, 3, 9, 17])))
-        got = cases.run_ours(pkg, synth, case, lib_path=os.path.join(simdir, "libx265la_sim%d.so" % depth), **extra)
+        got = cases.run_ours(pkg, synth, case, lib_path=_engine_lib(simdir, depth), **extra)
     except RuntimeError as e:
         print(name, "REFUSED by the host library:", str(e)[:160], la); return 2
     bad = compare.compare_runs(want, got, check_planes=True, cutree=la.get("cuTree", 1), weightp=la.get("weightp", 1) or la.get("weightb", 0),
@@ -205,7 +212,7 @@ def main():
 def _survives(pkg, synth, simdir, seed):
     case, _ = _case_setup(seed)
     try:
-        cases.run_ours(pkg, synth, case, lib_path=os.path.join(simdir, "libx265la_sim%d.so" % case[1]))
+        cases.run_ours(pkg, synth, case, lib_path=_engine_lib(simdir, case[1]))
     except RuntimeError:
         pass        # a refusal is fine
     return True
