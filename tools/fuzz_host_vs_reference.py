@@ -113,12 +113,18 @@ def run_reference_side(synth, seed, path):
     case, estimate = _case_setup(seed)
     if not refbind.available(case[1]):
         return 2
+    pass2 = None
     try:
+        if seed % 11 == 5 and not case[6].get("temporalLayers", 0) and case[0] not in cases.FORCED:
+            # a 2-pass encode: the types the reference decided in a first run come back as the argument of Lookahead::addPicture
+            first = cases.run_reference(refbind, synth, case, estimate=False, planes=False)
+            pass2 = {f["poc"]: f["sliceType"] for f in first}
+            cases.PASS2[case[0]] = pass2
         want = cases.run_reference(refbind, synth, case, estimate=estimate)
     except Exception as e:
         print(case[0], "reference refused:", repr(e)[:100]); return 2
     with open(path, "wb") as f:
-        pickle.dump(want, f)
+        pickle.dump((want, pass2), f)
     return 0
 
 
@@ -129,7 +135,9 @@ def run_our_side(pkg, synth, simdir, seed, path):
     case, estimate = _case_setup(seed)
     name, depth, w, h, n, skw, la = case
     with open(path, "rb") as f:
-        want = pickle.load(f)
+        want, pass2 = pickle.load(f)
+    if pass2:
+        cases.PASS2[name] = pass2
     try:
         # how the product schedules its GPU work must not show in the results: random scheduling mode and extra input delay
         r = np.random.default_rng(seed + 1000003)
@@ -138,7 +146,7 @@ def run_our_side(pkg, synth, simdir, seed, path):
     except RuntimeError as e:
         print(name, "REFUSED by the host library:", str(e)[:160], la); return 2
     bad = compare.compare_runs(want, got, check_planes=True, cutree=la.get("cuTree", 1), weightp=la.get("weightp", 1) or la.get("weightb", 0),
-                               vbv=bool(la.get("vbvBufferSize")), skip_propagate=tuple(cases.FORCED.get(name, {})))
+                               vbv=bool(la.get("vbvBufferSize")), skip_propagate=tuple(cases.FORCED.get(name, {})) + tuple(pass2 or ()))
     # a B frame of the analysis that slicetypeDecide turns into the P in front of an IDR (closed GOP, slicetype.cpp:2012-2016) was
     # a B frame to cuTree: its propagateCost is whatever the allocation held, like that of a forced-type frame (compare.py)
     idr_pocs = set(f["poc"] for f in want if f["sliceType"] == 1)
